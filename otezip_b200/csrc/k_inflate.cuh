@@ -1,0 +1,632 @@
+// k_inflate.cuh — batched raw-DEFLATE (RFC 1951) decoder, one tile of G lanes per entry.
+//
+// Replaces inflateInit2/inflate/inflateEnd as driven by otezip_extract_entry
+// (/root/reference/src/lib/otezip.c:503-529; decoder src/lib/deflate-dec.inc.c:547-831, abbreviated
+// "dec" below).  The reference decodes a symbol by pulling one bit at a time and scanning all
+// <=288 (length, code) pairs after every bit (dec:671-691, :743-764).  Here:
+//   * the compressed bytes are fetched as coalesced 32-bit words, G words per load, one word per
+//     lane; the 64-bit bit buffer is refilled by a tile shuffle from that register window
+//     (the next window is already in flight while the current one is consumed);
+//   * literal/length and distance codes are looked up in per-stream shared-memory tables
+//     (9-bit / 8-bit roots with second-level tables for longer codes), 16-bit entries;
+//   * literals are gathered one per lane and flushed with one coalesced store;
+//   * LZ77 copies are performed by all G lanes (bytes are independent once the period
+//     `distance` is taken into account, so no lane waits on another);
+//   * dynamic-block tables are built cooperatively (counts with shared-memory atomics, canonical
+//     order with match_any ranks, root fill in parallel).
+// The decoder is a strict RFC 1951 decoder.  It also evaluates the reference's end-of-input rule
+// (dec:811-816: Z_BUF_ERROR as soon as the last input byte has been loaded and the stream is not
+// finished — SURVEY.md F1) and reports it as the OTZ_STF_REF_EOB flag, so the host library can
+// reproduce the reference's accept/reject decision bit for bit.
+#pragma once
+#include "otz_common.cuh"
+#include "k_copy.cuh"
+
+#define INF_LIT_ROOT 9
+#define INF_DST_ROOT 8
+#define INF_LIT_CAP 852   // zlib's proven bound for (286 symbols, root 9, max 15)
+#define INF_DST_CAP 416   // >= 402, libdeflate's bound for (32 symbols, root 8, max 15)
+
+#define INF_K_LIT 0u
+#define INF_K_LEN 1u
+#define INF_K_EOB 2u
+#define INF_K_LINK 3u  // with nbits == 0: invalid code
+#define INF_ENTRY(nbits, kind, payload) ((uint16_t)((nbits) | ((kind) << 4) | ((payload) << 6)))
+#define INF_INVALID INF_ENTRY(0u, INF_K_LINK, 0u)
+
+struct __align__(16) InflateSmem {
+	uint16_t lit[INF_LIT_CAP];
+	uint16_t dst[INF_DST_CAP];
+	uint16_t sorted[288];
+	uint8_t lens[320];
+	uint32_t cnt[16];
+	uint16_t offs[16];
+	uint16_t run[16];
+	uint16_t first[16];
+	uint8_t pre[128];
+};
+
+__constant__ uint8_t c_cl_order[19] = { 16, 17, 18, 0, 8, 7, 9, 6, 10, 5, 11, 4, 12, 3, 13, 2, 14, 1, 15 };  // dec:146-148
+
+// ------------------------------------------------------------------------------------------------
+// Bit reader: every lane carries an identical copy of (bb, nb); the input window is spread over lanes.
+template <int G>
+struct BitReader {
+	const uint32_t *words;   // aligned base of the current stream position
+	uint32_t n_words;        // words available from `words`
+	uint32_t win_base;       // word index of win_cur[lane 0]
+	uint32_t win_cur, win_next;
+	uint32_t widx;           // next word of the current window to consume
+	int32_t words_left;      // words not yet moved into bb (negative once past the end)
+	uint32_t pad_bits;       // bits in the last word that lie beyond the stream end
+	uint64_t bb;
+	uint32_t nb;
+
+	__device__ __forceinline__ uint32_t load(uint32_t idx) const { return idx < n_words ? __ldg(words + idx) : 0u; }
+
+	template <typename Tile>
+	__device__ __forceinline__ void init(const Tile &tile, const uint8_t *p, uint64_t nbytes) {
+		const uint64_t a = reinterpret_cast<uint64_t>(p);
+		const uint32_t skip = (uint32_t)(a & 3);
+		words = reinterpret_cast<const uint32_t *>(a - skip);
+		n_words = (uint32_t)((skip + nbytes + 3) >> 2);
+		pad_bits = (uint32_t)(((uint64_t)n_words << 5) - ((skip + nbytes) << 3));
+		win_base = 0;
+		const int lane = tile.thread_rank();
+		win_cur = load(lane);
+		win_next = load(G + lane);
+		widx = 0;
+		words_left = (int32_t)n_words;
+		bb = 0;
+		nb = 0;
+		refill(tile);
+		bb >>= 8 * skip;
+		nb -= 8 * skip;
+	}
+	// after this nb >= 33
+	template <typename Tile>
+	__device__ __forceinline__ void refill(const Tile &tile) {
+		if (nb <= 32) {
+			const uint32_t w = tile.shfl(win_cur, widx);
+			bb |= (uint64_t)w << nb;
+			nb += 32;
+			words_left--;
+			if (++widx == G) {
+				widx = 0;
+				win_base += G;
+				win_cur = win_next;
+				win_next = load(win_base + G + tile.thread_rank());
+			}
+		}
+	}
+	__device__ __forceinline__ void consume(uint32_t n) {
+		bb >>= n;
+		nb -= n;
+	}
+	// bits of the stream not yet consumed (negative: read past the end)
+	__device__ __forceinline__ int64_t remaining_bits() const {
+		return ((int64_t)words_left << 5) + (int64_t)nb - (int64_t)pad_bits;
+	}
+};
+
+// ------------------------------------------------------------------------------------------------
+// Canonical table build from code lengths (dec:86-119 assigns the same canonical codes).
+// Returns 0 ok, nonzero = invalid set.  All lanes return the same value.
+template <int G, typename Tile>
+__device__ __noinline__ int build_table(const Tile &tile, InflateSmem &S, const uint8_t *lens, int n, int root, uint16_t *tbl, int cap,
+	bool is_dist) {
+	const int lane = tile.thread_rank();
+	for (int i = lane; i < 16; i += G) {
+		S.cnt[i] = 0;
+	}
+	tile.sync();
+	for (int s = lane; s < n; s += G) {
+		const uint32_t l = lens[s];
+		if (l) {
+			atomicAdd(&S.cnt[l], 1u);
+		}
+	}
+	tile.sync();
+	int left = 1, ncodes = 0, maxlen = 0;
+	{
+		int code = 0, off = 0;
+		for (int l = 1; l <= 15; l++) {
+			const int c = (int)S.cnt[l];
+			left = (left << 1) - c;
+			if (left < 0) {
+				return 1;  // over-subscribed
+			}
+			code = (code + (l > 1 ? (int)S.cnt[l - 1] : 0)) << 1;
+			if (lane == 0) {
+				S.offs[l] = (uint16_t)off;
+				S.run[l] = (uint16_t)off;
+				S.first[l] = (uint16_t)code;
+			}
+			off += c;
+			ncodes += c;
+			if (c) {
+				maxlen = l;
+			}
+		}
+	}
+	const int rootsz = 1 << root;
+	if (ncodes == 0) {
+		if (!is_dist) {
+			return 1;
+		}
+		for (int k = lane; k < rootsz; k += G) {
+			tbl[k] = INF_INVALID;  // a block of literals only: any distance code is an error
+		}
+		tile.sync();
+		return 0;
+	}
+	if (left > 0) {
+		if (!(ncodes == 1 && S.cnt[1] == 1)) {
+			return 1;  // incomplete set (zlib accepts only a single 1-bit code)
+		}
+		for (int k = lane; k < rootsz; k += G) {
+			tbl[k] = INF_INVALID;
+		}
+	}
+	tile.sync();
+	// canonical order: sorted[] = symbols by (length, symbol)
+	for (int base = 0; base < n; base += G) {
+		const int s = base + lane;
+		const uint32_t l = s < n ? lens[s] : 0u;
+		const uint32_t m = tile.match_any(l);
+		const int rank = __popc(m & ((1u << lane) - 1u));
+		if (l) {
+			S.sorted[S.run[l] + rank] = (uint16_t)s;
+		}
+		tile.sync();
+		if (l && rank == 0) {
+			S.run[l] = (uint16_t)(S.run[l] + __popc(m));
+		}
+		tile.sync();
+	}
+	// root entries, one canonical index per lane
+	for (int i = lane; i < ncodes; i += G) {
+		const uint32_t s = S.sorted[i];
+		const uint32_t l = lens[s];
+		if ((int)l > root) {
+			continue;
+		}
+		const uint32_t c = S.first[l] + (i - S.offs[l]);
+		const uint32_t rev = __brev(c) >> (32 - l);
+		uint16_t e;
+		if (is_dist) {
+			e = s < 30 ? INF_ENTRY(l, INF_K_LIT, s) : INF_INVALID;
+		} else {
+			e = s < 256 ? INF_ENTRY(l, INF_K_LIT, s) : s == 256 ? INF_ENTRY(l, INF_K_EOB, 0u) : s < 286 ? INF_ENTRY(l, INF_K_LEN, s - 257) : INF_INVALID;
+		}
+		for (int k = (int)rev; k < rootsz; k += (1 << l)) {
+			tbl[k] = e;
+		}
+	}
+	// codes longer than the root: second-level tables, walked in canonical order by the whole tile
+	if (maxlen > root) {
+		int next_free = rootsz, cur_prefix = -1, sub_off = 0, sub_bits = 0;
+		for (int i = S.offs[root + 1]; i < ncodes; i++) {
+			const uint32_t s = S.sorted[i];
+			const int l = lens[s];
+			const uint32_t c = S.first[l] + (i - S.offs[l]);
+			const uint32_t rev = __brev(c) >> (32 - l);
+			const int prefix = (int)(rev & (uint32_t)(rootsz - 1));
+			if (prefix != cur_prefix) {
+				int curr = l - root;
+				int lf = 1 << curr;
+				int rem = (int)S.offs[l] + (int)S.cnt[l] - i;  // codes of this length still to place
+				while (curr + root < maxlen) {
+					lf -= rem;
+					if (lf <= 0) {
+						break;
+					}
+					curr++;
+					lf <<= 1;
+					rem = (int)S.cnt[curr + root];
+				}
+				if (next_free + (1 << curr) > cap) {
+					return 1;  // cannot happen for a valid code (cap is the proven bound)
+				}
+				sub_off = next_free;
+				sub_bits = curr;
+				next_free += 1 << curr;
+				cur_prefix = prefix;
+				if (lane == 0) {
+					tbl[prefix] = INF_ENTRY((uint32_t)sub_bits, INF_K_LINK, (uint32_t)sub_off);
+				}
+			}
+			uint16_t e;
+			const uint32_t nb2 = (uint32_t)(l - root);
+			if (is_dist) {
+				e = s < 30 ? INF_ENTRY(nb2, INF_K_LIT, s) : INF_INVALID;
+			} else {
+				e = s < 256 ? INF_ENTRY(nb2, INF_K_LIT, s) : s == 256 ? INF_ENTRY(nb2, INF_K_EOB, 0u) : s < 286 ? INF_ENTRY(nb2, INF_K_LEN, s - 257) : INF_INVALID;
+			}
+			const int step = 1 << nb2;
+			for (int k = (int)(rev >> root) + lane * step; k < (1 << sub_bits); k += G * step) {
+				tbl[sub_off + k] = e;
+			}
+		}
+	}
+	tile.sync();
+	return 0;
+}
+
+// dec:322-349
+template <int G, typename Tile>
+__device__ __noinline__ int build_fixed(const Tile &tile, InflateSmem &S) {
+	const int lane = tile.thread_rank();
+	for (int i = lane; i < 320; i += G) {
+		S.lens[i] = i < 144 ? 8 : i < 256 ? 9 : i < 280 ? 7 : i < 288 ? 8 : 5;
+	}
+	tile.sync();
+	int r = build_table<G>(tile, S, S.lens, 288, INF_LIT_ROOT, S.lit, INF_LIT_CAP, false);
+	r |= build_table<G>(tile, S, S.lens + 288, 32, INF_DST_ROOT, S.dst, INF_DST_CAP, true);
+	return r;
+}
+
+// dec:122-266
+template <int G, typename Tile>
+__device__ __noinline__ int read_dynamic(const Tile &tile, InflateSmem &S, BitReader<G> &br) {
+	const int lane = tile.thread_rank();
+	br.refill(tile);
+	const int hlit = (int)(br.bb & 31) + 257, hdist = (int)((br.bb >> 5) & 31) + 1, hclen = (int)((br.bb >> 10) & 15) + 4;
+	br.consume(14);
+	if (hlit > 286 || hdist > 30) {
+		return 1;  // RFC 1951 limits; dec:165-168 would overflow its scratch instead
+	}
+	for (int i = lane; i < 19; i += G) {
+		S.lens[i] = 0;
+	}
+	tile.sync();
+	uint64_t cnt = 0;  // packed byte counters, cnt>>(8*l) & 0xFF = number of precode symbols of length l
+	for (int i = 0; i < hclen; i++) {
+		br.refill(tile);
+		const uint32_t v = (uint32_t)br.bb & 7u;
+		br.consume(3);
+		if (lane == 0) {
+			S.lens[c_cl_order[i]] = (uint8_t)v;
+		}
+		cnt += 1ull << (8 * v);
+	}
+	tile.sync();
+	// the code-length code must be complete (zlib: type CODES)
+	uint64_t first = 0;  // packed first canonical code per length
+	{
+		int left = 1, code = 0;
+		for (int l = 1; l <= 7; l++) {
+			const int c = (int)((cnt >> (8 * l)) & 0xFF);
+			left = (left << 1) - c;
+			if (left < 0) {
+				return 1;
+			}
+			code = (code + (l > 1 ? (int)((cnt >> (8 * (l - 1))) & 0xFF) : 0)) << 1;
+			first |= (uint64_t)(code & 0xFF) << (8 * l);
+		}
+		if (left != 0) {
+			return 1;
+		}
+	}
+	for (int s = lane; s < 19; s += G) {
+		const uint32_t l = S.lens[s];
+		if (l) {
+			int rank = 0;
+			for (int t = 0; t < s; t++) {
+				rank += (S.lens[t] == l);
+			}
+			const uint32_t c = (uint32_t)((first >> (8 * l)) & 0xFF) + rank;
+			const uint32_t rev = __brev(c) >> (32 - l);
+			for (uint32_t k = rev; k < 128; k += (1u << l)) {
+				S.pre[k] = (uint8_t)(s | (l << 5));
+			}
+		}
+	}
+	tile.sync();
+	// code lengths of the literal/length and distance alphabets (now overwrites S.lens)
+	const int total = hlit + hdist;
+	int idx = 0;
+	uint32_t prev = 0;
+	while (idx < total) {
+		br.refill(tile);
+		const uint32_t e = S.pre[(uint32_t)br.bb & 127u];
+		const uint32_t sym = e & 31u;
+		br.consume(e >> 5);
+		if (sym < 16) {
+			if (lane == 0) {
+				S.lens[idx] = (uint8_t)sym;
+			}
+			idx++;
+			prev = sym;
+			continue;
+		}
+		int rep;
+		uint32_t val = 0;
+		if (sym == 16) {  // dec:209-219
+			if (idx == 0) {
+				return 1;
+			}
+			val = prev;
+			rep = 3 + (int)((uint32_t)br.bb & 3u);
+			br.consume(2);
+		} else if (sym == 17) {  // dec:221-228
+			rep = 3 + (int)((uint32_t)br.bb & 7u);
+			br.consume(3);
+		} else {  // dec:230-237
+			rep = 11 + (int)((uint32_t)br.bb & 127u);
+			br.consume(7);
+		}
+		if (idx + rep > total) {
+			return 1;  // dec:244
+		}
+		for (int i = lane; i < rep; i += G) {
+			S.lens[idx + i] = (uint8_t)val;
+		}
+		idx += rep;
+		prev = val;
+	}
+	tile.sync();
+	if (S.lens[256] == 0) {
+		return 1;  // no end-of-block code
+	}
+	int r = build_table<G>(tile, S, S.lens, hlit, INF_LIT_ROOT, S.lit, INF_LIT_CAP, false);
+	if (r) {
+		return r;
+	}
+	return build_table<G>(tile, S, S.lens + hlit, hdist, INF_DST_ROOT, S.dst, INF_DST_CAP, true);
+}
+
+// ------------------------------------------------------------------------------------------------
+// Decode one raw stream.  Returns the status word; *produced = bytes written.
+template <int G, typename Tile>
+__device__ __forceinline__ int32_t inflate_stream(const Tile &tile, InflateSmem &S, const uint8_t *__restrict__ in, uint32_t comp,
+	uint8_t *__restrict__ out, uint32_t cap, uint32_t *produced) {
+	const int lane = tile.thread_rank();
+	*produced = 0;
+	if (comp == 0) {
+		return OTZ_ST_TRUNCATED;  // dec:610: the loop never runs; Z_OK or Z_BUF_ERROR, never STREAM_END
+	}
+	BitReader<G> br;
+	br.init(tile, in, comp);
+	uint32_t op = 0;
+	uint32_t npend = 0, mylit = 0;  // pending literals, one per lane
+	bool ref_eob = false;
+	int32_t err = 0;
+
+// The reference returns Z_BUF_ERROR once ceil(bitpos/8) == comp while the stream is unfinished, i.e.
+// fewer than 8 stream bits remain.  Only reachable when at most one word is left to load.
+#define INF_STEP_CHECK()                                \
+	if (br.words_left <= 1) {                           \
+		const int64_t rem_ = br.remaining_bits();       \
+		if (rem_ < 0) {                                 \
+			err = OTZ_ST_TRUNCATED;                     \
+			break;                                      \
+		}                                               \
+		if (rem_ < 8) {                                 \
+			ref_eob = true;                             \
+		}                                               \
+	}
+#define INF_FLUSH_LITS()                                \
+	if (npend) {                                        \
+		if ((uint32_t)lane < npend) {                   \
+			out[op + lane] = (uint8_t)mylit;            \
+		}                                               \
+		op += npend;                                    \
+		npend = 0;                                      \
+	}
+
+	for (;;) {
+		// ---- block header, dec:613-627
+		br.refill(tile);
+		const uint32_t final_blk = (uint32_t)br.bb & 1u;
+		const uint32_t btype = ((uint32_t)br.bb >> 1) & 3u;
+		br.consume(3);
+		INF_STEP_CHECK();
+		if (btype == 0) {
+			// ---- stored block, dec:269-319
+			INF_FLUSH_LITS();
+			const int64_t rem = br.remaining_bits();
+			const uint64_t pos = (uint64_t)comp - (uint64_t)(rem >> 3);  // partial byte dropped
+			if ((uint64_t)comp - pos < 4) {
+				err = OTZ_ST_DATA;
+				break;
+			}
+			const uint32_t len = ld_le16(in + pos), nlen = ld_le16(in + pos + 2);
+			if (len != ((~nlen) & 0xFFFFu) || (uint64_t)comp - pos - 4 < len) {
+				err = OTZ_ST_DATA;
+				break;
+			}
+			if (cap - op < len) {
+				err = OTZ_ST_OVERFLOW;
+				break;
+			}
+			tile.sync();
+			tile_copy<G>(out + op, in + pos + 4, len, lane);
+			op += len;
+			const uint64_t npos = pos + 4 + len;
+			br.init(tile, in + npos, (uint64_t)comp - npos);
+			if (final_blk) {
+				break;
+			}
+			if (npos >= comp) {  // dec:811-816 after a non-final stored block
+				ref_eob = true;
+			}
+			continue;
+		}
+		if (btype == 3) {
+			err = OTZ_ST_DATA;  // dec:657-658
+			break;
+		}
+		if ((btype == 1 ? build_fixed<G>(tile, S) : read_dynamic<G>(tile, S, br)) != 0) {
+			err = OTZ_ST_DATA;
+			break;
+		}
+		INF_STEP_CHECK();
+		// ---- symbols, dec:662-799
+		bool eob = false;
+		for (;;) {
+			br.refill(tile);
+			uint32_t e = S.lit[(uint32_t)br.bb & ((1u << INF_LIT_ROOT) - 1u)];
+			if ((e & 0x30u) == (INF_K_LINK << 4)) {
+				const uint32_t sb = e & 15u;
+				if (sb == 0) {
+					err = OTZ_ST_DATA;  // dec:693-695: no code matches
+					break;
+				}
+				br.consume(INF_LIT_ROOT);
+				e = S.lit[(e >> 6) + ((uint32_t)br.bb & ((1u << sb) - 1u))];
+				if ((e & 0x30u) == (INF_K_LINK << 4)) {
+					err = OTZ_ST_DATA;
+					break;
+				}
+			}
+			br.consume(e & 15u);
+			const uint32_t kind = (e >> 4) & 3u, val = e >> 6;
+			if (kind == INF_K_LIT) {
+				if (op + npend >= cap) {
+					err = OTZ_ST_OVERFLOW;  // dec:700-703
+					break;
+				}
+				if ((uint32_t)lane == npend) {
+					mylit = val;
+				}
+				if (++npend == G) {
+					INF_FLUSH_LITS();
+				}
+			} else if (kind == INF_K_EOB) {
+				eob = true;
+				break;  // dec:711-716
+			} else {
+				// length symbol val = sym-257 (dec:720-737), then distance (dec:740-782)
+				uint32_t length, xb;
+				if (val < 8) {
+					length = 3 + val;
+					xb = 0;
+				} else if (val == 28) {
+					length = 258;
+					xb = 0;
+				} else {
+					xb = (val - 4) >> 2;
+					length = 3 + ((4 + (val & 3)) << xb);
+				}
+				length += (uint32_t)br.bb & ((1u << xb) - 1u);
+				br.consume(xb);
+				br.refill(tile);
+				uint32_t d = S.dst[(uint32_t)br.bb & ((1u << INF_DST_ROOT) - 1u)];
+				if ((d & 0x30u) == (INF_K_LINK << 4)) {
+					const uint32_t sb = d & 15u;
+					if (sb == 0) {
+						err = OTZ_ST_DATA;  // dec:762-764
+						break;
+					}
+					br.consume(INF_DST_ROOT);
+					d = S.dst[(d >> 6) + ((uint32_t)br.bb & ((1u << sb) - 1u))];
+					if ((d & 0x30u) == (INF_K_LINK << 4)) {
+						err = OTZ_ST_DATA;
+						break;
+					}
+				}
+				br.consume(d & 15u);
+				const uint32_t dsym = d >> 6;
+				uint32_t dist, dxb;
+				if (dsym < 4) {
+					dist = 1 + dsym;
+					dxb = 0;
+				} else {
+					dxb = (dsym - 2) >> 1;
+					dist = 1 + ((2 + (dsym & 1)) << dxb);
+				}
+				dist += (uint32_t)br.bb & ((1u << dxb) - 1u);
+				br.consume(dxb);
+				INF_FLUSH_LITS();
+				if (dist > op) {
+					err = OTZ_ST_DATA;  // reaches before the start of the output (dec:785 does not check; strict)
+					break;
+				}
+				if (length > cap - op) {
+					err = OTZ_ST_OVERFLOW;  // dec:535-541, :791-793
+					break;
+				}
+				tile.sync();  // earlier stores of this tile are visible to the loads below
+				uint8_t *dp = out + op;
+				const uint8_t *sp = dp - dist;
+				if (dist >= length) {
+					for (uint32_t i = lane; i < length; i += G) {
+						dp[i] = sp[i];
+					}
+				} else {
+					// overlapping copy = periodic extension of the last `dist` bytes (dec:521-533)
+					uint32_t r = dist > (uint32_t)lane ? (uint32_t)lane : (uint32_t)lane % dist;
+					const uint32_t step = dist > (uint32_t)G ? (uint32_t)G : (uint32_t)G % dist;
+					for (uint32_t i = lane; i < length; i += G) {
+						dp[i] = sp[r];
+						r += step;
+						r = r >= dist ? r - dist : r;
+					}
+				}
+				op += length;
+			}
+			INF_STEP_CHECK();
+		}
+		if (err) {
+			break;
+		}
+		if (!eob) {
+			break;  // left the symbol loop through INF_STEP_CHECK's break with err set
+		}
+		if (final_blk) {
+			if (br.remaining_bits() < 0) {
+				err = OTZ_ST_TRUNCATED;
+			}
+			break;  // dec:714-716
+		}
+		INF_STEP_CHECK();
+	}
+	INF_FLUSH_LITS();
+#undef INF_STEP_CHECK
+#undef INF_FLUSH_LITS
+	*produced = op;
+	if (err) {
+		return err;
+	}
+	return OTZ_ST_OK | (ref_eob ? OTZ_STF_REF_EOB : 0) | (op < cap ? OTZ_STF_SHORT : 0);
+}
+
+// grid: persistent; each tile pulls the next entry of `list` (largest first) from a global counter.
+template <int G>
+__global__ void __launch_bounds__(256) k_inflate(const uint8_t *__restrict__ archive, uint8_t *__restrict__ out,
+	const otz_entry *__restrict__ ents, const OtzEntryState *__restrict__ est, int32_t *__restrict__ status,
+	const uint32_t *__restrict__ list, uint32_t n_list, uint32_t *__restrict__ work_counter) {
+	extern __shared__ __align__(16) uint8_t smem_raw[];
+	auto tile = cg::tiled_partition<G>(cg::this_thread_block());
+	const int lane = tile.thread_rank();
+	InflateSmem &S = reinterpret_cast<InflateSmem *>(smem_raw)[threadIdx.x / G];
+	for (;;) {
+		uint32_t k = 0;
+		if (lane == 0) {
+			k = atomicAdd(work_counter, 1u);
+		}
+		k = tile.shfl(k, 0);
+		if (k >= n_list) {
+			break;
+		}
+		const uint32_t ei = list[k];
+		if (OTZ_ST_CODE(status[ei]) != OTZ_ST_OK) {
+			continue;
+		}
+		const otz_entry e = ents[ei];
+		uint8_t *dst = out + e.out_ofs;
+		uint32_t produced = 0;
+		int32_t st = inflate_stream<G>(tile, S, archive + est[ei].data_ofs, e.comp_size, dst, e.uncomp_size, &produced);
+		if (OTZ_ST_CODE(st) == OTZ_ST_OK && produced < e.uncomp_size) {
+			// otezip.c:500 pre-zeroes the buffer and never compares total_out: short streams are zero-padded
+			for (uint64_t i = (uint64_t)produced + lane; i < e.uncomp_size; i += G) {
+				dst[i] = 0;
+			}
+		}
+		if (lane == 0) {
+			status[ei] = st;
+		}
+		tile.sync();
+	}
+}

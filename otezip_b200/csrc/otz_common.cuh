@@ -1,0 +1,74 @@
+// otz_common.cuh — shared device helpers for the otezip_b200 kernels (sm_100a).
+#pragma once
+
+#include <cooperative_groups.h>
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "../../include/otz_gpu.h"
+
+namespace cg = cooperative_groups;
+
+#define OTZ_SIG_LFH 0x04034b50u
+#define OTZ_MAX_PAYLOAD (2ull * 1024ull * 1024ull * 1024ull)  // otezip.c:102
+
+// Per-entry device state produced by k_resolve and consumed by the decoders.
+struct OtzEntryState {
+	uint64_t data_ofs;   // offset of the compressed payload in the archive image
+};
+
+// ---------------------------------------------------------------- unaligned little-endian reads
+__device__ __forceinline__ uint32_t ld_u8(const uint8_t *p) { return *p; }
+__device__ __forceinline__ uint32_t ld_le16(const uint8_t *p) { return p[0] | (p[1] << 8); }
+__device__ __forceinline__ uint32_t ld_le32(const uint8_t *p) {
+	return p[0] | (p[1] << 8) | (p[2] << 16) | ((uint32_t)p[3] << 24);
+}
+
+// 16-byte streaming load (read-once data: keep it out of L1)
+__device__ __forceinline__ uint4 ld_stream16(const void *p) {
+	uint4 r;
+	asm volatile("ld.global.nc.L1::no_allocate.v4.u32 {%0,%1,%2,%3}, [%4];"
+		: "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w) : "l"(p));
+	return r;
+}
+__device__ __forceinline__ void st_stream16(void *p, uint4 v) {
+	asm volatile("st.global.L1::no_allocate.v4.u32 [%0], {%1,%2,%3,%4};" ::"l"(p), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory");
+}
+
+// ---------------------------------------------------------------- CRC-32 polynomial arithmetic
+// Reflected representation, as crc32.inc.c:40-47 uses it: bit 31 is x^0.
+#define OTZ_CRC_POLY 0xEDB88320u
+
+// a(x) * b(x) mod P(x)
+__device__ __forceinline__ uint32_t crc_mulmod(uint32_t a, uint32_t b) {
+	uint32_t p = 0;
+#pragma unroll
+	for (int i = 0; i < 32; i++) {
+		p ^= (a & (0x80000000u >> i)) ? b : 0u;
+		b = (b >> 1) ^ ((b & 1u) ? OTZ_CRC_POLY : 0u);
+	}
+	return p;
+}
+
+// Tables resident in global memory (filled once per context by the host).
+struct OtzCrcTables {
+	uint32_t skip[16][256];   // skip[i][b]: CRC state contribution of byte b followed by 511-i zero bytes
+	uint32_t x2n[32];         // x^(2^k) mod P
+	uint32_t xp8[1024 + 64];  // xp8[k + OTZ_XP8_BIAS] = x^(8k) mod P for k in [-OTZ_XP8_BIAS, 1024+64-BIAS)
+	uint32_t t0[256];         // plain byte table
+};
+#define OTZ_XP8_BIAS 528
+
+// x^(8*n) mod P for arbitrary byte counts (serial square-and-multiply over the bits of n).
+__device__ __forceinline__ uint32_t crc_xpow8(uint64_t nbytes, const uint32_t *__restrict__ x2n) {
+	uint32_t p = 0x80000000u;  // x^0
+	int k = 3;                 // x^(2^3) = x^8
+	while (nbytes) {
+		if (nbytes & 1) {
+			p = crc_mulmod(x2n[k & 31], p);
+		}
+		nbytes >>= 1;
+		k++;
+	}
+	return p;
+}

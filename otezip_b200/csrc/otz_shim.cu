@@ -1,0 +1,518 @@
+// otz_shim.cu — the extern "C" seam declared in include/otz_gpu.h: device/stream management,
+// H2D/D2H, work-list construction and kernel launches.  CUDA runtime only; no torch, no NCCL.
+#include <algorithm>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <new>
+#include <vector>
+
+#include "k_copy.cuh"
+#include "k_crc32.cuh"
+#include "k_inflate.cuh"
+#include "k_resolve.cuh"
+#include "otz_common.cuh"
+
+static thread_local char g_err[512] = "";
+
+static int fail_cuda(cudaError_t e, const char *what) {
+	snprintf(g_err, sizeof(g_err), "%s: %s", what, cudaGetErrorString(e));
+	return OTZ_ERR_CUDA;
+}
+#define CK(call)                          \
+	do {                                  \
+		cudaError_t e_ = (call);          \
+		if (e_ != cudaSuccess) {          \
+			return fail_cuda(e_, #call);  \
+		}                                 \
+	} while (0)
+
+struct otz_ctx {
+	int device;
+	int sm_count;
+	cudaStream_t stream;
+	cudaEvent_t ev0, ev1;
+	cudaEvent_t pev[5];
+	int profile;
+	OtzCrcTables *d_tabs;
+	uint8_t *d_flush;
+	uint64_t flush_bytes;
+	uint64_t launches;
+	int inflate_tile;   // lanes per DEFLATE stream (OTZ_INFLATE_TILE, default 32)
+};
+
+struct otz_plan {
+	uint32_t n;
+	otz_extract_opts opts;
+	otz_entry *d_ents;
+	OtzEntryState *d_est;
+	int32_t *d_status;
+	uint32_t *d_acc, *d_crc;
+	OtzCrcChunk *d_chunks;
+	uint32_t n_chunks;
+	uint32_t n_store_chunks;   // chunks [0, n_store_chunks) belong to STORE entries
+	uint32_t *d_inflate_list, n_inflate;
+	uint32_t *d_zstd_list, n_zstd;
+	uint32_t *d_counter;
+	uint64_t out_bytes_needed;
+};
+
+// ---------------------------------------------------------------- CRC tables (host)
+static uint32_t h_mulmod(uint32_t a, uint32_t b) {
+	uint32_t p = 0;
+	for (int i = 0; i < 32; i++) {
+		if (a & (0x80000000u >> i)) {
+			p ^= b;
+		}
+		b = (b >> 1) ^ ((b & 1u) ? OTZ_CRC_POLY : 0u);
+	}
+	return p;
+}
+
+static void build_crc_tables(OtzCrcTables *t) {
+	for (uint32_t i = 0; i < 256; i++) {
+		uint32_t c = i;
+		for (int k = 0; k < 8; k++) {
+			c = (c & 1) ? OTZ_CRC_POLY ^ (c >> 1) : c >> 1;
+		}
+		t->t0[i] = c;
+	}
+	// z[k][b] = state contribution of byte b followed by k zero bytes
+	std::vector<uint32_t> cur(t->t0, t->t0 + 256);
+	for (int k = 0; k <= 511; k++) {
+		if (k >= 496) {
+			memcpy(t->skip[511 - k], cur.data(), 1024);  // skip[i] = z[511 - i]
+		}
+		for (int b = 0; b < 256; b++) {
+			cur[b] = (cur[b] >> 8) ^ t->t0[cur[b] & 0xFF];
+		}
+	}
+	t->x2n[0] = 0x40000000u;  // x^1
+	for (int k = 1; k < 32; k++) {
+		t->x2n[k] = h_mulmod(t->x2n[k - 1], t->x2n[k - 1]);
+	}
+	// x^8 and its inverse x^(2^32-1-8)
+	uint32_t x8 = t->x2n[3], x8inv = 0x80000000u;
+	{
+		uint64_t ex = 0xFFFFFFFFull - 8ull;
+		for (int k = 0; ex; k++, ex >>= 1) {
+			if (ex & 1) {
+				x8inv = h_mulmod(x8inv, t->x2n[k & 31]);
+			}
+		}
+	}
+	const int nxp = (int)(sizeof(t->xp8) / sizeof(t->xp8[0]));
+	t->xp8[OTZ_XP8_BIAS] = 0x80000000u;
+	for (int k = OTZ_XP8_BIAS + 1; k < nxp; k++) {
+		t->xp8[k] = h_mulmod(t->xp8[k - 1], x8);
+	}
+	for (int k = OTZ_XP8_BIAS - 1; k >= 0; k--) {
+		t->xp8[k] = h_mulmod(t->xp8[k + 1], x8inv);
+	}
+}
+
+// ---------------------------------------------------------------- context
+extern "C" const char *otz_last_error(void) { return g_err; }
+
+extern "C" int otz_device_count(void) {
+	int n = 0;
+	if (cudaGetDeviceCount(&n) != cudaSuccess) {
+		cudaGetLastError();
+		return 0;
+	}
+	return n;
+}
+
+extern "C" int otz_ctx_create(int device, otz_ctx **out) {
+	if (!out) {
+		return OTZ_ERR_ARG;
+	}
+	*out = nullptr;
+	CK(cudaSetDevice(device));
+	otz_ctx *c = new (std::nothrow) otz_ctx();
+	if (!c) {
+		return OTZ_ERR_NOMEM;
+	}
+	memset(c, 0, sizeof(*c));
+	c->device = device;
+	cudaDeviceProp prop;
+	CK(cudaGetDeviceProperties(&prop, device));
+	c->sm_count = prop.multiProcessorCount;
+	CK(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
+	CK(cudaEventCreate(&c->ev0));
+	CK(cudaEventCreate(&c->ev1));
+	for (auto &e : c->pev) {
+		CK(cudaEventCreate(&e));
+	}
+	OtzCrcTables *h = new OtzCrcTables();
+	build_crc_tables(h);
+	CK(cudaMalloc(&c->d_tabs, sizeof(OtzCrcTables)));
+	CK(cudaMemcpy(c->d_tabs, h, sizeof(OtzCrcTables), cudaMemcpyHostToDevice));
+	delete h;
+	const char *t = getenv("OTZ_INFLATE_TILE");
+	c->inflate_tile = t ? atoi(t) : 32;
+	if (c->inflate_tile != 4 && c->inflate_tile != 8 && c->inflate_tile != 16 && c->inflate_tile != 32) {
+		c->inflate_tile = 32;
+	}
+	*out = c;
+	return OTZ_SUCCESS;
+}
+
+extern "C" void otz_ctx_destroy(otz_ctx *c) {
+	if (!c) {
+		return;
+	}
+	cudaSetDevice(c->device);
+	cudaStreamSynchronize(c->stream);
+	cudaFree(c->d_tabs);
+	cudaFree(c->d_flush);
+	cudaEventDestroy(c->ev0);
+	cudaEventDestroy(c->ev1);
+	for (auto &e : c->pev) {
+		cudaEventDestroy(e);
+	}
+	cudaStreamDestroy(c->stream);
+	delete c;
+}
+
+extern "C" int otz_sm_count(otz_ctx *c) { return c ? c->sm_count : 0; }
+extern "C" uint64_t otz_launch_count(otz_ctx *c) { return c ? c->launches : 0; }
+
+// ---------------------------------------------------------------- memory
+extern "C" int otz_dev_alloc(otz_ctx *c, uint64_t bytes, void **dptr) {
+	if (!c || !dptr) {
+		return OTZ_ERR_ARG;
+	}
+	CK(cudaSetDevice(c->device));
+	CK(cudaMalloc(dptr, bytes + 64));
+	return OTZ_SUCCESS;
+}
+extern "C" int otz_dev_free(otz_ctx *c, void *dptr) {
+	if (!c) {
+		return OTZ_ERR_ARG;
+	}
+	CK(cudaSetDevice(c->device));
+	CK(cudaFree(dptr));
+	return OTZ_SUCCESS;
+}
+extern "C" int otz_host_alloc(uint64_t bytes, void **hptr) {
+	CK(cudaHostAlloc(hptr, bytes ? bytes : 1, cudaHostAllocDefault));
+	return OTZ_SUCCESS;
+}
+extern "C" int otz_host_free(void *hptr) {
+	CK(cudaFreeHost(hptr));
+	return OTZ_SUCCESS;
+}
+extern "C" int otz_h2d(otz_ctx *c, void *dptr, const void *hptr, uint64_t bytes) {
+	CK(cudaSetDevice(c->device));
+	CK(cudaMemcpyAsync(dptr, hptr, bytes, cudaMemcpyHostToDevice, c->stream));
+	return OTZ_SUCCESS;
+}
+extern "C" int otz_d2h(otz_ctx *c, void *hptr, const void *dptr, uint64_t bytes) {
+	CK(cudaSetDevice(c->device));
+	CK(cudaMemcpyAsync(hptr, dptr, bytes, cudaMemcpyDeviceToHost, c->stream));
+	return OTZ_SUCCESS;
+}
+extern "C" int otz_dev_memset(otz_ctx *c, void *dptr, int value, uint64_t bytes) {
+	CK(cudaSetDevice(c->device));
+	CK(cudaMemsetAsync(dptr, value, bytes, c->stream));
+	return OTZ_SUCCESS;
+}
+extern "C" int otz_sync(otz_ctx *c) {
+	CK(cudaSetDevice(c->device));
+	CK(cudaStreamSynchronize(c->stream));
+	return OTZ_SUCCESS;
+}
+
+// ---------------------------------------------------------------- timing
+extern "C" int otz_timer_start(otz_ctx *c) {
+	CK(cudaSetDevice(c->device));
+	CK(cudaEventRecord(c->ev0, c->stream));
+	return OTZ_SUCCESS;
+}
+extern "C" int otz_timer_stop(otz_ctx *c, float *ms) {
+	CK(cudaSetDevice(c->device));
+	CK(cudaEventRecord(c->ev1, c->stream));
+	CK(cudaEventSynchronize(c->ev1));
+	CK(cudaEventElapsedTime(ms, c->ev0, c->ev1));
+	return OTZ_SUCCESS;
+}
+extern "C" int otz_profile_enable(otz_ctx *c, int on) {
+	c->profile = on;
+	return OTZ_SUCCESS;
+}
+extern "C" int otz_profile_get(otz_ctx *c, float *r, float *d, float *k, float *f) {
+	CK(cudaSetDevice(c->device));
+	CK(cudaEventSynchronize(c->pev[4]));
+	float *dst[4] = { r, d, k, f };
+	for (int i = 0; i < 4; i++) {
+		if (dst[i]) {
+			CK(cudaEventElapsedTime(dst[i], c->pev[i], c->pev[i + 1]));
+		}
+	}
+	return OTZ_SUCCESS;
+}
+
+__global__ void k_flush_fill(uint4 *p, uint64_t n, uint32_t v) {
+	for (uint64_t i = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x; i < n; i += (uint64_t)gridDim.x * blockDim.x) {
+		p[i] = make_uint4(v, v, v, v);
+	}
+}
+extern "C" int otz_flush_l2(otz_ctx *c) {
+	CK(cudaSetDevice(c->device));
+	if (!c->d_flush) {
+		c->flush_bytes = 256ull << 20;  // 2x the 126 MB L2
+		CK(cudaMalloc(&c->d_flush, c->flush_bytes));
+	}
+	k_flush_fill<<<c->sm_count * 4, 256, 0, c->stream>>>(reinterpret_cast<uint4 *>(c->d_flush), c->flush_bytes / 16, (uint32_t)c->launches);
+	CK(cudaGetLastError());
+	return OTZ_SUCCESS;
+}
+
+// ---------------------------------------------------------------- read path
+template <typename T>
+static int upload(T **d, const std::vector<T> &h, cudaStream_t s) {
+	*d = nullptr;
+	CK(cudaMalloc(d, std::max<size_t>(h.size(), 1) * sizeof(T)));
+	if (!h.empty()) {
+		CK(cudaMemcpyAsync(*d, h.data(), h.size() * sizeof(T), cudaMemcpyHostToDevice, s));
+	}
+	return OTZ_SUCCESS;
+}
+
+extern "C" void otz_plan_destroy(otz_ctx *c, otz_plan *p) {
+	if (!p) {
+		return;
+	}
+	if (c) {
+		cudaSetDevice(c->device);
+		cudaStreamSynchronize(c->stream);
+	}
+	cudaFree(p->d_ents);
+	cudaFree(p->d_est);
+	cudaFree(p->d_status);
+	cudaFree(p->d_acc);
+	cudaFree(p->d_crc);
+	cudaFree(p->d_chunks);
+	cudaFree(p->d_inflate_list);
+	cudaFree(p->d_zstd_list);
+	cudaFree(p->d_counter);
+	delete p;
+}
+
+extern "C" int otz_plan_create(otz_ctx *c, const otz_entry *ents, uint32_t n, const otz_extract_opts *opts, otz_plan **out) {
+	if (!c || !out || (n && !ents) || !opts) {
+		return OTZ_ERR_ARG;
+	}
+	*out = nullptr;
+	CK(cudaSetDevice(c->device));
+	otz_plan *p = new (std::nothrow) otz_plan();
+	if (!p) {
+		return OTZ_ERR_NOMEM;
+	}
+	memset(p, 0, sizeof(*p));
+	p->n = n;
+	p->opts = *opts;
+	// Work lists.  CRC chunks: STORE entries first (they are also the copy list), then the rest.
+	std::vector<OtzCrcChunk> chunks;
+	std::vector<uint32_t> infl, zst;
+	uint64_t need = 0;
+	for (int pass = 0; pass < 2; pass++) {
+		for (uint32_t i = 0; i < n; i++) {
+			const bool is_store = ents[i].method == OTZ_M_STORE;
+			if ((pass == 0) != is_store) {
+				continue;
+			}
+			const uint32_t nc = (uint32_t)(((uint64_t)ents[i].uncomp_size + OTZ_CRC_CHUNK - 1) / OTZ_CRC_CHUNK);
+			for (uint32_t k = 0; k < nc; k++) {
+				chunks.push_back(OtzCrcChunk{ i, k });
+			}
+		}
+		if (pass == 0) {
+			p->n_store_chunks = (uint32_t)chunks.size();
+		}
+	}
+	for (uint32_t i = 0; i < n; i++) {
+		if (ents[i].method == OTZ_M_DEFLATE) {
+			infl.push_back(i);
+		} else if (ents[i].method == OTZ_M_ZSTD) {
+			zst.push_back(i);
+		}
+		if (!(opts->verify_only && ents[i].method == OTZ_M_STORE)) {
+			need = std::max<uint64_t>(need, ents[i].out_ofs + ents[i].uncomp_size);
+		}
+	}
+	// longest streams first: the tail of the batch is then made of short ones
+	std::stable_sort(infl.begin(), infl.end(), [&](uint32_t a, uint32_t b) { return ents[a].comp_size > ents[b].comp_size; });
+	p->n_chunks = (uint32_t)chunks.size();
+	p->n_inflate = (uint32_t)infl.size();
+	p->n_zstd = (uint32_t)zst.size();
+	p->out_bytes_needed = need;
+	int rc;
+	std::vector<otz_entry> ev(ents, ents + n);
+	if ((rc = upload(&p->d_ents, ev, c->stream)) || (rc = upload(&p->d_chunks, chunks, c->stream)) ||
+		(rc = upload(&p->d_inflate_list, infl, c->stream)) || (rc = upload(&p->d_zstd_list, zst, c->stream))) {
+		otz_plan_destroy(c, p);
+		return rc;
+	}
+	const size_t n1 = std::max<uint32_t>(n, 1);
+	if (cudaMalloc(&p->d_est, n1 * sizeof(OtzEntryState)) != cudaSuccess || cudaMalloc(&p->d_status, n1 * 4) != cudaSuccess ||
+		cudaMalloc(&p->d_acc, n1 * 4) != cudaSuccess || cudaMalloc(&p->d_crc, n1 * 4) != cudaSuccess ||
+		cudaMalloc(&p->d_counter, 64) != cudaSuccess) {
+		otz_plan_destroy(c, p);
+		return fail_cuda(cudaGetLastError(), "cudaMalloc(plan)");
+	}
+	CK(cudaStreamSynchronize(c->stream));  // the host vectors die here
+	*out = p;
+	return OTZ_SUCCESS;
+}
+
+template <int G>
+static int launch_inflate(otz_ctx *c, otz_plan *p, const uint8_t *d_archive, uint8_t *d_out) {
+	const int threads = 256;
+	const size_t smem = (threads / G) * sizeof(InflateSmem);
+	static bool attr_done = false;
+	if (!attr_done) {
+		CK(cudaFuncSetAttribute(k_inflate<G>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+		attr_done = true;
+	}
+	int per_sm = 0;
+	CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_inflate<G>, threads, smem));
+	if (per_sm < 1) {
+		per_sm = 1;
+	}
+	const uint32_t tiles_per_cta = threads / G;
+	uint32_t grid = (uint32_t)(c->sm_count * per_sm);
+	const uint32_t want = (p->n_inflate + tiles_per_cta - 1) / tiles_per_cta;
+	grid = std::max(1u, std::min(grid, want));
+	k_inflate<G><<<grid, threads, smem, c->stream>>>(d_archive, d_out, p->d_ents, p->d_est, p->d_status, p->d_inflate_list,
+		p->n_inflate, p->d_counter);
+	c->launches++;
+	CK(cudaGetLastError());
+	return OTZ_SUCCESS;
+}
+
+extern "C" int otz_extract_run(otz_ctx *c, otz_plan *p, const uint8_t *d_archive, uint64_t archive_len, uint8_t *d_out,
+	uint64_t out_len) {
+	if (!c || !p || (!d_archive && archive_len)) {
+		return OTZ_ERR_ARG;
+	}
+	if (p->out_bytes_needed > out_len || (p->out_bytes_needed && !d_out)) {
+		snprintf(g_err, sizeof(g_err), "output arena too small: need %llu, have %llu", (unsigned long long)p->out_bytes_needed,
+			(unsigned long long)out_len);
+		return OTZ_ERR_ARG;
+	}
+	CK(cudaSetDevice(c->device));
+	cudaStream_t s = c->stream;
+	const uint32_t n = p->n;
+	if (c->profile) {
+		CK(cudaEventRecord(c->pev[0], s));
+	}
+	if (n) {
+		CK(cudaMemsetAsync(p->d_counter, 0, 64, s));
+		k_resolve<<<(n + 255) / 256, 256, 0, s>>>(d_archive, archive_len, out_len, p->d_ents, n, p->d_est, p->d_status, p->d_acc, p->opts);
+		c->launches++;
+	}
+	if (c->profile) {
+		CK(cudaEventRecord(c->pev[1], s));
+	}
+	const uint32_t persistent = (uint32_t)c->sm_count * 8;  // 8 CTAs x 8 warps = 64 warps per SM
+	if (p->n_store_chunks && !p->opts.verify_only) {
+		k_store_copy<<<std::min(persistent, (p->n_store_chunks + 7) / 8), 256, 0, s>>>(d_archive, d_out, p->d_ents, p->d_est, p->d_status,
+			p->d_chunks, p->n_store_chunks);
+		c->launches++;
+	}
+	if (p->n_zstd) {
+		k_zstdref<<<std::min(persistent, (p->n_zstd + 7) / 8), 256, 0, s>>>(d_archive, d_out, p->d_ents, p->d_est, p->d_status, p->d_zstd_list,
+			p->n_zstd);
+		c->launches++;
+	}
+	if (p->n_inflate) {
+		int rc;
+		switch (c->inflate_tile) {
+		case 4: rc = launch_inflate<4>(c, p, d_archive, d_out); break;
+		case 8: rc = launch_inflate<8>(c, p, d_archive, d_out); break;
+		case 16: rc = launch_inflate<16>(c, p, d_archive, d_out); break;
+		default: rc = launch_inflate<32>(c, p, d_archive, d_out); break;
+		}
+		if (rc) {
+			return rc;
+		}
+	}
+	if (c->profile) {
+		CK(cudaEventRecord(c->pev[2], s));
+	}
+	if (p->n_chunks) {
+		// 4 CTAs x 256 threads per SM (16 KiB of tables each)
+		const uint32_t grid = std::min((uint32_t)c->sm_count * 4, (p->n_chunks + 7) / 8);
+		k_crc_chunks<<<grid, 256, 0, s>>>(d_archive, d_out, p->d_ents, p->d_est, p->d_status, p->d_chunks, p->n_chunks, p->d_acc, c->d_tabs,
+			p->opts.verify_only);
+		c->launches++;
+	}
+	if (c->profile) {
+		CK(cudaEventRecord(c->pev[3], s));
+	}
+	if (n) {
+		k_crc_finalize<<<(n + 255) / 256, 256, 0, s>>>(p->d_ents, n, p->d_acc, p->d_crc, p->d_status, c->d_tabs);
+		c->launches++;
+	}
+	if (c->profile) {
+		CK(cudaEventRecord(c->pev[4], s));
+	}
+	CK(cudaGetLastError());
+	return OTZ_SUCCESS;
+}
+
+extern "C" int otz_extract_results(otz_ctx *c, otz_plan *p, uint32_t *crc, int32_t *status) {
+	if (!c || !p) {
+		return OTZ_ERR_ARG;
+	}
+	CK(cudaSetDevice(c->device));
+	if (p->n && crc) {
+		CK(cudaMemcpyAsync(crc, p->d_crc, p->n * 4ull, cudaMemcpyDeviceToHost, c->stream));
+	}
+	if (p->n && status) {
+		CK(cudaMemcpyAsync(status, p->d_status, p->n * 4ull, cudaMemcpyDeviceToHost, c->stream));
+	}
+	CK(cudaStreamSynchronize(c->stream));
+	return OTZ_SUCCESS;
+}
+
+extern "C" int otz_extract_host(otz_ctx *c, const uint8_t *archive, uint64_t archive_len, const otz_entry *ents, uint32_t n,
+	const otz_extract_opts *opts, uint8_t *out, uint64_t out_len, uint32_t *crc, int32_t *status) {
+	if (!c || !opts) {
+		return OTZ_ERR_ARG;
+	}
+	otz_plan *p = nullptr;
+	int rc = otz_plan_create(c, ents, n, opts, &p);
+	if (rc) {
+		return rc;
+	}
+	void *d_arch = nullptr, *d_out = nullptr;
+	do {
+		if ((rc = otz_dev_alloc(c, archive_len, &d_arch))) break;
+		if (out_len && (rc = otz_dev_alloc(c, out_len, &d_out))) break;
+		if ((rc = otz_h2d(c, d_arch, archive, archive_len))) break;
+		if ((rc = otz_extract_run(c, p, (const uint8_t *)d_arch, archive_len, (uint8_t *)d_out, out_len))) break;
+		if (out && p->out_bytes_needed && (rc = otz_d2h(c, out, d_out, p->out_bytes_needed))) break;
+		rc = otz_extract_results(c, p, crc, status);
+	} while (0);
+	cudaStreamSynchronize(c->stream);
+	if (d_arch) cudaFree(d_arch);
+	if (d_out) cudaFree(d_out);
+	otz_plan_destroy(c, p);
+	return rc;
+}
+
+extern "C" int otz_status_accepts(int32_t st, int verify_crc, int ref_compat) {
+	if (OTZ_ST_CODE(st) != OTZ_ST_OK) {
+		return 0;
+	}
+	if (ref_compat && (st & OTZ_STF_REF_EOB)) {
+		return 0;  // dec:811-816: the reference answers Z_BUF_ERROR
+	}
+	if (verify_crc && (st & OTZ_STF_CRC_MISMATCH)) {
+		return 0;  // otezip.c:670-673
+	}
+	return 1;
+}

@@ -1,0 +1,216 @@
+"""ctypes loader for libotezip_b200.so (include/otz_gpu.h).  Fails loudly when the library is
+missing; there is no fallback."""
+from __future__ import annotations
+
+import ctypes as C
+import os
+import struct
+
+import numpy as np
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+
+
+def lib_path() -> str:
+    return os.path.join(HERE, "libotezip_b200.so")
+
+
+class OtzEntry(C.Structure):  # struct otz_entry, include/otz_gpu.h
+    _fields_ = [("lfh_ofs", C.c_uint64), ("out_ofs", C.c_uint64), ("comp_size", C.c_uint32),
+                ("uncomp_size", C.c_uint32), ("crc32", C.c_uint32), ("method", C.c_uint16), ("flags", C.c_uint16)]
+
+
+ENTRY_DTYPE = np.dtype([("lfh_ofs", "<u8"), ("out_ofs", "<u8"), ("comp_size", "<u4"), ("uncomp_size", "<u4"),
+                        ("crc32", "<u4"), ("method", "<u2"), ("flags", "<u2")])
+assert ENTRY_DTYPE.itemsize == C.sizeof(OtzEntry) == 32
+
+
+class OtzOpts(C.Structure):  # struct otz_extract_opts
+    _fields_ = [("ignore_zipbomb", C.c_int), ("max_ratio", C.c_uint64), ("max_slack", C.c_uint64),
+                ("verify_only", C.c_int)]
+
+
+def default_opts(verify_only: int = 0, ignore_zipbomb: int = 0) -> OtzOpts:
+    return OtzOpts(ignore_zipbomb, 1000, 1 << 20, verify_only)
+
+
+ST_OK = 0
+STF_CRC_MISMATCH, STF_REF_EOB, STF_SHORT = 0x100, 0x200, 0x400
+
+
+class Lib:
+    _inst = None
+
+    def __init__(self):
+        p = lib_path()
+        if not os.path.exists(p):
+            raise RuntimeError("libotezip_b200.so is not built (run `make` or __graft_entry__.build()); "
+                               "there is no CPU fallback")
+        L = self.L = C.CDLL(p)
+        vp, u64, u32p, i32p = C.c_void_p, C.c_uint64, C.POINTER(C.c_uint32), C.POINTER(C.c_int32)
+        L.otz_last_error.restype = C.c_char_p
+        L.otz_ctx_create.argtypes = [C.c_int, C.POINTER(vp)]
+        L.otz_ctx_destroy.argtypes = [vp]
+        L.otz_ctx_destroy.restype = None
+        L.otz_sm_count.argtypes = [vp]
+        L.otz_launch_count.argtypes = [vp]
+        L.otz_launch_count.restype = u64
+        L.otz_dev_alloc.argtypes = [vp, u64, C.POINTER(vp)]
+        L.otz_dev_free.argtypes = [vp, vp]
+        L.otz_host_alloc.argtypes = [u64, C.POINTER(vp)]
+        L.otz_host_free.argtypes = [vp]
+        L.otz_h2d.argtypes = [vp, vp, vp, u64]
+        L.otz_d2h.argtypes = [vp, vp, vp, u64]
+        L.otz_dev_memset.argtypes = [vp, vp, C.c_int, u64]
+        L.otz_sync.argtypes = [vp]
+        L.otz_timer_start.argtypes = [vp]
+        L.otz_timer_stop.argtypes = [vp, C.POINTER(C.c_float)]
+        L.otz_profile_enable.argtypes = [vp, C.c_int]
+        L.otz_profile_get.argtypes = [vp] + [C.POINTER(C.c_float)] * 4
+        L.otz_flush_l2.argtypes = [vp]
+        L.otz_plan_create.argtypes = [vp, vp, C.c_uint32, C.POINTER(OtzOpts), C.POINTER(vp)]
+        L.otz_plan_destroy.argtypes = [vp, vp]
+        L.otz_plan_destroy.restype = None
+        L.otz_extract_run.argtypes = [vp, vp, vp, u64, vp, u64]
+        L.otz_extract_results.argtypes = [vp, vp, vp, vp]
+        L.otz_extract_host.argtypes = [vp, vp, u64, vp, C.c_uint32, C.POINTER(OtzOpts), vp, u64, vp, vp]
+        L.otz_status_accepts.argtypes = [C.c_int32, C.c_int, C.c_int]
+
+    @classmethod
+    def get(cls) -> "Lib":
+        if cls._inst is None:
+            cls._inst = Lib()
+        return cls._inst
+
+    def check(self, rc: int, what: str = ""):
+        if rc != 0:
+            raise RuntimeError("%s failed (%d): %s" % (what, rc, self.L.otz_last_error().decode()))
+
+
+def parse_central(img) -> np.ndarray:
+    """Entry table (ENTRY_DTYPE, out_ofs 16-byte aligned prefix sums) from a ZIP image.  Test/bench helper
+    mirroring what the C host library's central-directory walk emits; not a decoder."""
+    b = memoryview(img)
+    n = len(b)
+    pos = -1
+    lo = max(0, n - 65558)
+    tail = bytes(b[lo:])
+    i = len(tail) - 22
+    while i >= 0:
+        if tail[i:i + 4] == b"PK\x05\x06":
+            ents, sz, ofs = struct.unpack_from("<HII", tail, i + 10)
+            if ofs + sz <= n and (ents == 0 or bytes(b[ofs:ofs + 4]) == b"PK\x01\x02"):
+                pos = lo + i
+                break
+        i -= 1
+    if pos < 0:
+        raise ValueError("no EOCD")
+    tab = np.zeros(ents, dtype=ENTRY_DTYPE)
+    off = ofs
+    out = 0
+    for k in range(ents):
+        (sig, _, _, _, method, _, _, crc, comp, uncomp, fl, xl, cl, _, _, _, lfh) = struct.unpack_from(
+            "<IHHHHHHIIIHHHHHII", b, off)
+        assert sig == 0x02014B50
+        tab[k] = (lfh, out, comp, uncomp, crc, method, 0)
+        out += (uncomp + 15) & ~15
+        off += 46 + fl + xl + cl
+    return tab
+
+
+class Ctx:
+    """One device context (stream, CRC tables, scratch)."""
+
+    def __init__(self, device: int = 0):
+        self.lib = Lib.get()
+        self.L = self.lib.L
+        h = C.c_void_p()
+        self.lib.check(self.L.otz_ctx_create(device, C.byref(h)), "otz_ctx_create")
+        self.h = h
+
+    def close(self):
+        if self.h:
+            self.L.otz_ctx_destroy(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    # -- memory
+    def dev_alloc(self, nbytes: int) -> C.c_void_p:
+        p = C.c_void_p()
+        self.lib.check(self.L.otz_dev_alloc(self.h, nbytes, C.byref(p)), "otz_dev_alloc")
+        return p
+
+    def dev_free(self, p):
+        self.L.otz_dev_free(self.h, p)
+
+    def pinned(self, nbytes: int) -> np.ndarray:
+        p = C.c_void_p()
+        self.lib.check(self.L.otz_host_alloc(nbytes, C.byref(p)), "otz_host_alloc")
+        arr = np.ctypeslib.as_array(C.cast(p, C.POINTER(C.c_uint8)), shape=(max(nbytes, 1),))
+        return arr[:nbytes]
+
+    def h2d(self, d, h: np.ndarray, nbytes: int | None = None):
+        self.lib.check(self.L.otz_h2d(self.h, d, h.ctypes.data_as(C.c_void_p), h.nbytes if nbytes is None else nbytes), "h2d")
+
+    def d2h(self, h: np.ndarray, d, nbytes: int | None = None):
+        self.lib.check(self.L.otz_d2h(self.h, h.ctypes.data_as(C.c_void_p), d, h.nbytes if nbytes is None else nbytes), "d2h")
+
+    def sync(self):
+        self.lib.check(self.L.otz_sync(self.h), "otz_sync")
+
+    def timer_start(self):
+        self.lib.check(self.L.otz_timer_start(self.h), "timer_start")
+
+    def timer_stop(self) -> float:
+        ms = C.c_float()
+        self.lib.check(self.L.otz_timer_stop(self.h, C.byref(ms)), "timer_stop")
+        return ms.value
+
+    def flush_l2(self):
+        self.lib.check(self.L.otz_flush_l2(self.h), "flush_l2")
+
+    def launches(self) -> int:
+        return int(self.L.otz_launch_count(self.h))
+
+    # -- read path
+    def plan(self, table: np.ndarray, opts: OtzOpts):
+        p = C.c_void_p()
+        t = np.ascontiguousarray(table)
+        self.lib.check(self.L.otz_plan_create(self.h, t.ctypes.data_as(C.c_void_p), len(t), C.byref(opts), C.byref(p)),
+                       "otz_plan_create")
+        return p
+
+    def plan_destroy(self, p):
+        self.L.otz_plan_destroy(self.h, p)
+
+    def run(self, plan, d_archive, archive_len: int, d_out, out_len: int):
+        self.lib.check(self.L.otz_extract_run(self.h, plan, d_archive, archive_len, d_out, out_len), "otz_extract_run")
+
+    def results(self, plan, n: int):
+        crc = np.zeros(max(n, 1), dtype=np.uint32)
+        st = np.zeros(max(n, 1), dtype=np.int32)
+        self.lib.check(self.L.otz_extract_results(self.h, plan, crc.ctypes.data_as(C.c_void_p),
+                                                  st.ctypes.data_as(C.c_void_p)), "otz_extract_results")
+        return crc[:n], st[:n]
+
+    def extract_host(self, img, table: np.ndarray, opts: OtzOpts | None = None):
+        """H2D image -> batch extract -> D2H arena. -> (out uint8[], crc uint32[n], status int32[n])"""
+        opts = opts or default_opts()
+        n = len(table)
+        t = np.ascontiguousarray(table)
+        out_len = int((t["out_ofs"].astype(np.int64) + t["uncomp_size"]).max()) if n else 0
+        out = np.zeros(max(out_len, 1), dtype=np.uint8)
+        crc = np.zeros(max(n, 1), dtype=np.uint32)
+        st = np.zeros(max(n, 1), dtype=np.int32)
+        buf = np.frombuffer(img, dtype=np.uint8) if not isinstance(img, np.ndarray) else img
+        self.lib.check(self.L.otz_extract_host(self.h, buf.ctypes.data_as(C.c_void_p), buf.nbytes,
+                                               t.ctypes.data_as(C.c_void_p), n, C.byref(opts),
+                                               out.ctypes.data_as(C.c_void_p), out_len,
+                                               crc.ctypes.data_as(C.c_void_p), st.ctypes.data_as(C.c_void_p)),
+                       "otz_extract_host")
+        return out[:out_len], crc[:n], st[:n]
