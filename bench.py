@@ -1,0 +1,467 @@
+#!/usr/bin/env python
+"""bench.py — extract GB/s (uncompressed output, device-timed) of the otezip_b200 hot path.
+
+  python bench.py [--gpus N] [--steps K] [--warmup W] [--workload c2|c1|c3|c4] [--impl reference]
+
+One "step" = one pass of the batched extract over one synthetic archive set.  The default
+workload (N=1 headline) is BASELINE.json configs[1]: STORE + CRC-32 verify only, 10,000 entries
+of 1 MiB random bytes, laid out as an archive set of 8 x 1,250-entry ZIP32 files
+resident in HBM as one image.  Under torchrun (N>1) every rank owns one GPU and its own archive
+set (entries shard by index, no data-path collective): weak scaling, value = all ranks' bytes
+over the max-over-ranks device time.
+
+Output: ONE JSON line (see the contract in the task statement), with `roofline` for the dominant
+kernel and `cpu_baseline` = the compiled reference (oracle/_ref) on the host cores.
+"""
+from __future__ import annotations
+
+import argparse
+import concurrent.futures as cf
+import json
+import os
+import struct
+import sys
+import threading
+import time
+import zlib
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+GB = 1e9
+
+
+# ----------------------------------------------------------------------------- workloads
+def _zip_headers(name: bytes, method: int, crc: int, comp: int, uncomp: int, lfh_ofs: int):
+    lfh = struct.pack("<IHHHHHIIIHH", 0x04034B50, 20, 0, method, 0, 0x21, crc, comp, uncomp, len(name), 0) + name
+    cdh = struct.pack("<IHHHHHHIIIHHHHHII", 0x02014B50, 0x031E, 20, 0, method, 0, 0x21, crc, comp, uncomp, len(name),
+                      0, 0, 0, 0, 0o100644 << 16, lfh_ofs) + name
+    return lfh, cdh
+
+
+def build_archive_set(alloc, payloads_fn, n_entries: int, per_archive: int, method: int, threads: int = 8):
+    """Lay out ceil(n/per_archive) ZIP32 archives back to back in one buffer from alloc(nbytes).
+    payloads_fn(i) -> (payload bytes-like, uncomp_size, crc32).  Returns (image, entry table)."""
+    from otezip_b200.native import ENTRY_DTYPE
+    # pass 1: sizes
+    metas = []
+    with cf.ThreadPoolExecutor(threads) as ex:
+        metas = list(ex.map(payloads_fn, range(n_entries)))
+    n_arch = (n_entries + per_archive - 1) // per_archive
+    total = 0
+    layout = []
+    for a in range(n_arch):
+        base = total
+        ents = range(a * per_archive, min(n_entries, (a + 1) * per_archive))
+        pos = 0
+        cd_len = 0
+        recs = []
+        for i in ents:
+            name = b"e/%05d.bin" % i
+            recs.append((i, pos, name))
+            pos += 30 + len(name) + len(metas[i][0])
+            cd_len += 46 + len(name)
+        layout.append((base, recs, pos, cd_len))
+        total += pos + cd_len + 22
+        total = (total + 15) & ~15
+    img = alloc(total)
+    tab = np.zeros(n_entries, dtype=ENTRY_DTYPE)
+    out_ofs = 0
+    for base, recs, cd_ofs, cd_len in layout:
+        cd = bytearray()
+        for i, pos, name in recs:
+            payload, uncomp, crc = metas[i]
+            lfh, cdh = _zip_headers(name, method, crc, len(payload), uncomp, pos)
+            o = base + pos
+            img[o:o + len(lfh)] = np.frombuffer(lfh, dtype=np.uint8)
+            o += len(lfh)
+            img[o:o + len(payload)] = np.frombuffer(payload, dtype=np.uint8)
+            cd += cdh
+            tab[i] = (base + pos, out_ofs, len(payload), uncomp, crc, method, 0)
+            out_ofs += (uncomp + 15) & ~15
+        o = base + cd_ofs
+        img[o:o + len(cd)] = np.frombuffer(bytes(cd), dtype=np.uint8)
+        o += len(cd)
+        eocd = struct.pack("<IHHHHIIH", 0x06054B50, 0, 0, len(recs), len(recs), len(cd), cd_ofs, 0)
+        img[o:o + 22] = np.frombuffer(eocd, dtype=np.uint8)
+    return img, tab, out_ofs
+
+
+def workload(name: str, rank: int, n_entries: int | None, alloc):
+    """-> dict(image, table, out_bytes, uncomp_bytes, algo_bytes, opts, desc)"""
+    from otezip_b200 import synth
+    from otezip_b200.native import default_opts
+    if name == "c2":
+        n = n_entries or 10000
+        size = 1 << 20
+
+        def gen(i):
+            rng = np.random.Generator(np.random.PCG64([2, rank, i]))
+            d = rng.bit_generator.random_raw(size // 8).view(np.uint8)
+            return d, size, zlib.crc32(d) & 0xFFFFFFFF
+        img, tab, out_bytes = build_archive_set(alloc, gen, n, 1250, 0)
+        un = int(tab["uncomp_size"].astype(np.int64).sum())
+        return dict(image=img, table=tab, out_bytes=0, uncomp_bytes=un, algo_bytes=un, opts=default_opts(verify_only=1),
+                    desc="STORE + CRC-32 verify only, %d entries x 1 MiB random bytes (archive set of %d ZIP32 files)"
+                    % (n, (n + 1249) // 1250), dominant="crc")
+    pool = synth.TextPool(64 << 20, seed={"c1": 1234, "c3": 3, "c4": 4}[name] + 7919 * rank)
+    if name == "c1":
+        n = n_entries or 1000
+        sizes = [65536] * n
+        method, per = 8, 60000
+        desc = "DEFLATE inflate + CRC-32, %d entries x 64 KiB JSON-log text, zlib level 6, ref-safe tail" % n
+    elif name == "c3":
+        n = n_entries or 2000
+        sizes = synth.config_c3_sizes(n, seed=3 + rank, lo=12, hi=24)
+        method, per = 8, 60000
+        desc = "DEFLATE inflate + CRC-32, %d mixed entries 4 KiB-16 MiB JSON-log text, zlib level 6" % n
+    elif name == "c4":
+        n = n_entries or 10000
+        sizes = [262144] * n
+        method, per = 93, 15000
+        desc = "method-93 (reference container) decode + CRC-32, %d entries x 256 KiB" % n
+    else:
+        raise SystemExit("unknown workload " + name)
+    datas = [pool.take(s) for s in sizes]
+
+    def gen(i):
+        d = datas[i]
+        crc = zlib.crc32(d) & 0xFFFFFFFF
+        pl = synth.deflate_raw(d, 6, True) if method == 8 else synth.zstdref_container(d)
+        return pl, len(d), crc
+    img, tab, out_bytes = build_archive_set(alloc, gen, n, per, method)
+    un = int(tab["uncomp_size"].astype(np.int64).sum())
+    comp = int(tab["comp_size"].astype(np.int64).sum())
+    return dict(image=img, table=tab, out_bytes=out_bytes, uncomp_bytes=un, algo_bytes=un + comp,
+                opts=default_opts(), desc=desc, dominant="decode")
+
+
+# ----------------------------------------------------------------------------- clocks
+class ClockSampler(threading.Thread):
+    """Samples SM clock / throttle reasons of one GPU through NVML while the timed region runs."""
+
+    REASONS = {0x8: "hw_slowdown", 0x40: "hw_thermal_slowdown", 0x20: "sw_thermal_slowdown", 0x4: "sw_power_cap"}
+
+    def __init__(self, pci_bus_id: str, period: float = 0.02):
+        super().__init__(daemon=True)
+        self.samples = []
+        self.period = period
+        self.stop_ev = threading.Event()
+        self.ok = False
+        self.marks = []
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            self.nv = pynvml
+            self.h = pynvml.nvmlDeviceGetHandleByPciBusId(pci_bus_id.encode())
+            self.max_sm = pynvml.nvmlDeviceGetMaxClockInfo(self.h, pynvml.NVML_CLOCK_SM)
+            self.ok = True
+        except Exception as e:  # pragma: no cover
+            self.err = repr(e)
+
+    def run(self):
+        if not self.ok:
+            return
+        nv = self.nv
+        while not self.stop_ev.is_set():
+            try:
+                sm = nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM)
+                rs = nv.nvmlDeviceGetCurrentClocksThrottleReasons(self.h)
+                self.samples.append((time.perf_counter(), sm, rs))
+            except Exception:
+                pass
+            time.sleep(self.period)
+
+    def mark(self):
+        self.marks.append(time.perf_counter())
+
+    def summary(self):
+        if not self.ok or not self.samples:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "note": "NVML unavailable"}
+        t0, t1 = (self.marks + [None, None])[:2]
+        sel = [s for s in self.samples if t0 is not None and t1 is not None and t0 <= s[0] <= t1]
+        where = "timed region"
+        if len(sel) < 2:
+            sel, where = self.samples, "whole bench (timed region shorter than the sampling period)"
+        sm = sorted(s[1] for s in sel)
+        bits = 0
+        for s in sel:
+            bits |= s[2]
+        return {"sm_mhz": sm[len(sm) // 2], "sm_max_mhz": self.max_sm,
+                "reasons": [v for k, v in self.REASONS.items() if bits & k], "samples": len(sel), "window": where}
+
+
+# ----------------------------------------------------------------------------- distributed plumbing
+class Dist:
+    def __init__(self, n):
+        self.world = int(os.environ.get("WORLD_SIZE", "1"))
+        self.rank = int(os.environ.get("RANK", "0"))
+        self.local = int(os.environ.get("LOCAL_RANK", "0"))
+        self.torch = None
+        if self.world > 1:
+            import torch
+            import torch.distributed as dist
+            self.torch, self.dist = torch, dist
+            os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+            backend = "nccl" if torch.cuda.is_available() else "gloo"
+            if backend == "nccl":
+                torch.cuda.set_device(self.local)
+            dist.init_process_group(backend)
+            self.dev = torch.device("cuda", self.local) if backend == "nccl" else torch.device("cpu")
+
+    def barrier(self):
+        if self.world > 1:
+            self.dist.barrier()
+            if self.dev.type == "cuda":
+                self.torch.cuda.synchronize()
+
+    def max(self, v: float) -> float:
+        if self.world == 1:
+            return v
+        t = self.torch.tensor([v], dtype=self.torch.float64, device=self.dev)
+        self.dist.all_reduce(t, op=self.dist.ReduceOp.MAX)
+        return float(t.item())
+
+    def sum(self, v: float) -> float:
+        if self.world == 1:
+            return v
+        t = self.torch.tensor([v], dtype=self.torch.float64, device=self.dev)
+        self.dist.all_reduce(t, op=self.dist.ReduceOp.SUM)
+        return float(t.item())
+
+    def close(self):
+        if self.world > 1:
+            self.dist.destroy_process_group()
+
+
+# ----------------------------------------------------------------------------- reference arm (CPU)
+def reference_sample_archive(wl_name: str, tmpdir: str):
+    """A bounded sample of the workload as one ZIP32 file on disk (the reference reads FILE*)."""
+    from otezip_b200 import synth
+    if wl_name == "c2":
+        ms = synth.config_c2(64, 1 << 20, seed=2)
+        what = "64 x 1 MiB STORE entries per thread per pass"
+    elif wl_name == "c1":
+        ms = synth.config_c1(8, 65536)
+        what = "8 x 64 KiB DEFLATE entries per thread per pass"
+    elif wl_name == "c3":
+        ms = synth.config_c3(8, seed=3, lo=12, hi=18)
+        what = "8 mixed DEFLATE entries (4-256 KiB) per thread per pass"
+    else:
+        ms = synth.config_c4(32, 262144)
+        what = "32 x 256 KiB method-93 entries per thread per pass"
+    path = os.path.join(tmpdir, "otz_ref_sample_%s_%d.zip" % (wl_name, os.getpid()))
+    with open(path, "wb") as f:
+        f.write(synth.build_zip(ms))
+    return path, sum(m.uncomp_size for m in ms), what
+
+
+def reference_pass(ref, path: str, threads: int) -> float:
+    """All threads run zip_open -> zip_fopen_index(i) -> zip_fclose over the sample; returns seconds."""
+    def one(_):
+        err, res = ref.extract_file(path, verify_crc=1, keep_data=False)
+        assert err == 0 and all(r is not None for r in res)
+    t0 = time.perf_counter()
+    with cf.ThreadPoolExecutor(threads) as ex:
+        list(ex.map(one, range(threads)))
+    return time.perf_counter() - t0
+
+
+def cpu_baseline(wl_name: str, budget_s: float = 12.0):
+    from oracle import RefLib
+    ref = RefLib()
+    cores = os.cpu_count() or 1
+    tmp = "/dev/shm" if os.path.isdir("/dev/shm") else "/tmp"
+    path, nbytes, what = reference_sample_archive(wl_name, tmp)
+    try:
+        t = reference_pass(ref, path, cores)          # also warms the page cache
+        passes = max(1, min(50, int(budget_s / max(t, 1e-3))))
+        t0 = time.perf_counter()
+        for _ in range(passes):
+            reference_pass(ref, path, cores)
+        dt = time.perf_counter() - t0
+    finally:
+        os.unlink(path)
+    return {"value": cores * passes * nbytes / dt / GB, "unit": "GB/s", "cores": cores, "kind": "reference",
+            "sample": "%s, %d threads x %d passes (compiled reference oracle/_ref, zip_open/zip_fopen_index/zip_fclose, "
+                      "otezip_verify_crc=1)" % (what, cores, passes)}
+
+
+def run_reference(args, dist: Dist):
+    if dist.rank != 0:
+        return
+    from oracle import RefLib
+    ref = RefLib()
+    cores = os.cpu_count() or 1
+    tmp = "/dev/shm" if os.path.isdir("/dev/shm") else "/tmp"
+    path, nbytes, what = reference_sample_archive(args.workload, tmp)
+    try:
+        for _ in range(args.warmup):
+            reference_pass(ref, path, cores)
+        t0 = time.perf_counter()
+        for _ in range(args.steps):
+            reference_pass(ref, path, cores)
+        dt = time.perf_counter() - t0
+    finally:
+        os.unlink(path)
+    v = cores * args.steps * nbytes / dt / GB
+    print(json.dumps({
+        "impl": "reference", "metric": "extract GB/s (uncompressed output) — reference CPU path on the host cores",
+        "value": v, "unit": "GB/s", "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
+        "ms_per_step": dt / args.steps * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "u8", "data": "synthetic", "config": {"workload": WORKLOADS[args.workload]},
+        "cpu_baseline": {"value": v, "unit": "GB/s", "cores": cores, "kind": "reference",
+                         "sample": "each step: " + what + ", %d threads" % cores},
+        "e2e": {"value": v, "unit": "GB/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0}))
+
+
+WORKLOADS = {
+    "c2": "configs[1]: STORE + CRC-32 verify only, 10,000 entries of 1 MiB random bytes",
+    "c1": "configs[0]: 1,000-entry DEFLATE archive, 64 KiB text-like entries, CRC-32 check",
+    "c3": "configs[2]: DEFLATE inflate of mixed-size entries (4 KiB-16 MiB) JSON-log text",
+    "c4": "configs[3]: method 93 decode of 256 KiB entries (reference container)",
+}
+
+
+# ----------------------------------------------------------------------------- main arm
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=50)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--workload", default="c2", choices=list(WORKLOADS))
+    ap.add_argument("--entries", type=int, default=None, help="override the entry count (quick runs)")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--e2e-steps", type=int, default=None)
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3) if args.impl == "b200" else args.warmup
+    dist = Dist(args.gpus)
+    if args.impl == "reference":
+        run_reference(args, dist)
+        dist.close()
+        return
+
+    from otezip_b200 import Ctx
+    from otezip_b200 import native
+    ctx = Ctx(dist.local)
+    wl = workload(args.workload, dist.rank, args.entries, ctx.pinned)
+    img, tab = wl["image"], wl["table"]
+    n = len(tab)
+    d_img = ctx.dev_alloc(img.nbytes)
+    ctx.h2d(d_img, img)
+    d_out = ctx.dev_alloc(wl["out_bytes"]) if wl["out_bytes"] else None
+    plan = ctx.plan(tab, wl["opts"])
+    ctx.sync()
+
+    def step():
+        ctx.run(plan, d_img, img.nbytes, d_out, wl["out_bytes"])
+
+    sampler = ClockSampler(ctx.pci_bus_id())
+    sampler.start()
+    for _ in range(args.warmup):
+        step()
+    ctx.sync()
+    crc, st = ctx.results(plan, n)
+    bad = int(np.count_nonzero(st != 0))
+    if bad or not np.array_equal(crc, tab["crc32"]):
+        raise SystemExit("bench: %d entries failed on the GPU path (status/CRC) — number would be invalid" % bad)
+
+    # ---- device-timed region: K steps, inputs resident in HBM
+    dist.barrier()
+    ctx.sync()
+    ctx.profile(1)
+    l0 = ctx.launches()
+    sampler.mark()
+    ctx.timer_start()
+    for _ in range(args.steps):
+        step()
+    ms = ctx.timer_stop()
+    sampler.mark()
+    dist.barrier()
+    launches = ctx.launches() - l0
+    prof = ctx.profile_read()
+    ctx.profile(0)
+    ms_max = dist.max(ms)
+    total_uncomp = dist.sum(float(wl["uncomp_bytes"]))
+    value = total_uncomp * args.steps / (ms_max / 1e3) / GB
+
+    # ---- end to end through the C-ABI host-buffer call: pinned host image -> H2D -> kernels -> D2H
+    e2e_steps = args.e2e_steps or max(3, min(args.steps, 10))
+    out_host = ctx.pinned(wl["out_bytes"]) if wl["out_bytes"] else None
+    L = ctx.L
+    import ctypes as C
+    crc_h = np.zeros(n, dtype=np.uint32)
+    st_h = np.zeros(n, dtype=np.int32)
+
+    def e2e_step():
+        ctx.lib.check(L.otz_extract_host(ctx.h, img.ctypes.data_as(C.c_void_p), img.nbytes, tab.ctypes.data_as(C.c_void_p), n,
+                                         C.byref(wl["opts"]), out_host.ctypes.data_as(C.c_void_p) if out_host is not None else None,
+                                         wl["out_bytes"], crc_h.ctypes.data_as(C.c_void_p), st_h.ctypes.data_as(C.c_void_p)),
+                      "otz_extract_host")
+    e2e_step()
+    e2e_step()
+    dist.barrier()
+    ctx.sync()
+    t0 = time.perf_counter()
+    for _ in range(e2e_steps):
+        e2e_step()
+    ctx.sync()
+    e2e_s = time.perf_counter() - t0
+    dist.barrier()
+    assert not np.count_nonzero(st_h) and np.array_equal(crc_h, tab["crc32"])
+    e2e_max = dist.max(e2e_s)
+    e2e_value = total_uncomp * e2e_steps / e2e_max / GB
+    sampler.stop_ev.set()
+    sampler.join(timeout=2)
+
+    if dist.rank == 0:
+        peaks = {}
+        try:
+            peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+        except Exception:
+            pass
+        peak = float(peaks.get("hbm_gbs", 6650.0))
+        peak_src = "measured (MEASURED_PEAKS.json hbm_gbs)" if "hbm_gbs" in peaks else "fallback 6.65 TB/s (B200_PROFILING.md)"
+        idx = {"resolve": 0, "decode": 1, "crc": 2, "finalize": 3}
+        dom = wl["dominant"]
+        k_ms = float(np.mean([p[idx[dom]] for p in prof])) if prof else float("nan")
+        shares = {k: float(np.mean([p[i] for p in prof])) for k, i in idx.items()} if prof else {}
+        achieved = wl["algo_bytes"] / (k_ms / 1e3) / GB
+        traffic = None
+        try:
+            traffic = json.load(open(os.path.join(ROOT, "profiles", "roofline_traffic.json"))).get(args.workload)
+        except Exception:
+            pass
+        line = {
+            "metric": "extract GB/s (uncompressed output, device-timed)", "value": value, "unit": "GB/s",
+            "n_gpus": dist.world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_max / args.steps,
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u8", "data": "synthetic",
+            "config": {"workload": WORKLOADS[args.workload], "detail": wl["desc"], "entries_per_gpu": n,
+                       "uncomp_bytes_per_gpu": wl["uncomp_bytes"], "algorithmic_bytes_per_gpu": wl["algo_bytes"],
+                       "cache": "inputs larger than L2 (no flush needed)" if wl["algo_bytes"] > 256e6 else
+                                "inputs smaller than L2: steady-state L2-resident", "parallelism": "entries sharded by index, no collective"},
+            "roofline": {"bound": "hbm", "kernel": {"crc": "k_crc_chunks", "decode": "k_inflate/k_zstdref/k_store_copy"}[dom],
+                         "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": traffic,
+                         "peak_source": peak_src, "kernel_ms": k_ms, "phase_ms": shares},
+            "e2e": {"value": e2e_value, "unit": "GB/s", "h2d_bytes_per_step": int(img.nbytes + tab.nbytes),
+                    "d2h_bytes_per_step": int(wl["out_bytes"] + 8 * n), "steps": e2e_steps,
+                    "timing": "host wall clock around otz_extract_host (C-ABI, pinned host buffers), device-synchronised, max over ranks"},
+            "gpu_launches": int(launches),
+            "clocks": sampler.summary(),
+        }
+        if dist.world == 1 and not args.no_cpu_baseline:
+            try:
+                line["cpu_baseline"] = cpu_baseline(args.workload)
+            except Exception as e:
+                line["cpu_baseline"] = {"value": None, "unit": "GB/s", "cores": 0, "kind": "reference", "sample": "unavailable: %r" % e}
+        print(json.dumps(line))
+    ctx.plan_destroy(plan)
+    dist.close()
+
+
+if __name__ == "__main__":
+    main()

@@ -96,6 +96,7 @@ int otz_ctx_create(int device, otz_ctx **out);
 void otz_ctx_destroy(otz_ctx *ctx);
 const char *otz_last_error(void);
 int otz_sm_count(otz_ctx *ctx);
+int otz_pci_bus_id(otz_ctx *ctx, char *buf, int len);   /* for NVML clock sampling */
 
 /* ---- device / pinned memory and copies (all on the context's stream) ---- */
 int otz_dev_alloc(otz_ctx *ctx, uint64_t bytes, void **dptr);   /* padded by 64 bytes */
@@ -110,9 +111,12 @@ int otz_sync(otz_ctx *ctx);
 /* ---- device timing on the launching stream (cudaEvent pair) ---- */
 int otz_timer_start(otz_ctx *ctx);
 int otz_timer_stop(otz_ctx *ctx, float *ms);   /* records, synchronises, returns elapsed */
-/* per-kernel event timing of the last otz_extract_run (ms; enable before the run) */
+/* per-phase event timing of otz_extract_run (ms).  otz_profile_enable(ctx,1) resets the run
+ * counter; every later run records 5 events on the stream (no synchronisation); the last 64
+ * runs can be read back by index after the timed region. */
 int otz_profile_enable(otz_ctx *ctx, int on);
-int otz_profile_get(otz_ctx *ctx, float *ms_resolve, float *ms_decode, float *ms_crc, float *ms_finalize);
+int otz_profile_runs(otz_ctx *ctx);
+int otz_profile_get(otz_ctx *ctx, int run, float *ms_resolve, float *ms_decode, float *ms_crc, float *ms_finalize);
 /* kernel launches issued by this context so far */
 uint64_t otz_launch_count(otz_ctx *ctx);
 /* write `bytes` of scratch larger than L2 (flushes L2 between timed iterations) */

@@ -27,13 +27,17 @@ static int fail_cuda(cudaError_t e, const char *what) {
 		}                                 \
 	} while (0)
 
+#define OTZ_PROF_SLOTS 64
 struct otz_ctx {
 	int device;
 	int sm_count;
 	cudaStream_t stream;
 	cudaEvent_t ev0, ev1;
-	cudaEvent_t pev[5];
+	cudaEvent_t pev[OTZ_PROF_SLOTS][5];
 	int profile;
+	uint32_t prof_runs;      // runs recorded since otz_profile_enable(ctx, 1)
+	void *d_arch_cache, *d_out_cache;   // grow-only device buffers behind otz_extract_host
+	uint64_t arch_cache_bytes, out_cache_bytes;
 	OtzCrcTables *d_tabs;
 	uint8_t *d_flush;
 	uint64_t flush_bytes;
@@ -141,8 +145,10 @@ extern "C" int otz_ctx_create(int device, otz_ctx **out) {
 	CK(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
 	CK(cudaEventCreate(&c->ev0));
 	CK(cudaEventCreate(&c->ev1));
-	for (auto &e : c->pev) {
-		CK(cudaEventCreate(&e));
+	for (auto &slot : c->pev) {
+		for (auto &e : slot) {
+			CK(cudaEventCreate(&e));
+		}
 	}
 	OtzCrcTables *h = new OtzCrcTables();
 	build_crc_tables(h);
@@ -166,16 +172,24 @@ extern "C" void otz_ctx_destroy(otz_ctx *c) {
 	cudaStreamSynchronize(c->stream);
 	cudaFree(c->d_tabs);
 	cudaFree(c->d_flush);
+	cudaFree(c->d_arch_cache);
+	cudaFree(c->d_out_cache);
 	cudaEventDestroy(c->ev0);
 	cudaEventDestroy(c->ev1);
-	for (auto &e : c->pev) {
-		cudaEventDestroy(e);
+	for (auto &slot : c->pev) {
+		for (auto &e : slot) {
+			cudaEventDestroy(e);
+		}
 	}
 	cudaStreamDestroy(c->stream);
 	delete c;
 }
 
 extern "C" int otz_sm_count(otz_ctx *c) { return c ? c->sm_count : 0; }
+extern "C" int otz_pci_bus_id(otz_ctx *c, char *buf, int len) {
+	CK(cudaDeviceGetPCIBusId(buf, len, c->device));
+	return OTZ_SUCCESS;
+}
 extern "C" uint64_t otz_launch_count(otz_ctx *c) { return c ? c->launches : 0; }
 
 // ---------------------------------------------------------------- memory
@@ -239,15 +253,21 @@ extern "C" int otz_timer_stop(otz_ctx *c, float *ms) {
 }
 extern "C" int otz_profile_enable(otz_ctx *c, int on) {
 	c->profile = on;
+	c->prof_runs = 0;
 	return OTZ_SUCCESS;
 }
-extern "C" int otz_profile_get(otz_ctx *c, float *r, float *d, float *k, float *f) {
+extern "C" int otz_profile_runs(otz_ctx *c) { return (int)c->prof_runs; }
+extern "C" int otz_profile_get(otz_ctx *c, int run, float *r, float *d, float *k, float *f) {
 	CK(cudaSetDevice(c->device));
-	CK(cudaEventSynchronize(c->pev[4]));
+	if (run < 0 || (uint32_t)run >= c->prof_runs || c->prof_runs - (uint32_t)run > OTZ_PROF_SLOTS) {
+		return OTZ_ERR_ARG;
+	}
+	cudaEvent_t *ev = c->pev[run % OTZ_PROF_SLOTS];
+	CK(cudaEventSynchronize(ev[4]));
 	float *dst[4] = { r, d, k, f };
 	for (int i = 0; i < 4; i++) {
 		if (dst[i]) {
-			CK(cudaEventElapsedTime(dst[i], c->pev[i], c->pev[i + 1]));
+			CK(cudaEventElapsedTime(dst[i], ev[i], ev[i + 1]));
 		}
 	}
 	return OTZ_SUCCESS;
@@ -405,8 +425,9 @@ extern "C" int otz_extract_run(otz_ctx *c, otz_plan *p, const uint8_t *d_archive
 	CK(cudaSetDevice(c->device));
 	cudaStream_t s = c->stream;
 	const uint32_t n = p->n;
+	cudaEvent_t *pev = c->pev[c->prof_runs % OTZ_PROF_SLOTS];
 	if (c->profile) {
-		CK(cudaEventRecord(c->pev[0], s));
+		CK(cudaEventRecord(pev[0], s));
 	}
 	if (n) {
 		CK(cudaMemsetAsync(p->d_counter, 0, 64, s));
@@ -414,7 +435,7 @@ extern "C" int otz_extract_run(otz_ctx *c, otz_plan *p, const uint8_t *d_archive
 		c->launches++;
 	}
 	if (c->profile) {
-		CK(cudaEventRecord(c->pev[1], s));
+		CK(cudaEventRecord(pev[1], s));
 	}
 	const uint32_t persistent = (uint32_t)c->sm_count * 8;  // 8 CTAs x 8 warps = 64 warps per SM
 	if (p->n_store_chunks && !p->opts.verify_only) {
@@ -440,7 +461,7 @@ extern "C" int otz_extract_run(otz_ctx *c, otz_plan *p, const uint8_t *d_archive
 		}
 	}
 	if (c->profile) {
-		CK(cudaEventRecord(c->pev[2], s));
+		CK(cudaEventRecord(pev[2], s));
 	}
 	if (p->n_chunks) {
 		// 4 CTAs x 256 threads per SM (16 KiB of tables each)
@@ -450,14 +471,15 @@ extern "C" int otz_extract_run(otz_ctx *c, otz_plan *p, const uint8_t *d_archive
 		c->launches++;
 	}
 	if (c->profile) {
-		CK(cudaEventRecord(c->pev[3], s));
+		CK(cudaEventRecord(pev[3], s));
 	}
 	if (n) {
 		k_crc_finalize<<<(n + 255) / 256, 256, 0, s>>>(p->d_ents, n, p->d_acc, p->d_crc, p->d_status, c->d_tabs);
 		c->launches++;
 	}
 	if (c->profile) {
-		CK(cudaEventRecord(c->pev[4], s));
+		CK(cudaEventRecord(pev[4], s));
+		c->prof_runs++;
 	}
 	CK(cudaGetLastError());
 	return OTZ_SUCCESS;
@@ -488,18 +510,33 @@ extern "C" int otz_extract_host(otz_ctx *c, const uint8_t *archive, uint64_t arc
 	if (rc) {
 		return rc;
 	}
-	void *d_arch = nullptr, *d_out = nullptr;
 	do {
-		if ((rc = otz_dev_alloc(c, archive_len, &d_arch))) break;
-		if (out_len && (rc = otz_dev_alloc(c, out_len, &d_out))) break;
-		if ((rc = otz_h2d(c, d_arch, archive, archive_len))) break;
-		if ((rc = otz_extract_run(c, p, (const uint8_t *)d_arch, archive_len, (uint8_t *)d_out, out_len))) break;
-		if (out && p->out_bytes_needed && (rc = otz_d2h(c, out, d_out, p->out_bytes_needed))) break;
+		// device staging buffers are kept (grow-only) so repeated calls pay only for the copies
+		if (archive_len > c->arch_cache_bytes || !c->d_arch_cache) {
+			cudaFree(c->d_arch_cache);
+			c->d_arch_cache = nullptr;
+			c->arch_cache_bytes = 0;
+			if ((rc = otz_dev_alloc(c, archive_len, &c->d_arch_cache))) break;
+			c->arch_cache_bytes = archive_len;
+		}
+		const uint64_t need = p->out_bytes_needed;
+		if (need > out_len) {
+			rc = OTZ_ERR_ARG;
+			break;
+		}
+		if (need > c->out_cache_bytes) {
+			cudaFree(c->d_out_cache);
+			c->d_out_cache = nullptr;
+			c->out_cache_bytes = 0;
+			if ((rc = otz_dev_alloc(c, need, &c->d_out_cache))) break;
+			c->out_cache_bytes = need;
+		}
+		if ((rc = otz_h2d(c, c->d_arch_cache, archive, archive_len))) break;
+		if ((rc = otz_extract_run(c, p, (const uint8_t *)c->d_arch_cache, archive_len, (uint8_t *)c->d_out_cache, need))) break;
+		if (out && need && (rc = otz_d2h(c, out, c->d_out_cache, need))) break;
 		rc = otz_extract_results(c, p, crc, status);
 	} while (0);
 	cudaStreamSynchronize(c->stream);
-	if (d_arch) cudaFree(d_arch);
-	if (d_out) cudaFree(d_out);
 	otz_plan_destroy(c, p);
 	return rc;
 }

@@ -53,6 +53,7 @@ class Lib:
         L.otz_ctx_destroy.argtypes = [vp]
         L.otz_ctx_destroy.restype = None
         L.otz_sm_count.argtypes = [vp]
+        L.otz_pci_bus_id.argtypes = [vp, C.c_char_p, C.c_int]
         L.otz_launch_count.argtypes = [vp]
         L.otz_launch_count.restype = u64
         L.otz_dev_alloc.argtypes = [vp, u64, C.POINTER(vp)]
@@ -66,7 +67,8 @@ class Lib:
         L.otz_timer_start.argtypes = [vp]
         L.otz_timer_stop.argtypes = [vp, C.POINTER(C.c_float)]
         L.otz_profile_enable.argtypes = [vp, C.c_int]
-        L.otz_profile_get.argtypes = [vp] + [C.POINTER(C.c_float)] * 4
+        L.otz_profile_get.argtypes = [vp, C.c_int] + [C.POINTER(C.c_float)] * 4
+        L.otz_profile_runs.argtypes = [vp]
         L.otz_flush_l2.argtypes = [vp]
         L.otz_plan_create.argtypes = [vp, vp, C.c_uint32, C.POINTER(OtzOpts), C.POINTER(vp)]
         L.otz_plan_destroy.argtypes = [vp, vp]
@@ -173,6 +175,27 @@ class Ctx:
 
     def flush_l2(self):
         self.lib.check(self.L.otz_flush_l2(self.h), "flush_l2")
+
+    def profile(self, on: int):
+        self.L.otz_profile_enable(self.h, on)
+
+    def profile_read(self):
+        """-> list of (ms_resolve, ms_decode, ms_crc, ms_finalize) for the runs since profile(1)"""
+        out = []
+        n = self.L.otz_profile_runs(self.h)
+        for i in range(max(0, n - 64), n):
+            f = [C.c_float() for _ in range(4)]
+            self.lib.check(self.L.otz_profile_get(self.h, i, *[C.byref(x) for x in f]), "otz_profile_get")
+            out.append(tuple(x.value for x in f))
+        return out
+
+    def pci_bus_id(self) -> str:
+        b = C.create_string_buffer(64)
+        self.lib.check(self.L.otz_pci_bus_id(self.h, b, 64), "otz_pci_bus_id")
+        return b.value.decode()
+
+    def sm_count(self) -> int:
+        return int(self.L.otz_sm_count(self.h))
 
     def launches(self) -> int:
         return int(self.L.otz_launch_count(self.h))
