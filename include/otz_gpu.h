@@ -138,6 +138,30 @@ int otz_extract_results(otz_ctx *ctx, otz_plan *plan, uint32_t *crc, int32_t *st
 int otz_extract_host(otz_ctx *ctx, const uint8_t *archive, uint64_t archive_len, const otz_entry *entries,
 	uint32_t n, const otz_extract_opts *opts, uint8_t *out, uint64_t out_len, uint32_t *crc, int32_t *status);
 
+/* ---- write path ----
+ * Batched otezip_compress_data (otezip.c:788-852) + CRC (otezip.c:1124) for n sources laid out in one
+ * input buffer: source i = in[in_ofs[i] .. in_ofs[i]+in_len[i]), requested method[i] in {0, 8}.
+ * Per source: zero length -> STORE; DEFLATE whose stream is not smaller than the input -> STORE
+ * (otezip.c:793-801, :846-850).  Results: method_out[i], out_size[i], out_ofs[i] (offset in the dense
+ * output arena), crc[i] = CRC-32 of the uncompressed bytes. */
+typedef struct otz_deflate_job otz_deflate_job;
+int otz_deflate_plan(otz_ctx *ctx, const uint64_t *in_ofs, const uint32_t *in_len, const uint16_t *method, uint32_t n,
+	otz_deflate_job **out);
+void otz_deflate_destroy(otz_ctx *ctx, otz_deflate_job *job);
+/* Launch CRC + compress + compaction on a device-resident input (asynchronous). */
+int otz_deflate_run(otz_ctx *ctx, otz_deflate_job *job, const uint8_t *d_in, uint64_t in_bytes);
+/* Per-source results (synchronises; any pointer may be NULL). *total = bytes in the dense arena. */
+int otz_deflate_results(otz_ctx *ctx, otz_deflate_job *job, uint64_t *out_ofs, uint32_t *out_size, uint32_t *crc,
+	uint16_t *method_out, uint64_t *total);
+/* Device pointer of the dense output arena (valid until the job is destroyed). */
+const uint8_t *otz_deflate_device_output(otz_deflate_job *job);
+/* Copy the dense arena (first `bytes` bytes) to the host (synchronises). */
+int otz_deflate_fetch(otz_ctx *ctx, otz_deflate_job *job, uint8_t *out, uint64_t bytes);
+/* Host-buffer convenience: H2D input, run, D2H results + arena.  out_cap >= sum(in_len) always suffices. */
+int otz_deflate_host(otz_ctx *ctx, const uint8_t *in, uint64_t in_bytes, const uint64_t *in_ofs, const uint32_t *in_len,
+	const uint16_t *method, uint32_t n, uint8_t *out, uint64_t out_cap, uint64_t *out_ofs, uint32_t *out_size,
+	uint32_t *crc, uint16_t *method_out, uint64_t *total);
+
 /* Policy helper shared by the host library and the tests: does a status word
  * mean "zip_fopen_index returns the buffer" under the given globals?
  * ref_compat != 0 reproduces the reference's end-of-block rule (F1). */

@@ -10,6 +10,7 @@
 #include "k_copy.cuh"
 #include "k_crc32.cuh"
 #include "k_inflate.cuh"
+#include "k_deflate.cuh"
 #include "k_resolve.cuh"
 #include "otz_common.cuh"
 
@@ -552,4 +553,237 @@ extern "C" int otz_status_accepts(int32_t st, int verify_crc, int ref_compat) {
 		return 0;  // otezip.c:670-673
 	}
 	return 1;
+}
+
+// ---------------------------------------------------------------- write path
+struct otz_deflate_job {
+	uint32_t n, n_chunks, n_crc_chunks, n_slots;
+	uint64_t in_total;
+	OtzDflEntry *d_ents;
+	OtzDflChunk *d_chunks;
+	otz_entry *d_crc_ents;       // the sources described as entries of an "arena" = the input buffer
+	OtzCrcChunk *d_crc_chunks;
+	OtzEntryState *d_est;
+	int32_t *d_status;
+	uint32_t *d_acc, *d_crc;
+	uint32_t *d_tokens;
+	uint8_t *d_cout;
+	uint32_t *d_csize;
+	uint32_t *d_out_size;
+	uint16_t *d_method_out;
+	uint64_t *d_out_ofs, *d_total;
+	uint8_t *d_dense;
+	uint32_t *d_counter;
+	int grid;
+};
+
+extern "C" void otz_deflate_destroy(otz_ctx *c, otz_deflate_job *j) {
+	if (!j) {
+		return;
+	}
+	if (c) {
+		cudaSetDevice(c->device);
+		cudaStreamSynchronize(c->stream);
+	}
+	void *ptrs[] = { j->d_ents, j->d_chunks, j->d_crc_ents, j->d_crc_chunks, j->d_est, j->d_status, j->d_acc, j->d_crc, j->d_tokens,
+		j->d_cout, j->d_csize, j->d_out_size, j->d_method_out, j->d_out_ofs, j->d_total, j->d_dense, j->d_counter };
+	for (void *p : ptrs) {
+		cudaFree(p);
+	}
+	delete j;
+}
+
+extern "C" int otz_deflate_plan(otz_ctx *c, const uint64_t *in_ofs, const uint32_t *in_len, const uint16_t *method, uint32_t n,
+	otz_deflate_job **out) {
+	if (!c || !out || (n && (!in_ofs || !in_len || !method))) {
+		return OTZ_ERR_ARG;
+	}
+	*out = nullptr;
+	CK(cudaSetDevice(c->device));
+	otz_deflate_job *j = new (std::nothrow) otz_deflate_job();
+	if (!j) {
+		return OTZ_ERR_NOMEM;
+	}
+	memset(j, 0, sizeof(*j));
+	j->n = n;
+	std::vector<OtzDflEntry> ents(n);
+	std::vector<OtzDflChunk> chunks;
+	std::vector<otz_entry> cents(n);
+	std::vector<OtzCrcChunk> cchunks;
+	uint64_t total = 0;
+	for (uint32_t i = 0; i < n; i++) {
+		if (method[i] != OTZ_M_STORE && method[i] != OTZ_M_DEFLATE) {
+			delete j;
+			snprintf(g_err, sizeof(g_err), "otz_deflate_plan: method %u is not on the GPU write path", method[i]);
+			return OTZ_ERR_ARG;
+		}
+		OtzDflEntry &e = ents[i];
+		e.in_ofs = in_ofs[i];
+		e.len = in_len[i];
+		e.method_in = method[i];
+		e.pad = 0;
+		e.first_chunk = (uint32_t)chunks.size();
+		const uint32_t nc = (in_len[i] + DFL_CHUNK - 1) / DFL_CHUNK;
+		e.n_chunks = nc;
+		for (uint32_t k = 0; k < nc; k++) {
+			OtzDflChunk ck;
+			ck.in_ofs = in_ofs[i] + (uint64_t)k * DFL_CHUNK;
+			ck.len = std::min<uint32_t>(DFL_CHUNK, in_len[i] - k * DFL_CHUNK);
+			ck.entry = i;
+			ck.last = (k + 1 == nc);
+			ck.pad = 0;
+			chunks.push_back(ck);
+		}
+		otz_entry &ce = cents[i];
+		memset(&ce, 0, sizeof(ce));
+		ce.out_ofs = in_ofs[i];
+		ce.comp_size = ce.uncomp_size = in_len[i];
+		ce.method = OTZ_M_DEFLATE;
+		const uint32_t ncc = (uint32_t)(((uint64_t)in_len[i] + OTZ_CRC_CHUNK - 1) / OTZ_CRC_CHUNK);
+		for (uint32_t k = 0; k < ncc; k++) {
+			cchunks.push_back(OtzCrcChunk{ i, k });
+		}
+		total += in_len[i];
+	}
+	j->n_chunks = (uint32_t)chunks.size();
+	j->n_crc_chunks = (uint32_t)cchunks.size();
+	j->in_total = total;
+	// persistent grid for the compressor: 2 CTAs x 8 warps per SM
+	j->grid = std::max(1, std::min<int>(c->sm_count * 2, (int)((j->n_chunks + 7) / 8)));
+	j->n_slots = (uint32_t)j->grid * 8u;
+	int rc;
+	if ((rc = upload(&j->d_ents, ents, c->stream)) || (rc = upload(&j->d_chunks, chunks, c->stream)) ||
+		(rc = upload(&j->d_crc_ents, cents, c->stream)) || (rc = upload(&j->d_crc_chunks, cchunks, c->stream))) {
+		otz_deflate_destroy(c, j);
+		return rc;
+	}
+	const size_t n1 = std::max<uint32_t>(n, 1), nc1 = std::max<uint32_t>(j->n_chunks, 1);
+	bool ok = cudaMalloc(&j->d_est, n1 * sizeof(OtzEntryState)) == cudaSuccess && cudaMalloc(&j->d_status, n1 * 4) == cudaSuccess &&
+		cudaMalloc(&j->d_acc, n1 * 4) == cudaSuccess && cudaMalloc(&j->d_crc, n1 * 4) == cudaSuccess &&
+		cudaMalloc(&j->d_tokens, (size_t)j->n_slots * DFL_CHUNK * 4) == cudaSuccess &&
+		cudaMalloc(&j->d_cout, nc1 * (size_t)DFL_OUT_STRIDE) == cudaSuccess && cudaMalloc(&j->d_csize, nc1 * 4) == cudaSuccess &&
+		cudaMalloc(&j->d_out_size, n1 * 4) == cudaSuccess && cudaMalloc(&j->d_method_out, n1 * 2) == cudaSuccess &&
+		cudaMalloc(&j->d_out_ofs, n1 * 8) == cudaSuccess && cudaMalloc(&j->d_total, 8) == cudaSuccess &&
+		cudaMalloc(&j->d_dense, total + 64) == cudaSuccess && cudaMalloc(&j->d_counter, 64) == cudaSuccess;
+	if (!ok) {
+		int r = fail_cuda(cudaGetLastError(), "cudaMalloc(deflate job)");
+		otz_deflate_destroy(c, j);
+		return r;
+	}
+	CK(cudaMemsetAsync(j->d_status, 0, n1 * 4, c->stream));
+	CK(cudaMemsetAsync(j->d_est, 0, n1 * sizeof(OtzEntryState), c->stream));
+	CK(cudaStreamSynchronize(c->stream));
+	*out = j;
+	return OTZ_SUCCESS;
+}
+
+extern "C" int otz_deflate_run(otz_ctx *c, otz_deflate_job *j, const uint8_t *d_in, uint64_t in_bytes) {
+	if (!c || !j) {
+		return OTZ_ERR_ARG;
+	}
+	(void)in_bytes;
+	CK(cudaSetDevice(c->device));
+	cudaStream_t s = c->stream;
+	const uint32_t n = j->n;
+	if (!n) {
+		CK(cudaMemsetAsync(j->d_total, 0, 8, s));
+		return OTZ_SUCCESS;
+	}
+	CK(cudaMemsetAsync(j->d_counter, 0, 64, s));
+	CK(cudaMemsetAsync(j->d_acc, 0, (size_t)n * 4, s));
+	if (j->n_crc_chunks) {
+		const uint32_t grid = std::min((uint32_t)c->sm_count * 4, (j->n_crc_chunks + 7) / 8);
+		k_crc_chunks<<<grid, 256, 0, s>>>(nullptr, d_in, j->d_crc_ents, j->d_est, j->d_status, j->d_crc_chunks, j->n_crc_chunks, j->d_acc,
+			c->d_tabs, 0);
+		c->launches++;
+	}
+	k_crc_finalize<<<(n + 255) / 256, 256, 0, s>>>(j->d_crc_ents, n, j->d_acc, j->d_crc, j->d_status, c->d_tabs);
+	c->launches++;
+	if (j->n_chunks) {
+		const size_t smem = 8 * sizeof(DeflateSmem);
+		static bool attr_done = false;
+		if (!attr_done) {
+			CK(cudaFuncSetAttribute(k_deflate_chunks, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+			attr_done = true;
+		}
+		k_deflate_chunks<<<j->grid, 256, smem, s>>>(d_in, j->d_chunks, j->n_chunks, j->d_tokens, j->d_cout, j->d_csize, j->d_counter,
+			j->n_slots);
+		c->launches++;
+	}
+	k_deflate_entry_sizes<<<(n + 255) / 256, 256, 0, s>>>(j->d_ents, n, j->d_csize, j->d_out_size, j->d_method_out);
+	k_deflate_scan<<<1, 1024, 0, s>>>(j->d_out_size, n, j->d_out_ofs, j->d_total);
+	c->launches += 2;
+	if (j->n_chunks) {
+		const uint32_t grid = std::min((uint32_t)c->sm_count * 8, (j->n_chunks + 7) / 8);
+		k_deflate_gather<<<grid, 256, 0, s>>>(d_in, j->d_cout, j->d_chunks, j->n_chunks, j->d_ents, j->d_csize, j->d_method_out, j->d_out_ofs,
+			j->d_dense);
+		c->launches++;
+	}
+	CK(cudaGetLastError());
+	return OTZ_SUCCESS;
+}
+
+extern "C" int otz_deflate_results(otz_ctx *c, otz_deflate_job *j, uint64_t *out_ofs, uint32_t *out_size, uint32_t *crc, uint16_t *method_out,
+	uint64_t *total) {
+	if (!c || !j) {
+		return OTZ_ERR_ARG;
+	}
+	CK(cudaSetDevice(c->device));
+	cudaStream_t s = c->stream;
+	const size_t n = j->n;
+	if (n && out_ofs) CK(cudaMemcpyAsync(out_ofs, j->d_out_ofs, n * 8, cudaMemcpyDeviceToHost, s));
+	if (n && out_size) CK(cudaMemcpyAsync(out_size, j->d_out_size, n * 4, cudaMemcpyDeviceToHost, s));
+	if (n && crc) CK(cudaMemcpyAsync(crc, j->d_crc, n * 4, cudaMemcpyDeviceToHost, s));
+	if (n && method_out) CK(cudaMemcpyAsync(method_out, j->d_method_out, n * 2, cudaMemcpyDeviceToHost, s));
+	if (total) CK(cudaMemcpyAsync(total, j->d_total, 8, cudaMemcpyDeviceToHost, s));
+	CK(cudaStreamSynchronize(s));
+	return OTZ_SUCCESS;
+}
+
+extern "C" const uint8_t *otz_deflate_device_output(otz_deflate_job *j) { return j ? j->d_dense : nullptr; }
+
+extern "C" int otz_deflate_fetch(otz_ctx *c, otz_deflate_job *j, uint8_t *out, uint64_t bytes) {
+	if (!c || !j || (bytes && !out) || bytes > j->in_total) {
+		return OTZ_ERR_ARG;
+	}
+	CK(cudaSetDevice(c->device));
+	if (bytes) {
+		CK(cudaMemcpyAsync(out, j->d_dense, bytes, cudaMemcpyDeviceToHost, c->stream));
+	}
+	CK(cudaStreamSynchronize(c->stream));
+	return OTZ_SUCCESS;
+}
+
+extern "C" int otz_deflate_host(otz_ctx *c, const uint8_t *in, uint64_t in_bytes, const uint64_t *in_ofs, const uint32_t *in_len,
+	const uint16_t *method, uint32_t n, uint8_t *out, uint64_t out_cap, uint64_t *out_ofs, uint32_t *out_size, uint32_t *crc,
+	uint16_t *method_out, uint64_t *total) {
+	otz_deflate_job *j = nullptr;
+	int rc = otz_deflate_plan(c, in_ofs, in_len, method, n, &j);
+	if (rc) {
+		return rc;
+	}
+	void *d_in = nullptr;
+	uint64_t tot = 0;
+	do {
+		if ((rc = otz_dev_alloc(c, in_bytes, &d_in))) break;
+		if (in_bytes && (rc = otz_h2d(c, d_in, in, in_bytes))) break;
+		if ((rc = otz_deflate_run(c, j, (const uint8_t *)d_in, in_bytes))) break;
+		if ((rc = otz_deflate_results(c, j, out_ofs, out_size, crc, method_out, &tot))) break;
+		if (tot > out_cap) {
+			snprintf(g_err, sizeof(g_err), "otz_deflate_host: output needs %llu bytes, capacity %llu", (unsigned long long)tot,
+				(unsigned long long)out_cap);
+			rc = OTZ_ERR_ARG;
+			break;
+		}
+		rc = otz_deflate_fetch(c, j, out, tot);
+	} while (0);
+	if (total) {
+		*total = tot;
+	}
+	cudaStreamSynchronize(c->stream);
+	if (d_in) {
+		cudaFree(d_in);
+	}
+	otz_deflate_destroy(c, j);
+	return rc;
 }

@@ -77,6 +77,15 @@ class Lib:
         L.otz_extract_results.argtypes = [vp, vp, vp, vp]
         L.otz_extract_host.argtypes = [vp, vp, u64, vp, C.c_uint32, C.POINTER(OtzOpts), vp, u64, vp, vp]
         L.otz_status_accepts.argtypes = [C.c_int32, C.c_int, C.c_int]
+        L.otz_deflate_plan.argtypes = [vp, vp, vp, vp, C.c_uint32, C.POINTER(vp)]
+        L.otz_deflate_destroy.argtypes = [vp, vp]
+        L.otz_deflate_destroy.restype = None
+        L.otz_deflate_run.argtypes = [vp, vp, vp, u64]
+        L.otz_deflate_results.argtypes = [vp, vp, vp, vp, vp, vp, C.POINTER(u64)]
+        L.otz_deflate_device_output.argtypes = [vp]
+        L.otz_deflate_device_output.restype = vp
+        L.otz_deflate_fetch.argtypes = [vp, vp, vp, u64]
+        L.otz_deflate_host.argtypes = [vp, vp, u64, vp, vp, vp, C.c_uint32, vp, u64, vp, vp, vp, vp, C.POINTER(u64)]
 
     @classmethod
     def get(cls) -> "Lib":
@@ -237,3 +246,30 @@ class Ctx:
                                                crc.ctypes.data_as(C.c_void_p), st.ctypes.data_as(C.c_void_p)),
                        "otz_extract_host")
         return out[:out_len], crc[:n], st[:n]
+
+    # -- write path
+    def deflate_host(self, sources: list, methods: list | None = None):
+        """Batched otezip_compress_data + CRC through the C-ABI host-buffer call.
+        -> list of (method_out, payload bytes, crc32)"""
+        n = len(sources)
+        methods = methods or [8] * n
+        lens = np.array([len(s) for s in sources], dtype=np.uint32)
+        ofs = np.zeros(n, dtype=np.uint64)
+        pos = 0
+        for i in range(n):
+            ofs[i] = pos
+            pos += (int(lens[i]) + 15) & ~15
+        buf = np.zeros(max(pos, 1), dtype=np.uint8)
+        for i, s in enumerate(sources):
+            buf[int(ofs[i]):int(ofs[i]) + len(s)] = np.frombuffer(s, dtype=np.uint8)
+        meth = np.array(methods, dtype=np.uint16)
+        out = np.zeros(max(int(lens.astype(np.int64).sum()), 1), dtype=np.uint8)
+        o_ofs = np.zeros(max(n, 1), dtype=np.uint64)
+        o_sz = np.zeros(max(n, 1), dtype=np.uint32)
+        crc = np.zeros(max(n, 1), dtype=np.uint32)
+        m_out = np.zeros(max(n, 1), dtype=np.uint16)
+        tot = C.c_uint64()
+        vp = lambda a: a.ctypes.data_as(C.c_void_p)
+        self.lib.check(self.L.otz_deflate_host(self.h, vp(buf), pos, vp(ofs), vp(lens), vp(meth), n, vp(out), out.nbytes,
+                                               vp(o_ofs), vp(o_sz), vp(crc), vp(m_out), C.byref(tot)), "otz_deflate_host")
+        return [(int(m_out[i]), bytes(out[int(o_ofs[i]):int(o_ofs[i]) + int(o_sz[i])]), int(crc[i])) for i in range(n)]
