@@ -20,7 +20,7 @@ $(CSRC)/host/%.o: $(CSRC)/host/%.c $(wildcard include/otezip/*.h) include/otz_gp
 $(LIB): $(CSRC)/otz_shim.o $(HOST_O)
 	$(NVCC) $(ARCH) -shared -o $@ $^ -lcudart_static -lpthread -ldl -lrt
 
-oracle:
+oracle: $(LIB)
 	$(MAKE) -C oracle
 
 clean:

@@ -1,0 +1,1038 @@
+/* otezip.c — plain-C99 host side of the B200 build: the libzip-subset API of include/otezip/zip.h
+ * over the batched GPU codec behind include/otz_gpu.h.
+ *
+ * Mirrors the reference's container layer and API (paths relative to /root/reference):
+ *   EOCD search + central-directory walk     src/lib/otezip.c:199-396   (same accept/reject rules; the
+ *                                             walk now also emits the device entry table)
+ *   zip_open / zip_close / accessors         src/lib/otezip.c:693-785, :1273-1404
+ *   zip_fopen_index / zip_fclose / zip_fread src/lib/otezip.c:1315-1357 (+ otezip_extract_entry :399-684)
+ *   zip_file_add / zip_set_file_compression  src/lib/otezip.c:1079-1237
+ *   LFH / CDH / EOCD writers                 src/lib/otezip.c:1443-1590 (exact field values)
+ *   DOS time                                 src/lib/time.inc.c:29-70
+ * There is no codec in this file and no CPU fallback: every decode, encode and CRC goes through
+ * otz_extract_host() / otz_deflate_host().  Without a CUDA device zip_fopen_index() returns NULL and
+ * zip_close() of a written archive returns -1, each with a message on stderr.
+ */
+#include <errno.h>
+#include <fcntl.h>
+#include <sys/stat.h>
+#include <unistd.h>
+
+#include "otezip/zip.h"
+#include "otz_gpu.h"
+
+#define SIG_LFH 0x04034b50u
+#define SIG_CDH 0x02014b50u
+#define SIG_EOCD 0x06054b50u
+#define MAX_FIELD_LEN 65535u                            /* otezip.c:101 */
+#define MAX_PAYLOAD (2ULL * 1024 * 1024 * 1024)         /* otezip.c:102 */
+#define ERR_READ (-1)                                   /* otezip.c:191 */
+#define ERR_INCONS (-2)                                 /* otezip.c:192 */
+
+/* otezip.c:157-166 */
+int otezip_verify_crc = 0;
+uint64_t otezip_max_expansion_ratio = 1000ULL;
+uint64_t otezip_max_expansion_slack = 1024ULL * 1024ULL;
+int otezip_ignore_zipbomb = 0;
+int otezip_ref_compat = 1;
+
+/* ---- private archive state; `pub` must stay first: zip_t* == struct otz_archive* ---- */
+struct otz_window {               /* one decoded batch of consecutive entries */
+	struct otz_window *next;
+	zip_uint64_t first, last;     /* entries [first, last) */
+	uint8_t *arena;               /* pinned host memory holding the decoded bytes */
+	uint64_t arena_len;
+	uint64_t *ofs;                /* per entry offset into arena */
+	int32_t *status;
+	uint32_t *crc;
+	uint32_t refs;                /* zip_file_t handles pointing into arena */
+	int current;
+};
+
+struct otz_pending {              /* a queued source (write path) */
+	void *buf;
+	uint64_t len;
+	int owned;                    /* free(buf) after the archive is written */
+};
+
+struct otz_archive {
+	struct zip pub;
+	uint32_t magic;
+	char *path;
+	/* read side */
+	uint8_t *image;               /* pinned copy of the archive file (filled on first extract) */
+	uint64_t image_len;
+	struct otz_window *windows;
+	int32_t *last_status;
+	/* write side */
+	struct otz_pending *pend;     /* parallel to pub.entries for entries added in this session */
+	zip_uint64_t n_existing;      /* entries loaded from an existing archive (append mode) */
+	uint64_t append_ofs;          /* where new data starts in append mode */
+};
+#define OTZ_MAGIC 0x5a32424fu
+
+struct otz_file {                 /* zip_file_t plus the window it borrows from */
+	struct zip_file pub;
+	struct otz_window *win;
+	uint8_t *own;                 /* malloc'd data (zero-length entries) */
+};
+
+static otz_ctx *g_ctx;
+static int g_ctx_failed;
+
+static otz_ctx *gpu(void) {
+	if (!g_ctx && !g_ctx_failed) {
+		int dev = 0;
+		const char *e = getenv ("OTEZIP_DEVICE");
+		if (e) {
+			dev = atoi (e);
+		}
+		if (otz_ctx_create (dev, &g_ctx) != OTZ_SUCCESS) {
+			fprintf (stderr, "otezip-b200: no usable CUDA device (%s); this build has no CPU codec\n", otz_last_error ());
+			g_ctx_failed = 1;
+			g_ctx = NULL;
+		}
+	}
+	return g_ctx;
+}
+
+static struct otz_archive *priv(zip_t *za) {
+	struct otz_archive *a = (struct otz_archive *)za;
+	return (a && a->magic == OTZ_MAGIC) ? a : NULL;
+}
+
+static int is_valid(const zip_t *za) {
+	return za != NULL && za->fp != NULL; /* otezip.c:687-689 */
+}
+
+/* ---- method names, otezip.c:112-154 (only what this build implements) ---- */
+int otezip_method_from_string(const char *s) {
+	if (!s) {
+		return -1;
+	}
+	if (!strcmp (s, "store")) {
+		return OTEZIP_METHOD_STORE;
+	}
+	if (!strcmp (s, "deflate")) {
+		return OTEZIP_METHOD_DEFLATE;
+	}
+	if (!strcmp (s, "zstd")) {
+		return OTEZIP_METHOD_ZSTD;
+	}
+	return -1;
+}
+
+/* ---- DOS time, time.inc.c:29-70 ---- */
+static int clampi(int v, int lo, int hi) {
+	return v < lo ? lo : v > hi ? hi : v;
+}
+static void dos_now(uint16_t *t, uint16_t *d) {
+	time_t now = time (NULL);
+	struct tm tmv;
+	if (now == (time_t)-1 || !localtime_r (&now, &tmv)) {
+		*t = 0;
+		*d = (uint16_t)((1 << 5) | 1);
+		return;
+	}
+	*t = (uint16_t)((clampi (tmv.tm_hour, 0, 23) << 11) | (clampi (tmv.tm_min, 0, 59) << 5) | clampi (tmv.tm_sec / 2, 0, 29));
+	*d = (uint16_t)((clampi (tmv.tm_year + 1900 - 1980, 0, 127) << 9) | (clampi (tmv.tm_mon + 1, 1, 12) << 5) |
+		clampi (tmv.tm_mday, 1, 31));
+}
+
+/* ---------------------------------------------------------------- central directory */
+
+static int read_at(FILE *fp, long ofs, void *dst, size_t n) {
+	if (fseek (fp, ofs, SEEK_SET) != 0) {
+		return -1;
+	}
+	return fread (dst, 1, n, fp) == n ? 0 : -1;
+}
+
+/* otezip.c:199-272: newest EOCD whose directory range lies in the file and starts with a CDH */
+static int find_eocd(FILE *fp, long file_size, uint32_t *cd_size, uint32_t *cd_ofs, uint16_t *n_entries) {
+	if (file_size < 22) {
+		return ERR_INCONS;
+	}
+	size_t span = file_size < 0x10000 + 22 ? (size_t)file_size : (size_t)(0x10000 + 22);
+	uint8_t *tail = (uint8_t *)malloc (span);
+	if (!tail) {
+		return ERR_READ;
+	}
+	if (read_at (fp, file_size - (long)span, tail, span) != 0) {
+		free (tail);
+		return ERR_READ;
+	}
+	int rc = ERR_INCONS;
+	for (size_t i = span - 22 + 1; i-- > 0;) {
+		if (otezip_read_le32 (tail + i) != SIG_EOCD) {
+			continue;
+		}
+		uint16_t ents = otezip_read_le16 (tail + i + 10);
+		uint32_t sz = otezip_read_le32 (tail + i + 12), ofs = otezip_read_le32 (tail + i + 16);
+		if (ofs > (uint32_t)file_size || (uint64_t)ofs + sz > (uint64_t)file_size) {
+			continue;
+		}
+		if (ents > 0 && sz >= 4) {
+			uint8_t sig[4];
+			if (read_at (fp, (long)ofs, sig, 4) != 0 || otezip_read_le32 (sig) != SIG_CDH) {
+				continue;
+			}
+		}
+		*n_entries = ents;
+		*cd_size = sz;
+		*cd_ofs = ofs;
+		rc = 0;
+		break;
+	}
+	free (tail);
+	return rc;
+}
+
+/* otezip.c:275-396 */
+static int load_central(struct otz_archive *a) {
+	zip_t *za = &a->pub;
+	if (fseek (za->fp, 0, SEEK_END) != 0) {
+		return ERR_READ;
+	}
+	long fsz = ftell (za->fp);
+	if (fsz < 0) {
+		return ERR_READ;
+	}
+	uint32_t cd_size = 0, cd_ofs = 0;
+	uint16_t n = 0;
+	int rc = find_eocd (za->fp, fsz, &cd_size, &cd_ofs, &n);
+	if (rc != 0) {
+		return rc;
+	}
+	if ((uint64_t)cd_ofs + cd_size > (uint64_t)fsz) {
+		return ERR_INCONS;
+	}
+	a->append_ofs = cd_ofs;
+	if (n == 0) {
+		return cd_size != 0 ? ERR_INCONS : 0;
+	}
+	if ((uint64_t)cd_size > MAX_PAYLOAD) {
+		return ERR_INCONS;
+	}
+	uint8_t *cd = (uint8_t *)malloc (cd_size);
+	if (!cd) {
+		return ERR_READ;
+	}
+	if (read_at (za->fp, (long)cd_ofs, cd, cd_size) != 0) {
+		free (cd);
+		return ERR_READ;
+	}
+	if ((size_t)n * 46 > cd_size) {
+		free (cd);
+		return ERR_INCONS;
+	}
+	za->entries = (struct otezip_entry *)calloc (n, sizeof (struct otezip_entry));
+	if (!za->entries) {
+		free (cd);
+		return ERR_READ;
+	}
+	za->n_entries = n;
+	size_t off = 0;
+	for (uint32_t i = 0; i < n; i++) {
+		if (off + 46 > cd_size || otezip_read_le32 (cd + off) != SIG_CDH) {
+			free (cd);
+			return ERR_INCONS;
+		}
+		const uint8_t *h = cd + off;
+		size_t fl = otezip_read_le16 (h + 28), xl = otezip_read_le16 (h + 30), cl = otezip_read_le16 (h + 32);
+		if (46 + fl + xl + cl > cd_size - off) {
+			free (cd);
+			return ERR_INCONS;
+		}
+		struct otezip_entry *e = &za->entries[i];
+		e->method = otezip_read_le16 (h + 10);
+		e->file_time = otezip_read_le16 (h + 12);
+		e->file_date = otezip_read_le16 (h + 14);
+		e->crc32 = otezip_read_le32 (h + 16);
+		e->comp_size = otezip_read_le32 (h + 20);
+		e->uncomp_size = otezip_read_le32 (h + 24);
+		e->external_attr = otezip_read_le32 (h + 38);
+		e->local_hdr_ofs = otezip_read_le32 (h + 42);
+		if ((uint64_t)e->comp_size > MAX_PAYLOAD || (uint64_t)e->uncomp_size > MAX_PAYLOAD) {
+			free (cd);
+			return ERR_INCONS;
+		}
+		e->name = (char *)malloc (fl + 1);
+		if (!e->name) {
+			free (cd);
+			return ERR_READ;
+		}
+		memcpy (e->name, h + 46, fl);
+		e->name[fl] = '\0';
+		off += 46 + fl + xl + cl;
+	}
+	free (cd);
+	return 0;
+}
+
+/* The device entry table the walk emits: one otz_entry per directory entry. */
+zip_uint64_t otezip_b200_entry_table(zip_t *za, void *rows, zip_uint64_t max_rows) {
+	if (!is_valid (za) || !rows) {
+		return 0;
+	}
+	otz_entry *t = (otz_entry *)rows;
+	uint64_t out = 0;
+	zip_uint64_t n = za->n_entries < max_rows ? za->n_entries : max_rows;
+	for (zip_uint64_t i = 0; i < n; i++) {
+		const struct otezip_entry *e = &za->entries[i];
+		t[i].lfh_ofs = e->local_hdr_ofs;
+		t[i].out_ofs = out;
+		t[i].comp_size = e->comp_size;
+		t[i].uncomp_size = e->uncomp_size;
+		t[i].crc32 = e->crc32;
+		t[i].method = e->method;
+		t[i].flags = 0;
+		out += ((uint64_t)e->uncomp_size + 15) & ~15ULL;
+	}
+	return n;
+}
+
+/* ---------------------------------------------------------------- open / close */
+
+static void free_windows(struct otz_archive *a);
+
+zip_t *zip_open(const char *path, int flags, int *errorp) {
+	struct otz_archive *a = (struct otz_archive *)calloc (1, sizeof (*a));
+	if (!a || !path) {
+		free (a);
+		if (errorp) {
+			*errorp = -1;
+		}
+		return NULL;
+	}
+	a->magic = OTZ_MAGIC;
+	zip_t *za = &a->pub;
+	const char *mode = "rb";
+	int exists = 0;
+	if (flags & ZIP_CREATE) { /* otezip.c:708-738 */
+		if ((flags & ZIP_EXCL) && (flags & ZIP_TRUNCATE)) {
+			goto fail_flags;
+		}
+		FILE *probe = fopen (path, "rb");
+		exists = probe != NULL;
+		if (probe) {
+			fclose (probe);
+		}
+		if (exists && (flags & ZIP_EXCL)) {
+			goto fail_flags;
+		}
+		mode = (exists && !(flags & ZIP_TRUNCATE)) ? "r+b" : "w+b";
+		za->mode = 1;
+	}
+	if (mode[0] == 'w') {
+		unlink (path); /* otezip.c:744-747 */
+	}
+	za->fp = fopen (path, mode);
+	if (!za->fp) {
+		if (errorp) {
+			*errorp = ZIP_ER_OPEN;
+		}
+		free (a);
+		return NULL;
+	}
+	a->path = strdup (path);
+	if (za->mode == 0 || (exists && !(flags & ZIP_TRUNCATE))) { /* otezip.c:758-780 */
+		int rc = load_central (a);
+		if (rc != 0) {
+			if (errorp) {
+				*errorp = rc == ERR_READ ? ZIP_ER_READ : rc == ERR_INCONS ? ZIP_ER_INCONS : ZIP_ER_NOZIP;
+			}
+			za->mode = 0; /* nothing to finalize */
+			zip_close (za);
+			return NULL;
+		}
+		a->n_existing = za->n_entries;
+		if (za->mode == 1) {
+			za->next_index = za->n_entries;
+		}
+	}
+	if (errorp) {
+		*errorp = 0;
+	}
+	return za;
+fail_flags:
+	if (errorp) {
+		*errorp = -1;
+	}
+	free (a);
+	return NULL;
+}
+
+/* otezip.c:1406-1440: temp-file trampoline */
+zip_t *zip_open_from_source(zip_source_t *src, int flags, zip_error_t *error) {
+	(void)error;
+	if (!src) {
+		return NULL;
+	}
+	char tmp[] = "/tmp/otezip_XXXXXX";
+	mode_t old = umask (077);
+	int fd = mkstemp (tmp);
+	umask (old);
+	if (fd < 0) {
+		return NULL;
+	}
+	ssize_t w = write (fd, src->buf, (size_t)src->len);
+	close (fd);
+	if (w < 0 || (zip_uint64_t)w != src->len) {
+		unlink (tmp);
+		return NULL;
+	}
+	int err = 0;
+	zip_t *za = zip_open (tmp, flags, &err);
+	if (!za) {
+		unlink (tmp);
+	}
+	return za;
+}
+
+static int finalize_archive(struct otz_archive *a);
+
+int zip_close(zip_t *za) {
+	struct otz_archive *a = priv (za);
+	if (!is_valid (za) || !a) {
+		free (za); /* otezip.c:1274-1277 */
+		return -1;
+	}
+	int rc = 0;
+	if (za->mode == 1) {
+		rc = finalize_archive (a);
+	}
+	fclose (za->fp);
+	for (zip_uint64_t i = 0; i < za->n_entries; i++) {
+		free (za->entries[i].name);
+	}
+	if (a->pend) {
+		for (zip_uint64_t i = 0; i < za->n_entries; i++) {
+			if (a->pend[i].owned) {
+				free (a->pend[i].buf);
+			}
+		}
+		free (a->pend);
+	}
+	free (za->entries);
+	free_windows (a);
+	if (a->image) {
+		otz_host_free (a->image);
+	}
+	free (a->last_status);
+	free (a->path);
+	a->magic = 0;
+	free (a);
+	return rc;
+}
+
+zip_uint64_t zip_get_num_files(zip_t *za) {
+	return za ? za->n_entries : 0u; /* otezip.c:1297-1299 */
+}
+
+zip_int64_t zip_name_locate(zip_t *za, const char *fname, zip_flags_t flags) {
+	(void)flags;
+	if (!is_valid (za) || !fname) {
+		return -1;
+	}
+	for (zip_uint64_t i = 0; i < za->n_entries; i++) {
+		if (!strcmp (za->entries[i].name, fname)) {
+			return (zip_int64_t)i;
+		}
+	}
+	return -1;
+}
+
+const char *zip_get_name(zip_t *za, zip_uint64_t index, zip_flags_t flags) {
+	(void)flags;
+	return (is_valid (za) && index < za->n_entries) ? za->entries[index].name : NULL;
+}
+
+void zip_stat_init(zip_stat_t *st) { /* otezip.c:1359-1371 */
+	if (st) {
+		memset (st, 0, sizeof (*st));
+		st->index = ZIP_UINT64_MAX;
+		st->mtime = (time_t)-1;
+		st->comp_method = ZIP_CM_STORE;
+	}
+}
+
+int zip_stat_index(zip_t *za, zip_uint64_t index, zip_flags_t flags, zip_stat_t *st) {
+	(void)flags;
+	if (!is_valid (za) || !st || index >= za->n_entries) {
+		return -1;
+	}
+	const struct otezip_entry *e = &za->entries[index];
+	zip_stat_init (st);
+	st->name = e->name;
+	st->index = index;
+	st->size = e->uncomp_size;
+	st->comp_size = e->comp_size;
+	st->crc = e->crc32;
+	st->comp_method = e->method;
+	st->valid = ZIP_STAT_NAME | ZIP_STAT_INDEX | ZIP_STAT_SIZE | ZIP_STAT_COMP_SIZE | ZIP_STAT_CRC | ZIP_STAT_COMP_METHOD;
+	return 0;
+}
+
+int zip_stat(zip_t *za, const char *fname, zip_flags_t flags, zip_stat_t *st) {
+	zip_int64_t i = zip_name_locate (za, fname, flags);
+	return i < 0 ? -1 : zip_stat_index (za, (zip_uint64_t)i, flags, st);
+}
+
+/* ---------------------------------------------------------------- read path: batched extract */
+
+static uint64_t batch_budget(void) {
+	const char *e = getenv ("OTEZIP_BATCH_BYTES");
+	uint64_t v = e ? strtoull (e, NULL, 10) : 0;
+	return v ? v : (4ULL << 30); /* decoded bytes per batch */
+}
+
+static void free_window(struct otz_window *w) {
+	if (w->arena) {
+		otz_host_free (w->arena);
+	}
+	free (w->ofs);
+	free (w->status);
+	free (w->crc);
+	free (w);
+}
+
+static void free_windows(struct otz_archive *a) {
+	struct otz_window *w = a->windows;
+	while (w) {
+		struct otz_window *n = w->next;
+		free_window (w);
+		w = n;
+	}
+	a->windows = NULL;
+}
+
+static void drop_idle_windows(struct otz_archive *a) {
+	struct otz_window **pp = &a->windows;
+	while (*pp) {
+		struct otz_window *w = *pp;
+		if (!w->current && w->refs == 0) {
+			*pp = w->next;
+			free_window (w);
+		} else {
+			pp = &w->next;
+		}
+	}
+}
+
+/* the zip-bomb rule of otezip.c:454-462, evaluated with the globals as they are NOW */
+static int bomb_rejects(const struct otezip_entry *e) {
+	if (otezip_ignore_zipbomb || e->comp_size == 0) {
+		return 0;
+	}
+	uint64_t allowed = (uint64_t)e->comp_size * otezip_max_expansion_ratio + otezip_max_expansion_slack;
+	return (uint64_t)e->uncomp_size > allowed;
+}
+
+static int load_image(struct otz_archive *a) {
+	if (a->image) {
+		return 0;
+	}
+	FILE *fp = a->pub.fp;
+	if (fseek (fp, 0, SEEK_END) != 0) {
+		return -1;
+	}
+	long fsz = ftell (fp);
+	if (fsz < 0) {
+		return -1;
+	}
+	void *p = NULL;
+	if (otz_host_alloc ((uint64_t)fsz + 64, &p) != OTZ_SUCCESS) {
+		fprintf (stderr, "otezip-b200: %s\n", otz_last_error ());
+		return -1;
+	}
+	if (read_at (fp, 0, p, (size_t)fsz) != 0) {
+		otz_host_free (p);
+		return -1;
+	}
+	a->image = (uint8_t *)p;
+	a->image_len = (uint64_t)fsz;
+	return 0;
+}
+
+/* Decode a batch starting at `index`: consecutive entries until the byte budget is reached. */
+static struct otz_window *run_window(struct otz_archive *a, zip_uint64_t index) {
+	zip_t *za = &a->pub;
+	otz_ctx *ctx = gpu ();
+	if (!ctx || load_image (a) != 0) {
+		return NULL;
+	}
+	const uint64_t budget = batch_budget ();
+	zip_uint64_t last = index;
+	uint64_t bytes = 0;
+	while (last < za->n_entries) {
+		uint64_t sz = ((uint64_t)za->entries[last].uncomp_size + 15) & ~15ULL;
+		if (last > index && bytes + sz > budget) {
+			break;
+		}
+		bytes += sz;
+		last++;
+	}
+	const uint32_t n = (uint32_t)(last - index);
+	struct otz_window *w = (struct otz_window *)calloc (1, sizeof (*w));
+	otz_entry *tab = (otz_entry *)calloc (n, sizeof (otz_entry));
+	if (!w || !tab) {
+		free (w);
+		free (tab);
+		return NULL;
+	}
+	w->first = index;
+	w->last = last;
+	w->ofs = (uint64_t *)calloc (n, sizeof (uint64_t));
+	w->status = (int32_t *)calloc (n, sizeof (int32_t));
+	w->crc = (uint32_t *)calloc (n, sizeof (uint32_t));
+	uint64_t out = 0;
+	for (uint32_t k = 0; k < n; k++) {
+		const struct otezip_entry *e = &za->entries[index + k];
+		tab[k].lfh_ofs = e->local_hdr_ofs;
+		tab[k].out_ofs = out;
+		tab[k].comp_size = e->comp_size;
+		tab[k].uncomp_size = e->uncomp_size;
+		tab[k].crc32 = e->crc32;
+		tab[k].method = e->method;
+		w->ofs[k] = out;
+		out += ((uint64_t)e->uncomp_size + 15) & ~15ULL;
+	}
+	w->arena_len = out;
+	void *arena = NULL;
+	otz_extract_opts o;
+	o.ignore_zipbomb = otezip_ignore_zipbomb;
+	o.max_ratio = otezip_max_expansion_ratio;
+	o.max_slack = otezip_max_expansion_slack;
+	o.verify_only = 0;
+	int rc = otz_host_alloc (out + 64, &arena);
+	if (rc == OTZ_SUCCESS) {
+		w->arena = (uint8_t *)arena;
+		rc = otz_extract_host (ctx, a->image, a->image_len, tab, n, &o, w->arena, out, w->crc, w->status);
+	}
+	free (tab);
+	if (rc != OTZ_SUCCESS) {
+		fprintf (stderr, "otezip-b200: GPU extract failed: %s\n", otz_last_error ());
+		free_window (w);
+		return NULL;
+	}
+	for (struct otz_window *p = a->windows; p; p = p->next) {
+		p->current = 0;
+	}
+	w->current = 1;
+	w->next = a->windows;
+	a->windows = w;
+	drop_idle_windows (a);
+	if (!a->last_status) {
+		a->last_status = (int32_t *)malloc (za->n_entries * sizeof (int32_t));
+		for (zip_uint64_t i = 0; a->last_status && i < za->n_entries; i++) {
+			a->last_status[i] = -1;
+		}
+	}
+	for (uint32_t k = 0; a->last_status && k < n; k++) {
+		a->last_status[index + k] = w->status[k];
+	}
+	return w;
+}
+
+int otezip_b200_entry_status(zip_t *za, zip_uint64_t index) {
+	struct otz_archive *a = priv (za);
+	if (!a || !a->last_status || index >= za->n_entries) {
+		return -1;
+	}
+	return a->last_status[index];
+}
+
+/* otezip.c:1315-1334 + :399-684 */
+zip_file_t *zip_fopen_index(zip_t *za, zip_uint64_t index, zip_flags_t flags) {
+	(void)flags;
+	struct otz_archive *a = priv (za);
+	if (!is_valid (za) || !a || index >= za->n_entries) {
+		return NULL;
+	}
+	if (za->mode == 1 && index >= a->n_existing) {
+		return NULL; /* queued, not yet written */
+	}
+	struct otezip_entry *e = &za->entries[index];
+	struct otz_window *w = NULL;
+	for (struct otz_window *p = a->windows; p; p = p->next) {
+		if (index >= p->first && index < p->last) {
+			w = p;
+			break;
+		}
+	}
+	/* a batch decoded under other zip-bomb globals may have skipped this entry: decide again */
+	if (w) {
+		int st = w->status[index - w->first];
+		if (OTZ_ST_CODE (st) == OTZ_ST_ZIPBOMB && !bomb_rejects (e)) {
+			w = NULL;
+		}
+	}
+	if (!w) {
+		w = run_window (a, index);
+		if (!w) {
+			return NULL;
+		}
+	}
+	const uint32_t k = (uint32_t)(index - w->first);
+	int32_t st = w->status[k];
+	if (OTZ_ST_CODE (st) == OTZ_ST_OK && bomb_rejects (e)) {
+		st = OTZ_ST_ZIPBOMB; /* the guard tightened since the batch ran */
+	}
+	if (OTZ_ST_CODE (st) == OTZ_ST_ZIPBOMB) { /* otezip.c:459, verbatim */
+		fprintf (stderr, "mzip: entry '%s' claims huge uncompressed size (%u), rejecting to avoid zipbomb\n",
+			e->name ? e->name : "<unknown>", e->uncomp_size);
+		return NULL;
+	}
+	if (OTZ_ST_CODE (st) != OTZ_ST_OK || (otezip_ref_compat && (st & OTZ_STF_REF_EOB))) {
+		return NULL;
+	}
+	if (st & OTZ_STF_CRC_MISMATCH) { /* otezip.c:669-678 */
+		if (otezip_verify_crc) {
+			return NULL;
+		}
+		fprintf (stderr, "Warning: CRC mismatch for '%s' (expected 0x%08x, got 0x%08x)\n", e->name ? e->name : "<unknown>", e->crc32,
+			w->crc[k]);
+	}
+	struct otz_file *f = (struct otz_file *)calloc (1, sizeof (*f));
+	if (!f) {
+		return NULL;
+	}
+	f->pub.data = w->arena + w->ofs[k];
+	f->pub.size = e->uncomp_size;
+	f->pub.pos = 0;
+	f->win = w;
+	w->refs++;
+	return &f->pub;
+}
+
+int zip_fclose(zip_file_t *zf) { /* otezip.c:1336-1343: the library owns zf->data */
+	if (!zf) {
+		return -1;
+	}
+	struct otz_file *f = (struct otz_file *)zf;
+	if (f->win && f->win->refs) {
+		f->win->refs--;
+	}
+	free (f->own);
+	free (f);
+	return 0;
+}
+
+zip_int64_t zip_fread(zip_file_t *zf, void *buf, zip_uint64_t nbytes) { /* otezip.c:1345-1357 */
+	if (!zf || !buf) {
+		return -1;
+	}
+	if (zf->pos >= zf->size) {
+		return 0;
+	}
+	zip_uint64_t left = zf->size - zf->pos;
+	zip_uint64_t n = nbytes < left ? nbytes : left;
+	memcpy (buf, zf->data + zf->pos, n);
+	zf->pos += n;
+	return (zip_int64_t)n;
+}
+
+/* ---------------------------------------------------------------- write path: queue, then one GPU batch */
+
+zip_source_t *zip_source_buffer(zip_t *za, const void *data, zip_uint64_t len, int freep) { /* otezip.c:1592-1599 */
+	(void)za;
+	zip_source_t *s = (zip_source_t *)malloc (sizeof (*s));
+	if (s) {
+		s->buf = data;
+		s->len = len;
+		s->freep = freep;
+	}
+	return s;
+}
+
+zip_source_t *zip_source_buffer_create(const void *data, zip_uint64_t len, int freep, zip_error_t *error) {
+	(void)error;
+	return zip_source_buffer (NULL, data, len, freep);
+}
+
+void zip_source_free(zip_source_t *src) { /* otezip.c:1606-1614 */
+	if (src) {
+		if (src->freep && src->buf) {
+			free ((void *)src->buf);
+		}
+		free (src);
+	}
+}
+
+/* Take the bytes of a source for later compression.  freep: the library owns the caller's buffer from
+ * now on (otezip.c:1172-1174 frees it right away; here it lives until zip_close).  !freep: the
+ * reference has consumed the bytes when zip_file_add returns, so the caller may reuse the buffer:
+ * keep a private copy. */
+static int take_source(struct otz_pending *p, zip_source_t *src) {
+	p->len = src->len;
+	if (src->freep || src->len == 0) {
+		p->buf = (void *)src->buf;
+		p->owned = src->freep;
+		return 0;
+	}
+	p->buf = malloc ((size_t)src->len);
+	if (!p->buf) {
+		return -1;
+	}
+	memcpy (p->buf, src->buf, (size_t)src->len);
+	p->owned = 1;
+	return 0;
+}
+
+/* otezip.c:1079-1183, with compression deferred to zip_close */
+zip_int64_t zip_file_add(zip_t *za, const char *name, zip_source_t *src, zip_flags_t flags) {
+	(void)flags;
+	struct otz_archive *a = priv (za);
+	if (!a || !name || !src || za->mode != 1) {
+		return -1;
+	}
+	size_t nlen = strlen (name);
+	if (nlen > MAX_FIELD_LEN || (uint64_t)src->len > MAX_PAYLOAD) {
+		return -1;
+	}
+	struct otezip_entry *ne = (struct otezip_entry *)realloc (za->entries, (za->n_entries + 1) * sizeof (*ne));
+	if (!ne) {
+		return -1;
+	}
+	za->entries = ne;
+	struct otz_pending *np = (struct otz_pending *)realloc (a->pend, (za->n_entries + 1) * sizeof (*np));
+	if (!np) {
+		return -1;
+	}
+	if (!a->pend) {
+		memset (np, 0, za->n_entries * sizeof (*np));
+	}
+	a->pend = np;
+	struct otezip_entry *e = &za->entries[za->n_entries];
+	struct otz_pending *p = &a->pend[za->n_entries];
+	memset (e, 0, sizeof (*e));
+	memset (p, 0, sizeof (*p));
+	e->name = (char *)malloc (nlen + 1);
+	if (!e->name) {
+		return -1;
+	}
+	memcpy (e->name, name, nlen + 1);
+	e->method = za->default_method > 0 ? za->default_method : 0; /* otezip.c:1109-1114 */
+	e->uncomp_size = (uint32_t)src->len;
+	dos_now (&e->file_time, &e->file_date);                      /* otezip.c:1127 */
+	e->external_attr = 0100644u << 16;                            /* otezip.c:1130 */
+	if (take_source (p, src) != 0) {
+		free (e->name);
+		return -1;
+	}
+	free (src); /* consumed, otezip.c:1175 */
+	zip_uint64_t idx = za->n_entries++;
+	za->next_index = za->n_entries;
+	return (zip_int64_t)idx;
+}
+
+zip_int64_t zip_add(zip_t *za, const char *name, zip_source_t *src) {
+	return zip_file_add (za, name, src, 0);
+}
+
+/* otezip.c:1186-1237 — the method now really applies, because nothing has been compressed yet */
+int zip_set_file_compression(zip_t *za, zip_uint64_t index, zip_int32_t comp, zip_uint32_t comp_flags) {
+	(void)comp_flags;
+	struct otz_archive *a = priv (za);
+	if (!is_valid (za) || !a || index >= za->n_entries || za->mode != 1) {
+		return -1;
+	}
+	if (comp != OTEZIP_METHOD_STORE && comp != OTEZIP_METHOD_DEFLATE && comp != OTEZIP_METHOD_ZSTD) {
+		return -1;
+	}
+	if (index < a->n_existing) {
+		return -1; /* already on disk: relabelling would corrupt it (the reference's F4 bug) */
+	}
+	za->entries[index].method = (uint16_t)comp;
+	return 0;
+}
+
+/* otezip.c:1617-1663: replace the queued bytes of an entry added in this session */
+int zip_file_replace(zip_t *za, zip_uint64_t index, zip_source_t *src, zip_flags_t flags) {
+	(void)flags;
+	struct otz_archive *a = priv (za);
+	if (!is_valid (za) || !a || !src || za->mode != 1 || index >= za->n_entries || index < a->n_existing ||
+		(uint64_t)src->len > MAX_PAYLOAD) {
+		return -1;
+	}
+	struct otz_pending np;
+	memset (&np, 0, sizeof (np));
+	if (take_source (&np, src) != 0) {
+		return -1;
+	}
+	if (a->pend[index].owned) {
+		free (a->pend[index].buf);
+	}
+	a->pend[index] = np;
+	za->entries[index].uncomp_size = (uint32_t)src->len;
+	return 0;
+}
+
+int zip_replace(zip_t *za, zip_uint64_t index, zip_source_t *src) {
+	return zip_file_replace (za, index, src, 0);
+}
+
+/* otezip.c:1443-1491 */
+static int write_lfh(FILE *fp, const struct otezip_entry *e) {
+	uint8_t h[30];
+	uint16_t t, d;
+	size_t nl = strlen (e->name);
+	dos_now (&t, &d); /* the reference re-samples the clock here, otezip.c:1464-1467 */
+	otezip_write_le32 (h, SIG_LFH);
+	otezip_write_le16 (h + 4, 20);
+	otezip_write_le16 (h + 6, 0);
+	otezip_write_le16 (h + 8, e->method);
+	otezip_write_le16 (h + 10, t);
+	otezip_write_le16 (h + 12, d);
+	otezip_write_le32 (h + 14, e->crc32);
+	otezip_write_le32 (h + 18, e->comp_size);
+	otezip_write_le32 (h + 22, e->uncomp_size);
+	otezip_write_le16 (h + 26, (uint16_t)nl);
+	otezip_write_le16 (h + 28, 0);
+	return fwrite (h, 1, 30, fp) == 30 && fwrite (e->name, 1, nl, fp) == nl ? 0 : -1;
+}
+
+/* otezip.c:1494-1558 */
+static uint32_t write_cdh(FILE *fp, const struct otezip_entry *e) {
+	uint8_t h[46];
+	size_t nl = strlen (e->name);
+	memset (h, 0, sizeof (h));
+	otezip_write_le32 (h, SIG_CDH);
+	otezip_write_le16 (h + 4, 0x031e);
+	otezip_write_le16 (h + 6, 20);
+	otezip_write_le16 (h + 10, e->method);
+	otezip_write_le16 (h + 12, e->file_time);
+	otezip_write_le16 (h + 14, e->file_date);
+	otezip_write_le32 (h + 16, e->crc32);
+	otezip_write_le32 (h + 20, e->comp_size);
+	otezip_write_le32 (h + 24, e->uncomp_size);
+	otezip_write_le16 (h + 28, (uint16_t)nl);
+	otezip_write_le32 (h + 38, e->external_attr);
+	otezip_write_le32 (h + 42, e->local_hdr_ofs);
+	fwrite (h, 1, 46, fp);
+	fwrite (e->name, 1, nl, fp);
+	return (uint32_t)(46 + nl);
+}
+
+/* zip_close of a written archive: one GPU batch (CRC + DEFLATE/STORE decision), then LFH+payload per
+ * entry in add order, the central directory and the EOCD (otezip.c:1240-1271, :1561-1590). */
+static int finalize_archive(struct otz_archive *a) {
+	zip_t *za = &a->pub;
+	const zip_uint64_t n_new = za->n_entries - a->n_existing;
+	uint64_t *in_ofs = NULL, *out_ofs = NULL;
+	uint32_t *in_len = NULL, *out_size = NULL, *crc = NULL;
+	uint16_t *method = NULL, *method_out = NULL;
+	uint8_t *in = NULL, *out = NULL;
+	int rc = -1;
+	uint64_t pos = a->n_existing ? a->append_ofs : 0;
+	if (fseek (za->fp, (long)pos, SEEK_SET) != 0) {
+		return -1;
+	}
+	if (n_new) {
+		otz_ctx *ctx = gpu ();
+		if (!ctx) {
+			return -1;
+		}
+		in_ofs = (uint64_t *)calloc (n_new, 8);
+		out_ofs = (uint64_t *)calloc (n_new, 8);
+		in_len = (uint32_t *)calloc (n_new, 4);
+		out_size = (uint32_t *)calloc (n_new, 4);
+		crc = (uint32_t *)calloc (n_new, 4);
+		method = (uint16_t *)calloc (n_new, 2);
+		method_out = (uint16_t *)calloc (n_new, 2);
+		if (!in_ofs || !out_ofs || !in_len || !out_size || !crc || !method || !method_out) {
+			goto done;
+		}
+		uint64_t total = 0;
+		for (zip_uint64_t k = 0; k < n_new; k++) {
+			const struct otezip_entry *e = &za->entries[a->n_existing + k];
+			in_ofs[k] = total;
+			in_len[k] = (uint32_t)a->pend[a->n_existing + k].len;
+			/* method 93: the reference's writer cannot produce a stream its reader accepts and always falls
+			 * back to STORE (zstd.inc.c:269, otezip.c:894-899) — same result here */
+			method[k] = e->method == OTEZIP_METHOD_DEFLATE ? OTZ_M_DEFLATE : OTZ_M_STORE;
+			total += ((uint64_t)in_len[k] + 15) & ~15ULL;
+		}
+		void *pin = NULL, *pout = NULL;
+		if (otz_host_alloc (total + 64, &pin) != OTZ_SUCCESS || otz_host_alloc (total + 64, &pout) != OTZ_SUCCESS) {
+			fprintf (stderr, "otezip-b200: %s\n", otz_last_error ());
+			if (pin) {
+				otz_host_free (pin);
+			}
+			goto done;
+		}
+		in = (uint8_t *)pin;
+		out = (uint8_t *)pout;
+		for (zip_uint64_t k = 0; k < n_new; k++) {
+			if (in_len[k]) {
+				memcpy (in + in_ofs[k], a->pend[a->n_existing + k].buf, in_len[k]);
+			}
+		}
+		uint64_t out_total = 0;
+		if (otz_deflate_host (ctx, in, total, in_ofs, in_len, method, (uint32_t)n_new, out, total, out_ofs, out_size, crc, method_out,
+			&out_total) != OTZ_SUCCESS) {
+			fprintf (stderr, "otezip-b200: GPU compress failed: %s\n", otz_last_error ());
+			goto done;
+		}
+		for (zip_uint64_t k = 0; k < n_new; k++) {
+			struct otezip_entry *e = &za->entries[a->n_existing + k];
+			e->crc32 = crc[k];
+			e->comp_size = out_size[k];
+			e->method = method_out[k];
+			if (pos > 0xFFFFFFFFULL) { /* otezip.c:1140 */
+				goto done;
+			}
+			e->local_hdr_ofs = (uint32_t)pos;
+			if (write_lfh (za->fp, e) != 0 || (out_size[k] && fwrite (out + out_ofs[k], 1, out_size[k], za->fp) != out_size[k])) {
+				goto done;
+			}
+			pos += 30 + strlen (e->name) + out_size[k];
+		}
+	}
+	{
+		if (pos > 0xFFFFFFFFULL) { /* otezip.c:1264 */
+			goto done;
+		}
+		uint64_t cd_size = 0;
+		for (zip_uint64_t i = 0; i < za->n_entries; i++) {
+			cd_size += write_cdh (za->fp, &za->entries[i]);
+			if (cd_size > 0xFFFFFFFFULL) {
+				goto done;
+			}
+		}
+		uint8_t eocd[22];
+		memset (eocd, 0, sizeof (eocd));
+		otezip_write_le32 (eocd, SIG_EOCD);
+		otezip_write_le16 (eocd + 8, (uint16_t)za->n_entries);
+		otezip_write_le16 (eocd + 10, (uint16_t)za->n_entries);
+		otezip_write_le32 (eocd + 12, (uint32_t)cd_size);
+		otezip_write_le32 (eocd + 16, (uint32_t)pos);
+		if (fwrite (eocd, 1, 22, za->fp) != 22) {
+			goto done;
+		}
+		fflush (za->fp);
+		if (a->n_existing) {
+			long end = ftell (za->fp);
+			if (end > 0 && ftruncate (fileno (za->fp), end) != 0) {
+				goto done;
+			}
+		}
+		rc = 0;
+	}
+done:
+	if (in) {
+		otz_host_free (in);
+	}
+	if (out) {
+		otz_host_free (out);
+	}
+	free (in_ofs);
+	free (out_ofs);
+	free (in_len);
+	free (out_size);
+	free (crc);
+	free (method);
+	free (method_out);
+	return rc;
+}

@@ -1,0 +1,135 @@
+"""The drop-in boundary: the reference's libzip-subset API served by libotezip_b200.so.  Scenarios follow
+the reference's own tests (test/unit/test_empty_zip.c, test_set_file_compression.c, test/test.sh)."""
+import ctypes as C
+import hashlib
+import json
+import os
+import subprocess
+import zipfile
+import zlib
+
+import pytest
+
+from otezip_b200 import synth
+from otezip_b200.zipapi import ZipApi, ZIP_CM_DEFLATE, ZIP_CM_STORE
+
+pytestmark = pytest.mark.gpu
+G = os.path.join(os.path.dirname(__file__), "golden")
+EXPECTED = json.load(open(os.path.join(G, "expected.json")))
+REFDIR = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "oracle", "_ref")
+
+
+@pytest.fixture(scope="module")
+def api():
+    return ZipApi()
+
+
+def test_empty_zip(api, tmp_path):
+    # test/unit/test_empty_zip.c:10-19
+    p = tmp_path / "empty.zip"
+    p.write_bytes(bytes([0x50, 0x4b, 0x05, 0x06] + [0] * 18))
+    err, names, datas = api.read_all(str(p))
+    assert err == 0 and names == [] and datas == []
+
+
+def test_open_errors(api, tmp_path):
+    err = C.c_int(0)
+    assert not api.L.zip_open(str(tmp_path / "missing.zip").encode(), 0, C.byref(err)) and err.value == 11   # ZIP_ER_OPEN
+    (tmp_path / "junk.zip").write_bytes(b"this is not a zip archive, not at all")
+    assert not api.L.zip_open(str(tmp_path / "junk.zip").encode(), 0, C.byref(err)) and err.value == 21     # ZIP_ER_INCONS
+    assert not api.L.zip_open(str(tmp_path / "x.zip").encode(), 1 | 2 | 8, C.byref(err)) and err.value == -1  # EXCL+TRUNCATE
+
+
+@pytest.mark.parametrize("name", sorted(EXPECTED))
+def test_read_path_matches_reference_golden(api, name):
+    err, names, datas = api.read_all(os.path.join(G, name + ".zip"), verify_crc=1)
+    assert err == 0
+    exp = EXPECTED[name]
+    assert len(datas) == len(exp)
+    for i, e in enumerate(exp):
+        if e is None:
+            assert datas[i] is None, (name, i)
+        else:
+            d = datas[i]
+            assert d is not None, (name, i)
+            assert [len(d), zlib.crc32(d) & 0xFFFFFFFF, hashlib.sha256(d).hexdigest()] == e, (name, i)
+
+
+def test_crc_warning_mode_returns_data(api, capfd):
+    # otezip.c:674-677: without otezip_verify_crc a mismatch only warns
+    err, names, datas = api.read_all(os.path.join(G, "edges.zip"), verify_crc=0)
+    i = names.index(b"bad_crc")
+    assert datas[i] is not None
+    assert "Warning: CRC mismatch for 'bad_crc'" in capfd.readouterr().err
+
+
+def test_set_file_compression_after_add(api, tmp_path, reflib):
+    # test/unit/test_set_file_compression.c:10-127 (fails on the reference; must pass here)
+    p = str(tmp_path / "c.zip")
+    payload = b"A" * 4096
+    assert api.write_archive(p, [("hello.txt", payload)], ZIP_CM_DEFLATE) == 0
+    err, names, datas = api.read_all(p)
+    assert names == [b"hello.txt"] and datas == [payload]
+    with zipfile.ZipFile(p) as z:
+        info = z.infolist()[0]
+        assert info.compress_type == zipfile.ZIP_DEFLATED and info.compress_size < 200 and z.read("hello.txt") == payload
+    e2, got = reflib.extract_file(p, verify_crc=1)           # the reference reads what we wrote
+    assert e2 == 0 and got == [payload]
+
+
+def test_write_path_mixed_methods_and_fallbacks(api, tmp_path, reflib):
+    files = [("text.json", synth.jsonlog_text(300000, 1)), ("empty", b""), ("rand.bin", synth.random_bytes(70000, 2)),
+             ("stored.txt", synth.jsonlog_text(5000, 3), ZIP_CM_STORE), ("tiny", b"hello\n"), ("name with spaces.txt", b"x" * 1000),
+             ("zstd-falls-back-to-store", synth.jsonlog_text(4000, 4), 93)]
+    p = str(tmp_path / "m.zip")
+    assert api.write_archive(p, files, ZIP_CM_DEFLATE) == 0
+    want = [f[1] for f in files]
+    assert api.read_all(p)[2] == want
+    e2, got = reflib.extract_file(p, verify_crc=1)
+    assert e2 == 0 and got == want
+    with zipfile.ZipFile(p) as z:
+        infos = z.infolist()
+        assert z.testzip() is None
+        assert [i.compress_type for i in infos] == [8, 0, 0, 0, 0, 8, 0]     # fallbacks: empty, random, tiny, zstd -> STORE
+        assert all(i.create_version == 30 and i.extract_version == 20 and i.external_attr == 0o100644 << 16 for i in infos)
+
+
+def _tree(d):
+    out = {}
+    for root, _, fs in os.walk(d):
+        for f in fs:
+            q = os.path.join(root, f)
+            out[os.path.relpath(q, d)] = open(q, "rb").read()
+    return out
+
+
+@pytest.mark.skipif(not os.path.exists(os.path.join(REFDIR, "otezip_relinked")), reason="relinked CLI not built")
+def test_unchanged_cli_relinked_against_the_gpu_library(tmp_path):
+    """The reference's unmodified main.c linked against libotezip_b200.so (oracle/Makefile) must behave like
+    the reference CLI: same stdout, same extracted files (main.c:429-585 extract, :177-262 create)."""
+    ref, new = os.path.join(REFDIR, "otezip_ref"), os.path.join(REFDIR, "otezip_relinked")
+    z = os.path.join(G, "mixed.zip")
+    outs = {}
+    for tag, exe in (("ref", ref), ("new", new)):
+        d = tmp_path / tag
+        d.mkdir()
+        r = subprocess.run([exe, "-x", z, "--verify-crc"], cwd=d, capture_output=True, text=True, timeout=300)
+        outs[tag] = (r.returncode, r.stdout, _tree(d))
+    assert outs["ref"][0] == outs["new"][0] == 0
+    assert outs["ref"][1] == outs["new"][1]
+    assert outs["ref"][2] == outs["new"][2] and len(outs["new"][2]) > 100
+    # create with the relinked CLI, extract with the reference CLI
+    src = tmp_path / "src"
+    src.mkdir()
+    (src / "a.json").write_bytes(synth.jsonlog_text(200000, 5))
+    (src / "b.bin").write_bytes(synth.random_bytes(30000, 6))
+    (src / "c.txt").write_bytes(b"hello\n")
+    r = subprocess.run([new, "-c", "out.zip", "a.json", "b.bin", "c.txt", "-z", "deflate"], cwd=src, capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
+    d = tmp_path / "back"
+    d.mkdir()
+    r = subprocess.run([ref, "-x", str(src / "out.zip"), "--verify-crc"], cwd=d, capture_output=True, text=True)
+    assert r.returncode == 0
+    want = {k: v for k, v in _tree(src).items() if k != "out.zip"}
+    assert _tree(d) == want
+    assert os.path.getsize(src / "out.zip") < 80000     # a.json really got deflated
