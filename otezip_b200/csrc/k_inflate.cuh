@@ -8,8 +8,10 @@
 //     lane; the 64-bit bit buffer is refilled by a tile shuffle from that register window
 //     (the next window is already in flight while the current one is consumed);
 //   * literal/length and distance codes are looked up in per-stream shared-memory tables
-//     (9-bit / 8-bit roots with second-level tables for longer codes), 16-bit entries;
-//   * literals are gathered one per lane and flushed with one coalesced store;
+//     (9-bit / 8-bit roots with second-level tables for longer codes); an entry carries the code
+//     length, the extra-bit count and the length / distance base, so a symbol costs one lookup;
+//   * the most recent W output bytes live in a per-stream shared-memory ring: literals and LZ77 copies
+//     touch only shared memory, completed 16*G-byte segments leave for HBM as coalesced 16-byte stores;
 //   * LZ77 copies are performed by all G lanes (bytes are independent once the period
 //     `distance` is taken into account, so no lane waits on another);
 //   * dynamic-block tables are built cooperatively (counts with shared-memory atomics, canonical
@@ -27,16 +29,21 @@
 #define INF_LIT_CAP 852   // zlib's proven bound for (286 symbols, root 9, max 15)
 #define INF_DST_CAP 416   // >= 402, libdeflate's bound for (32 symbols, root 8, max 15)
 
-#define INF_K_LIT 0u
+// 32-bit table entry: [4:0] code bits consumed at this level (LINK: index bits of the second-level
+// table, 0 = invalid code), [8:5] number of extra bits, [10:9] kind, [31:16] value — literal byte,
+// length base, distance base or second-level offset.  Bases and extra-bit counts are the tables of
+// dec:720-725 / dec:766-771, folded into the entry when the table is built.
+#define INF_K_LIT 0u   // literal (or, in the distance table, a valid distance symbol)
 #define INF_K_LEN 1u
 #define INF_K_EOB 2u
-#define INF_K_LINK 3u  // with nbits == 0: invalid code
-#define INF_ENTRY(nbits, kind, payload) ((uint16_t)((nbits) | ((kind) << 4) | ((payload) << 6)))
-#define INF_INVALID INF_ENTRY(0u, INF_K_LINK, 0u)
+#define INF_K_LINK 3u
+#define INF_ENTRY(cb, xb, kind, value) ((uint32_t)(cb) | ((uint32_t)(xb) << 5) | ((uint32_t)(kind) << 9) | ((uint32_t)(value) << 16))
+#define INF_INVALID INF_ENTRY(0u, 0u, INF_K_LINK, 0u)
+#define INF_KIND(e) (((e) >> 9) & 3u)
 
 struct __align__(16) InflateSmem {
-	uint16_t lit[INF_LIT_CAP];
-	uint16_t dst[INF_DST_CAP];
+	uint32_t lit[INF_LIT_CAP];
+	uint32_t dst[INF_DST_CAP];
 	uint16_t sorted[288];
 	uint8_t lens[320];
 	uint32_t cnt[16];
@@ -109,11 +116,43 @@ struct BitReader {
 	}
 };
 
+// Table entry of symbol s whose code takes cb bits at this table level.
+__device__ __forceinline__ uint32_t inf_symbol_entry(uint32_t s, uint32_t cb, bool is_dist) {
+	if (is_dist) {
+		if (s >= 30) {
+			return INF_INVALID;  // fixed-table symbols 30/31 (dec:766-774 would index past dist_base)
+		}
+		if (s < 4) {
+			return INF_ENTRY(cb, 0u, INF_K_LIT, 1u + s);
+		}
+		const uint32_t xb = (s - 2) >> 1;
+		return INF_ENTRY(cb, xb, INF_K_LIT, 1u + ((2u + (s & 1u)) << xb));  // dec:766-771
+	}
+	if (s < 256) {
+		return INF_ENTRY(cb, 0u, INF_K_LIT, s);
+	}
+	if (s == 256) {
+		return INF_ENTRY(cb, 0u, INF_K_EOB, 0u);
+	}
+	if (s >= 286) {
+		return INF_INVALID;  // dec:794-797
+	}
+	const uint32_t v = s - 257;
+	if (v < 8) {
+		return INF_ENTRY(cb, 0u, INF_K_LEN, 3u + v);
+	}
+	if (v == 28) {
+		return INF_ENTRY(cb, 0u, INF_K_LEN, 258u);
+	}
+	const uint32_t xb = (v - 4) >> 2;
+	return INF_ENTRY(cb, xb, INF_K_LEN, 3u + ((4u + (v & 3u)) << xb));  // dec:720-725
+}
+
 // ------------------------------------------------------------------------------------------------
 // Canonical table build from code lengths (dec:86-119 assigns the same canonical codes).
 // Returns 0 ok, nonzero = invalid set.  All lanes return the same value.
 template <int G, typename Tile>
-__device__ __noinline__ int build_table(const Tile &tile, InflateSmem &S, const uint8_t *lens, int n, int root, uint16_t *tbl, int cap,
+__device__ __noinline__ int build_table(const Tile &tile, InflateSmem &S, const uint8_t *lens, int n, int root, uint32_t *tbl, int cap,
 	bool is_dist) {
 	const int lane = tile.thread_rank();
 	for (int i = lane; i < 16; i += G) {
@@ -193,12 +232,7 @@ __device__ __noinline__ int build_table(const Tile &tile, InflateSmem &S, const 
 		}
 		const uint32_t c = S.first[l] + (i - S.offs[l]);
 		const uint32_t rev = __brev(c) >> (32 - l);
-		uint16_t e;
-		if (is_dist) {
-			e = s < 30 ? INF_ENTRY(l, INF_K_LIT, s) : INF_INVALID;
-		} else {
-			e = s < 256 ? INF_ENTRY(l, INF_K_LIT, s) : s == 256 ? INF_ENTRY(l, INF_K_EOB, 0u) : s < 286 ? INF_ENTRY(l, INF_K_LEN, s - 257) : INF_INVALID;
-		}
+		const uint32_t e = inf_symbol_entry(s, l, is_dist);
 		for (int k = (int)rev; k < rootsz; k += (1 << l)) {
 			tbl[k] = e;
 		}
@@ -233,16 +267,11 @@ __device__ __noinline__ int build_table(const Tile &tile, InflateSmem &S, const 
 				next_free += 1 << curr;
 				cur_prefix = prefix;
 				if (lane == 0) {
-					tbl[prefix] = INF_ENTRY((uint32_t)sub_bits, INF_K_LINK, (uint32_t)sub_off);
+					tbl[prefix] = INF_ENTRY((uint32_t)sub_bits, 0u, INF_K_LINK, (uint32_t)sub_off);
 				}
 			}
-			uint16_t e;
 			const uint32_t nb2 = (uint32_t)(l - root);
-			if (is_dist) {
-				e = s < 30 ? INF_ENTRY(nb2, INF_K_LIT, s) : INF_INVALID;
-			} else {
-				e = s < 256 ? INF_ENTRY(nb2, INF_K_LIT, s) : s == 256 ? INF_ENTRY(nb2, INF_K_EOB, 0u) : s < 286 ? INF_ENTRY(nb2, INF_K_LEN, s - 257) : INF_INVALID;
-			}
+			const uint32_t e = inf_symbol_entry(s, nb2, is_dist);
 			const int step = 1 << nb2;
 			for (int k = (int)(rev >> root) + lane * step; k < (1 << sub_bits); k += G * step) {
 				tbl[sub_off + k] = e;
@@ -268,7 +297,7 @@ __device__ __noinline__ int build_fixed(const Tile &tile, InflateSmem &S) {
 
 // dec:122-266
 template <int G, typename Tile>
-__device__ __noinline__ int read_dynamic(const Tile &tile, InflateSmem &S, BitReader<G> &br) {
+__device__ __forceinline__ int read_dynamic(const Tile &tile, InflateSmem &S, BitReader<G> &br) {
 	const int lane = tile.thread_rank();
 	br.refill(tile);
 	const int hlit = (int)(br.bb & 31) + 257, hdist = (int)((br.bb >> 5) & 31) + 1, hclen = (int)((br.bb >> 10) & 15) + 4;
@@ -377,19 +406,90 @@ __device__ __noinline__ int read_dynamic(const Tile &tile, InflateSmem &S, BitRe
 }
 
 // ------------------------------------------------------------------------------------------------
+// Output ring.  The last W bytes of a stream's output live in shared memory: literals are single
+// byte stores by lane 0, LZ77 copies run ring -> ring (shared-memory latency instead of an L2 round
+// trip per dependent copy), and every completed 16*G-byte segment goes to HBM as one coalesced
+// 16-byte-per-lane store.  Ring index of output byte p is (p + mis) & (W-1) with mis = dst & 15, so ring
+// vectors line up with 16-byte aligned global vectors.  A back-reference that reaches further than the ring
+// holds is read from HBM (those bytes were flushed long ago: W >= 16*G + 516).
+template <int G, int W>
+struct __align__(16) InflateSmemV2 {
+	InflateSmem t;
+	uint8_t ring[W];
+};
+
+template <int G, int W>
+struct OutRing {
+	uint8_t *ring;
+	uint8_t *gbase;     // dst - mis (16-byte aligned)
+	uint32_t mis;
+	uint32_t q;         // linear write position = bytes produced + mis
+	uint32_t qf;        // linear position up to which HBM holds the data
+	static constexpr uint32_t MASK = W - 1;
+	static constexpr uint32_t SEG = 16 * G;
+
+	__device__ __forceinline__ void init(uint8_t *r, uint8_t *dst) {
+		ring = r;
+		mis = (uint32_t)(reinterpret_cast<uint64_t>(dst) & 15);
+		gbase = dst - mis;
+		q = qf = mis;
+	}
+	__device__ __forceinline__ uint32_t produced() const { return q - mis; }
+	// write ring[a, b) (linear positions) to HBM; whole tile, ring contents visible (caller synced)
+	__device__ __forceinline__ void flush_range(uint32_t a, uint32_t b, int lane) {
+		uint32_t a16 = (a + 15u) & ~15u, b16 = b & ~15u;
+		if (a16 >= b16) {
+			for (uint32_t x = a + lane; x < b; x += G) {
+				gbase[x] = ring[x & MASK];
+			}
+			return;
+		}
+		for (uint32_t x = a + lane; x < a16; x += G) {
+			gbase[x] = ring[x & MASK];
+		}
+		for (uint32_t x = a16 + 16u * lane; x < b16; x += SEG) {
+			*reinterpret_cast<uint4 *>(gbase + x) = *reinterpret_cast<const uint4 *>(ring + (x & MASK));
+		}
+		for (uint32_t x = b16 + lane; x < b; x += G) {
+			gbase[x] = ring[x & MASK];
+		}
+	}
+	template <typename Tile>
+	__device__ __forceinline__ void maybe_flush(const Tile &tile, int lane) {
+		const uint32_t qa = q & ~(SEG - 1u);
+		if (qa > qf) {
+			tile.sync();
+			flush_range(qf, qa, lane);
+			qf = qa;
+		}
+	}
+	template <typename Tile>
+	__device__ __forceinline__ void finish(const Tile &tile, int lane) {
+		tile.sync();
+		if (q > qf) {
+			flush_range(qf, q, lane);
+			qf = q;
+		}
+	}
+};
+
 // Decode one raw stream.  Returns the status word; *produced = bytes written.
-template <int G, typename Tile>
-__device__ __forceinline__ int32_t inflate_stream(const Tile &tile, InflateSmem &S, const uint8_t *__restrict__ in, uint32_t comp,
+template <int G, int W, typename Tile>
+__device__ __forceinline__ int32_t inflate_stream(const Tile &tile, InflateSmemV2<G, W> &SS, const uint8_t *__restrict__ in, uint32_t comp,
 	uint8_t *__restrict__ out, uint32_t cap, uint32_t *produced) {
 	const int lane = tile.thread_rank();
+	InflateSmem &S = SS.t;
 	*produced = 0;
 	if (comp == 0) {
 		return OTZ_ST_TRUNCATED;  // dec:610: the loop never runs; Z_OK or Z_BUF_ERROR, never STREAM_END
 	}
 	BitReader<G> br;
 	br.init(tile, in, comp);
-	uint32_t op = 0;
-	uint32_t npend = 0, mylit = 0;  // pending literals, one per lane
+	OutRing<G, W> ring;
+	ring.init(SS.ring, out);
+	uint8_t *const rb = SS.ring;
+	constexpr uint32_t MASK = W - 1;
+	const uint32_t qcap = cap + ring.mis;   // linear end of the output buffer
 	bool ref_eob = false;
 	int32_t err = 0;
 
@@ -406,14 +506,6 @@ __device__ __forceinline__ int32_t inflate_stream(const Tile &tile, InflateSmem 
 			ref_eob = true;                             \
 		}                                               \
 	}
-#define INF_FLUSH_LITS()                                \
-	if (npend) {                                        \
-		if ((uint32_t)lane < npend) {                   \
-			out[op + lane] = (uint8_t)mylit;            \
-		}                                               \
-		op += npend;                                    \
-		npend = 0;                                      \
-	}
 
 	for (;;) {
 		// ---- block header, dec:613-627
@@ -424,7 +516,6 @@ __device__ __forceinline__ int32_t inflate_stream(const Tile &tile, InflateSmem 
 		INF_STEP_CHECK();
 		if (btype == 0) {
 			// ---- stored block, dec:269-319
-			INF_FLUSH_LITS();
 			const int64_t rem = br.remaining_bits();
 			const uint64_t pos = (uint64_t)comp - (uint64_t)(rem >> 3);  // partial byte dropped
 			if ((uint64_t)comp - pos < 4) {
@@ -436,13 +527,20 @@ __device__ __forceinline__ int32_t inflate_stream(const Tile &tile, InflateSmem 
 				err = OTZ_ST_DATA;
 				break;
 			}
-			if (cap - op < len) {
+			if (qcap - ring.q < len) {
 				err = OTZ_ST_OVERFLOW;
 				break;
 			}
-			tile.sync();
-			tile_copy<G>(out + op, in + pos + 4, len, lane);
-			op += len;
+			const uint8_t *sp = in + pos + 4;
+			for (uint32_t done = 0; done < len;) {
+				const uint32_t n = min(len - done, OutRing<G, W>::SEG);
+				for (uint32_t i = lane; i < n; i += G) {
+					rb[(ring.q + i) & MASK] = sp[done + i];
+				}
+				ring.q += n;
+				done += n;
+				ring.maybe_flush(tile, lane);
+			}
 			const uint64_t npos = pos + 4 + len;
 			br.init(tile, in + npos, (uint64_t)comp - npos);
 			if (final_blk) {
@@ -462,111 +560,104 @@ __device__ __forceinline__ int32_t inflate_stream(const Tile &tile, InflateSmem 
 			break;
 		}
 		INF_STEP_CHECK();
-		// ---- symbols, dec:662-799
+		// ---- symbols, dec:662-799.  One loop; the per-step checks that only matter near the end of the
+		// input or of the output buffer are skipped while both are far away (`slow` is false).
 		bool eob = false;
+		const uint32_t qfast = qcap >= 258u ? qcap - 258u : 0u;
 		for (;;) {
 			br.refill(tile);
+			const bool slow = br.words_left <= 1 || ring.q > qfast;
 			uint32_t e = S.lit[(uint32_t)br.bb & ((1u << INF_LIT_ROOT) - 1u)];
-			if ((e & 0x30u) == (INF_K_LINK << 4)) {
-				const uint32_t sb = e & 15u;
+			if (INF_KIND(e) == INF_K_LINK) {
+				const uint32_t sb = e & 31u;
 				if (sb == 0) {
 					err = OTZ_ST_DATA;  // dec:693-695: no code matches
 					break;
 				}
 				br.consume(INF_LIT_ROOT);
-				e = S.lit[(e >> 6) + ((uint32_t)br.bb & ((1u << sb) - 1u))];
-				if ((e & 0x30u) == (INF_K_LINK << 4)) {
+				e = S.lit[(e >> 16) + ((uint32_t)br.bb & ((1u << sb) - 1u))];
+				if (INF_KIND(e) == INF_K_LINK) {
 					err = OTZ_ST_DATA;
 					break;
 				}
 			}
-			br.consume(e & 15u);
-			const uint32_t kind = (e >> 4) & 3u, val = e >> 6;
-			if (kind == INF_K_LIT) {
-				if (op + npend >= cap) {
+			const uint32_t cb = e & 31u;
+			if (INF_KIND(e) == INF_K_LIT) {
+				br.consume(cb);
+				if (slow && ring.q >= qcap) {
 					err = OTZ_ST_OVERFLOW;  // dec:700-703
 					break;
 				}
-				if ((uint32_t)lane == npend) {
-					mylit = val;
+				if (lane == 0) {
+					rb[ring.q & MASK] = (uint8_t)(e >> 16);
 				}
-				if (++npend == G) {
-					INF_FLUSH_LITS();
-				}
-			} else if (kind == INF_K_EOB) {
-				eob = true;
-				break;  // dec:711-716
-			} else {
-				// length symbol val = sym-257 (dec:720-737), then distance (dec:740-782)
-				uint32_t length, xb;
-				if (val < 8) {
-					length = 3 + val;
-					xb = 0;
-				} else if (val == 28) {
-					length = 258;
-					xb = 0;
-				} else {
-					xb = (val - 4) >> 2;
-					length = 3 + ((4 + (val & 3)) << xb);
-				}
-				length += (uint32_t)br.bb & ((1u << xb) - 1u);
-				br.consume(xb);
+				ring.q++;
+			} else if (INF_KIND(e) == INF_K_LEN) {
+				// length (dec:720-737), then distance (dec:740-782)
+				const uint32_t xb = (e >> 5) & 15u;
+				const uint32_t length = (e >> 16) + (((uint32_t)(br.bb >> cb)) & ((1u << xb) - 1u));
+				br.consume(cb + xb);
 				br.refill(tile);
 				uint32_t d = S.dst[(uint32_t)br.bb & ((1u << INF_DST_ROOT) - 1u)];
-				if ((d & 0x30u) == (INF_K_LINK << 4)) {
-					const uint32_t sb = d & 15u;
+				if (INF_KIND(d) == INF_K_LINK) {
+					const uint32_t sb = d & 31u;
 					if (sb == 0) {
 						err = OTZ_ST_DATA;  // dec:762-764
 						break;
 					}
 					br.consume(INF_DST_ROOT);
-					d = S.dst[(d >> 6) + ((uint32_t)br.bb & ((1u << sb) - 1u))];
-					if ((d & 0x30u) == (INF_K_LINK << 4)) {
+					d = S.dst[(d >> 16) + ((uint32_t)br.bb & ((1u << sb) - 1u))];
+					if (INF_KIND(d) == INF_K_LINK) {
 						err = OTZ_ST_DATA;
 						break;
 					}
 				}
-				br.consume(d & 15u);
-				const uint32_t dsym = d >> 6;
-				uint32_t dist, dxb;
-				if (dsym < 4) {
-					dist = 1 + dsym;
-					dxb = 0;
-				} else {
-					dxb = (dsym - 2) >> 1;
-					dist = 1 + ((2 + (dsym & 1)) << dxb);
-				}
-				dist += (uint32_t)br.bb & ((1u << dxb) - 1u);
-				br.consume(dxb);
-				INF_FLUSH_LITS();
-				if (dist > op) {
+				const uint32_t db = d & 31u, dxb = (d >> 5) & 15u;
+				const uint32_t dist = (d >> 16) + (((uint32_t)(br.bb >> db)) & ((1u << dxb) - 1u));
+				br.consume(db + dxb);
+				const uint32_t dq = ring.q;
+				if (dist > dq - ring.mis) {
 					err = OTZ_ST_DATA;  // reaches before the start of the output (dec:785 does not check; strict)
 					break;
 				}
-				if (length > cap - op) {
+				if (slow && length > qcap - dq) {
 					err = OTZ_ST_OVERFLOW;  // dec:535-541, :791-793
 					break;
 				}
-				tile.sync();  // earlier stores of this tile are visible to the loads below
-				uint8_t *dp = out + op;
-				const uint8_t *sp = dp - dist;
-				if (dist >= length) {
-					for (uint32_t i = lane; i < length; i += G) {
-						dp[i] = sp[i];
+				tile.sync();  // earlier ring stores of this tile are visible to the loads below
+				if (dist + length <= (uint32_t)W) {
+					const uint32_t sq = dq - dist;
+					if (dist >= length) {
+						for (uint32_t i = lane; i < length; i += G) {
+							rb[(dq + i) & MASK] = rb[(sq + i) & MASK];
+						}
+					} else {
+						// overlapping copy = periodic extension of the last `dist` bytes (dec:521-533)
+						uint32_t r = dist > (uint32_t)lane ? (uint32_t)lane : (uint32_t)lane % dist;
+						const uint32_t step = dist > (uint32_t)G ? (uint32_t)G : (uint32_t)G % dist;
+						for (uint32_t i = lane; i < length; i += G) {
+							rb[(dq + i) & MASK] = rb[(sq + r) & MASK];
+							r += step;
+							r = r >= dist ? r - dist : r;
+						}
 					}
 				} else {
-					// overlapping copy = periodic extension of the last `dist` bytes (dec:521-533)
-					uint32_t r = dist > (uint32_t)lane ? (uint32_t)lane : (uint32_t)lane % dist;
-					const uint32_t step = dist > (uint32_t)G ? (uint32_t)G : (uint32_t)G % dist;
+					// far back-reference: the source left the ring and is in HBM already (dist > W - 258 >= length)
+					const uint8_t *sp = ring.gbase + (dq - dist);
 					for (uint32_t i = lane; i < length; i += G) {
-						dp[i] = sp[r];
-						r += step;
-						r = r >= dist ? r - dist : r;
+						rb[(dq + i) & MASK] = sp[i];
 					}
 				}
-				op += length;
+				ring.q = dq + length;
+			} else {
+				br.consume(cb);
+				eob = true;
+				break;  // dec:711-716
 			}
-			INF_STEP_CHECK();
+			ring.maybe_flush(tile, lane);
+			if (slow) {
+				INF_STEP_CHECK();
+			}
 		}
 		if (err) {
 			break;
@@ -582,9 +673,9 @@ __device__ __forceinline__ int32_t inflate_stream(const Tile &tile, InflateSmem 
 		}
 		INF_STEP_CHECK();
 	}
-	INF_FLUSH_LITS();
 #undef INF_STEP_CHECK
-#undef INF_FLUSH_LITS
+	ring.finish(tile, lane);
+	const uint32_t op = ring.produced();
 	*produced = op;
 	if (err) {
 		return err;
@@ -593,14 +684,14 @@ __device__ __forceinline__ int32_t inflate_stream(const Tile &tile, InflateSmem 
 }
 
 // grid: persistent; each tile pulls the next entry of `list` (largest first) from a global counter.
-template <int G>
+template <int G, int W>
 __global__ void __launch_bounds__(256) k_inflate(const uint8_t *__restrict__ archive, uint8_t *__restrict__ out,
 	const otz_entry *__restrict__ ents, const OtzEntryState *__restrict__ est, int32_t *__restrict__ status,
 	const uint32_t *__restrict__ list, uint32_t n_list, uint32_t *__restrict__ work_counter) {
 	extern __shared__ __align__(16) uint8_t smem_raw[];
 	auto tile = cg::tiled_partition<G>(cg::this_thread_block());
 	const int lane = tile.thread_rank();
-	InflateSmem &S = reinterpret_cast<InflateSmem *>(smem_raw)[threadIdx.x / G];
+	InflateSmemV2<G, W> &S = reinterpret_cast<InflateSmemV2<G, W> *>(smem_raw)[threadIdx.x / G];
 	for (;;) {
 		uint32_t k = 0;
 		if (lane == 0) {
@@ -617,7 +708,7 @@ __global__ void __launch_bounds__(256) k_inflate(const uint8_t *__restrict__ arc
 		const otz_entry e = ents[ei];
 		uint8_t *dst = out + e.out_ofs;
 		uint32_t produced = 0;
-		int32_t st = inflate_stream<G>(tile, S, archive + est[ei].data_ofs, e.comp_size, dst, e.uncomp_size, &produced);
+		int32_t st = inflate_stream<G, W>(tile, S, archive + est[ei].data_ofs, e.comp_size, dst, e.uncomp_size, &produced);
 		if (OTZ_ST_CODE(st) == OTZ_ST_OK && produced < e.uncomp_size) {
 			// otezip.c:500 pre-zeroes the buffer and never compares total_out: short streams are zero-padded
 			for (uint64_t i = (uint64_t)produced + lane; i < e.uncomp_size; i += G) {

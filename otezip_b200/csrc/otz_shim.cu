@@ -43,7 +43,8 @@ struct otz_ctx {
 	uint8_t *d_flush;
 	uint64_t flush_bytes;
 	uint64_t launches;
-	int inflate_tile;   // lanes per DEFLATE stream (OTZ_INFLATE_TILE, default 32)
+	int inflate_tile;   // lanes per DEFLATE stream (OTZ_INFLATE_TILE; 0 = per batch)
+	int inflate_ring;   // bytes of shared-memory output ring per stream (OTZ_INFLATE_RING; 0 = per batch)
 };
 
 struct otz_plan {
@@ -156,11 +157,10 @@ extern "C" int otz_ctx_create(int device, otz_ctx **out) {
 	CK(cudaMalloc(&c->d_tabs, sizeof(OtzCrcTables)));
 	CK(cudaMemcpy(c->d_tabs, h, sizeof(OtzCrcTables), cudaMemcpyHostToDevice));
 	delete h;
-	const char *t = getenv("OTZ_INFLATE_TILE");
-	c->inflate_tile = t ? atoi(t) : 32;
-	if (c->inflate_tile != 4 && c->inflate_tile != 8 && c->inflate_tile != 16 && c->inflate_tile != 32) {
-		c->inflate_tile = 32;
-	}
+	const char *t = getenv("OTZ_INFLATE_TILE");   // 0 / unset: chosen per batch
+	c->inflate_tile = t ? atoi(t) : 0;
+	t = getenv("OTZ_INFLATE_RING");
+	c->inflate_ring = t ? atoi(t) : 0;
 	*out = c;
 	return OTZ_SUCCESS;
 }
@@ -388,29 +388,59 @@ extern "C" int otz_plan_create(otz_ctx *c, const otz_entry *ents, uint32_t n, co
 	return OTZ_SUCCESS;
 }
 
-template <int G>
+template <int G, int W>
 static int launch_inflate(otz_ctx *c, otz_plan *p, const uint8_t *d_archive, uint8_t *d_out) {
-	const int threads = 256;
-	const size_t smem = (threads / G) * sizeof(InflateSmem);
+	const int threads = 8 * G;   // 8 streams per CTA
+	const size_t smem = 8 * sizeof(InflateSmemV2<G, W>);
 	static bool attr_done = false;
 	if (!attr_done) {
-		CK(cudaFuncSetAttribute(k_inflate<G>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+		CK(cudaFuncSetAttribute(k_inflate<G, W>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
 		attr_done = true;
 	}
 	int per_sm = 0;
-	CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_inflate<G>, threads, smem));
+	CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_inflate<G, W>, threads, smem));
 	if (per_sm < 1) {
-		per_sm = 1;
+		snprintf(g_err, sizeof(g_err), "k_inflate<%d,%d> does not fit an SM (%zu bytes of shared memory)", G, W, smem);
+		return OTZ_ERR_CUDA;
 	}
 	const uint32_t tiles_per_cta = threads / G;
 	uint32_t grid = (uint32_t)(c->sm_count * per_sm);
 	const uint32_t want = (p->n_inflate + tiles_per_cta - 1) / tiles_per_cta;
 	grid = std::max(1u, std::min(grid, want));
-	k_inflate<G><<<grid, threads, smem, c->stream>>>(d_archive, d_out, p->d_ents, p->d_est, p->d_status, p->d_inflate_list,
+	k_inflate<G, W><<<grid, threads, smem, c->stream>>>(d_archive, d_out, p->d_ents, p->d_est, p->d_status, p->d_inflate_list,
 		p->n_inflate, p->d_counter);
 	c->launches++;
 	CK(cudaGetLastError());
 	return OTZ_SUCCESS;
+}
+
+// Lanes per stream and ring size.  Few streams: a whole warp and a 16 KiB ring per stream (latency);
+// many streams: narrow tiles and small rings so that more streams are resident per SM (throughput).
+static int dispatch_inflate(otz_ctx *c, otz_plan *p, const uint8_t *d_archive, uint8_t *d_out) {
+	int g = c->inflate_tile, w = c->inflate_ring;
+	if (g == 0) {
+		g = p->n_inflate <= (uint32_t)c->sm_count * 10u ? 32 : 8;
+	}
+	if (w == 0) {
+		w = g == 32 ? (p->n_inflate <= (uint32_t)c->sm_count * 10u ? 16384 : 2048) : 2048;
+	}
+#define OTZ_INF_CASE(G_, W_)        \
+	if (g == G_ && w == W_) {       \
+		return launch_inflate<G_, W_>(c, p, d_archive, d_out); \
+	}
+	OTZ_INF_CASE(32, 16384)
+	OTZ_INF_CASE(32, 4096)
+	OTZ_INF_CASE(32, 2048)
+	OTZ_INF_CASE(16, 4096)
+	OTZ_INF_CASE(16, 2048)
+	OTZ_INF_CASE(8, 4096)
+	OTZ_INF_CASE(8, 2048)
+	OTZ_INF_CASE(8, 1024)
+	OTZ_INF_CASE(4, 2048)
+	OTZ_INF_CASE(4, 1024)
+#undef OTZ_INF_CASE
+	snprintf(g_err, sizeof(g_err), "unsupported OTZ_INFLATE_TILE/OTZ_INFLATE_RING combination %d/%d", g, w);
+	return OTZ_ERR_ARG;
 }
 
 extern "C" int otz_extract_run(otz_ctx *c, otz_plan *p, const uint8_t *d_archive, uint64_t archive_len, uint8_t *d_out,
@@ -450,13 +480,7 @@ extern "C" int otz_extract_run(otz_ctx *c, otz_plan *p, const uint8_t *d_archive
 		c->launches++;
 	}
 	if (p->n_inflate) {
-		int rc;
-		switch (c->inflate_tile) {
-		case 4: rc = launch_inflate<4>(c, p, d_archive, d_out); break;
-		case 8: rc = launch_inflate<8>(c, p, d_archive, d_out); break;
-		case 16: rc = launch_inflate<16>(c, p, d_archive, d_out); break;
-		default: rc = launch_inflate<32>(c, p, d_archive, d_out); break;
-		}
+		int rc = dispatch_inflate(c, p, d_archive, d_out);
 		if (rc) {
 			return rc;
 		}
