@@ -56,6 +56,7 @@ struct OtzCrcTables {
 	uint32_t x2n[32];         // x^(2^k) mod P
 	uint32_t xp8[1024 + 64];  // xp8[k + OTZ_XP8_BIAS] = x^(8k) mod P for k in [-OTZ_XP8_BIAS, 1024+64-BIAS)
 	uint32_t t0[256];         // plain byte table
+	uint32_t x_inv_fold;      // x^(-8 * 512 * FOLD_K): undoes the zero rows the fold path appends
 };
 #define OTZ_XP8_BIAS 528
 

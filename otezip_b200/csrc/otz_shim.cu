@@ -115,6 +115,10 @@ static void build_crc_tables(OtzCrcTables *t) {
 	for (int k = OTZ_XP8_BIAS - 1; k >= 0; k--) {
 		t->xp8[k] = h_mulmod(t->xp8[k + 1], x8inv);
 	}
+	t->x_inv_fold = 0x80000000u;
+	for (int k = 0; k < 512 * FOLD_K; k++) {
+		t->x_inv_fold = h_mulmod(t->x_inv_fold, x8inv);
+	}
 }
 
 // ---------------------------------------------------------------- context
@@ -291,6 +295,16 @@ extern "C" int otz_flush_l2(otz_ctx *c) {
 }
 
 // ---------------------------------------------------------------- read path
+static uint32_t crc_ctas_per_sm() {
+	static int per_sm = 0;
+	if (!per_sm) {
+		if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_crc_chunks, 256, 0) != cudaSuccess || per_sm < 1) {
+			per_sm = 1;
+		}
+	}
+	return (uint32_t)per_sm;
+}
+
 template <typename T>
 static int upload(T **d, const std::vector<T> &h, cudaStream_t s) {
 	*d = nullptr;
@@ -489,8 +503,8 @@ extern "C" int otz_extract_run(otz_ctx *c, otz_plan *p, const uint8_t *d_archive
 		CK(cudaEventRecord(pev[2], s));
 	}
 	if (p->n_chunks) {
-		// 4 CTAs x 256 threads per SM (16 KiB of tables each)
-		const uint32_t grid = std::min((uint32_t)c->sm_count * 4, (p->n_chunks + 7) / 8);
+		// persistent: exactly the resident CTAs (register-limited), each striding over the chunk list
+		const uint32_t grid = std::min((uint32_t)c->sm_count * crc_ctas_per_sm(), (p->n_chunks + 7) / 8);
 		k_crc_chunks<<<grid, 256, 0, s>>>(d_archive, d_out, p->d_ents, p->d_est, p->d_status, p->d_chunks, p->n_chunks, p->d_acc, c->d_tabs,
 			p->opts.verify_only);
 		c->launches++;
@@ -716,7 +730,7 @@ extern "C" int otz_deflate_run(otz_ctx *c, otz_deflate_job *j, const uint8_t *d_
 	CK(cudaMemsetAsync(j->d_counter, 0, 64, s));
 	CK(cudaMemsetAsync(j->d_acc, 0, (size_t)n * 4, s));
 	if (j->n_crc_chunks) {
-		const uint32_t grid = std::min((uint32_t)c->sm_count * 4, (j->n_crc_chunks + 7) / 8);
+		const uint32_t grid = std::min((uint32_t)c->sm_count * crc_ctas_per_sm(), (j->n_crc_chunks + 7) / 8);
 		k_crc_chunks<<<grid, 256, 0, s>>>(nullptr, d_in, j->d_crc_ents, j->d_est, j->d_status, j->d_crc_chunks, j->n_crc_chunks, j->d_acc,
 			c->d_tabs, 0);
 		c->launches++;
