@@ -56,63 +56,67 @@ struct __align__(16) InflateSmem {
 __constant__ uint8_t c_cl_order[19] = { 16, 17, 18, 0, 8, 7, 9, 6, 10, 5, 11, 4, 12, 3, 13, 2, 14, 1, 15 };  // dec:146-148
 
 // ------------------------------------------------------------------------------------------------
-// Bit reader: every lane carries an identical copy of (bb, nb); the input window is spread over lanes.
+// Bit reader.  Every lane carries an identical copy of a 64-bit window {hi:lo} of the stream and a bit
+// offset `pos` into it; the next 32 stream bits are one funnel shift away (peek), consuming is one add
+// (skip).  When pos reaches 32 the window slides by one word (norm); that word comes from a register
+// window of G words spread over the lanes (tile shuffle), refilled by one coalesced load per G words
+// with the following window already in flight.
 template <int G>
 struct BitReader {
 	const uint32_t *words;   // aligned base of the current stream position
 	uint32_t n_words;        // words available from `words`
 	uint32_t win_base;       // word index of win_cur[lane 0]
 	uint32_t win_cur, win_next;
-	uint32_t widx;           // next word of the current window to consume
-	int32_t words_left;      // words not yet moved into bb (negative once past the end)
+	uint32_t widx;           // next word of the current window to hand out
+	int32_t words_left;      // words not yet moved into {hi:lo} (negative once past the end)
 	uint32_t pad_bits;       // bits in the last word that lie beyond the stream end
-	uint64_t bb;
-	uint32_t nb;
+	uint32_t lo, hi, pos;
 
 	__device__ __forceinline__ uint32_t load(uint32_t idx) const { return idx < n_words ? __ldg(words + idx) : 0u; }
 
 	template <typename Tile>
+	__device__ __forceinline__ uint32_t next_word(const Tile &tile) {
+		const uint32_t w = tile.shfl(win_cur, widx);
+		words_left--;
+		if (++widx == G) {
+			widx = 0;
+			win_base += G;
+			win_cur = win_next;
+			win_next = load(win_base + G + tile.thread_rank());
+		}
+		return w;
+	}
+	template <typename Tile>
 	__device__ __forceinline__ void init(const Tile &tile, const uint8_t *p, uint64_t nbytes) {
 		const uint64_t a = reinterpret_cast<uint64_t>(p);
-		const uint32_t skip = (uint32_t)(a & 3);
-		words = reinterpret_cast<const uint32_t *>(a - skip);
-		n_words = (uint32_t)((skip + nbytes + 3) >> 2);
-		pad_bits = (uint32_t)(((uint64_t)n_words << 5) - ((skip + nbytes) << 3));
+		const uint32_t skipb = (uint32_t)(a & 3);
+		words = reinterpret_cast<const uint32_t *>(a - skipb);
+		n_words = (uint32_t)((skipb + nbytes + 3) >> 2);
+		pad_bits = (uint32_t)(((uint64_t)n_words << 5) - ((skipb + nbytes) << 3));
 		win_base = 0;
 		const int lane = tile.thread_rank();
 		win_cur = load(lane);
 		win_next = load(G + lane);
 		widx = 0;
 		words_left = (int32_t)n_words;
-		bb = 0;
-		nb = 0;
-		refill(tile);
-		bb >>= 8 * skip;
-		nb -= 8 * skip;
+		lo = next_word(tile);
+		hi = next_word(tile);
+		pos = 8 * skipb;
 	}
-	// after this nb >= 33
+	// afterwards pos < 32: at least 33 bits can be peeked/skipped before the next norm
 	template <typename Tile>
-	__device__ __forceinline__ void refill(const Tile &tile) {
-		if (nb <= 32) {
-			const uint32_t w = tile.shfl(win_cur, widx);
-			bb |= (uint64_t)w << nb;
-			nb += 32;
-			words_left--;
-			if (++widx == G) {
-				widx = 0;
-				win_base += G;
-				win_cur = win_next;
-				win_next = load(win_base + G + tile.thread_rank());
-			}
+	__device__ __forceinline__ void norm(const Tile &tile) {
+		if (pos >= 32) {
+			lo = hi;
+			hi = next_word(tile);
+			pos -= 32;
 		}
 	}
-	__device__ __forceinline__ void consume(uint32_t n) {
-		bb >>= n;
-		nb -= n;
-	}
+	__device__ __forceinline__ uint32_t peek() const { return __funnelshift_r(lo, hi, pos); }   // needs pos < 32
+	__device__ __forceinline__ void skip(uint32_t n) { pos += n; }
 	// bits of the stream not yet consumed (negative: read past the end)
 	__device__ __forceinline__ int64_t remaining_bits() const {
-		return ((int64_t)words_left << 5) + (int64_t)nb - (int64_t)pad_bits;
+		return ((int64_t)words_left << 5) + 64 - (int64_t)pos - (int64_t)pad_bits;
 	}
 };
 
@@ -299,9 +303,10 @@ __device__ __noinline__ int build_fixed(const Tile &tile, InflateSmem &S) {
 template <int G, typename Tile>
 __device__ __forceinline__ int read_dynamic(const Tile &tile, InflateSmem &S, BitReader<G> &br) {
 	const int lane = tile.thread_rank();
-	br.refill(tile);
-	const int hlit = (int)(br.bb & 31) + 257, hdist = (int)((br.bb >> 5) & 31) + 1, hclen = (int)((br.bb >> 10) & 15) + 4;
-	br.consume(14);
+	br.norm(tile);
+	uint32_t bits = br.peek();
+	const int hlit = (int)(bits & 31) + 257, hdist = (int)((bits >> 5) & 31) + 1, hclen = (int)((bits >> 10) & 15) + 4;
+	br.skip(14);
 	if (hlit > 286 || hdist > 30) {
 		return 1;  // RFC 1951 limits; dec:165-168 would overflow its scratch instead
 	}
@@ -311,9 +316,9 @@ __device__ __forceinline__ int read_dynamic(const Tile &tile, InflateSmem &S, Bi
 	tile.sync();
 	uint64_t cnt = 0;  // packed byte counters, cnt>>(8*l) & 0xFF = number of precode symbols of length l
 	for (int i = 0; i < hclen; i++) {
-		br.refill(tile);
-		const uint32_t v = (uint32_t)br.bb & 7u;
-		br.consume(3);
+		br.norm(tile);
+		const uint32_t v = br.peek() & 7u;
+		br.skip(3);
 		if (lane == 0) {
 			S.lens[c_cl_order[i]] = (uint8_t)v;
 		}
@@ -357,11 +362,12 @@ __device__ __forceinline__ int read_dynamic(const Tile &tile, InflateSmem &S, Bi
 	int idx = 0;
 	uint32_t prev = 0;
 	while (idx < total) {
-		br.refill(tile);
-		const uint32_t e = S.pre[(uint32_t)br.bb & 127u];
-		const uint32_t sym = e & 31u;
-		br.consume(e >> 5);
+		br.norm(tile);
+		bits = br.peek();
+		const uint32_t e = S.pre[bits & 127u];
+		const uint32_t sym = e & 31u, cl = e >> 5;
 		if (sym < 16) {
+			br.skip(cl);
 			if (lane == 0) {
 				S.lens[idx] = (uint8_t)sym;
 			}
@@ -376,14 +382,14 @@ __device__ __forceinline__ int read_dynamic(const Tile &tile, InflateSmem &S, Bi
 				return 1;
 			}
 			val = prev;
-			rep = 3 + (int)((uint32_t)br.bb & 3u);
-			br.consume(2);
+			rep = 3 + (int)((bits >> cl) & 3u);
+			br.skip(cl + 2);
 		} else if (sym == 17) {  // dec:221-228
-			rep = 3 + (int)((uint32_t)br.bb & 7u);
-			br.consume(3);
+			rep = 3 + (int)((bits >> cl) & 7u);
+			br.skip(cl + 3);
 		} else {  // dec:230-237
-			rep = 11 + (int)((uint32_t)br.bb & 127u);
-			br.consume(7);
+			rep = 11 + (int)((bits >> cl) & 127u);
+			br.skip(cl + 7);
 		}
 		if (idx + rep > total) {
 			return 1;  // dec:244
@@ -473,6 +479,96 @@ struct OutRing {
 	}
 };
 
+// One literal / end-of-block / length+distance step (dec:662-799).  CHECKED adds the tests that only matter
+// near the end of the input or of the output buffer.  Returns 0 = continue, 1 = end of block, <0 = -status.
+template <int G, int W, bool CHECKED, typename Tile>
+__device__ __forceinline__ int inflate_event(const Tile &tile, const InflateSmem &S, BitReader<G> &br, OutRing<G, W> &ring, uint8_t *rb,
+	uint32_t qcap, int lane) {
+	constexpr uint32_t MASK = W - 1;
+	uint32_t bits = br.peek();
+	uint32_t e = S.lit[bits & ((1u << INF_LIT_ROOT) - 1u)];
+	uint32_t cb = e & 31u;
+	if (INF_KIND(e) == INF_K_LINK) {
+		if (cb == 0) {
+			return -OTZ_ST_DATA;  // dec:693-695: no code matches
+		}
+		e = S.lit[(e >> 16) + ((bits >> INF_LIT_ROOT) & ((1u << cb) - 1u))];
+		if (INF_KIND(e) == INF_K_LINK) {
+			return -OTZ_ST_DATA;
+		}
+		cb = (e & 31u) + INF_LIT_ROOT;
+	}
+	if (INF_KIND(e) == INF_K_LIT) {
+		br.skip(cb);
+		if (CHECKED && ring.q >= qcap) {
+			return -OTZ_ST_OVERFLOW;  // dec:700-703
+		}
+		if (lane == 0) {
+			rb[ring.q & MASK] = (uint8_t)(e >> 16);
+		}
+		ring.q++;
+		return 0;
+	}
+	if (INF_KIND(e) == INF_K_EOB) {
+		br.skip(cb);
+		return 1;  // dec:711-716
+	}
+	// length (dec:720-737), then distance (dec:740-782)
+	const uint32_t xb = (e >> 5) & 15u;
+	const uint32_t length = (e >> 16) + ((bits >> cb) & ((1u << xb) - 1u));
+	br.skip(cb + xb);
+	br.norm(tile);
+	bits = br.peek();
+	uint32_t d = S.dst[bits & ((1u << INF_DST_ROOT) - 1u)];
+	uint32_t db = d & 31u;
+	if (INF_KIND(d) == INF_K_LINK) {
+		if (db == 0) {
+			return -OTZ_ST_DATA;  // dec:762-764
+		}
+		d = S.dst[(d >> 16) + ((bits >> INF_DST_ROOT) & ((1u << db) - 1u))];
+		if (INF_KIND(d) == INF_K_LINK) {
+			return -OTZ_ST_DATA;
+		}
+		db = (d & 31u) + INF_DST_ROOT;
+	}
+	const uint32_t dxb = (d >> 5) & 15u;
+	const uint32_t dist = (d >> 16) + ((bits >> db) & ((1u << dxb) - 1u));
+	br.skip(db + dxb);
+	const uint32_t dq = ring.q;
+	if (dist > dq - ring.mis) {
+		return -OTZ_ST_DATA;  // reaches before the start of the output (dec:785 does not check; strict)
+	}
+	if (CHECKED && length > qcap - dq) {
+		return -OTZ_ST_OVERFLOW;  // dec:535-541, :791-793
+	}
+	tile.sync();  // earlier ring stores of this tile are visible to the loads below
+	if (dist + length <= (uint32_t)W) {
+		const uint32_t sq = dq - dist;
+		if (dist >= length) {
+			for (uint32_t i = lane; i < length; i += G) {
+				rb[(dq + i) & MASK] = rb[(sq + i) & MASK];
+			}
+		} else {
+			// overlapping copy = periodic extension of the last `dist` bytes (dec:521-533)
+			uint32_t r = dist > (uint32_t)lane ? (uint32_t)lane : (uint32_t)lane % dist;
+			const uint32_t step = dist > (uint32_t)G ? (uint32_t)G : (uint32_t)G % dist;
+			for (uint32_t i = lane; i < length; i += G) {
+				rb[(dq + i) & MASK] = rb[(sq + r) & MASK];
+				r += step;
+				r = r >= dist ? r - dist : r;
+			}
+		}
+	} else {
+		// far back-reference: the source left the ring and is in HBM already (dist > W - 258 >= length)
+		const uint8_t *sp = ring.gbase + (dq - dist);
+		for (uint32_t i = lane; i < length; i += G) {
+			rb[(dq + i) & MASK] = sp[i];
+		}
+	}
+	ring.q = dq + length;
+	return 0;
+}
+
 // Decode one raw stream.  Returns the status word; *produced = bytes written.
 template <int G, int W, typename Tile>
 __device__ __forceinline__ int32_t inflate_stream(const Tile &tile, InflateSmemV2<G, W> &SS, const uint8_t *__restrict__ in, uint32_t comp,
@@ -509,10 +605,11 @@ __device__ __forceinline__ int32_t inflate_stream(const Tile &tile, InflateSmemV
 
 	for (;;) {
 		// ---- block header, dec:613-627
-		br.refill(tile);
-		const uint32_t final_blk = (uint32_t)br.bb & 1u;
-		const uint32_t btype = ((uint32_t)br.bb >> 1) & 3u;
-		br.consume(3);
+		br.norm(tile);
+		const uint32_t hdr = br.peek();
+		const uint32_t final_blk = hdr & 1u;
+		const uint32_t btype = (hdr >> 1) & 3u;
+		br.skip(3);
 		INF_STEP_CHECK();
 		if (btype == 0) {
 			// ---- stored block, dec:269-319
@@ -560,110 +657,43 @@ __device__ __forceinline__ int32_t inflate_stream(const Tile &tile, InflateSmemV
 			break;
 		}
 		INF_STEP_CHECK();
-		// ---- symbols, dec:662-799.  One loop; the per-step checks that only matter near the end of the
-		// input or of the output buffer are skipped while both are far away (`slow` is false).
+		// ---- symbols.  An event consumes at most 48 bits (two window words) and produces at most 258 bytes, so
+		// `budget` events can run without any end-of-input / end-of-output test; the rest run one by one.
 		bool eob = false;
-		const uint32_t qfast = qcap >= 258u ? qcap - 258u : 0u;
 		for (;;) {
-			br.refill(tile);
-			const bool slow = br.words_left <= 1 || ring.q > qfast;
-			uint32_t e = S.lit[(uint32_t)br.bb & ((1u << INF_LIT_ROOT) - 1u)];
-			if (INF_KIND(e) == INF_K_LINK) {
-				const uint32_t sb = e & 31u;
-				if (sb == 0) {
-					err = OTZ_ST_DATA;  // dec:693-695: no code matches
+			int64_t budget = min(((int64_t)br.words_left - 2) >> 1, (int64_t)((qcap - ring.q) / 258u));
+			budget = min(budget, (int64_t)1 << 20);
+			int rc = 0;
+			for (int32_t n = (int32_t)budget; n > 0; n--) {
+				br.norm(tile);
+				rc = inflate_event<G, W, false>(tile, S, br, ring, rb, qcap, lane);
+				if (rc) {
 					break;
 				}
-				br.consume(INF_LIT_ROOT);
-				e = S.lit[(e >> 16) + ((uint32_t)br.bb & ((1u << sb) - 1u))];
-				if (INF_KIND(e) == INF_K_LINK) {
-					err = OTZ_ST_DATA;
-					break;
+				ring.maybe_flush(tile, lane);
+			}
+			if (rc == 0 && budget <= 0) {
+				br.norm(tile);
+				rc = inflate_event<G, W, true>(tile, S, br, ring, rb, qcap, lane);
+				if (rc == 0) {
+					ring.maybe_flush(tile, lane);
+					INF_STEP_CHECK();
 				}
 			}
-			const uint32_t cb = e & 31u;
-			if (INF_KIND(e) == INF_K_LIT) {
-				br.consume(cb);
-				if (slow && ring.q >= qcap) {
-					err = OTZ_ST_OVERFLOW;  // dec:700-703
-					break;
-				}
-				if (lane == 0) {
-					rb[ring.q & MASK] = (uint8_t)(e >> 16);
-				}
-				ring.q++;
-			} else if (INF_KIND(e) == INF_K_LEN) {
-				// length (dec:720-737), then distance (dec:740-782)
-				const uint32_t xb = (e >> 5) & 15u;
-				const uint32_t length = (e >> 16) + (((uint32_t)(br.bb >> cb)) & ((1u << xb) - 1u));
-				br.consume(cb + xb);
-				br.refill(tile);
-				uint32_t d = S.dst[(uint32_t)br.bb & ((1u << INF_DST_ROOT) - 1u)];
-				if (INF_KIND(d) == INF_K_LINK) {
-					const uint32_t sb = d & 31u;
-					if (sb == 0) {
-						err = OTZ_ST_DATA;  // dec:762-764
-						break;
-					}
-					br.consume(INF_DST_ROOT);
-					d = S.dst[(d >> 16) + ((uint32_t)br.bb & ((1u << sb) - 1u))];
-					if (INF_KIND(d) == INF_K_LINK) {
-						err = OTZ_ST_DATA;
-						break;
-					}
-				}
-				const uint32_t db = d & 31u, dxb = (d >> 5) & 15u;
-				const uint32_t dist = (d >> 16) + (((uint32_t)(br.bb >> db)) & ((1u << dxb) - 1u));
-				br.consume(db + dxb);
-				const uint32_t dq = ring.q;
-				if (dist > dq - ring.mis) {
-					err = OTZ_ST_DATA;  // reaches before the start of the output (dec:785 does not check; strict)
-					break;
-				}
-				if (slow && length > qcap - dq) {
-					err = OTZ_ST_OVERFLOW;  // dec:535-541, :791-793
-					break;
-				}
-				tile.sync();  // earlier ring stores of this tile are visible to the loads below
-				if (dist + length <= (uint32_t)W) {
-					const uint32_t sq = dq - dist;
-					if (dist >= length) {
-						for (uint32_t i = lane; i < length; i += G) {
-							rb[(dq + i) & MASK] = rb[(sq + i) & MASK];
-						}
-					} else {
-						// overlapping copy = periodic extension of the last `dist` bytes (dec:521-533)
-						uint32_t r = dist > (uint32_t)lane ? (uint32_t)lane : (uint32_t)lane % dist;
-						const uint32_t step = dist > (uint32_t)G ? (uint32_t)G : (uint32_t)G % dist;
-						for (uint32_t i = lane; i < length; i += G) {
-							rb[(dq + i) & MASK] = rb[(sq + r) & MASK];
-							r += step;
-							r = r >= dist ? r - dist : r;
-						}
-					}
-				} else {
-					// far back-reference: the source left the ring and is in HBM already (dist > W - 258 >= length)
-					const uint8_t *sp = ring.gbase + (dq - dist);
-					for (uint32_t i = lane; i < length; i += G) {
-						rb[(dq + i) & MASK] = sp[i];
-					}
-				}
-				ring.q = dq + length;
-			} else {
-				br.consume(cb);
+			if (rc > 0) {
 				eob = true;
-				break;  // dec:711-716
+				break;
 			}
-			ring.maybe_flush(tile, lane);
-			if (slow) {
-				INF_STEP_CHECK();
+			if (rc < 0) {
+				err = -rc;
+				break;
 			}
 		}
 		if (err) {
 			break;
 		}
 		if (!eob) {
-			break;  // left the symbol loop through INF_STEP_CHECK's break with err set
+			break;  // INF_STEP_CHECK left the loop with err set
 		}
 		if (final_blk) {
 			if (br.remaining_bits() < 0) {
