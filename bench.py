@@ -318,11 +318,119 @@ def run_reference(args, dist: Dist):
         "gpu_launches": 0}))
 
 
+def run_c5(args, dist: "Dist"):
+    """configs[4]: archive creation — batched DEFLATE compress + CRC-32 of a synthetic corpus (default 16,384 x 256 KiB
+    JSON-log = 4 GiB), device-timed; every stream verified (zlib on all entries, the compiled reference on a sample)."""
+    import ctypes as C
+    from otezip_b200 import Ctx, synth
+    ctx = Ctx(dist.local)
+    n = args.entries or 16384
+    size = 262144
+    pool = synth.TextPool(64 << 20, seed=5 + 7919 * dist.rank)
+    stride = size
+    img = ctx.pinned(n * stride)
+    srcs = []
+    for i in range(n):
+        d = pool.take(size)
+        img[i * stride:(i + 1) * stride] = np.frombuffer(d, dtype=np.uint8)
+        srcs.append(d)
+    in_ofs = np.arange(n, dtype=np.uint64) * stride
+    in_len = np.full(n, size, dtype=np.uint32)
+    meth = np.full(n, 8, dtype=np.uint16)
+    d_in = ctx.dev_alloc(img.nbytes)
+    ctx.h2d(d_in, img)
+    job = ctx.deflate_plan(in_ofs, in_len, meth)
+    ctx.sync()
+    sampler = ClockSampler(ctx.pci_bus_id())
+    sampler.start()
+    for _ in range(args.warmup):
+        ctx.deflate_run(job, d_in, img.nbytes)
+    ctx.sync()
+    dist.barrier()
+    ctx.sync()
+    l0 = ctx.launches()
+    sampler.mark()
+    ctx.timer_start()
+    for _ in range(args.steps):
+        ctx.deflate_run(job, d_in, img.nbytes)
+    ms = ctx.timer_stop()
+    sampler.mark()
+    dist.barrier()
+    launches = ctx.launches() - l0
+    ofs, sz, crc, m, total = ctx.deflate_results(job, n)
+    out = ctx.deflate_fetch(job, total)
+    # verification: every stream through zlib, CRCs against zlib.crc32, a sample through the compiled reference
+    def chk(i):
+        p = bytes(out[int(ofs[i]):int(ofs[i]) + int(sz[i])])
+        ok = (zlib.decompress(p, -15) if m[i] == 8 else p) == srcs[i] and int(crc[i]) == (zlib.crc32(srcs[i]) & 0xFFFFFFFF)
+        return ok
+    with cf.ThreadPoolExecutor(os.cpu_count() or 4) as ex:
+        n_ok = sum(ex.map(chk, range(n)))
+    ref_ok = None
+    try:
+        from oracle import RefLib
+        k = min(n, 32)
+        ms_ = [synth.Member("f%d" % i, int(m[i]), bytes(out[int(ofs[i]):int(ofs[i]) + int(sz[i])]), size, int(crc[i])) for i in range(k)]
+        err, got = RefLib().extract_bytes(synth.build_zip(ms_), verify_crc=1)
+        ref_ok = err == 0 and got == srcs[:k]
+    except Exception as e:  # pragma: no cover
+        ref_ok = "unavailable: %r" % e
+    if n_ok != n or ref_ok is False:
+        raise SystemExit("bench c5: %d/%d streams verified, reference sample ok=%s" % (n_ok, n, ref_ok))
+    # e2e: host buffers through otz_deflate_host
+    e2e_steps = args.e2e_steps or 3
+    o_ofs = np.zeros(n, dtype=np.uint64); o_sz = np.zeros(n, dtype=np.uint32); o_crc = np.zeros(n, dtype=np.uint32)
+    o_m = np.zeros(n, dtype=np.uint16); tot = C.c_uint64()
+    out_host = ctx.pinned(img.nbytes)
+    vp = lambda a: a.ctypes.data_as(C.c_void_p)
+    def e2e_step():
+        ctx.lib.check(ctx.L.otz_deflate_host(ctx.h, vp(img), img.nbytes, vp(in_ofs), vp(in_len), vp(meth), n, vp(out_host), out_host.nbytes,
+                                             vp(o_ofs), vp(o_sz), vp(o_crc), vp(o_m), C.byref(tot)), "otz_deflate_host")
+    e2e_step()
+    dist.barrier(); ctx.sync()
+    t0 = time.perf_counter()
+    for _ in range(e2e_steps):
+        e2e_step()
+    ctx.sync()
+    e2e_s = time.perf_counter() - t0
+    sampler.stop_ev.set(); sampler.join(timeout=2)
+    ms_max = dist.max(ms)
+    tot_in = dist.sum(float(n * size))
+    e2e_max = dist.max(e2e_s)
+    if dist.rank == 0:
+        peaks = {}
+        try:
+            peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+        except Exception:
+            pass
+        peak = float(peaks.get("hbm_gbs", 6650.0))
+        algo = n * size + total
+        achieved = algo / (ms / args.steps / 1e3) / GB
+        print(json.dumps({
+            "metric": "compress GB/s (uncompressed input, device-timed; CRC-32 + DEFLATE + compaction)",
+            "value": tot_in * args.steps / (ms_max / 1e3) / GB, "unit": "GB/s", "n_gpus": dist.world, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": ms_max / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "u8", "data": "synthetic",
+            "config": {"workload": WORKLOADS["c5"], "entries_per_gpu": n, "uncomp_bytes_per_gpu": n * size, "compressed_bytes_per_gpu": total,
+                       "ratio": n * size / total, "reference_ratio_same_level": 4.36, "zlib6_ratio": 9.0,
+                       "verified": {"zlib_streams_ok": n_ok, "of": n, "compiled_reference_sample_ok": ref_ok},
+                       "cache": "inputs larger than L2 (no flush needed)"},
+            "roofline": {"bound": "hbm", "kernel": "k_deflate_chunks (+crc, scan, gather)", "achieved": achieved, "peak": peak, "unit": "GB/s",
+                         "frac": achieved / peak, "traffic": None, "peak_source": "measured (MEASURED_PEAKS.json hbm_gbs)" if peaks else "fallback"},
+            "e2e": {"value": tot_in * e2e_steps / e2e_max / GB, "unit": "GB/s", "h2d_bytes_per_step": int(img.nbytes),
+                    "d2h_bytes_per_step": int(total + 18 * n), "steps": e2e_steps,
+                    "timing": "host wall clock around otz_deflate_host (C-ABI, pinned host buffers), device-synchronised"},
+            "gpu_launches": int(launches), "clocks": sampler.summary()}))
+    ctx.deflate_destroy(job)
+    dist.close()
+
+
 WORKLOADS = {
     "c2": "configs[1]: STORE + CRC-32 verify only, 10,000 entries of 1 MiB random bytes",
     "c1": "configs[0]: 1,000-entry DEFLATE archive, 64 KiB text-like entries, CRC-32 check",
     "c3": "configs[2]: DEFLATE inflate of mixed-size entries (4 KiB-16 MiB) JSON-log text",
     "c4": "configs[3]: method 93 decode of 256 KiB entries (reference container)",
+    "c5": "configs[4]: archive creation, batched DEFLATE compress + CRC-32, 4 GiB synthetic corpus",
 }
 
 
@@ -345,6 +453,9 @@ def main():
         dist.close()
         return
 
+    if args.workload == "c5":
+        run_c5(args, dist)
+        return
     from otezip_b200 import Ctx
     from otezip_b200 import native
     ctx = Ctx(dist.local)

@@ -61,10 +61,14 @@ __device__ __forceinline__ void tile_copy(uint8_t *__restrict__ dst, const uint8
 	}
 }
 
-// STORE extract: one warp per 64 KiB chunk of the shared chunk list.
-__global__ void __launch_bounds__(256) k_store_copy(const uint8_t *__restrict__ archive, uint8_t *__restrict__ out,
+// STORE extract: one warp per chunk of the shared chunk list.  The chunk is copied, then its CRC is folded
+// from the SOURCE bytes, which the copy has just pulled through L2 — HBM sees the payload once.
+__global__ void __launch_bounds__(256, 2) k_store_copy(const uint8_t *__restrict__ archive, uint8_t *__restrict__ out,
 	const otz_entry *__restrict__ ents, const OtzEntryState *__restrict__ est, const int32_t *__restrict__ status,
-	const OtzCrcChunk *__restrict__ chunks, uint32_t n_chunks) {
+	const OtzCrcChunk *__restrict__ chunks, uint32_t n_chunks, uint32_t *__restrict__ acc, const OtzCrcTables *__restrict__ tabs) {
+	__shared__ __align__(16) uint32_t s_skip[16 * 256];
+	crc_tables_to_smem(s_skip, tabs);
+	__syncthreads();
 	const uint32_t warps_per_cta = blockDim.x >> 5;
 	const uint32_t total_warps = gridDim.x * warps_per_cta;
 	const int lane = threadIdx.x & 31;
@@ -76,14 +80,23 @@ __global__ void __launch_bounds__(256) k_store_copy(const uint8_t *__restrict__ 
 		}
 		const uint64_t off = (uint64_t)ck.chunk * OTZ_CRC_CHUNK;
 		const uint64_t len = min((uint64_t)OTZ_CRC_CHUNK, (uint64_t)e.uncomp_size - off);
-		tile_copy<32>(out + e.out_ofs + off, archive + est[ck.entry].data_ofs + off, len, lane);
+		const uint8_t *src = archive + est[ck.entry].data_ofs + off;
+		tile_copy<32>(out + e.out_ofs + off, src, len, lane);
+		const uint32_t raw = len >= OTZ_CRC_FOLD_MIN ? crc_raw_warp_fold(src, len, s_skip, tabs) : crc_raw_warp(src, len, s_skip, tabs);
+		if (lane == 0) {
+			const uint64_t after = (uint64_t)e.uncomp_size - off - len;
+			atomicXor(&acc[ck.entry], after ? crc_mulmod(raw, crc_xpow8(after, tabs->x2n)) : raw);
+		}
 	}
 }
 
 // Method 93, reference container: one warp per entry walks the block chain and copies payloads.
-__global__ void __launch_bounds__(256) k_zstdref(const uint8_t *__restrict__ archive, uint8_t *__restrict__ out,
+__global__ void __launch_bounds__(256, 2) k_zstdref(const uint8_t *__restrict__ archive, uint8_t *__restrict__ out,
 	const otz_entry *__restrict__ ents, const OtzEntryState *__restrict__ est, int32_t *__restrict__ status,
-	const uint32_t *__restrict__ list, uint32_t n_list) {
+	const uint32_t *__restrict__ list, uint32_t n_list, uint32_t *__restrict__ acc, const OtzCrcTables *__restrict__ tabs) {
+	__shared__ __align__(16) uint32_t s_skip[16 * 256];
+	crc_tables_to_smem(s_skip, tabs);
+	__syncthreads();
 	const uint32_t warps_per_cta = blockDim.x >> 5;
 	const uint32_t total_warps = gridDim.x * warps_per_cta;
 	const int lane = threadIdx.x & 31;
@@ -98,6 +111,7 @@ __global__ void __launch_bounds__(256) k_zstdref(const uint8_t *__restrict__ arc
 		const uint32_t n = e.comp_size, cap = e.uncomp_size;
 		int32_t st = OTZ_ST_OK;
 		uint32_t ip = 5, op = 0;
+		uint32_t rtot = 0, mul_len = 0, mul = 0x80000000u;   // running remainder of the output; cached x^(8*mul_len)
 		if (n < 5) {
 			st = OTZ_ST_TRUNCATED;  // zstd:490-492
 		} else if (ld_le32(in) != 0xFD2FB528u) {
@@ -129,6 +143,17 @@ __global__ void __launch_bounds__(256) k_zstdref(const uint8_t *__restrict__ arc
 					break;
 				}
 				tile_copy<32>(dst + op, in + ip, bsz, lane);
+				if (bsz) {
+					// CRC of the payload from the source bytes (still in L2), appended to the running remainder:
+					// R(A||B) = R(A) * x^(8|B|) ^ R(B)
+					const uint32_t rb = bsz >= OTZ_CRC_FOLD_MIN ? crc_raw_warp_fold(in + ip, bsz, s_skip, tabs)
+					                                            : crc_raw_warp(in + ip, bsz, s_skip, tabs);
+					if (bsz != mul_len) {
+						mul_len = bsz;
+						mul = crc_xpow8(bsz, tabs->x2n);
+					}
+					rtot = crc_mulmod(rtot, mul) ^ rb;
+				}
 				ip += bsz;
 				op += bsz;
 				if (h & 1) {
@@ -139,8 +164,12 @@ __global__ void __launch_bounds__(256) k_zstdref(const uint8_t *__restrict__ arc
 				st = OTZ_ST_SIZE;  // otezip.c:555
 			}
 		}
-		if (lane == 0 && st != OTZ_ST_OK) {
-			status[ei] = st;
+		if (lane == 0) {
+			if (st != OTZ_ST_OK) {
+				status[ei] = st;
+			} else {
+				acc[ei] = rtot;
+			}
 		}
 	}
 }

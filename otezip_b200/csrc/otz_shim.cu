@@ -355,8 +355,8 @@ extern "C" int otz_plan_create(otz_ctx *c, const otz_entry *ents, uint32_t n, co
 	for (int pass = 0; pass < 2; pass++) {
 		for (uint32_t i = 0; i < n; i++) {
 			const bool is_store = ents[i].method == OTZ_M_STORE;
-			if ((pass == 0) != is_store) {
-				continue;
+			if ((pass == 0) != is_store || ents[i].method == OTZ_M_ZSTD) {
+				continue;   // method 93 folds its CRC inside k_zstdref
 			}
 			const uint32_t nc = (uint32_t)(((uint64_t)ents[i].uncomp_size + OTZ_CRC_CHUNK - 1) / OTZ_CRC_CHUNK);
 			for (uint32_t k = 0; k < nc; k++) {
@@ -482,15 +482,14 @@ extern "C" int otz_extract_run(otz_ctx *c, otz_plan *p, const uint8_t *d_archive
 	if (c->profile) {
 		CK(cudaEventRecord(pev[1], s));
 	}
-	const uint32_t persistent = (uint32_t)c->sm_count * 8;  // 8 CTAs x 8 warps = 64 warps per SM
 	if (p->n_store_chunks && !p->opts.verify_only) {
-		k_store_copy<<<std::min(persistent, (p->n_store_chunks + 7) / 8), 256, 0, s>>>(d_archive, d_out, p->d_ents, p->d_est, p->d_status,
-			p->d_chunks, p->n_store_chunks);
+		k_store_copy<<<std::min((uint32_t)c->sm_count * 2, (p->n_store_chunks + 7) / 8), 256, 0, s>>>(d_archive, d_out, p->d_ents, p->d_est,
+			p->d_status, p->d_chunks, p->n_store_chunks, p->d_acc, c->d_tabs);
 		c->launches++;
 	}
 	if (p->n_zstd) {
-		k_zstdref<<<std::min(persistent, (p->n_zstd + 7) / 8), 256, 0, s>>>(d_archive, d_out, p->d_ents, p->d_est, p->d_status, p->d_zstd_list,
-			p->n_zstd);
+		k_zstdref<<<std::min((uint32_t)c->sm_count * 2, (p->n_zstd + 7) / 8), 256, 0, s>>>(d_archive, d_out, p->d_ents, p->d_est, p->d_status,
+			p->d_zstd_list, p->n_zstd, p->d_acc, c->d_tabs);
 		c->launches++;
 	}
 	if (p->n_inflate) {
@@ -502,10 +501,13 @@ extern "C" int otz_extract_run(otz_ctx *c, otz_plan *p, const uint8_t *d_archive
 	if (c->profile) {
 		CK(cudaEventRecord(pev[2], s));
 	}
-	if (p->n_chunks) {
+	// STORE chunks were CRC'd by k_store_copy unless they are verified in place
+	const uint32_t crc_first = p->opts.verify_only ? 0u : p->n_store_chunks;
+	if (p->n_chunks > crc_first) {
 		// persistent: exactly the resident CTAs (register-limited), each striding over the chunk list
-		const uint32_t grid = std::min((uint32_t)c->sm_count * crc_ctas_per_sm(), (p->n_chunks + 7) / 8);
-		k_crc_chunks<<<grid, 256, 0, s>>>(d_archive, d_out, p->d_ents, p->d_est, p->d_status, p->d_chunks, p->n_chunks, p->d_acc, c->d_tabs,
+		const uint32_t nc = p->n_chunks - crc_first;
+		const uint32_t grid = std::min((uint32_t)c->sm_count * crc_ctas_per_sm(), (nc + 7) / 8);
+		k_crc_chunks<<<grid, 256, 0, s>>>(d_archive, d_out, p->d_ents, p->d_est, p->d_status, p->d_chunks + crc_first, nc, p->d_acc, c->d_tabs,
 			p->opts.verify_only);
 		c->launches++;
 	}

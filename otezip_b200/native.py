@@ -273,3 +273,35 @@ class Ctx:
         self.lib.check(self.L.otz_deflate_host(self.h, vp(buf), pos, vp(ofs), vp(lens), vp(meth), n, vp(out), out.nbytes,
                                                vp(o_ofs), vp(o_sz), vp(crc), vp(m_out), C.byref(tot)), "otz_deflate_host")
         return [(int(m_out[i]), bytes(out[int(o_ofs[i]):int(o_ofs[i]) + int(o_sz[i])]), int(crc[i])) for i in range(n)]
+
+    # -- write path, device-resident (what bench.py times)
+    def deflate_plan(self, in_ofs: np.ndarray, in_len: np.ndarray, methods: np.ndarray):
+        j = C.c_void_p()
+        vp = lambda a: np.ascontiguousarray(a).ctypes.data_as(C.c_void_p)
+        self._dfl_keep = (np.ascontiguousarray(in_ofs, dtype=np.uint64), np.ascontiguousarray(in_len, dtype=np.uint32),
+                          np.ascontiguousarray(methods, dtype=np.uint16))
+        a, b, c = self._dfl_keep
+        self.lib.check(self.L.otz_deflate_plan(self.h, a.ctypes.data_as(C.c_void_p), b.ctypes.data_as(C.c_void_p),
+                                               c.ctypes.data_as(C.c_void_p), len(a), C.byref(j)), "otz_deflate_plan")
+        return j
+
+    def deflate_run(self, job, d_in, in_bytes: int):
+        self.lib.check(self.L.otz_deflate_run(self.h, job, d_in, in_bytes), "otz_deflate_run")
+
+    def deflate_results(self, job, n: int):
+        ofs = np.zeros(max(n, 1), dtype=np.uint64)
+        sz = np.zeros(max(n, 1), dtype=np.uint32)
+        crc = np.zeros(max(n, 1), dtype=np.uint32)
+        m = np.zeros(max(n, 1), dtype=np.uint16)
+        tot = C.c_uint64()
+        vp = lambda a: a.ctypes.data_as(C.c_void_p)
+        self.lib.check(self.L.otz_deflate_results(self.h, job, vp(ofs), vp(sz), vp(crc), vp(m), C.byref(tot)), "otz_deflate_results")
+        return ofs[:n], sz[:n], crc[:n], m[:n], int(tot.value)
+
+    def deflate_fetch(self, job, nbytes: int) -> np.ndarray:
+        out = np.zeros(max(nbytes, 1), dtype=np.uint8)
+        self.lib.check(self.L.otz_deflate_fetch(self.h, job, out.ctypes.data_as(C.c_void_p), nbytes), "otz_deflate_fetch")
+        return out[:nbytes]
+
+    def deflate_destroy(self, job):
+        self.L.otz_deflate_destroy(self.h, job)
