@@ -162,6 +162,13 @@ int otz_deflate_host(otz_ctx *ctx, const uint8_t *in, uint64_t in_bytes, const u
 	const uint16_t *method, uint32_t n, uint8_t *out, uint64_t out_cap, uint64_t *out_ofs, uint32_t *out_size,
 	uint32_t *crc, uint16_t *method_out, uint64_t *total);
 
+/* Same, plus produced[i] = bytes the stream of entry i actually produced (== uncomp_size except for DEFLATE
+ * streams that end early, whose tail is zero: OTZ_STF_SHORT). */
+int otz_extract_host_ex(otz_ctx *ctx, const uint8_t *archive, uint64_t archive_len, const otz_entry *entries,
+	uint32_t n, const otz_extract_opts *opts, uint8_t *out, uint64_t out_len, uint32_t *crc, int32_t *status,
+	uint32_t *produced);
+int otz_extract_produced(otz_ctx *ctx, otz_plan *plan, uint32_t *produced);
+
 /* Policy helper shared by the host library and the tests: does a status word
  * mean "zip_fopen_index returns the buffer" under the given globals?
  * ref_compat != 0 reproduces the reference's end-of-block rule (F1). */

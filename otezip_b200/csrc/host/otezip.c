@@ -80,7 +80,8 @@ struct otz_file {                 /* zip_file_t plus the window it borrows from 
 static otz_ctx *g_ctx;
 static int g_ctx_failed;
 
-static otz_ctx *gpu(void) {
+otz_ctx *otezip_b200_ctx(void);   /* shared with zcompat.c */
+otz_ctx *otezip_b200_ctx(void) {
 	if (!g_ctx && !g_ctx_failed) {
 		int dev = 0;
 		const char *e = getenv ("OTEZIP_DEVICE");
@@ -558,7 +559,7 @@ static int load_image(struct otz_archive *a) {
 /* Decode a batch starting at `index`: consecutive entries until the byte budget is reached. */
 static struct otz_window *run_window(struct otz_archive *a, zip_uint64_t index) {
 	zip_t *za = &a->pub;
-	otz_ctx *ctx = gpu ();
+	otz_ctx *ctx = otezip_b200_ctx ();
 	if (!ctx || load_image (a) != 0) {
 		return NULL;
 	}
@@ -930,7 +931,7 @@ static int finalize_archive(struct otz_archive *a) {
 		return -1;
 	}
 	if (n_new) {
-		otz_ctx *ctx = gpu ();
+		otz_ctx *ctx = otezip_b200_ctx ();
 		if (!ctx) {
 			return -1;
 		}

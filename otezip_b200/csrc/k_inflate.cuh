@@ -717,7 +717,7 @@ __device__ __forceinline__ int32_t inflate_stream(const Tile &tile, InflateSmemV
 template <int G, int W>
 __global__ void __launch_bounds__(256) k_inflate(const uint8_t *__restrict__ archive, uint8_t *__restrict__ out,
 	const otz_entry *__restrict__ ents, const OtzEntryState *__restrict__ est, int32_t *__restrict__ status,
-	const uint32_t *__restrict__ list, uint32_t n_list, uint32_t *__restrict__ work_counter) {
+	const uint32_t *__restrict__ list, uint32_t n_list, uint32_t *__restrict__ work_counter, uint32_t *__restrict__ produced_out) {
 	extern __shared__ __align__(16) uint8_t smem_raw[];
 	auto tile = cg::tiled_partition<G>(cg::this_thread_block());
 	const int lane = tile.thread_rank();
@@ -747,6 +747,7 @@ __global__ void __launch_bounds__(256) k_inflate(const uint8_t *__restrict__ arc
 		}
 		if (lane == 0) {
 			status[ei] = st;
+			produced_out[ei] = produced;
 		}
 		tile.sync();
 	}

@@ -9,13 +9,14 @@
 
 __global__ void k_resolve(const uint8_t *__restrict__ archive, uint64_t archive_len, uint64_t out_len,
 	const otz_entry *__restrict__ ents, uint32_t n, OtzEntryState *__restrict__ est, int32_t *__restrict__ status,
-	uint32_t *__restrict__ acc, otz_extract_opts opts) {
+	uint32_t *__restrict__ acc, uint32_t *__restrict__ produced, otz_extract_opts opts) {
 	uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
 	if (i >= n) {
 		return;
 	}
 	const otz_entry e = ents[i];
 	acc[i] = 0;
+	produced[i] = e.uncomp_size;   // DEFLATE streams that end early overwrite this (zero-padded tail)
 	est[i].data_ofs = 0;
 	int32_t st = OTZ_ST_OK;
 	do {

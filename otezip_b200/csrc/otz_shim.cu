@@ -53,7 +53,7 @@ struct otz_plan {
 	otz_entry *d_ents;
 	OtzEntryState *d_est;
 	int32_t *d_status;
-	uint32_t *d_acc, *d_crc;
+	uint32_t *d_acc, *d_crc, *d_produced;
 	OtzCrcChunk *d_chunks;
 	uint32_t n_chunks;
 	uint32_t n_store_chunks;   // chunks [0, n_store_chunks) belong to STORE entries
@@ -328,6 +328,7 @@ extern "C" void otz_plan_destroy(otz_ctx *c, otz_plan *p) {
 	cudaFree(p->d_status);
 	cudaFree(p->d_acc);
 	cudaFree(p->d_crc);
+	cudaFree(p->d_produced);
 	cudaFree(p->d_chunks);
 	cudaFree(p->d_inflate_list);
 	cudaFree(p->d_zstd_list);
@@ -393,6 +394,7 @@ extern "C" int otz_plan_create(otz_ctx *c, const otz_entry *ents, uint32_t n, co
 	const size_t n1 = std::max<uint32_t>(n, 1);
 	if (cudaMalloc(&p->d_est, n1 * sizeof(OtzEntryState)) != cudaSuccess || cudaMalloc(&p->d_status, n1 * 4) != cudaSuccess ||
 		cudaMalloc(&p->d_acc, n1 * 4) != cudaSuccess || cudaMalloc(&p->d_crc, n1 * 4) != cudaSuccess ||
+		cudaMalloc(&p->d_produced, n1 * 4) != cudaSuccess ||
 		cudaMalloc(&p->d_counter, 64) != cudaSuccess) {
 		otz_plan_destroy(c, p);
 		return fail_cuda(cudaGetLastError(), "cudaMalloc(plan)");
@@ -422,7 +424,7 @@ static int launch_inflate(otz_ctx *c, otz_plan *p, const uint8_t *d_archive, uin
 	const uint32_t want = (p->n_inflate + tiles_per_cta - 1) / tiles_per_cta;
 	grid = std::max(1u, std::min(grid, want));
 	k_inflate<G, W><<<grid, threads, smem, c->stream>>>(d_archive, d_out, p->d_ents, p->d_est, p->d_status, p->d_inflate_list,
-		p->n_inflate, p->d_counter);
+		p->n_inflate, p->d_counter, p->d_produced);
 	c->launches++;
 	CK(cudaGetLastError());
 	return OTZ_SUCCESS;
@@ -476,7 +478,8 @@ extern "C" int otz_extract_run(otz_ctx *c, otz_plan *p, const uint8_t *d_archive
 	}
 	if (n) {
 		CK(cudaMemsetAsync(p->d_counter, 0, 64, s));
-		k_resolve<<<(n + 255) / 256, 256, 0, s>>>(d_archive, archive_len, out_len, p->d_ents, n, p->d_est, p->d_status, p->d_acc, p->opts);
+		k_resolve<<<(n + 255) / 256, 256, 0, s>>>(d_archive, archive_len, out_len, p->d_ents, n, p->d_est, p->d_status, p->d_acc, p->d_produced,
+			p->opts);
 		c->launches++;
 	}
 	if (c->profile) {
@@ -541,8 +544,25 @@ extern "C" int otz_extract_results(otz_ctx *c, otz_plan *p, uint32_t *crc, int32
 	return OTZ_SUCCESS;
 }
 
+extern "C" int otz_extract_produced(otz_ctx *c, otz_plan *p, uint32_t *produced) {
+	if (!c || !p || !produced) {
+		return OTZ_ERR_ARG;
+	}
+	CK(cudaSetDevice(c->device));
+	if (p->n) {
+		CK(cudaMemcpyAsync(produced, p->d_produced, p->n * 4ull, cudaMemcpyDeviceToHost, c->stream));
+	}
+	CK(cudaStreamSynchronize(c->stream));
+	return OTZ_SUCCESS;
+}
+
 extern "C" int otz_extract_host(otz_ctx *c, const uint8_t *archive, uint64_t archive_len, const otz_entry *ents, uint32_t n,
 	const otz_extract_opts *opts, uint8_t *out, uint64_t out_len, uint32_t *crc, int32_t *status) {
+	return otz_extract_host_ex(c, archive, archive_len, ents, n, opts, out, out_len, crc, status, nullptr);
+}
+
+extern "C" int otz_extract_host_ex(otz_ctx *c, const uint8_t *archive, uint64_t archive_len, const otz_entry *ents, uint32_t n,
+	const otz_extract_opts *opts, uint8_t *out, uint64_t out_len, uint32_t *crc, int32_t *status, uint32_t *produced) {
 	if (!c || !opts) {
 		return OTZ_ERR_ARG;
 	}
@@ -576,6 +596,9 @@ extern "C" int otz_extract_host(otz_ctx *c, const uint8_t *archive, uint64_t arc
 		if ((rc = otz_extract_run(c, p, (const uint8_t *)c->d_arch_cache, archive_len, (uint8_t *)c->d_out_cache, need))) break;
 		if (out && need && (rc = otz_d2h(c, out, c->d_out_cache, need))) break;
 		rc = otz_extract_results(c, p, crc, status);
+		if (!rc && produced) {
+			rc = otz_extract_produced(c, p, produced);
+		}
 	} while (0);
 	cudaStreamSynchronize(c->stream);
 	otz_plan_destroy(c, p);

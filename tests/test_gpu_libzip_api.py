@@ -133,3 +133,27 @@ def test_unchanged_cli_relinked_against_the_gpu_library(tmp_path):
     want = {k: v for k, v in _tree(src).items() if k != "out.zip"}
     assert _tree(d) == want
     assert os.path.getsize(src / "out.zip") < 80000     # a.json really got deflated
+
+
+@pytest.mark.skipif(not os.path.exists(os.path.join(REFDIR, "otezip_relinked")), reason="relinked CLI not built")
+def test_cli_gzip_modes_on_the_gpu_path(tmp_path):
+    """-g / -d of the unchanged CLI (main.c:590-832) through the zlib-named one-shot entry points (zcompat.c)."""
+    import gzip
+    new = os.path.join(REFDIR, "otezip_relinked")
+    text = synth.jsonlog_text(400000, 9)
+    rnd = synth.random_bytes(100000, 10)
+    for name, data in (("t.json", text), ("r.bin", rnd), ("tiny", b"hello world\n")):
+        (tmp_path / name).write_bytes(data)
+        r = subprocess.run([new, "-g", name], cwd=tmp_path, capture_output=True, text=True, timeout=300)
+        assert r.returncode == 0, r.stderr
+        gz = (tmp_path / (name + ".gz")).read_bytes()
+        assert gzip.decompress(gz) == data                           # CRC-32 + ISIZE trailer checked by Python's gzip
+        if data is text:
+            assert len(gz) < len(data) // 5
+        # gunzip what gzip(1)-compatible tools produce, and what we produced
+        (tmp_path / "std.gz").write_bytes(gzip.compress(data, 6))
+        for src in ("std.gz", name + ".gz"):
+            r = subprocess.run([new, "-d", src, "back.out"], cwd=tmp_path, capture_output=True, text=True, timeout=300)
+            assert r.returncode == 0, r.stderr
+            assert (tmp_path / "back.out").read_bytes() == data
+            os.unlink(tmp_path / "back.out")
