@@ -32,8 +32,8 @@ static int fail_cuda(cudaError_t e, const char *what) {
 struct otz_ctx {
 	int device;
 	int sm_count;
-	cudaStream_t stream;
-	cudaEvent_t ev0, ev1;
+	cudaStream_t stream, stream2;
+	cudaEvent_t ev0, ev1, ev_fork, ev_join;
 	cudaEvent_t pev[OTZ_PROF_SLOTS][5];
 	int profile;
 	uint32_t prof_runs;      // runs recorded since otz_profile_enable(ctx, 1)
@@ -57,7 +57,8 @@ struct otz_plan {
 	OtzCrcChunk *d_chunks;
 	uint32_t n_chunks;
 	uint32_t n_store_chunks;   // chunks [0, n_store_chunks) belong to STORE entries
-	uint32_t *d_inflate_list, n_inflate;
+	uint32_t *d_inflate_list, n_inflate;   // DEFLATE entries, longest first; [0, n_inflate_big) are the large ones
+	uint32_t n_inflate_big;
 	uint32_t *d_zstd_list, n_zstd;
 	uint32_t *d_counter;
 	uint64_t out_bytes_needed;
@@ -149,6 +150,9 @@ extern "C" int otz_ctx_create(int device, otz_ctx **out) {
 	CK(cudaGetDeviceProperties(&prop, device));
 	c->sm_count = prop.multiProcessorCount;
 	CK(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
+	CK(cudaStreamCreateWithFlags(&c->stream2, cudaStreamNonBlocking));
+	CK(cudaEventCreateWithFlags(&c->ev_fork, cudaEventDisableTiming));
+	CK(cudaEventCreateWithFlags(&c->ev_join, cudaEventDisableTiming));
 	CK(cudaEventCreate(&c->ev0));
 	CK(cudaEventCreate(&c->ev1));
 	for (auto &slot : c->pev) {
@@ -186,6 +190,9 @@ extern "C" void otz_ctx_destroy(otz_ctx *c) {
 			cudaEventDestroy(e);
 		}
 	}
+	cudaEventDestroy(c->ev_fork);
+	cudaEventDestroy(c->ev_join);
+	cudaStreamDestroy(c->stream2);
 	cudaStreamDestroy(c->stream);
 	delete c;
 }
@@ -379,7 +386,16 @@ extern "C" int otz_plan_create(otz_ctx *c, const otz_entry *ents, uint32_t n, co
 		}
 	}
 	// longest streams first: the tail of the batch is then made of short ones
-	std::stable_sort(infl.begin(), infl.end(), [&](uint32_t a, uint32_t b) { return ents[a].comp_size > ents[b].comp_size; });
+	// large entries first (they get the 16 KiB ring kernel), inside each class longest streams first
+	const uint32_t big_bytes = 256u * 1024u;
+	std::stable_sort(infl.begin(), infl.end(), [&](uint32_t a, uint32_t b) {
+		const bool ba = ents[a].uncomp_size >= big_bytes, bb = ents[b].uncomp_size >= big_bytes;
+		return ba != bb ? ba : ents[a].comp_size > ents[b].comp_size;
+	});
+	p->n_inflate_big = 0;
+	for (uint32_t i : infl) {
+		p->n_inflate_big += ents[i].uncomp_size >= big_bytes;
+	}
 	p->n_chunks = (uint32_t)chunks.size();
 	p->n_inflate = (uint32_t)infl.size();
 	p->n_zstd = (uint32_t)zst.size();
@@ -395,7 +411,7 @@ extern "C" int otz_plan_create(otz_ctx *c, const otz_entry *ents, uint32_t n, co
 	if (cudaMalloc(&p->d_est, n1 * sizeof(OtzEntryState)) != cudaSuccess || cudaMalloc(&p->d_status, n1 * 4) != cudaSuccess ||
 		cudaMalloc(&p->d_acc, n1 * 4) != cudaSuccess || cudaMalloc(&p->d_crc, n1 * 4) != cudaSuccess ||
 		cudaMalloc(&p->d_produced, n1 * 4) != cudaSuccess ||
-		cudaMalloc(&p->d_counter, 64) != cudaSuccess) {
+		cudaMalloc(&p->d_counter, 256) != cudaSuccess) {
 		otz_plan_destroy(c, p);
 		return fail_cuda(cudaGetLastError(), "cudaMalloc(plan)");
 	}
@@ -405,7 +421,8 @@ extern "C" int otz_plan_create(otz_ctx *c, const otz_entry *ents, uint32_t n, co
 }
 
 template <int G, int W>
-static int launch_inflate(otz_ctx *c, otz_plan *p, const uint8_t *d_archive, uint8_t *d_out) {
+static int launch_inflate(otz_ctx *c, otz_plan *p, const uint8_t *d_archive, uint8_t *d_out, uint32_t first, uint32_t count, int slot,
+	cudaStream_t st) {
 	const int threads = 8 * G;   // 8 streams per CTA
 	const size_t smem = 8 * sizeof(InflateSmemV2<G, W>);
 	static bool attr_done = false;
@@ -421,28 +438,20 @@ static int launch_inflate(otz_ctx *c, otz_plan *p, const uint8_t *d_archive, uin
 	}
 	const uint32_t tiles_per_cta = threads / G;
 	uint32_t grid = (uint32_t)(c->sm_count * per_sm);
-	const uint32_t want = (p->n_inflate + tiles_per_cta - 1) / tiles_per_cta;
+	const uint32_t want = (count + tiles_per_cta - 1) / tiles_per_cta;
 	grid = std::max(1u, std::min(grid, want));
-	k_inflate<G, W><<<grid, threads, smem, c->stream>>>(d_archive, d_out, p->d_ents, p->d_est, p->d_status, p->d_inflate_list,
-		p->n_inflate, p->d_counter, p->d_produced);
+	k_inflate<G, W><<<grid, threads, smem, st>>>(d_archive, d_out, p->d_ents, p->d_est, p->d_status, p->d_inflate_list + first, count,
+		p->d_counter + 16 * slot, p->d_produced);
 	c->launches++;
 	CK(cudaGetLastError());
 	return OTZ_SUCCESS;
 }
 
-// Lanes per stream and ring size.  Few streams: a whole warp and a 16 KiB ring per stream (latency);
-// many streams: narrow tiles and small rings so that more streams are resident per SM (throughput).
-static int dispatch_inflate(otz_ctx *c, otz_plan *p, const uint8_t *d_archive, uint8_t *d_out) {
-	int g = c->inflate_tile, w = c->inflate_ring;
-	if (g == 0) {
-		g = p->n_inflate <= (uint32_t)c->sm_count * 10u ? 32 : 8;
-	}
-	if (w == 0) {
-		w = g == 32 ? (p->n_inflate <= (uint32_t)c->sm_count * 10u ? 16384 : 2048) : 2048;
-	}
+static int launch_inflate_cfg(otz_ctx *c, otz_plan *p, const uint8_t *d_archive, uint8_t *d_out, int g, int w, uint32_t first, uint32_t count,
+	int slot, cudaStream_t st) {
 #define OTZ_INF_CASE(G_, W_)        \
 	if (g == G_ && w == W_) {       \
-		return launch_inflate<G_, W_>(c, p, d_archive, d_out); \
+		return launch_inflate<G_, W_>(c, p, d_archive, d_out, first, count, slot, st); \
 	}
 	OTZ_INF_CASE(32, 16384)
 	OTZ_INF_CASE(32, 4096)
@@ -457,6 +466,37 @@ static int dispatch_inflate(otz_ctx *c, otz_plan *p, const uint8_t *d_archive, u
 #undef OTZ_INF_CASE
 	snprintf(g_err, sizeof(g_err), "unsupported OTZ_INFLATE_TILE/OTZ_INFLATE_RING combination %d/%d", g, w);
 	return OTZ_ERR_ARG;
+}
+
+// One warp per stream.  The ring size trades per-stream speed (a 16 KiB ring serves ~85% of the back-references
+// of text from shared memory, a 2 KiB ring ~35%) against resident streams per SM (10 vs 24).  Large entries set
+// the critical path of a batch, so they always get the big ring, on a second stream so that both kernels can
+// share the machine; small entries get the big ring only when there are too few of them to fill the SMs.
+static int dispatch_inflate(otz_ctx *c, otz_plan *p, const uint8_t *d_archive, uint8_t *d_out) {
+	if (c->inflate_tile || c->inflate_ring) {   // explicit configuration (tests, sweeps): one kernel for everything
+		const int g = c->inflate_tile ? c->inflate_tile : 32;
+		const int w = c->inflate_ring ? c->inflate_ring : 2048;
+		return launch_inflate_cfg(c, p, d_archive, d_out, g, w, 0, p->n_inflate, 0, c->stream);
+	}
+	const uint32_t n_big = p->n_inflate_big, n_small = p->n_inflate - n_big;
+	const bool small_big_ring = n_small <= (uint32_t)c->sm_count * 10u;
+	int rc = OTZ_SUCCESS;
+	if (n_big && n_small && !small_big_ring) {
+		CK(cudaEventRecord(c->ev_fork, c->stream));
+		CK(cudaStreamWaitEvent(c->stream2, c->ev_fork, 0));
+		rc = launch_inflate_cfg(c, p, d_archive, d_out, 32, 16384, 0, n_big, 0, c->stream2);
+		if (rc) {
+			return rc;
+		}
+		rc = launch_inflate_cfg(c, p, d_archive, d_out, 32, 2048, n_big, n_small, 1, c->stream);
+		CK(cudaEventRecord(c->ev_join, c->stream2));
+		CK(cudaStreamWaitEvent(c->stream, c->ev_join, 0));
+		return rc;
+	}
+	if (small_big_ring) {
+		return launch_inflate_cfg(c, p, d_archive, d_out, 32, 16384, 0, p->n_inflate, 0, c->stream);
+	}
+	return launch_inflate_cfg(c, p, d_archive, d_out, 32, 2048, 0, p->n_inflate, 0, c->stream);
 }
 
 extern "C" int otz_extract_run(otz_ctx *c, otz_plan *p, const uint8_t *d_archive, uint64_t archive_len, uint8_t *d_out,
@@ -477,7 +517,7 @@ extern "C" int otz_extract_run(otz_ctx *c, otz_plan *p, const uint8_t *d_archive
 		CK(cudaEventRecord(pev[0], s));
 	}
 	if (n) {
-		CK(cudaMemsetAsync(p->d_counter, 0, 64, s));
+		CK(cudaMemsetAsync(p->d_counter, 0, 256, s));
 		k_resolve<<<(n + 255) / 256, 256, 0, s>>>(d_archive, archive_len, out_len, p->d_ents, n, p->d_est, p->d_status, p->d_acc, p->d_produced,
 			p->opts);
 		c->launches++;
