@@ -76,8 +76,17 @@ typedef struct otz_entry {
 	uint32_t uncomp_size;
 	uint32_t crc32;       /* expected CRC-32 from the central directory */
 	uint16_t method;
-	uint16_t flags;       /* reserved, 0 */
+	uint16_t flags;       /* OTZ_EF_* */
 } otz_entry;
+
+/* Row flags.  Archives written by this library carry, in the LFH extra field of a multi-chunk DEFLATE entry,
+ * the compressed size of each independently decodable chunk (otezip/zip.h, "chunk index").  The directory walk
+ * then emits one PARENT row (resolved, CRC'd and reported like any entry, but not decoded as one stream) plus one
+ * CHUNK row per chunk: lfh_ofs = offset of the chunk's first byte in the image, out_ofs = where its bytes go,
+ * crc32 = row number of its parent.  A failing chunk fails its parent. */
+#define OTZ_EF_PARENT 0x0001
+#define OTZ_EF_CHUNK 0x0002
+#define OTZ_EF_LAST_CHUNK 0x0004   /* must end with the stream's final block */
 
 typedef struct otz_extract_opts {
 	int ignore_zipbomb;       /* otezip_ignore_zipbomb        otezip.c:166 */
@@ -153,6 +162,11 @@ int otz_deflate_run(otz_ctx *ctx, otz_deflate_job *job, const uint8_t *d_in, uin
 /* Per-source results (synchronises; any pointer may be NULL). *total = bytes in the dense arena. */
 int otz_deflate_results(otz_ctx *ctx, otz_deflate_job *job, uint64_t *out_ofs, uint32_t *out_size, uint32_t *crc,
 	uint16_t *method_out, uint64_t *total);
+/* Chunk layout of the job: first_chunk[i] / n_chunks[i] per source, csize[] = compressed bytes of every chunk
+ * (valid after otz_deflate_results; the bytes of a DEFLATE source are its chunks back to back, each one
+ * independently decodable).  chunk_bytes = uncompressed bytes per chunk.  Returns the total number of chunks. */
+int otz_deflate_chunks(otz_ctx *ctx, otz_deflate_job *job, uint32_t *first_chunk, uint32_t *n_chunks, uint32_t *csize,
+	uint32_t csize_cap, uint32_t *chunk_bytes);
 /* Device pointer of the dense output arena (valid until the job is destroyed). */
 const uint8_t *otz_deflate_device_output(otz_deflate_job *job);
 /* Copy the dense arena (first `bytes` bytes) to the host (synchronises). */

@@ -28,6 +28,11 @@
 #define MAX_PAYLOAD (2ULL * 1024 * 1024 * 1024)         /* otezip.c:102 */
 #define ERR_READ (-1)                                   /* otezip.c:191 */
 #define ERR_INCONS (-2)                                 /* otezip.c:192 */
+/* Chunk index: LFH extra field written for multi-chunk DEFLATE entries (ignored by the reference, which skips
+ * extra fields, otezip.c:429-437): id 'OZ', then {u8 version=1, u8 0, u16 0, u32 chunk_bytes, u32 n_chunks,
+ * u32 csize[n_chunks]}.  Each chunk is an independently decodable run of DEFLATE blocks (k_deflate.cuh). */
+#define OZ_EXTRA_ID 0x5A4Fu
+#define OZ_EXTRA_MAX_CHUNKS 16000u
 
 /* otezip.c:157-166 */
 int otezip_verify_crc = 0;
@@ -54,6 +59,11 @@ struct otz_pending {              /* a queued source (write path) */
 	uint64_t len;
 	int owned;                    /* free(buf) after the archive is written */
 };
+
+static int index_enabled(void) {
+	const char *e = getenv ("OTEZIP_NO_INDEX");
+	return !(e && e[0] == '1');
+}
 
 struct otz_archive {
 	struct zip pub;
@@ -556,7 +566,55 @@ static int load_image(struct otz_archive *a) {
 	return 0;
 }
 
-/* Decode a batch starting at `index`: consecutive entries until the byte budget is reached. */
+/* Chunk index of an entry (LFH extra field 'OZ'), validated against the directory values.  Returns the number of
+ * chunks (>= 2) and points *csize at the u32 LE array inside the image, or 0 when the entry has no usable index. */
+static uint32_t chunk_index_of(const struct otz_archive *a, const struct otezip_entry *e, uint32_t *chunk_bytes, const uint8_t **csize,
+	uint64_t *data_ofs) {
+	if (!index_enabled () || e->method != OTEZIP_METHOD_DEFLATE || (uint64_t)e->local_hdr_ofs + 30 > a->image_len) {
+		return 0;
+	}
+	const uint8_t *lfh = a->image + e->local_hdr_ofs;
+	if (otezip_read_le32 (lfh) != SIG_LFH) {
+		return 0;
+	}
+	const uint64_t nl = otezip_read_le16 (lfh + 26), xl = otezip_read_le16 (lfh + 28);
+	const uint64_t xofs = (uint64_t)e->local_hdr_ofs + 30 + nl;
+	if (xofs + xl + e->comp_size > a->image_len) {
+		return 0;
+	}
+	const uint8_t *x = a->image + xofs;
+	for (uint64_t o = 0; o + 4 <= xl;) {
+		const uint32_t id = otezip_read_le16 (x + o), sz = otezip_read_le16 (x + o + 2);
+		if (o + 4 + sz > xl) {
+			return 0;
+		}
+		if (id == OZ_EXTRA_ID && sz >= 12 && x[o + 4] == 1) {
+			const uint32_t cb = otezip_read_le32 (x + o + 8), nc = otezip_read_le32 (x + o + 12);
+			if (cb == 0 || cb > 65535 || nc < 2 || nc > OZ_EXTRA_MAX_CHUNKS || sz != 12 + 4 * nc ||
+				(uint64_t)nc != ((uint64_t)e->uncomp_size + cb - 1) / cb) {
+				return 0;
+			}
+			uint64_t sum = 0;
+			for (uint32_t c = 0; c < nc; c++) {
+				sum += otezip_read_le32 (x + o + 16 + 4 * c);
+			}
+			if (sum != e->comp_size) {
+				return 0;
+			}
+			*chunk_bytes = cb;
+			*csize = x + o + 16;
+			*data_ofs = xofs + xl;
+			return nc;
+		}
+		o += 4 + sz;
+	}
+	return 0;
+}
+
+/* Decode a batch starting at `index`: consecutive entries until the byte budget is reached.  Entries that carry
+ * a chunk index become one parent row plus one row per chunk; if any chunk fails (or the CRC of the assembled
+ * entry does not match) the entry is decoded again as one plain stream, so a wrong index can never change the
+ * result the reference's sequential decoder would produce. */
 static struct otz_window *run_window(struct otz_archive *a, zip_uint64_t index) {
 	zip_t *za = &a->pub;
 	otz_ctx *ctx = otezip_b200_ctx ();
@@ -575,11 +633,23 @@ static struct otz_window *run_window(struct otz_archive *a, zip_uint64_t index) 
 		last++;
 	}
 	const uint32_t n = (uint32_t)(last - index);
+	/* pass 0 counts rows, pass 1 fills them */
+	uint32_t n_rows = n;
+	for (uint32_t k = 0; k < n; k++) {
+		uint32_t cb;
+		const uint8_t *cs;
+		uint64_t dofs;
+		n_rows += chunk_index_of (a, &za->entries[index + k], &cb, &cs, &dofs);
+	}
 	struct otz_window *w = (struct otz_window *)calloc (1, sizeof (*w));
-	otz_entry *tab = (otz_entry *)calloc (n, sizeof (otz_entry));
-	if (!w || !tab) {
+	otz_entry *tab = (otz_entry *)calloc (n_rows, sizeof (otz_entry));
+	int32_t *row_status = (int32_t *)calloc (n_rows, sizeof (int32_t));
+	uint32_t *row_crc = (uint32_t *)calloc (n_rows, sizeof (uint32_t));
+	if (!w || !tab || !row_status || !row_crc) {
 		free (w);
 		free (tab);
+		free (row_status);
+		free (row_crc);
 		return NULL;
 	}
 	w->first = index;
@@ -588,6 +658,7 @@ static struct otz_window *run_window(struct otz_archive *a, zip_uint64_t index) 
 	w->status = (int32_t *)calloc (n, sizeof (int32_t));
 	w->crc = (uint32_t *)calloc (n, sizeof (uint32_t));
 	uint64_t out = 0;
+	uint32_t next_row = n; /* chunk rows follow the n entry rows */
 	for (uint32_t k = 0; k < n; k++) {
 		const struct otezip_entry *e = &za->entries[index + k];
 		tab[k].lfh_ofs = e->local_hdr_ofs;
@@ -596,6 +667,27 @@ static struct otz_window *run_window(struct otz_archive *a, zip_uint64_t index) 
 		tab[k].uncomp_size = e->uncomp_size;
 		tab[k].crc32 = e->crc32;
 		tab[k].method = e->method;
+		uint32_t cb = 0;
+		const uint8_t *cs = NULL;
+		uint64_t dofs = 0;
+		const uint32_t nc = chunk_index_of (a, e, &cb, &cs, &dofs);
+		if (nc) {
+			tab[k].flags = OTZ_EF_PARENT;
+			uint64_t cofs = dofs, uofs = 0;
+			for (uint32_t c = 0; c < nc; c++) {
+				otz_entry *r = &tab[next_row++];
+				const uint32_t csz = otezip_read_le32 (cs + 4 * c);
+				r->lfh_ofs = cofs;
+				r->out_ofs = out + uofs;
+				r->comp_size = csz;
+				r->uncomp_size = (uint32_t)((uint64_t)e->uncomp_size - uofs < cb ? (uint64_t)e->uncomp_size - uofs : cb);
+				r->crc32 = k; /* parent row */
+				r->method = OTZ_M_DEFLATE;
+				r->flags = (uint16_t)(OTZ_EF_CHUNK | (c + 1 == nc ? OTZ_EF_LAST_CHUNK : 0));
+				cofs += csz;
+				uofs += r->uncomp_size;
+			}
+		}
 		w->ofs[k] = out;
 		out += ((uint64_t)e->uncomp_size + 15) & ~15ULL;
 	}
@@ -609,9 +701,48 @@ static struct otz_window *run_window(struct otz_archive *a, zip_uint64_t index) 
 	int rc = otz_host_alloc (out + 64, &arena);
 	if (rc == OTZ_SUCCESS) {
 		w->arena = (uint8_t *)arena;
-		rc = otz_extract_host (ctx, a->image, a->image_len, tab, n, &o, w->arena, out, w->crc, w->status);
+		rc = otz_extract_host (ctx, a->image, a->image_len, tab, n_rows, &o, w->arena, out, row_crc, row_status);
+	}
+	/* entries whose indexed decode did not come out clean are decoded again as plain streams */
+	uint32_t n_redo = 0;
+	for (uint32_t k = 0; rc == OTZ_SUCCESS && k < n; k++) {
+		if ((tab[k].flags & OTZ_EF_PARENT) && row_status[k] != OTZ_ST_OK) {
+			n_redo++;
+		}
+	}
+	if (rc == OTZ_SUCCESS && n_redo) {
+		otz_entry *rt = (otz_entry *)calloc (n_redo, sizeof (otz_entry));
+		int32_t *rs = (int32_t *)calloc (n_redo, sizeof (int32_t));
+		uint32_t *rcv = (uint32_t *)calloc (n_redo, sizeof (uint32_t)), *map = (uint32_t *)calloc (n_redo, sizeof (uint32_t));
+		if (rt && rs && rcv && map) {
+			uint32_t m = 0;
+			for (uint32_t k = 0; k < n; k++) {
+				if ((tab[k].flags & OTZ_EF_PARENT) && row_status[k] != OTZ_ST_OK) {
+					rt[m] = tab[k];
+					rt[m].flags = 0;
+					map[m++] = k;
+				}
+			}
+			rc = otz_extract_host (ctx, a->image, a->image_len, rt, n_redo, &o, w->arena, out, rcv, rs);
+			for (uint32_t i = 0; rc == OTZ_SUCCESS && i < n_redo; i++) {
+				row_status[map[i]] = rs[i];
+				row_crc[map[i]] = rcv[i];
+			}
+		} else {
+			rc = OTZ_ERR_NOMEM;
+		}
+		free (rt);
+		free (rs);
+		free (rcv);
+		free (map);
+	}
+	for (uint32_t k = 0; k < n; k++) {
+		w->status[k] = row_status[k];
+		w->crc[k] = row_crc[k];
 	}
 	free (tab);
+	free (row_status);
+	free (row_crc);
 	if (rc != OTZ_SUCCESS) {
 		fprintf (stderr, "otezip-b200: GPU extract failed: %s\n", otz_last_error ());
 		free_window (w);
@@ -875,7 +1006,7 @@ int zip_replace(zip_t *za, zip_uint64_t index, zip_source_t *src) {
 }
 
 /* otezip.c:1443-1491 */
-static int write_lfh(FILE *fp, const struct otezip_entry *e) {
+static int write_lfh(FILE *fp, const struct otezip_entry *e, const uint8_t *extra, uint16_t extra_len) {
 	uint8_t h[30];
 	uint16_t t, d;
 	size_t nl = strlen (e->name);
@@ -890,8 +1021,11 @@ static int write_lfh(FILE *fp, const struct otezip_entry *e) {
 	otezip_write_le32 (h + 18, e->comp_size);
 	otezip_write_le32 (h + 22, e->uncomp_size);
 	otezip_write_le16 (h + 26, (uint16_t)nl);
-	otezip_write_le16 (h + 28, 0);
-	return fwrite (h, 1, 30, fp) == 30 && fwrite (e->name, 1, nl, fp) == nl ? 0 : -1;
+	otezip_write_le16 (h + 28, extra_len);
+	return fwrite (h, 1, 30, fp) == 30 && fwrite (e->name, 1, nl, fp) == nl &&
+			(!extra_len || fwrite (extra, 1, extra_len, fp) == extra_len)
+		? 0
+		: -1;
 }
 
 /* otezip.c:1494-1558 */
@@ -971,9 +1105,31 @@ static int finalize_archive(struct otz_archive *a) {
 			}
 		}
 		uint64_t out_total = 0;
-		if (otz_deflate_host (ctx, in, total, in_ofs, in_len, method, (uint32_t)n_new, out, total, out_ofs, out_size, crc, method_out,
-			&out_total) != OTZ_SUCCESS) {
+		otz_deflate_job *job = NULL;
+		void *d_in = NULL;
+		uint32_t *first_chunk = (uint32_t *)calloc (n_new, 4), *n_chunks = (uint32_t *)calloc (n_new, 4), *csize = NULL;
+		uint32_t chunk_bytes = 0;
+		int ok = first_chunk && n_chunks && otz_deflate_plan (ctx, in_ofs, in_len, method, (uint32_t)n_new, &job) == OTZ_SUCCESS &&
+			otz_dev_alloc (ctx, total, &d_in) == OTZ_SUCCESS && otz_h2d (ctx, d_in, in, total) == OTZ_SUCCESS &&
+			otz_deflate_run (ctx, job, (const uint8_t *)d_in, total) == OTZ_SUCCESS &&
+			otz_deflate_results (ctx, job, out_ofs, out_size, crc, method_out, &out_total) == OTZ_SUCCESS && out_total <= total &&
+			otz_deflate_fetch (ctx, job, out, out_total) == OTZ_SUCCESS;
+		if (ok) {
+			int nc_total = otz_deflate_chunks (ctx, job, first_chunk, n_chunks, NULL, 0, &chunk_bytes);
+			csize = nc_total > 0 ? (uint32_t *)calloc ((size_t)nc_total, 4) : NULL;
+			if (nc_total > 0 && (!csize || otz_deflate_chunks (ctx, job, NULL, NULL, csize, (uint32_t)nc_total, NULL) < 0)) {
+				ok = 0;
+			}
+		}
+		if (d_in) {
+			otz_dev_free (ctx, d_in);
+		}
+		otz_deflate_destroy (ctx, job);
+		if (!ok) {
 			fprintf (stderr, "otezip-b200: GPU compress failed: %s\n", otz_last_error ());
+			free (first_chunk);
+			free (n_chunks);
+			free (csize);
 			goto done;
 		}
 		for (zip_uint64_t k = 0; k < n_new; k++) {
@@ -982,13 +1138,42 @@ static int finalize_archive(struct otz_archive *a) {
 			e->comp_size = out_size[k];
 			e->method = method_out[k];
 			if (pos > 0xFFFFFFFFULL) { /* otezip.c:1140 */
-				goto done;
+				ok = 0;
+				break;
 			}
 			e->local_hdr_ofs = (uint32_t)pos;
-			if (write_lfh (za->fp, e) != 0 || (out_size[k] && fwrite (out + out_ofs[k], 1, out_size[k], za->fp) != out_size[k])) {
-				goto done;
+			/* chunk index for multi-chunk DEFLATE entries */
+			uint8_t *extra = NULL;
+			uint16_t extra_len = 0;
+			if (index_enabled () && e->method == OTEZIP_METHOD_DEFLATE && n_chunks[k] >= 2 && n_chunks[k] <= OZ_EXTRA_MAX_CHUNKS) {
+				extra_len = (uint16_t)(4 + 12 + 4 * n_chunks[k]);
+				extra = (uint8_t *)calloc (1, extra_len);
+				if (extra) {
+					otezip_write_le16 (extra, OZ_EXTRA_ID);
+					otezip_write_le16 (extra + 2, (uint16_t)(extra_len - 4));
+					extra[4] = 1;
+					otezip_write_le32 (extra + 8, chunk_bytes);
+					otezip_write_le32 (extra + 12, n_chunks[k]);
+					for (uint32_t c = 0; c < n_chunks[k]; c++) {
+						otezip_write_le32 (extra + 16 + 4 * c, csize[first_chunk[k] + c]);
+					}
+				} else {
+					extra_len = 0;
+				}
 			}
-			pos += 30 + strlen (e->name) + out_size[k];
+			int wrc = write_lfh (za->fp, e, extra, extra_len);
+			free (extra);
+			if (wrc != 0 || (out_size[k] && fwrite (out + out_ofs[k], 1, out_size[k], za->fp) != out_size[k])) {
+				ok = 0;
+				break;
+			}
+			pos += 30 + strlen (e->name) + extra_len + out_size[k];
+		}
+		free (first_chunk);
+		free (n_chunks);
+		free (csize);
+		if (!ok) {
+			goto done;
 		}
 	}
 	{

@@ -43,7 +43,30 @@ __device__ __forceinline__ void tile_copy(uint8_t *__restrict__ dst, const uint8
 		const uint32_t sh = (uint32_t)(sa & 3) * 8;
 		const uint32_t *w = reinterpret_cast<const uint32_t *>(sa & ~3ull);
 		uint4 *d4 = reinterpret_cast<uint4 *>(dst);
-		for (uint64_t v = lane; v < nv; v += G) {
+		uint64_t v = lane;
+		// 4 vectors per lane per trip: 20 independent word loads in flight before the first store
+		for (; v + 3 * G < nv; v += 4 * G) {
+			uint32_t a[4][5];
+#pragma unroll
+			for (int k = 0; k < 4; k++) {
+				const uint32_t *p = w + 4 * (v + k * G);
+#pragma unroll
+				for (int i = 0; i < 4; i++) {
+					a[k][i] = __ldg(p + i);
+				}
+				a[k][4] = sh ? __ldg(p + 4) : 0u;
+			}
+#pragma unroll
+			for (int k = 0; k < 4; k++) {
+				uint4 o;
+				o.x = __funnelshift_r(a[k][0], a[k][1], sh);
+				o.y = __funnelshift_r(a[k][1], a[k][2], sh);
+				o.z = __funnelshift_r(a[k][2], a[k][3], sh);
+				o.w = __funnelshift_r(a[k][3], a[k][4], sh);
+				d4[v + k * G] = o;
+			}
+		}
+		for (; v < nv; v += G) {
 			const uint32_t *p = w + 4 * v;
 			uint32_t w0 = __ldg(p), w1 = __ldg(p + 1), w2 = __ldg(p + 2), w3 = __ldg(p + 3);
 			uint32_t w4 = sh ? __ldg(p + 4) : 0u;

@@ -293,8 +293,8 @@ __global__ void k_crc_finalize(const otz_entry *__restrict__ ents, uint32_t n, c
 		return;
 	}
 	int32_t st = status[i];
-	if (OTZ_ST_CODE(st) != OTZ_ST_OK) {
-		crc_out[i] = 0;
+	if (OTZ_ST_CODE(st) != OTZ_ST_OK || (ents[i].flags & OTZ_EF_CHUNK)) {
+		crc_out[i] = 0;   // failed, or a chunk row (its parent row carries the CRC)
 		return;
 	}
 	uint32_t N = ents[i].uncomp_size;

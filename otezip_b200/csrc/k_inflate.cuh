@@ -572,10 +572,12 @@ __device__ __forceinline__ int inflate_event(const Tile &tile, const InflateSmem
 // Decode one raw stream.  Returns the status word; *produced = bytes written.
 template <int G, int W, typename Tile>
 __device__ __forceinline__ int32_t inflate_stream(const Tile &tile, InflateSmemV2<G, W> &SS, const uint8_t *__restrict__ in, uint32_t comp,
-	uint8_t *__restrict__ out, uint32_t cap, uint32_t *produced) {
+	uint8_t *__restrict__ out, uint32_t cap, uint32_t *produced, uint32_t row_flags) {
 	const int lane = tile.thread_rank();
 	InflateSmem &S = SS.t;
 	*produced = 0;
+	// a chunk row stops at the block boundary where its input ends (the last chunk at the stream's final block)
+	const bool chunk_mid = (row_flags & OTZ_EF_CHUNK) && !(row_flags & OTZ_EF_LAST_CHUNK);
 	if (comp == 0) {
 		return OTZ_ST_TRUNCATED;  // dec:610: the loop never runs; Z_OK or Z_BUF_ERROR, never STREAM_END
 	}
@@ -644,6 +646,9 @@ __device__ __forceinline__ int32_t inflate_stream(const Tile &tile, InflateSmemV
 				break;
 			}
 			if (npos >= comp) {  // dec:811-816 after a non-final stored block
+				if (chunk_mid) {
+					break;   // end of this chunk
+				}
 				ref_eob = true;
 			}
 			continue;
@@ -701,6 +706,9 @@ __device__ __forceinline__ int32_t inflate_stream(const Tile &tile, InflateSmemV
 			}
 			break;  // dec:714-716
 		}
+		if (chunk_mid && br.remaining_bits() < 8 && br.remaining_bits() >= 0) {
+			break;   // end of this chunk
+		}
 		INF_STEP_CHECK();
 	}
 #undef INF_STEP_CHECK
@@ -709,6 +717,9 @@ __device__ __forceinline__ int32_t inflate_stream(const Tile &tile, InflateSmemV
 	*produced = op;
 	if (err) {
 		return err;
+	}
+	if (row_flags & OTZ_EF_CHUNK) {
+		return op == cap ? OTZ_ST_OK : OTZ_ST_SIZE;   // a chunk must fill its slice exactly
 	}
 	return OTZ_ST_OK | (ref_eob ? OTZ_STF_REF_EOB : 0) | (op < cap ? OTZ_STF_SHORT : 0);
 }
@@ -738,7 +749,10 @@ __global__ void __launch_bounds__(256) k_inflate(const uint8_t *__restrict__ arc
 		const otz_entry e = ents[ei];
 		uint8_t *dst = out + e.out_ofs;
 		uint32_t produced = 0;
-		int32_t st = inflate_stream<G, W>(tile, S, archive + est[ei].data_ofs, e.comp_size, dst, e.uncomp_size, &produced);
+		int32_t st = inflate_stream<G, W>(tile, S, archive + est[ei].data_ofs, e.comp_size, dst, e.uncomp_size, &produced, e.flags);
+		if ((e.flags & OTZ_EF_CHUNK) && OTZ_ST_CODE(st) != OTZ_ST_OK && lane == 0) {
+			status[e.crc32] = OTZ_ST_DATA;   // a failing chunk fails its parent row (e.crc32 = parent row)
+		}
 		if (OTZ_ST_CODE(st) == OTZ_ST_OK && produced < e.uncomp_size) {
 			// otezip.c:500 pre-zeroes the buffer and never compares total_out: short streams are zero-padded
 			for (uint64_t i = (uint64_t)produced + lane; i < e.uncomp_size; i += G) {

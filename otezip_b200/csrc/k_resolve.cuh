@@ -19,6 +19,16 @@ __global__ void k_resolve(const uint8_t *__restrict__ archive, uint64_t archive_
 	produced[i] = e.uncomp_size;   // DEFLATE streams that end early overwrite this (zero-padded tail)
 	est[i].data_ofs = 0;
 	int32_t st = OTZ_ST_OK;
+	if (e.flags & OTZ_EF_CHUNK) {
+		// a chunk of an indexed DEFLATE entry: lfh_ofs is the payload offset itself
+		if (e.method != OTZ_M_DEFLATE || e.lfh_ofs > archive_len || archive_len - e.lfh_ofs < e.comp_size || e.out_ofs > out_len ||
+			out_len - e.out_ofs < e.uncomp_size) {
+			st = OTZ_ST_DATA_RANGE;
+		}
+		est[i].data_ofs = e.lfh_ofs;
+		status[i] = st;
+		return;
+	}
 	do {
 		// otezip.c:411-420: seek to the LFH and read 30 bytes
 		if (e.lfh_ofs > archive_len || archive_len - e.lfh_ofs < 30) {

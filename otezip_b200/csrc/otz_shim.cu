@@ -363,8 +363,8 @@ extern "C" int otz_plan_create(otz_ctx *c, const otz_entry *ents, uint32_t n, co
 	for (int pass = 0; pass < 2; pass++) {
 		for (uint32_t i = 0; i < n; i++) {
 			const bool is_store = ents[i].method == OTZ_M_STORE;
-			if ((pass == 0) != is_store || ents[i].method == OTZ_M_ZSTD) {
-				continue;   // method 93 folds its CRC inside k_zstdref
+			if ((pass == 0) != is_store || ents[i].method == OTZ_M_ZSTD || (ents[i].flags & OTZ_EF_CHUNK)) {
+				continue;   // method 93 folds its CRC inside k_zstdref; chunk rows are CRC'd through their parent
 			}
 			const uint32_t nc = (uint32_t)(((uint64_t)ents[i].uncomp_size + OTZ_CRC_CHUNK - 1) / OTZ_CRC_CHUNK);
 			for (uint32_t k = 0; k < nc; k++) {
@@ -377,7 +377,9 @@ extern "C" int otz_plan_create(otz_ctx *c, const otz_entry *ents, uint32_t n, co
 	}
 	for (uint32_t i = 0; i < n; i++) {
 		if (ents[i].method == OTZ_M_DEFLATE) {
-			infl.push_back(i);
+			if (!(ents[i].flags & OTZ_EF_PARENT)) {
+				infl.push_back(i);   // a parent row is decoded through its chunk rows
+			}
 		} else if (ents[i].method == OTZ_M_ZSTD) {
 			zst.push_back(i);
 		}
@@ -844,6 +846,42 @@ extern "C" int otz_deflate_results(otz_ctx *c, otz_deflate_job *j, uint64_t *out
 }
 
 extern "C" const uint8_t *otz_deflate_device_output(otz_deflate_job *j) { return j ? j->d_dense : nullptr; }
+
+extern "C" int otz_deflate_chunks(otz_ctx *c, otz_deflate_job *j, uint32_t *first_chunk, uint32_t *n_chunks, uint32_t *csize, uint32_t csize_cap,
+	uint32_t *chunk_bytes) {
+	if (!c || !j) {
+		return OTZ_ERR_ARG;
+	}
+	CK(cudaSetDevice(c->device));
+	if (chunk_bytes) {
+		*chunk_bytes = DFL_CHUNK;
+	}
+	if (csize) {
+		if (csize_cap < j->n_chunks) {
+			return OTZ_ERR_ARG;
+		}
+		if (j->n_chunks) {
+			CK(cudaMemcpyAsync(csize, j->d_csize, (size_t)j->n_chunks * 4, cudaMemcpyDeviceToHost, c->stream));
+		}
+	}
+	if (first_chunk || n_chunks) {
+		std::vector<OtzDflEntry> ev(j->n);
+		if (j->n) {
+			CK(cudaMemcpyAsync(ev.data(), j->d_ents, (size_t)j->n * sizeof(OtzDflEntry), cudaMemcpyDeviceToHost, c->stream));
+		}
+		CK(cudaStreamSynchronize(c->stream));
+		for (uint32_t i = 0; i < j->n; i++) {
+			if (first_chunk) {
+				first_chunk[i] = ev[i].first_chunk;
+			}
+			if (n_chunks) {
+				n_chunks[i] = ev[i].n_chunks;
+			}
+		}
+	}
+	CK(cudaStreamSynchronize(c->stream));
+	return (int)j->n_chunks;
+}
 
 extern "C" int otz_deflate_fetch(otz_ctx *c, otz_deflate_job *j, uint8_t *out, uint64_t bytes) {
 	if (!c || !j || (bytes && !out) || bytes > j->in_total) {

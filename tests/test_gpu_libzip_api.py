@@ -157,3 +157,52 @@ def test_cli_gzip_modes_on_the_gpu_path(tmp_path):
             assert r.returncode == 0, r.stderr
             assert (tmp_path / "back.out").read_bytes() == data
             os.unlink(tmp_path / "back.out")
+
+
+def _lfh_extra(img: bytes, lfh_ofs: int) -> bytes:
+    import struct
+    sig, = struct.unpack_from("<I", img, lfh_ofs)
+    assert sig == 0x04034B50
+    nl, xl = struct.unpack_from("<HH", img, lfh_ofs + 26)
+    return img[lfh_ofs + 30 + nl:lfh_ofs + 30 + nl + xl]
+
+
+def test_chunk_index_roundtrip_and_fallback(api, tmp_path, reflib):
+    """Multi-chunk DEFLATE entries written by this library carry a chunk index in the LFH extra field; reading
+    decodes the chunks in parallel.  The reference (which skips extra fields) reads the same archive, and a
+    corrupted index must fall back to the sequential decode with identical bytes."""
+    import struct
+    files = [("big.json", synth.jsonlog_text(3 << 20, 31)), ("mid.json", synth.jsonlog_text(200000, 32)),
+             ("one-chunk.json", synth.jsonlog_text(60000, 33)), ("rand.bin", synth.random_bytes(300000, 34)),
+             ("mixed.bin", synth.jsonlog_text(150000, 35) + synth.random_bytes(140000, 36) + synth.jsonlog_text(100000, 37))]
+    p = str(tmp_path / "idx.zip")
+    assert api.write_archive(p, files, ZIP_CM_DEFLATE) == 0
+    want = [f[1] for f in files]
+    img = open(p, "rb").read()
+    with zipfile.ZipFile(p) as z:
+        assert z.testzip() is None
+        infos = z.infolist()
+    x = _lfh_extra(img, infos[0].header_offset)
+    hid, hsz, ver = struct.unpack_from("<HHB", x, 0)
+    cb, nc = struct.unpack_from("<II", x, 8)
+    assert (hid, ver, cb) == (0x5A4F, 1, 65280) and nc == -(-len(want[0]) // 65280) and hsz == 12 + 4 * nc
+    assert _lfh_extra(img, infos[2].header_offset) == b"" and _lfh_extra(img, infos[3].header_offset) == b""   # 1 chunk / STORE
+    err, names, datas = api.read_all(p)
+    assert datas == want
+    e2, got = reflib.extract_file(p, verify_crc=1)          # the reference skips the extra field and decodes sequentially
+    assert e2 == 0 and got == want
+    # without the index: same bytes
+    os.environ["OTEZIP_NO_INDEX"] = "1"
+    try:
+        assert api.read_all(p)[2] == want
+    finally:
+        del os.environ["OTEZIP_NO_INDEX"]
+    # a lying index (two chunk sizes swapped: the sum still matches) must not change the result
+    b = bytearray(img)
+    xo = infos[0].header_offset + 30 + len(b"big.json") + 16
+    s0, s1 = struct.unpack_from("<II", b, xo)
+    assert s0 != s1
+    struct.pack_into("<II", b, xo, s1, s0)
+    q = str(tmp_path / "lie.zip")
+    open(q, "wb").write(bytes(b))
+    assert api.read_all(q)[2] == want
