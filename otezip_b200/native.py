@@ -85,6 +85,7 @@ class Lib:
         L.otz_deflate_device_output.argtypes = [vp]
         L.otz_deflate_device_output.restype = vp
         L.otz_deflate_fetch.argtypes = [vp, vp, vp, u64]
+        L.otz_deflate_chunks.argtypes = [vp, vp, vp, vp, vp, C.c_uint32, C.POINTER(C.c_uint32)]
         L.otz_deflate_host.argtypes = [vp, vp, u64, vp, vp, vp, C.c_uint32, vp, u64, vp, vp, vp, vp, C.POINTER(u64)]
 
     @classmethod
@@ -96,6 +97,45 @@ class Lib:
     def check(self, rc: int, what: str = ""):
         if rc != 0:
             raise RuntimeError("%s failed (%d): %s" % (what, rc, self.L.otz_last_error().decode()))
+
+
+EF_PARENT, EF_CHUNK, EF_LAST_CHUNK = 1, 2, 4
+
+
+def expand_chunk_index(img, tab: np.ndarray) -> np.ndarray:
+    """Host-side mirror of otezip.c:chunk_index_of/run_window: entries whose LFH extra field carries the 'OZ' chunk
+    index become a PARENT row plus one CHUNK row per chunk (appended after the entry rows)."""
+    b = memoryview(img)
+    rows = []
+    out = tab.copy()
+    for k in range(len(tab)):
+        if int(tab["method"][k]) != 8:
+            continue
+        lfh = int(tab["lfh_ofs"][k])
+        nl, xl = struct.unpack_from("<HH", b, lfh + 26)
+        x = bytes(b[lfh + 30 + nl:lfh + 30 + nl + xl])
+        o = 0
+        while o + 4 <= len(x):
+            hid, sz = struct.unpack_from("<HH", x, o)
+            if hid == 0x5A4F and sz >= 12 and x[o + 4] == 1:
+                cb, nc = struct.unpack_from("<II", x, o + 8)
+                cs = struct.unpack_from("<%dI" % nc, x, o + 16)
+                un = int(tab["uncomp_size"][k])
+                if nc >= 2 and nc == -(-un // cb) and sum(cs) == int(tab["comp_size"][k]):
+                    out["flags"][k] = EF_PARENT
+                    cofs, uofs = lfh + 30 + nl + xl, 0
+                    for c in range(nc):
+                        u = min(cb, un - uofs)
+                        rows.append((cofs, int(tab["out_ofs"][k]) + uofs, cs[c], u, k, 8,
+                                     EF_CHUNK | (EF_LAST_CHUNK if c + 1 == nc else 0)))
+                        cofs += cs[c]
+                        uofs += u
+                break
+            o += 4 + sz
+    if not rows:
+        return out
+    extra = np.array(rows, dtype=ENTRY_DTYPE)
+    return np.concatenate([out, extra])
 
 
 def parse_central(img) -> np.ndarray:
@@ -305,3 +345,19 @@ class Ctx:
 
     def deflate_destroy(self, job):
         self.L.otz_deflate_destroy(self.h, job)
+
+    def deflate_chunks(self, job, n: int):
+        """-> (first_chunk[n], n_chunks[n], csize[total], chunk_bytes)"""
+        first = np.zeros(max(n, 1), dtype=np.uint32)
+        cnt = np.zeros(max(n, 1), dtype=np.uint32)
+        cb = C.c_uint32()
+        vp = lambda a: a.ctypes.data_as(C.c_void_p)
+        tot = self.L.otz_deflate_chunks(self.h, job, vp(first), vp(cnt), None, 0, C.byref(cb))
+        if tot < 0:
+            self.lib.check(tot, "otz_deflate_chunks")
+        cs = np.zeros(max(tot, 1), dtype=np.uint32)
+        if tot:
+            r = self.L.otz_deflate_chunks(self.h, job, None, None, vp(cs), tot, None)
+            if r < 0:
+                self.lib.check(r, "otz_deflate_chunks")
+        return first[:n], cnt[:n], cs[:tot], int(cb.value)
