@@ -189,7 +189,9 @@ __global__ void __launch_bounds__(256, 2) k_zstdref(const uint8_t *__restrict__ 
 		}
 		if (lane == 0) {
 			if (st != OTZ_ST_OK) {
-				status[ei] = st;
+				// not a consistent reference container: if it carries the Zstandard magic, k_zstd tries it as an
+				// RFC 8878 frame (the reference itself would reject it either way)
+				status[ei] = (n >= 4 && ld_le32(in) == 0xFD2FB528u) ? OTZ_ST_PENDING : st;
 			} else {
 				acc[ei] = rtot;
 			}

@@ -258,7 +258,7 @@ struct OtzCrcChunk {
 __global__ void __launch_bounds__(256, 2) k_crc_chunks(const uint8_t *__restrict__ archive, const uint8_t *__restrict__ out,
 	const otz_entry *__restrict__ ents, const OtzEntryState *__restrict__ est, const int32_t *__restrict__ status,
 	const OtzCrcChunk *__restrict__ chunks, uint32_t n_chunks, uint32_t *__restrict__ acc, const OtzCrcTables *__restrict__ tabs,
-	int verify_only) {
+	int verify_only, int only_ref_rejected) {
 	__shared__ __align__(16) uint32_t s_skip[16 * 256];
 	crc_tables_to_smem(s_skip, tabs);
 	__syncthreads();
@@ -267,8 +267,9 @@ __global__ void __launch_bounds__(256, 2) k_crc_chunks(const uint8_t *__restrict
 	const int lane = threadIdx.x & 31;
 	for (uint32_t c = blockIdx.x * warps_per_cta + (threadIdx.x >> 5); c < n_chunks; c += total_warps) {
 		const OtzCrcChunk ck = chunks[c];
-		if (OTZ_ST_CODE(status[ck.entry]) != OTZ_ST_OK) {
-			continue;
+		const int32_t est_ = status[ck.entry];
+		if (OTZ_ST_CODE(est_) != OTZ_ST_OK || (only_ref_rejected && !(est_ & OTZ_STF_REF_EOB))) {
+			continue;   // failed; or (method 93) already CRC'd inside k_zstdref
 		}
 		const otz_entry e = ents[ck.entry];
 		const uint64_t off = (uint64_t)ck.chunk * OTZ_CRC_CHUNK;

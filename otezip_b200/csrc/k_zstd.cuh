@@ -1,0 +1,870 @@
+// k_zstd.cuh — Zstandard (RFC 8878) frame decoder, one warp per entry.
+//
+// The reference's method 93 is NOT Zstandard: it accepts only its own raw-block container
+// (/root/reference/src/lib/zstd.inc.c:479-705) and rejects real frames; k_zstdref reproduces
+// that.  This kernel is what BASELINE.json's north_star additionally asks for (FSE / Huffman decode on
+// the GPU): entries that are not a consistent reference container are tried as RFC 8878 frames.  Since the
+// reference would reject them, a successful decode is reported with OTZ_STF_REF_EOB ("valid stream the
+// reference rejects"), so the default reference-compatible policy still matches the reference bit for bit.
+// Parity for this kernel is pinned against libzstd 1.5.5 (tests/test_gpu_zstd.py), not against the reference.
+//
+// Work split inside the warp (first correct version, not tuned):
+//   * lane 0 parses headers and builds the FSE / Huffman tables in shared memory;
+//   * Huffman literals: the 4 streams of a block are decoded by lanes 0..3 into a per-warp scratch in HBM;
+//   * sequences: lane 0 runs the three interleaved FSE states over the backward bitstream and queues up to 32
+//     (literal length, match length, offset) triples in shared memory, then all lanes execute them
+//     (literal copy from the scratch, match copy from the output already written).
+#pragma once
+#include "otz_common.cuh"
+#include "k_copy.cuh"
+
+#define ZS_BLOCK_MAX (128u * 1024u)
+#define ZS_HUF_LOG_MAX 11
+#define ZS_LL_LOG_MAX 9
+#define ZS_ML_LOG_MAX 9
+#define ZS_OF_LOG_MAX 8
+
+struct __align__(16) ZstdSmem {
+	uint16_t huf[1 << ZS_HUF_LOG_MAX];   // (symbol << 8) | nbits
+	uint32_t ll[1 << ZS_LL_LOG_MAX];     // symbol | nbits << 8 | new-state base << 16
+	uint32_t ml[1 << ZS_ML_LOG_MAX];
+	uint32_t of[1 << ZS_OF_LOG_MAX];
+	uint32_t seq_ll[32], seq_ml[32], seq_of[32];
+	uint32_t huf_log, ll_log, ml_log, of_log;
+	uint32_t have_huf, have_ll, have_ml, have_of;
+	int32_t err;
+	uint32_t n_batch;
+	uint32_t lit_sizes[4];   // regenerated sizes / stream byte offsets for the 4-stream literal decode
+	uint32_t lit_ofs[5];
+	uint32_t huf_used;       // bytes taken by the Huffman tree description
+	uint32_t seq_start;      // offset of the sequence bitstream inside the sequences section
+};
+
+__constant__ int16_t c_zs_ll_default[36] = { 4, 3, 2, 2, 2, 2, 2, 2, 2, 2, 2, 2, 2, 1, 1, 1, 2, 2, 2, 2, 2, 2, 2, 2, 2, 3, 2, 1, 1, 1, 1, 1, -1, -1, -1, -1 };
+__constant__ int16_t c_zs_ml_default[53] = { 1, 4, 3, 2, 2, 2, 2, 2, 2, 1, 1, 1, 1, 1, 1, 1, 1, 1, 1, 1, 1, 1, 1, 1, 1, 1, 1, 1, 1, 1, 1, 1, 1, 1, 1, 1, 1, 1, 1, 1, 1, 1, 1, 1, 1, 1, -1, -1, -1, -1, -1, -1, -1 };
+__constant__ int16_t c_zs_of_default[29] = { 1, 1, 1, 1, 1, 1, 2, 2, 2, 1, 1, 1, 1, 1, 1, 1, 1, 1, 1, 1, 1, 1, 1, 1, -1, -1, -1, -1, -1 };
+__constant__ uint32_t c_zs_ll_base[36] = { 0, 1, 2, 3, 4, 5, 6, 7, 8, 9, 10, 11, 12, 13, 14, 15, 16, 18, 20, 22, 24, 28, 32, 40, 48, 64, 128, 256, 512, 1024, 2048, 4096, 8192, 16384, 32768, 65536 };
+__constant__ uint8_t c_zs_ll_bits[36] = { 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 1, 1, 1, 1, 2, 2, 3, 3, 4, 6, 7, 8, 9, 10, 11, 12, 13, 14, 15, 16 };
+__constant__ uint32_t c_zs_ml_base[53] = { 3, 4, 5, 6, 7, 8, 9, 10, 11, 12, 13, 14, 15, 16, 17, 18, 19, 20, 21, 22, 23, 24, 25, 26, 27, 28, 29, 30, 31, 32, 33, 34, 35, 37, 39, 41, 43, 47, 51, 59, 67, 83, 99, 131, 259, 515, 1027, 2051, 4099, 8195, 16387, 32771, 65539 };
+__constant__ uint8_t c_zs_ml_bits[53] = { 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 1, 1, 1, 1, 2, 2, 3, 3, 4, 4, 5, 7, 8, 9, 10, 11, 12, 13, 14, 15, 16 };
+
+// ---- forward (LSB-first) bit reader over a byte range, used for FSE table descriptions
+struct ZsFwd {
+	const uint8_t *p;
+	uint32_t n;        // bytes available
+	uint32_t bit;      // bits consumed
+	__device__ __forceinline__ uint32_t peek(uint32_t nb) const {   // nb <= 24
+		const uint32_t by = bit >> 3;
+		uint32_t v = 0;
+		for (uint32_t i = 0; i < 4; i++) {
+			v |= (by + i < n ? (uint32_t)p[by + i] : 0u) << (8 * i);
+		}
+		return (v >> (bit & 7)) & ((1u << nb) - 1u);
+	}
+};
+
+// ---- backward bit reader (RFC 8878 4.1): the stream is a little-endian integer read from its top
+struct ZsBack {
+	const uint8_t *p;
+	int32_t pos;       // bits still unread (can go negative: over-read)
+	__device__ __forceinline__ bool init(const uint8_t *base, uint32_t n) {
+		p = base;
+		if (n == 0 || base[n - 1] == 0) {
+			pos = 0;
+			return false;
+		}
+		pos = (int32_t)(8 * (n - 1) + (31 - __clz((uint32_t)base[n - 1])));   // the highest set bit is the end mark
+		return true;
+	}
+	// nb bits below the current position, zero filled below bit 0 (nb <= 32)
+	__device__ __forceinline__ uint32_t peek(uint32_t nb) const {
+		if (nb == 0) {
+			return 0;
+		}
+		int32_t lo = pos - (int32_t)nb;
+		uint32_t sh = 0;
+		if (lo < 0) {
+			sh = (uint32_t)(-lo);
+			if (sh >= nb) {
+				return 0;
+			}
+			lo = 0;
+		}
+		const uint32_t by = (uint32_t)lo >> 3;
+		uint64_t v = 0;
+		const uint32_t need = ((uint32_t)(lo & 7) + (nb - sh) + 7) >> 3;
+		for (uint32_t i = 0; i < need; i++) {
+			v |= (uint64_t)p[by + i] << (8 * i);
+		}
+		const uint32_t got = (uint32_t)((v >> (lo & 7)) & ((1ull << (nb - sh)) - 1ull));
+		return got << sh;
+	}
+	__device__ __forceinline__ uint32_t read(uint32_t nb) {
+		const uint32_t v = peek(nb);
+		pos -= (int32_t)nb;
+		return v;
+	}
+};
+
+// FSE_readNCount: normalised counts from a table description; returns bytes consumed, 0 on error
+__device__ uint32_t zs_read_ncount(const uint8_t *p, uint32_t n, int16_t *norm, uint32_t max_sym, uint32_t max_log, uint32_t *log_out,
+	uint32_t *nsym_out) {
+	ZsFwd f = { p, n, 0 };
+	const uint32_t al = f.peek(4) + 5;
+	f.bit += 4;
+	if (al > max_log) {
+		return 0;
+	}
+	int32_t remaining = (1 << al) + 1, threshold = 1 << al;
+	uint32_t nbits = al + 1, sym = 0;
+	bool prev0 = false;
+	while (remaining > 1 && sym <= max_sym) {
+		if (prev0) {
+			uint32_t n0 = sym;
+			for (;;) {
+				const uint32_t r = f.peek(2);
+				f.bit += 2;
+				n0 += r;
+				if (r != 3) {
+					break;
+				}
+			}
+			if (n0 > max_sym + 1) {
+				return 0;
+			}
+			while (sym < n0) {
+				norm[sym++] = 0;
+			}
+			if (sym > max_sym) {
+				break;
+			}
+		}
+		const int32_t mx = (2 * threshold - 1) - remaining;
+		int32_t count;
+		const uint32_t v = f.peek(nbits);
+		if ((int32_t)(v & (uint32_t)(threshold - 1)) < mx) {
+			count = (int32_t)(v & (uint32_t)(threshold - 1));
+			f.bit += nbits - 1;
+		} else {
+			count = (int32_t)(v & (uint32_t)(2 * threshold - 1));
+			if (count >= threshold) {
+				count -= mx;
+			}
+			f.bit += nbits;
+		}
+		count--;   // -1 = "less than one"
+		remaining -= count < 0 ? -count : count;
+		norm[sym++] = (int16_t)count;
+		prev0 = count == 0;
+		while (remaining < threshold) {
+			nbits--;
+			threshold >>= 1;
+		}
+		if ((f.bit >> 3) > n + 4) {
+			return 0;
+		}
+	}
+	if (remaining != 1 || sym > max_sym + 1) {
+		return 0;
+	}
+	*log_out = al;
+	*nsym_out = sym;
+	const uint32_t used = (f.bit + 7) >> 3;
+	return used <= n ? used : 0;
+}
+
+// FSE_buildDTable: entry = symbol | nbBits << 8 | newStateBase << 16
+__device__ void zs_build_fse(uint32_t *tbl, const int16_t *norm, uint32_t nsym, uint32_t al) {
+	const uint32_t size = 1u << al;
+	uint16_t next[64];
+	uint32_t high = size - 1;
+	for (uint32_t s = 0; s < nsym; s++) {
+		if (norm[s] == -1) {
+			tbl[high--] = s;
+			next[s] = 1;
+		} else {
+			next[s] = (uint16_t)norm[s];
+		}
+	}
+	const uint32_t step = (size >> 1) + (size >> 3) + 3, mask = size - 1;
+	uint32_t pos = 0;
+	for (uint32_t s = 0; s < nsym; s++) {
+		for (int i = 0; i < norm[s]; i++) {
+			tbl[pos] = s;
+			pos = (pos + step) & mask;
+			while (pos > high) {
+				pos = (pos + step) & mask;
+			}
+		}
+	}
+	for (uint32_t u = 0; u < size; u++) {
+		const uint32_t s = tbl[u] & 0xFF;
+		const uint32_t ns = next[s]++;
+		const uint32_t nb = al - (31 - __clz(ns));
+		tbl[u] = s | (nb << 8) | (((ns << nb) - size) << 16);
+	}
+}
+
+// Huffman decoding table from weights[0..n) (the last weight is implied); returns table log or 0
+__device__ uint32_t zs_build_huf(uint16_t *tbl, uint8_t *w, uint32_t n) {
+	uint32_t sum = 0;
+	for (uint32_t i = 0; i < n; i++) {
+		if (w[i] > ZS_HUF_LOG_MAX) {
+			return 0;
+		}
+		sum += w[i] ? (1u << (w[i] - 1)) : 0u;
+	}
+	if (sum == 0) {
+		return 0;
+	}
+	const uint32_t log = 32 - __clz(sum);            // next power of two strictly above sum's top bit
+	if (log > ZS_HUF_LOG_MAX) {
+		return 0;
+	}
+	const uint32_t rest = (1u << log) - sum;
+	if (rest == 0 || (rest & (rest - 1))) {
+		return 0;                                      // the implied last weight must be a power of two
+	}
+	w[n] = (uint8_t)(32 - __clz(rest));
+	n++;
+	uint32_t pos = 0;
+	for (uint32_t wt = 1; wt <= log; wt++) {
+		for (uint32_t s = 0; s < n; s++) {
+			if (w[s] == wt) {
+				const uint32_t cnt = 1u << (wt - 1), nb = log + 1 - wt;
+				for (uint32_t k = 0; k < cnt; k++) {
+					tbl[pos++] = (uint16_t)((s << 8) | nb);
+				}
+			}
+		}
+	}
+	return pos == (1u << log) ? log : 0;
+}
+
+// Huffman tree description (RFC 8878 4.2.1); returns bytes consumed or 0
+__device__ uint32_t zs_read_huf(ZstdSmem &S, const uint8_t *p, uint32_t n) {
+	if (n == 0) {
+		return 0;
+	}
+	uint8_t w[257];
+	uint32_t nw = 0, used;
+	const uint32_t hb = p[0];
+	if (hb >= 128) {
+		nw = hb - 127;
+		used = 1 + (nw + 1) / 2;
+		if (used > n) {
+			return 0;
+		}
+		for (uint32_t i = 0; i < nw; i++) {
+			const uint8_t b = p[1 + i / 2];
+			w[i] = (i & 1) ? (b & 15) : (b >> 4);
+		}
+	} else {
+		used = 1 + hb;
+		if (used > n || hb < 2) {
+			return 0;
+		}
+		int16_t norm[16];
+		uint32_t al, nsym;
+		const uint32_t hdr = zs_read_ncount(p + 1, hb, norm, 12, 6, &al, &nsym);
+		if (hdr == 0) {
+			return 0;
+		}
+		uint32_t *tbl = S.seq_ll;   // 64-entry scratch (seq_ll + seq_ml are adjacent); the sequence tables must survive for repeat mode
+		zs_build_fse(tbl, norm, nsym, al);
+		ZsBack b;
+		if (!b.init(p + 1 + hdr, hb - hdr)) {
+			return 0;
+		}
+		uint32_t s1 = b.read(al), s2 = b.read(al);
+		for (;;) {   // two interleaved states until the stream runs dry
+			if (nw >= 255) {
+				return 0;
+			}
+			uint32_t e = tbl[s1];
+			w[nw++] = (uint8_t)(e & 0xFF);
+			if (b.pos < (int32_t)((e >> 8) & 0xFF)) {
+				w[nw++] = (uint8_t)(tbl[s2] & 0xFF);
+				break;
+			}
+			s1 = (e >> 16) + b.read((e >> 8) & 0xFF);
+			if (nw >= 255) {
+				return 0;
+			}
+			e = tbl[s2];
+			w[nw++] = (uint8_t)(e & 0xFF);
+			if (b.pos < (int32_t)((e >> 8) & 0xFF)) {
+				w[nw++] = (uint8_t)(tbl[s1] & 0xFF);
+				break;
+			}
+			s2 = (e >> 16) + b.read((e >> 8) & 0xFF);
+		}
+	}
+	if (nw == 0 || nw > 255) {
+		return 0;
+	}
+	const uint32_t log = zs_build_huf(S.huf, w, nw);
+	if (log == 0) {
+		return 0;
+	}
+	S.huf_log = log;
+	S.have_huf = 1;
+	return used;
+}
+
+// one Huffman-coded stream -> dst[0..count)
+__device__ bool zs_huf_stream(const ZstdSmem &S, const uint8_t *p, uint32_t n, uint8_t *dst, uint32_t count) {
+	ZsBack b;
+	if (!b.init(p, n)) {
+		return false;
+	}
+	const uint32_t log = S.huf_log;
+	for (uint32_t i = 0; i < count; i++) {
+		const uint32_t e = S.huf[b.peek(log)];
+		b.pos -= (int32_t)(e & 0xFF);
+		dst[i] = (uint8_t)(e >> 8);
+	}
+	return b.pos == 0;
+}
+
+// sequence table for one of LL / OF / ML according to its compression mode; returns bytes consumed or -1
+__device__ int zs_seq_table(uint32_t mode, const uint8_t *p, uint32_t n, uint32_t *tbl, uint32_t *log, uint32_t *have, const int16_t *def,
+	uint32_t def_n, uint32_t def_log, uint32_t max_sym, uint32_t max_log) {
+	if (mode == 0) {
+		int16_t norm[53];
+		for (uint32_t i = 0; i < def_n; i++) {
+			norm[i] = def[i];
+		}
+		zs_build_fse(tbl, norm, def_n, def_log);
+		*log = def_log;
+		*have = 1;
+		return 0;
+	}
+	if (mode == 1) {
+		if (n < 1 || p[0] > max_sym) {
+			return -1;
+		}
+		tbl[0] = p[0];   // nbBits 0, base 0: a one-entry table
+		*log = 0;
+		*have = 1;
+		return 1;
+	}
+	if (mode == 2) {
+		int16_t norm[53];
+		uint32_t al, nsym;
+		const uint32_t used = zs_read_ncount(p, n, norm, max_sym, max_log, &al, &nsym);
+		if (used == 0) {
+			return -1;
+		}
+		zs_build_fse(tbl, norm, nsym, al);
+		*log = al;
+		*have = 1;
+		return (int)used;
+	}
+	return *have ? 0 : -1;   // repeat mode needs a previous table
+}
+
+// Decode all frames of one entry.  Whole warp; returns the status code.
+__device__ int32_t zstd_decode_entry(ZstdSmem &S, const uint8_t *__restrict__ in, uint32_t n, uint8_t *__restrict__ out, uint32_t cap,
+	uint8_t *__restrict__ lit /* ZS_BLOCK_MAX + 32 bytes of scratch */, uint32_t *produced) {
+	const int lane = threadIdx.x & 31;
+	uint32_t ip = 0, op = 0;
+	int32_t err = 0;
+	uint32_t n_frames = 0;
+	while (ip < n && !err) {
+		if (n - ip < 4) {
+			err = OTZ_ST_TRUNCATED;
+			break;
+		}
+		const uint32_t magic = ld_le32(in + ip);
+		if ((magic & 0xFFFFFFF0u) == 0x184D2A50u) {   // skippable frame
+			if (n - ip < 8 || n - ip - 8 < ld_le32(in + ip + 4)) {
+				err = OTZ_ST_TRUNCATED;
+				break;
+			}
+			ip += 8 + ld_le32(in + ip + 4);
+			continue;
+		}
+		if (magic != 0xFD2FB528u) {
+			err = OTZ_ST_DATA;
+			break;
+		}
+		ip += 4;
+		if (ip >= n) {
+			err = OTZ_ST_TRUNCATED;
+			break;
+		}
+		// ---- frame header (RFC 8878 3.1.1.1)
+		const uint32_t fhd = in[ip++];
+		const uint32_t fcs_flag = fhd >> 6, single = (fhd >> 5) & 1, has_cksum = (fhd >> 2) & 1, did_flag = fhd & 3;
+		if (fhd & 0x08) {
+			err = OTZ_ST_DATA;
+			break;
+		}
+		const uint32_t did_len = did_flag == 3 ? 4 : did_flag;
+		const uint32_t fcs_len = fcs_flag == 0 ? single : (fcs_flag == 1 ? 2 : fcs_flag == 2 ? 4 : 8);
+		if (n - ip < (single ? 0 : 1) + did_len + fcs_len) {
+			err = OTZ_ST_TRUNCATED;
+			break;
+		}
+		if (!single) {
+			ip++;   // window descriptor: the whole output is addressable here
+		}
+		uint32_t did = 0;
+		for (uint32_t i = 0; i < did_len; i++) {
+			did |= (uint32_t)in[ip++] << (8 * i);
+		}
+		if (did) {
+			err = OTZ_ST_DATA;   // dictionaries are not available to a ZIP entry
+			break;
+		}
+		uint64_t fcs = 0;
+		for (uint32_t i = 0; i < fcs_len; i++) {
+			fcs |= (uint64_t)in[ip++] << (8 * i);
+		}
+		if (fcs_len == 2) {
+			fcs += 256;
+		}
+		const uint32_t frame_start = op;
+		uint32_t rep1 = 1, rep2 = 4, rep3 = 8;
+		if (lane == 0) {
+			S.have_huf = S.have_ll = S.have_ml = S.have_of = 0;
+			S.err = 0;
+		}
+		__syncwarp();
+		// ---- blocks
+		for (;;) {
+			if (n - ip < 3) {
+				err = OTZ_ST_TRUNCATED;
+				break;
+			}
+			const uint32_t bh = in[ip] | (in[ip + 1] << 8) | (in[ip + 2] << 16);
+			ip += 3;
+			const uint32_t last = bh & 1, btype = (bh >> 1) & 3, bsz = bh >> 3;
+			if (btype == 3 || bsz > ZS_BLOCK_MAX) {
+				err = OTZ_ST_DATA;
+				break;
+			}
+			if (btype == 0) {   // raw
+				if (n - ip < bsz) {
+					err = OTZ_ST_TRUNCATED;
+					break;
+				}
+				if (cap - op < bsz) {
+					err = OTZ_ST_OVERFLOW;
+					break;
+				}
+				tile_copy<32>(out + op, in + ip, bsz, lane);
+				ip += bsz;
+				op += bsz;
+			} else if (btype == 1) {   // RLE
+				if (n - ip < 1) {
+					err = OTZ_ST_TRUNCATED;
+					break;
+				}
+				if (cap - op < bsz) {
+					err = OTZ_ST_OVERFLOW;
+					break;
+				}
+				const uint8_t b = in[ip++];
+				for (uint32_t i = lane; i < bsz; i += 32) {
+					out[op + i] = b;
+				}
+				op += bsz;
+			} else {   // compressed
+				if (n - ip < bsz || bsz < 2) {
+					err = n - ip < bsz ? OTZ_ST_TRUNCATED : OTZ_ST_DATA;
+					break;
+				}
+				const uint8_t *bp = in + ip;
+				ip += bsz;
+				// ---- literals section header
+				const uint32_t b0 = bp[0];
+				const uint32_t ltype = b0 & 3, sf = (b0 >> 2) & 3;
+				uint32_t regen, lcomp = 0, lhdr, nstreams = 1;
+				if (ltype < 2) {
+					if ((sf & 1) == 0) {
+						regen = b0 >> 3;
+						lhdr = 1;
+					} else if (sf == 1) {
+						regen = (b0 >> 4) | (bp[1] << 4);
+						lhdr = 2;
+					} else {
+						if (bsz < 3) {
+							err = OTZ_ST_DATA;
+							break;
+						}
+						regen = (b0 >> 4) | (bp[1] << 4) | (bp[2] << 12);
+						lhdr = 3;
+					}
+				} else {
+					if (bsz < 5) {
+						err = OTZ_ST_DATA;
+						break;
+					}
+					const uint64_t v = (uint64_t)ld_le32(bp) | ((uint64_t)bp[4] << 32);
+					if (sf <= 1) {
+						regen = (uint32_t)(v >> 4) & 0x3FF;
+						lcomp = (uint32_t)(v >> 14) & 0x3FF;
+						lhdr = 3;
+						nstreams = sf == 0 ? 1 : 4;
+					} else if (sf == 2) {
+						regen = (uint32_t)(v >> 4) & 0x3FFF;
+						lcomp = (uint32_t)(v >> 18) & 0x3FFF;
+						lhdr = 4;
+						nstreams = 4;
+					} else {
+						regen = (uint32_t)(v >> 4) & 0x3FFFF;
+						lcomp = (uint32_t)(v >> 22) & 0x3FFFF;
+						lhdr = 5;
+						nstreams = 4;
+					}
+				}
+				if (regen > ZS_BLOCK_MAX) {
+					err = OTZ_ST_DATA;
+					break;
+				}
+				uint32_t lsec;   // bytes of the whole literals section
+				const uint8_t *litp = lit;   // where the literals of this block are
+				if (ltype == 0) {
+					lsec = lhdr + regen;
+					if (lsec > bsz) {
+						err = OTZ_ST_DATA;
+						break;
+					}
+					litp = bp + lhdr;   // raw literals are used in place
+				} else if (ltype == 1) {
+					lsec = lhdr + 1;
+					if (lsec > bsz) {
+						err = OTZ_ST_DATA;
+						break;
+					}
+					const uint8_t b = bp[lhdr];
+					for (uint32_t i = lane; i < regen; i += 32) {
+						lit[i] = b;
+					}
+				} else {
+					lsec = lhdr + lcomp;
+					if (lsec > bsz) {
+						err = OTZ_ST_DATA;
+						break;
+					}
+					const uint8_t *hp = bp + lhdr;
+					uint32_t hrem = lcomp;
+					if (lane == 0) {
+						if (ltype == 2) {
+							const uint32_t used = zs_read_huf(S, hp, hrem);
+							if (used == 0) {
+								S.err = OTZ_ST_DATA;
+							}
+							S.huf_used = used;
+						} else {
+							if (!S.have_huf) {
+								S.err = OTZ_ST_DATA;
+							}
+							S.huf_used = 0;
+						}
+					}
+					__syncwarp();
+					if (S.err) {
+						err = S.err;
+						break;
+					}
+					hp += S.huf_used;
+					hrem -= S.huf_used;
+					if (lane == 0) {
+						if (nstreams == 1) {
+							S.lit_ofs[0] = 0;
+							S.lit_ofs[1] = hrem;
+							S.lit_sizes[0] = regen;
+						} else if (hrem < 6) {
+							S.err = OTZ_ST_DATA;
+						} else {
+							const uint32_t s1 = ld_le16(hp), s2 = ld_le16(hp + 2), s3 = ld_le16(hp + 4);
+							if (6ull + s1 + s2 + s3 > hrem) {
+								S.err = OTZ_ST_DATA;
+							} else {
+								S.lit_ofs[0] = 6;
+								S.lit_ofs[1] = 6 + s1;
+								S.lit_ofs[2] = 6 + s1 + s2;
+								S.lit_ofs[3] = 6 + s1 + s2 + s3;
+								S.lit_ofs[4] = hrem;   // end of stream 4
+								const uint32_t q = (regen + 3) / 4;
+								S.lit_sizes[0] = S.lit_sizes[1] = S.lit_sizes[2] = q;
+								S.lit_sizes[3] = regen - 3 * q;
+								if (regen < 3 * q) {
+									S.err = OTZ_ST_DATA;
+								}
+							}
+						}
+					}
+					__syncwarp();
+					if (S.err) {
+						err = S.err;
+						break;
+					}
+					bool ok = true;
+					if ((uint32_t)lane < nstreams) {
+						const uint32_t so = S.lit_ofs[lane], se = nstreams == 1 ? S.lit_ofs[1] : S.lit_ofs[lane + 1];
+						uint32_t dsto = 0;
+						for (int k = 0; k < lane; k++) {
+							dsto += S.lit_sizes[k];
+						}
+						ok = zs_huf_stream(S, hp + so, se - so, lit + dsto, S.lit_sizes[lane]);
+					}
+					if (__any_sync(0xFFFFFFFFu, !ok)) {
+						err = OTZ_ST_DATA;
+						break;
+					}
+				}
+				__syncwarp();
+				// ---- sequences section
+				const uint8_t *sp = bp + lsec;
+				uint32_t srem = bsz - lsec;
+				if (srem < 1) {
+					err = OTZ_ST_DATA;
+					break;
+				}
+				uint32_t nseq = sp[0], shdr = 1;
+				if (nseq >= 128) {
+					if (nseq == 255) {
+						if (srem < 3) {
+							err = OTZ_ST_DATA;
+							break;
+						}
+						nseq = sp[1] + (sp[2] << 8) + 0x7F00;
+						shdr = 3;
+					} else {
+						if (srem < 2) {
+							err = OTZ_ST_DATA;
+							break;
+						}
+						nseq = ((nseq - 128) << 8) + sp[1];
+						shdr = 2;
+					}
+				}
+				uint32_t lit_pos = 0;
+				if (nseq) {
+					if (srem < shdr + 1) {
+						err = OTZ_ST_DATA;
+						break;
+					}
+					const uint32_t modes = sp[shdr];
+					if (modes & 3) {
+						err = OTZ_ST_DATA;
+						break;
+					}
+					if (lane == 0) {
+						uint32_t o = shdr + 1;
+						int r = zs_seq_table(modes >> 6, sp + o, srem - o, S.ll, &S.ll_log, &S.have_ll, c_zs_ll_default, 36, 6, 35, ZS_LL_LOG_MAX);
+						if (r >= 0) {
+							o += r;
+							r = zs_seq_table((modes >> 4) & 3, sp + o, srem - o, S.of, &S.of_log, &S.have_of, c_zs_of_default, 29, 5, 31, ZS_OF_LOG_MAX);
+						}
+						if (r >= 0) {
+							o += r;
+							r = zs_seq_table((modes >> 2) & 3, sp + o, srem - o, S.ml, &S.ml_log, &S.have_ml, c_zs_ml_default, 53, 6, 52, ZS_ML_LOG_MAX);
+						}
+						if (r >= 0) {
+							o += r;
+						}
+						if (r < 0 || o > srem) {
+							S.err = OTZ_ST_DATA;
+						}
+						S.seq_start = o;
+					}
+					__syncwarp();
+					if (S.err) {
+						err = S.err;
+						break;
+					}
+					const uint32_t so = S.seq_start;
+					// lane 0 owns the bitstream and the three states
+					ZsBack b;
+					uint32_t st_ll = 0, st_of = 0, st_ml = 0;
+					if (lane == 0) {
+						if (!b.init(sp + so, srem - so)) {
+							S.err = OTZ_ST_DATA;
+						} else {
+							st_ll = b.read(S.ll_log);
+							st_of = b.read(S.of_log);
+							st_ml = b.read(S.ml_log);
+						}
+					}
+					__syncwarp();
+					if (S.err) {
+						err = S.err;
+						break;
+					}
+					for (uint32_t done = 0; done < nseq && !err;) {
+						const uint32_t nb = min(32u, nseq - done);
+						if (lane == 0) {
+							for (uint32_t k = 0; k < nb; k++) {
+								const uint32_t el = S.ll[st_ll], eo = S.of[st_of], em = S.ml[st_ml];
+								const uint32_t lc = el & 0xFF, oc = eo & 0xFF, mc = em & 0xFF;
+								if (lc > 35 || mc > 52 || oc > 31) {
+									S.err = OTZ_ST_DATA;
+									break;
+								}
+								const uint32_t ofv = (1u << oc) + b.read(oc);
+								const uint32_t mlv = c_zs_ml_base[mc] + b.read(c_zs_ml_bits[mc]);
+								const uint32_t llv = c_zs_ll_base[lc] + b.read(c_zs_ll_bits[lc]);
+								uint32_t offset;
+								if (ofv > 3) {
+									offset = ofv - 3;
+									rep3 = rep2;
+									rep2 = rep1;
+									rep1 = offset;
+								} else {
+									const uint32_t idx = ofv + (llv == 0 ? 1 : 0);   // 1..4
+									if (idx == 1) {
+										offset = rep1;
+									} else {
+										offset = idx == 2 ? rep2 : idx == 3 ? rep3 : rep1 - 1;
+										if (offset == 0) {
+											S.err = OTZ_ST_DATA;
+											break;
+										}
+										if (idx != 2) {
+											rep3 = rep2;
+										}
+										rep2 = rep1;
+										rep1 = offset;
+									}
+								}
+								S.seq_ll[k] = llv;
+								S.seq_ml[k] = mlv;
+								S.seq_of[k] = offset;
+								if (done + k + 1 < nseq) {   // state updates: LL, ML, OF (RFC 8878 4.1.1 decoding order)
+									st_ll = (el >> 16) + b.read((el >> 8) & 0xFF);
+									st_ml = (em >> 16) + b.read((em >> 8) & 0xFF);
+									st_of = (eo >> 16) + b.read((eo >> 8) & 0xFF);
+								}
+								if (b.pos < 0) {
+									S.err = OTZ_ST_DATA;
+									break;
+								}
+							}
+							if (done + nb == nseq && b.pos != 0 && !S.err) {
+								S.err = OTZ_ST_DATA;   // the bitstream must be consumed exactly
+							}
+						}
+						__syncwarp();
+						if (S.err) {
+							err = S.err;
+							break;
+						}
+						for (uint32_t k = 0; k < nb; k++) {
+							const uint32_t llv = S.seq_ll[k], mlv = S.seq_ml[k], offset = S.seq_of[k];
+							if (llv > regen - lit_pos || (uint64_t)llv + mlv > (uint64_t)(cap - op)) {
+								err = llv > regen - lit_pos ? OTZ_ST_DATA : OTZ_ST_OVERFLOW;
+								break;
+							}
+							for (uint32_t i = lane; i < llv; i += 32) {
+								out[op + i] = litp[lit_pos + i];
+							}
+							op += llv;
+							lit_pos += llv;
+							if (offset > op - frame_start) {
+								err = OTZ_ST_DATA;
+								break;
+							}
+							__syncwarp();
+							const uint8_t *src = out + op - offset;
+							if (offset >= mlv) {
+								for (uint32_t i = lane; i < mlv; i += 32) {
+									out[op + i] = src[i];
+								}
+							} else {
+								uint32_t r = offset > (uint32_t)lane ? (uint32_t)lane : (uint32_t)lane % offset;
+								const uint32_t step = offset > 32u ? 32u : 32u % offset;
+								for (uint32_t i = lane; i < mlv; i += 32) {
+									out[op + i] = src[r];
+									r += step;
+									r = r >= offset ? r - offset : r;
+								}
+							}
+							op += mlv;
+							__syncwarp();
+						}
+						done += nb;
+					}
+					if (err) {
+						break;
+					}
+				}
+				// ---- literals after the last sequence
+				const uint32_t tail = regen - lit_pos;
+				if (cap - op < tail) {
+					err = OTZ_ST_OVERFLOW;
+					break;
+				}
+				for (uint32_t i = lane; i < tail; i += 32) {
+					out[op + i] = litp[lit_pos + i];
+				}
+				op += tail;
+				__syncwarp();
+			}
+			if (last) {
+				break;
+			}
+		}
+		if (err) {
+			break;
+		}
+		if (has_cksum) {
+			if (n - ip < 4) {
+				err = OTZ_ST_TRUNCATED;
+				break;
+			}
+			ip += 4;   // XXH64 low word: not verified here, the ZIP CRC-32 covers the entry
+		}
+		if (fcs_len && fcs != (uint64_t)(op - frame_start)) {
+			err = OTZ_ST_DATA;
+			break;
+		}
+		n_frames++;
+	}
+	*produced = op;
+	if (err) {
+		return err;
+	}
+	if (n_frames == 0) {
+		return OTZ_ST_DATA;
+	}
+	return op == cap ? OTZ_ST_OK : OTZ_ST_SIZE;
+}
+
+// grid: persistent; one warp per method-93 entry that k_zstdref could not read as a reference container.
+__global__ void __launch_bounds__(128) k_zstd(const uint8_t *__restrict__ archive, uint8_t *__restrict__ out, const otz_entry *__restrict__ ents,
+	const OtzEntryState *__restrict__ est, int32_t *__restrict__ status, const uint32_t *__restrict__ list, uint32_t n_list,
+	uint8_t *__restrict__ lit_scratch, uint32_t *__restrict__ work_counter) {
+	extern __shared__ __align__(16) uint8_t smem_raw[];
+	const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+	ZstdSmem &S = reinterpret_cast<ZstdSmem *>(smem_raw)[warp];
+	uint8_t *lit = lit_scratch + (uint64_t)(blockIdx.x * (blockDim.x >> 5) + warp) * (ZS_BLOCK_MAX + 64);
+	for (;;) {
+		uint32_t k = 0;
+		if (lane == 0) {
+			k = atomicAdd(work_counter, 1u);
+		}
+		k = __shfl_sync(0xFFFFFFFFu, k, 0);
+		if (k >= n_list) {
+			break;
+		}
+		const uint32_t ei = list[k];
+		if (status[ei] != OTZ_ST_PENDING) {
+			continue;   // resolved as a reference container (or failed earlier)
+		}
+		const otz_entry e = ents[ei];
+		uint32_t produced = 0;
+		int32_t st = zstd_decode_entry(S, archive + est[ei].data_ofs, e.comp_size, out + e.out_ofs, e.uncomp_size, lit, &produced);
+		if (st == OTZ_ST_OK) {
+			st |= OTZ_STF_REF_EOB;   // a valid stream that the reference rejects
+		}
+		if (lane == 0) {
+			status[ei] = st;
+		}
+		__syncwarp();
+	}
+}

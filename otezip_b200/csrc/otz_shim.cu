@@ -12,6 +12,7 @@
 #include "k_inflate.cuh"
 #include "k_deflate.cuh"
 #include "k_resolve.cuh"
+#include "k_zstd.cuh"
 #include "otz_common.cuh"
 
 static thread_local char g_err[512] = "";
@@ -60,6 +61,10 @@ struct otz_plan {
 	uint32_t *d_inflate_list, n_inflate;   // DEFLATE entries, longest first; [0, n_inflate_big) are the large ones
 	uint32_t n_inflate_big;
 	uint32_t *d_zstd_list, n_zstd;
+	OtzCrcChunk *d_zchunks;    // CRC chunks of the method-93 entries (used for real Zstandard frames only)
+	uint32_t n_zchunks;
+	uint8_t *d_zstd_lit;       // literal scratch of k_zstd, one slot per resident warp
+	uint32_t zstd_grid;
 	uint32_t *d_counter;
 	uint64_t out_bytes_needed;
 };
@@ -339,6 +344,8 @@ extern "C" void otz_plan_destroy(otz_ctx *c, otz_plan *p) {
 	cudaFree(p->d_chunks);
 	cudaFree(p->d_inflate_list);
 	cudaFree(p->d_zstd_list);
+	cudaFree(p->d_zchunks);
+	cudaFree(p->d_zstd_lit);
 	cudaFree(p->d_counter);
 	delete p;
 }
@@ -387,6 +394,14 @@ extern "C" int otz_plan_create(otz_ctx *c, const otz_entry *ents, uint32_t n, co
 			need = std::max<uint64_t>(need, ents[i].out_ofs + ents[i].uncomp_size);
 		}
 	}
+	std::vector<OtzCrcChunk> zchunks;
+	for (uint32_t i : zst) {
+		const uint32_t nc = (uint32_t)(((uint64_t)ents[i].uncomp_size + OTZ_CRC_CHUNK - 1) / OTZ_CRC_CHUNK);
+		for (uint32_t k = 0; k < nc; k++) {
+			zchunks.push_back(OtzCrcChunk{ i, k });
+		}
+	}
+	p->n_zchunks = (uint32_t)zchunks.size();
 	// longest streams first: the tail of the batch is then made of short ones
 	// large entries first (they get the 16 KiB ring kernel), inside each class longest streams first
 	const uint32_t big_bytes = 256u * 1024u;
@@ -405,7 +420,8 @@ extern "C" int otz_plan_create(otz_ctx *c, const otz_entry *ents, uint32_t n, co
 	int rc;
 	std::vector<otz_entry> ev(ents, ents + n);
 	if ((rc = upload(&p->d_ents, ev, c->stream)) || (rc = upload(&p->d_chunks, chunks, c->stream)) ||
-		(rc = upload(&p->d_inflate_list, infl, c->stream)) || (rc = upload(&p->d_zstd_list, zst, c->stream))) {
+		(rc = upload(&p->d_inflate_list, infl, c->stream)) || (rc = upload(&p->d_zstd_list, zst, c->stream)) ||
+		(rc = upload(&p->d_zchunks, zchunks, c->stream))) {
 		otz_plan_destroy(c, p);
 		return rc;
 	}
@@ -416,6 +432,13 @@ extern "C" int otz_plan_create(otz_ctx *c, const otz_entry *ents, uint32_t n, co
 		cudaMalloc(&p->d_counter, 256) != cudaSuccess) {
 		otz_plan_destroy(c, p);
 		return fail_cuda(cudaGetLastError(), "cudaMalloc(plan)");
+	}
+	if (p->n_zstd) {
+		p->zstd_grid = std::min<uint32_t>((uint32_t)c->sm_count * 2, (p->n_zstd + 3) / 4);
+		if (cudaMalloc(&p->d_zstd_lit, (size_t)p->zstd_grid * 4 * (ZS_BLOCK_MAX + 64)) != cudaSuccess) {
+			otz_plan_destroy(c, p);
+			return fail_cuda(cudaGetLastError(), "cudaMalloc(zstd literal scratch)");
+		}
 	}
 	CK(cudaStreamSynchronize(c->stream));  // the host vectors die here
 	*out = p;
@@ -536,6 +559,16 @@ extern "C" int otz_extract_run(otz_ctx *c, otz_plan *p, const uint8_t *d_archive
 		k_zstdref<<<std::min((uint32_t)c->sm_count * 2, (p->n_zstd + 7) / 8), 256, 0, s>>>(d_archive, d_out, p->d_ents, p->d_est, p->d_status,
 			p->d_zstd_list, p->n_zstd, p->d_acc, c->d_tabs);
 		c->launches++;
+		// entries that are not a reference container but carry the Zstandard magic: RFC 8878 frames
+		const size_t zsmem = 4 * sizeof(ZstdSmem);
+		static bool zattr = false;
+		if (!zattr) {
+			CK(cudaFuncSetAttribute(k_zstd, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)zsmem));
+			zattr = true;
+		}
+		k_zstd<<<p->zstd_grid, 128, zsmem, s>>>(d_archive, d_out, p->d_ents, p->d_est, p->d_status, p->d_zstd_list, p->n_zstd, p->d_zstd_lit,
+			p->d_counter + 32);
+		c->launches++;
 	}
 	if (p->n_inflate) {
 		int rc = dispatch_inflate(c, p, d_archive, d_out);
@@ -553,7 +586,12 @@ extern "C" int otz_extract_run(otz_ctx *c, otz_plan *p, const uint8_t *d_archive
 		const uint32_t nc = p->n_chunks - crc_first;
 		const uint32_t grid = std::min((uint32_t)c->sm_count * crc_ctas_per_sm(), (nc + 7) / 8);
 		k_crc_chunks<<<grid, 256, 0, s>>>(d_archive, d_out, p->d_ents, p->d_est, p->d_status, p->d_chunks + crc_first, nc, p->d_acc, c->d_tabs,
-			p->opts.verify_only);
+			p->opts.verify_only, 0);
+		c->launches++;
+	}
+	if (p->n_zchunks) {
+		const uint32_t grid = std::min((uint32_t)c->sm_count * crc_ctas_per_sm(), (p->n_zchunks + 7) / 8);
+		k_crc_chunks<<<grid, 256, 0, s>>>(d_archive, d_out, p->d_ents, p->d_est, p->d_status, p->d_zchunks, p->n_zchunks, p->d_acc, c->d_tabs, 0, 1);
 		c->launches++;
 	}
 	if (c->profile) {
@@ -799,7 +837,7 @@ extern "C" int otz_deflate_run(otz_ctx *c, otz_deflate_job *j, const uint8_t *d_
 	if (j->n_crc_chunks) {
 		const uint32_t grid = std::min((uint32_t)c->sm_count * crc_ctas_per_sm(), (j->n_crc_chunks + 7) / 8);
 		k_crc_chunks<<<grid, 256, 0, s>>>(nullptr, d_in, j->d_crc_ents, j->d_est, j->d_status, j->d_crc_chunks, j->n_crc_chunks, j->d_acc,
-			c->d_tabs, 0);
+			c->d_tabs, 0, 0);
 		c->launches++;
 	}
 	k_crc_finalize<<<(n + 255) / 256, 256, 0, s>>>(j->d_crc_ents, n, j->d_acc, j->d_crc, j->d_status, c->d_tabs);

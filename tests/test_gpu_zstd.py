@@ -1,0 +1,86 @@
+"""Real Zstandard (RFC 8878) frames in method-93 entries: k_zstd.cuh against libzstd 1.5.5.
+Parity for this kernel is NOT pinned by the reference (which rejects such frames): the frames are
+made by libzstd and the decoded bytes must equal the source; the status carries the "reference rejects" flag so
+that the default reference-compatible policy still agrees with the reference."""
+import zlib
+
+import numpy as np
+import pytest
+
+from otezip_b200 import native, synth
+from otezip_b200.native import parse_central, default_opts
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def zs():
+    try:
+        from otezip_b200.zstdlib import Zstd
+        return Zstd()
+    except OSError:
+        pytest.skip("libzstd.so.1 not present")
+
+
+def sources():
+    out = [b"", b"a", b"hello zstd\n", b"A" * 100000, bytes(range(256)) * 40, synth.random_bytes(5000, 1), synth.random_bytes(300000, 2)]
+    out += [synth.jsonlog_text(n, 50 + i) for i, n in enumerate([100, 4096, 70000, 131072, 131073, 262144, 700000])]
+    out.append(synth.jsonlog_text(150000, 9) + synth.random_bytes(140000, 3) + b"\0" * 200000 + synth.jsonlog_text(90000, 10))
+    return out
+
+
+def test_zstd_frames_decode_bit_exact(ctx, zs, reflib):
+    ms, want = [], []
+    for i, d in enumerate(sources()):
+        for lvl in (1, 3, 9, 19):
+            f = zs.compress(d, lvl)
+            assert zs.decompress(f, len(d)) == d
+            ms.append(synth.Member("z%d_%d" % (i, lvl), 93, f, len(d), zlib.crc32(d) & 0xFFFFFFFF, raw=d))
+            want.append(d)
+    # reference-container entries mixed in: they keep going through k_zstdref
+    for i in range(4):
+        d = synth.jsonlog_text(100000 + i, 200 + i)
+        ms.append(synth.member("c%d" % i, d, 93))
+        want.append(d)
+    img = synth.build_zip(ms)
+    tab = parse_central(img)
+    out, crc, st = ctx.extract_host(img, tab, default_opts())
+    L = native.Lib.get().L
+    for i, (m, d) in enumerate(zip(ms, want)):
+        s = int(st[i])
+        assert (s & 0xFF) == 0, (m.name, hex(s))
+        assert not (s & native.STF_CRC_MISMATCH), m.name
+        real = m.name.startswith("z")
+        assert bool(s & native.STF_REF_EOB) == real, (m.name, hex(s))      # real frames: "the reference rejects this"
+        assert bool(L.otz_status_accepts(s, 1, 0)) and bool(L.otz_status_accepts(s, 1, 1)) == (not real)
+        o = int(tab["out_ofs"][i])
+        assert bytes(out[o:o + len(d)]) == d, m.name
+        assert int(crc[i]) == m.crc32
+    # and the compiled reference indeed rejects every real frame while reading its own container
+    err, got = reflib.extract_bytes(img, verify_crc=1)
+    assert err == 0
+    for m, g, d in zip(ms, got, want):
+        assert (g is None) == m.name.startswith("z") and (g is None or g == d)
+
+
+def test_corrupt_zstd_frames_are_rejected(ctx, zs):
+    d = synth.jsonlog_text(200000, 77)
+    f = zs.compress(d, 3)
+    ms = []
+    import random
+    rnd = random.Random(4)
+    for k in range(64):
+        b = bytearray(f)
+        pos = rnd.randrange(4, len(b))
+        b[pos] ^= 1 << rnd.randrange(8)
+        ms.append(synth.Member("x%d" % k, 93, bytes(b), len(d), zlib.crc32(d) & 0xFFFFFFFF))
+    ms.append(synth.Member("trunc", 93, f[:len(f) // 2], len(d), zlib.crc32(d) & 0xFFFFFFFF))
+    img = synth.build_zip(ms)
+    tab = parse_central(img)
+    out, crc, st = ctx.extract_host(img, tab, default_opts())      # must terminate and never report a clean success
+    for i in range(len(ms)):
+        s = int(st[i])
+        ok = (s & 0xFF) == 0 and not (s & native.STF_CRC_MISMATCH)
+        if ok:   # a flip in an unused header bit may leave the data intact
+            o = int(tab["out_ofs"][i])
+            assert bytes(out[o:o + len(d)]) == d
