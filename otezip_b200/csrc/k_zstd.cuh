@@ -63,41 +63,51 @@ struct ZsFwd {
 	}
 };
 
-// ---- backward bit reader (RFC 8878 4.1): the stream is a little-endian integer read from its top
+// ---- backward bit reader (RFC 8878 4.1): the stream is a little-endian integer read from its top.
+// A 64-bit register window [lo, lo+64) of the stream is cached; it is reloaded (8 byte loads) only when a
+// read reaches below it, i.e. about once per 30-60 bits consumed.
 struct ZsBack {
 	const uint8_t *p;
 	int32_t pos;       // bits still unread (can go negative: over-read)
+	int32_t lo;        // bit index of cache bit 0 (multiple of 8)
+	uint64_t cache;
+	__device__ __forceinline__ void fill() {
+		lo = pos > 64 ? ((pos - 64 + 7) & ~7) : 0;
+		const uint8_t *q = p + (lo >> 3);
+		uint64_t v = 0;
+#pragma unroll
+		for (int i = 0; i < 8; i++) {
+			v |= (uint64_t)q[i] << (8 * i);   // may touch up to 7 bytes past the stream: inside the padded image, ignored bits
+		}
+		cache = v;
+	}
 	__device__ __forceinline__ bool init(const uint8_t *base, uint32_t n) {
 		p = base;
+		lo = 0;
+		cache = 0;
 		if (n == 0 || base[n - 1] == 0) {
 			pos = 0;
 			return false;
 		}
 		pos = (int32_t)(8 * (n - 1) + (31 - __clz((uint32_t)base[n - 1])));   // the highest set bit is the end mark
+		fill();
 		return true;
 	}
 	// nb bits below the current position, zero filled below bit 0 (nb <= 32)
-	__device__ __forceinline__ uint32_t peek(uint32_t nb) const {
-		if (nb == 0) {
+	__device__ __forceinline__ uint32_t peek(uint32_t nb) {
+		if (nb == 0 || pos <= 0) {
 			return 0;
 		}
-		int32_t lo = pos - (int32_t)nb;
-		uint32_t sh = 0;
-		if (lo < 0) {
-			sh = (uint32_t)(-lo);
-			if (sh >= nb) {
-				return 0;
-			}
-			lo = 0;
+		const int32_t l = pos - (int32_t)nb;
+		if (l < lo && lo > 0) {
+			fill();
 		}
-		const uint32_t by = (uint32_t)lo >> 3;
-		uint64_t v = 0;
-		const uint32_t need = ((uint32_t)(lo & 7) + (nb - sh) + 7) >> 3;
-		for (uint32_t i = 0; i < need; i++) {
-			v |= (uint64_t)p[by + i] << (8 * i);
+		const uint64_t mask = (1ull << nb) - 1ull;
+		if (l >= 0) {
+			return (uint32_t)((cache >> (l - lo)) & mask);
 		}
-		const uint32_t got = (uint32_t)((v >> (lo & 7)) & ((1ull << (nb - sh)) - 1ull));
-		return got << sh;
+		// fewer than nb bits are left (then lo == 0): they become the high bits, zeros below
+		return (uint32_t)(((cache & ((1ull << pos) - 1ull)) << (-l)) & mask);
 	}
 	__device__ __forceinline__ uint32_t read(uint32_t nb) {
 		const uint32_t v = peek(nb);

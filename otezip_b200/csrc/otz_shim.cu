@@ -434,7 +434,7 @@ extern "C" int otz_plan_create(otz_ctx *c, const otz_entry *ents, uint32_t n, co
 		return fail_cuda(cudaGetLastError(), "cudaMalloc(plan)");
 	}
 	if (p->n_zstd) {
-		p->zstd_grid = std::min<uint32_t>((uint32_t)c->sm_count * 2, (p->n_zstd + 3) / 4);
+		p->zstd_grid = std::min<uint32_t>((uint32_t)c->sm_count * 5, (p->n_zstd + 3) / 4);   // 5 CTAs x 4 warps per SM (shared memory)
 		if (cudaMalloc(&p->d_zstd_lit, (size_t)p->zstd_grid * 4 * (ZS_BLOCK_MAX + 64)) != cudaSuccess) {
 			otz_plan_destroy(c, p);
 			return fail_cuda(cudaGetLastError(), "cudaMalloc(zstd literal scratch)");

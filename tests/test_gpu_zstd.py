@@ -84,3 +84,20 @@ def test_corrupt_zstd_frames_are_rejected(ctx, zs):
         if ok:   # a flip in an unused header bit may leave the data intact
             o = int(tab["out_ofs"][i])
             assert bytes(out[o:o + len(d)]) == d
+
+
+def test_zstd_through_libzip_api_policy(zs, tmp_path):
+    """zip_fopen_index: the reference rejects real Zstandard frames, so the default (otezip_ref_compat = 1) returns
+    NULL for them exactly like the reference; otezip_ref_compat = 0 hands out the decoded bytes."""
+    from otezip_b200.zipapi import ZipApi
+    api = ZipApi()
+    d = synth.jsonlog_text(300000, 5)
+    ms = [synth.Member("real.zst", 93, zs.compress(d, 3), len(d), zlib.crc32(d) & 0xFFFFFFFF), synth.member("container", d, 93)]
+    p = tmp_path / "z.zip"
+    p.write_bytes(synth.build_zip(ms))
+    assert api.read_all(str(p))[2] == [None, d]
+    api.ref_compat.value = 0
+    try:
+        assert api.read_all(str(p))[2] == [d, d]
+    finally:
+        api.ref_compat.value = 1
