@@ -547,6 +547,7 @@ def main():
         step()
     ctx.sync()
     crc, st = ctx.results(plan, n)
+    inflate_fallbacks = int(ctx.L.otz_inflate_fallbacks(ctx.h))
     real = (tab["flags"] & 2) == 0          # chunk rows carry no CRC of their own
     ok_mask = 0x200 if args.workload == "c4z" else 0      # real Zstandard frames carry the "reference rejects" flag
     bad = int(np.count_nonzero((st & ~ok_mask) != 0))
@@ -626,7 +627,8 @@ def main():
             "config": {"workload": WORKLOADS[args.workload], "detail": wl["desc"], "entries_per_gpu": int(wl.get("n_entries", n)), "table_rows_per_gpu": n,
                        "uncomp_bytes_per_gpu": wl["uncomp_bytes"], "algorithmic_bytes_per_gpu": wl["algo_bytes"],
                        "cache": "inputs larger than L2 (no flush needed)" if wl["algo_bytes"] > 256e6 else
-                                "inputs smaller than L2: steady-state L2-resident", "parallelism": "entries sharded by index, no collective"},
+                                "inputs smaller than L2: steady-state L2-resident", "parallelism": "entries sharded by index, no collective",
+                       "inflate_fallbacks": inflate_fallbacks},
             "roofline": {"bound": "hbm", "kernel": {"crc": "k_crc_chunks", "decode": "k_inflate/k_zstdref/k_store_copy"}[dom],
                          "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": traffic,
                          "peak_source": peak_src, "kernel_ms": k_ms, "phase_ms": shares},

@@ -183,6 +183,12 @@ int otz_extract_host_ex(otz_ctx *ctx, const uint8_t *archive, uint64_t archive_l
 	uint32_t *produced);
 int otz_extract_produced(otz_ctx *ctx, otz_plan *plan, uint32_t *produced);
 
+/* DEFLATE streams of the run last collected with otz_extract_results that the lane-per-stream decoder
+ * (k_inflate_tok/k_inflate_lz) declined and the warp-per-stream decoder (k_inflate) decoded instead:
+ * error and short streams, stored blocks with payload, code sets beyond the fixed table budget.  Both decoders
+ * implement dec:547-831 with identical results; this is a performance counter. */
+uint32_t otz_inflate_fallbacks(otz_ctx *ctx);
+
 /* Policy helper shared by the host library and the tests: does a status word
  * mean "zip_fopen_index returns the buffer" under the given globals?
  * ref_compat != 0 reproduces the reference's end-of-block rule (F1). */

@@ -725,11 +725,16 @@ __device__ __forceinline__ int32_t inflate_stream(const Tile &tile, InflateSmemV
 }
 
 // grid: persistent; each tile pulls the next entry of `list` (largest first) from a global counter.
+// n_list_dev != NULL: the list length lives in device memory (written by an earlier kernel of the same stream).
 template <int G, int W>
 __global__ void __launch_bounds__(256) k_inflate(const uint8_t *__restrict__ archive, uint8_t *__restrict__ out,
 	const otz_entry *__restrict__ ents, const OtzEntryState *__restrict__ est, int32_t *__restrict__ status,
-	const uint32_t *__restrict__ list, uint32_t n_list, uint32_t *__restrict__ work_counter, uint32_t *__restrict__ produced_out) {
+	const uint32_t *__restrict__ list, uint32_t n_list, uint32_t *__restrict__ work_counter, uint32_t *__restrict__ produced_out,
+	const uint32_t *__restrict__ n_list_dev) {
 	extern __shared__ __align__(16) uint8_t smem_raw[];
+	if (n_list_dev) {
+		n_list = *n_list_dev;   // list filled on the device (fallback list of k_inflate_tok)
+	}
 	auto tile = cg::tiled_partition<G>(cg::this_thread_block());
 	const int lane = tile.thread_rank();
 	InflateSmemV2<G, W> &S = reinterpret_cast<InflateSmemV2<G, W> *>(smem_raw)[threadIdx.x / G];

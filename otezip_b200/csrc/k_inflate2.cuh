@@ -1,0 +1,982 @@
+// k_inflate2.cuh — two-phase batched raw-DEFLATE (RFC 1951) decoder: one LANE per stream for the entropy
+// stage, one WARP per stream for the LZ77 stage.
+//
+// Replaces inflateInit2/inflate/inflateEnd as driven by otezip_extract_entry
+// (/root/reference/src/lib/otezip.c:503-529; decoder src/lib/deflate-dec.inc.c:547-831, "dec" below), like
+// k_inflate.cuh, but splits the decoder the way the work parallelises:
+//
+//   phase A  k_inflate_tok   Huffman decoding is a serial bit chain per stream, so a warp that decodes one
+//            stream spends 32 lanes on one symbol.  Here every lane of a warp owns a different stream: its
+//            own bit reader (32-bit words of the stream, two words of look-ahead in registers), its own
+//            16-bit two-level tables in shared memory (9-bit / 7-bit roots, 1796 bytes per lane, bank-skewed)
+//            and it emits, per stream, the literal bytes (dense, packed four per store) and one 32-bit
+//            sequence record per match {literal run : 9, length-3 : 8, distance-1 : 15}.  All lanes step in
+//            lock-step through literal / length+distance / end-of-block, so one warp instruction advances up
+//            to 32 streams.  Dynamic block headers (dec:122-266) are parsed by the lanes that need one, all at
+//            the same time; the decoding tables are then built by the whole warp, one lane's block at a time
+//            (code lengths in registers, canonical order by match_any ranks, every table slot computed
+//            independently from the 15-bit left-aligned code boundaries).
+//   phase B  k_inflate_lz    one warp per stream executes the sequences: 32 records per coalesced load, warp
+//            prefix sums give every record its output position, literal runs are placed in parallel, matches
+//            whose source has already left the shared-memory ring are fetched from HBM/L2 four at a time
+//            (independent of the batch being produced), the rest run ring -> ring in order; completed
+//            512-byte segments leave as coalesced 16-byte stores.
+//
+// Phase A only commits streams that are plainly valid: final block reached, exactly uncomp_size bytes, no
+// stored block with payload, tables within the fixed budget.  Anything else (errors, short streams, stored
+// payloads, exotic code sets) is appended to a fallback list and decoded from scratch by k_inflate, whose
+// status words define the behaviour in those cases; the two kernels agree bit for bit on every stream both
+// can decode, so the split is invisible to the caller.  The reference's end-of-input rule (dec:811-816,
+// SURVEY.md F1) is evaluated in phase A and reported as OTZ_STF_REF_EOB exactly as k_inflate reports it.
+#pragma once
+#include "otz_common.cuh"
+#include "k_inflate.cuh"
+
+#define I2_LIT_ROOT 9
+#define I2_DST_ROOT 7
+#define I2_LIT_CAP 704   // 512 root slots + 192 second-level slots
+#define I2_DST_CAP 192   // 128 root slots + 64 second-level slots
+#define I2_LANES 28      // table slots per warp (4 warps x 28 slots fit the 227 KB of one SM)
+#define I2_SLOT_BYTES 1796   // (704 + 192) * 2 + 4: an odd number of 32-bit words, so equal indices of different lanes hit different banks
+#define I2_LENS_OFS 0        // header parse scratch inside the lane's slot (dead once the tables are built)
+#define I2_PRE_OFS 320
+
+// 16-bit entries.  tb = bits the symbol consumes at this table level INCLUDING its extra bits, so the bit
+// position advances by one field of the entry; what the extra bits mean is worked out off the critical path.
+//   literal/length table: [3:0] tb, [5:4] kind, then  LIT: [13:6] byte   LEN: [8:6] extra bits, [13:9] symbol-257
+//                         LINK: tb = 0, [8:6] index bits of the second-level table (0 = invalid code),
+//                               [15:9] (its offset - 512) / 2   (second-level tables are even-sized and packed)
+//   distance table:       [4:0] tb, [8:5] extra bits, [13:9] symbol, [15:14] kind (0 = symbol, 3 = LINK/invalid)
+//                         LINK: tb = 0, [8:5] index bits (0 = invalid code), [13:9] (offset - 128) / 2
+// A LINK entry has tb = 0: the straight-line decoder may add every entry's tb to the bit position blindly.
+#define I2_K_LIT 0u
+#define I2_K_LEN 1u
+#define I2_K_EOB 2u
+#define I2_K_LINK 3u
+#define I2_LIT_ENTRY(tb, kind, rest) ((uint16_t)((tb) | ((kind) << 4) | ((rest) << 6)))
+#define I2_LIT_LINK(bits, off) I2_LIT_ENTRY(0u, I2_K_LINK, (bits) | ((((off) - (1u << I2_LIT_ROOT)) >> 1) << 3))
+#define I2_LIT_INVALID I2_LIT_ENTRY(0u, I2_K_LINK, 0u)
+#define I2_LIT_LINK_BITS(e) (((e) >> 6) & 7u)
+#define I2_LIT_LINK_OFS(e) ((1u << I2_LIT_ROOT) + (((e) >> 9) << 1))
+#define I2_DST_ENTRY(tb, xb, sym) ((uint16_t)((tb) | ((xb) << 5) | ((sym) << 9)))
+#define I2_DST_LINK(bits, off) ((uint16_t)(((bits) << 5) | ((((off) - (1u << I2_DST_ROOT)) >> 1) << 9) | (3u << 14)))
+#define I2_DST_INVALID I2_DST_LINK(0u, (1u << I2_DST_ROOT))
+#define I2_DST_LINK_BITS(d) (((d) >> 5) & 15u)
+#define I2_DST_LINK_OFS(d) ((1u << I2_DST_ROOT) + ((((d) >> 9) & 31u) << 1))
+
+// sequence record: [8:0] literal run, [16:9] match length - 3, [31:17] distance - 1
+#define I2_SEQ_ESC 511u   // literal run of exactly 511 bytes and no match
+
+struct I2TokRes {
+	uint32_t nseq;    // sequence records written (descending from the end of the stream's scratch)
+	uint32_t nlit;    // literal bytes written (ascending from the start)
+	int32_t status;   // status word to report when phase B has produced the bytes
+	uint32_t ok;      // 1: phase B executes this stream; 0: it went to the fallback list
+};
+
+struct I2WarpScratch {
+	uint32_t ring[4 * 32 * 4];   // input staging: 4 vectors of 16 bytes per lane, [vector slot][lane][word]
+	uint32_t cnt[16];
+	uint32_t first15[16];   // first canonical code of each length, left-aligned to 15 bits
+	uint32_t limit15[16];   // one past the last code of each length, left-aligned to 15 bits
+	uint32_t offs[16];      // index in sorted[] of the first symbol of each length
+	uint32_t run[16];
+	uint16_t sorted[320];
+	uint16_t len_base[32];    // dec:720-725 by symbol - 257
+	uint16_t dist_base[32];   // dec:766-771 by symbol
+};
+
+#define I2_SMEM_BYTES (I2_LANES * I2_SLOT_BYTES + (int)sizeof(I2WarpScratch))
+
+// worst-case scratch of a stream of n output bytes: literals + 4 bytes per match (>= 3 bytes each) + escapes
+__host__ __device__ __forceinline__ uint64_t i2_scratch_bytes(uint64_t n) {
+	return ((n + 4 * (n / 3 + n / 511 + 4) + 16 + 15) / 16) * 16;
+}
+
+// length / distance bases (dec:720-725, dec:766-771) from the symbol
+__device__ __forceinline__ uint32_t i2_len_base(uint32_t v, uint32_t xb) {
+	return v < 8u ? 3u + v : v == 28u ? 258u : 3u + ((4u + (v & 3u)) << xb);
+}
+__device__ __forceinline__ uint32_t i2_dist_base(uint32_t ds, uint32_t xb) { return ds < 4u ? 1u + ds : 1u + ((2u + (ds & 1u)) << xb); }
+
+// ------------------------------------------------------------------------------------------------
+// per-lane bit reader: {lo,hi} is a 64-bit window of the stream, pos < 32 after norm(); nx is the word after hi.
+// The stream is staged through shared memory as 16-byte vectors, four per lane, fetched with cp.async two
+// vectors (>= 5 decoding steps) ahead of their first use: in lock-step execution no lane's cache miss stalls
+// the other 31, and a refill is branch-free (two selects and one shared-memory load).
+struct I2Reader {
+	const uint4 *b16;        // 16-byte aligned base of the stream
+	uint32_t nvec;           // vectors that overlap the stream
+	uint32_t wi;             // word index (from b16) of nx
+	uint32_t lo, hi, nx, pos;
+	uint32_t wi_end;         // words_left() = wi_end - wi
+	uint32_t pad_bits;
+	uint32_t *col;           // this lane's column of the staging ring
+
+	// 32-bit words of the stream not yet moved into {lo,hi} (as BitReader::words_left in k_inflate.cuh)
+	__device__ __forceinline__ int32_t words_left() const { return (int32_t)(wi_end - wi); }
+
+	__device__ __forceinline__ uint32_t word(uint32_t i) const { return col[((i & 12u) << 5) | (i & 3u)]; }
+	__device__ __forceinline__ void fetch(uint32_t c) const {
+		const uint32_t cc = c < nvec ? c : nvec;   // never more than one vector past the stream
+		const uint32_t sa = (uint32_t)__cvta_generic_to_shared(col + ((c & 3u) << 7));
+		asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(sa), "l"(b16 + cc) : "memory");
+		asm volatile("cp.async.commit_group;" ::: "memory");
+	}
+	__device__ __forceinline__ void init(const uint8_t *p, uint64_t nbytes) {
+		const uint64_t a = reinterpret_cast<uint64_t>(p);
+		const uint32_t skipb = (uint32_t)(a & 3), i0 = (uint32_t)(a & 15) >> 2;
+		b16 = reinterpret_cast<const uint4 *>(a & ~15ull);
+		const uint32_t nw = (uint32_t)((skipb + nbytes + 3) >> 2);
+		nvec = (i0 + nw + 3) >> 2;
+		pad_bits = (uint32_t)(((uint64_t)nw << 5) - ((skipb + nbytes) << 3));
+		fetch(0);
+		fetch(1);
+		fetch(2);
+		fetch(3);
+		asm volatile("cp.async.wait_group 0;" ::: "memory");
+		lo = word(i0);
+		hi = word(i0 + 1);
+		wi = i0 + 2;
+		nx = word(wi);
+		wi_end = wi + nw - 2u;
+		pos = 8 * skipb;
+	}
+	// pos < 64 on entry
+	__device__ __forceinline__ void norm() {
+		const bool p = pos >= 32u;
+		lo = p ? hi : lo;
+		hi = p ? nx : hi;
+		pos &= 31u;
+		wi += p;
+		if (p && (wi & 3u) == 0u) {
+			fetch((wi >> 2) + 2u);   // entering vector wi>>2: it and the next one were requested earlier
+			asm volatile("cp.async.wait_group 2;" ::: "memory");
+		}
+		nx = word(wi);
+	}
+	__device__ __forceinline__ uint32_t peek() const { return __funnelshift_r(lo, hi, pos); }
+	__device__ __forceinline__ int64_t remaining_bits() const { return ((int64_t)words_left() << 5) + 64 - (int64_t)pos - (int64_t)pad_bits; }
+};
+
+// ------------------------------------------------------------------------------------------------
+// Warp-cooperative build of one two-level table from code lengths held in registers.
+// lens[j] = code length of combined symbol 32*j + lane (literal/length alphabet first, then distances);
+// this call covers combined symbols [b0, b0 + n).  Returns 0 ok, 1 = not usable on the fast path
+// (invalid / incomplete set in a shape k_inflate has to judge, or second-level budget exceeded).
+template <bool IS_DIST>
+__device__ __forceinline__ uint16_t i2_symbol_entry(uint32_t s, uint32_t cb) {
+	if (IS_DIST) {
+		const uint32_t xb = s < 4u ? 0u : (s - 2u) >> 1;
+		return s < 30u ? I2_DST_ENTRY(cb + xb, xb, s) : I2_DST_INVALID;
+	}
+	if (s < 256u) {
+		return I2_LIT_ENTRY(cb, I2_K_LIT, s);
+	}
+	if (s == 256u) {
+		return I2_LIT_ENTRY(cb, I2_K_EOB, 0u);
+	}
+	const uint32_t v = s - 257u;
+	const uint32_t xb = (v < 8u || v == 28u) ? 0u : (v - 4u) >> 2;
+	return s < 286u ? I2_LIT_ENTRY(cb + xb, I2_K_LEN, xb | (v << 3)) : I2_LIT_INVALID;
+}
+
+// length and position in sorted[] of the code that covers the 15-bit left-aligned value c15 (len 16 = none)
+__device__ __forceinline__ void i2_lookup15(const I2WarpScratch &S, uint32_t c15, uint32_t &len, uint32_t &idx) {
+	uint32_t l = 1;
+#pragma unroll
+	for (int j = 1; j <= 15; j++) {
+		l += (c15 >= S.limit15[j]);
+	}
+	len = l;
+	const uint32_t ll = l > 15u ? 15u : l;
+	idx = S.offs[ll] + ((c15 - S.first15[ll]) >> (15u - ll));
+}
+
+template <bool IS_DIST, int ROOT, int CAP>
+__device__ __noinline__ int i2_build_table(I2WarpScratch &S, const uint32_t (&lens)[10], uint32_t b0, uint32_t n, uint16_t *tbl) {
+	const uint32_t lane = threadIdx.x & 31u;
+	constexpr uint16_t INVALID = IS_DIST ? I2_DST_INVALID : I2_LIT_INVALID;
+	if (lane < 16) {
+		S.cnt[lane] = 0;
+	}
+	__syncwarp();
+	uint32_t mylen[10];
+#pragma unroll
+	for (int j = 0; j < 10; j++) {
+		const uint32_t s = 32u * j + lane - b0;
+		mylen[j] = s < n ? lens[j] : 0u;
+		if (mylen[j]) {
+			atomicAdd(&S.cnt[mylen[j]], 1u);
+		}
+	}
+	__syncwarp();
+	int left = 1;
+	uint32_t ncodes = 0;
+	{
+		uint32_t code = 0, off = 0;
+		for (uint32_t l = 1; l <= 15; l++) {
+			const uint32_t c = S.cnt[l];
+			left = (left << 1) - (int)c;
+			if (left < 0) {
+				return 1;   // over-subscribed
+			}
+			code = (code + (l > 1 ? S.cnt[l - 1] : 0u)) << 1;
+			if (lane == 0) {
+				S.offs[l] = off;
+				S.run[l] = off;
+				S.first15[l] = code << (15u - l);
+				S.limit15[l] = (code + c) << (15u - l);
+			}
+			off += c;
+			ncodes += c;
+		}
+	}
+	constexpr uint32_t ROOTSZ = 1u << ROOT;
+	if (ncodes == 0) {
+		if (!IS_DIST) {
+			return 1;
+		}
+		for (uint32_t k = lane; k < ROOTSZ; k += 32) {
+			tbl[k] = INVALID;   // a block of literals only: any distance code is an error
+		}
+		__syncwarp();
+		return 0;
+	}
+	if (left > 0 && !(ncodes == 1 && S.cnt[1] == 1)) {
+		return 1;   // incomplete set (zlib accepts only a single 1-bit code): k_inflate reports it
+	}
+	__syncwarp();
+	// canonical order: sorted[] = symbols by (length, symbol)
+#pragma unroll
+	for (int j = 0; j < 10; j++) {
+		const uint32_t l = mylen[j];
+		const uint32_t m = __match_any_sync(0xFFFFFFFFu, l);
+		const uint32_t rank = __popc(m & ((1u << lane) - 1u));
+		if (l) {
+			S.sorted[S.run[l] + rank] = (uint16_t)(32u * j + lane - b0);
+		}
+		__syncwarp();
+		if (l && rank == 0) {
+			S.run[l] += __popc(m);
+		}
+		__syncwarp();
+	}
+	// root slots: slot k holds the code whose bits, LSB first, are a prefix of k
+	const uint32_t long15 = S.limit15[ROOT];          // first 15-bit value whose code is longer than ROOT bits
+	const uint32_t end15 = S.limit15[15];             // one past the last covered value (32768 when complete)
+	for (uint32_t k = lane; k < ROOTSZ; k += 32) {
+		const uint32_t c15 = (__brev(k) >> (32 - ROOT)) << (15 - ROOT);
+		uint16_t e = INVALID;
+		if (c15 < long15) {
+			uint32_t len, idx;
+			i2_lookup15(S, c15, len, idx);
+			e = i2_symbol_entry<IS_DIST>(S.sorted[idx], len);
+		}
+		tbl[k] = e;
+	}
+	// prefixes of codes longer than ROOT bits: one second-level table each, sized by its longest code
+	if (end15 > long15) {
+		const uint32_t p0 = long15 >> (15 - ROOT), p1 = (end15 + (1u << (15 - ROOT)) - 1u) >> (15 - ROOT);
+		uint32_t next_free = ROOTSZ;
+		for (uint32_t pb = p0; pb < p1; pb += 32) {
+			const uint32_t p = pb + lane;
+			uint32_t sub_bits = 0;
+			if (p < p1) {
+				uint32_t v15 = ((p + 1u) << (15 - ROOT)) - 1u;
+				v15 = v15 < end15 ? v15 : end15 - 1u;
+				uint32_t len, idx;
+				i2_lookup15(S, v15, len, idx);
+				sub_bits = len - ROOT;
+			}
+			const uint32_t size = p < p1 ? (1u << sub_bits) : 0u;
+			uint32_t incl = size;
+#pragma unroll
+			for (int d = 1; d < 32; d <<= 1) {
+				const uint32_t t = __shfl_up_sync(0xFFFFFFFFu, incl, d);
+				if ((int)lane >= d) {
+					incl += t;
+				}
+			}
+			const uint32_t total = __shfl_sync(0xFFFFFFFFu, incl, 31);
+			if (next_free + total > (uint32_t)CAP) {
+				return 1;   // second-level budget exceeded: k_inflate (worst-case tables) takes the stream
+			}
+			const uint32_t sub_off = next_free + incl - size;
+			next_free += total;
+			if (p < p1) {
+				tbl[__brev(p) >> (32 - ROOT)] = IS_DIST ? I2_DST_LINK(sub_bits, sub_off) : I2_LIT_LINK(sub_bits, sub_off);
+				for (uint32_t t = 0; t < size; t++) {
+					const uint32_t c15 = (p << (15 - ROOT)) | ((__brev(t) >> (32u - sub_bits)) << (15u - ROOT - sub_bits));
+					uint16_t e = INVALID;
+					if (c15 < end15) {
+						uint32_t len, idx;
+						i2_lookup15(S, c15, len, idx);
+						e = i2_symbol_entry<IS_DIST>(S.sorted[idx], len - ROOT);
+					}
+					tbl[sub_off + t] = e;
+				}
+			}
+		}
+	}
+	__syncwarp();
+	return 0;
+}
+
+// ------------------------------------------------------------------------------------------------
+// lane states
+#define I2_S_IDLE 0u     // needs a stream
+#define I2_S_HDR 1u      // at a block header
+#define I2_S_BUILD 2u    // code lengths parsed into the slot; waiting for the cooperative table build
+#define I2_S_DEC 3u      // decoding symbols
+#define I2_S_DONE 4u     // no more work
+
+__device__ __forceinline__ uint32_t i2_ld_le16(const uint8_t *p) { return (uint32_t)p[0] | ((uint32_t)p[1] << 8); }
+
+// phase A.  grid: persistent, one warp per CTA; the first `lanes_active` (<= I2_LANES) lanes of every warp pull list
+// indices from *work_counter.  (Few streams are spread over all resident warps rather than packed into few:
+// a lock-step step costs the same whatever the number of live lanes.)
+__global__ void __launch_bounds__(32) k_inflate_tok(const uint8_t *__restrict__ archive, const otz_entry *__restrict__ ents,
+	const OtzEntryState *__restrict__ est, const int32_t *__restrict__ status, const uint32_t *__restrict__ list, uint32_t n_list,
+	uint32_t *__restrict__ work_counter, uint8_t *__restrict__ scratch, const uint64_t *__restrict__ tok_ofs, I2TokRes *__restrict__ tokres,
+	uint32_t *__restrict__ fb_list, uint32_t *__restrict__ fb_count, uint32_t lanes_active) {
+	extern __shared__ __align__(16) uint8_t smem_raw[];
+	const uint32_t lane = threadIdx.x;
+	// lanes without a slot never become active; their (predicated-off) table reads go to slot 0
+	uint8_t *const slot = smem_raw + (lane < I2_LANES ? lane : 0u) * I2_SLOT_BYTES;
+	const uint16_t *const lit = reinterpret_cast<const uint16_t *>(slot);
+	const uint16_t *const dst = lit + I2_LIT_CAP;
+	I2WarpScratch &WS = *reinterpret_cast<I2WarpScratch *>(smem_raw + I2_LANES * I2_SLOT_BYTES);
+
+	{
+		const uint32_t xl = (lane < 8u || lane == 28u) ? 0u : (lane - 4u) >> 2, xd = lane < 4u ? 0u : (lane - 2u) >> 1;
+		WS.len_base[lane] = (uint16_t)(lane < 29u ? i2_len_base(lane, xl) : 0u);
+		WS.dist_base[lane] = (uint16_t)(lane < 30u ? i2_dist_base(lane, xd) : 0u);
+	}
+	__syncwarp();
+	uint32_t state = lane < lanes_active ? I2_S_IDLE : I2_S_DONE;
+	I2Reader br;
+	// lanes that never get a stream still run the (predicated-off) refill logic: give them a harmless source
+	br.b16 = reinterpret_cast<const uint4 *>(reinterpret_cast<uint64_t>(archive) & ~15ull);
+	br.nvec = br.wi = br.lo = br.hi = br.nx = br.pos = br.pad_bits = br.wi_end = 0;
+	br.col = WS.ring + lane * 4u;
+	const uint8_t *in = nullptr;
+	uint32_t comp = 0, cap = 0, rflags = 0, k = 0, ei = 0;
+	// output bytes so far = nl + mb; the current literal run = nl - nl0
+	uint32_t nl = 0, nl0 = 0, mb = 0, nseq = 0;
+	uint8_t *litp = nullptr;
+	uint32_t *seqp = nullptr;
+	uint32_t final_blk = 0, ref_eob = 0, hlit = 0, hdist = 0;
+
+// leave the current stream: FALLBACK = hand it to k_inflate, COMMIT = release it to phase B
+#define I2_FALLBACK()                                                     \
+	do {                                                                  \
+		fb_list[atomicAdd(fb_count, 1u)] = ei;                            \
+		tokres[k].ok = 0u;                                                \
+		state = I2_S_IDLE;                                                \
+	} while (0)
+#define I2_COMMIT()                                                                         \
+	do {                                                                                    \
+		if (br.remaining_bits() < 0 || nl + mb != cap) {                                    \
+			I2_FALLBACK();                                                                  \
+		} else {                                                                            \
+			I2TokRes r;                                                                     \
+			r.nseq = nseq;                                                                  \
+			r.nlit = nl;                                                                    \
+			r.status = (rflags & OTZ_EF_CHUNK) ? OTZ_ST_OK : (OTZ_ST_OK | (ref_eob ? OTZ_STF_REF_EOB : 0)); \
+			r.ok = 1u;                                                                      \
+			tokres[k] = r;                                                                  \
+			state = I2_S_IDLE;                                                              \
+		}                                                                                   \
+	} while (0)
+// dec:811-816 as k_inflate evaluates it: after a step that leaves the stream unfinished
+#define I2_STEP_CHECK()                                   \
+	if (br.words_left() <= 1) {                             \
+		const int64_t rem_ = br.remaining_bits();         \
+		if (rem_ < 0) {                                   \
+			I2_FALLBACK();                                \
+		} else if (rem_ < 8) {                            \
+			ref_eob = 1u;                                 \
+		}                                                 \
+	}
+// one literal byte / one match into the stream's token scratch
+#define I2_EMIT_LIT(byte_)                      \
+	do {                                        \
+		litp[nl] = (uint8_t)(byte_);            \
+		nl++;                                   \
+	} while (0)
+#define I2_EMIT_MATCH(run_, len_, dist_)                                              \
+	do {                                                                              \
+		*--seqp = (run_) | (((len_) - 3u) << 9) | (((dist_) - 1u) << 17);             \
+		nseq++;                                                                       \
+		nl0 = nl;                                                                     \
+		mb += (len_);                                                                 \
+	} while (0)
+
+	for (;;) {
+		// ---- (1) hand streams to idle lanes
+		{
+			const uint32_t idle = __ballot_sync(0xFFFFFFFFu, state == I2_S_IDLE);
+			if (idle) {
+				uint32_t base = 0;
+				if (lane == (uint32_t)(__ffs(idle) - 1)) {
+					base = atomicAdd(work_counter, (uint32_t)__popc(idle));
+				}
+				base = __shfl_sync(0xFFFFFFFFu, base, __ffs(idle) - 1);
+				if (state == I2_S_IDLE) {
+					k = base + __popc(idle & ((1u << lane) - 1u));
+					if (k >= n_list) {
+						state = I2_S_DONE;
+					} else {
+						ei = list[k];
+						if (OTZ_ST_CODE(status[ei]) == OTZ_ST_OK) {
+							const otz_entry e = ents[ei];
+							in = archive + est[ei].data_ofs;
+							comp = e.comp_size;
+							cap = e.uncomp_size;
+							rflags = e.flags;
+							litp = scratch + tok_ofs[k];
+							seqp = reinterpret_cast<uint32_t *>(scratch + tok_ofs[k + 1]);
+							nl = nl0 = mb = nseq = 0;
+							ref_eob = 0;
+							if (comp == 0) {
+								I2_FALLBACK();   // dec:610: k_inflate answers TRUNCATED
+							} else {
+								br.init(in, comp);
+								state = I2_S_HDR;
+							}
+						} else {
+							tokres[k].ok = 0u;   // failed in k_resolve: nothing to decode (stays idle, picks the next one)
+						}
+					}
+				}
+			}
+			if (__all_sync(0xFFFFFFFFu, state == I2_S_DONE)) {
+				break;
+			}
+		}
+		// ---- (2) block headers (dec:613-627), every lane that stands at one, in lock-step
+		if (state == I2_S_HDR) {
+			const bool chunk_mid = (rflags & OTZ_EF_CHUNK) && !(rflags & OTZ_EF_LAST_CHUNK);
+			br.norm();
+			uint32_t bits = br.peek();
+			final_blk = bits & 1u;
+			const uint32_t btype = (bits >> 1) & 3u;
+			br.pos += 3;
+			I2_STEP_CHECK();
+			if (state != I2_S_HDR) {
+				// fell back
+			} else if (btype == 0) {
+				// stored block (dec:269-319): only the empty ones (flush points, chunk terminators) stay on this path
+				const int64_t rem = br.remaining_bits();
+				const uint64_t bpos = (uint64_t)comp - (uint64_t)(rem >> 3);
+				if ((uint64_t)comp - bpos < 4 || i2_ld_le16(in + bpos) != 0u || i2_ld_le16(in + bpos + 2) != 0xFFFFu) {
+					I2_FALLBACK();
+				} else {
+					const uint64_t npos = bpos + 4;
+					br.init(in + npos, (uint64_t)comp - npos);
+					if (final_blk) {
+						I2_COMMIT();
+					} else if (npos >= comp) {
+						if (chunk_mid) {
+							I2_COMMIT();   // end of this chunk
+						} else {
+							I2_FALLBACK();   // unfinished stream out of input
+						}
+					}
+				}
+			} else if (btype == 3) {
+				I2_FALLBACK();   // dec:657-658
+			} else if (btype == 1) {
+				br.norm();
+				if ((br.peek() & 127u) == 0u) {
+					// empty fixed block (zlib's Z_FINISH tail): end-of-block is the 7-bit code 0000000
+					br.pos += 7;
+					if (final_blk) {
+						I2_COMMIT();
+					} else if (chunk_mid && br.remaining_bits() < 8 && br.remaining_bits() >= 0) {
+						I2_COMMIT();
+					} else {
+						I2_STEP_CHECK();
+					}
+				} else {
+					uint8_t *lens = slot + I2_LENS_OFS;   // dec:322-349
+					for (int i = 0; i < 320; i++) {
+						lens[i] = i < 144 ? 8 : i < 256 ? 9 : i < 280 ? 7 : i < 288 ? 8 : 5;
+					}
+					hlit = 288;
+					hdist = 32;
+					state = I2_S_BUILD;
+				}
+			} else {
+				// dynamic block header, dec:122-266
+				uint8_t *lens = slot + I2_LENS_OFS;
+				uint8_t *pre = slot + I2_PRE_OFS;
+				br.norm();
+				bits = br.peek();
+				hlit = (bits & 31u) + 257u;
+				hdist = ((bits >> 5) & 31u) + 1u;
+				const uint32_t hclen = ((bits >> 10) & 15u) + 4u;
+				br.pos += 14;
+				bool bad = hlit > 286u || hdist > 30u;
+				uint64_t cl = 0;    // 19 code-length-code lengths, 3 bits each
+				uint64_t cnt = 0;   // packed byte counters per length
+				for (uint32_t i = 0; i < hclen; i++) {
+					br.norm();
+					const uint32_t v = br.peek() & 7u;
+					br.pos += 3;
+					cl |= (uint64_t)v << (3u * c_cl_order[i]);
+					cnt += 1ull << (8u * v);
+				}
+				uint64_t next = 0;   // packed next canonical code per length
+				{
+					int left = 1;
+					uint32_t code = 0;
+					for (uint32_t l = 1; l <= 7; l++) {
+						const uint32_t c = (uint32_t)(cnt >> (8u * l)) & 0xFFu;
+						left = (left << 1) - (int)c;
+						bad |= left < 0;
+						code = (code + (l > 1 ? (uint32_t)(cnt >> (8u * (l - 1))) & 0xFFu : 0u)) << 1;
+						next |= (uint64_t)(code & 0xFFu) << (8u * l);
+					}
+					bad |= left != 0;   // the code-length code must be complete
+				}
+				if (!bad) {
+					for (uint32_t s = 0; s < 19; s++) {
+						const uint32_t l = (uint32_t)(cl >> (3u * s)) & 7u;
+						if (l) {
+							const uint32_t c = (uint32_t)(next >> (8u * l)) & 0xFFu;
+							next += 1ull << (8u * l);
+							const uint32_t rev = __brev(c) >> (32u - l);
+							for (uint32_t x = rev; x < 128u; x += (1u << l)) {
+								pre[x] = (uint8_t)(s | (l << 5));
+							}
+						}
+					}
+					const uint32_t total = hlit + hdist;
+					uint32_t idx = 0, prev = 0;
+					while (idx < total) {
+						br.norm();
+						bits = br.peek();
+						const uint32_t e = pre[bits & 127u];
+						const uint32_t sym = e & 31u, cb = e >> 5;
+						if (sym < 16u) {
+							br.pos += cb;
+							lens[idx++] = (uint8_t)sym;
+							prev = sym;
+							continue;
+						}
+						uint32_t rep, val = 0;
+						if (sym == 16u) {   // dec:209-219
+							if (idx == 0) {
+								bad = true;
+								break;
+							}
+							val = prev;
+							rep = 3u + ((bits >> cb) & 3u);
+							br.pos += cb + 2;
+						} else if (sym == 17u) {   // dec:221-228
+							rep = 3u + ((bits >> cb) & 7u);
+							br.pos += cb + 3;
+						} else {   // dec:230-237
+							rep = 11u + ((bits >> cb) & 127u);
+							br.pos += cb + 7;
+						}
+						if (idx + rep > total) {
+							bad = true;   // dec:244
+							break;
+						}
+						for (uint32_t i = 0; i < rep; i++) {
+							lens[idx + i] = (uint8_t)val;
+						}
+						idx += rep;
+						prev = val;
+					}
+					for (uint32_t i = total; i < 320u; i++) {
+						lens[i] = 0;
+					}
+					bad |= !bad && lens[256] == 0;   // no end-of-block code
+				}
+				if (bad || br.remaining_bits() < 0) {
+					I2_FALLBACK();
+				} else {
+					state = I2_S_BUILD;
+				}
+			}
+		}
+		// ---- (2b) tables, one requesting lane at a time, whole warp
+		{
+			uint32_t need = __ballot_sync(0xFFFFFFFFu, state == I2_S_BUILD);
+			while (need) {
+				const int x = __ffs(need) - 1;
+				need &= need - 1;
+				__syncwarp();
+				const uint8_t *xl = smem_raw + x * I2_SLOT_BYTES + I2_LENS_OFS;
+				uint32_t lens[10];
+#pragma unroll
+				for (int j = 0; j < 10; j++) {
+					lens[j] = xl[32 * j + lane];
+				}
+				__syncwarp();
+				const uint32_t xh = __shfl_sync(0xFFFFFFFFu, hlit, x), xd = __shfl_sync(0xFFFFFFFFu, hdist, x);
+				uint16_t *xt = reinterpret_cast<uint16_t *>(smem_raw + x * I2_SLOT_BYTES);
+				int r = i2_build_table<false, I2_LIT_ROOT, I2_LIT_CAP>(WS, lens, 0u, xh, xt);
+				if (!r) {
+					r = i2_build_table<true, I2_DST_ROOT, I2_DST_CAP>(WS, lens, xh, xd, xt + I2_LIT_CAP);
+				}
+				__syncwarp();
+				if ((int)lane == x) {
+					if (r) {
+						I2_FALLBACK();
+					} else {
+						state = I2_S_DEC;
+						I2_STEP_CHECK();
+					}
+				}
+			}
+		}
+		// ---- (3) symbols (dec:662-799).  One literal/length symbol and — used by the lanes that got a length —
+		// one distance symbol per step, as straight-line code: every lane runs the same instructions.  Everything
+		// unusual (second-level tables, end of block, long literal runs, errors, end of input) is left untouched
+		// by the main path and finished, lane by lane, behind ONE warp vote at the end of the step.
+		while (__all_sync(0xFFFFFFFFu, state == I2_S_DEC || state == I2_S_DONE) && __any_sync(0xFFFFFFFFu, state == I2_S_DEC)) {
+			bool leave = false;
+#pragma unroll 1
+			for (int burst = 0; burst < 32 && !leave; burst++) {
+				const bool act = state == I2_S_DEC;
+				br.norm();
+				const uint32_t bits = br.peek();
+				const uint32_t e = lit[bits & ((1u << I2_LIT_ROOT) - 1u)];
+				const uint32_t tb = e & 15u, kind = (e >> 4) & 3u;
+				const bool is_lit = act && kind == I2_K_LIT, is_len = act && kind == I2_K_LEN;
+				br.pos += tb;   // (0 for a LINK entry; idle lanes do not care)
+				// length (dec:720-737)
+				const uint32_t xb = (e >> 6) & 7u, v = (e >> 9) & 31u;
+				const uint32_t length = WS.len_base[v] + ((bits >> (tb - xb)) & ((1u << xb) - 1u));
+				// distance (dec:740-782); lanes without a length decode garbage and ignore it
+				br.norm();
+				const uint32_t bits2 = br.peek();
+				const uint32_t d = dst[bits2 & ((1u << I2_DST_ROOT) - 1u)];
+				const uint32_t tb2 = d & 31u, dxb = (d >> 5) & 15u, ds = (d >> 9) & 31u;
+				const uint32_t dist = WS.dist_base[ds] + ((bits2 >> (tb2 - dxb)) & ((1u << dxb) - 1u));
+				const uint32_t run = nl - nl0, opos = nl + mb;
+				// a match the main path completes: root-level distance code, short literal run, source inside the output
+				const bool len_ok = is_len && (d >> 14) == 0u && run < I2_SEQ_ESC && dist <= opos;
+				br.pos += len_ok ? tb2 : 0u;
+				if (is_lit) {
+					I2_EMIT_LIT((e >> 6) & 0xFFu);
+				}
+				if (len_ok) {
+					I2_EMIT_MATCH(run, length, dist);
+				}
+				// (the token scratch has room for the one literal or record that may exceed `cap` here)
+				const bool special = act && ((!is_lit && !len_ok) || nl + mb > cap || br.words_left() <= 1);
+				if (__any_sync(0xFFFFFFFFu, special)) {
+					if (special) {
+						bool bad = nl + mb > cap;   // dec:700-703, dec:791-793
+						bool eob = kind == I2_K_EOB;
+						bool want_dist = is_len && !len_ok;   // length consumed, distance still to do
+						uint32_t len2 = length;
+						if (!bad && kind == I2_K_LINK) {
+							// second-level literal/length table
+							const uint32_t sb = I2_LIT_LINK_BITS(e);
+							if (sb == 0u) {
+								bad = true;   // dec:693-695: no code matches
+							} else {
+								const uint32_t e2 = lit[I2_LIT_LINK_OFS(e) + ((bits >> I2_LIT_ROOT) & ((1u << sb) - 1u))];
+								const uint32_t k2 = (e2 >> 4) & 3u, t2 = e2 & 15u;
+								if (k2 == I2_K_LINK) {
+									bad = true;
+								} else {
+									br.pos += I2_LIT_ROOT + t2;
+									if (k2 == I2_K_LIT) {
+										I2_EMIT_LIT((e2 >> 6) & 0xFFu);
+										bad = nl + mb > cap;
+									} else if (k2 == I2_K_EOB) {
+										eob = true;
+									} else {
+										const uint32_t x2 = (e2 >> 6) & 7u;
+										len2 = WS.len_base[(e2 >> 9) & 31u] + ((bits >> (I2_LIT_ROOT + t2 - x2)) & ((1u << x2) - 1u));
+										want_dist = true;
+									}
+								}
+							}
+						}
+						if (!bad && want_dist) {
+							br.norm();
+							const uint32_t b3 = br.peek();
+							uint32_t dd = dst[b3 & ((1u << I2_DST_ROOT) - 1u)];
+							uint32_t used = 0;
+							if ((dd >> 14) != 0u) {
+								const uint32_t sb = I2_DST_LINK_BITS(dd);
+								if (sb == 0u) {
+									bad = true;   // dec:762-764
+								} else {
+									dd = dst[I2_DST_LINK_OFS(dd) + ((b3 >> I2_DST_ROOT) & ((1u << sb) - 1u))];
+									used = I2_DST_ROOT;
+									bad = (dd >> 14) != 0u;
+								}
+							}
+							if (!bad) {
+								const uint32_t t3 = dd & 31u, x3 = (dd >> 5) & 15u;
+								const uint32_t dist3 = WS.dist_base[(dd >> 9) & 31u] + ((b3 >> (used + t3 - x3)) & ((1u << x3) - 1u));
+								br.pos += used + t3;
+								uint32_t r3 = nl - nl0;
+								if (dist3 > nl + mb) {
+									bad = true;   // reaches before the start of the output (strict; dec:785 does not check)
+								} else {
+									while (r3 >= I2_SEQ_ESC) {
+										*--seqp = I2_SEQ_ESC;
+										nseq++;
+										r3 -= I2_SEQ_ESC;
+									}
+									I2_EMIT_MATCH(r3, len2, dist3);
+									bad = nl + mb > cap;
+								}
+							}
+						}
+						if (bad) {
+							I2_FALLBACK();
+						} else if (eob) {
+							// end of block, dec:711-716 (pos already stands behind the code)
+							const bool chunk_mid = (rflags & OTZ_EF_CHUNK) && !(rflags & OTZ_EF_LAST_CHUNK);
+							if (final_blk) {
+								I2_COMMIT();
+							} else if (chunk_mid && br.remaining_bits() < 8 && br.remaining_bits() >= 0) {
+								I2_COMMIT();   // end of this chunk
+							} else {
+								state = I2_S_HDR;
+								I2_STEP_CHECK();
+							}
+						} else {
+							I2_STEP_CHECK();
+						}
+					}
+					leave = __any_sync(0xFFFFFFFFu, state != I2_S_DEC && state != I2_S_DONE);
+				}
+			}
+		}
+	}
+#undef I2_FALLBACK
+#undef I2_COMMIT
+#undef I2_STEP_CHECK
+#undef I2_EMIT_LIT
+#undef I2_EMIT_MATCH
+}
+
+// ------------------------------------------------------------------------------------------------
+// phase B.  One warp per committed stream; W = bytes of shared-memory ring per warp.  Ring index of output
+// byte p is (p + mis) & (W-1) with mis = dst & 15 (as OutRing in k_inflate.cuh), so ring vectors line up with
+// 16-byte aligned global vectors.
+template <int W>
+struct I2Ring {
+	static constexpr uint32_t MASK = W - 1;
+	static constexpr uint32_t SEG = 512;
+	// output bytes per batch.  W >= SPAN_MAX + SEG + 770 guarantees that a match source outside the ring window
+	// of a batch has been flushed to HBM before the batch starts.
+	static constexpr uint32_t SPAN_MAX = W >= 8192 ? 2048u : 1024u;
+};
+
+// write ring[a, b) (linear positions) to HBM; whole warp, ring contents visible (caller synced)
+template <int W>
+__device__ __forceinline__ void i2_flush_range(uint8_t *gbase, const uint8_t *ring, uint32_t a, uint32_t b, uint32_t lane) {
+	constexpr uint32_t MASK = W - 1;
+	const uint32_t a16 = (a + 15u) & ~15u, b16 = b & ~15u;
+	if (a16 >= b16) {
+		for (uint32_t x = a + lane; x < b; x += 32) {
+			gbase[x] = ring[x & MASK];
+		}
+		return;
+	}
+	for (uint32_t x = a + lane; x < a16; x += 32) {
+		gbase[x] = ring[x & MASK];
+	}
+	for (uint32_t x = a16 + 16u * lane; x < b16; x += 512u) {
+		*reinterpret_cast<uint4 *>(gbase + x) = *reinterpret_cast<const uint4 *>(ring + (x & MASK));
+	}
+	for (uint32_t x = b16 + lane; x < b; x += 32) {
+		gbase[x] = ring[x & MASK];
+	}
+}
+
+// overlapping LZ77 copy (distance < length): periodic extension of the last `dd` bytes, whole warp
+template <int W>
+__device__ __noinline__ void i2_copy_periodic(uint8_t *rb, uint32_t dq, uint32_t sq, uint32_t dd, uint32_t len, uint32_t lane) {
+	constexpr uint32_t MASK = W - 1;
+	uint32_t r = dd > lane ? lane : lane % dd;
+	const uint32_t step = dd > 32u ? 32u : 32u % dd;
+	for (uint32_t x = lane; x < len; x += 32) {
+		rb[(dq + x) & MASK] = rb[(sq + r) & MASK];
+		r += step;
+		r = r >= dd ? r - dd : r;
+	}
+}
+
+template <int W>
+__global__ void __launch_bounds__(256) k_inflate_lz(uint8_t *__restrict__ out, const otz_entry *__restrict__ ents, const uint32_t *__restrict__ list,
+	uint32_t n_list, uint32_t *__restrict__ work_counter, const uint8_t *__restrict__ scratch, const uint64_t *__restrict__ tok_ofs,
+	const I2TokRes *__restrict__ tokres, int32_t *__restrict__ status, uint32_t *__restrict__ produced_out) {
+	extern __shared__ __align__(16) uint8_t smem_raw[];
+	constexpr uint32_t MASK = I2Ring<W>::MASK, SEG = I2Ring<W>::SEG, SPAN_MAX = I2Ring<W>::SPAN_MAX;
+	const uint32_t lane = threadIdx.x & 31u;
+	uint8_t *const rb = smem_raw + (threadIdx.x >> 5) * (W + 512);
+	uint2 *const far_l = reinterpret_cast<uint2 *>(rb + W);
+	uint2 *const near_l = far_l + 32;
+	const uint32_t lt_mask = (1u << lane) - 1u;
+	for (;;) {
+		uint32_t k = 0;
+		if (lane == 0) {
+			k = atomicAdd(work_counter, 1u);
+		}
+		k = __shfl_sync(0xFFFFFFFFu, k, 0);
+		if (k >= n_list) {
+			break;
+		}
+		const I2TokRes tr = tokres[k];
+		if (!tr.ok) {
+			continue;
+		}
+		const uint32_t ei = list[k];
+		const otz_entry e = ents[ei];
+		uint8_t *const dstp = out + e.out_ofs;
+		const uint32_t mis = (uint32_t)(reinterpret_cast<uint64_t>(dstp) & 15u);
+		uint8_t *const gbase = dstp - mis;
+		const uint8_t *const lits = scratch + tok_ofs[k];
+		const uint32_t *const seq_end = reinterpret_cast<const uint32_t *>(scratch + tok_ofs[k + 1]);
+		uint32_t q = mis, qf = mis;   // linear write position / position up to which HBM holds the data
+		uint32_t lp = 0;              // literals consumed
+		__syncwarp();
+		for (uint32_t b = 0; b < tr.nseq;) {
+			const uint32_t i = b + lane;
+			const bool have = i < tr.nseq;
+			const uint32_t rec = have ? __ldcs(seq_end - 1 - i) : 0u;
+			const uint32_t lr = rec & 511u;
+			const uint32_t ml = (have && lr != I2_SEQ_ESC) ? ((rec >> 9) & 255u) + 3u : 0u;
+			const uint32_t dist = (rec >> 17) + 1u;
+			uint32_t lsum = lr, osum = lr + ml;
+#pragma unroll
+			for (int d = 1; d < 32; d <<= 1) {
+				const uint32_t a = __shfl_up_sync(0xFFFFFFFFu, lsum, d), c = __shfl_up_sync(0xFFFFFFFFu, osum, d);
+				if ((int)lane >= d) {
+					lsum += a;
+					osum += c;
+				}
+			}
+			// take the longest prefix of the batch whose output fits SPAN_MAX (one record is at most 769 bytes)
+			const uint32_t fit = __ballot_sync(0xFFFFFFFFu, have && osum <= SPAN_MAX);
+			const uint32_t ntake = __popc(fit);   // osum is monotonic, so `fit` is a prefix mask
+			const bool mine = lane < ntake;
+			const uint32_t tot_l = __shfl_sync(0xFFFFFFFFu, lsum, ntake - 1), tot_o = __shfl_sync(0xFFFFFFFFu, osum, ntake - 1);
+			const uint32_t my_lit = lp + lsum - lr;         // first literal of this record
+			const uint32_t my_out = q + osum - lr - ml;     // linear output position of this record
+			const uint32_t q_end = q + tot_o;
+			// literal runs, all records at once
+			if (mine) {
+				for (uint32_t t = 0; t < lr; t++) {
+					rb[(my_out + t) & MASK] = lits[my_lit + t];
+				}
+			}
+			// Match descriptors {destination, distance-1 | length << 15}, compacted into two per-warp lists.
+			// far: the source lies below the ring window [q_end - W, q_end): flushed to HBM before this batch
+			// started and independent of anything the batch produces.  near: everything else, in stream order.
+			const uint32_t mq = my_out + lr;   // match destination
+			const bool is_match = mine && ml != 0u;
+			const bool is_far = is_match && dist > (uint32_t)W - (q_end - mq);
+			const uint32_t far_m = __ballot_sync(0xFFFFFFFFu, is_far);
+			const uint32_t near_m = __ballot_sync(0xFFFFFFFFu, is_match && !is_far);
+			const bool far_long = __any_sync(0xFFFFFFFFu, is_far && ml > 32u);
+			if (is_match) {
+				const uint2 dsc = make_uint2(mq, (dist - 1u) | (ml << 15));
+				if (is_far) {
+					far_l[__popc(far_m & lt_mask)] = dsc;
+				} else {
+					near_l[__popc(near_m & lt_mask)] = dsc;
+				}
+			}
+			__syncwarp();
+			const uint32_t n_far = __popc(far_m), n_near = __popc(near_m);
+			// far: four matches per trip, 32-byte slices, all loads of a slice in flight before the first store
+			for (uint32_t f = 0; f < n_far; f += 4) {
+				uint32_t dq[4], ln[4];
+				const uint8_t *sp[4];
+				uint32_t maxl = 0;
+#pragma unroll
+				for (int u = 0; u < 4; u++) {
+					const uint2 dsc = far_l[(f + u) & 31u];
+					dq[u] = dsc.x + lane;
+					ln[u] = f + u < n_far ? dsc.y >> 15 : 0u;
+					sp[u] = gbase + dsc.x - (dsc.y & 0x7FFFu) - 1u + lane;
+					maxl = max(maxl, ln[u]);
+				}
+				for (uint32_t off = 0; off < maxl; off += 32) {
+					uint32_t v[4];
+#pragma unroll
+					for (int u = 0; u < 4; u++) {
+						v[u] = 0;
+						if (off + lane < ln[u]) {
+							v[u] = __ldcg(sp[u] + off);
+						}
+					}
+#pragma unroll
+					for (int u = 0; u < 4; u++) {
+						if (off + lane < ln[u]) {
+							rb[(dq[u] + off) & MASK] = (uint8_t)v[u];
+						}
+					}
+				}
+			}
+			(void)far_long;
+			// the rest in stream order, ring -> ring (dec:521-533: an overlapping copy is a periodic extension)
+			for (uint32_t f = 0; f < n_near; f++) {
+				const uint2 dsc = near_l[f];
+				const uint32_t dq = dsc.x, dd = (dsc.y & 0x7FFFu) + 1u, len = dsc.y >> 15;
+				const uint32_t sq = dq - dd;
+				__syncwarp();   // earlier ring stores are visible to the loads below
+				if (dd >= len) {
+					if (lane < len) {
+						rb[(dq + lane) & MASK] = rb[(sq + lane) & MASK];
+					}
+					for (uint32_t x = lane + 32u; x < len; x += 32) {
+						rb[(dq + x) & MASK] = rb[(sq + x) & MASK];
+					}
+				} else {
+					i2_copy_periodic<W>(rb, dq, sq, dd, len, lane);
+				}
+			}
+			b += ntake;
+			lp += tot_l;
+			q = q_end;
+			__syncwarp();
+			const uint32_t qa = q & ~(SEG - 1u);
+			if (qa > qf) {
+				i2_flush_range<W>(gbase, rb, qf, qa, lane);
+				qf = qa;
+				__syncwarp();
+			}
+		}
+		// literals after the last match
+		while (lp < tr.nlit) {
+			const uint32_t n = min(tr.nlit - lp, SPAN_MAX);
+			for (uint32_t t = lane; t < n; t += 32) {
+				rb[(q + t) & MASK] = lits[lp + t];
+			}
+			lp += n;
+			q += n;
+			__syncwarp();
+			const uint32_t qa = q & ~(SEG - 1u);
+			if (qa > qf) {
+				i2_flush_range<W>(gbase, rb, qf, qa, lane);
+				qf = qa;
+				__syncwarp();
+			}
+		}
+		if (q > qf) {
+			i2_flush_range<W>(gbase, rb, qf, q, lane);
+		}
+		if (lane == 0) {
+			status[ei] = tr.status;
+			produced_out[ei] = e.uncomp_size;
+		}
+		__syncwarp();
+	}
+}

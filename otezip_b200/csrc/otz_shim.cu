@@ -10,6 +10,7 @@
 #include "k_copy.cuh"
 #include "k_crc32.cuh"
 #include "k_inflate.cuh"
+#include "k_inflate2.cuh"
 #include "k_deflate.cuh"
 #include "k_resolve.cuh"
 #include "k_zstd.cuh"
@@ -46,6 +47,11 @@ struct otz_ctx {
 	uint64_t launches;
 	int inflate_tile;   // lanes per DEFLATE stream (OTZ_INFLATE_TILE; 0 = per batch)
 	int inflate_ring;   // bytes of shared-memory output ring per stream (OTZ_INFLATE_RING; 0 = per batch)
+	int inflate_mode;   // OTZ_INFLATE_MODE: 0 = two-phase (k_inflate_tok + k_inflate_lz, k_inflate as fallback), 1 = k_inflate only
+	int lz_ring;        // OTZ_LZ_RING: ring bytes per warp of k_inflate_lz (4096 / 8192 / 16384)
+	uint32_t last_fallbacks;   // DEFLATE streams of the last collected run that phase A handed to k_inflate
+	uint8_t *d_tok_cache;   // grow-only token scratch of the two-phase inflate (literals + sequence records)
+	uint64_t tok_cache_bytes;
 };
 
 struct otz_plan {
@@ -60,6 +66,10 @@ struct otz_plan {
 	uint32_t n_store_chunks;   // chunks [0, n_store_chunks) belong to STORE entries
 	uint32_t *d_inflate_list, n_inflate;   // DEFLATE entries, longest first; [0, n_inflate_big) are the large ones
 	uint32_t n_inflate_big;
+	uint64_t *d_tok_ofs;       // two-phase inflate: scratch offset of every list slot (+ end), bytes
+	uint64_t tok_bytes;
+	I2TokRes *d_tokres;
+	uint32_t *d_fb_list;       // entries phase A hands to k_inflate
 	uint32_t *d_zstd_list, n_zstd;
 	OtzCrcChunk *d_zchunks;    // CRC chunks of the method-93 entries (used for real Zstandard frames only)
 	uint32_t n_zchunks;
@@ -174,6 +184,10 @@ extern "C" int otz_ctx_create(int device, otz_ctx **out) {
 	c->inflate_tile = t ? atoi(t) : 0;
 	t = getenv("OTZ_INFLATE_RING");
 	c->inflate_ring = t ? atoi(t) : 0;
+	t = getenv("OTZ_INFLATE_MODE");
+	c->inflate_mode = (t && !strcmp(t, "legacy")) ? 1 : 0;
+	t = getenv("OTZ_LZ_RING");
+	c->lz_ring = t ? atoi(t) : 8192;
 	*out = c;
 	return OTZ_SUCCESS;
 }
@@ -188,6 +202,7 @@ extern "C" void otz_ctx_destroy(otz_ctx *c) {
 	cudaFree(c->d_flush);
 	cudaFree(c->d_arch_cache);
 	cudaFree(c->d_out_cache);
+	cudaFree(c->d_tok_cache);
 	cudaEventDestroy(c->ev0);
 	cudaEventDestroy(c->ev1);
 	for (auto &slot : c->pev) {
@@ -343,6 +358,9 @@ extern "C" void otz_plan_destroy(otz_ctx *c, otz_plan *p) {
 	cudaFree(p->d_produced);
 	cudaFree(p->d_chunks);
 	cudaFree(p->d_inflate_list);
+	cudaFree(p->d_tok_ofs);
+	cudaFree(p->d_tokres);
+	cudaFree(p->d_fb_list);
 	cudaFree(p->d_zstd_list);
 	cudaFree(p->d_zchunks);
 	cudaFree(p->d_zstd_lit);
@@ -419,6 +437,19 @@ extern "C" int otz_plan_create(otz_ctx *c, const otz_entry *ents, uint32_t n, co
 	p->out_bytes_needed = need;
 	int rc;
 	std::vector<otz_entry> ev(ents, ents + n);
+	// two-phase inflate: worst-case token scratch per list slot
+	std::vector<uint64_t> tofs(infl.size() + 1);
+	tofs[0] = 0;
+	for (size_t k = 0; k < infl.size(); k++) {
+		tofs[k + 1] = tofs[k] + i2_scratch_bytes(ents[infl[k]].uncomp_size);
+	}
+	p->tok_bytes = tofs.back();
+	if (p->n_inflate && ((rc = upload(&p->d_tok_ofs, tofs, c->stream)) ||
+			cudaMalloc(&p->d_tokres, infl.size() * sizeof(I2TokRes)) != cudaSuccess ||
+			cudaMalloc(&p->d_fb_list, infl.size() * 4) != cudaSuccess)) {
+		otz_plan_destroy(c, p);
+		return rc ? rc : fail_cuda(cudaGetLastError(), "cudaMalloc(two-phase inflate lists)");
+	}
 	if ((rc = upload(&p->d_ents, ev, c->stream)) || (rc = upload(&p->d_chunks, chunks, c->stream)) ||
 		(rc = upload(&p->d_inflate_list, infl, c->stream)) || (rc = upload(&p->d_zstd_list, zst, c->stream)) ||
 		(rc = upload(&p->d_zchunks, zchunks, c->stream))) {
@@ -440,14 +471,15 @@ extern "C" int otz_plan_create(otz_ctx *c, const otz_entry *ents, uint32_t n, co
 			return fail_cuda(cudaGetLastError(), "cudaMalloc(zstd literal scratch)");
 		}
 	}
+	CK(cudaMemsetAsync(p->d_counter, 0, 256, c->stream));
 	CK(cudaStreamSynchronize(c->stream));  // the host vectors die here
 	*out = p;
 	return OTZ_SUCCESS;
 }
 
 template <int G, int W>
-static int launch_inflate(otz_ctx *c, otz_plan *p, const uint8_t *d_archive, uint8_t *d_out, uint32_t first, uint32_t count, int slot,
-	cudaStream_t st) {
+static int launch_inflate(otz_ctx *c, otz_plan *p, const uint8_t *d_archive, uint8_t *d_out, const uint32_t *d_list, uint32_t count, int slot,
+	cudaStream_t st, const uint32_t *d_count) {
 	const int threads = 8 * G;   // 8 streams per CTA
 	const size_t smem = 8 * sizeof(InflateSmemV2<G, W>);
 	static bool attr_done = false;
@@ -465,18 +497,21 @@ static int launch_inflate(otz_ctx *c, otz_plan *p, const uint8_t *d_archive, uin
 	uint32_t grid = (uint32_t)(c->sm_count * per_sm);
 	const uint32_t want = (count + tiles_per_cta - 1) / tiles_per_cta;
 	grid = std::max(1u, std::min(grid, want));
-	k_inflate<G, W><<<grid, threads, smem, st>>>(d_archive, d_out, p->d_ents, p->d_est, p->d_status, p->d_inflate_list + first, count,
-		p->d_counter + 16 * slot, p->d_produced);
+	k_inflate<G, W><<<grid, threads, smem, st>>>(d_archive, d_out, p->d_ents, p->d_est, p->d_status, d_list, count, p->d_counter + 16 * slot,
+		p->d_produced, d_count);
 	c->launches++;
 	CK(cudaGetLastError());
 	return OTZ_SUCCESS;
 }
 
 static int launch_inflate_cfg(otz_ctx *c, otz_plan *p, const uint8_t *d_archive, uint8_t *d_out, int g, int w, uint32_t first, uint32_t count,
-	int slot, cudaStream_t st) {
+	int slot, cudaStream_t st, const uint32_t *d_list = nullptr, const uint32_t *d_count = nullptr) {
+	if (!d_list) {
+		d_list = p->d_inflate_list + first;
+	}
 #define OTZ_INF_CASE(G_, W_)        \
 	if (g == G_ && w == W_) {       \
-		return launch_inflate<G_, W_>(c, p, d_archive, d_out, first, count, slot, st); \
+		return launch_inflate<G_, W_>(c, p, d_archive, d_out, d_list, count, slot, st, d_count); \
 	}
 	OTZ_INF_CASE(32, 16384)
 	OTZ_INF_CASE(32, 4096)
@@ -497,7 +532,80 @@ static int launch_inflate_cfg(otz_ctx *c, otz_plan *p, const uint8_t *d_archive,
 // of text from shared memory, a 2 KiB ring ~35%) against resident streams per SM (10 vs 24).  Large entries set
 // the critical path of a batch, so they always get the big ring, on a second stream so that both kernels can
 // share the machine; small entries get the big ring only when there are too few of them to fill the SMs.
+template <int W>
+static int launch_lz(otz_ctx *c, otz_plan *p, uint8_t *d_out, cudaStream_t st) {
+	const size_t smem = 8 * ((size_t)W + 512);
+	static bool attr_done = false;
+	if (!attr_done) {
+		CK(cudaFuncSetAttribute(k_inflate_lz<W>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+		attr_done = true;
+	}
+	int per_sm = 0;
+	CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_inflate_lz<W>, 256, smem));
+	if (per_sm < 1) {
+		snprintf(g_err, sizeof(g_err), "k_inflate_lz<%d> does not fit an SM", W);
+		return OTZ_ERR_CUDA;
+	}
+	const uint32_t grid = std::max(1u, std::min((uint32_t)(c->sm_count * per_sm), (p->n_inflate + 7) / 8));
+	k_inflate_lz<W><<<grid, 256, smem, st>>>(d_out, p->d_ents, p->d_inflate_list, p->n_inflate, p->d_counter + 48, c->d_tok_cache, p->d_tok_ofs,
+		p->d_tokres, p->d_status, p->d_produced);
+	c->launches++;
+	CK(cudaGetLastError());
+	return OTZ_SUCCESS;
+}
+
+// Two-phase inflate: lane-per-stream entropy decode into tokens, warp-per-stream LZ77 execution, then k_inflate over
+// whatever phase A declined (d_counter + 52 counts those entries).
+static int dispatch_inflate2(otz_ctx *c, otz_plan *p, const uint8_t *d_archive, uint8_t *d_out) {
+	cudaStream_t s = c->stream;
+	static bool attr_done = false;
+	if (!attr_done) {
+		CK(cudaFuncSetAttribute(k_inflate_tok, cudaFuncAttributeMaxDynamicSharedMemorySize, I2_SMEM_BYTES));
+		attr_done = true;
+	}
+	int per_sm = 0;
+	CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_inflate_tok, 32, I2_SMEM_BYTES));
+	if (per_sm < 1) {
+		snprintf(g_err, sizeof(g_err), "k_inflate_tok does not fit an SM (%d bytes of shared memory)", I2_SMEM_BYTES);
+		return OTZ_ERR_CUDA;
+	}
+	// few streams are spread over all resident warps (a lock-step step costs the same for 1 or 28 live lanes)
+	const uint32_t grid = std::max(1u, std::min((uint32_t)(c->sm_count * per_sm), p->n_inflate));
+	const uint32_t lanes = std::min<uint32_t>(I2_LANES, (p->n_inflate + grid - 1) / grid);
+	k_inflate_tok<<<grid, 32, I2_SMEM_BYTES, s>>>(d_archive, p->d_ents, p->d_est, p->d_status, p->d_inflate_list, p->n_inflate, p->d_counter,
+		c->d_tok_cache, p->d_tok_ofs, p->d_tokres, p->d_fb_list, p->d_counter + 52, lanes);
+	c->launches++;
+	CK(cudaGetLastError());
+	int rc;
+	switch (c->lz_ring) {
+	case 4096: rc = launch_lz<4096>(c, p, d_out, s); break;
+	case 16384: rc = launch_lz<16384>(c, p, d_out, s); break;
+	default: rc = launch_lz<8192>(c, p, d_out, s); break;
+	}
+	if (rc) {
+		return rc;
+	}
+	return launch_inflate_cfg(c, p, d_archive, d_out, 32, 4096, 0, p->n_inflate, 1, s, p->d_fb_list, p->d_counter + 52);
+}
+
 static int dispatch_inflate(otz_ctx *c, otz_plan *p, const uint8_t *d_archive, uint8_t *d_out) {
+	if (!c->inflate_mode && !c->inflate_tile && !c->inflate_ring) {
+		// token scratch: grow-only, shared by the runs of this context (they are ordered on its stream)
+		if (p->tok_bytes + 64 > c->tok_cache_bytes) {
+			CK(cudaStreamSynchronize(c->stream));
+			cudaFree(c->d_tok_cache);
+			c->d_tok_cache = nullptr;
+			c->tok_cache_bytes = 0;
+			if (cudaMalloc(&c->d_tok_cache, p->tok_bytes + 64) == cudaSuccess) {
+				c->tok_cache_bytes = p->tok_bytes + 64;
+			} else {
+				cudaGetLastError();   // not enough memory for the token scratch: the one-kernel decoder needs none
+			}
+		}
+		if (c->d_tok_cache) {
+			return dispatch_inflate2(c, p, d_archive, d_out);
+		}
+	}
 	if (c->inflate_tile || c->inflate_ring) {   // explicit configuration (tests, sweeps): one kernel for everything
 		const int g = c->inflate_tile ? c->inflate_tile : 32;
 		const int w = c->inflate_ring ? c->inflate_ring : 2048;
@@ -620,9 +728,12 @@ extern "C" int otz_extract_results(otz_ctx *c, otz_plan *p, uint32_t *crc, int32
 	if (p->n && status) {
 		CK(cudaMemcpyAsync(status, p->d_status, p->n * 4ull, cudaMemcpyDeviceToHost, c->stream));
 	}
+	CK(cudaMemcpyAsync(&c->last_fallbacks, p->d_counter + 52, 4, cudaMemcpyDeviceToHost, c->stream));
 	CK(cudaStreamSynchronize(c->stream));
 	return OTZ_SUCCESS;
 }
+
+extern "C" uint32_t otz_inflate_fallbacks(otz_ctx *c) { return c ? c->last_fallbacks : 0; }
 
 extern "C" int otz_extract_produced(otz_ctx *c, otz_plan *p, uint32_t *produced) {
 	if (!c || !p || !produced) {

@@ -77,6 +77,8 @@ class Lib:
         L.otz_extract_results.argtypes = [vp, vp, vp, vp]
         L.otz_extract_host.argtypes = [vp, vp, u64, vp, C.c_uint32, C.POINTER(OtzOpts), vp, u64, vp, vp]
         L.otz_status_accepts.argtypes = [C.c_int32, C.c_int, C.c_int]
+        L.otz_inflate_fallbacks.argtypes = [vp]
+        L.otz_inflate_fallbacks.restype = C.c_uint32
         L.otz_deflate_plan.argtypes = [vp, vp, vp, vp, C.c_uint32, C.POINTER(vp)]
         L.otz_deflate_destroy.argtypes = [vp, vp]
         L.otz_deflate_destroy.restype = None

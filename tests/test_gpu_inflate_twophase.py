@@ -1,0 +1,132 @@
+"""Two-phase inflate (k_inflate_tok lane-per-stream entropy decode + k_inflate_lz warp-per-stream LZ77 execution,
+k_inflate as the fallback for declined streams) against the oracle and against the one-kernel decoder."""
+import os
+import random
+import zlib
+
+import numpy as np
+import pytest
+
+from otezip_b200 import Ctx, synth
+from otezip_b200.native import parse_central, default_opts
+from tests import cases
+
+pytestmark = pytest.mark.gpu
+
+
+def _ctx(mode=None, ring=None):
+    env = {}
+    if mode:
+        env["OTZ_INFLATE_MODE"] = mode
+    if ring:
+        env["OTZ_LZ_RING"] = str(ring)
+    os.environ.update(env)
+    try:
+        return Ctx(0)
+    finally:
+        for k in env:
+            del os.environ[k]
+
+
+def _check(img, oracle, c, expect_fallbacks=None):
+    tab = parse_central(img)
+    out, crc, st = c.extract_host(img, tab, default_opts())
+    fb = int(c.L.otz_inflate_fallbacks(c.h))
+    rc, oents = oracle.load_central(img)
+    ost, ocrc, oout, oofs = oracle.extract_all(img, oents)
+    for i in range(len(tab)):
+        ok = (int(st[i]) & 0xFF) == 0 and not (int(st[i]) & 0x300)
+        assert ok == (ost[i] == 0), (i, hex(int(st[i])), int(ost[i]))
+        if ok:
+            n = int(tab["uncomp_size"][i])
+            a = out[int(tab["out_ofs"][i]):int(tab["out_ofs"][i]) + n]
+            b = oout[int(oofs[i]):int(oofs[i]) + n]
+            assert np.array_equal(a, b), (i, n, int(np.argmax(a != b)) if n else -1)
+            assert int(crc[i]) == int(ocrc[i]), i
+    if expect_fallbacks is not None:
+        assert fb == expect_fallbacks, fb
+    return fb, st, out
+
+
+def _shapes():
+    rnd = random.Random(5)
+    ms = []
+    blob = synth.random_bytes(30000, 5)
+    ms.append(synth.member("far", blob + blob + blob[:5000], 8, level=9))                      # 30000-byte distances
+    ms.append(synth.member("runs", b"ab" * 40000 + b"x" * 70000 + bytes(range(256)) * 100, 8, level=9))   # overlapping copies
+    ms.append(synth.member("big", synth.jsonlog_text(3 << 20, 77), 8, level=6))               # many blocks
+    ms.append(synth.member("lits", synth.random_bytes(70000, 9), 8, strategy=zlib.Z_HUFFMAN_ONLY))  # literal runs > 511
+    ms.append(synth.member("fixed", synth.jsonlog_text(50000, 3), 8, strategy=zlib.Z_FIXED))
+    ms.append(synth.member("rle", b"".join(bytes([rnd.randrange(256)]) * rnd.randint(1, 600) for _ in range(500)), 8, strategy=zlib.Z_RLE))
+    ms.append(synth.member("flush", synth.jsonlog_text(300000, 4), 8, full_flush_every=4096))   # empty stored blocks mid-stream
+    ms.append(synth.member("empty", b"", 8))
+    ms.append(synth.member("one", b"x", 8))
+    ms.append(synth.member("stored", synth.random_bytes(5000, 1), 8, level=0))                 # stored payload -> fallback
+    for i in range(40):
+        ms.append(synth.member("j%d" % i, synth.jsonlog_text(rnd.randint(1, 90000), 100 + i), 8, level=rnd.choice([1, 6, 9]),
+                               ref_safe=bool(i & 1)))
+    # binary-like data: long literal/length codes -> second-level tables
+    for i in range(8):
+        d = bytes((rnd.randrange(256) if rnd.random() < 0.7 else 0) for _ in range(rnd.randint(3000, 60000)))
+        ms.append(synth.member("b%d" % i, d, 8))
+    return ms
+
+
+def test_shapes_match_oracle(oracle):
+    img = synth.build_zip(_shapes())
+    c = _ctx()
+    fb, st, out = _check(img, oracle, c)
+    c.close()
+    assert fb <= 3, fb   # only the stored-payload stream (and nothing structural) may take the fallback
+
+
+@pytest.mark.parametrize("ring", [4096, 8192, 16384])
+def test_rings(ring, oracle):
+    img = synth.build_zip(_shapes())
+    c = _ctx(ring=ring)
+    _check(img, oracle, c)
+    c.close()
+
+
+def test_mixed_archive_with_errors(oracle):
+    # tiny entries (many trip the reference's end-of-block rule), every strategy/level, stored blocks
+    ms = cases.mixed_archive(seed=33, n_tiny=300, n_mid=60, n_z=5, n_s=5)
+    img = synth.build_zip(ms)
+    c = _ctx()
+    _check(img, oracle, c)
+    c.close()
+
+
+def test_same_status_words_as_one_kernel_decoder():
+    ms = cases.mixed_archive(seed=34, n_tiny=200, n_mid=40, n_z=0, n_s=0)
+    img = bytearray(synth.build_zip(ms))
+    tab = parse_central(bytes(img))
+    # corrupt a few payloads: both decoders must report the same status words and produce the same bytes where accepted
+    rnd = random.Random(3)
+    for _ in range(25):
+        i = rnd.randrange(len(tab))
+        if int(tab["comp_size"][i]) > 8:
+            lfh = int(tab["lfh_ofs"][i])
+            img[lfh + 30 + len(ms[i].name) + rnd.randrange(int(tab["comp_size"][i]))] ^= 1 << rnd.randrange(8)
+    img = bytes(img)
+    a = _ctx()
+    out_a, crc_a, st_a = a.extract_host(img, tab, default_opts())
+    a.close()
+    b = _ctx(mode="legacy")
+    out_b, crc_b, st_b = b.extract_host(img, tab, default_opts())
+    b.close()
+    assert np.array_equal(st_a, st_b)
+    for i in range(len(tab)):
+        if (int(st_a[i]) & 0xFF) == 0:
+            n, o = int(tab["uncomp_size"][i]), int(tab["out_ofs"][i])
+            assert np.array_equal(out_a[o:o + n], out_b[o:o + n]), i
+            assert int(crc_a[i]) == int(crc_b[i])
+
+
+def test_many_uniform_streams_no_fallback(oracle):
+    pool = synth.TextPool(4 << 20, 11)
+    ms = [synth.member("e%d" % i, pool.take(65536), 8) for i in range(600)]
+    img = synth.build_zip(ms)
+    c = _ctx()
+    _check(img, oracle, c, expect_fallbacks=0)
+    c.close()
