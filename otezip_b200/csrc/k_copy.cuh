@@ -28,13 +28,27 @@ __device__ __forceinline__ void tile_copy(uint8_t *__restrict__ dst, const uint8
 		const uint4 *s4 = reinterpret_cast<const uint4 *>(src);
 		uint4 *d4 = reinterpret_cast<uint4 *>(dst);
 		uint64_t v = lane;
-		for (; v + 3 * G < nv; v += 4 * G) {
-			uint4 a = ld_stream16(s4 + v), b = ld_stream16(s4 + v + G), c = ld_stream16(s4 + v + 2 * G),
-			      d = ld_stream16(s4 + v + 3 * G);
+		// software pipeline: the four vectors of trip t+1 are requested before those of trip t are stored,
+		// so a lane keeps 64-128 bytes in flight (a warp 2-4 KiB) without more resident warps
+		if (v + 3 * G < nv) {
+			uint4 a = ld_stream16(s4 + v), b = ld_stream16(s4 + v + G), c = ld_stream16(s4 + v + 2 * G), d = ld_stream16(s4 + v + 3 * G);
+			for (; v + 7 * G < nv; v += 4 * G) {
+				const uint4 a2 = ld_stream16(s4 + v + 4 * G), b2 = ld_stream16(s4 + v + 5 * G), c2 = ld_stream16(s4 + v + 6 * G),
+				            d2 = ld_stream16(s4 + v + 7 * G);
+				d4[v] = a;
+				d4[v + G] = b;
+				d4[v + 2 * G] = c;
+				d4[v + 3 * G] = d;
+				a = a2;
+				b = b2;
+				c = c2;
+				d = d2;
+			}
 			d4[v] = a;
 			d4[v + G] = b;
 			d4[v + 2 * G] = c;
 			d4[v + 3 * G] = d;
+			v += 4 * G;
 		}
 		for (; v < nv; v += G) {
 			d4[v] = ld_stream16(s4 + v);
@@ -44,8 +58,8 @@ __device__ __forceinline__ void tile_copy(uint8_t *__restrict__ dst, const uint8
 		const uint32_t *w = reinterpret_cast<const uint32_t *>(sa & ~3ull);
 		uint4 *d4 = reinterpret_cast<uint4 *>(dst);
 		uint64_t v = lane;
-		// 4 vectors per lane per trip: 20 independent word loads in flight before the first store
-		for (; v + 3 * G < nv; v += 4 * G) {
+		// 4 vectors per lane per trip (20 independent word loads), the next trip's loads in flight before this trip's stores
+		if (v + 3 * G < nv) {
 			uint32_t a[4][5];
 #pragma unroll
 			for (int k = 0; k < 4; k++) {
@@ -56,6 +70,31 @@ __device__ __forceinline__ void tile_copy(uint8_t *__restrict__ dst, const uint8
 				}
 				a[k][4] = sh ? __ldg(p + 4) : 0u;
 			}
+			for (; v + 7 * G < nv; v += 4 * G) {
+				uint32_t n[4][5];
+#pragma unroll
+				for (int k = 0; k < 4; k++) {
+					const uint32_t *p = w + 4 * (v + (k + 4) * G);
+#pragma unroll
+					for (int i = 0; i < 4; i++) {
+						n[k][i] = __ldg(p + i);
+					}
+					n[k][4] = sh ? __ldg(p + 4) : 0u;
+				}
+#pragma unroll
+				for (int k = 0; k < 4; k++) {
+					uint4 o;
+					o.x = __funnelshift_r(a[k][0], a[k][1], sh);
+					o.y = __funnelshift_r(a[k][1], a[k][2], sh);
+					o.z = __funnelshift_r(a[k][2], a[k][3], sh);
+					o.w = __funnelshift_r(a[k][3], a[k][4], sh);
+					d4[v + k * G] = o;
+#pragma unroll
+					for (int i = 0; i < 5; i++) {
+						a[k][i] = n[k][i];
+					}
+				}
+			}
 #pragma unroll
 			for (int k = 0; k < 4; k++) {
 				uint4 o;
@@ -65,6 +104,7 @@ __device__ __forceinline__ void tile_copy(uint8_t *__restrict__ dst, const uint8
 				o.w = __funnelshift_r(a[k][3], a[k][4], sh);
 				d4[v + k * G] = o;
 			}
+			v += 4 * G;
 		}
 		for (; v < nv; v += G) {
 			const uint32_t *p = w + 4 * v;

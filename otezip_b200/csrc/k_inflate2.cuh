@@ -768,13 +768,30 @@ __global__ void __launch_bounds__(32) k_inflate_tok(const uint8_t *__restrict__ 
 // phase B.  One warp per committed stream; W = bytes of shared-memory ring per warp.  Ring index of output
 // byte p is (p + mis) & (W-1) with mis = dst & 15 (as OutRing in k_inflate.cuh), so ring vectors line up with
 // 16-byte aligned global vectors.
+//
+// The sequence records are executed in batches of up to 32 (one per lane), software-pipelined over two batches:
+// while batch k runs, batch k+1 has already been scanned (warp prefix sums give every record its literal and
+// output positions), its match descriptors sit in shared memory, the first literals of every run are in
+// registers and — the point of the exercise — the sources of its FAR matches (those that left the ring; they
+// were flushed to HBM before batch k started, see SPAN_MAX) are on their way into a staging buffer as 16-byte
+// cp.async copies.  Executing a batch therefore touches shared memory only.
+#define I2_STAGE 1024   // staging bytes per batch (64 vectors); far matches beyond it are fetched directly
+
 template <int W>
 struct I2Ring {
 	static constexpr uint32_t MASK = W - 1;
 	static constexpr uint32_t SEG = 512;
-	// output bytes per batch.  W >= SPAN_MAX + SEG + 770 guarantees that a match source outside the ring window
-	// of a batch has been flushed to HBM before the batch starts.
+	// output bytes per batch.  W >= 2 * SPAN_MAX + SEG + 258 guarantees that a far source of batch k+1 has been
+	// flushed to HBM before batch k starts (when its copy is issued).
 	static constexpr uint32_t SPAN_MAX = W >= 8192 ? 2048u : 1024u;
+};
+
+template <int W>
+struct __align__(16) I2LzSmem {
+	uint8_t ring[W];
+	uint8_t stage[2][I2_STAGE];
+	uint2 far_l[2][32];    // {destination (linear), distance-1 | length << 15 | staging vector << 24 (127 = fetch directly)}
+	uint2 near_l[2][32];   // {ring index of the destination | length << 16, ring index of the source | distance << 16}
 };
 
 // write ring[a, b) (linear positions) to HBM; whole warp, ring contents visible (caller synced)
@@ -791,6 +808,7 @@ __device__ __forceinline__ void i2_flush_range(uint8_t *gbase, const uint8_t *ri
 	for (uint32_t x = a + lane; x < a16; x += 32) {
 		gbase[x] = ring[x & MASK];
 	}
+#pragma unroll 1
 	for (uint32_t x = a16 + 16u * lane; x < b16; x += 512u) {
 		*reinterpret_cast<uint4 *>(gbase + x) = *reinterpret_cast<const uint4 *>(ring + (x & MASK));
 	}
@@ -799,7 +817,7 @@ __device__ __forceinline__ void i2_flush_range(uint8_t *gbase, const uint8_t *ri
 	}
 }
 
-// overlapping LZ77 copy (distance < length): periodic extension of the last `dd` bytes, whole warp
+// overlapping LZ77 copy (distance < length): periodic extension of the last `dd` bytes, whole warp (dec:521-533)
 template <int W>
 __device__ __noinline__ void i2_copy_periodic(uint8_t *rb, uint32_t dq, uint32_t sq, uint32_t dd, uint32_t len, uint32_t lane) {
 	constexpr uint32_t MASK = W - 1;
@@ -812,17 +830,112 @@ __device__ __noinline__ void i2_copy_periodic(uint8_t *rb, uint32_t dq, uint32_t
 	}
 }
 
+// what the scan of one batch leaves in registers for its execution
+struct I2Batch {
+	uint32_t ntake;     // records in the batch (0 = none left)
+	uint32_t tot_l;     // literals it consumes
+	uint32_t q_end;     // linear output position behind it
+	uint32_t n_far, n_near;
+	uint32_t lr;        // this lane's record: literal run,
+	uint32_t my_lit;    //   its first literal,
+	uint32_t my_out;    //   its linear output position
+	uint32_t lit4;      //   and its first four literal bytes
+};
+
+// scan records [b, b + 32) (this lane holds record b + lane in `rec`), write the match descriptors of the batch into
+// list buffer `buf` and start the copies of its far sources into staging buffer `buf`.
 template <int W>
-__global__ void __launch_bounds__(256) k_inflate_lz(uint8_t *__restrict__ out, const otz_entry *__restrict__ ents, const uint32_t *__restrict__ list,
+__device__ __forceinline__ I2Batch i2_scan_batch(I2LzSmem<W> &S, int buf, uint32_t rec, uint32_t b, uint32_t nseq, uint32_t q, uint32_t lp,
+	const uint8_t *__restrict__ lits, const uint8_t *gbase, uint32_t lane) {
+	constexpr uint32_t MASK = I2Ring<W>::MASK, SPAN_MAX = I2Ring<W>::SPAN_MAX;
+	const uint32_t lt_mask = (1u << lane) - 1u;
+	I2Batch B;
+	const bool have = b + lane < nseq;
+	const uint32_t lr = have ? rec & 511u : 0u;
+	const uint32_t ml = (have && lr != I2_SEQ_ESC) ? ((rec >> 9) & 255u) + 3u : 0u;
+	const uint32_t dist = (rec >> 17) + 1u;
+	uint32_t lsum = lr, osum = lr + ml;
+#pragma unroll
+	for (int d = 1; d < 32; d <<= 1) {
+		const uint32_t a = __shfl_up_sync(0xFFFFFFFFu, lsum, d), c = __shfl_up_sync(0xFFFFFFFFu, osum, d);
+		if ((int)lane >= d) {
+			lsum += a;
+			osum += c;
+		}
+	}
+	// the longest prefix of the batch whose output fits SPAN_MAX (one record is at most 769 bytes)
+	const uint32_t fit = __ballot_sync(0xFFFFFFFFu, have && osum <= SPAN_MAX);
+	B.ntake = __popc(fit);   // osum is monotonic, so `fit` is a prefix mask
+	const uint32_t last = B.ntake ? B.ntake - 1u : 0u;
+	B.tot_l = B.ntake ? __shfl_sync(0xFFFFFFFFu, lsum, last) : 0u;
+	const uint32_t tot_o = B.ntake ? __shfl_sync(0xFFFFFFFFu, osum, last) : 0u;
+	const bool mine = lane < B.ntake;
+	B.lr = mine ? lr : 0u;
+	B.my_lit = lp + lsum - lr;
+	B.my_out = q + osum - lr - ml;
+	B.q_end = q + tot_o;
+	// the first literals of the run travel in a register
+	B.lit4 = 0;
+#pragma unroll
+	for (int t = 0; t < 4; t++) {
+		if ((uint32_t)t < B.lr) {
+			B.lit4 |= (uint32_t)lits[B.my_lit + t] << (8 * t);
+		}
+	}
+	// far: the source lies below the ring window [q_end - W, q_end) of this batch
+	const uint32_t mq = B.my_out + lr;   // match destination
+	const bool is_match = mine && ml != 0u;
+	const bool is_far = is_match && dist > (uint32_t)W - (B.q_end - mq);
+	const uint32_t far_m = __ballot_sync(0xFFFFFFFFu, is_far);
+	const uint32_t near_m = __ballot_sync(0xFFFFFFFFu, is_match && !is_far);
+	B.n_far = __popc(far_m);
+	B.n_near = __popc(near_m);
+	if (is_match && !is_far) {
+		S.near_l[buf][__popc(near_m & lt_mask)] = make_uint2((mq & MASK) | (ml << 16), ((mq - dist) & MASK) | (dist << 16));
+	}
+	if (far_m) {
+		// staging vectors per far match (the source is copied as whole 16-byte vectors)
+		const uint32_t soff = (mq - dist) & 15u;
+		const uint32_t nch = is_far ? (soff + ml + 15u) >> 4 : 0u;
+		uint32_t incl = nch;
+#pragma unroll
+		for (int d = 1; d < 32; d <<= 1) {
+			const uint32_t a = __shfl_up_sync(0xFFFFFFFFu, incl, d);
+			if ((int)lane >= d) {
+				incl += a;
+			}
+		}
+		if (is_far) {
+			const uint32_t cst = incl <= I2_STAGE / 16u ? incl - nch : 127u;
+			S.far_l[buf][__popc(far_m & lt_mask)] = make_uint2(mq, (dist - 1u) | (ml << 15) | (cst << 24));
+		}
+		__syncwarp();
+		for (uint32_t f = 0; f < B.n_far; f++) {
+			const uint2 d = S.far_l[buf][f];
+			const uint32_t cst = d.y >> 24;
+			if (cst != 127u) {
+				const uint32_t src = d.x - (d.y & 0x7FFFu) - 1u, len = (d.y >> 15) & 511u;
+				const uint32_t n = ((src & 15u) + len + 15u) >> 4;
+				if (lane < n) {
+					const uint32_t sa = (uint32_t)__cvta_generic_to_shared(&S.stage[buf][16u * (cst + lane)]);
+					asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(sa), "l"(gbase + (src & ~15u) + 16u * lane) : "memory");
+				}
+			}
+		}
+	}
+	asm volatile("cp.async.commit_group;" ::: "memory");
+	return B;
+}
+
+template <int W>
+__global__ void __launch_bounds__(128) k_inflate_lz(uint8_t *__restrict__ out, const otz_entry *__restrict__ ents, const uint32_t *__restrict__ list,
 	uint32_t n_list, uint32_t *__restrict__ work_counter, const uint8_t *__restrict__ scratch, const uint64_t *__restrict__ tok_ofs,
 	const I2TokRes *__restrict__ tokres, int32_t *__restrict__ status, uint32_t *__restrict__ produced_out) {
 	extern __shared__ __align__(16) uint8_t smem_raw[];
 	constexpr uint32_t MASK = I2Ring<W>::MASK, SEG = I2Ring<W>::SEG, SPAN_MAX = I2Ring<W>::SPAN_MAX;
 	const uint32_t lane = threadIdx.x & 31u;
-	uint8_t *const rb = smem_raw + (threadIdx.x >> 5) * (W + 512);
-	uint2 *const far_l = reinterpret_cast<uint2 *>(rb + W);
-	uint2 *const near_l = far_l + 32;
-	const uint32_t lt_mask = (1u << lane) - 1u;
+	I2LzSmem<W> &S = reinterpret_cast<I2LzSmem<W> *>(smem_raw)[threadIdx.x >> 5];
+	uint8_t *const rb = S.ring;
 	for (;;) {
 		uint32_t k = 0;
 		if (lane == 0) {
@@ -843,109 +956,88 @@ __global__ void __launch_bounds__(256) k_inflate_lz(uint8_t *__restrict__ out, c
 		uint8_t *const gbase = dstp - mis;
 		const uint8_t *const lits = scratch + tok_ofs[k];
 		const uint32_t *const seq_end = reinterpret_cast<const uint32_t *>(scratch + tok_ofs[k + 1]);
+		const uint32_t nseq = tr.nseq;
 		uint32_t q = mis, qf = mis;   // linear write position / position up to which HBM holds the data
-		uint32_t lp = 0;              // literals consumed
+		uint32_t lp = 0, b = 0;       // literals / records consumed
 		__syncwarp();
-		for (uint32_t b = 0; b < tr.nseq;) {
-			const uint32_t i = b + lane;
-			const bool have = i < tr.nseq;
-			const uint32_t rec = have ? __ldcs(seq_end - 1 - i) : 0u;
-			const uint32_t lr = rec & 511u;
-			const uint32_t ml = (have && lr != I2_SEQ_ESC) ? ((rec >> 9) & 255u) + 3u : 0u;
-			const uint32_t dist = (rec >> 17) + 1u;
-			uint32_t lsum = lr, osum = lr + ml;
-#pragma unroll
-			for (int d = 1; d < 32; d <<= 1) {
-				const uint32_t a = __shfl_up_sync(0xFFFFFFFFu, lsum, d), c = __shfl_up_sync(0xFFFFFFFFu, osum, d);
-				if ((int)lane >= d) {
-					lsum += a;
-					osum += c;
-				}
+		// records b + lane (recA) and b + 32 + lane (recB)
+		uint32_t recA = lane < nseq ? __ldcs(seq_end - 1 - lane) : 0u;
+		uint32_t recB = 32u + lane < nseq ? __ldcs(seq_end - 33 - lane) : 0u;
+		int buf = 0;
+		I2Batch cur = i2_scan_batch<W>(S, 0, recA, 0u, nseq, q, lp, lits, gbase, lane);
+		while (cur.ntake) {
+			// ---- scan batch k+1 and start its far copies
+			const uint32_t b2 = b + cur.ntake;
+			{
+				const uint32_t j = cur.ntake + lane;
+				const uint32_t fromA = __shfl_sync(0xFFFFFFFFu, recA, j & 31u), fromB = __shfl_sync(0xFFFFFFFFu, recB, j & 31u);
+				recA = j < 32u ? fromA : fromB;
+				recB = b2 + 32u + lane < nseq ? __ldcs(seq_end - 33 - (b2 + lane)) : 0u;
 			}
-			// take the longest prefix of the batch whose output fits SPAN_MAX (one record is at most 769 bytes)
-			const uint32_t fit = __ballot_sync(0xFFFFFFFFu, have && osum <= SPAN_MAX);
-			const uint32_t ntake = __popc(fit);   // osum is monotonic, so `fit` is a prefix mask
-			const bool mine = lane < ntake;
-			const uint32_t tot_l = __shfl_sync(0xFFFFFFFFu, lsum, ntake - 1), tot_o = __shfl_sync(0xFFFFFFFFu, osum, ntake - 1);
-			const uint32_t my_lit = lp + lsum - lr;         // first literal of this record
-			const uint32_t my_out = q + osum - lr - ml;     // linear output position of this record
-			const uint32_t q_end = q + tot_o;
-			// literal runs, all records at once
-			if (mine) {
-				for (uint32_t t = 0; t < lr; t++) {
-					rb[(my_out + t) & MASK] = lits[my_lit + t];
-				}
-			}
-			// Match descriptors {destination, distance-1 | length << 15}, compacted into two per-warp lists.
-			// far: the source lies below the ring window [q_end - W, q_end): flushed to HBM before this batch
-			// started and independent of anything the batch produces.  near: everything else, in stream order.
-			const uint32_t mq = my_out + lr;   // match destination
-			const bool is_match = mine && ml != 0u;
-			const bool is_far = is_match && dist > (uint32_t)W - (q_end - mq);
-			const uint32_t far_m = __ballot_sync(0xFFFFFFFFu, is_far);
-			const uint32_t near_m = __ballot_sync(0xFFFFFFFFu, is_match && !is_far);
-			const bool far_long = __any_sync(0xFFFFFFFFu, is_far && ml > 32u);
-			if (is_match) {
-				const uint2 dsc = make_uint2(mq, (dist - 1u) | (ml << 15));
-				if (is_far) {
-					far_l[__popc(far_m & lt_mask)] = dsc;
-				} else {
-					near_l[__popc(near_m & lt_mask)] = dsc;
-				}
-			}
+			const I2Batch nxt = i2_scan_batch<W>(S, buf ^ 1, recA, b2, nseq, cur.q_end, lp + cur.tot_l, lits, gbase, lane);
+			// ---- execute batch k: its far sources have landed in stage[buf]
+			asm volatile("cp.async.wait_group 1;" ::: "memory");
 			__syncwarp();
-			const uint32_t n_far = __popc(far_m), n_near = __popc(near_m);
-			// far: four matches per trip, 32-byte slices, all loads of a slice in flight before the first store
-			for (uint32_t f = 0; f < n_far; f += 4) {
-				uint32_t dq[4], ln[4];
-				const uint8_t *sp[4];
-				uint32_t maxl = 0;
-#pragma unroll
-				for (int u = 0; u < 4; u++) {
-					const uint2 dsc = far_l[(f + u) & 31u];
-					dq[u] = dsc.x + lane;
-					ln[u] = f + u < n_far ? dsc.y >> 15 : 0u;
-					sp[u] = gbase + dsc.x - (dsc.y & 0x7FFFu) - 1u + lane;
-					maxl = max(maxl, ln[u]);
+			{
+				// literal runs, all records at once
+				const uint32_t n4 = min(cur.lr, 4u);
+				for (uint32_t t = 0; t < n4; t++) {
+					rb[(cur.my_out + t) & MASK] = (uint8_t)(cur.lit4 >> (8u * t));
 				}
-				for (uint32_t off = 0; off < maxl; off += 32) {
-					uint32_t v[4];
-#pragma unroll
-					for (int u = 0; u < 4; u++) {
-						v[u] = 0;
-						if (off + lane < ln[u]) {
-							v[u] = __ldcg(sp[u] + off);
+#pragma unroll 1
+				for (uint32_t t = 4; t < cur.lr; t++) {
+					rb[(cur.my_out + t) & MASK] = lits[cur.my_lit + t];
+				}
+			}
+			uint2 dn = S.far_l[buf][0];
+#pragma unroll 1
+			for (uint32_t f = 0; f < cur.n_far; f++) {
+				const uint2 d = dn;
+				dn = S.far_l[buf][(f + 1u) & 31u];   // next descriptor in flight while this match is copied
+				const uint32_t cst = d.y >> 24, len = (d.y >> 15) & 511u, src = d.x - (d.y & 0x7FFFu) - 1u;
+				if (cst != 127u) {
+					const uint8_t *sp = &S.stage[buf][16u * cst + (src & 15u)];
+					if (lane < len) {
+						rb[(d.x + lane) & MASK] = sp[lane];
+					}
+					if (len > 32u) {
+#pragma unroll 1
+						for (uint32_t x = lane + 32u; x < len; x += 32) {
+							rb[(d.x + x) & MASK] = sp[x];
 						}
 					}
-#pragma unroll
-					for (int u = 0; u < 4; u++) {
-						if (off + lane < ln[u]) {
-							rb[(dq[u] + off) & MASK] = (uint8_t)v[u];
-						}
+				} else {
+#pragma unroll 1
+					for (uint32_t x = lane; x < len; x += 32) {
+						rb[(d.x + x) & MASK] = __ldcg(gbase + src + x);
 					}
 				}
 			}
-			(void)far_long;
-			// the rest in stream order, ring -> ring (dec:521-533: an overlapping copy is a periodic extension)
-			for (uint32_t f = 0; f < n_near; f++) {
-				const uint2 dsc = near_l[f];
-				const uint32_t dq = dsc.x, dd = (dsc.y & 0x7FFFu) + 1u, len = dsc.y >> 15;
-				const uint32_t sq = dq - dd;
+			// the rest in stream order, ring -> ring
+			dn = S.near_l[buf][0];
+#pragma unroll 1
+			for (uint32_t f = 0; f < cur.n_near; f++) {
+				const uint2 d = dn;
+				dn = S.near_l[buf][(f + 1u) & 31u];
+				const uint32_t dqm = d.x & 0xFFFFu, len = d.x >> 16, sqm = d.y & 0xFFFFu, dd = d.y >> 16;
 				__syncwarp();   // earlier ring stores are visible to the loads below
 				if (dd >= len) {
 					if (lane < len) {
-						rb[(dq + lane) & MASK] = rb[(sq + lane) & MASK];
+						rb[(dqm + lane) & MASK] = rb[(sqm + lane) & MASK];
 					}
-					for (uint32_t x = lane + 32u; x < len; x += 32) {
-						rb[(dq + x) & MASK] = rb[(sq + x) & MASK];
+					if (len > 32u) {
+#pragma unroll 1
+						for (uint32_t x = lane + 32u; x < len; x += 32) {
+							rb[(dqm + x) & MASK] = rb[(sqm + x) & MASK];
+						}
 					}
 				} else {
-					i2_copy_periodic<W>(rb, dq, sq, dd, len, lane);
+					i2_copy_periodic<W>(rb, dqm, sqm, dd, len, lane);
 				}
 			}
-			b += ntake;
-			lp += tot_l;
-			q = q_end;
+			b = b2;
+			lp += cur.tot_l;
+			q = cur.q_end;
 			__syncwarp();
 			const uint32_t qa = q & ~(SEG - 1u);
 			if (qa > qf) {
@@ -953,7 +1045,10 @@ __global__ void __launch_bounds__(256) k_inflate_lz(uint8_t *__restrict__ out, c
 				qf = qa;
 				__syncwarp();
 			}
+			cur = nxt;
+			buf ^= 1;
 		}
+		asm volatile("cp.async.wait_group 0;" ::: "memory");
 		// literals after the last match
 		while (lp < tr.nlit) {
 			const uint32_t n = min(tr.nlit - lp, SPAN_MAX);

@@ -187,7 +187,7 @@ extern "C" int otz_ctx_create(int device, otz_ctx **out) {
 	t = getenv("OTZ_INFLATE_MODE");
 	c->inflate_mode = (t && !strcmp(t, "legacy")) ? 1 : 0;
 	t = getenv("OTZ_LZ_RING");
-	c->lz_ring = t ? atoi(t) : 8192;
+	c->lz_ring = t ? atoi(t) : 4096;
 	*out = c;
 	return OTZ_SUCCESS;
 }
@@ -534,21 +534,22 @@ static int launch_inflate_cfg(otz_ctx *c, otz_plan *p, const uint8_t *d_archive,
 // share the machine; small entries get the big ring only when there are too few of them to fill the SMs.
 template <int W>
 static int launch_lz(otz_ctx *c, otz_plan *p, uint8_t *d_out, cudaStream_t st) {
-	const size_t smem = 8 * ((size_t)W + 512);
+	const int warps = 4;
+	const size_t smem = warps * sizeof(I2LzSmem<W>);
 	static bool attr_done = false;
 	if (!attr_done) {
 		CK(cudaFuncSetAttribute(k_inflate_lz<W>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
 		attr_done = true;
 	}
 	int per_sm = 0;
-	CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_inflate_lz<W>, 256, smem));
+	CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_inflate_lz<W>, 32 * warps, smem));
 	if (per_sm < 1) {
 		snprintf(g_err, sizeof(g_err), "k_inflate_lz<%d> does not fit an SM", W);
 		return OTZ_ERR_CUDA;
 	}
-	const uint32_t grid = std::max(1u, std::min((uint32_t)(c->sm_count * per_sm), (p->n_inflate + 7) / 8));
-	k_inflate_lz<W><<<grid, 256, smem, st>>>(d_out, p->d_ents, p->d_inflate_list, p->n_inflate, p->d_counter + 48, c->d_tok_cache, p->d_tok_ofs,
-		p->d_tokres, p->d_status, p->d_produced);
+	const uint32_t grid = std::max(1u, std::min((uint32_t)(c->sm_count * per_sm), (p->n_inflate + warps - 1) / warps));
+	k_inflate_lz<W><<<grid, 32 * warps, smem, st>>>(d_out, p->d_ents, p->d_inflate_list, p->n_inflate, p->d_counter + 48, c->d_tok_cache,
+		p->d_tok_ofs, p->d_tokres, p->d_status, p->d_produced);
 	c->launches++;
 	CK(cudaGetLastError());
 	return OTZ_SUCCESS;
@@ -578,9 +579,9 @@ static int dispatch_inflate2(otz_ctx *c, otz_plan *p, const uint8_t *d_archive, 
 	CK(cudaGetLastError());
 	int rc;
 	switch (c->lz_ring) {
-	case 4096: rc = launch_lz<4096>(c, p, d_out, s); break;
+	case 8192: rc = launch_lz<8192>(c, p, d_out, s); break;
 	case 16384: rc = launch_lz<16384>(c, p, d_out, s); break;
-	default: rc = launch_lz<8192>(c, p, d_out, s); break;
+	default: rc = launch_lz<4096>(c, p, d_out, s); break;
 	}
 	if (rc) {
 		return rc;
