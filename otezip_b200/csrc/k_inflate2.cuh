@@ -36,7 +36,7 @@
 #define I2_DST_ROOT 7
 #define I2_LIT_CAP 704   // 512 root slots + 192 second-level slots
 #define I2_DST_CAP 192   // 128 root slots + 64 second-level slots
-#define I2_LANES 28      // table slots per warp (4 warps x 28 slots fit the 227 KB of one SM)
+#define I2_LANES 28      // most table slots per warp (4 warps x 28 slots fit the 227 KB of one SM)
 #define I2_SLOT_BYTES 1796   // (704 + 192) * 2 + 4: an odd number of 32-bit words, so equal indices of different lanes hit different banks
 #define I2_LENS_OFS 0        // header parse scratch inside the lane's slot (dead once the tables are built)
 #define I2_PRE_OFS 320
@@ -75,7 +75,7 @@ struct I2TokRes {
 };
 
 struct I2WarpScratch {
-	uint32_t ring[4 * 32 * 4];   // input staging: 4 vectors of 16 bytes per lane, [vector slot][lane][word]
+	uint32_t ring[8 * 32 * 4];   // input staging: 8 vectors of 16 bytes per lane, [vector slot][lane][word]
 	uint32_t cnt[16];
 	uint32_t first15[16];   // first canonical code of each length, left-aligned to 15 bits
 	uint32_t limit15[16];   // one past the last code of each length, left-aligned to 15 bits
@@ -86,7 +86,7 @@ struct I2WarpScratch {
 	uint16_t dist_base[32];   // dec:766-771 by symbol
 };
 
-#define I2_SMEM_BYTES (I2_LANES * I2_SLOT_BYTES + (int)sizeof(I2WarpScratch))
+#define I2_SMEM_BYTES(lanes) ((int)sizeof(I2WarpScratch) + (int)(lanes) * I2_SLOT_BYTES)
 
 // worst-case scratch of a stream of n output bytes: literals + 4 bytes per match (>= 3 bytes each) + escapes
 __host__ __device__ __forceinline__ uint64_t i2_scratch_bytes(uint64_t n) {
@@ -101,8 +101,8 @@ __device__ __forceinline__ uint32_t i2_dist_base(uint32_t ds, uint32_t xb) { ret
 
 // ------------------------------------------------------------------------------------------------
 // per-lane bit reader: {lo,hi} is a 64-bit window of the stream, pos < 32 after norm(); nx is the word after hi.
-// The stream is staged through shared memory as 16-byte vectors, four per lane, fetched with cp.async two
-// vectors (>= 5 decoding steps) ahead of their first use: in lock-step execution no lane's cache miss stalls
+// The stream is staged through shared memory as 16-byte vectors, eight slots per lane, requested with cp.async
+// three vectors (>= 8 decoding steps) ahead of their first use: in lock-step execution no lane's cache miss stalls
 // the other 31, and a refill is branch-free (two selects and one shared-memory load).
 struct I2Reader {
 	const uint4 *b16;        // 16-byte aligned base of the stream
@@ -111,17 +111,26 @@ struct I2Reader {
 	uint32_t lo, hi, nx, pos;
 	uint32_t wi_end;         // words_left() = wi_end - wi
 	uint32_t pad_bits;
-	uint32_t *col;           // this lane's column of the staging ring
+	uint32_t fu;             // vectors [0, fu) have been requested
+	volatile uint32_t *col;  // this lane's column of the staging ring (written by cp.async)
+	uint32_t col_sa;         // its shared-window address
 
 	// 32-bit words of the stream not yet moved into {lo,hi} (as BitReader::words_left in k_inflate.cuh)
 	__device__ __forceinline__ int32_t words_left() const { return (int32_t)(wi_end - wi); }
-
-	__device__ __forceinline__ uint32_t word(uint32_t i) const { return col[((i & 12u) << 5) | (i & 3u)]; }
-	__device__ __forceinline__ void fetch(uint32_t c) const {
-		const uint32_t cc = c < nvec ? c : nvec;   // never more than one vector past the stream
-		const uint32_t sa = (uint32_t)__cvta_generic_to_shared(col + ((c & 3u) << 7));
-		asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(sa), "l"(b16 + cc) : "memory");
-		asm volatile("cp.async.commit_group;" ::: "memory");
+	__device__ __forceinline__ uint32_t word(uint32_t i) const { return col[((i & 28u) << 5) | (i & 3u)]; }
+	// Keep vectors up to (wi >> 2) + 3 requested; at most one new vector per call, which is enough for one decoding
+	// step (<= 48 bits).  Straight-line: the copy is predicated, not branched around.
+	__device__ __forceinline__ void top() {
+		const uint32_t pred = fu <= (wi >> 2) + 3u;
+		const uint32_t cc = fu < nvec ? fu : nvec;   // never more than one vector past the stream
+		const uint32_t sa = col_sa + ((fu & 7u) << 9);
+		// one (possibly empty) copy group per call: "at most 6 groups pending" then means that everything requested
+		// seven or more steps ago has landed — a vector is requested at least 8 steps before its first word is read
+		asm volatile(
+			"{\n\t.reg .pred p;\n\tsetp.ne.u32 p, %2, 0;\n\t@p cp.async.cg.shared.global [%0], [%1], 16;\n\t}\n\t"
+			"cp.async.commit_group;\n\tcp.async.wait_group 6;" ::"r"(sa),
+			"l"(b16 + cc), "r"(pred));
+		fu += pred;
 	}
 	__device__ __forceinline__ void init(const uint8_t *p, uint64_t nbytes) {
 		const uint64_t a = reinterpret_cast<uint64_t>(p);
@@ -130,10 +139,11 @@ struct I2Reader {
 		const uint32_t nw = (uint32_t)((skipb + nbytes + 3) >> 2);
 		nvec = (i0 + nw + 3) >> 2;
 		pad_bits = (uint32_t)(((uint64_t)nw << 5) - ((skipb + nbytes) << 3));
-		fetch(0);
-		fetch(1);
-		fetch(2);
-		fetch(3);
+		for (fu = 0; fu < 4u; fu++) {
+			const uint32_t cc = fu < nvec ? fu : nvec;
+			const uint32_t sa = col_sa + ((fu & 7u) << 9);
+			asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n\tcp.async.commit_group;" ::"r"(sa), "l"(b16 + cc) : "memory");
+		}
 		asm volatile("cp.async.wait_group 0;" ::: "memory");
 		lo = word(i0);
 		hi = word(i0 + 1);
@@ -142,18 +152,19 @@ struct I2Reader {
 		wi_end = wi + nw - 2u;
 		pos = 8 * skipb;
 	}
-	// pos < 64 on entry
+	// pos < 64 on entry; the caller keeps the staging ring ahead with top()
 	__device__ __forceinline__ void norm() {
 		const bool p = pos >= 32u;
 		lo = p ? hi : lo;
 		hi = p ? nx : hi;
 		pos &= 31u;
 		wi += p;
-		if (p && (wi & 3u) == 0u) {
-			fetch((wi >> 2) + 2u);   // entering vector wi>>2: it and the next one were requested earlier
-			asm volatile("cp.async.wait_group 2;" ::: "memory");
-		}
 		nx = word(wi);
+	}
+	// for the (branchy, rare) header code: refill check + norm
+	__device__ __forceinline__ void norm_hdr() {
+		top();
+		norm();
 	}
 	__device__ __forceinline__ uint32_t peek() const { return __funnelshift_r(lo, hi, pos); }
 	__device__ __forceinline__ int64_t remaining_bits() const { return ((int64_t)words_left() << 5) + 64 - (int64_t)pos - (int64_t)pad_bits; }
@@ -181,12 +192,13 @@ __device__ __forceinline__ uint16_t i2_symbol_entry(uint32_t s, uint32_t cb) {
 	return s < 286u ? I2_LIT_ENTRY(cb + xb, I2_K_LEN, xb | (v << 3)) : I2_LIT_INVALID;
 }
 
-// length and position in sorted[] of the code that covers the 15-bit left-aligned value c15 (len 16 = none)
-__device__ __forceinline__ void i2_lookup15(const I2WarpScratch &S, uint32_t c15, uint32_t &len, uint32_t &idx) {
+// length and position in sorted[] of the code that covers the 15-bit left-aligned value c15 (len 16 = none);
+// lim[j] = S.limit15[j], held in registers by the caller
+__device__ __forceinline__ void i2_lookup15(const I2WarpScratch &S, const uint32_t (&lim)[16], uint32_t c15, uint32_t &len, uint32_t &idx) {
 	uint32_t l = 1;
 #pragma unroll
 	for (int j = 1; j <= 15; j++) {
-		l += (c15 >= S.limit15[j]);
+		l += (c15 >= lim[j]);
 	}
 	len = l;
 	const uint32_t ll = l > 15u ? 15u : l;
@@ -263,6 +275,11 @@ __device__ __noinline__ int i2_build_table(I2WarpScratch &S, const uint32_t (&le
 		__syncwarp();
 	}
 	// root slots: slot k holds the code whose bits, LSB first, are a prefix of k
+	uint32_t lim[16];
+#pragma unroll
+	for (int j = 0; j < 16; j++) {
+		lim[j] = S.limit15[j];
+	}
 	const uint32_t long15 = S.limit15[ROOT];          // first 15-bit value whose code is longer than ROOT bits
 	const uint32_t end15 = S.limit15[15];             // one past the last covered value (32768 when complete)
 	for (uint32_t k = lane; k < ROOTSZ; k += 32) {
@@ -270,7 +287,7 @@ __device__ __noinline__ int i2_build_table(I2WarpScratch &S, const uint32_t (&le
 		uint16_t e = INVALID;
 		if (c15 < long15) {
 			uint32_t len, idx;
-			i2_lookup15(S, c15, len, idx);
+			i2_lookup15(S, lim, c15, len, idx);
 			e = i2_symbol_entry<IS_DIST>(S.sorted[idx], len);
 		}
 		tbl[k] = e;
@@ -286,7 +303,7 @@ __device__ __noinline__ int i2_build_table(I2WarpScratch &S, const uint32_t (&le
 				uint32_t v15 = ((p + 1u) << (15 - ROOT)) - 1u;
 				v15 = v15 < end15 ? v15 : end15 - 1u;
 				uint32_t len, idx;
-				i2_lookup15(S, v15, len, idx);
+				i2_lookup15(S, lim, v15, len, idx);
 				sub_bits = len - ROOT;
 			}
 			const uint32_t size = p < p1 ? (1u << sub_bits) : 0u;
@@ -311,7 +328,7 @@ __device__ __noinline__ int i2_build_table(I2WarpScratch &S, const uint32_t (&le
 					uint16_t e = INVALID;
 					if (c15 < end15) {
 						uint32_t len, idx;
-						i2_lookup15(S, c15, len, idx);
+						i2_lookup15(S, lim, c15, len, idx);
 						e = i2_symbol_entry<IS_DIST>(S.sorted[idx], len - ROOT);
 					}
 					tbl[sub_off + t] = e;
@@ -333,6 +350,175 @@ __device__ __noinline__ int i2_build_table(I2WarpScratch &S, const uint32_t (&le
 
 __device__ __forceinline__ uint32_t i2_ld_le16(const uint8_t *p) { return (uint32_t)p[0] | ((uint32_t)p[1] << 8); }
 
+// what a lane has to do after i2_header()
+#define I2_A_NONE 0u       // still at a block header (an empty stored / fixed block was consumed)
+#define I2_A_BUILD 1u      // code lengths are in the slot: build the tables, then decode
+#define I2_A_COMMIT 2u     // the stream (or chunk) ended here
+#define I2_A_FALLBACK 3u   // k_inflate takes the stream
+
+// dec:811-816 as k_inflate evaluates it: after a step that leaves the stream unfinished
+#define I2_HDR_STEP_CHECK()                               \
+	if (br.words_left() <= 1) {                           \
+		const int64_t rem_ = br.remaining_bits();         \
+		if (rem_ < 0) {                                   \
+			return I2_A_FALLBACK;                         \
+		} else if (rem_ < 8) {                            \
+			ref_eob = 1u;                                 \
+		}                                                 \
+	}
+
+// One block header (dec:613-627) of the lane's stream: stored blocks (dec:269-319; only empty ones stay on this path),
+// fixed (dec:322-349) and dynamic (dec:122-266) code lengths into the lane's slot.  Lanes run this in lock-step.
+__device__ __forceinline__ uint32_t i2_header(I2Reader &br, uint8_t *slot, const uint8_t *in, uint32_t comp, uint32_t rflags, uint32_t &final_blk,
+	uint32_t &ref_eob, uint32_t &hlit, uint32_t &hdist) {
+	const bool chunk_mid = (rflags & OTZ_EF_CHUNK) && !(rflags & OTZ_EF_LAST_CHUNK);
+	br.norm_hdr();
+	uint32_t bits = br.peek();
+	final_blk = bits & 1u;
+	const uint32_t btype = (bits >> 1) & 3u;
+	br.pos += 3;
+	I2_HDR_STEP_CHECK();
+	if (btype == 0) {
+		// stored block (dec:269-319): only the empty ones (flush points, chunk terminators) stay on this path
+		const int64_t rem = br.remaining_bits();
+		const uint64_t bpos = (uint64_t)comp - (uint64_t)(rem >> 3);
+		if ((uint64_t)comp - bpos < 4 || i2_ld_le16(in + bpos) != 0u || i2_ld_le16(in + bpos + 2) != 0xFFFFu) {
+			return I2_A_FALLBACK;
+		} else {
+			const uint64_t npos = bpos + 4;
+			br.init(in + npos, (uint64_t)comp - npos);
+			if (final_blk) {
+				return I2_A_COMMIT;
+			} else if (npos >= comp) {
+				if (chunk_mid) {
+					return I2_A_COMMIT;   // end of this chunk
+				} else {
+					return I2_A_FALLBACK;   // unfinished stream out of input
+				}
+			}
+		}
+	} else if (btype == 3) {
+		return I2_A_FALLBACK;   // dec:657-658
+	} else if (btype == 1) {
+		br.norm_hdr();
+		if ((br.peek() & 127u) == 0u) {
+			// empty fixed block (zlib's Z_FINISH tail): end-of-block is the 7-bit code 0000000
+			br.pos += 7;
+			if (final_blk) {
+				return I2_A_COMMIT;
+			} else if (chunk_mid && br.remaining_bits() < 8 && br.remaining_bits() >= 0) {
+				return I2_A_COMMIT;
+			} else {
+				I2_HDR_STEP_CHECK();
+			}
+		} else {
+			uint8_t *lens = slot + I2_LENS_OFS;   // dec:322-349
+			for (int i = 0; i < 320; i++) {
+				lens[i] = i < 144 ? 8 : i < 256 ? 9 : i < 280 ? 7 : i < 288 ? 8 : 5;
+			}
+			hlit = 288;
+			hdist = 32;
+			return I2_A_BUILD;
+		}
+	} else {
+		// dynamic block header, dec:122-266
+		uint8_t *lens = slot + I2_LENS_OFS;
+		uint8_t *pre = slot + I2_PRE_OFS;
+		br.norm_hdr();
+		bits = br.peek();
+		hlit = (bits & 31u) + 257u;
+		hdist = ((bits >> 5) & 31u) + 1u;
+		const uint32_t hclen = ((bits >> 10) & 15u) + 4u;
+		br.pos += 14;
+		bool bad = hlit > 286u || hdist > 30u;
+		uint64_t cl = 0;    // 19 code-length-code lengths, 3 bits each
+		uint64_t cnt = 0;   // packed byte counters per length
+		for (uint32_t i = 0; i < hclen; i++) {
+			br.norm_hdr();
+			const uint32_t v = br.peek() & 7u;
+			br.pos += 3;
+			cl |= (uint64_t)v << (3u * c_cl_order[i]);
+			cnt += 1ull << (8u * v);
+		}
+		uint64_t next = 0;   // packed next canonical code per length
+		{
+			int left = 1;
+			uint32_t code = 0;
+			for (uint32_t l = 1; l <= 7; l++) {
+				const uint32_t c = (uint32_t)(cnt >> (8u * l)) & 0xFFu;
+				left = (left << 1) - (int)c;
+				bad |= left < 0;
+				code = (code + (l > 1 ? (uint32_t)(cnt >> (8u * (l - 1))) & 0xFFu : 0u)) << 1;
+				next |= (uint64_t)(code & 0xFFu) << (8u * l);
+			}
+			bad |= left != 0;   // the code-length code must be complete
+		}
+		if (!bad) {
+			for (uint32_t s = 0; s < 19; s++) {
+				const uint32_t l = (uint32_t)(cl >> (3u * s)) & 7u;
+				if (l) {
+					const uint32_t c = (uint32_t)(next >> (8u * l)) & 0xFFu;
+					next += 1ull << (8u * l);
+					const uint32_t rev = __brev(c) >> (32u - l);
+					for (uint32_t x = rev; x < 128u; x += (1u << l)) {
+						pre[x] = (uint8_t)(s | (l << 5));
+					}
+				}
+			}
+			const uint32_t total = hlit + hdist;
+			uint32_t idx = 0, prev = 0;
+			while (idx < total) {
+				br.norm_hdr();
+				bits = br.peek();
+				const uint32_t e = pre[bits & 127u];
+				const uint32_t sym = e & 31u, cb = e >> 5;
+				if (sym < 16u) {
+					br.pos += cb;
+					lens[idx++] = (uint8_t)sym;
+					prev = sym;
+					continue;
+				}
+				uint32_t rep, val = 0;
+				if (sym == 16u) {   // dec:209-219
+					if (idx == 0) {
+						bad = true;
+						break;
+					}
+					val = prev;
+					rep = 3u + ((bits >> cb) & 3u);
+					br.pos += cb + 2;
+				} else if (sym == 17u) {   // dec:221-228
+					rep = 3u + ((bits >> cb) & 7u);
+					br.pos += cb + 3;
+				} else {   // dec:230-237
+					rep = 11u + ((bits >> cb) & 127u);
+					br.pos += cb + 7;
+				}
+				if (idx + rep > total) {
+					bad = true;   // dec:244
+					break;
+				}
+				for (uint32_t i = 0; i < rep; i++) {
+					lens[idx + i] = (uint8_t)val;
+				}
+				idx += rep;
+				prev = val;
+			}
+			for (uint32_t i = total; i < 320u; i++) {
+				lens[i] = 0;
+			}
+			bad |= !bad && lens[256] == 0;   // no end-of-block code
+		}
+		if (bad || br.remaining_bits() < 0) {
+			return I2_A_FALLBACK;
+		} else {
+			return I2_A_BUILD;
+		}
+	}
+		return I2_A_NONE;
+}
+#undef I2_HDR_STEP_CHECK
+
 // phase A.  grid: persistent, one warp per CTA; the first `lanes_active` (<= I2_LANES) lanes of every warp pull list
 // indices from *work_counter.  (Few streams are spread over all resident warps rather than packed into few:
 // a lock-step step costs the same whatever the number of live lanes.)
@@ -342,11 +528,13 @@ __global__ void __launch_bounds__(32) k_inflate_tok(const uint8_t *__restrict__ 
 	uint32_t *__restrict__ fb_list, uint32_t *__restrict__ fb_count, uint32_t lanes_active) {
 	extern __shared__ __align__(16) uint8_t smem_raw[];
 	const uint32_t lane = threadIdx.x;
-	// lanes without a slot never become active; their (predicated-off) table reads go to slot 0
-	uint8_t *const slot = smem_raw + (lane < I2_LANES ? lane : 0u) * I2_SLOT_BYTES;
+	// shared memory: the warp scratch, then `lanes_active` table slots.  Lanes without a slot never become active;
+	// their (predicated-off) table reads go to slot 0
+	I2WarpScratch &WS = *reinterpret_cast<I2WarpScratch *>(smem_raw);
+	uint8_t *const slots = smem_raw + sizeof(I2WarpScratch);
+	uint8_t *const slot = slots + (lane < lanes_active ? lane : 0u) * I2_SLOT_BYTES;
 	const uint16_t *const lit = reinterpret_cast<const uint16_t *>(slot);
 	const uint16_t *const dst = lit + I2_LIT_CAP;
-	I2WarpScratch &WS = *reinterpret_cast<I2WarpScratch *>(smem_raw + I2_LANES * I2_SLOT_BYTES);
 
 	{
 		const uint32_t xl = (lane < 8u || lane == 28u) ? 0u : (lane - 4u) >> 2, xd = lane < 4u ? 0u : (lane - 2u) >> 1;
@@ -359,7 +547,9 @@ __global__ void __launch_bounds__(32) k_inflate_tok(const uint8_t *__restrict__ 
 	// lanes that never get a stream still run the (predicated-off) refill logic: give them a harmless source
 	br.b16 = reinterpret_cast<const uint4 *>(reinterpret_cast<uint64_t>(archive) & ~15ull);
 	br.nvec = br.wi = br.lo = br.hi = br.nx = br.pos = br.pad_bits = br.wi_end = 0;
+	br.fu = 8;   // nothing to request
 	br.col = WS.ring + lane * 4u;
+	br.col_sa = (uint32_t)__cvta_generic_to_shared(WS.ring + lane * 4u);
 	const uint8_t *in = nullptr;
 	uint32_t comp = 0, cap = 0, rflags = 0, k = 0, ei = 0;
 	// output bytes so far = nl + mb; the current literal run = nl - nl0
@@ -367,6 +557,9 @@ __global__ void __launch_bounds__(32) k_inflate_tok(const uint8_t *__restrict__ 
 	uint8_t *litp = nullptr;
 	uint32_t *seqp = nullptr;
 	uint32_t final_blk = 0, ref_eob = 0, hlit = 0, hdist = 0;
+	// step parsed but not yet emitted (software pipeline of the decode loop): entries and bit windows
+	bool pv = false;
+	uint32_t pe = 0, pd = 0, pb = 0, pb2 = 0;
 
 // leave the current stream: FALLBACK = hand it to k_inflate, COMMIT = release it to phase B
 #define I2_FALLBACK()                                                     \
@@ -457,151 +650,13 @@ __global__ void __launch_bounds__(32) k_inflate_tok(const uint8_t *__restrict__ 
 		}
 		// ---- (2) block headers (dec:613-627), every lane that stands at one, in lock-step
 		if (state == I2_S_HDR) {
-			const bool chunk_mid = (rflags & OTZ_EF_CHUNK) && !(rflags & OTZ_EF_LAST_CHUNK);
-			br.norm();
-			uint32_t bits = br.peek();
-			final_blk = bits & 1u;
-			const uint32_t btype = (bits >> 1) & 3u;
-			br.pos += 3;
-			I2_STEP_CHECK();
-			if (state != I2_S_HDR) {
-				// fell back
-			} else if (btype == 0) {
-				// stored block (dec:269-319): only the empty ones (flush points, chunk terminators) stay on this path
-				const int64_t rem = br.remaining_bits();
-				const uint64_t bpos = (uint64_t)comp - (uint64_t)(rem >> 3);
-				if ((uint64_t)comp - bpos < 4 || i2_ld_le16(in + bpos) != 0u || i2_ld_le16(in + bpos + 2) != 0xFFFFu) {
-					I2_FALLBACK();
-				} else {
-					const uint64_t npos = bpos + 4;
-					br.init(in + npos, (uint64_t)comp - npos);
-					if (final_blk) {
-						I2_COMMIT();
-					} else if (npos >= comp) {
-						if (chunk_mid) {
-							I2_COMMIT();   // end of this chunk
-						} else {
-							I2_FALLBACK();   // unfinished stream out of input
-						}
-					}
-				}
-			} else if (btype == 3) {
-				I2_FALLBACK();   // dec:657-658
-			} else if (btype == 1) {
-				br.norm();
-				if ((br.peek() & 127u) == 0u) {
-					// empty fixed block (zlib's Z_FINISH tail): end-of-block is the 7-bit code 0000000
-					br.pos += 7;
-					if (final_blk) {
-						I2_COMMIT();
-					} else if (chunk_mid && br.remaining_bits() < 8 && br.remaining_bits() >= 0) {
-						I2_COMMIT();
-					} else {
-						I2_STEP_CHECK();
-					}
-				} else {
-					uint8_t *lens = slot + I2_LENS_OFS;   // dec:322-349
-					for (int i = 0; i < 320; i++) {
-						lens[i] = i < 144 ? 8 : i < 256 ? 9 : i < 280 ? 7 : i < 288 ? 8 : 5;
-					}
-					hlit = 288;
-					hdist = 32;
-					state = I2_S_BUILD;
-				}
-			} else {
-				// dynamic block header, dec:122-266
-				uint8_t *lens = slot + I2_LENS_OFS;
-				uint8_t *pre = slot + I2_PRE_OFS;
-				br.norm();
-				bits = br.peek();
-				hlit = (bits & 31u) + 257u;
-				hdist = ((bits >> 5) & 31u) + 1u;
-				const uint32_t hclen = ((bits >> 10) & 15u) + 4u;
-				br.pos += 14;
-				bool bad = hlit > 286u || hdist > 30u;
-				uint64_t cl = 0;    // 19 code-length-code lengths, 3 bits each
-				uint64_t cnt = 0;   // packed byte counters per length
-				for (uint32_t i = 0; i < hclen; i++) {
-					br.norm();
-					const uint32_t v = br.peek() & 7u;
-					br.pos += 3;
-					cl |= (uint64_t)v << (3u * c_cl_order[i]);
-					cnt += 1ull << (8u * v);
-				}
-				uint64_t next = 0;   // packed next canonical code per length
-				{
-					int left = 1;
-					uint32_t code = 0;
-					for (uint32_t l = 1; l <= 7; l++) {
-						const uint32_t c = (uint32_t)(cnt >> (8u * l)) & 0xFFu;
-						left = (left << 1) - (int)c;
-						bad |= left < 0;
-						code = (code + (l > 1 ? (uint32_t)(cnt >> (8u * (l - 1))) & 0xFFu : 0u)) << 1;
-						next |= (uint64_t)(code & 0xFFu) << (8u * l);
-					}
-					bad |= left != 0;   // the code-length code must be complete
-				}
-				if (!bad) {
-					for (uint32_t s = 0; s < 19; s++) {
-						const uint32_t l = (uint32_t)(cl >> (3u * s)) & 7u;
-						if (l) {
-							const uint32_t c = (uint32_t)(next >> (8u * l)) & 0xFFu;
-							next += 1ull << (8u * l);
-							const uint32_t rev = __brev(c) >> (32u - l);
-							for (uint32_t x = rev; x < 128u; x += (1u << l)) {
-								pre[x] = (uint8_t)(s | (l << 5));
-							}
-						}
-					}
-					const uint32_t total = hlit + hdist;
-					uint32_t idx = 0, prev = 0;
-					while (idx < total) {
-						br.norm();
-						bits = br.peek();
-						const uint32_t e = pre[bits & 127u];
-						const uint32_t sym = e & 31u, cb = e >> 5;
-						if (sym < 16u) {
-							br.pos += cb;
-							lens[idx++] = (uint8_t)sym;
-							prev = sym;
-							continue;
-						}
-						uint32_t rep, val = 0;
-						if (sym == 16u) {   // dec:209-219
-							if (idx == 0) {
-								bad = true;
-								break;
-							}
-							val = prev;
-							rep = 3u + ((bits >> cb) & 3u);
-							br.pos += cb + 2;
-						} else if (sym == 17u) {   // dec:221-228
-							rep = 3u + ((bits >> cb) & 7u);
-							br.pos += cb + 3;
-						} else {   // dec:230-237
-							rep = 11u + ((bits >> cb) & 127u);
-							br.pos += cb + 7;
-						}
-						if (idx + rep > total) {
-							bad = true;   // dec:244
-							break;
-						}
-						for (uint32_t i = 0; i < rep; i++) {
-							lens[idx + i] = (uint8_t)val;
-						}
-						idx += rep;
-						prev = val;
-					}
-					for (uint32_t i = total; i < 320u; i++) {
-						lens[i] = 0;
-					}
-					bad |= !bad && lens[256] == 0;   // no end-of-block code
-				}
-				if (bad || br.remaining_bits() < 0) {
-					I2_FALLBACK();
-				} else {
-					state = I2_S_BUILD;
-				}
+			const uint32_t act_ = i2_header(br, slot, in, comp, rflags, final_blk, ref_eob, hlit, hdist);
+			if (act_ == I2_A_BUILD) {
+				state = I2_S_BUILD;
+			} else if (act_ == I2_A_COMMIT) {
+				I2_COMMIT();
+			} else if (act_ == I2_A_FALLBACK) {
+				I2_FALLBACK();
 			}
 		}
 		// ---- (2b) tables, one requesting lane at a time, whole warp
@@ -611,7 +666,7 @@ __global__ void __launch_bounds__(32) k_inflate_tok(const uint8_t *__restrict__ 
 				const int x = __ffs(need) - 1;
 				need &= need - 1;
 				__syncwarp();
-				const uint8_t *xl = smem_raw + x * I2_SLOT_BYTES + I2_LENS_OFS;
+				const uint8_t *xl = slots + x * I2_SLOT_BYTES + I2_LENS_OFS;
 				uint32_t lens[10];
 #pragma unroll
 				for (int j = 0; j < 10; j++) {
@@ -619,7 +674,7 @@ __global__ void __launch_bounds__(32) k_inflate_tok(const uint8_t *__restrict__ 
 				}
 				__syncwarp();
 				const uint32_t xh = __shfl_sync(0xFFFFFFFFu, hlit, x), xd = __shfl_sync(0xFFFFFFFFu, hdist, x);
-				uint16_t *xt = reinterpret_cast<uint16_t *>(smem_raw + x * I2_SLOT_BYTES);
+				uint16_t *xt = reinterpret_cast<uint16_t *>(slots + x * I2_SLOT_BYTES);
 				int r = i2_build_table<false, I2_LIT_ROOT, I2_LIT_CAP>(WS, lens, 0u, xh, xt);
 				if (!r) {
 					r = i2_build_table<true, I2_DST_ROOT, I2_DST_CAP>(WS, lens, xh, xd, xt + I2_LIT_CAP);
@@ -636,102 +691,140 @@ __global__ void __launch_bounds__(32) k_inflate_tok(const uint8_t *__restrict__ 
 			}
 		}
 		// ---- (3) symbols (dec:662-799).  One literal/length symbol and — used by the lanes that got a length —
-		// one distance symbol per step, as straight-line code: every lane runs the same instructions.  Everything
-		// unusual (second-level tables, end of block, long literal runs, errors, end of input) is left untouched
-		// by the main path and finished, lane by lane, behind ONE warp vote at the end of the step.
+		// one distance symbol per step, as straight-line code: every lane runs the same instructions.  A step is
+		// software-pipelined over two iterations: iteration i PARSES step i (bit position, two table lookups — the
+		// serial chain of the stream) and EMITS step i-1 (length/distance arithmetic, bounds, token stores) from the
+		// entries and bit windows saved in registers, so the two dependency chains interleave in the one warp.
+		// Everything unusual (second-level tables, end of block, long literal runs, errors, end of input) is left
+		// untouched by the main path and finished, lane by lane, behind ONE warp vote at the end of the iteration.
 		while (__all_sync(0xFFFFFFFFu, state == I2_S_DEC || state == I2_S_DONE) && __any_sync(0xFFFFFFFFu, state == I2_S_DEC)) {
 			bool leave = false;
 #pragma unroll 1
-			for (int burst = 0; burst < 32 && !leave; burst++) {
+			for (int burst = 0; burst < 64 && !leave; burst++) {
 				const bool act = state == I2_S_DEC;
+				// ---- emit step i-1
+				bool e_special;
+				{
+					const uint32_t tb = pe & 15u, kind = (pe >> 4) & 3u, xb = (pe >> 6) & 7u, v = (pe >> 9) & 31u;
+					const uint32_t length = WS.len_base[v] + ((pb >> (tb - xb)) & ((1u << xb) - 1u));
+					const uint32_t tb2 = pd & 31u, dxb = (pd >> 5) & 15u, ds = (pd >> 9) & 31u;
+					const uint32_t dist = WS.dist_base[ds] + ((pb2 >> (tb2 - dxb)) & ((1u << dxb) - 1u));
+					const uint32_t run = nl - nl0, opos = nl + mb;
+					const bool e_lit = pv && kind == I2_K_LIT, e_len = pv && kind == I2_K_LEN;
+					const bool e_ok = e_len && run < I2_SEQ_ESC && dist <= opos;
+					if (e_lit) {
+						I2_EMIT_LIT((pe >> 6) & 0xFFu);
+					}
+					if (e_ok) {
+						I2_EMIT_MATCH(run, length, dist);
+					}
+					// (the token scratch has room for the one literal or record that may exceed `cap` here)
+					pv = e_len && !e_ok;   // still pending only if the special path has to finish it
+					e_special = pv || nl + mb > cap;
+				}
+				// ---- parse step i
+				br.top();
 				br.norm();
 				const uint32_t bits = br.peek();
 				const uint32_t e = lit[bits & ((1u << I2_LIT_ROOT) - 1u)];
-				const uint32_t tb = e & 15u, kind = (e >> 4) & 3u;
-				const bool is_lit = act && kind == I2_K_LIT, is_len = act && kind == I2_K_LEN;
-				br.pos += tb;   // (0 for a LINK entry; idle lanes do not care)
-				// length (dec:720-737)
-				const uint32_t xb = (e >> 6) & 7u, v = (e >> 9) & 31u;
-				const uint32_t length = WS.len_base[v] + ((bits >> (tb - xb)) & ((1u << xb) - 1u));
-				// distance (dec:740-782); lanes without a length decode garbage and ignore it
+				const uint32_t kind = (e >> 4) & 3u;
+				br.pos += act ? (e & 15u) : 0u;   // (0 for a LINK entry)
 				br.norm();
 				const uint32_t bits2 = br.peek();
 				const uint32_t d = dst[bits2 & ((1u << I2_DST_ROOT) - 1u)];
-				const uint32_t tb2 = d & 31u, dxb = (d >> 5) & 15u, ds = (d >> 9) & 31u;
-				const uint32_t dist = WS.dist_base[ds] + ((bits2 >> (tb2 - dxb)) & ((1u << dxb) - 1u));
-				const uint32_t run = nl - nl0, opos = nl + mb;
-				// a match the main path completes: root-level distance code, short literal run, source inside the output
-				const bool len_ok = is_len && (d >> 14) == 0u && run < I2_SEQ_ESC && dist <= opos;
-				br.pos += len_ok ? tb2 : 0u;
-				if (is_lit) {
-					I2_EMIT_LIT((e >> 6) & 0xFFu);
-				}
-				if (len_ok) {
-					I2_EMIT_MATCH(run, length, dist);
-				}
-				// (the token scratch has room for the one literal or record that may exceed `cap` here)
-				const bool special = act && ((!is_lit && !len_ok) || nl + mb > cap || br.words_left() <= 1);
+				const bool p_len = act && kind == I2_K_LEN, p_root = (d >> 14) == 0u;
+				br.pos += (p_len && p_root) ? (d & 31u) : 0u;
+				const bool p_plain = act && (kind == I2_K_LIT || (p_len && p_root));
+				const bool special = e_special || (act && (!p_plain || br.words_left() <= 1));
 				if (__any_sync(0xFFFFFFFFu, special)) {
 					if (special) {
-						bool bad = nl + mb > cap;   // dec:700-703, dec:791-793
-						bool eob = kind == I2_K_EOB;
-						bool want_dist = is_len && !len_ok;   // length consumed, distance still to do
-						uint32_t len2 = length;
-						if (!bad && kind == I2_K_LINK) {
-							// second-level literal/length table
-							const uint32_t sb = I2_LIT_LINK_BITS(e);
-							if (sb == 0u) {
-								bad = true;   // dec:693-695: no code matches
+						bool bad = false;
+						// -- finish step i-1 (a match after >= 511 literals, or an error)
+						if (pv) {
+							const uint32_t tb = pe & 15u, xb = (pe >> 6) & 7u, v = (pe >> 9) & 31u;
+							const uint32_t length = WS.len_base[v] + ((pb >> (tb - xb)) & ((1u << xb) - 1u));
+							const uint32_t tb2 = pd & 31u, dxb = (pd >> 5) & 15u, ds = (pd >> 9) & 31u;
+							const uint32_t dist = WS.dist_base[ds] + ((pb2 >> (tb2 - dxb)) & ((1u << dxb) - 1u));
+							uint32_t r3 = nl - nl0;
+							if (dist > nl + mb) {
+								bad = true;   // reaches before the start of the output (strict; dec:785 does not check)
 							} else {
-								const uint32_t e2 = lit[I2_LIT_LINK_OFS(e) + ((bits >> I2_LIT_ROOT) & ((1u << sb) - 1u))];
-								const uint32_t k2 = (e2 >> 4) & 3u, t2 = e2 & 15u;
-								if (k2 == I2_K_LINK) {
-									bad = true;
-								} else {
-									br.pos += I2_LIT_ROOT + t2;
-									if (k2 == I2_K_LIT) {
-										I2_EMIT_LIT((e2 >> 6) & 0xFFu);
-										bad = nl + mb > cap;
-									} else if (k2 == I2_K_EOB) {
-										eob = true;
-									} else {
-										const uint32_t x2 = (e2 >> 6) & 7u;
-										len2 = WS.len_base[(e2 >> 9) & 31u] + ((bits >> (I2_LIT_ROOT + t2 - x2)) & ((1u << x2) - 1u));
-										want_dist = true;
-									}
+								while (r3 >= I2_SEQ_ESC) {
+									*--seqp = I2_SEQ_ESC;
+									nseq++;
+									r3 -= I2_SEQ_ESC;
 								}
+								I2_EMIT_MATCH(r3, length, dist);
 							}
+							pv = false;
 						}
-						if (!bad && want_dist) {
-							br.norm();
-							const uint32_t b3 = br.peek();
-							uint32_t dd = dst[b3 & ((1u << I2_DST_ROOT) - 1u)];
-							uint32_t used = 0;
-							if ((dd >> 14) != 0u) {
-								const uint32_t sb = I2_DST_LINK_BITS(dd);
+						bad = bad || nl + mb > cap;   // dec:700-703, dec:791-793
+						// -- step i, when it is not a plain literal / root-level match: decode and emit it here
+						bool eob = false;
+						if (!bad && act && !p_plain) {
+							bool want_dist = p_len;   // (then the length code is consumed, the distance code is not)
+							uint32_t len2 = 0;
+							if (p_len) {
+								const uint32_t tb = e & 15u, xb = (e >> 6) & 7u;
+								len2 = WS.len_base[(e >> 9) & 31u] + ((bits >> (tb - xb)) & ((1u << xb) - 1u));
+							} else if (kind == I2_K_EOB) {
+								eob = true;
+							} else {
+								// second-level literal/length table
+								const uint32_t sb = I2_LIT_LINK_BITS(e);
 								if (sb == 0u) {
-									bad = true;   // dec:762-764
+									bad = true;   // dec:693-695: no code matches
 								} else {
-									dd = dst[I2_DST_LINK_OFS(dd) + ((b3 >> I2_DST_ROOT) & ((1u << sb) - 1u))];
-									used = I2_DST_ROOT;
-									bad = (dd >> 14) != 0u;
+									const uint32_t e2 = lit[I2_LIT_LINK_OFS(e) + ((bits >> I2_LIT_ROOT) & ((1u << sb) - 1u))];
+									const uint32_t k2 = (e2 >> 4) & 3u, t2 = e2 & 15u;
+									if (k2 == I2_K_LINK) {
+										bad = true;
+									} else {
+										br.pos += I2_LIT_ROOT + t2;
+										if (k2 == I2_K_LIT) {
+											I2_EMIT_LIT((e2 >> 6) & 0xFFu);
+											bad = nl + mb > cap;
+										} else if (k2 == I2_K_EOB) {
+											eob = true;
+										} else {
+											const uint32_t x2 = (e2 >> 6) & 7u;
+											len2 = WS.len_base[(e2 >> 9) & 31u] + ((bits >> (I2_LIT_ROOT + t2 - x2)) & ((1u << x2) - 1u));
+											want_dist = true;
+										}
+									}
 								}
 							}
-							if (!bad) {
-								const uint32_t t3 = dd & 31u, x3 = (dd >> 5) & 15u;
-								const uint32_t dist3 = WS.dist_base[(dd >> 9) & 31u] + ((b3 >> (used + t3 - x3)) & ((1u << x3) - 1u));
-								br.pos += used + t3;
-								uint32_t r3 = nl - nl0;
-								if (dist3 > nl + mb) {
-									bad = true;   // reaches before the start of the output (strict; dec:785 does not check)
-								} else {
-									while (r3 >= I2_SEQ_ESC) {
-										*--seqp = I2_SEQ_ESC;
-										nseq++;
-										r3 -= I2_SEQ_ESC;
+							if (!bad && want_dist) {
+								br.norm_hdr();
+								const uint32_t b3 = br.peek();
+								uint32_t dd = dst[b3 & ((1u << I2_DST_ROOT) - 1u)];
+								uint32_t used = 0;
+								if ((dd >> 14) != 0u) {
+									const uint32_t sb = I2_DST_LINK_BITS(dd);
+									if (sb == 0u) {
+										bad = true;   // dec:762-764
+									} else {
+										dd = dst[I2_DST_LINK_OFS(dd) + ((b3 >> I2_DST_ROOT) & ((1u << sb) - 1u))];
+										used = I2_DST_ROOT;
+										bad = (dd >> 14) != 0u;
 									}
-									I2_EMIT_MATCH(r3, len2, dist3);
-									bad = nl + mb > cap;
+								}
+								if (!bad) {
+									const uint32_t t3 = dd & 31u, x3 = (dd >> 5) & 15u;
+									const uint32_t dist3 = WS.dist_base[(dd >> 9) & 31u] + ((b3 >> (used + t3 - x3)) & ((1u << x3) - 1u));
+									br.pos += used + t3;
+									uint32_t r3 = nl - nl0;
+									if (dist3 > nl + mb) {
+										bad = true;
+									} else {
+										while (r3 >= I2_SEQ_ESC) {
+											*--seqp = I2_SEQ_ESC;
+											nseq++;
+											r3 -= I2_SEQ_ESC;
+										}
+										I2_EMIT_MATCH(r3, len2, dist3);
+										bad = nl + mb > cap;
+									}
 								}
 							}
 						}
@@ -748,12 +841,18 @@ __global__ void __launch_bounds__(32) k_inflate_tok(const uint8_t *__restrict__ 
 								state = I2_S_HDR;
 								I2_STEP_CHECK();
 							}
-						} else {
+						} else if (act) {
 							I2_STEP_CHECK();
 						}
 					}
 					leave = __any_sync(0xFFFFFFFFu, state != I2_S_DEC && state != I2_S_DONE);
 				}
+				// step i waits for the next iteration if it is plain and its lane is still decoding
+				pv = pv || (p_plain && state == I2_S_DEC);
+				pe = p_plain ? e : pe;
+				pd = p_plain ? d : pd;
+				pb = p_plain ? bits : pb;
+				pb2 = p_plain ? bits2 : pb2;
 			}
 		}
 	}

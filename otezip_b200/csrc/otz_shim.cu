@@ -561,20 +561,38 @@ static int dispatch_inflate2(otz_ctx *c, otz_plan *p, const uint8_t *d_archive, 
 	cudaStream_t s = c->stream;
 	static bool attr_done = false;
 	if (!attr_done) {
-		CK(cudaFuncSetAttribute(k_inflate_tok, cudaFuncAttributeMaxDynamicSharedMemorySize, I2_SMEM_BYTES));
+		CK(cudaFuncSetAttribute(k_inflate_tok, cudaFuncAttributeMaxDynamicSharedMemorySize, I2_SMEM_BYTES(I2_LANES)));
 		attr_done = true;
 	}
+	// A lock-step step costs the same for 1 or 28 live lanes and a stream advances one symbol per step, so the
+	// streams are spread over as many CTAs as the SM holds (more warps = more latency hidden): pick the number
+	// of resident CTAs per SM (8..4) that gives the most table slots for this batch, most CTAs first.
+	const long fixed = (long)I2_SMEM_BYTES(0);
+	const uint32_t per_sm_streams = (p->n_inflate + (uint32_t)c->sm_count - 1) / (uint32_t)c->sm_count;
+	uint32_t best_c = 4, best_l = 1, best_cov = 0;
+	for (uint32_t cw = 8; cw >= 4; cw--) {
+		const long budget = (long)(227 * 1024) / (long)cw - 1024 - fixed;
+		const uint32_t l = (uint32_t)std::max(1L, std::min<long>(I2_LANES, budget / I2_SLOT_BYTES));
+		const uint32_t cov = std::min(per_sm_streams, cw * l);
+		if (cov > best_cov) {
+			best_cov = cov;
+			best_c = cw;
+			best_l = l;
+		}
+	}
+	uint32_t lanes = std::max(1u, std::min(best_l, (per_sm_streams + best_c - 1) / best_c));
+	const size_t smem_l = (size_t)I2_SMEM_BYTES(best_l);
 	int per_sm = 0;
-	CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_inflate_tok, 32, I2_SMEM_BYTES));
+	CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_inflate_tok, 32, smem_l));
 	if (per_sm < 1) {
-		snprintf(g_err, sizeof(g_err), "k_inflate_tok does not fit an SM (%d bytes of shared memory)", I2_SMEM_BYTES);
+		snprintf(g_err, sizeof(g_err), "k_inflate_tok does not fit an SM (%zu bytes of shared memory)", smem_l);
 		return OTZ_ERR_CUDA;
 	}
-	// few streams are spread over all resident warps (a lock-step step costs the same for 1 or 28 live lanes)
+	per_sm = std::min<int>(per_sm, (int)best_c);
 	const uint32_t grid = std::max(1u, std::min((uint32_t)(c->sm_count * per_sm), p->n_inflate));
-	const uint32_t lanes = std::min<uint32_t>(I2_LANES, (p->n_inflate + grid - 1) / grid);
-	k_inflate_tok<<<grid, 32, I2_SMEM_BYTES, s>>>(d_archive, p->d_ents, p->d_est, p->d_status, p->d_inflate_list, p->n_inflate, p->d_counter,
-		c->d_tok_cache, p->d_tok_ofs, p->d_tokres, p->d_fb_list, p->d_counter + 52, lanes);
+	lanes = std::max(lanes, std::min<uint32_t>(best_l, (p->n_inflate + grid - 1) / grid));
+	k_inflate_tok<<<grid, 32, I2_SMEM_BYTES(lanes), s>>>(d_archive, p->d_ents, p->d_est, p->d_status, p->d_inflate_list, p->n_inflate,
+		p->d_counter, c->d_tok_cache, p->d_tok_ofs, p->d_tokres, p->d_fb_list, p->d_counter + 52, lanes);
 	c->launches++;
 	CK(cudaGetLastError());
 	int rc;
