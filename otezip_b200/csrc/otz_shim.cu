@@ -66,6 +66,7 @@ struct otz_plan {
 	uint32_t n_store_chunks;   // chunks [0, n_store_chunks) belong to STORE entries
 	uint32_t *d_inflate_list, n_inflate;   // DEFLATE entries, longest first; [0, n_inflate_big) are the large ones
 	uint32_t n_inflate_big;
+	uint32_t n_inflate_huge;   // [0, n_inflate_huge): entries whose serial decode time sets the critical path of a batch
 	uint64_t *d_tok_ofs;       // two-phase inflate: scratch offset of every list slot (+ end), bytes
 	uint64_t tok_bytes;
 	I2TokRes *d_tokres;
@@ -423,13 +424,18 @@ extern "C" int otz_plan_create(otz_ctx *c, const otz_entry *ents, uint32_t n, co
 	// longest streams first: the tail of the batch is then made of short ones
 	// large entries first (they get the 16 KiB ring kernel), inside each class longest streams first
 	const uint32_t big_bytes = 256u * 1024u;
+	const char *hb = getenv("OTZ_HUGE_BYTES");
+	const uint32_t huge_bytes = hb ? (uint32_t)strtoul(hb, nullptr, 0) : 2u * 1024u * 1024u;
+	auto cls = [&](uint32_t i) { return ents[i].uncomp_size >= huge_bytes ? 2 : ents[i].uncomp_size >= big_bytes ? 1 : 0; };
 	std::stable_sort(infl.begin(), infl.end(), [&](uint32_t a, uint32_t b) {
-		const bool ba = ents[a].uncomp_size >= big_bytes, bb = ents[b].uncomp_size >= big_bytes;
-		return ba != bb ? ba : ents[a].comp_size > ents[b].comp_size;
+		const int ca = cls(a), cb = cls(b);
+		return ca != cb ? ca > cb : ents[a].comp_size > ents[b].comp_size;
 	});
 	p->n_inflate_big = 0;
+	p->n_inflate_huge = 0;
 	for (uint32_t i : infl) {
 		p->n_inflate_big += ents[i].uncomp_size >= big_bytes;
+		p->n_inflate_huge += ents[i].uncomp_size >= huge_bytes;
 	}
 	p->n_chunks = (uint32_t)chunks.size();
 	p->n_inflate = (uint32_t)infl.size();
@@ -478,8 +484,8 @@ extern "C" int otz_plan_create(otz_ctx *c, const otz_entry *ents, uint32_t n, co
 }
 
 template <int G, int W>
-static int launch_inflate(otz_ctx *c, otz_plan *p, const uint8_t *d_archive, uint8_t *d_out, const uint32_t *d_list, uint32_t count, int slot,
-	cudaStream_t st, const uint32_t *d_count) {
+static int launch_inflate(otz_ctx *c, otz_plan *p, const uint8_t *d_archive, uint8_t *d_out, const uint32_t *d_list, uint32_t count,
+	uint32_t *d_work, cudaStream_t st, const uint32_t *d_count) {
 	const int threads = 8 * G;   // 8 streams per CTA
 	const size_t smem = 8 * sizeof(InflateSmemV2<G, W>);
 	static bool attr_done = false;
@@ -497,21 +503,21 @@ static int launch_inflate(otz_ctx *c, otz_plan *p, const uint8_t *d_archive, uin
 	uint32_t grid = (uint32_t)(c->sm_count * per_sm);
 	const uint32_t want = (count + tiles_per_cta - 1) / tiles_per_cta;
 	grid = std::max(1u, std::min(grid, want));
-	k_inflate<G, W><<<grid, threads, smem, st>>>(d_archive, d_out, p->d_ents, p->d_est, p->d_status, d_list, count, p->d_counter + 16 * slot,
-		p->d_produced, d_count);
+	k_inflate<G, W><<<grid, threads, smem, st>>>(d_archive, d_out, p->d_ents, p->d_est, p->d_status, d_list, count, d_work, p->d_produced, d_count);
 	c->launches++;
 	CK(cudaGetLastError());
 	return OTZ_SUCCESS;
 }
 
 static int launch_inflate_cfg(otz_ctx *c, otz_plan *p, const uint8_t *d_archive, uint8_t *d_out, int g, int w, uint32_t first, uint32_t count,
-	int slot, cudaStream_t st, const uint32_t *d_list = nullptr, const uint32_t *d_count = nullptr) {
+	int slot /* word of d_counter used as the work counter */, cudaStream_t st, const uint32_t *d_list = nullptr,
+	const uint32_t *d_count = nullptr) {
 	if (!d_list) {
 		d_list = p->d_inflate_list + first;
 	}
 #define OTZ_INF_CASE(G_, W_)        \
 	if (g == G_ && w == W_) {       \
-		return launch_inflate<G_, W_>(c, p, d_archive, d_out, d_list, count, slot, st, d_count); \
+		return launch_inflate<G_, W_>(c, p, d_archive, d_out, d_list, count, p->d_counter + slot, st, d_count); \
 	}
 	OTZ_INF_CASE(32, 16384)
 	OTZ_INF_CASE(32, 4096)
@@ -533,7 +539,7 @@ static int launch_inflate_cfg(otz_ctx *c, otz_plan *p, const uint8_t *d_archive,
 // the critical path of a batch, so they always get the big ring, on a second stream so that both kernels can
 // share the machine; small entries get the big ring only when there are too few of them to fill the SMs.
 template <int W>
-static int launch_lz(otz_ctx *c, otz_plan *p, uint8_t *d_out, cudaStream_t st) {
+static int launch_lz(otz_ctx *c, otz_plan *p, uint8_t *d_out, uint32_t first, uint32_t count, cudaStream_t st) {
 	const int warps = 4;
 	const size_t smem = warps * sizeof(I2LzSmem<W>);
 	static bool attr_done = false;
@@ -547,9 +553,9 @@ static int launch_lz(otz_ctx *c, otz_plan *p, uint8_t *d_out, cudaStream_t st) {
 		snprintf(g_err, sizeof(g_err), "k_inflate_lz<%d> does not fit an SM", W);
 		return OTZ_ERR_CUDA;
 	}
-	const uint32_t grid = std::max(1u, std::min((uint32_t)(c->sm_count * per_sm), (p->n_inflate + warps - 1) / warps));
-	k_inflate_lz<W><<<grid, 32 * warps, smem, st>>>(d_out, p->d_ents, p->d_inflate_list, p->n_inflate, p->d_counter + 48, c->d_tok_cache,
-		p->d_tok_ofs, p->d_tokres, p->d_status, p->d_produced);
+	const uint32_t grid = std::max(1u, std::min((uint32_t)(c->sm_count * per_sm), (count + warps - 1) / warps));
+	k_inflate_lz<W><<<grid, 32 * warps, smem, st>>>(d_out, p->d_ents, p->d_inflate_list + first, count, p->d_counter + 48, c->d_tok_cache,
+		p->d_tok_ofs + first, p->d_tokres + first, p->d_status, p->d_produced);
 	c->launches++;
 	CK(cudaGetLastError());
 	return OTZ_SUCCESS;
@@ -559,6 +565,27 @@ static int launch_lz(otz_ctx *c, otz_plan *p, uint8_t *d_out, cudaStream_t st) {
 // whatever phase A declined (d_counter + 52 counts those entries).
 static int dispatch_inflate2(otz_ctx *c, otz_plan *p, const uint8_t *d_archive, uint8_t *d_out) {
 	cudaStream_t s = c->stream;
+	// Huge entries: a stream advances one symbol per step wherever it is decoded, so the largest entries set the
+	// critical path of the batch.  They go to the decoder with the shortest step — one warp per stream with a 16 KiB
+	// ring (k_inflate) — on the second stream, next to the lane-per-stream kernels that take everything else.
+	uint32_t first = 0;
+	bool forked = false;
+	if (p->n_inflate_huge && p->n_inflate_huge <= (uint32_t)c->sm_count * 10u) {
+		first = p->n_inflate_huge;
+		CK(cudaEventRecord(c->ev_fork, s));
+		CK(cudaStreamWaitEvent(c->stream2, c->ev_fork, 0));
+		int rc_ = launch_inflate_cfg(c, p, d_archive, d_out, 32, 16384, 0, first, 56, c->stream2);
+		if (rc_) {
+			return rc_;
+		}
+		CK(cudaEventRecord(c->ev_join, c->stream2));
+		forked = true;
+	}
+	const uint32_t count = p->n_inflate - first;
+	if (!count) {
+		CK(cudaStreamWaitEvent(s, c->ev_join, 0));
+		return OTZ_SUCCESS;
+	}
 	static bool attr_done = false;
 	if (!attr_done) {
 		CK(cudaFuncSetAttribute(k_inflate_tok, cudaFuncAttributeMaxDynamicSharedMemorySize, I2_SMEM_BYTES(I2_LANES)));
@@ -568,7 +595,7 @@ static int dispatch_inflate2(otz_ctx *c, otz_plan *p, const uint8_t *d_archive, 
 	// streams are spread over as many CTAs as the SM holds (more warps = more latency hidden): pick the number
 	// of resident CTAs per SM (8..4) that gives the most table slots for this batch, most CTAs first.
 	const long fixed = (long)I2_SMEM_BYTES(0);
-	const uint32_t per_sm_streams = (p->n_inflate + (uint32_t)c->sm_count - 1) / (uint32_t)c->sm_count;
+	const uint32_t per_sm_streams = (count + (uint32_t)c->sm_count - 1) / (uint32_t)c->sm_count;
 	uint32_t best_c = 4, best_l = 1, best_cov = 0;
 	for (uint32_t cw = 8; cw >= 4; cw--) {
 		const long budget = (long)(227 * 1024) / (long)cw - 1024 - fixed;
@@ -589,22 +616,26 @@ static int dispatch_inflate2(otz_ctx *c, otz_plan *p, const uint8_t *d_archive, 
 		return OTZ_ERR_CUDA;
 	}
 	per_sm = std::min<int>(per_sm, (int)best_c);
-	const uint32_t grid = std::max(1u, std::min((uint32_t)(c->sm_count * per_sm), p->n_inflate));
-	lanes = std::max(lanes, std::min<uint32_t>(best_l, (p->n_inflate + grid - 1) / grid));
-	k_inflate_tok<<<grid, 32, I2_SMEM_BYTES(lanes), s>>>(d_archive, p->d_ents, p->d_est, p->d_status, p->d_inflate_list, p->n_inflate,
-		p->d_counter, c->d_tok_cache, p->d_tok_ofs, p->d_tokres, p->d_fb_list, p->d_counter + 52, lanes);
+	const uint32_t grid = std::max(1u, std::min((uint32_t)(c->sm_count * per_sm), count));
+	lanes = std::max(lanes, std::min<uint32_t>(best_l, (count + grid - 1) / grid));
+	k_inflate_tok<<<grid, 32, I2_SMEM_BYTES(lanes), s>>>(d_archive, p->d_ents, p->d_est, p->d_status, p->d_inflate_list + first, count,
+		p->d_counter, c->d_tok_cache, p->d_tok_ofs + first, p->d_tokres + first, p->d_fb_list, p->d_counter + 52, lanes);
 	c->launches++;
 	CK(cudaGetLastError());
 	int rc;
 	switch (c->lz_ring) {
-	case 8192: rc = launch_lz<8192>(c, p, d_out, s); break;
-	case 16384: rc = launch_lz<16384>(c, p, d_out, s); break;
-	default: rc = launch_lz<4096>(c, p, d_out, s); break;
+	case 8192: rc = launch_lz<8192>(c, p, d_out, first, count, s); break;
+	case 16384: rc = launch_lz<16384>(c, p, d_out, first, count, s); break;
+	default: rc = launch_lz<4096>(c, p, d_out, first, count, s); break;
 	}
 	if (rc) {
 		return rc;
 	}
-	return launch_inflate_cfg(c, p, d_archive, d_out, 32, 4096, 0, p->n_inflate, 1, s, p->d_fb_list, p->d_counter + 52);
+	rc = launch_inflate_cfg(c, p, d_archive, d_out, 32, 4096, 0, count, 16, s, p->d_fb_list, p->d_counter + 52);
+	if (forked) {
+		CK(cudaStreamWaitEvent(s, c->ev_join, 0));
+	}
+	return rc;
 }
 
 static int dispatch_inflate(otz_ctx *c, otz_plan *p, const uint8_t *d_archive, uint8_t *d_out) {
@@ -640,7 +671,7 @@ static int dispatch_inflate(otz_ctx *c, otz_plan *p, const uint8_t *d_archive, u
 		if (rc) {
 			return rc;
 		}
-		rc = launch_inflate_cfg(c, p, d_archive, d_out, 32, 2048, n_big, n_small, 1, c->stream);
+		rc = launch_inflate_cfg(c, p, d_archive, d_out, 32, 2048, n_big, n_small, 16, c->stream);
 		CK(cudaEventRecord(c->ev_join, c->stream2));
 		CK(cudaStreamWaitEvent(c->stream, c->ev_join, 0));
 		return rc;
