@@ -493,6 +493,13 @@ def run_c5(args, dist: "Dist"):
     dist.close()
 
 
+DECODE_KERNELS = {
+    "c1": "k_inflate_tok + k_inflate_lz (+ k_inflate for declined / huge streams)",
+    "c3": "k_inflate_tok + k_inflate_lz (+ k_inflate for declined / huge streams)",
+    "c3w": "k_inflate_tok + k_inflate_lz (+ k_inflate for declined / huge streams)",
+    "c4": "k_zstdref", "c4z": "k_zstd", "c2": "k_store_copy",
+}
+
 WORKLOADS = {
     "c2": "configs[1]: STORE + CRC-32 verify only, 10,000 entries of 1 MiB random bytes",
     "c1": "configs[0]: 1,000-entry DEFLATE archive, 64 KiB text-like entries, CRC-32 check",
@@ -615,9 +622,13 @@ def main():
         k_ms = float(np.mean([p[idx[dom]] for p in prof])) if prof else float("nan")
         shares = {k: float(np.mean([p[i] for p in prof])) for k, i in idx.items()} if prof else {}
         achieved = wl["algo_bytes"] / (k_ms / 1e3) / GB
+        # DRAM bytes of one launch of the dominant kernel from the committed `ncu --set full` capture of this very
+        # configuration (tools/profile_final.sh writes the file); null when the entry count differs
         traffic = None
         try:
-            traffic = json.load(open(os.path.join(ROOT, "profiles", "roofline_traffic.json"))).get(args.workload)
+            tr = json.load(open(os.path.join(ROOT, "profiles", "roofline_traffic.json"))).get(args.workload)
+            if tr and int(tr.get("entries", -1)) == int(wl.get("n_entries", n)):
+                traffic = tr["traffic"]
         except Exception:
             pass
         line = {
@@ -629,7 +640,7 @@ def main():
                        "cache": "inputs larger than L2 (no flush needed)" if wl["algo_bytes"] > 256e6 else
                                 "inputs smaller than L2: steady-state L2-resident", "parallelism": "entries sharded by index, no collective",
                        "inflate_fallbacks": inflate_fallbacks},
-            "roofline": {"bound": "hbm", "kernel": {"crc": "k_crc_chunks", "decode": "k_inflate/k_zstdref/k_store_copy"}[dom],
+            "roofline": {"bound": "hbm", "kernel": {"crc": "k_crc_chunks", "decode": DECODE_KERNELS.get(args.workload, "decode")}[dom],
                          "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": traffic,
                          "peak_source": peak_src, "kernel_ms": k_ms, "phase_ms": shares},
             "e2e": {"value": e2e_value, "unit": "GB/s", "h2d_bytes_per_step": int(img.nbytes + tab.nbytes),

@@ -153,13 +153,13 @@ __global__ void __launch_bounds__(256, 2) k_store_copy(const uint8_t *__restrict
 	}
 }
 
-// Method 93, reference container: one warp per entry walks the block chain and copies payloads.
-__global__ void __launch_bounds__(256, 2) k_zstdref(const uint8_t *__restrict__ archive, uint8_t *__restrict__ out,
+// Method 93, reference container: one warp per entry walks the block chain and copies payloads (software-pipelined
+// 16-byte copies, 2-4 KiB in flight per warp).  The CRC is taken afterwards by k_crc_chunks from the output, most of
+// which is still in L2: a copy-only kernel needs a quarter of the registers of the fused one, so four times as many
+// warps keep loads in flight.
+__global__ void __launch_bounds__(256, 4) k_zstdref(const uint8_t *__restrict__ archive, uint8_t *__restrict__ out,
 	const otz_entry *__restrict__ ents, const OtzEntryState *__restrict__ est, int32_t *__restrict__ status,
-	const uint32_t *__restrict__ list, uint32_t n_list, uint32_t *__restrict__ acc, const OtzCrcTables *__restrict__ tabs) {
-	__shared__ __align__(16) uint32_t s_skip[16 * 256];
-	crc_tables_to_smem(s_skip, tabs);
-	__syncthreads();
+	const uint32_t *__restrict__ list, uint32_t n_list) {
 	const uint32_t warps_per_cta = blockDim.x >> 5;
 	const uint32_t total_warps = gridDim.x * warps_per_cta;
 	const int lane = threadIdx.x & 31;
@@ -174,7 +174,6 @@ __global__ void __launch_bounds__(256, 2) k_zstdref(const uint8_t *__restrict__ 
 		const uint32_t n = e.comp_size, cap = e.uncomp_size;
 		int32_t st = OTZ_ST_OK;
 		uint32_t ip = 5, op = 0;
-		uint32_t rtot = 0, mul_len = 0, mul = 0x80000000u;   // running remainder of the output; cached x^(8*mul_len)
 		if (n < 5) {
 			st = OTZ_ST_TRUNCATED;  // zstd:490-492
 		} else if (ld_le32(in) != 0xFD2FB528u) {
@@ -206,17 +205,6 @@ __global__ void __launch_bounds__(256, 2) k_zstdref(const uint8_t *__restrict__ 
 					break;
 				}
 				tile_copy<32>(dst + op, in + ip, bsz, lane);
-				if (bsz) {
-					// CRC of the payload from the source bytes (still in L2), appended to the running remainder:
-					// R(A||B) = R(A) * x^(8|B|) ^ R(B)
-					const uint32_t rb = bsz >= OTZ_CRC_FOLD_MIN ? crc_raw_warp_fold(in + ip, bsz, s_skip, tabs)
-					                                            : crc_raw_warp(in + ip, bsz, s_skip, tabs);
-					if (bsz != mul_len) {
-						mul_len = bsz;
-						mul = crc_xpow8(bsz, tabs->x2n);
-					}
-					rtot = crc_mulmod(rtot, mul) ^ rb;
-				}
 				ip += bsz;
 				op += bsz;
 				if (h & 1) {
@@ -232,8 +220,6 @@ __global__ void __launch_bounds__(256, 2) k_zstdref(const uint8_t *__restrict__ 
 				// not a consistent reference container: if it carries the Zstandard magic, k_zstd tries it as an
 				// RFC 8878 frame (the reference itself would reject it either way)
 				status[ei] = (n >= 4 && ld_le32(in) == 0xFD2FB528u) ? OTZ_ST_PENDING : st;
-			} else {
-				acc[ei] = rtot;
 			}
 		}
 	}

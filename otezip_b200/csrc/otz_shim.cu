@@ -72,7 +72,7 @@ struct otz_plan {
 	I2TokRes *d_tokres;
 	uint32_t *d_fb_list;       // entries phase A hands to k_inflate
 	uint32_t *d_zstd_list, n_zstd;
-	OtzCrcChunk *d_zchunks;    // CRC chunks of the method-93 entries (used for real Zstandard frames only)
+	OtzCrcChunk *d_zchunks;    // CRC chunks of the method-93 entries (reference containers and real Zstandard frames)
 	uint32_t n_zchunks;
 	uint8_t *d_zstd_lit;       // literal scratch of k_zstd, one slot per resident warp
 	uint32_t zstd_grid;
@@ -390,7 +390,7 @@ extern "C" int otz_plan_create(otz_ctx *c, const otz_entry *ents, uint32_t n, co
 		for (uint32_t i = 0; i < n; i++) {
 			const bool is_store = ents[i].method == OTZ_M_STORE;
 			if ((pass == 0) != is_store || ents[i].method == OTZ_M_ZSTD || (ents[i].flags & OTZ_EF_CHUNK)) {
-				continue;   // method 93 folds its CRC inside k_zstdref; chunk rows are CRC'd through their parent
+				continue;   // method 93 has its own chunk list (below); chunk rows are CRC'd through their parent
 			}
 			const uint32_t nc = (uint32_t)(((uint64_t)ents[i].uncomp_size + OTZ_CRC_CHUNK - 1) / OTZ_CRC_CHUNK);
 			for (uint32_t k = 0; k < nc; k++) {
@@ -714,8 +714,8 @@ extern "C" int otz_extract_run(otz_ctx *c, otz_plan *p, const uint8_t *d_archive
 		c->launches++;
 	}
 	if (p->n_zstd) {
-		k_zstdref<<<std::min((uint32_t)c->sm_count * 2, (p->n_zstd + 7) / 8), 256, 0, s>>>(d_archive, d_out, p->d_ents, p->d_est, p->d_status,
-			p->d_zstd_list, p->n_zstd, p->d_acc, c->d_tabs);
+		k_zstdref<<<std::min((uint32_t)c->sm_count * 4, (p->n_zstd + 7) / 8), 256, 0, s>>>(d_archive, d_out, p->d_ents, p->d_est, p->d_status,
+			p->d_zstd_list, p->n_zstd);
 		c->launches++;
 		// entries that are not a reference container but carry the Zstandard magic: RFC 8878 frames
 		const size_t zsmem = 4 * sizeof(ZstdSmem);
@@ -749,7 +749,7 @@ extern "C" int otz_extract_run(otz_ctx *c, otz_plan *p, const uint8_t *d_archive
 	}
 	if (p->n_zchunks) {
 		const uint32_t grid = std::min((uint32_t)c->sm_count * crc_ctas_per_sm(), (p->n_zchunks + 7) / 8);
-		k_crc_chunks<<<grid, 256, 0, s>>>(d_archive, d_out, p->d_ents, p->d_est, p->d_status, p->d_zchunks, p->n_zchunks, p->d_acc, c->d_tabs, 0, 1);
+		k_crc_chunks<<<grid, 256, 0, s>>>(d_archive, d_out, p->d_ents, p->d_est, p->d_status, p->d_zchunks, p->n_zchunks, p->d_acc, c->d_tabs, 0, 0);
 		c->launches++;
 	}
 	if (c->profile) {
