@@ -93,7 +93,7 @@ def workload(name: str, rank: int, n_entries: int | None, alloc):
     """-> dict(image, table, out_bytes, uncomp_bytes, algo_bytes, opts, desc)"""
     from otezip_b200 import synth
     from otezip_b200.native import default_opts
-    if name == "c2":
+    if name in ("c2", "c2x"):
         n = n_entries or 10000
         size = 1 << 20
 
@@ -103,6 +103,10 @@ def workload(name: str, rank: int, n_entries: int | None, alloc):
             return d, size, zlib.crc32(d) & 0xFFFFFFFF
         img, tab, out_bytes = build_archive_set(alloc, gen, n, 1250, 0)
         un = int(tab["uncomp_size"].astype(np.int64).sum())
+        if name == "c2x":   # STORE extract: payload copied to the arena, then CRC'd
+            return dict(image=img, table=tab, out_bytes=out_bytes, uncomp_bytes=un, algo_bytes=2 * un, opts=default_opts(),
+                        desc="STORE extract (copy + CRC-32), %d entries x 1 MiB random bytes (archive set of %d ZIP32 files)"
+                        % (n, (n + 1249) // 1250), dominant="decode")
         return dict(image=img, table=tab, out_bytes=0, uncomp_bytes=un, algo_bytes=un, opts=default_opts(verify_only=1),
                     desc="STORE + CRC-32 verify only, %d entries x 1 MiB random bytes (archive set of %d ZIP32 files)"
                     % (n, (n + 1249) // 1250), dominant="crc")
@@ -308,10 +312,10 @@ class Dist:
 def reference_sample_archive(wl_name: str, tmpdir: str):
     """A bounded sample of the workload as one ZIP32 file on disk (the reference reads FILE*)."""
     from otezip_b200 import synth
-    if wl_name == "c2":
+    if wl_name in ("c2", "c2x"):
         ms = synth.config_c2(64, 1 << 20, seed=2)
         what = "64 x 1 MiB STORE entries per thread per pass"
-    elif wl_name == "c1":
+    elif wl_name in ("c1", "c3w"):
         ms = synth.config_c1(8, 65536)
         what = "8 x 64 KiB DEFLATE entries per thread per pass"
     elif wl_name == "c3":
@@ -497,7 +501,7 @@ DECODE_KERNELS = {
     "c1": "k_inflate_tok + k_inflate_lz (+ k_inflate for declined / huge streams)",
     "c3": "k_inflate_tok + k_inflate_lz (+ k_inflate for declined / huge streams)",
     "c3w": "k_inflate_tok + k_inflate_lz (+ k_inflate for declined / huge streams)",
-    "c4": "k_zstdref", "c4z": "k_zstd", "c2": "k_store_copy",
+    "c4": "k_zstdref", "c4z": "k_zstd", "c2": "k_store_copy", "c2x": "k_store_copy",
 }
 
 WORKLOADS = {
@@ -507,6 +511,7 @@ WORKLOADS = {
     "c4": "configs[3]: method 93 decode of 256 KiB entries (reference container)",
     "c5": "configs[4]: archive creation, batched DEFLATE compress + CRC-32, 4 GiB synthetic corpus",
     "c3w": "configs[2] shape, archive written by this library (chunk-indexed DEFLATE entries)",
+    "c2x": "configs[1] shape, STORE entries extracted (copied to the arena) and CRC-checked",
     "c4z": "configs[3] shape with real Zstandard (RFC 8878) frames from libzstd level 3",
 }
 

@@ -124,14 +124,11 @@ __device__ __forceinline__ void tile_copy(uint8_t *__restrict__ dst, const uint8
 	}
 }
 
-// STORE extract: one warp per chunk of the shared chunk list.  The chunk is copied, then its CRC is folded
-// from the SOURCE bytes, which the copy has just pulled through L2 — HBM sees the payload once.
-__global__ void __launch_bounds__(256, 2) k_store_copy(const uint8_t *__restrict__ archive, uint8_t *__restrict__ out,
+// STORE extract: one warp per chunk of the shared chunk list, copy only (the CRC is taken by k_crc_chunks from the
+// output while it is still warm in L2; a copy-only kernel keeps four times as many warps, i.e. loads, in flight).
+__global__ void __launch_bounds__(256, 4) k_store_copy(const uint8_t *__restrict__ archive, uint8_t *__restrict__ out,
 	const otz_entry *__restrict__ ents, const OtzEntryState *__restrict__ est, const int32_t *__restrict__ status,
-	const OtzCrcChunk *__restrict__ chunks, uint32_t n_chunks, uint32_t *__restrict__ acc, const OtzCrcTables *__restrict__ tabs) {
-	__shared__ __align__(16) uint32_t s_skip[16 * 256];
-	crc_tables_to_smem(s_skip, tabs);
-	__syncthreads();
+	const OtzCrcChunk *__restrict__ chunks, uint32_t n_chunks) {
 	const uint32_t warps_per_cta = blockDim.x >> 5;
 	const uint32_t total_warps = gridDim.x * warps_per_cta;
 	const int lane = threadIdx.x & 31;
@@ -143,13 +140,7 @@ __global__ void __launch_bounds__(256, 2) k_store_copy(const uint8_t *__restrict
 		}
 		const uint64_t off = (uint64_t)ck.chunk * OTZ_CRC_CHUNK;
 		const uint64_t len = min((uint64_t)OTZ_CRC_CHUNK, (uint64_t)e.uncomp_size - off);
-		const uint8_t *src = archive + est[ck.entry].data_ofs + off;
-		tile_copy<32>(out + e.out_ofs + off, src, len, lane);
-		const uint32_t raw = len >= OTZ_CRC_FOLD_MIN ? crc_raw_warp_fold(src, len, s_skip, tabs) : crc_raw_warp(src, len, s_skip, tabs);
-		if (lane == 0) {
-			const uint64_t after = (uint64_t)e.uncomp_size - off - len;
-			atomicXor(&acc[ck.entry], after ? crc_mulmod(raw, crc_xpow8(after, tabs->x2n)) : raw);
-		}
+		tile_copy<32>(out + e.out_ofs + off, archive + est[ck.entry].data_ofs + off, len, lane);
 	}
 }
 

@@ -709,8 +709,8 @@ extern "C" int otz_extract_run(otz_ctx *c, otz_plan *p, const uint8_t *d_archive
 		CK(cudaEventRecord(pev[1], s));
 	}
 	if (p->n_store_chunks && !p->opts.verify_only) {
-		k_store_copy<<<std::min((uint32_t)c->sm_count * 2, (p->n_store_chunks + 7) / 8), 256, 0, s>>>(d_archive, d_out, p->d_ents, p->d_est,
-			p->d_status, p->d_chunks, p->n_store_chunks, p->d_acc, c->d_tabs);
+		k_store_copy<<<std::min((uint32_t)c->sm_count * 4, (p->n_store_chunks + 7) / 8), 256, 0, s>>>(d_archive, d_out, p->d_ents, p->d_est,
+			p->d_status, p->d_chunks, p->n_store_chunks);
 		c->launches++;
 	}
 	if (p->n_zstd) {
@@ -737,8 +737,8 @@ extern "C" int otz_extract_run(otz_ctx *c, otz_plan *p, const uint8_t *d_archive
 	if (c->profile) {
 		CK(cudaEventRecord(pev[2], s));
 	}
-	// STORE chunks were CRC'd by k_store_copy unless they are verified in place
-	const uint32_t crc_first = p->opts.verify_only ? 0u : p->n_store_chunks;
+	// every chunk: STORE payloads in place when verify_only, else from the arena
+	const uint32_t crc_first = 0u;
 	if (p->n_chunks > crc_first) {
 		// persistent: exactly the resident CTAs (register-limited), each striding over the chunk list
 		const uint32_t nc = p->n_chunks - crc_first;
