@@ -116,6 +116,78 @@ struct ZsBack {
 	}
 };
 
+// ---- word-based backward reader for the two hot loops (Huffman literals, FSE sequences).  The stream is read as
+// aligned 32-bit words; the three words that end at the current position live in registers, so the next 64 bits
+// below the position are two funnel shifts away and a whole sequence (three extra-bit fields + three state
+// updates) is ONE window read instead of six cache-checked reads.
+struct ZsBackW {
+	const uint32_t *w;   // base & ~3
+	int32_t low;         // 8 * (base & 3): bits of word 0 below it are not stream bits
+	int32_t apos;        // bit index from w, one past the next bit to read (= unread bits + low)
+	int32_t k;           // word index of w2
+	uint32_t w0, w1, w2;
+
+	__device__ __forceinline__ uint32_t load(int32_t i) const {
+		if (i < 0) {
+			return 0u;   // below the stream: zeros (RFC 8878 4.1: a short read is zero filled)
+		}
+		const uint32_t v = __ldg(w + i);
+		return i == 0 ? (v >> low) << low : v;
+	}
+	__device__ __forceinline__ void reload() {
+		k = (apos - 1) >> 5;
+		w2 = load(k);
+		w1 = load(k - 1);
+		w0 = load(k - 2);
+	}
+	__device__ __forceinline__ bool init(const uint8_t *base, uint32_t n) {
+		const uint64_t a = reinterpret_cast<uint64_t>(base);
+		w = reinterpret_cast<const uint32_t *>(a & ~3ull);
+		low = (int32_t)(a & 3) * 8;
+		apos = low;
+		k = -1;
+		w0 = w1 = w2 = 0;
+		if (n == 0 || base[n - 1] == 0) {
+			return false;
+		}
+		apos = low + (int32_t)(8 * (n - 1) + (31 - __clz((uint32_t)base[n - 1])));   // the highest set bit is the end mark
+		reload();
+		return true;
+	}
+	__device__ __forceinline__ int32_t pos() const { return apos - low; }   // bits still unread (negative: over-read)
+	// the 64 bits below the position, top-aligned
+	__device__ __forceinline__ uint64_t top64() const {
+		const uint32_t r = (uint32_t)(32 * (k + 1) - apos) & 31u;
+		const uint32_t hi = __funnelshift_l(w1, w2, r), lo = __funnelshift_l(w0, w1, r);
+		return ((uint64_t)hi << 32) | lo;
+	}
+	__device__ __forceinline__ void skip(uint32_t nbits) {
+		apos -= (int32_t)nbits;
+		const int32_t nk = (apos - 1) >> 5;
+		if (nk != k) {
+			if (nk == k - 1) {
+				w2 = w1;
+				w1 = w0;
+				w0 = load(k - 3);
+				k = nk;
+			} else {
+				reload();
+			}
+		}
+	}
+	__device__ __forceinline__ uint32_t read(uint32_t nbits) {   // nbits <= 32
+		const uint64_t x = top64();
+		skip(nbits);
+		return nbits ? (uint32_t)(x >> (64u - nbits)) : 0u;
+	}
+};
+// take the top n (<= 32) bits of x and shift them out
+__device__ __forceinline__ uint32_t zs_take(uint64_t &x, uint32_t n) {
+	const uint32_t v = n ? (uint32_t)(x >> (64u - n)) : 0u;
+	x <<= n;
+	return v;
+}
+
 // FSE_readNCount: normalised counts from a table description; returns bytes consumed, 0 on error
 __device__ uint32_t zs_read_ncount(const uint8_t *p, uint32_t n, int16_t *norm, uint32_t max_sym, uint32_t max_log, uint32_t *log_out,
 	uint32_t *nsym_out) {
@@ -324,17 +396,28 @@ __device__ uint32_t zs_read_huf(ZstdSmem &S, const uint8_t *p, uint32_t n) {
 
 // one Huffman-coded stream -> dst[0..count)
 __device__ bool zs_huf_stream(const ZstdSmem &S, const uint8_t *p, uint32_t n, uint8_t *dst, uint32_t count) {
-	ZsBack b;
+	ZsBackW b;
 	if (!b.init(p, n)) {
 		return false;
 	}
-	const uint32_t log = S.huf_log;
-	for (uint32_t i = 0; i < count; i++) {
-		const uint32_t e = S.huf[b.peek(log)];
-		b.pos -= (int32_t)(e & 0xFF);
-		dst[i] = (uint8_t)(e >> 8);
+	const uint32_t log = S.huf_log;   // <= 11: five symbols fit one 64-bit window
+	uint32_t i = 0;
+	while (i < count) {
+		uint64_t x = b.top64();
+		uint32_t used = 0;
+#pragma unroll
+		for (int j = 0; j < 5; j++) {
+			if (i < count) {
+				const uint32_t e = S.huf[(uint32_t)(x >> (64u - log))];
+				const uint32_t nb = e & 0xFF;
+				dst[i++] = (uint8_t)(e >> 8);
+				x <<= nb;
+				used += nb;
+			}
+		}
+		b.skip(used);
 	}
-	return b.pos == 0;
+	return b.pos() == 0;
 }
 
 // sequence table for one of LL / OF / ML according to its compression mode; returns bytes consumed or -1
@@ -690,7 +773,7 @@ __device__ int32_t zstd_decode_entry(ZstdSmem &S, const uint8_t *__restrict__ in
 					}
 					const uint32_t so = S.seq_start;
 					// lane 0 owns the bitstream and the three states
-					ZsBack b;
+					ZsBackW b;
 					uint32_t st_ll = 0, st_of = 0, st_ml = 0;
 					if (lane == 0) {
 						if (!b.init(sp + so, srem - so)) {
@@ -716,9 +799,43 @@ __device__ int32_t zstd_decode_entry(ZstdSmem &S, const uint8_t *__restrict__ in
 									S.err = OTZ_ST_DATA;
 									break;
 								}
-								const uint32_t ofv = (1u << oc) + b.read(oc);
-								const uint32_t mlv = c_zs_ml_base[mc] + b.read(c_zs_ml_bits[mc]);
-								const uint32_t llv = c_zs_ll_base[lc] + b.read(c_zs_ll_bits[lc]);
+								// one window for the whole sequence: three extra-bit fields, then (unless it is the last
+								// sequence) the three state updates, in the RFC 8878 4.1.1 order
+								const bool last_seq = done + k + 1 >= nseq;
+								const uint32_t n_ml = c_zs_ml_bits[mc], n_ll = c_zs_ll_bits[lc];
+								const uint32_t u_ll = last_seq ? 0u : (el >> 8) & 0xFF, u_ml = last_seq ? 0u : (em >> 8) & 0xFF,
+								               u_of = last_seq ? 0u : (eo >> 8) & 0xFF;
+								uint64_t x = b.top64();
+								if (oc + n_ml + n_ll + u_ll + u_ml + u_of > 64u) {
+									// (offset codes of 30+ bits: take the offset field on its own; the rest is at most 58 bits)
+									const uint32_t f = zs_take(x, oc);
+									b.skip(oc);
+									const uint64_t y = b.top64();
+									b.skip(n_ml + n_ll + u_ll + u_ml + u_of);
+									uint64_t yy = y;
+									const uint32_t ofv_ = (1u << oc) + f;
+									const uint32_t mlv_ = c_zs_ml_base[mc] + zs_take(yy, n_ml);
+									const uint32_t llv_ = c_zs_ll_base[lc] + zs_take(yy, n_ll);
+									S.seq_ll[k] = llv_;
+									S.seq_ml[k] = mlv_;
+									S.seq_of[k] = ofv_;   // raw offset value; resolved below
+									if (!last_seq) {
+										st_ll = (el >> 16) + zs_take(yy, u_ll);
+										st_ml = (em >> 16) + zs_take(yy, u_ml);
+										st_of = (eo >> 16) + zs_take(yy, u_of);
+									}
+								} else {
+									b.skip(oc + n_ml + n_ll + u_ll + u_ml + u_of);
+									S.seq_of[k] = (1u << oc) + zs_take(x, oc);
+									S.seq_ml[k] = c_zs_ml_base[mc] + zs_take(x, n_ml);
+									S.seq_ll[k] = c_zs_ll_base[lc] + zs_take(x, n_ll);
+									if (!last_seq) {
+										st_ll = (el >> 16) + zs_take(x, u_ll);
+										st_ml = (em >> 16) + zs_take(x, u_ml);
+										st_of = (eo >> 16) + zs_take(x, u_of);
+									}
+								}
+								const uint32_t ofv = S.seq_of[k], mlv = S.seq_ml[k], llv = S.seq_ll[k];
 								uint32_t offset;
 								if (ofv > 3) {
 									offset = ofv - 3;
@@ -742,20 +859,14 @@ __device__ int32_t zstd_decode_entry(ZstdSmem &S, const uint8_t *__restrict__ in
 										rep1 = offset;
 									}
 								}
-								S.seq_ll[k] = llv;
-								S.seq_ml[k] = mlv;
 								S.seq_of[k] = offset;
-								if (done + k + 1 < nseq) {   // state updates: LL, ML, OF (RFC 8878 4.1.1 decoding order)
-									st_ll = (el >> 16) + b.read((el >> 8) & 0xFF);
-									st_ml = (em >> 16) + b.read((em >> 8) & 0xFF);
-									st_of = (eo >> 16) + b.read((eo >> 8) & 0xFF);
-								}
-								if (b.pos < 0) {
+								(void)mlv;
+								if (b.pos() < 0) {
 									S.err = OTZ_ST_DATA;
 									break;
 								}
 							}
-							if (done + nb == nseq && b.pos != 0 && !S.err) {
+							if (done + nb == nseq && b.pos() != 0 && !S.err) {
 								S.err = OTZ_ST_DATA;   // the bitstream must be consumed exactly
 							}
 						}
