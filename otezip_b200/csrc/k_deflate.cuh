@@ -311,13 +311,20 @@ __global__ void __launch_bounds__(256) k_deflate_chunks(const uint8_t *__restric
 				const uint32_t c = cand - 1;
 				const uint32_t maxl = min((uint32_t)DFL_MAX_MATCH, n - p);
 				uint32_t l = 0;
+				// 8 bytes per trip: the eight word loads of a trip are in flight together (the bytes read beyond maxl
+				// lie inside the padded input buffer and are cut off below)
 				while (l < maxl) {
-					const uint32_t x = dfl_word(w, sh0 + c + l) ^ dfl_word(w, sh0 + p + l);
-					if (x) {
-						l += (__ffs(x) - 1) >> 3;
+					const uint32_t x0 = dfl_word(w, sh0 + c + l) ^ dfl_word(w, sh0 + p + l);
+					const uint32_t x1 = dfl_word(w, sh0 + c + l + 4) ^ dfl_word(w, sh0 + p + l + 4);
+					if (x0) {
+						l += (__ffs(x0) - 1) >> 3;
 						break;
 					}
-					l += 4;
+					if (x1) {
+						l += 4 + ((__ffs(x1) - 1) >> 3);
+						break;
+					}
+					l += 8;
 				}
 				l = min(l, maxl);
 				if (l >= DFL_MIN_MATCH) {
