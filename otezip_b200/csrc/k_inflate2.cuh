@@ -889,7 +889,8 @@ template <int W>
 struct __align__(16) I2LzSmem {
 	uint8_t ring[W];
 	uint8_t stage[2][I2_STAGE];
-	uint2 far_l[2][32];    // {destination (linear), distance-1 | length << 15 | staging vector << 24 (127 = fetch directly)}
+	uint2 far_l[2][32];    // {destination (linear), length | staging vector << 9 (127 = fetch directly)}
+	uint32_t far_s[2][32]; // source of the far match (linear)
 	uint2 near_l[2][32];   // {ring index of the destination | length << 16, ring index of the source | distance << 16}
 };
 
@@ -943,16 +944,18 @@ struct I2Batch {
 
 // scan records [b, b + 32) (this lane holds record b + lane in `rec`), write the match descriptors of the batch into
 // list buffer `buf` and start the copies of its far sources into staging buffer `buf`.
-template <int W>
-__device__ __forceinline__ I2Batch i2_scan_batch(I2LzSmem<W> &S, int buf, uint32_t rec, uint32_t b, uint32_t nseq, uint32_t q, uint32_t lp,
-	const uint8_t *__restrict__ lits, const uint8_t *gbase, uint32_t lane) {
+// WIDE: 8-byte records {literal run | (length - 3) << 9, distance} (Zstandard: distances beyond 32 KiB); `rec` is the first
+// word, `wdist` the second.  Otherwise the distance sits in rec[31:17].
+template <int W, bool WIDE>
+__device__ __forceinline__ I2Batch i2_scan_batch(I2LzSmem<W> &S, int buf, uint32_t rec, uint32_t wdist, uint32_t b, uint32_t nseq, uint32_t q,
+	uint32_t lp, const uint8_t *__restrict__ lits, const uint8_t *gbase, uint32_t lane) {
 	constexpr uint32_t MASK = I2Ring<W>::MASK, SPAN_MAX = I2Ring<W>::SPAN_MAX;
 	const uint32_t lt_mask = (1u << lane) - 1u;
 	I2Batch B;
 	const bool have = b + lane < nseq;
 	const uint32_t lr = have ? rec & 511u : 0u;
 	const uint32_t ml = (have && lr != I2_SEQ_ESC) ? ((rec >> 9) & 255u) + 3u : 0u;
-	const uint32_t dist = (rec >> 17) + 1u;
+	const uint32_t dist = WIDE ? wdist : (rec >> 17) + 1u;
 	uint32_t lsum = lr, osum = lr + ml;
 #pragma unroll
 	for (int d = 1; d < 32; d <<= 1) {
@@ -990,7 +993,7 @@ __device__ __forceinline__ I2Batch i2_scan_batch(I2LzSmem<W> &S, int buf, uint32
 	B.n_far = __popc(far_m);
 	B.n_near = __popc(near_m);
 	if (is_match && !is_far) {
-		S.near_l[buf][__popc(near_m & lt_mask)] = make_uint2((mq & MASK) | (ml << 16), ((mq - dist) & MASK) | (dist << 16));
+		S.near_l[buf][__popc(near_m & lt_mask)] = make_uint2((mq & MASK) | (ml << 16), ((mq - dist) & MASK) | (dist << 16));   // near: dist < W <= 16 KiB
 	}
 	if (far_m) {
 		// staging vectors per far match (the source is copied as whole 16-byte vectors)
@@ -1006,14 +1009,16 @@ __device__ __forceinline__ I2Batch i2_scan_batch(I2LzSmem<W> &S, int buf, uint32
 		}
 		if (is_far) {
 			const uint32_t cst = incl <= I2_STAGE / 16u ? incl - nch : 127u;
-			S.far_l[buf][__popc(far_m & lt_mask)] = make_uint2(mq, (dist - 1u) | (ml << 15) | (cst << 24));
+			const uint32_t j = __popc(far_m & lt_mask);
+			S.far_l[buf][j] = make_uint2(mq, ml | (cst << 9));
+			S.far_s[buf][j] = mq - dist;
 		}
 		__syncwarp();
 		for (uint32_t f = 0; f < B.n_far; f++) {
 			const uint2 d = S.far_l[buf][f];
-			const uint32_t cst = d.y >> 24;
+			const uint32_t cst = d.y >> 9;
 			if (cst != 127u) {
-				const uint32_t src = d.x - (d.y & 0x7FFFu) - 1u, len = (d.y >> 15) & 511u;
+				const uint32_t src = S.far_s[buf][f], len = d.y & 511u;
 				const uint32_t n = ((src & 15u) + len + 15u) >> 4;
 				if (lane < n) {
 					const uint32_t sa = (uint32_t)__cvta_generic_to_shared(&S.stage[buf][16u * (cst + lane)]);
@@ -1026,7 +1031,7 @@ __device__ __forceinline__ I2Batch i2_scan_batch(I2LzSmem<W> &S, int buf, uint32
 	return B;
 }
 
-template <int W>
+template <int W, bool WIDE>
 __global__ void __launch_bounds__(128) k_inflate_lz(uint8_t *__restrict__ out, const otz_entry *__restrict__ ents, const uint32_t *__restrict__ list,
 	uint32_t n_list, uint32_t *__restrict__ work_counter, const uint8_t *__restrict__ scratch, const uint64_t *__restrict__ tok_ofs,
 	const I2TokRes *__restrict__ tokres, int32_t *__restrict__ status, uint32_t *__restrict__ produced_out) {
@@ -1059,11 +1064,26 @@ __global__ void __launch_bounds__(128) k_inflate_lz(uint8_t *__restrict__ out, c
 		uint32_t q = mis, qf = mis;   // linear write position / position up to which HBM holds the data
 		uint32_t lp = 0, b = 0;       // literals / records consumed
 		__syncwarp();
-		// records b + lane (recA) and b + 32 + lane (recB)
-		uint32_t recA = lane < nseq ? __ldcs(seq_end - 1 - lane) : 0u;
-		uint32_t recB = 32u + lane < nseq ? __ldcs(seq_end - 33 - lane) : 0u;
+		// records b + lane (recA) and b + 32 + lane (recB); WIDE: their second words in offA / offB
+		const uint2 *const seq_end2 = reinterpret_cast<const uint2 *>(seq_end);
+		uint32_t recA = 0, recB = 0, offA = 0, offB = 0;
+		if (WIDE) {
+			if (lane < nseq) {
+				const uint2 r = seq_end2[-1 - (int32_t)lane];
+				recA = r.x;
+				offA = r.y;
+			}
+			if (32u + lane < nseq) {
+				const uint2 r = seq_end2[-33 - (int32_t)lane];
+				recB = r.x;
+				offB = r.y;
+			}
+		} else {
+			recA = lane < nseq ? __ldcs(seq_end - 1 - lane) : 0u;
+			recB = 32u + lane < nseq ? __ldcs(seq_end - 33 - lane) : 0u;
+		}
 		int buf = 0;
-		I2Batch cur = i2_scan_batch<W>(S, 0, recA, 0u, nseq, q, lp, lits, gbase, lane);
+		I2Batch cur = i2_scan_batch<W, WIDE>(S, 0, recA, offA, 0u, nseq, q, lp, lits, gbase, lane);
 		while (cur.ntake) {
 			// ---- scan batch k+1 and start its far copies
 			const uint32_t b2 = b + cur.ntake;
@@ -1071,9 +1091,20 @@ __global__ void __launch_bounds__(128) k_inflate_lz(uint8_t *__restrict__ out, c
 				const uint32_t j = cur.ntake + lane;
 				const uint32_t fromA = __shfl_sync(0xFFFFFFFFu, recA, j & 31u), fromB = __shfl_sync(0xFFFFFFFFu, recB, j & 31u);
 				recA = j < 32u ? fromA : fromB;
-				recB = b2 + 32u + lane < nseq ? __ldcs(seq_end - 33 - (b2 + lane)) : 0u;
+				if (WIDE) {
+					const uint32_t oA = __shfl_sync(0xFFFFFFFFu, offA, j & 31u), oB = __shfl_sync(0xFFFFFFFFu, offB, j & 31u);
+					offA = j < 32u ? oA : oB;
+					recB = offB = 0;
+					if (b2 + 32u + lane < nseq) {
+						const uint2 r = seq_end2[-33 - (int32_t)(b2 + lane)];
+						recB = r.x;
+						offB = r.y;
+					}
+				} else {
+					recB = b2 + 32u + lane < nseq ? __ldcs(seq_end - 33 - (b2 + lane)) : 0u;
+				}
 			}
-			const I2Batch nxt = i2_scan_batch<W>(S, buf ^ 1, recA, b2, nseq, cur.q_end, lp + cur.tot_l, lits, gbase, lane);
+			const I2Batch nxt = i2_scan_batch<W, WIDE>(S, buf ^ 1, recA, offA, b2, nseq, cur.q_end, lp + cur.tot_l, lits, gbase, lane);
 			// ---- execute batch k: its far sources have landed in stage[buf]
 			asm volatile("cp.async.wait_group 1;" ::: "memory");
 			__syncwarp();
@@ -1093,7 +1124,7 @@ __global__ void __launch_bounds__(128) k_inflate_lz(uint8_t *__restrict__ out, c
 			for (uint32_t f = 0; f < cur.n_far; f++) {
 				const uint2 d = dn;
 				dn = S.far_l[buf][(f + 1u) & 31u];   // next descriptor in flight while this match is copied
-				const uint32_t cst = d.y >> 24, len = (d.y >> 15) & 511u, src = d.x - (d.y & 0x7FFFu) - 1u;
+				const uint32_t cst = d.y >> 9, len = d.y & 511u, src = S.far_s[buf][f];
 				if (cst != 127u) {
 					const uint8_t *sp = &S.stage[buf][16u * cst + (src & 15u)];
 					if (lane < len) {

@@ -50,6 +50,9 @@ struct otz_ctx {
 	int inflate_mode;   // OTZ_INFLATE_MODE: 0 = two-phase (k_inflate_tok + k_inflate_lz, k_inflate as fallback), 1 = k_inflate only
 	int lz_ring;        // OTZ_LZ_RING: ring bytes per warp of k_inflate_lz (4096 / 8192 / 16384)
 	uint32_t last_fallbacks;   // DEFLATE streams of the last collected run that phase A handed to k_inflate
+	int zstd_legacy;        // OTZ_ZSTD_MODE=legacy: warp-per-entry k_zstd instead of k_zstd_tok + k_inflate_lz
+	uint8_t *d_ztok_cache;  // grow-only token scratch of the two-phase Zstandard path
+	uint64_t ztok_cache_bytes;
 	uint8_t *d_tok_cache;   // grow-only token scratch of the two-phase inflate (literals + sequence records)
 	uint64_t tok_cache_bytes;
 };
@@ -74,6 +77,9 @@ struct otz_plan {
 	uint32_t *d_zstd_list, n_zstd;
 	OtzCrcChunk *d_zchunks;    // CRC chunks of the method-93 entries (reference containers and real Zstandard frames)
 	uint32_t n_zchunks;
+	uint64_t *d_ztok_ofs;      // two-phase Zstandard: token scratch offset of every method-93 list slot (+ end)
+	uint64_t ztok_bytes;
+	I2TokRes *d_ztokres;
 	uint8_t *d_zstd_lit;       // literal scratch of k_zstd, one slot per resident warp
 	uint32_t zstd_grid;
 	uint32_t *d_counter;
@@ -187,6 +193,8 @@ extern "C" int otz_ctx_create(int device, otz_ctx **out) {
 	c->inflate_ring = t ? atoi(t) : 0;
 	t = getenv("OTZ_INFLATE_MODE");
 	c->inflate_mode = (t && !strcmp(t, "legacy")) ? 1 : 0;
+	t = getenv("OTZ_ZSTD_MODE");
+	c->zstd_legacy = (t && !strcmp(t, "legacy")) ? 1 : 0;
 	t = getenv("OTZ_LZ_RING");
 	c->lz_ring = t ? atoi(t) : 4096;
 	*out = c;
@@ -204,6 +212,7 @@ extern "C" void otz_ctx_destroy(otz_ctx *c) {
 	cudaFree(c->d_arch_cache);
 	cudaFree(c->d_out_cache);
 	cudaFree(c->d_tok_cache);
+	cudaFree(c->d_ztok_cache);
 	cudaEventDestroy(c->ev0);
 	cudaEventDestroy(c->ev1);
 	for (auto &slot : c->pev) {
@@ -365,6 +374,8 @@ extern "C" void otz_plan_destroy(otz_ctx *c, otz_plan *p) {
 	cudaFree(p->d_zstd_list);
 	cudaFree(p->d_zchunks);
 	cudaFree(p->d_zstd_lit);
+	cudaFree(p->d_ztok_ofs);
+	cudaFree(p->d_ztokres);
 	cudaFree(p->d_counter);
 	delete p;
 }
@@ -471,6 +482,17 @@ extern "C" int otz_plan_create(otz_ctx *c, const otz_entry *ents, uint32_t n, co
 		return fail_cuda(cudaGetLastError(), "cudaMalloc(plan)");
 	}
 	if (p->n_zstd) {
+		std::vector<uint64_t> zofs(zst.size() + 1);
+		zofs[0] = 0;
+		for (size_t k = 0; k < zst.size(); k++) {
+			zofs[k + 1] = zofs[k] + zs_scratch_bytes(ents[zst[k]].uncomp_size);
+		}
+		p->ztok_bytes = zofs.back();
+		if ((rc = upload(&p->d_ztok_ofs, zofs, c->stream)) || cudaMalloc(&p->d_ztokres, zst.size() * sizeof(I2TokRes)) != cudaSuccess) {
+			otz_plan_destroy(c, p);
+			return rc ? rc : fail_cuda(cudaGetLastError(), "cudaMalloc(two-phase zstd lists)");
+		}
+		CK(cudaStreamSynchronize(c->stream));   // zofs dies here
 		p->zstd_grid = std::min<uint32_t>((uint32_t)c->sm_count * 5, (p->n_zstd + 3) / 4);   // 5 CTAs x 4 warps per SM (shared memory)
 		if (cudaMalloc(&p->d_zstd_lit, (size_t)p->zstd_grid * 4 * (ZS_BLOCK_MAX + 64)) != cudaSuccess) {
 			otz_plan_destroy(c, p);
@@ -540,21 +562,22 @@ static int launch_inflate_cfg(otz_ctx *c, otz_plan *p, const uint8_t *d_archive,
 // share the machine; small entries get the big ring only when there are too few of them to fill the SMs.
 template <int W>
 static int launch_lz(otz_ctx *c, otz_plan *p, uint8_t *d_out, uint32_t first, uint32_t count, cudaStream_t st) {
+	auto kern = k_inflate_lz<W, false>;
 	const int warps = 4;
 	const size_t smem = warps * sizeof(I2LzSmem<W>);
 	static bool attr_done = false;
 	if (!attr_done) {
-		CK(cudaFuncSetAttribute(k_inflate_lz<W>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+		CK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
 		attr_done = true;
 	}
 	int per_sm = 0;
-	CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_inflate_lz<W>, 32 * warps, smem));
+	CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, 32 * warps, smem));
 	if (per_sm < 1) {
 		snprintf(g_err, sizeof(g_err), "k_inflate_lz<%d> does not fit an SM", W);
 		return OTZ_ERR_CUDA;
 	}
 	const uint32_t grid = std::max(1u, std::min((uint32_t)(c->sm_count * per_sm), (count + warps - 1) / warps));
-	k_inflate_lz<W><<<grid, 32 * warps, smem, st>>>(d_out, p->d_ents, p->d_inflate_list + first, count, p->d_counter + 48, c->d_tok_cache,
+	kern<<<grid, 32 * warps, smem, st>>>(d_out, p->d_ents, p->d_inflate_list + first, count, p->d_counter + 48, c->d_tok_cache,
 		p->d_tok_ofs + first, p->d_tokres + first, p->d_status, p->d_produced);
 	c->launches++;
 	CK(cudaGetLastError());
@@ -717,16 +740,53 @@ extern "C" int otz_extract_run(otz_ctx *c, otz_plan *p, const uint8_t *d_archive
 		k_zstdref<<<std::min((uint32_t)c->sm_count * 4, (p->n_zstd + 7) / 8), 256, 0, s>>>(d_archive, d_out, p->d_ents, p->d_est, p->d_status,
 			p->d_zstd_list, p->n_zstd);
 		c->launches++;
-		// entries that are not a reference container but carry the Zstandard magic: RFC 8878 frames
-		const size_t zsmem = 4 * sizeof(ZstdSmem);
-		static bool zattr = false;
-		if (!zattr) {
-			CK(cudaFuncSetAttribute(k_zstd, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)zsmem));
-			zattr = true;
+		// entries that are not a reference container but carry the Zstandard magic: RFC 8878 frames.
+		// Two-phase (lane-per-entry tokenizer + the LZ executor of the inflate path) when the token scratch can be
+		// had and OTZ_ZSTD_MODE is not "legacy"; else the warp-per-entry decoder.
+		bool two_phase = !c->zstd_legacy;
+		if (two_phase && p->ztok_bytes + 64 > c->ztok_cache_bytes) {
+			CK(cudaStreamSynchronize(c->stream));
+			cudaFree(c->d_ztok_cache);
+			c->d_ztok_cache = nullptr;
+			c->ztok_cache_bytes = 0;
+			if (cudaMalloc(&c->d_ztok_cache, p->ztok_bytes + 64) == cudaSuccess) {
+				c->ztok_cache_bytes = p->ztok_bytes + 64;
+			} else {
+				cudaGetLastError();
+				two_phase = false;
+			}
 		}
-		k_zstd<<<p->zstd_grid, 128, zsmem, s>>>(d_archive, d_out, p->d_ents, p->d_est, p->d_status, p->d_zstd_list, p->n_zstd, p->d_zstd_lit,
-			p->d_counter + 32);
-		c->launches++;
+		if (two_phase) {
+			static bool zattr2 = false;
+			const uint32_t zl = 5;   // lanes (entries) per warp: 4 warps x 5 slots of 9.7 KB per SM
+			const int zsmem2 = (int)zl * ZS_LANE_STRIDE;
+			if (!zattr2) {
+				CK(cudaFuncSetAttribute(k_zstd_tok, cudaFuncAttributeMaxDynamicSharedMemorySize, zsmem2));
+				CK(cudaFuncSetAttribute(k_inflate_lz<4096, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(4 * sizeof(I2LzSmem<4096>))));
+				zattr2 = true;
+			}
+			int per_sm = 0;
+			CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_zstd_tok, 32, zsmem2));
+			const uint32_t zgrid = std::max(1u, std::min((uint32_t)(c->sm_count * std::max(per_sm, 1)), (p->n_zstd + zl - 1) / zl));
+			k_zstd_tok<<<zgrid, 32, zsmem2, s>>>(d_archive, p->d_ents, p->d_est, p->d_status, p->d_zstd_list, p->n_zstd, c->d_ztok_cache,
+				p->d_ztok_ofs, p->d_ztokres, p->d_counter + 32, zl);
+			c->launches++;
+			CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_inflate_lz<4096, true>, 128, 4 * sizeof(I2LzSmem<4096>)));
+			const uint32_t lgrid = std::max(1u, std::min((uint32_t)(c->sm_count * std::max(per_sm, 1)), (p->n_zstd + 3) / 4));
+			k_inflate_lz<4096, true><<<lgrid, 128, 4 * sizeof(I2LzSmem<4096>), s>>>(d_out, p->d_ents, p->d_zstd_list, p->n_zstd, p->d_counter + 36,
+				c->d_ztok_cache, p->d_ztok_ofs, p->d_ztokres, p->d_status, p->d_produced);
+			c->launches++;
+		} else {
+			const size_t zsmem = 4 * sizeof(ZstdSmem);
+			static bool zattr = false;
+			if (!zattr) {
+				CK(cudaFuncSetAttribute(k_zstd, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)zsmem));
+				zattr = true;
+			}
+			k_zstd<<<p->zstd_grid, 128, zsmem, s>>>(d_archive, d_out, p->d_ents, p->d_est, p->d_status, p->d_zstd_list, p->n_zstd, p->d_zstd_lit,
+				p->d_counter + 32);
+			c->launches++;
+		}
 	}
 	if (p->n_inflate) {
 		int rc = dispatch_inflate(c, p, d_archive, d_out);

@@ -22,6 +22,21 @@ def zs():
         pytest.skip("libzstd.so.1 not present")
 
 
+@pytest.fixture(params=["twophase", "legacy"])
+def zctx(request):
+    """A context per Zstandard decoder: lane-per-entry tokenizer + k_inflate_lz (default) and the warp-per-entry k_zstd."""
+    import os
+    from otezip_b200 import Ctx
+    if request.param == "legacy":
+        os.environ["OTZ_ZSTD_MODE"] = "legacy"
+    try:
+        c = Ctx(0)
+    finally:
+        os.environ.pop("OTZ_ZSTD_MODE", None)
+    yield c
+    c.close()
+
+
 def sources():
     out = [b"", b"a", b"hello zstd\n", b"A" * 100000, bytes(range(256)) * 40, synth.random_bytes(5000, 1), synth.random_bytes(300000, 2)]
     out += [synth.jsonlog_text(n, 50 + i) for i, n in enumerate([100, 4096, 70000, 131072, 131073, 262144, 700000])]
@@ -29,7 +44,8 @@ def sources():
     return out
 
 
-def test_zstd_frames_decode_bit_exact(ctx, zs, reflib):
+def test_zstd_frames_decode_bit_exact(zctx, zs, reflib):
+    ctx = zctx
     ms, want = [], []
     for i, d in enumerate(sources()):
         for lvl in (1, 3, 9, 19):
@@ -63,7 +79,8 @@ def test_zstd_frames_decode_bit_exact(ctx, zs, reflib):
         assert (g is None) == m.name.startswith("z") and (g is None or g == d)
 
 
-def test_corrupt_zstd_frames_are_rejected(ctx, zs):
+def test_corrupt_zstd_frames_are_rejected(zctx, zs):
+    ctx = zctx
     d = synth.jsonlog_text(200000, 77)
     f = zs.compress(d, 3)
     ms = []
