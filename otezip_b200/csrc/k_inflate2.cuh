@@ -341,6 +341,42 @@ __device__ __noinline__ int i2_build_table(I2WarpScratch &S, const uint32_t (&le
 }
 
 // ------------------------------------------------------------------------------------------------
+// Segmented decode of HUGE streams.  A stream advances one symbol per step wherever it is decoded, so one 16 MiB entry
+// (1.1 M symbols) sets the critical path of a whole batch.  Its entropy stage, however, only needs to know where
+// blocks start: k_block_search tests every bit offset of the stream for a plausible dynamic-block header (the
+// checks are so selective that false positives are practically absent), each candidate becomes a SEGMENT that a lane
+// of k_inflate_tok<true> decodes from its candidate to the next live one, and k_seg_stitch accepts the stream only if
+// the segments chain exactly (each one ends where the next starts, the last one with the final block, the sizes add
+// up, no match reaches before the stream).  Tokens do not care where they were produced: k_inflate_lz walks the
+// chain.  Nothing depends on the search being right — a wrong candidate is skipped (the decoder that passes it marks
+// it dead) or fails the chain, and the stream then goes to k_inflate like every other declined stream.
+#define I2_MAXSEG 256
+#define I2_SEGF_OK 1u
+#define I2_SEGF_FINAL 2u
+#define I2_SEGF_DEAD 4u
+#define I2_SEGF_REF_EOB 8u
+
+struct I2SegRes {
+	uint32_t nseq, nlit;    // tokens of the segment
+	uint32_t produced;      // output bytes of the segment
+	uint32_t end_bit;       // bit position (in the stream) where the segment stopped
+	uint32_t reach;         // how far a match reaches before the segment's first output byte
+	uint32_t flags;         // I2_SEGF_*
+	uint64_t scr_lo, scr_hi;   // its slice of the stream's token scratch (literals up from lo, records down from hi)
+};
+
+struct I2SegCtl {
+	uint32_t *count;     // [n_huge] candidates found / segments of the stream
+	uint32_t *start;     // [n_huge][I2_MAXSEG] start bit of every segment, ascending, [0] = 0
+	I2SegRes *res;       // [n_huge][I2_MAXSEG]
+	uint32_t *items;     // compact work list: stream << 16 | segment
+	uint32_t *n_items;
+	uint32_t *live;      // [n_huge][I2_MAXSEG] the chain of segments that make up the stream
+	uint32_t *nlive;     // [n_huge] length of the chain (0 = the stream was declined)
+	int32_t *seg_status; // [n_huge] status word of an accepted stream
+};
+
+// ------------------------------------------------------------------------------------------------
 // lane states
 #define I2_S_IDLE 0u     // needs a stream
 #define I2_S_HDR 1u      // at a block header
@@ -522,10 +558,15 @@ __device__ __forceinline__ uint32_t i2_header(I2Reader &br, uint8_t *slot, const
 // phase A.  grid: persistent, one warp per CTA; the first `lanes_active` (<= I2_LANES) lanes of every warp pull list
 // indices from *work_counter.  (Few streams are spread over all resident warps rather than packed into few:
 // a lock-step step costs the same whatever the number of live lanes.)
+// SEG: the work items are the segments of huge streams (`list`, `tok_ofs` index those streams; see I2SegCtl).
+template <bool SEG>
 __global__ void __launch_bounds__(32) k_inflate_tok(const uint8_t *__restrict__ archive, const otz_entry *__restrict__ ents,
 	const OtzEntryState *__restrict__ est, const int32_t *__restrict__ status, const uint32_t *__restrict__ list, uint32_t n_list,
 	uint32_t *__restrict__ work_counter, uint8_t *__restrict__ scratch, const uint64_t *__restrict__ tok_ofs, I2TokRes *__restrict__ tokres,
-	uint32_t *__restrict__ fb_list, uint32_t *__restrict__ fb_count, uint32_t lanes_active) {
+	uint32_t *__restrict__ fb_list, uint32_t *__restrict__ fb_count, uint32_t lanes_active, I2SegCtl seg) {
+	if (SEG) {
+		n_list = *seg.n_items;
+	}
 	extern __shared__ __align__(16) uint8_t smem_raw[];
 	const uint32_t lane = threadIdx.x;
 	// shared memory: the warp scratch, then `lanes_active` table slots.  Lanes without a slot never become active;
@@ -560,17 +601,39 @@ __global__ void __launch_bounds__(32) k_inflate_tok(const uint8_t *__restrict__ 
 	// step parsed but not yet emitted (software pipeline of the decode loop): entries and bit windows
 	bool pv = false;
 	uint32_t pe = 0, pd = 0, pb = 0, pb2 = 0;
+	// SEG: stream / segment of this lane, the next candidate start, bytes a match reached before the segment
+	uint32_t sh = 0, sj = 0, sjn = 0, s_next = 0xFFFFFFFFu, s_own = 0, reach = 0;
+	uint8_t *seq_floor = nullptr;   // SEG: the records must stay above the literals (scr_lo .. scr_hi is a guess)
 
 // leave the current stream: FALLBACK = hand it to k_inflate, COMMIT = release it to phase B
+// (SEG: the segment is left without the OK flag / with its result; k_seg_stitch decides about the stream)
 #define I2_FALLBACK()                                                     \
 	do {                                                                  \
-		fb_list[atomicAdd(fb_count, 1u)] = ei;                            \
-		tokres[k].ok = 0u;                                                \
+		if (!SEG) {                                                       \
+			fb_list[atomicAdd(fb_count, 1u)] = ei;                        \
+			tokres[k].ok = 0u;                                            \
+		}                                                                 \
 		state = I2_S_IDLE;                                                \
+	} while (0)
+#define I2_SEG_COMMIT(final_)                                                               \
+	do {                                                                                    \
+		const int64_t rem_c = br.remaining_bits();                                          \
+		if (rem_c >= 0) {                                                                   \
+			I2SegRes *r_ = &seg.res[sh * I2_MAXSEG + sj];                                   \
+			r_->nseq = nseq;                                                                \
+			r_->nlit = nl;                                                                  \
+			r_->produced = nl + mb;                                                         \
+			r_->end_bit = (uint32_t)((int64_t)comp * 8 - rem_c);                            \
+			r_->reach = reach;                                                              \
+			atomicOr(&r_->flags, I2_SEGF_OK | ((final_) ? I2_SEGF_FINAL : 0u) | (ref_eob ? I2_SEGF_REF_EOB : 0u)); \
+		}                                                                                   \
+		state = I2_S_IDLE;                                                                  \
 	} while (0)
 #define I2_COMMIT()                                                                         \
 	do {                                                                                    \
-		if (br.remaining_bits() < 0 || nl + mb != cap) {                                    \
+		if (SEG) {                                                                          \
+			I2_SEG_COMMIT(true);                                                            \
+		} else if (br.remaining_bits() < 0 || nl + mb != cap) {                             \
 			I2_FALLBACK();                                                                  \
 		} else {                                                                            \
 			I2TokRes r;                                                                     \
@@ -620,6 +683,33 @@ __global__ void __launch_bounds__(32) k_inflate_tok(const uint8_t *__restrict__ 
 					k = base + __popc(idle & ((1u << lane) - 1u));
 					if (k >= n_list) {
 						state = I2_S_DONE;
+					} else if (SEG) {
+						const uint32_t item = seg.items[k];
+						sh = item >> 16;
+						sj = item & 0xFFFFu;
+						ei = list[sh];
+						const otz_entry e = ents[ei];
+						in = archive + est[ei].data_ofs;
+						comp = e.comp_size;
+						cap = e.uncomp_size;
+						rflags = e.flags;
+						const uint32_t cnt = seg.count[sh];
+						s_own = seg.start[sh * I2_MAXSEG + sj];
+						sjn = sj + 1;
+						s_next = sjn < cnt ? seg.start[sh * I2_MAXSEG + sjn] : 0xFFFFFFFFu;
+						I2SegRes *r_ = &seg.res[sh * I2_MAXSEG + sj];
+						litp = scratch + r_->scr_lo;
+						seq_floor = litp;
+						seqp = reinterpret_cast<uint32_t *>(scratch + r_->scr_hi);
+						nl = nl0 = mb = nseq = 0;
+						ref_eob = 0;
+						reach = 0;
+						pv = false;
+						if (r_->scr_hi - r_->scr_lo >= 128u) {
+							br.init(in + (s_own >> 3), (uint64_t)comp - (s_own >> 3));
+							br.pos += s_own & 7u;
+							state = I2_S_HDR;
+						}   // else: two candidates a few bits apart, no room for tokens — the segment simply fails (stays idle)
 					} else {
 						ei = list[k];
 						if (OTZ_ST_CODE(status[ei]) == OTZ_ST_OK) {
@@ -649,6 +739,22 @@ __global__ void __launch_bounds__(32) k_inflate_tok(const uint8_t *__restrict__ 
 			}
 		}
 		// ---- (2) block headers (dec:613-627), every lane that stands at one, in lock-step
+		if (SEG && state == I2_S_HDR) {
+			// a block boundary: the segment ends where the next live candidate starts; candidates it has run past
+			// were false (or inside a block) and are marked dead
+			const uint32_t P = (uint32_t)((int64_t)comp * 8 - br.remaining_bits());
+			if (P != s_own) {
+				const uint32_t cnt = seg.count[sh];
+				while (P > s_next) {
+					atomicOr(&seg.res[sh * I2_MAXSEG + sjn].flags, I2_SEGF_DEAD);
+					sjn++;
+					s_next = sjn < cnt ? seg.start[sh * I2_MAXSEG + sjn] : 0xFFFFFFFFu;
+				}
+				if (P == s_next) {
+					I2_SEG_COMMIT(false);
+				}
+			}
+		}
 		if (state == I2_S_HDR) {
 			const uint32_t act_ = i2_header(br, slot, in, comp, rflags, final_blk, ref_eob, hlit, hdist);
 			if (act_ == I2_A_BUILD) {
@@ -711,7 +817,12 @@ __global__ void __launch_bounds__(32) k_inflate_tok(const uint8_t *__restrict__ 
 					const uint32_t dist = WS.dist_base[ds] + ((pb2 >> (tb2 - dxb)) & ((1u << dxb) - 1u));
 					const uint32_t run = nl - nl0, opos = nl + mb;
 					const bool e_lit = pv && kind == I2_K_LIT, e_len = pv && kind == I2_K_LEN;
-					const bool e_ok = e_len && run < I2_SEQ_ESC && dist <= opos;
+					// SEG (not the first segment): the output position in the stream is unknown; remember how far back
+					// the matches reach instead (k_seg_stitch checks it against the position the chain gives)
+					const bool e_ok = e_len && run < I2_SEQ_ESC && (SEG ? (s_own != 0u || dist <= opos) : dist <= opos);
+					if (SEG && e_ok && dist > opos) {
+						reach = max(reach, dist - opos);
+					}
 					if (e_lit) {
 						I2_EMIT_LIT((pe >> 6) & 0xFFu);
 					}
@@ -720,7 +831,7 @@ __global__ void __launch_bounds__(32) k_inflate_tok(const uint8_t *__restrict__ 
 					}
 					// (the token scratch has room for the one literal or record that may exceed `cap` here)
 					pv = e_len && !e_ok;   // still pending only if the special path has to finish it
-					e_special = pv || nl + mb > cap;
+					e_special = pv || (act && (nl + mb > cap || (SEG && (uint8_t *)seqp - (seq_floor + nl) < 32)));
 				}
 				// ---- parse step i
 				br.top();
@@ -746,9 +857,13 @@ __global__ void __launch_bounds__(32) k_inflate_tok(const uint8_t *__restrict__ 
 							const uint32_t tb2 = pd & 31u, dxb = (pd >> 5) & 15u, ds = (pd >> 9) & 31u;
 							const uint32_t dist = WS.dist_base[ds] + ((pb2 >> (tb2 - dxb)) & ((1u << dxb) - 1u));
 							uint32_t r3 = nl - nl0;
-							if (dist > nl + mb) {
-								bad = true;   // reaches before the start of the output (strict; dec:785 does not check)
+							if ((dist > nl + mb && !(SEG && s_own != 0u)) ||
+								(SEG && (uint8_t *)seqp - (seq_floor + nl) < (int64_t)(4u * (r3 / I2_SEQ_ESC) + 32u))) {
+								bad = true;   // reaches before the start of the output (strict; dec:785 does not check) / slice full
 							} else {
+								if (SEG && dist > nl + mb) {
+									reach = max(reach, dist - (nl + mb));
+								}
 								while (r3 >= I2_SEQ_ESC) {
 									*--seqp = I2_SEQ_ESC;
 									nseq++;
@@ -759,6 +874,7 @@ __global__ void __launch_bounds__(32) k_inflate_tok(const uint8_t *__restrict__ 
 							pv = false;
 						}
 						bad = bad || nl + mb > cap;   // dec:700-703, dec:791-793
+						bad = bad || (SEG && (uint8_t *)seqp - (seq_floor + nl) < 32);   // the guessed scratch slice is full
 						// -- step i, when it is not a plain literal / root-level match: decode and emit it here
 						bool eob = false;
 						if (!bad && act && !p_plain) {
@@ -814,9 +930,13 @@ __global__ void __launch_bounds__(32) k_inflate_tok(const uint8_t *__restrict__ 
 									const uint32_t dist3 = WS.dist_base[(dd >> 9) & 31u] + ((b3 >> (used + t3 - x3)) & ((1u << x3) - 1u));
 									br.pos += used + t3;
 									uint32_t r3 = nl - nl0;
-									if (dist3 > nl + mb) {
+									if ((dist3 > nl + mb && !(SEG && s_own != 0u)) ||
+										(SEG && (uint8_t *)seqp - (seq_floor + nl) < (int64_t)(4u * (r3 / I2_SEQ_ESC) + 32u))) {
 										bad = true;
 									} else {
+										if (SEG && dist3 > nl + mb) {
+											reach = max(reach, dist3 - (nl + mb));
+										}
 										while (r3 >= I2_SEQ_ESC) {
 											*--seqp = I2_SEQ_ESC;
 											nseq++;
@@ -857,10 +977,289 @@ __global__ void __launch_bounds__(32) k_inflate_tok(const uint8_t *__restrict__ 
 		}
 	}
 #undef I2_FALLBACK
+#undef I2_SEG_COMMIT
 #undef I2_COMMIT
 #undef I2_STEP_CHECK
 #undef I2_EMIT_LIT
 #undef I2_EMIT_MATCH
+}
+
+// ------------------------------------------------------------------------------------------------
+// k_block_search: one thread per byte of a huge stream tests its 8 bit offsets for a dynamic-block header:
+// BTYPE = 2, HLIT <= 29, HDIST <= 29, a complete code-length code (Kraft sum), then — for the ~0.1 % that get this
+// far — the code lengths themselves: exactly HLIT + HDIST of them, an end-of-block code, complete literal/length
+// and distance codes.  grid: (ceil(max comp / 256), n_huge).
+__device__ __forceinline__ uint32_t i2_bits_at(const uint8_t *p, uint64_t bit, uint32_t n) {   // n <= 24
+	const uint8_t *q = p + (bit >> 3);
+	const uint32_t v = (uint32_t)q[0] | ((uint32_t)q[1] << 8) | ((uint32_t)q[2] << 16) | ((uint32_t)q[3] << 24);
+	return (v >> (bit & 7)) & ((1u << n) - 1u);
+}
+
+__device__ __noinline__ bool i2_plausible_header(const uint8_t *in, uint64_t nbits, uint64_t p, uint32_t hlit, uint32_t hdist, uint32_t hclen) {
+	// (in + nbits/8 + 4 is readable: the image is padded)
+	uint8_t pre[128];
+	uint32_t cl[19];
+	uint64_t q = p + 17;
+	for (uint32_t i = 0; i < 19; i++) {
+		cl[i] = 0;
+	}
+	for (uint32_t i = 0; i < hclen; i++) {
+		cl[c_cl_order[i]] = i2_bits_at(in, q, 3);
+		q += 3;
+	}
+	uint32_t next[8], cnt[8];
+	for (int l = 0; l < 8; l++) {
+		cnt[l] = 0;
+	}
+	for (uint32_t i = 0; i < 19; i++) {
+		cnt[cl[i]]++;
+	}
+	uint32_t code = 0;
+	cnt[0] = 0;
+	for (int l = 1; l < 8; l++) {
+		code = (code + cnt[l - 1]) << 1;
+		next[l] = code;
+	}
+	for (uint32_t sym = 0; sym < 19; sym++) {
+		const uint32_t l = cl[sym];
+		if (l) {
+			const uint32_t c = next[l]++;
+			const uint32_t rev = __brev(c) >> (32u - l);
+			for (uint32_t x = rev; x < 128u; x += (1u << l)) {
+				pre[x] = (uint8_t)(sym | (l << 5));
+			}
+		}
+	}
+	const uint32_t total = hlit + hdist;
+	uint32_t idx = 0, prev = 0;
+	uint32_t kl = 0, kd = 0, nd = 0;   // Kraft sums (units of 2^-15), distance codes used
+	bool eob = false;
+	while (idx < total) {
+		if (q + 14 > nbits) {
+			return false;
+		}
+		const uint32_t bits = i2_bits_at(in, q, 14);
+		const uint32_t e = pre[bits & 127u];
+		const uint32_t sym = e & 31u, cb = e >> 5;
+		uint32_t rep = 1, val = sym;
+		if (sym < 16u) {
+			q += cb;
+			prev = sym;
+		} else if (sym == 16u) {
+			if (idx == 0) {
+				return false;
+			}
+			val = prev;
+			rep = 3u + ((bits >> cb) & 3u);
+			q += cb + 2;
+		} else if (sym == 17u) {
+			val = 0;
+			rep = 3u + ((bits >> cb) & 7u);
+			q += cb + 3;
+			prev = 0;
+		} else {
+			val = 0;
+			rep = 11u + ((bits >> cb) & 127u);
+			q += cb + 7;
+			prev = 0;
+		}
+		if (idx + rep > total) {
+			return false;
+		}
+		if (val) {
+			for (uint32_t i = 0; i < rep; i++) {
+				const uint32_t sidx = idx + i;
+				if (sidx < hlit) {
+					kl += 32768u >> val;
+					eob = eob || sidx == 256u;
+				} else {
+					kd += 32768u >> val;
+					nd++;
+				}
+			}
+		}
+		idx += rep;
+	}
+	return eob && kl == 32768u && (kd == 32768u || nd <= 1u);
+}
+
+// grid: persistent (any size); task t = 256 consecutive bytes of one stream, task_ofs[h] = first task of stream h
+__global__ void __launch_bounds__(256) k_block_search(const uint8_t *__restrict__ archive, const otz_entry *__restrict__ ents,
+	const OtzEntryState *__restrict__ est, const int32_t *__restrict__ status, const uint32_t *__restrict__ list, uint32_t n_huge,
+	const uint32_t *__restrict__ task_ofs, uint2 *__restrict__ surv, uint32_t surv_cap, uint32_t *__restrict__ n_surv) {
+	const uint32_t n_tasks = task_ofs[n_huge];
+	for (uint32_t t = blockIdx.x; t < n_tasks; t += gridDim.x) {
+	// stream of this task: the last h with task_ofs[h] <= t
+	uint32_t lo_h = 0, hi_h = n_huge;
+	while (hi_h - lo_h > 1) {
+		const uint32_t mid = (lo_h + hi_h) >> 1;
+		if (task_ofs[mid] <= t) {
+			lo_h = mid;
+		} else {
+			hi_h = mid;
+		}
+	}
+	const uint32_t h = lo_h;
+	const uint32_t ei = list[h];
+	if (OTZ_ST_CODE(status[ei]) != OTZ_ST_OK) {
+		continue;
+	}
+	const uint32_t comp = ents[ei].comp_size;
+	const uint32_t byte = (t - task_ofs[h]) * 256u + threadIdx.x;
+	if (byte + 12u > comp) {
+		continue;   // a block header needs more than that; the tail belongs to the last segment anyway
+	}
+	const uint8_t *in = archive + est[ei].data_ofs;
+	const uint8_t *q = in + byte;
+	uint64_t lo = 0;
+	uint32_t hi = 0;
+#pragma unroll
+	for (int i = 0; i < 8; i++) {
+		lo |= (uint64_t)q[i] << (8 * i);
+	}
+#pragma unroll
+	for (int i = 0; i < 4; i++) {
+		hi |= (uint32_t)q[8 + i] << (8 * i);
+	}
+	for (uint32_t o = byte == 0 ? 1u : 0u; o < 8u; o++) {
+		const uint64_t v = o ? (lo >> o) | ((uint64_t)hi << (64u - o)) : lo;
+		const uint32_t w = (uint32_t)v;
+		if (((w >> 1) & 3u) != 2u) {
+			continue;
+		}
+		const uint32_t hl = (w >> 3) & 31u, hd = (w >> 8) & 31u, hc = ((w >> 13) & 15u) + 4u;
+		if (hl > 29u || hd > 29u) {
+			continue;
+		}
+		// Kraft sum of the code-length code: 3 bits each from bit 17
+		const uint64_t v2 = (v >> 17) | ((uint64_t)(hi >> o) << (47u)) ;   // bits 17.. of the header (81 - 17 = 64 bits are enough: 19 * 3 = 57)
+		uint32_t kr = 0;
+		for (uint32_t i = 0; i < hc; i++) {
+			const uint32_t l = (uint32_t)(v2 >> (3u * i)) & 7u;
+			kr += l ? (128u >> l) : 0u;
+		}
+		if (kr != 128u) {
+			continue;
+		}
+		// survivors (~0.1 % of the offsets) go to a list: checking their code lengths here, one lane at a time,
+		// would cost more than everything else together
+		const uint32_t at = atomicAdd(n_surv, 1u);
+		if (at < surv_cap) {
+			surv[at] = make_uint2(h, byte * 8u + o);
+		}
+	}
+	}
+}
+
+// second stage of the search: one thread per surviving offset decodes the code lengths of the would-be header
+__global__ void __launch_bounds__(256) k_block_verify(const uint8_t *__restrict__ archive, const otz_entry *__restrict__ ents,
+	const OtzEntryState *__restrict__ est, const uint32_t *__restrict__ list, const uint2 *__restrict__ surv, uint32_t surv_cap,
+	const uint32_t *__restrict__ n_surv, I2SegCtl seg) {
+	const uint32_t n = min(*n_surv, surv_cap);
+	for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+		const uint2 sv = surv[i];
+		const uint32_t h = sv.x, ei = list[h];
+		const uint8_t *in = archive + est[ei].data_ofs;
+		const uint32_t w = i2_bits_at(in, sv.y, 17);
+		if (i2_plausible_header(in, (uint64_t)ents[ei].comp_size * 8u, sv.y, ((w >> 3) & 31u) + 257u, ((w >> 8) & 31u) + 1u, ((w >> 13) & 15u) + 4u)) {
+			const uint32_t at = atomicAdd(&seg.count[h], 1u);
+			if (at < I2_MAXSEG - 1u) {
+				seg.start[h * I2_MAXSEG + 1u + at] = sv.y;
+			}
+		}
+	}
+}
+
+// One thread per huge stream: candidates in ascending order behind the true start (bit 0), result rows cleared, every
+// segment gets a slice of the stream's token scratch in proportion to its share of the compressed bits, and the
+// segments are appended to the work list.
+__global__ void k_seg_prepare(const otz_entry *__restrict__ ents, const uint32_t *__restrict__ list, uint32_t n_huge,
+	const uint64_t *__restrict__ tok_ofs, I2SegCtl seg) {
+	const uint32_t h = blockIdx.x * blockDim.x + threadIdx.x;
+	if (h >= n_huge) {
+		return;
+	}
+	uint32_t *st = seg.start + h * I2_MAXSEG;
+	uint32_t n = min(seg.count[h], (uint32_t)I2_MAXSEG - 1u);
+	for (uint32_t i = 2; i <= n; i++) {   // insertion sort of st[1..n]
+		const uint32_t v = st[i];
+		uint32_t j = i;
+		while (j > 1 && st[j - 1] > v) {
+			st[j] = st[j - 1];
+			j--;
+		}
+		st[j] = v;
+	}
+	st[0] = 0;
+	n += 1;
+	seg.count[h] = n;
+	seg.nlive[h] = 0;
+	const uint32_t ei = list[h];
+	const double bits_total = (double)ents[ei].comp_size * 8.0;
+	const uint64_t base = tok_ofs[h], total = tok_ofs[h + 1] - tok_ofs[h];
+	const uint32_t at = atomicAdd(seg.n_items, n);
+	uint64_t lo = base;
+	for (uint32_t j = 0; j < n; j++) {
+		const uint64_t hi = j + 1 < n ? base + ((uint64_t)((double)total * ((double)st[j + 1] / bits_total)) & ~15ull) : base + total;
+		I2SegRes r;
+		r.nseq = r.nlit = r.produced = r.end_bit = r.reach = r.flags = 0;
+		r.scr_lo = lo;
+		r.scr_hi = hi;
+		seg.res[h * I2_MAXSEG + j] = r;
+		seg.items[at + j] = (h << 16) | j;
+		lo = hi;
+	}
+}
+
+// One thread per huge stream: follow the chain of segments.  The stream is accepted (nlive > 0) only if every link
+// fits; otherwise it is appended to the fallback list of k_inflate.
+__global__ void k_seg_stitch(const otz_entry *__restrict__ ents, const int32_t *__restrict__ status, const uint32_t *__restrict__ list,
+	uint32_t n_huge, I2SegCtl seg, uint32_t *__restrict__ fb_list, uint32_t *__restrict__ fb_count) {
+	const uint32_t h = blockIdx.x * blockDim.x + threadIdx.x;
+	if (h >= n_huge) {
+		return;
+	}
+	const uint32_t ei = list[h];
+	if (OTZ_ST_CODE(status[ei]) != OTZ_ST_OK) {
+		return;
+	}
+	const uint32_t n = seg.count[h], cap = ents[ei].uncomp_size;
+	const I2SegRes *res = seg.res + h * I2_MAXSEG;
+	const uint32_t *st = seg.start + h * I2_MAXSEG;
+	uint32_t *live = seg.live + h * I2_MAXSEG;
+	uint32_t j = 0, nlive = 0;
+	uint64_t out = 0;
+	bool ok = true, done = false, ref_eob = false;
+	while (ok && !done) {
+		const I2SegRes r = res[j];
+		if (!(r.flags & I2_SEGF_OK) || r.reach > out || out + r.produced > cap) {
+			ok = false;
+			break;
+		}
+		live[nlive++] = j;
+		out += r.produced;
+		if (r.flags & I2_SEGF_FINAL) {
+			done = true;
+			ref_eob = (r.flags & I2_SEGF_REF_EOB) != 0u;
+			break;
+		}
+		uint32_t jn = j + 1;
+		while (jn < n && st[jn] < r.end_bit) {
+			jn++;
+		}
+		if (jn >= n || st[jn] != r.end_bit) {
+			ok = false;
+			break;
+		}
+		j = jn;
+	}
+	if (ok && done && out == cap) {
+		seg.nlive[h] = nlive;
+		seg.seg_status[h] = OTZ_ST_OK | (ref_eob ? OTZ_STF_REF_EOB : 0);
+	} else {
+		seg.nlive[h] = 0;
+		fb_list[atomicAdd(fb_count, 1u)] = ei;
+	}
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -1031,12 +1430,13 @@ __device__ __forceinline__ I2Batch i2_scan_batch(I2LzSmem<W> &S, int buf, uint32
 	return B;
 }
 
-template <int W, bool WIDE>
+// SEG: `list` holds huge streams; the tokens of a stream are the chain of segments k_seg_stitch accepted.
+template <int W, bool WIDE, bool SEG>
 __global__ void __launch_bounds__(128) k_inflate_lz(uint8_t *__restrict__ out, const otz_entry *__restrict__ ents, const uint32_t *__restrict__ list,
 	uint32_t n_list, uint32_t *__restrict__ work_counter, const uint8_t *__restrict__ scratch, const uint64_t *__restrict__ tok_ofs,
-	const I2TokRes *__restrict__ tokres, int32_t *__restrict__ status, uint32_t *__restrict__ produced_out) {
+	const I2TokRes *__restrict__ tokres, int32_t *__restrict__ status, uint32_t *__restrict__ produced_out, I2SegCtl seg) {
 	extern __shared__ __align__(16) uint8_t smem_raw[];
-	constexpr uint32_t MASK = I2Ring<W>::MASK, SEG = I2Ring<W>::SEG, SPAN_MAX = I2Ring<W>::SPAN_MAX;
+	constexpr uint32_t MASK = I2Ring<W>::MASK, SEGB = I2Ring<W>::SEG, SPAN_MAX = I2Ring<W>::SPAN_MAX;
 	const uint32_t lane = threadIdx.x & 31u;
 	I2LzSmem<W> &S = reinterpret_cast<I2LzSmem<W> *>(smem_raw)[threadIdx.x >> 5];
 	uint8_t *const rb = S.ring;
@@ -1049,7 +1449,16 @@ __global__ void __launch_bounds__(128) k_inflate_lz(uint8_t *__restrict__ out, c
 		if (k >= n_list) {
 			break;
 		}
-		const I2TokRes tr = tokres[k];
+		I2TokRes tr;
+		uint32_t nsegs = 1;
+		if (SEG) {
+			nsegs = seg.nlive[k];
+			tr.ok = nsegs != 0u;
+			tr.status = seg.seg_status[k];
+			tr.nseq = tr.nlit = 0;
+		} else {
+			tr = tokres[k];
+		}
 		if (!tr.ok) {
 			continue;
 		}
@@ -1058,10 +1467,23 @@ __global__ void __launch_bounds__(128) k_inflate_lz(uint8_t *__restrict__ out, c
 		uint8_t *const dstp = out + e.out_ofs;
 		const uint32_t mis = (uint32_t)(reinterpret_cast<uint64_t>(dstp) & 15u);
 		uint8_t *const gbase = dstp - mis;
-		const uint8_t *const lits = scratch + tok_ofs[k];
-		const uint32_t *const seq_end = reinterpret_cast<const uint32_t *>(scratch + tok_ofs[k + 1]);
-		const uint32_t nseq = tr.nseq;
 		uint32_t q = mis, qf = mis;   // linear write position / position up to which HBM holds the data
+		for (uint32_t sgi = 0; sgi < nsegs; sgi++) {
+		const uint8_t *lits;
+		const uint32_t *seq_end;
+		uint32_t nseq, nlit;
+		if (SEG) {
+			const I2SegRes *r_ = &seg.res[k * I2_MAXSEG + seg.live[k * I2_MAXSEG + sgi]];
+			lits = scratch + r_->scr_lo;
+			seq_end = reinterpret_cast<const uint32_t *>(scratch + r_->scr_hi);
+			nseq = r_->nseq;
+			nlit = r_->nlit;
+		} else {
+			lits = scratch + tok_ofs[k];
+			seq_end = reinterpret_cast<const uint32_t *>(scratch + tok_ofs[k + 1]);
+			nseq = tr.nseq;
+			nlit = tr.nlit;
+		}
 		uint32_t lp = 0, b = 0;       // literals / records consumed
 		__syncwarp();
 		// records b + lane (recA) and b + 32 + lane (recB); WIDE: their second words in offA / offB
@@ -1169,7 +1591,7 @@ __global__ void __launch_bounds__(128) k_inflate_lz(uint8_t *__restrict__ out, c
 			lp += cur.tot_l;
 			q = cur.q_end;
 			__syncwarp();
-			const uint32_t qa = q & ~(SEG - 1u);
+			const uint32_t qa = q & ~(SEGB - 1u);
 			if (qa > qf) {
 				i2_flush_range<W>(gbase, rb, qf, qa, lane);
 				qf = qa;
@@ -1180,21 +1602,22 @@ __global__ void __launch_bounds__(128) k_inflate_lz(uint8_t *__restrict__ out, c
 		}
 		asm volatile("cp.async.wait_group 0;" ::: "memory");
 		// literals after the last match
-		while (lp < tr.nlit) {
-			const uint32_t n = min(tr.nlit - lp, SPAN_MAX);
+		while (lp < nlit) {
+			const uint32_t n = min(nlit - lp, SPAN_MAX);
 			for (uint32_t t = lane; t < n; t += 32) {
 				rb[(q + t) & MASK] = lits[lp + t];
 			}
 			lp += n;
 			q += n;
 			__syncwarp();
-			const uint32_t qa = q & ~(SEG - 1u);
+			const uint32_t qa = q & ~(SEGB - 1u);
 			if (qa > qf) {
 				i2_flush_range<W>(gbase, rb, qf, qa, lane);
 				qf = qa;
 				__syncwarp();
 			}
 		}
+		}   // segments
 		if (q > qf) {
 			i2_flush_range<W>(gbase, rb, qf, q, lane);
 		}

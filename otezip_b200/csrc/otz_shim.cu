@@ -30,6 +30,9 @@ static int fail_cuda(cudaError_t e, const char *what) {
 		}                                 \
 	} while (0)
 
+// ring of the LZ executor for huge (segmented) streams: few streams, each one the critical path — a large ring keeps
+// most match sources in shared memory
+#define OTZ_SEG_RING 16384
 #define OTZ_PROF_SLOTS 64
 struct otz_ctx {
 	int device;
@@ -50,6 +53,7 @@ struct otz_ctx {
 	int inflate_mode;   // OTZ_INFLATE_MODE: 0 = two-phase (k_inflate_tok + k_inflate_lz, k_inflate as fallback), 1 = k_inflate only
 	int lz_ring;        // OTZ_LZ_RING: ring bytes per warp of k_inflate_lz (4096 / 8192 / 16384)
 	uint32_t last_fallbacks;   // DEFLATE streams of the last collected run that phase A handed to k_inflate
+	int huge_legacy;        // OTZ_HUGE_MODE=legacy: huge DEFLATE entries on k_inflate<32,16384> instead of the segmented decode
 	int zstd_legacy;        // OTZ_ZSTD_MODE=legacy: warp-per-entry k_zstd instead of k_zstd_tok + k_inflate_lz
 	uint8_t *d_ztok_cache;  // grow-only token scratch of the two-phase Zstandard path
 	uint64_t ztok_cache_bytes;
@@ -70,6 +74,11 @@ struct otz_plan {
 	uint32_t *d_inflate_list, n_inflate;   // DEFLATE entries, longest first; [0, n_inflate_big) are the large ones
 	uint32_t n_inflate_big;
 	uint32_t n_inflate_huge;   // [0, n_inflate_huge): entries whose serial decode time sets the critical path of a batch
+	I2SegCtl seg;              // segmented decode of the huge entries (device arrays; null when there are none)
+	uint32_t huge_max_comp;
+	uint32_t *d_search_ofs;    // [n_huge + 1] first 256-byte search task of every huge stream
+	uint2 *d_surv;             // offsets that passed the cheap header checks of k_block_search
+	uint32_t surv_cap;
 	uint64_t *d_tok_ofs;       // two-phase inflate: scratch offset of every list slot (+ end), bytes
 	uint64_t tok_bytes;
 	I2TokRes *d_tokres;
@@ -193,6 +202,8 @@ extern "C" int otz_ctx_create(int device, otz_ctx **out) {
 	c->inflate_ring = t ? atoi(t) : 0;
 	t = getenv("OTZ_INFLATE_MODE");
 	c->inflate_mode = (t && !strcmp(t, "legacy")) ? 1 : 0;
+	t = getenv("OTZ_HUGE_MODE");
+	c->huge_legacy = (t && !strcmp(t, "legacy")) ? 1 : 0;
 	t = getenv("OTZ_ZSTD_MODE");
 	c->zstd_legacy = (t && !strcmp(t, "legacy")) ? 1 : 0;
 	t = getenv("OTZ_LZ_RING");
@@ -368,6 +379,16 @@ extern "C" void otz_plan_destroy(otz_ctx *c, otz_plan *p) {
 	cudaFree(p->d_produced);
 	cudaFree(p->d_chunks);
 	cudaFree(p->d_inflate_list);
+	cudaFree(p->d_search_ofs);
+	cudaFree(p->d_surv);
+	cudaFree(p->seg.count);
+	cudaFree(p->seg.start);
+	cudaFree(p->seg.res);
+	cudaFree(p->seg.items);
+	cudaFree(p->seg.n_items);
+	cudaFree(p->seg.live);
+	cudaFree(p->seg.nlive);
+	cudaFree(p->seg.seg_status);
 	cudaFree(p->d_tok_ofs);
 	cudaFree(p->d_tokres);
 	cudaFree(p->d_fb_list);
@@ -436,7 +457,7 @@ extern "C" int otz_plan_create(otz_ctx *c, const otz_entry *ents, uint32_t n, co
 	// large entries first (they get the 16 KiB ring kernel), inside each class longest streams first
 	const uint32_t big_bytes = 256u * 1024u;
 	const char *hb = getenv("OTZ_HUGE_BYTES");
-	const uint32_t huge_bytes = hb ? (uint32_t)strtoul(hb, nullptr, 0) : 2u * 1024u * 1024u;
+	const uint32_t huge_bytes = hb ? (uint32_t)strtoul(hb, nullptr, 0) : 1024u * 1024u;
 	auto cls = [&](uint32_t i) { return ents[i].uncomp_size >= huge_bytes ? 2 : ents[i].uncomp_size >= big_bytes ? 1 : 0; };
 	std::stable_sort(infl.begin(), infl.end(), [&](uint32_t a, uint32_t b) {
 		const int ca = cls(a), cb = cls(b);
@@ -447,6 +468,9 @@ extern "C" int otz_plan_create(otz_ctx *c, const otz_entry *ents, uint32_t n, co
 	for (uint32_t i : infl) {
 		p->n_inflate_big += ents[i].uncomp_size >= big_bytes;
 		p->n_inflate_huge += ents[i].uncomp_size >= huge_bytes;
+		if (ents[i].uncomp_size >= huge_bytes) {
+			p->huge_max_comp = std::max(p->huge_max_comp, ents[i].comp_size);
+		}
 	}
 	p->n_chunks = (uint32_t)chunks.size();
 	p->n_inflate = (uint32_t)infl.size();
@@ -466,6 +490,31 @@ extern "C" int otz_plan_create(otz_ctx *c, const otz_entry *ents, uint32_t n, co
 			cudaMalloc(&p->d_fb_list, infl.size() * 4) != cudaSuccess)) {
 		otz_plan_destroy(c, p);
 		return rc ? rc : fail_cuda(cudaGetLastError(), "cudaMalloc(two-phase inflate lists)");
+	}
+	if (p->n_inflate_huge && p->n_inflate_huge <= 4096u) {
+		const size_t nh = p->n_inflate_huge, ns = nh * I2_MAXSEG;
+		std::vector<uint32_t> sofs(nh + 1);
+		sofs[0] = 0;
+		for (size_t h = 0; h < nh; h++) {
+			sofs[h + 1] = sofs[h] + (ents[infl[h]].comp_size + 255u) / 256u;
+		}
+		if ((rc = upload(&p->d_search_ofs, sofs, c->stream))) {
+			otz_plan_destroy(c, p);
+			return rc;
+		}
+		CK(cudaStreamSynchronize(c->stream));   // sofs dies here
+		p->surv_cap = std::max<uint32_t>(1u << 16, sofs[nh] * 4u);   // one per 64 bytes of compressed data (expected: one per ~135)
+		if (cudaMalloc(&p->d_surv, (size_t)p->surv_cap * sizeof(uint2)) != cudaSuccess) {
+			otz_plan_destroy(c, p);
+			return fail_cuda(cudaGetLastError(), "cudaMalloc(search survivors)");
+		}
+		if (cudaMalloc(&p->seg.count, nh * 4) != cudaSuccess || cudaMalloc(&p->seg.start, ns * 4) != cudaSuccess ||
+			cudaMalloc(&p->seg.res, ns * sizeof(I2SegRes)) != cudaSuccess || cudaMalloc(&p->seg.items, ns * 4) != cudaSuccess ||
+			cudaMalloc(&p->seg.n_items, 4) != cudaSuccess || cudaMalloc(&p->seg.live, ns * 4) != cudaSuccess ||
+			cudaMalloc(&p->seg.nlive, nh * 4) != cudaSuccess || cudaMalloc(&p->seg.seg_status, nh * 4) != cudaSuccess) {
+			otz_plan_destroy(c, p);
+			return fail_cuda(cudaGetLastError(), "cudaMalloc(segment tables)");
+		}
 	}
 	if ((rc = upload(&p->d_ents, ev, c->stream)) || (rc = upload(&p->d_chunks, chunks, c->stream)) ||
 		(rc = upload(&p->d_inflate_list, infl, c->stream)) || (rc = upload(&p->d_zstd_list, zst, c->stream)) ||
@@ -562,7 +611,7 @@ static int launch_inflate_cfg(otz_ctx *c, otz_plan *p, const uint8_t *d_archive,
 // share the machine; small entries get the big ring only when there are too few of them to fill the SMs.
 template <int W>
 static int launch_lz(otz_ctx *c, otz_plan *p, uint8_t *d_out, uint32_t first, uint32_t count, cudaStream_t st) {
-	auto kern = k_inflate_lz<W, false>;
+	auto kern = k_inflate_lz<W, false, false>;
 	const int warps = 4;
 	const size_t smem = warps * sizeof(I2LzSmem<W>);
 	static bool attr_done = false;
@@ -578,7 +627,7 @@ static int launch_lz(otz_ctx *c, otz_plan *p, uint8_t *d_out, uint32_t first, ui
 	}
 	const uint32_t grid = std::max(1u, std::min((uint32_t)(c->sm_count * per_sm), (count + warps - 1) / warps));
 	kern<<<grid, 32 * warps, smem, st>>>(d_out, p->d_ents, p->d_inflate_list + first, count, p->d_counter + 48, c->d_tok_cache,
-		p->d_tok_ofs + first, p->d_tokres + first, p->d_status, p->d_produced);
+		p->d_tok_ofs + first, p->d_tokres + first, p->d_status, p->d_produced, I2SegCtl{});
 	c->launches++;
 	CK(cudaGetLastError());
 	return OTZ_SUCCESS;
@@ -593,7 +642,58 @@ static int dispatch_inflate2(otz_ctx *c, otz_plan *p, const uint8_t *d_archive, 
 	// ring (k_inflate) — on the second stream, next to the lane-per-stream kernels that take everything else.
 	uint32_t first = 0;
 	bool forked = false;
-	if (p->n_inflate_huge && p->n_inflate_huge <= (uint32_t)c->sm_count * 10u) {
+	static bool attr_done = false;
+	if (!attr_done) {
+		CK(cudaFuncSetAttribute(k_inflate_tok<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, I2_SMEM_BYTES(I2_LANES)));
+		CK(cudaFuncSetAttribute(k_inflate_tok<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, I2_SMEM_BYTES(I2_LANES)));
+		CK(cudaFuncSetAttribute(k_inflate_lz<OTZ_SEG_RING, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(4 * sizeof(I2LzSmem<OTZ_SEG_RING>))));
+		attr_done = true;
+	}
+	if (p->n_inflate_huge && p->seg.count && !c->huge_legacy) {
+		// segmented decode: block search -> one lane per block run -> chain check -> one warp per stream executes the tokens
+		const uint32_t nh = p->n_inflate_huge;
+		first = nh;
+		cudaStream_t s2 = c->stream2;
+		CK(cudaEventRecord(c->ev_fork, s));
+		CK(cudaStreamWaitEvent(s2, c->ev_fork, 0));
+		CK(cudaMemsetAsync(p->seg.count, 0, nh * 4, s2));
+		CK(cudaMemsetAsync(p->seg.n_items, 0, 4, s2));
+		const bool dbg = getenv("OTZ_DEBUG_SYNC") != nullptr;
+#define OTZ_DBG(name_)                                                                                     \
+	if (dbg) {                                                                                             \
+		cudaError_t e_ = cudaStreamSynchronize(s2);                                                        \
+		fprintf(stderr, "[otz] %s: %s\n", name_, cudaGetErrorString(e_));                                  \
+	}
+		CK(cudaMemsetAsync(p->d_counter + 59, 0, 4, s2));
+		k_block_search<<<c->sm_count * 8, 256, 0, s2>>>(d_archive, p->d_ents, p->d_est, p->d_status, p->d_inflate_list, nh, p->d_search_ofs, p->d_surv,
+			p->surv_cap, p->d_counter + 59);
+		k_block_verify<<<c->sm_count * 8, 256, 0, s2>>>(d_archive, p->d_ents, p->d_est, p->d_inflate_list, p->d_surv, p->surv_cap, p->d_counter + 59, p->seg);
+		OTZ_DBG("k_block_search");
+		k_seg_prepare<<<(nh + 63) / 64, 64, 0, s2>>>(p->d_ents, p->d_inflate_list, nh, p->d_tok_ofs, p->seg);
+		OTZ_DBG("k_seg_prepare");
+		const uint32_t sl = 12;   // lanes per warp: 8 warps x 12 table slots per SM
+		int per_sm2 = 0;
+		CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm2, k_inflate_tok<true>, 32, I2_SMEM_BYTES(sl)));
+		uint32_t sgrid = (uint32_t)c->sm_count * (uint32_t)std::max(1, std::min(per_sm2, 8));
+		if (getenv("OTZ_SEG_GRID")) {
+			sgrid = (uint32_t)atoi(getenv("OTZ_SEG_GRID"));   // (tests: few lanes, so that every lane decodes many segments)
+		}
+		k_inflate_tok<true><<<sgrid, 32, I2_SMEM_BYTES(sl), s2>>>(d_archive, p->d_ents, p->d_est, p->d_status, p->d_inflate_list, 0u, p->d_counter + 57,
+			c->d_tok_cache, p->d_tok_ofs, p->d_tokres, p->d_fb_list, p->d_counter + 52, sl, p->seg);
+		OTZ_DBG("k_inflate_tok<true>");
+		k_seg_stitch<<<(nh + 63) / 64, 64, 0, s2>>>(p->d_ents, p->d_status, p->d_inflate_list, nh, p->seg, p->d_fb_list, p->d_counter + 52);
+		OTZ_DBG("k_seg_stitch");
+		CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm2, k_inflate_lz<OTZ_SEG_RING, false, true>, 128, 4 * sizeof(I2LzSmem<OTZ_SEG_RING>)));
+		const uint32_t lgrid = std::max(1u, std::min((uint32_t)(c->sm_count * std::max(per_sm2, 1)), (nh + 3) / 4));
+		k_inflate_lz<OTZ_SEG_RING, false, true><<<lgrid, 128, 4 * sizeof(I2LzSmem<OTZ_SEG_RING>), s2>>>(d_out, p->d_ents, p->d_inflate_list, nh, p->d_counter + 58,
+			c->d_tok_cache, p->d_tok_ofs, p->d_tokres, p->d_status, p->d_produced, p->seg);
+		OTZ_DBG("k_inflate_lz<seg>");
+#undef OTZ_DBG
+		c->launches += 6;
+		CK(cudaGetLastError());
+		CK(cudaEventRecord(c->ev_join, s2));
+		forked = true;
+	} else if (p->n_inflate_huge && p->n_inflate_huge <= (uint32_t)c->sm_count * 10u) {
 		first = p->n_inflate_huge;
 		CK(cudaEventRecord(c->ev_fork, s));
 		CK(cudaStreamWaitEvent(c->stream2, c->ev_fork, 0));
@@ -607,12 +707,7 @@ static int dispatch_inflate2(otz_ctx *c, otz_plan *p, const uint8_t *d_archive, 
 	const uint32_t count = p->n_inflate - first;
 	if (!count) {
 		CK(cudaStreamWaitEvent(s, c->ev_join, 0));
-		return OTZ_SUCCESS;
-	}
-	static bool attr_done = false;
-	if (!attr_done) {
-		CK(cudaFuncSetAttribute(k_inflate_tok, cudaFuncAttributeMaxDynamicSharedMemorySize, I2_SMEM_BYTES(I2_LANES)));
-		attr_done = true;
+		return launch_inflate_cfg(c, p, d_archive, d_out, 32, 4096, 0, p->n_inflate, 16, s, p->d_fb_list, p->d_counter + 52);
 	}
 	// A lock-step step costs the same for 1 or 28 live lanes and a stream advances one symbol per step, so the
 	// streams are spread over as many CTAs as the SM holds (more warps = more latency hidden): pick the number
@@ -633,7 +728,7 @@ static int dispatch_inflate2(otz_ctx *c, otz_plan *p, const uint8_t *d_archive, 
 	uint32_t lanes = std::max(1u, std::min(best_l, (per_sm_streams + best_c - 1) / best_c));
 	const size_t smem_l = (size_t)I2_SMEM_BYTES(best_l);
 	int per_sm = 0;
-	CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_inflate_tok, 32, smem_l));
+	CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_inflate_tok<false>, 32, smem_l));
 	if (per_sm < 1) {
 		snprintf(g_err, sizeof(g_err), "k_inflate_tok does not fit an SM (%zu bytes of shared memory)", smem_l);
 		return OTZ_ERR_CUDA;
@@ -641,8 +736,8 @@ static int dispatch_inflate2(otz_ctx *c, otz_plan *p, const uint8_t *d_archive, 
 	per_sm = std::min<int>(per_sm, (int)best_c);
 	const uint32_t grid = std::max(1u, std::min((uint32_t)(c->sm_count * per_sm), count));
 	lanes = std::max(lanes, std::min<uint32_t>(best_l, (count + grid - 1) / grid));
-	k_inflate_tok<<<grid, 32, I2_SMEM_BYTES(lanes), s>>>(d_archive, p->d_ents, p->d_est, p->d_status, p->d_inflate_list + first, count,
-		p->d_counter, c->d_tok_cache, p->d_tok_ofs + first, p->d_tokres + first, p->d_fb_list, p->d_counter + 52, lanes);
+	k_inflate_tok<false><<<grid, 32, I2_SMEM_BYTES(lanes), s>>>(d_archive, p->d_ents, p->d_est, p->d_status, p->d_inflate_list + first, count,
+		p->d_counter, c->d_tok_cache, p->d_tok_ofs + first, p->d_tokres + first, p->d_fb_list, p->d_counter + 52, lanes, I2SegCtl{});
 	c->launches++;
 	CK(cudaGetLastError());
 	int rc;
@@ -654,11 +749,10 @@ static int dispatch_inflate2(otz_ctx *c, otz_plan *p, const uint8_t *d_archive, 
 	if (rc) {
 		return rc;
 	}
-	rc = launch_inflate_cfg(c, p, d_archive, d_out, 32, 4096, 0, count, 16, s, p->d_fb_list, p->d_counter + 52);
 	if (forked) {
-		CK(cudaStreamWaitEvent(s, c->ev_join, 0));
+		CK(cudaStreamWaitEvent(s, c->ev_join, 0));   // (the segmented decode of the huge entries appends to the same list)
 	}
-	return rc;
+	return launch_inflate_cfg(c, p, d_archive, d_out, 32, 4096, 0, p->n_inflate, 16, s, p->d_fb_list, p->d_counter + 52);
 }
 
 static int dispatch_inflate(otz_ctx *c, otz_plan *p, const uint8_t *d_archive, uint8_t *d_out) {
@@ -762,7 +856,7 @@ extern "C" int otz_extract_run(otz_ctx *c, otz_plan *p, const uint8_t *d_archive
 			const int zsmem2 = (int)zl * ZS_LANE_STRIDE;
 			if (!zattr2) {
 				CK(cudaFuncSetAttribute(k_zstd_tok, cudaFuncAttributeMaxDynamicSharedMemorySize, zsmem2));
-				CK(cudaFuncSetAttribute(k_inflate_lz<4096, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(4 * sizeof(I2LzSmem<4096>))));
+				CK(cudaFuncSetAttribute(k_inflate_lz<4096, true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(4 * sizeof(I2LzSmem<4096>))));
 				zattr2 = true;
 			}
 			int per_sm = 0;
@@ -771,10 +865,10 @@ extern "C" int otz_extract_run(otz_ctx *c, otz_plan *p, const uint8_t *d_archive
 			k_zstd_tok<<<zgrid, 32, zsmem2, s>>>(d_archive, p->d_ents, p->d_est, p->d_status, p->d_zstd_list, p->n_zstd, c->d_ztok_cache,
 				p->d_ztok_ofs, p->d_ztokres, p->d_counter + 32, zl);
 			c->launches++;
-			CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_inflate_lz<4096, true>, 128, 4 * sizeof(I2LzSmem<4096>)));
+			CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_inflate_lz<4096, true, false>, 128, 4 * sizeof(I2LzSmem<4096>)));
 			const uint32_t lgrid = std::max(1u, std::min((uint32_t)(c->sm_count * std::max(per_sm, 1)), (p->n_zstd + 3) / 4));
-			k_inflate_lz<4096, true><<<lgrid, 128, 4 * sizeof(I2LzSmem<4096>), s>>>(d_out, p->d_ents, p->d_zstd_list, p->n_zstd, p->d_counter + 36,
-				c->d_ztok_cache, p->d_ztok_ofs, p->d_ztokres, p->d_status, p->d_produced);
+			k_inflate_lz<4096, true, false><<<lgrid, 128, 4 * sizeof(I2LzSmem<4096>), s>>>(d_out, p->d_ents, p->d_zstd_list, p->n_zstd, p->d_counter + 36,
+				c->d_ztok_cache, p->d_ztok_ofs, p->d_ztokres, p->d_status, p->d_produced, I2SegCtl{});
 			c->launches++;
 		} else {
 			const size_t zsmem = 4 * sizeof(ZstdSmem);

@@ -130,3 +130,24 @@ def test_many_uniform_streams_no_fallback(oracle):
     c = _ctx()
     _check(img, oracle, c, expect_fallbacks=0)
     c.close()
+
+
+def test_huge_streams_segmented(oracle):
+    """Entries >= 2 MiB: block-start search + one lane per block run + chain check (k_block_search / k_inflate_tok<true> /
+    k_seg_stitch) against the oracle, in shapes that stress the chain: many blocks, stored and fixed blocks in between,
+    full-flush points, an incompressible middle, a stream that is one single block."""
+    rnd = random.Random(9)
+    ms = [synth.member("h0", synth.jsonlog_text(5 << 20, 1), 8),
+          synth.member("h1", synth.jsonlog_text(3 << 20, 2), 8, level=1),
+          synth.member("h2", synth.jsonlog_text(3 << 20, 3), 8, level=9, ref_safe=False),
+          synth.member("h3", synth.jsonlog_text(2 << 20, 4) + synth.random_bytes(600000, 5) + synth.jsonlog_text(1 << 20, 6), 8),
+          synth.member("h4", synth.jsonlog_text(4 << 20, 7), 8, full_flush_every=300000),
+          synth.member("h5", synth.jsonlog_text(2500000, 8), 8, strategy=zlib.Z_FIXED),
+          synth.member("h6", b"".join(bytes([rnd.randrange(256)]) * rnd.randint(1, 2000) for _ in range(3000)), 8, strategy=zlib.Z_RLE),
+          synth.member("h7", synth.jsonlog_text(2200000, 10), 8, strategy=zlib.Z_HUFFMAN_ONLY)]
+    ms += [synth.member("s%d" % i, synth.jsonlog_text(rnd.randint(1000, 300000), 20 + i), 8) for i in range(30)]
+    img = synth.build_zip(ms)
+    c = _ctx()
+    fb, st, out = _check(img, oracle, c)
+    c.close()
+    assert fb <= 3, fb   # (the incompressible middle of h3 is stored blocks with payload: k_inflate takes that stream)
