@@ -1391,8 +1391,17 @@ __device__ __forceinline__ I2Batch i2_scan_batch(I2LzSmem<W> &S, int buf, uint32
 	const uint32_t near_m = __ballot_sync(0xFFFFFFFFu, is_match && !is_far);
 	B.n_far = __popc(far_m);
 	B.n_near = __popc(near_m);
-	if (is_match && !is_far) {
-		S.near_l[buf][__popc(near_m & lt_mask)] = make_uint2((mq & MASK) | (ml << 16), ((mq - dist) & MASK) | (dist << 16));   // near: dist < W <= 16 KiB
+	{
+		// x bit 31: this match and the near match before it are short, plain (distance >= length) and independent
+		// (it does not read what the other writes), so the executor runs the two as one step
+		const uint32_t before = near_m & lt_mask;
+		const int pl = before ? 31 - __clz(before) : 0;
+		const uint32_t pmq = __shfl_sync(0xFFFFFFFFu, mq, pl), pml = __shfl_sync(0xFFFFFFFFu, ml, pl), pdist = __shfl_sync(0xFFFFFFFFu, dist, pl);
+		if (is_match && !is_far) {
+			const uint32_t src = mq - dist;
+			const bool pair = before != 0u && dist >= ml && ml <= 32u && pdist >= pml && pml <= 32u && (src + ml <= pmq || src >= pmq + pml);
+			S.near_l[buf][__popc(before)] = make_uint2((mq & MASK) | (ml << 16) | (pair ? 0x80000000u : 0u), (src & MASK) | (dist << 16));   // near: dist < W <= 16 KiB
+		}
 	}
 	if (far_m) {
 		// staging vectors per far match (the source is copied as whole 16-byte vectors)
@@ -1565,14 +1574,35 @@ __global__ void __launch_bounds__(128) k_inflate_lz(uint8_t *__restrict__ out, c
 					}
 				}
 			}
-			// the rest in stream order, ring -> ring
+			// the rest in stream order, ring -> ring; two independent short matches per step where the scan said so
 			dn = S.near_l[buf][0];
 #pragma unroll 1
-			for (uint32_t f = 0; f < cur.n_near; f++) {
+			for (uint32_t f = 0; f < cur.n_near;) {
 				const uint2 d = dn;
-				dn = S.near_l[buf][(f + 1u) & 31u];
-				const uint32_t dqm = d.x & 0xFFFFu, len = d.x >> 16, sqm = d.y & 0xFFFFu, dd = d.y >> 16;
+				const uint2 d1 = S.near_l[buf][(f + 1u) & 31u];
+				const uint32_t dqm = d.x & 0xFFFFu, len = (d.x >> 16) & 0x1FFu, sqm = d.y & 0xFFFFu, dd = d.y >> 16;
 				__syncwarp();   // earlier ring stores are visible to the loads below
+				if (f + 1u < cur.n_near && (d1.x >> 31)) {
+					const uint32_t dqm1 = d1.x & 0xFFFFu, len1 = (d1.x >> 16) & 0x1FFu, sqm1 = d1.y & 0xFFFFu;
+					dn = S.near_l[buf][(f + 2u) & 31u];
+					uint8_t v0 = 0, v1 = 0;
+					if (lane < len) {
+						v0 = rb[(sqm + lane) & MASK];
+					}
+					if (lane < len1) {
+						v1 = rb[(sqm1 + lane) & MASK];
+					}
+					if (lane < len) {
+						rb[(dqm + lane) & MASK] = v0;
+					}
+					if (lane < len1) {
+						rb[(dqm1 + lane) & MASK] = v1;
+					}
+					f += 2;
+					continue;
+				}
+				dn = d1;
+				f += 1;
 				if (dd >= len) {
 					if (lane < len) {
 						rb[(dqm + lane) & MASK] = rb[(sqm + lane) & MASK];

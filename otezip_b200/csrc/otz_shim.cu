@@ -658,19 +658,11 @@ static int dispatch_inflate2(otz_ctx *c, otz_plan *p, const uint8_t *d_archive, 
 		CK(cudaStreamWaitEvent(s2, c->ev_fork, 0));
 		CK(cudaMemsetAsync(p->seg.count, 0, nh * 4, s2));
 		CK(cudaMemsetAsync(p->seg.n_items, 0, 4, s2));
-		const bool dbg = getenv("OTZ_DEBUG_SYNC") != nullptr;
-#define OTZ_DBG(name_)                                                                                     \
-	if (dbg) {                                                                                             \
-		cudaError_t e_ = cudaStreamSynchronize(s2);                                                        \
-		fprintf(stderr, "[otz] %s: %s\n", name_, cudaGetErrorString(e_));                                  \
-	}
 		CK(cudaMemsetAsync(p->d_counter + 59, 0, 4, s2));
 		k_block_search<<<c->sm_count * 8, 256, 0, s2>>>(d_archive, p->d_ents, p->d_est, p->d_status, p->d_inflate_list, nh, p->d_search_ofs, p->d_surv,
 			p->surv_cap, p->d_counter + 59);
 		k_block_verify<<<c->sm_count * 8, 256, 0, s2>>>(d_archive, p->d_ents, p->d_est, p->d_inflate_list, p->d_surv, p->surv_cap, p->d_counter + 59, p->seg);
-		OTZ_DBG("k_block_search");
 		k_seg_prepare<<<(nh + 63) / 64, 64, 0, s2>>>(p->d_ents, p->d_inflate_list, nh, p->d_tok_ofs, p->seg);
-		OTZ_DBG("k_seg_prepare");
 		const uint32_t sl = 12;   // lanes per warp: 8 warps x 12 table slots per SM
 		int per_sm2 = 0;
 		CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm2, k_inflate_tok<true>, 32, I2_SMEM_BYTES(sl)));
@@ -680,15 +672,11 @@ static int dispatch_inflate2(otz_ctx *c, otz_plan *p, const uint8_t *d_archive, 
 		}
 		k_inflate_tok<true><<<sgrid, 32, I2_SMEM_BYTES(sl), s2>>>(d_archive, p->d_ents, p->d_est, p->d_status, p->d_inflate_list, 0u, p->d_counter + 57,
 			c->d_tok_cache, p->d_tok_ofs, p->d_tokres, p->d_fb_list, p->d_counter + 52, sl, p->seg);
-		OTZ_DBG("k_inflate_tok<true>");
 		k_seg_stitch<<<(nh + 63) / 64, 64, 0, s2>>>(p->d_ents, p->d_status, p->d_inflate_list, nh, p->seg, p->d_fb_list, p->d_counter + 52);
-		OTZ_DBG("k_seg_stitch");
 		CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm2, k_inflate_lz<OTZ_SEG_RING, false, true>, 128, 4 * sizeof(I2LzSmem<OTZ_SEG_RING>)));
 		const uint32_t lgrid = std::max(1u, std::min((uint32_t)(c->sm_count * std::max(per_sm2, 1)), (nh + 3) / 4));
 		k_inflate_lz<OTZ_SEG_RING, false, true><<<lgrid, 128, 4 * sizeof(I2LzSmem<OTZ_SEG_RING>), s2>>>(d_out, p->d_ents, p->d_inflate_list, nh, p->d_counter + 58,
 			c->d_tok_cache, p->d_tok_ofs, p->d_tokres, p->d_status, p->d_produced, p->seg);
-		OTZ_DBG("k_inflate_lz<seg>");
-#undef OTZ_DBG
 		c->launches += 6;
 		CK(cudaGetLastError());
 		CK(cudaEventRecord(c->ev_join, s2));

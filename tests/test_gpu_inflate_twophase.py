@@ -132,7 +132,8 @@ def test_many_uniform_streams_no_fallback(oracle):
     c.close()
 
 
-def test_huge_streams_segmented(oracle):
+@pytest.mark.parametrize("seg_grid", [None, "2"])
+def test_huge_streams_segmented(oracle, seg_grid):
     """Entries >= 2 MiB: block-start search + one lane per block run + chain check (k_block_search / k_inflate_tok<true> /
     k_seg_stitch) against the oracle, in shapes that stress the chain: many blocks, stored and fixed blocks in between,
     full-flush points, an incompressible middle, a stream that is one single block."""
@@ -147,7 +148,12 @@ def test_huge_streams_segmented(oracle):
           synth.member("h7", synth.jsonlog_text(2200000, 10), 8, strategy=zlib.Z_HUFFMAN_ONLY)]
     ms += [synth.member("s%d" % i, synth.jsonlog_text(rnd.randint(1000, 300000), 20 + i), 8) for i in range(30)]
     img = synth.build_zip(ms)
-    c = _ctx()
-    fb, st, out = _check(img, oracle, c)
-    c.close()
+    if seg_grid:   # two warps for all segments: every lane decodes many segments one after the other
+        os.environ["OTZ_SEG_GRID"] = seg_grid
+    try:
+        c = _ctx()
+        fb, st, out = _check(img, oracle, c)
+        c.close()
+    finally:
+        os.environ.pop("OTZ_SEG_GRID", None)
     assert fb <= 3, fb   # (the incompressible middle of h3 is stored blocks with payload: k_inflate takes that stream)
