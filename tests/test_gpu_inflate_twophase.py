@@ -157,3 +157,46 @@ def test_huge_streams_segmented(oracle, seg_grid):
     finally:
         os.environ.pop("OTZ_SEG_GRID", None)
     assert fb <= 3, fb   # (the incompressible middle of h3 is stored blocks with payload: k_inflate takes that stream)
+
+
+def test_corrupt_huge_streams_same_status_as_one_kernel_decoder():
+    """Huge entries with flipped bits / cut tails / a planted fake block header: the segmented decode must end with
+    exactly the status words and bytes of the one-kernel decoder (it hands every stream whose chain does not close
+    to that decoder)."""
+    rnd = random.Random(12)
+    base = synth.jsonlog_text(3 << 20, 31)
+    good = synth.deflate_raw(base, 6)
+    ms = []
+    for i in range(10):
+        b = bytearray(good)
+        for _ in range(1 + i % 3):
+            b[rnd.randrange(len(b))] ^= 1 << rnd.randrange(8)
+        ms.append(synth.Member("flip%d" % i, 8, bytes(b), len(base), zlib.crc32(base) & 0xFFFFFFFF))
+    for i in range(4):
+        ms.append(synth.Member("cut%d" % i, 8, good[:len(good) - rnd.randrange(1, len(good) // 2)], len(base), zlib.crc32(base) & 0xFFFFFFFF))
+    ms.append(synth.Member("wrongsize", 8, good, len(base) - 5, zlib.crc32(base) & 0xFFFFFFFF))
+    ms.append(synth.Member("short", 8, good, len(base) + 100, zlib.crc32(base + b"\0" * 100) & 0xFFFFFFFF))
+    # a valid dynamic-block header (copied from the stream's own first block) planted inside incompressible data:
+    # the search finds it, the chain must not follow it
+    noise = synth.random_bytes(200000, 6)
+    planted = noise[:100000] + good[:4000] + noise[100000:]
+    d2 = base[:1 << 20] + planted + base[1 << 20:]
+    ms.append(synth.member("planted", d2, 8))
+    ms.append(synth.member("ok", base, 8))
+    img = synth.build_zip(ms)
+    tab = parse_central(img)
+    a = _ctx()
+    out_a, crc_a, st_a = a.extract_host(img, tab, default_opts())
+    a.close()
+    b = _ctx(mode="legacy")
+    out_b, crc_b, st_b = b.extract_host(img, tab, default_opts())
+    b.close()
+    assert np.array_equal(st_a, st_b), (list(map(hex, st_a)), list(map(hex, st_b)))
+    n_ok = 0
+    for i in range(len(tab)):
+        if (int(st_a[i]) & 0xFF) == 0:
+            n, o = int(tab["uncomp_size"][i]), int(tab["out_ofs"][i])
+            assert np.array_equal(out_a[o:o + n], out_b[o:o + n]), i
+            assert int(crc_a[i]) == int(crc_b[i])
+            n_ok += 1
+    assert n_ok >= 3
