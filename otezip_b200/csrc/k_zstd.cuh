@@ -129,19 +129,18 @@ struct ZsBackW {
 	uint32_t w0, w1, w2; // words k-2, k-1, k
 	uint32_t wm;         // word k-3, loaded one step ahead of its use
 
-	__device__ __forceinline__ uint32_t load(int32_t i) const {
-		if (i < 0) {
-			return 0u;   // below the stream: zeros (RFC 8878 4.1: a short read is zero filled)
-		}
-		const uint32_t v = __ldg(w + i);
-		return i == 0 ? (v >> low) << low : v;
-	}
+	// word i of the stream; below the stream zeros (RFC 8878 4.1: a short read is zero filled).  raw(): the bits of
+	// word 0 that precede the stream are still in it — fix0() clears them when the word is taken into use, so that
+	// the look-ahead load is not waited for at the moment it is issued
+	__device__ __forceinline__ uint32_t raw(int32_t i) const { return i < 0 ? 0u : __ldg(w + i); }
+	__device__ __forceinline__ uint32_t fix0(uint32_t v, int32_t i) const { return i == 0 ? (v >> low) << low : v; }
+	__device__ __forceinline__ uint32_t load(int32_t i) const { return fix0(raw(i), i); }
 	__device__ __forceinline__ void reload() {
 		k = (apos - 1) >> 5;
 		w2 = load(k);
 		w1 = load(k - 1);
 		w0 = load(k - 2);
-		wm = load(k - 3);
+		wm = raw(k - 3);
 	}
 	__device__ __forceinline__ bool init(const uint8_t *base, uint32_t n) {
 		const uint64_t a = reinterpret_cast<uint64_t>(base);
@@ -171,9 +170,9 @@ struct ZsBackW {
 			if (nk == k - 1) {
 				w2 = w1;
 				w1 = w0;
-				w0 = wm;
 				k = nk;
-				wm = load(k - 3);   // not needed before the next step down
+				w0 = fix0(wm, k - 2);
+				wm = raw(k - 3);   // not needed before the next step down
 			} else {
 				reload();
 			}
