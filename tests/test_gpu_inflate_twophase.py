@@ -200,3 +200,37 @@ def test_corrupt_huge_streams_same_status_as_one_kernel_decoder():
             assert int(crc_a[i]) == int(crc_b[i])
             n_ok += 1
     assert n_ok >= 3
+
+
+def test_random_encoder_settings_match_oracle(oracle):
+    """Streams from every corner of zlib's parameter space — window 512 B..32 KiB, memLevel 1..9 (memLevel 1 ends a block
+    every 128 symbols: thousands of block headers per entry), all levels and strategies, sync / full flushes at random
+    points — through the lane-per-stream path, against the oracle."""
+    rnd = random.Random(77)
+    ms = []
+    for i in range(160):
+        n = rnd.choice([0, 1, 17, 300, 5000, 40000, 150000, 400000])
+        kind = rnd.randrange(4)
+        if kind == 0:
+            d = synth.jsonlog_text(n, 300 + i)
+        elif kind == 1:
+            d = synth.random_bytes(n, i)
+        elif kind == 2:
+            d = bytes((rnd.randrange(256) if rnd.random() < 0.3 else 65) for _ in range(n))
+        else:
+            d = (synth.jsonlog_text(max(n // 3, 1), i) * 3)[:n]
+        c = zlib.compressobj(rnd.choice([1, 2, 4, 6, 9]), zlib.DEFLATED, -rnd.randint(9, 15), rnd.randint(1, 9),
+                             rnd.choice([zlib.Z_DEFAULT_STRATEGY, zlib.Z_FILTERED, zlib.Z_HUFFMAN_ONLY, zlib.Z_RLE, zlib.Z_FIXED]))
+        parts, o = [], 0
+        while o < len(d):
+            step = rnd.randint(1, max(1, len(d)))
+            parts.append(c.compress(d[o:o + step]))
+            o += step
+            if rnd.random() < 0.3:
+                parts.append(c.flush(rnd.choice([zlib.Z_SYNC_FLUSH, zlib.Z_FULL_FLUSH])))
+        parts.append(c.flush())
+        ms.append(synth.Member("r%d" % i, 8, b"".join(parts), len(d), zlib.crc32(d) & 0xFFFFFFFF, raw=d))
+    img = synth.build_zip(ms)
+    c = _ctx()
+    _check(img, oracle, c)
+    c.close()
