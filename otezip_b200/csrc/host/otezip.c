@@ -74,6 +74,8 @@ struct otz_archive {
 	uint64_t image_len;
 	struct otz_window *windows;
 	int32_t *last_status;
+	uint64_t *lfh64;              /* local header offset of every entry (ZIP64: may exceed the public u32 field) */
+	uint64_t lfh64_cap;
 	/* write side */
 	struct otz_pending *pend;     /* parallel to pub.entries for entries added in this session */
 	zip_uint64_t n_existing;      /* entries loaded from an existing archive (append mode) */
@@ -114,6 +116,14 @@ static struct otz_archive *priv(zip_t *za) {
 
 static int is_valid(const zip_t *za) {
 	return za != NULL && za->fp != NULL; /* otezip.c:687-689 */
+}
+
+#define OTZ_MAX_ENTRIES (1ull << 24)   /* ZIP64 lifts the 65,535 of the EOCD; this bounds the entry table */
+
+/* local header offset of entry i: 64-bit (the public struct otezip_entry keeps the reference's u32 field) */
+static uint64_t entry_lfh(const zip_t *za, zip_uint64_t i) {
+	const struct otz_archive *a = (const struct otz_archive *)za;
+	return (a->magic == OTZ_MAGIC && a->lfh64 && i < a->lfh64_cap) ? a->lfh64[i] : za->entries[i].local_hdr_ofs;
 }
 
 /* ---- method names, otezip.c:112-154 (only what this build implements) ---- */
@@ -159,8 +169,13 @@ static int read_at(FILE *fp, long ofs, void *dst, size_t n) {
 	return fread (dst, 1, n, fp) == n ? 0 : -1;
 }
 
-/* otezip.c:199-272: newest EOCD whose directory range lies in the file and starts with a CDH */
-static int find_eocd(FILE *fp, long file_size, uint32_t *cd_size, uint32_t *cd_ofs, uint16_t *n_entries) {
+/* otezip.c:199-272: newest EOCD whose directory range lies in the file and starts with a CDH.
+ * Beyond the reference: when the EOCD carries the ZIP64 escape values (0xFFFF entries,
+ * 0xFFFFFFFF size or offset) the ZIP64 locator in front of it and the ZIP64 end-of-central-directory record it points
+ * to (APPNOTE 4.3.14-4.3.15) supply the 64-bit count, size and offset. */
+#define SIG_EOCD64 0x06064b50u
+#define SIG_EOCD64_LOC 0x07064b50u
+static int find_eocd(FILE *fp, long file_size, uint64_t *cd_size, uint64_t *cd_ofs, uint64_t *n_entries) {
 	if (file_size < 22) {
 		return ERR_INCONS;
 	}
@@ -178,9 +193,23 @@ static int find_eocd(FILE *fp, long file_size, uint32_t *cd_size, uint32_t *cd_o
 		if (otezip_read_le32 (tail + i) != SIG_EOCD) {
 			continue;
 		}
-		uint16_t ents = otezip_read_le16 (tail + i + 10);
-		uint32_t sz = otezip_read_le32 (tail + i + 12), ofs = otezip_read_le32 (tail + i + 16);
-		if (ofs > (uint32_t)file_size || (uint64_t)ofs + sz > (uint64_t)file_size) {
+		uint64_t ents = otezip_read_le16 (tail + i + 10);
+		uint64_t sz = otezip_read_le32 (tail + i + 12), ofs = otezip_read_le32 (tail + i + 16);
+		if (ents == 0xFFFFu || sz == 0xFFFFFFFFu || ofs == 0xFFFFFFFFu) {
+			const long eocd_pos = file_size - (long)span + (long)i;
+			uint8_t loc[20], rec[56];
+			if (eocd_pos < 20 || read_at (fp, eocd_pos - 20, loc, 20) != 0 || otezip_read_le32 (loc) != SIG_EOCD64_LOC) {
+				continue;
+			}
+			const uint64_t rpos = (uint64_t)otezip_read_le32 (loc + 8) | ((uint64_t)otezip_read_le32 (loc + 12) << 32);
+			if (rpos + 56 > (uint64_t)file_size || read_at (fp, (long)rpos, rec, 56) != 0 || otezip_read_le32 (rec) != SIG_EOCD64) {
+				continue;
+			}
+			ents = (uint64_t)otezip_read_le32 (rec + 32) | ((uint64_t)otezip_read_le32 (rec + 36) << 32);
+			sz = (uint64_t)otezip_read_le32 (rec + 40) | ((uint64_t)otezip_read_le32 (rec + 44) << 32);
+			ofs = (uint64_t)otezip_read_le32 (rec + 48) | ((uint64_t)otezip_read_le32 (rec + 52) << 32);
+		}
+		if (ofs > (uint64_t)file_size || sz > (uint64_t)file_size || ofs + sz > (uint64_t)file_size) {
 			continue;
 		}
 		if (ents > 0 && sz >= 4) {
@@ -209,13 +238,12 @@ static int load_central(struct otz_archive *a) {
 	if (fsz < 0) {
 		return ERR_READ;
 	}
-	uint32_t cd_size = 0, cd_ofs = 0;
-	uint16_t n = 0;
+	uint64_t cd_size = 0, cd_ofs = 0, n = 0;
 	int rc = find_eocd (za->fp, fsz, &cd_size, &cd_ofs, &n);
 	if (rc != 0) {
 		return rc;
 	}
-	if ((uint64_t)cd_ofs + cd_size > (uint64_t)fsz) {
+	if (cd_ofs + cd_size > (uint64_t)fsz || n > OTZ_MAX_ENTRIES) {
 		return ERR_INCONS;
 	}
 	a->append_ofs = cd_ofs;
@@ -238,13 +266,15 @@ static int load_central(struct otz_archive *a) {
 		return ERR_INCONS;
 	}
 	za->entries = (struct otezip_entry *)calloc (n, sizeof (struct otezip_entry));
-	if (!za->entries) {
+	a->lfh64 = (uint64_t *)calloc (n, sizeof (uint64_t));
+	a->lfh64_cap = n;
+	if (!za->entries || !a->lfh64) {
 		free (cd);
 		return ERR_READ;
 	}
 	za->n_entries = n;
 	size_t off = 0;
-	for (uint32_t i = 0; i < n; i++) {
+	for (uint64_t i = 0; i < n; i++) {
 		if (off + 46 > cd_size || otezip_read_le32 (cd + off) != SIG_CDH) {
 			free (cd);
 			return ERR_INCONS;
@@ -264,10 +294,58 @@ static int load_central(struct otz_archive *a) {
 		e->uncomp_size = otezip_read_le32 (h + 24);
 		e->external_attr = otezip_read_le32 (h + 38);
 		e->local_hdr_ofs = otezip_read_le32 (h + 42);
-		if ((uint64_t)e->comp_size > MAX_PAYLOAD || (uint64_t)e->uncomp_size > MAX_PAYLOAD) {
+		uint64_t comp64 = e->comp_size, uncomp64 = e->uncomp_size, lfh = e->local_hdr_ofs;
+		if (e->comp_size == 0xFFFFFFFFu || e->uncomp_size == 0xFFFFFFFFu || e->local_hdr_ofs == 0xFFFFFFFFu) {
+			/* ZIP64 extended information (APPNOTE 4.5.3): the escaped fields, in this order, 8 bytes each */
+			const uint8_t *x = h + 46 + fl;
+			size_t xo = 0;
+			int found = 0;
+			while (xo + 4 <= xl) {
+				const size_t id = otezip_read_le16 (x + xo), sz = otezip_read_le16 (x + xo + 2);
+				if (xo + 4 + sz > xl) {
+					break;
+				}
+				if (id == 0x0001) {
+					size_t q = xo + 4;
+					const size_t end = xo + 4 + sz;
+					found = 1;
+					if (e->uncomp_size == 0xFFFFFFFFu) {
+						found = found && q + 8 <= end;
+						if (found) {
+							uncomp64 = (uint64_t)otezip_read_le32 (x + q) | ((uint64_t)otezip_read_le32 (x + q + 4) << 32);
+							q += 8;
+						}
+					}
+					if (found && e->comp_size == 0xFFFFFFFFu) {
+						found = q + 8 <= end;
+						if (found) {
+							comp64 = (uint64_t)otezip_read_le32 (x + q) | ((uint64_t)otezip_read_le32 (x + q + 4) << 32);
+							q += 8;
+						}
+					}
+					if (found && e->local_hdr_ofs == 0xFFFFFFFFu) {
+						found = q + 8 <= end;
+						if (found) {
+							lfh = (uint64_t)otezip_read_le32 (x + q) | ((uint64_t)otezip_read_le32 (x + q + 4) << 32);
+						}
+					}
+					break;
+				}
+				xo += 4 + sz;
+			}
+			if (!found) {
+				free (cd);
+				return ERR_INCONS;
+			}
+		}
+		if (comp64 > MAX_PAYLOAD || uncomp64 > MAX_PAYLOAD) {
 			free (cd);
 			return ERR_INCONS;
 		}
+		e->comp_size = (uint32_t)comp64;
+		e->uncomp_size = (uint32_t)uncomp64;
+		e->local_hdr_ofs = (uint32_t)lfh;   /* public field: low 32 bits; a->lfh64[] is what the library uses */
+		a->lfh64[i] = lfh;
 		e->name = (char *)malloc (fl + 1);
 		if (!e->name) {
 			free (cd);
@@ -291,7 +369,7 @@ zip_uint64_t otezip_b200_entry_table(zip_t *za, void *rows, zip_uint64_t max_row
 	zip_uint64_t n = za->n_entries < max_rows ? za->n_entries : max_rows;
 	for (zip_uint64_t i = 0; i < n; i++) {
 		const struct otezip_entry *e = &za->entries[i];
-		t[i].lfh_ofs = e->local_hdr_ofs;
+		t[i].lfh_ofs = entry_lfh (za, i);
 		t[i].out_ofs = out;
 		t[i].comp_size = e->comp_size;
 		t[i].uncomp_size = e->uncomp_size;
@@ -431,6 +509,7 @@ int zip_close(zip_t *za) {
 		otz_host_free (a->image);
 	}
 	free (a->last_status);
+	free (a->lfh64);
 	free (a->path);
 	a->magic = 0;
 	free (a);
@@ -570,15 +649,16 @@ static int load_image(struct otz_archive *a) {
  * chunks (>= 2) and points *csize at the u32 LE array inside the image, or 0 when the entry has no usable index. */
 static uint32_t chunk_index_of(const struct otz_archive *a, const struct otezip_entry *e, uint32_t *chunk_bytes, const uint8_t **csize,
 	uint64_t *data_ofs) {
-	if (!index_enabled () || e->method != OTEZIP_METHOD_DEFLATE || (uint64_t)e->local_hdr_ofs + 30 > a->image_len) {
+	const uint64_t lfh_ofs = entry_lfh (&a->pub, (zip_uint64_t)(e - a->pub.entries));
+	if (!index_enabled () || e->method != OTEZIP_METHOD_DEFLATE || lfh_ofs + 30 > a->image_len) {
 		return 0;
 	}
-	const uint8_t *lfh = a->image + e->local_hdr_ofs;
+	const uint8_t *lfh = a->image + lfh_ofs;
 	if (otezip_read_le32 (lfh) != SIG_LFH) {
 		return 0;
 	}
 	const uint64_t nl = otezip_read_le16 (lfh + 26), xl = otezip_read_le16 (lfh + 28);
-	const uint64_t xofs = (uint64_t)e->local_hdr_ofs + 30 + nl;
+	const uint64_t xofs = lfh_ofs + 30 + nl;
 	if (xofs + xl + e->comp_size > a->image_len) {
 		return 0;
 	}
@@ -661,7 +741,7 @@ static struct otz_window *run_window(struct otz_archive *a, zip_uint64_t index) 
 	uint32_t next_row = n; /* chunk rows follow the n entry rows */
 	for (uint32_t k = 0; k < n; k++) {
 		const struct otezip_entry *e = &za->entries[index + k];
-		tab[k].lfh_ofs = e->local_hdr_ofs;
+		tab[k].lfh_ofs = entry_lfh (za, index + k);
 		tab[k].out_ofs = out;
 		tab[k].comp_size = e->comp_size;
 		tab[k].uncomp_size = e->uncomp_size;
@@ -1028,14 +1108,15 @@ static int write_lfh(FILE *fp, const struct otezip_entry *e, const uint8_t *extr
 		: -1;
 }
 
-/* otezip.c:1494-1558 */
-static uint32_t write_cdh(FILE *fp, const struct otezip_entry *e) {
-	uint8_t h[46];
+/* otezip.c:1494-1558; a local header beyond 4 GiB is written as the ZIP64 escape + extended information field */
+static uint32_t write_cdh(FILE *fp, const struct otezip_entry *e, uint64_t lfh_ofs) {
+	uint8_t h[46], x[12];
 	size_t nl = strlen (e->name);
+	const int z64 = lfh_ofs >= 0xFFFFFFFFULL;
 	memset (h, 0, sizeof (h));
 	otezip_write_le32 (h, SIG_CDH);
 	otezip_write_le16 (h + 4, 0x031e);
-	otezip_write_le16 (h + 6, 20);
+	otezip_write_le16 (h + 6, z64 ? 45 : 20);
 	otezip_write_le16 (h + 10, e->method);
 	otezip_write_le16 (h + 12, e->file_time);
 	otezip_write_le16 (h + 14, e->file_date);
@@ -1043,11 +1124,19 @@ static uint32_t write_cdh(FILE *fp, const struct otezip_entry *e) {
 	otezip_write_le32 (h + 20, e->comp_size);
 	otezip_write_le32 (h + 24, e->uncomp_size);
 	otezip_write_le16 (h + 28, (uint16_t)nl);
+	otezip_write_le16 (h + 30, z64 ? 12 : 0);
 	otezip_write_le32 (h + 38, e->external_attr);
-	otezip_write_le32 (h + 42, e->local_hdr_ofs);
+	otezip_write_le32 (h + 42, z64 ? 0xFFFFFFFFu : (uint32_t)lfh_ofs);
 	fwrite (h, 1, 46, fp);
 	fwrite (e->name, 1, nl, fp);
-	return (uint32_t)(46 + nl);
+	if (z64) {
+		otezip_write_le16 (x, 0x0001);
+		otezip_write_le16 (x + 2, 8);
+		otezip_write_le32 (x + 4, (uint32_t)lfh_ofs);
+		otezip_write_le32 (x + 8, (uint32_t)(lfh_ofs >> 32));
+		fwrite (x, 1, 12, fp);
+	}
+	return (uint32_t)(46 + nl + (z64 ? 12 : 0));
 }
 
 /* zip_close of a written archive: one GPU batch (CRC + DEFLATE/STORE decision), then LFH+payload per
@@ -1063,6 +1152,14 @@ static int finalize_archive(struct otz_archive *a) {
 	uint64_t pos = a->n_existing ? a->append_ofs : 0;
 	if (fseek (za->fp, (long)pos, SEEK_SET) != 0) {
 		return -1;
+	}
+	if (za->n_entries > a->lfh64_cap) {
+		uint64_t *nl64 = (uint64_t *)realloc (a->lfh64, za->n_entries * sizeof (uint64_t));
+		if (!nl64) {
+			return -1;
+		}
+		a->lfh64 = nl64;
+		a->lfh64_cap = za->n_entries;
 	}
 	if (n_new) {
 		otz_ctx *ctx = otezip_b200_ctx ();
@@ -1137,11 +1234,8 @@ static int finalize_archive(struct otz_archive *a) {
 			e->crc32 = crc[k];
 			e->comp_size = out_size[k];
 			e->method = method_out[k];
-			if (pos > 0xFFFFFFFFULL) { /* otezip.c:1140 */
-				ok = 0;
-				break;
-			}
-			e->local_hdr_ofs = (uint32_t)pos;
+			e->local_hdr_ofs = (uint32_t)pos;   /* (the reference gives up beyond 4 GiB, otezip.c:1140; ZIP64 here) */
+			a->lfh64[a->n_existing + k] = pos;
 			/* chunk index for multi-chunk DEFLATE entries */
 			uint8_t *extra = NULL;
 			uint16_t extra_len = 0;
@@ -1177,23 +1271,44 @@ static int finalize_archive(struct otz_archive *a) {
 		}
 	}
 	{
-		if (pos > 0xFFFFFFFFULL) { /* otezip.c:1264 */
-			goto done;
-		}
 		uint64_t cd_size = 0;
 		for (zip_uint64_t i = 0; i < za->n_entries; i++) {
-			cd_size += write_cdh (za->fp, &za->entries[i]);
-			if (cd_size > 0xFFFFFFFFULL) {
+			cd_size += write_cdh (za->fp, &za->entries[i], entry_lfh (za, i));
+		}
+		/* otezip.c:1561-1590 truncates the counts to 16 bits and fails beyond 4 GiB (:1264); here the ZIP64 record and
+		 * locator (APPNOTE 4.3.14-4.3.15) are written whenever a field does not fit */
+		const int z64 = za->n_entries >= 0xFFFFu || pos >= 0xFFFFFFFFULL || cd_size >= 0xFFFFFFFFULL;
+		if (z64) {
+			uint8_t r[56 + 20];
+			memset (r, 0, sizeof (r));
+			otezip_write_le32 (r, SIG_EOCD64);
+			otezip_write_le32 (r + 4, 44);          /* size of the record after this field (low word) */
+			otezip_write_le16 (r + 12, 0x031e);
+			otezip_write_le16 (r + 14, 45);
+			otezip_write_le32 (r + 24, (uint32_t)za->n_entries);
+			otezip_write_le32 (r + 28, (uint32_t)(za->n_entries >> 32));
+			otezip_write_le32 (r + 32, (uint32_t)za->n_entries);
+			otezip_write_le32 (r + 36, (uint32_t)(za->n_entries >> 32));
+			otezip_write_le32 (r + 40, (uint32_t)cd_size);
+			otezip_write_le32 (r + 44, (uint32_t)(cd_size >> 32));
+			otezip_write_le32 (r + 48, (uint32_t)pos);
+			otezip_write_le32 (r + 52, (uint32_t)(pos >> 32));
+			const uint64_t rpos = pos + cd_size;
+			otezip_write_le32 (r + 56, SIG_EOCD64_LOC);
+			otezip_write_le32 (r + 56 + 8, (uint32_t)rpos);
+			otezip_write_le32 (r + 56 + 12, (uint32_t)(rpos >> 32));
+			otezip_write_le32 (r + 56 + 16, 1);
+			if (fwrite (r, 1, sizeof (r), za->fp) != sizeof (r)) {
 				goto done;
 			}
 		}
 		uint8_t eocd[22];
 		memset (eocd, 0, sizeof (eocd));
 		otezip_write_le32 (eocd, SIG_EOCD);
-		otezip_write_le16 (eocd + 8, (uint16_t)za->n_entries);
-		otezip_write_le16 (eocd + 10, (uint16_t)za->n_entries);
-		otezip_write_le32 (eocd + 12, (uint32_t)cd_size);
-		otezip_write_le32 (eocd + 16, (uint32_t)pos);
+		otezip_write_le16 (eocd + 8, za->n_entries >= 0xFFFFu ? 0xFFFFu : (uint16_t)za->n_entries);
+		otezip_write_le16 (eocd + 10, za->n_entries >= 0xFFFFu ? 0xFFFFu : (uint16_t)za->n_entries);
+		otezip_write_le32 (eocd + 12, cd_size >= 0xFFFFFFFFULL ? 0xFFFFFFFFu : (uint32_t)cd_size);
+		otezip_write_le32 (eocd + 16, pos >= 0xFFFFFFFFULL ? 0xFFFFFFFFu : (uint32_t)pos);
 		if (fwrite (eocd, 1, 22, za->fp) != 22) {
 			goto done;
 		}

@@ -152,6 +152,12 @@ def parse_central(img) -> np.ndarray:
     while i >= 0:
         if tail[i:i + 4] == b"PK\x05\x06":
             ents, sz, ofs = struct.unpack_from("<HII", tail, i + 10)
+            if ents == 0xFFFF or sz == 0xFFFFFFFF or ofs == 0xFFFFFFFF:   # ZIP64: locator + 64-bit record
+                p = lo + i
+                if p >= 20 and bytes(b[p - 20:p - 16]) == b"PK\x06\x07":
+                    rpos = struct.unpack_from("<Q", b, p - 12)[0]
+                    if rpos + 56 <= n and bytes(b[rpos:rpos + 4]) == b"PK\x06\x06":
+                        ents, sz, ofs = struct.unpack_from("<QQQ", b, rpos + 32)
             if ofs + sz <= n and (ents == 0 or bytes(b[ofs:ofs + 4]) == b"PK\x01\x02"):
                 pos = lo + i
                 break
@@ -165,6 +171,23 @@ def parse_central(img) -> np.ndarray:
         (sig, _, _, _, method, _, _, crc, comp, uncomp, fl, xl, cl, _, _, _, lfh) = struct.unpack_from(
             "<IHHHHHHIIIHHHHHII", b, off)
         assert sig == 0x02014B50
+        if comp == 0xFFFFFFFF or uncomp == 0xFFFFFFFF or lfh == 0xFFFFFFFF:   # ZIP64 extended information
+            x = bytes(b[off + 46 + fl:off + 46 + fl + xl])
+            o = 0
+            while o + 4 <= len(x):
+                hid, hsz = struct.unpack_from("<HH", x, o)
+                if hid == 1:
+                    q = o + 4
+                    if uncomp == 0xFFFFFFFF:
+                        uncomp = struct.unpack_from("<Q", x, q)[0]
+                        q += 8
+                    if comp == 0xFFFFFFFF:
+                        comp = struct.unpack_from("<Q", x, q)[0]
+                        q += 8
+                    if lfh == 0xFFFFFFFF:
+                        lfh = struct.unpack_from("<Q", x, q)[0]
+                    break
+                o += 4 + hsz
         tab[k] = (lfh, out, comp, uncomp, crc, method, 0)
         out += (uncomp + 15) & ~15
         off += 46 + fl + xl + cl
