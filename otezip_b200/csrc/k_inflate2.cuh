@@ -7,20 +7,25 @@
 //
 //   phase A  k_inflate_tok   Huffman decoding is a serial bit chain per stream, so a warp that decodes one
 //            stream spends 32 lanes on one symbol.  Here every lane of a warp owns a different stream: its
-//            own bit reader (32-bit words of the stream, two words of look-ahead in registers), its own
-//            16-bit two-level tables in shared memory (9-bit / 7-bit roots, 1796 bytes per lane, bank-skewed)
-//            and it emits, per stream, the literal bytes (dense, packed four per store) and one 32-bit
-//            sequence record per match {literal run : 9, length-3 : 8, distance-1 : 15}.  All lanes step in
-//            lock-step through literal / length+distance / end-of-block, so one warp instruction advances up
-//            to 32 streams.  Dynamic block headers (dec:122-266) are parsed by the lanes that need one, all at
-//            the same time; the decoding tables are then built by the whole warp, one lane's block at a time
-//            (code lengths in registers, canonical order by match_any ranks, every table slot computed
-//            independently from the 15-bit left-aligned code boundaries).
+//            own bit reader (64-bit window in registers; the stream is staged through a per-lane shared-memory
+//            ring of eight 16-byte vectors filled by cp.async three vectors ahead), its own 16-bit two-level
+//            tables in shared memory (9-bit / 7-bit roots, 1796 bytes per lane, bank-skewed) and it emits, per
+//            stream, the literal bytes (dense) and one 32-bit sequence record per match
+//            {literal run : 9, length-3 : 8, distance-1 : 15}.  All lanes step in lock-step through straight-
+//            line code — one literal/length look-up and one distance look-up per step, the step software-
+//            pipelined over two iterations (parse step i, emit step i-1), everything unusual behind one warp
+//            vote — so one warp instruction advances up to 28 streams.  Dynamic block headers (dec:122-266) are
+//            parsed by the lanes that need one, all at the same time; the decoding tables are then built by the
+//            whole warp, one lane's block at a time (code lengths in registers, canonical order by match_any
+//            ranks, every table slot computed independently from the 15-bit left-aligned code boundaries).
 //   phase B  k_inflate_lz    one warp per stream executes the sequences: 32 records per coalesced load, warp
-//            prefix sums give every record its output position, literal runs are placed in parallel, matches
-//            whose source has already left the shared-memory ring are fetched from HBM/L2 four at a time
-//            (independent of the batch being produced), the rest run ring -> ring in order; completed
-//            512-byte segments leave as coalesced 16-byte stores.
+//            prefix sums give every record its literal and output position; two batches are in flight — while
+//            batch k executes, batch k+1 has been scanned, its match descriptors compacted into near / far
+//            lists and the sources of its far matches (those that left the shared-memory ring) are on their
+//            way into a staging buffer by cp.async — so executing a batch touches shared memory only; near
+//            matches run ring -> ring in stream order; completed 512-byte segments leave as coalesced 16-byte
+//            stores.  The same kernel executes Zstandard sequences (8-byte records, k_zstd.cuh) and the token
+//            chains of segmented huge streams (below).
 //
 // Phase A only commits streams that are plainly valid: final block reached, exactly uncomp_size bytes, no
 // stored block with payload, tables within the fixed budget.  Anything else (errors, short streams, stored

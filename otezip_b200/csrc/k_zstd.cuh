@@ -1,4 +1,4 @@
-// k_zstd.cuh — Zstandard (RFC 8878) frame decoder, one warp per entry.
+// k_zstd.cuh — Zstandard (RFC 8878) frame decoders.
 //
 // The reference's method 93 is NOT Zstandard: it accepts only its own raw-block container
 // (/root/reference/src/lib/zstd.inc.c:479-705) and rejects real frames; k_zstdref reproduces
@@ -8,12 +8,15 @@
 // reference rejects"), so the default reference-compatible policy still matches the reference bit for bit.
 // Parity for this kernel is pinned against libzstd 1.5.5 (tests/test_gpu_zstd.py), not against the reference.
 //
-// Work split inside the warp (first correct version, not tuned):
-//   * lane 0 parses headers and builds the FSE / Huffman tables in shared memory;
-//   * Huffman literals: the 4 streams of a block are decoded by lanes 0..3 into a per-warp scratch in HBM;
-//   * sequences: lane 0 runs the three interleaved FSE states over the backward bitstream and queues up to 32
-//     (literal length, match length, offset) triples in shared memory, then all lanes execute them
-//     (literal copy from the scratch, match copy from the output already written).
+// Two decoders live here.
+//   * k_zstd_tok + k_inflate_lz<W, true> (default): ONE LANE per entry parses everything — headers, FSE / Huffman
+//     tables in its own shared-memory slot, literals, sequences — and emits tokens (literal bytes + 8-byte sequence
+//     records); the lanes of a warp run on different entries in lock-step; the LZ executor of the inflate path
+//     (k_inflate2.cuh) then writes the bytes.  See zstd_tok_entry.
+//   * k_zstd (OTZ_ZSTD_MODE=legacy, or when the token scratch cannot be allocated): one warp per entry; lane 0 parses
+//     headers, builds the tables and runs the three interleaved FSE states, lanes 0..3 decode the 4 Huffman literal
+//     streams into a per-warp HBM scratch, all lanes execute batches of 32 sequences straight in HBM.
+// Both use the word-based backward bit reader ZsBackW (one 64-bit window per sequence / per five Huffman symbols).
 #pragma once
 #include "otz_common.cuh"
 #include "k_copy.cuh"
