@@ -499,7 +499,7 @@ def run_c5(args, dist: "Dist"):
 
 DECODE_KERNELS = {
     "c1": "k_inflate_tok + k_inflate_lz (+ k_inflate for declined / huge streams)",
-    "c3": "k_inflate_tok + k_inflate_lz (+ k_inflate for declined / huge streams)",
+    "c3": "k_inflate_tok + k_inflate_lz; entries >= 1 MiB: k_block_search + k_inflate_tok<segments> + k_inflate_lz<symbols> + k_seg_window + k_seg_translate",
     "c3w": "k_inflate_tok + k_inflate_lz (+ k_inflate for declined / huge streams)",
     "c4": "k_zstdref", "c4z": "k_zstd", "c2": "k_store_copy", "c2x": "k_store_copy",
 }

@@ -356,6 +356,7 @@ __device__ __noinline__ int i2_build_table(I2WarpScratch &S, const uint32_t (&le
 // chain.  Nothing depends on the search being right — a wrong candidate is skipped (the decoder that passes it marks
 // it dead) or fails the chain, and the stream then goes to k_inflate like every other declined stream.
 #define I2_MAXSEG 256
+#define I2_PREWIN 32768u   // elements of history a segment may refer to (DEFLATE window)
 #define I2_SEGF_OK 1u
 #define I2_SEGF_FINAL 2u
 #define I2_SEGF_DEAD 4u
@@ -379,6 +380,15 @@ struct I2SegCtl {
 	uint32_t *live;      // [n_huge][I2_MAXSEG] the chain of segments that make up the stream
 	uint32_t *nlive;     // [n_huge] length of the chain (0 = the stream was declined)
 	int32_t *seg_status; // [n_huge] status word of an accepted stream
+	// parallel execution of the chain (k_inflate_lz<.., PAR> + k_seg_window + k_seg_translate)
+	uint32_t *par;       // [n_huge] 1 = the segments of the stream are executed in parallel into the symbol buffer
+	uint32_t *par_items; // work list: stream << 16 | position in the chain
+	uint32_t *n_par;
+	uint64_t *sym_start; // [n_huge][I2_MAXSEG] by chain position: first element of the segment in the symbol buffer
+	uint32_t *out_start; // [n_huge][I2_MAXSEG] by chain position: first output byte of the segment in the entry
+	unsigned long long *sym_top;   // bump allocator of the symbol buffer (elements)
+	uint64_t sym_cap;    // its capacity (0 = no parallel execution)
+	uint32_t out_mis;    // address of the output arena & 15
 };
 
 // ------------------------------------------------------------------------------------------------
@@ -1199,6 +1209,7 @@ __global__ void k_seg_prepare(const otz_entry *__restrict__ ents, const uint32_t
 	n += 1;
 	seg.count[h] = n;
 	seg.nlive[h] = 0;
+	seg.par[h] = 0;
 	const uint32_t ei = list[h];
 	const double bits_total = (double)ents[ei].comp_size * 8.0;
 	const uint64_t base = tok_ofs[h], total = tok_ofs[h + 1] - tok_ofs[h];
@@ -1218,6 +1229,10 @@ __global__ void k_seg_prepare(const otz_entry *__restrict__ ents, const uint32_t
 
 // One thread per huge stream: follow the chain of segments.  The stream is accepted (nlive > 0) only if every link
 // fits; otherwise it is appended to the fallback list of k_inflate.
+//
+// An accepted stream with more than one segment gets room in the symbol buffer (if there is any left): per segment
+// I2_PREWIN marker elements, then its output as 16-bit symbols, placed so that symbol i of the segment and output byte i
+// have the same index modulo 16 (k_seg_translate works on whole vectors of both).
 __global__ void k_seg_stitch(const otz_entry *__restrict__ ents, const int32_t *__restrict__ status, const uint32_t *__restrict__ list,
 	uint32_t n_huge, I2SegCtl seg, uint32_t *__restrict__ fb_list, uint32_t *__restrict__ fb_count) {
 	const uint32_t h = blockIdx.x * blockDim.x + threadIdx.x;
@@ -1261,9 +1276,130 @@ __global__ void k_seg_stitch(const otz_entry *__restrict__ ents, const int32_t *
 	if (ok && done && out == cap) {
 		seg.nlive[h] = nlive;
 		seg.seg_status[h] = OTZ_ST_OK | (ref_eob ? OTZ_STF_REF_EOB : 0);
+		uint32_t par = 0;
+		if (nlive > 1 && seg.sym_cap) {
+			const uint64_t need = (uint64_t)cap + (uint64_t)nlive * (I2_PREWIN + 16u);
+			const uint64_t base = atomicAdd(seg.sym_top, (unsigned long long)need);
+			if (base + need <= seg.sym_cap) {
+				par = 1;
+				uint64_t at = base;
+				uint32_t o = 0;
+				const uint32_t omis = (uint32_t)((seg.out_mis + ents[ei].out_ofs) & 15u);
+				for (uint32_t c = 0; c < nlive; c++) {
+					uint64_t first = at + I2_PREWIN;
+					first += ((omis + o) - (uint32_t)first) & 15u;
+					seg.sym_start[h * I2_MAXSEG + c] = first;
+					seg.out_start[h * I2_MAXSEG + c] = o;
+					const uint32_t pr = res[live[c]].produced;
+					at += I2_PREWIN + 16u + pr;
+					o += pr;
+				}
+				const uint32_t w = atomicAdd(seg.n_par, nlive);
+				for (uint32_t c = 0; c < nlive; c++) {
+					seg.par_items[w + c] = (h << 16) | c;
+				}
+			}
+		}
+		seg.par[h] = par;
 	} else {
+		seg.par[h] = 0;
 		seg.nlive[h] = 0;
 		fb_list[atomicAdd(fb_count, 1u)] = ei;
+	}
+}
+
+// Parallel execution of a huge stream.  Every segment of the chain is executed by its own warp over 16-bit symbols:
+// values below 256 are bytes, 256 + j stands for "byte j of the 32 KiB before this segment", unknown while the
+// segments before it are still being executed (k_inflate_lz<.., PAR> prefills those markers and copies them around
+// like any other element).  k_seg_window then walks the chain of ONE stream per CTA and resolves only the last
+// 32 KiB of every segment — the window of the next one — straight into the output; step c reads what steps < c
+// wrote.  k_seg_translate finally resolves everything in front of those tails, all segments at once.
+__global__ void __launch_bounds__(1024) k_seg_window(uint8_t *__restrict__ out, const otz_entry *__restrict__ ents, const uint32_t *__restrict__ list,
+	uint32_t n_huge, const uint16_t *__restrict__ sym, int32_t *__restrict__ status, uint32_t *__restrict__ produced_out, I2SegCtl seg) {
+	const uint32_t h = blockIdx.x;
+	if (h >= n_huge || !seg.par[h]) {
+		return;
+	}
+	const uint32_t ei = list[h];
+	uint8_t *const o = out + ents[ei].out_ofs;
+	const uint32_t nlive = seg.nlive[h];
+	for (uint32_t c = 0; c < nlive; c++) {
+		const uint32_t pr = seg.res[h * I2_MAXSEG + seg.live[h * I2_MAXSEG + c]].produced;
+		const uint32_t os = seg.out_start[h * I2_MAXSEG + c];
+		const uint16_t *sp = sym + seg.sym_start[h * I2_MAXSEG + c];
+		const uint32_t t0 = pr > I2_PREWIN ? pr - I2_PREWIN : 0u;
+		for (uint32_t i = t0 + threadIdx.x; i < pr; i += blockDim.x) {
+			const uint32_t v = __ldcs(sp + i);
+			// (a marker only exists where a match reached, and k_seg_stitch checked reach <= os)
+			o[os + i] = v < 256u ? (uint8_t)v : __ldcg(o + (os - I2_PREWIN + (v - 256u)));
+		}
+		__syncthreads();
+	}
+	if (threadIdx.x == 0) {
+		status[ei] = seg.seg_status[h];
+		produced_out[ei] = ents[ei].uncomp_size;
+	}
+}
+
+// One CTA per work item (segment): symbols [0, produced - 32 KiB) -> bytes.
+__global__ void __launch_bounds__(256) k_seg_translate(uint8_t *__restrict__ out, const otz_entry *__restrict__ ents, const uint32_t *__restrict__ list,
+	const uint16_t *__restrict__ sym, uint32_t *__restrict__ work_counter, I2SegCtl seg) {
+	__shared__ uint32_t s_k;
+	const uint32_t n = *seg.n_par;
+	for (;;) {
+		__syncthreads();
+		if (threadIdx.x == 0) {
+			s_k = atomicAdd(work_counter, 1u);
+		}
+		__syncthreads();
+		const uint32_t k = s_k;
+		if (k >= n) {
+			break;
+		}
+		const uint32_t it = seg.par_items[k], h = it >> 16, c = it & 0xFFFFu;
+		const uint32_t pr = seg.res[h * I2_MAXSEG + seg.live[h * I2_MAXSEG + c]].produced;
+		if (pr <= I2_PREWIN) {
+			continue;
+		}
+		const uint32_t body = pr - I2_PREWIN, os = seg.out_start[h * I2_MAXSEG + c];
+		uint8_t *const o = out + ents[list[h]].out_ofs + os;        // o[i] <- sp[i]
+		const uint8_t *const win = o - I2_PREWIN;                      // marker j -> win[j]
+		const uint16_t *const sp = sym + seg.sym_start[h * I2_MAXSEG + c];
+		const uint32_t head = min(body, (16u - (uint32_t)(reinterpret_cast<uint64_t>(o) & 15u)) & 15u);
+		const uint32_t nvec = (body - head) >> 4, tail0 = head + (nvec << 4);
+		for (uint32_t i = threadIdx.x; i < head; i += blockDim.x) {
+			const uint32_t v = sp[i];
+			o[i] = v < 256u ? (uint8_t)v : __ldcg(win + (v - 256u));
+		}
+		for (uint32_t i = tail0 + threadIdx.x; i < body; i += blockDim.x) {
+			const uint32_t v = sp[i];
+			o[i] = v < 256u ? (uint8_t)v : __ldcg(win + (v - 256u));
+		}
+		for (uint32_t x = threadIdx.x; x < nvec; x += blockDim.x) {
+			const uint32_t i = head + (x << 4);
+			const uint4 a = __ldcs(reinterpret_cast<const uint4 *>(sp + i)), b = __ldcs(reinterpret_cast<const uint4 *>(sp + i + 8));
+			uint32_t w[8] = { a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w };
+			uint32_t r[4];
+			if (((a.x | a.y | a.z | a.w | b.x | b.y | b.z | b.w) & 0xFF00FF00u) == 0u) {
+#pragma unroll
+				for (int j = 0; j < 4; j++) {
+					r[j] = __byte_perm(w[2 * j], w[2 * j + 1], 0x6420);
+				}
+			} else {
+#pragma unroll
+				for (int j = 0; j < 4; j++) {
+					uint32_t acc = 0;
+#pragma unroll
+					for (int t = 0; t < 4; t++) {
+						const uint32_t v = (w[2 * j + (t >> 1)] >> (16 * (t & 1))) & 0xFFFFu;
+						const uint32_t byte = v < 256u ? v : (uint32_t)__ldcg(win + (v - 256u));
+						acc |= byte << (8 * t);
+					}
+					r[j] = acc;
+				}
+			}
+			__stcs(reinterpret_cast<uint4 *>(o + i), make_uint4(r[0], r[1], r[2], r[3]));
+		}
 	}
 }
 
@@ -1278,7 +1414,24 @@ __global__ void k_seg_stitch(const otz_entry *__restrict__ ents, const int32_t *
 // registers and — the point of the exercise — the sources of its FAR matches (those that left the ring; they
 // were flushed to HBM before batch k started, see SPAN_MAX) are on their way into a staging buffer as 16-byte
 // cp.async copies.  Executing a batch therefore touches shared memory only.
-#define I2_STAGE 1024   // staging bytes per batch (64 vectors); far matches beyond it are fetched directly
+// The executor is written over an element type T: bytes for ordinary streams, 16-bit SYMBOLS for the segments of a
+// huge stream that are executed in parallel (k_seg_window below): positions, distances and lengths are in elements,
+// VEC = elements per 16-byte vector.
+template <typename T>
+struct I2Elem {
+	static constexpr uint32_t VEC = 16u / sizeof(T);
+	static constexpr uint32_t STAGE_VECS = sizeof(T) == 1 ? 64u : 96u;   // staging vectors per batch; far matches beyond them are fetched directly
+	static constexpr uint32_t STAGE = STAGE_VECS * VEC;
+};
+
+template <bool PAR>
+struct I2ElemOf {
+	typedef uint8_t type;
+};
+template <>
+struct I2ElemOf<true> {
+	typedef uint16_t type;
+};
 
 template <int W>
 struct I2Ring {
@@ -1289,20 +1442,20 @@ struct I2Ring {
 	static constexpr uint32_t SPAN_MAX = W >= 8192 ? 2048u : 1024u;
 };
 
-template <int W>
+template <int W, typename T = uint8_t>
 struct __align__(16) I2LzSmem {
-	uint8_t ring[W];
-	uint8_t stage[2][I2_STAGE];
+	T ring[W];
+	T stage[2][I2Elem<T>::STAGE];
 	uint2 far_l[2][32];    // {destination (linear), length | staging vector << 9 (127 = fetch directly)}
 	uint32_t far_s[2][32]; // source of the far match (linear)
 	uint2 near_l[2][32];   // {ring index of the destination | length << 16, ring index of the source | distance << 16}
 };
 
 // write ring[a, b) (linear positions) to HBM; whole warp, ring contents visible (caller synced)
-template <int W>
-__device__ __forceinline__ void i2_flush_range(uint8_t *gbase, const uint8_t *ring, uint32_t a, uint32_t b, uint32_t lane) {
-	constexpr uint32_t MASK = W - 1;
-	const uint32_t a16 = (a + 15u) & ~15u, b16 = b & ~15u;
+template <int W, typename T>
+__device__ __forceinline__ void i2_flush_range(T *gbase, const T *ring, uint32_t a, uint32_t b, uint32_t lane) {
+	constexpr uint32_t MASK = W - 1, VEC = I2Elem<T>::VEC;
+	const uint32_t a16 = (a + VEC - 1u) & ~(VEC - 1u), b16 = b & ~(VEC - 1u);
 	if (a16 >= b16) {
 		for (uint32_t x = a + lane; x < b; x += 32) {
 			gbase[x] = ring[x & MASK];
@@ -1313,7 +1466,7 @@ __device__ __forceinline__ void i2_flush_range(uint8_t *gbase, const uint8_t *ri
 		gbase[x] = ring[x & MASK];
 	}
 #pragma unroll 1
-	for (uint32_t x = a16 + 16u * lane; x < b16; x += 512u) {
+	for (uint32_t x = a16 + VEC * lane; x < b16; x += 32u * VEC) {
 		*reinterpret_cast<uint4 *>(gbase + x) = *reinterpret_cast<const uint4 *>(ring + (x & MASK));
 	}
 	for (uint32_t x = b16 + lane; x < b; x += 32) {
@@ -1322,8 +1475,8 @@ __device__ __forceinline__ void i2_flush_range(uint8_t *gbase, const uint8_t *ri
 }
 
 // overlapping LZ77 copy (distance < length): periodic extension of the last `dd` bytes, whole warp (dec:521-533)
-template <int W>
-__device__ __noinline__ void i2_copy_periodic(uint8_t *rb, uint32_t dq, uint32_t sq, uint32_t dd, uint32_t len, uint32_t lane) {
+template <int W, typename T>
+__device__ __noinline__ void i2_copy_periodic(T *rb, uint32_t dq, uint32_t sq, uint32_t dd, uint32_t len, uint32_t lane) {
 	constexpr uint32_t MASK = W - 1;
 	uint32_t r = dd > lane ? lane : lane % dd;
 	const uint32_t step = dd > 32u ? 32u : 32u % dd;
@@ -1350,10 +1503,10 @@ struct I2Batch {
 // list buffer `buf` and start the copies of its far sources into staging buffer `buf`.
 // WIDE: 8-byte records {literal run | (length - 3) << 9, distance} (Zstandard: distances beyond 32 KiB); `rec` is the first
 // word, `wdist` the second.  Otherwise the distance sits in rec[31:17].
-template <int W, bool WIDE>
-__device__ __forceinline__ I2Batch i2_scan_batch(I2LzSmem<W> &S, int buf, uint32_t rec, uint32_t wdist, uint32_t b, uint32_t nseq, uint32_t q,
-	uint32_t lp, const uint8_t *__restrict__ lits, const uint8_t *gbase, uint32_t lane) {
-	constexpr uint32_t MASK = I2Ring<W>::MASK, SPAN_MAX = I2Ring<W>::SPAN_MAX;
+template <int W, bool WIDE, typename T>
+__device__ __forceinline__ I2Batch i2_scan_batch(I2LzSmem<W, T> &S, int buf, uint32_t rec, uint32_t wdist, uint32_t b, uint32_t nseq, uint32_t q,
+	uint32_t lp, const uint8_t *__restrict__ lits, const T *gbase, uint32_t lane) {
+	constexpr uint32_t MASK = I2Ring<W>::MASK, SPAN_MAX = I2Ring<W>::SPAN_MAX, VEC = I2Elem<T>::VEC, STAGE_VECS = I2Elem<T>::STAGE_VECS;
 	const uint32_t lt_mask = (1u << lane) - 1u;
 	I2Batch B;
 	const bool have = b + lane < nseq;
@@ -1410,8 +1563,8 @@ __device__ __forceinline__ I2Batch i2_scan_batch(I2LzSmem<W> &S, int buf, uint32
 	}
 	if (far_m) {
 		// staging vectors per far match (the source is copied as whole 16-byte vectors)
-		const uint32_t soff = (mq - dist) & 15u;
-		const uint32_t nch = is_far ? (soff + ml + 15u) >> 4 : 0u;
+		const uint32_t soff = (mq - dist) & (VEC - 1u);
+		const uint32_t nch = is_far ? (soff + ml + VEC - 1u) / VEC : 0u;
 		uint32_t incl = nch;
 #pragma unroll
 		for (int d = 1; d < 32; d <<= 1) {
@@ -1421,7 +1574,7 @@ __device__ __forceinline__ I2Batch i2_scan_batch(I2LzSmem<W> &S, int buf, uint32
 			}
 		}
 		if (is_far) {
-			const uint32_t cst = incl <= I2_STAGE / 16u ? incl - nch : 127u;
+			const uint32_t cst = incl <= STAGE_VECS ? incl - nch : 127u;
 			const uint32_t j = __popc(far_m & lt_mask);
 			S.far_l[buf][j] = make_uint2(mq, ml | (cst << 9));
 			S.far_s[buf][j] = mq - dist;
@@ -1432,11 +1585,15 @@ __device__ __forceinline__ I2Batch i2_scan_batch(I2LzSmem<W> &S, int buf, uint32
 			const uint32_t cst = d.y >> 9;
 			if (cst != 127u) {
 				const uint32_t src = S.far_s[buf][f], len = d.y & 511u;
-				const uint32_t n = ((src & 15u) + len + 15u) >> 4;
-				if (lane < n) {
-					const uint32_t sa = (uint32_t)__cvta_generic_to_shared(&S.stage[buf][16u * (cst + lane)]);
-					asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(sa), "l"(gbase + (src & ~15u) + 16u * lane) : "memory");
-				}
+				const uint32_t n = ((src & (VEC - 1u)) + len + VEC - 1u) / VEC;
+				uint32_t v = lane;
+				do {   // bytes: n <= 18, one trip; symbols: n <= 34
+					if (v < n) {
+						const uint32_t sa = (uint32_t)__cvta_generic_to_shared(&S.stage[buf][VEC * (cst + v)]);
+						asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(sa), "l"(gbase + (src & ~(VEC - 1u)) + VEC * v) : "memory");
+					}
+					v += 32;
+				} while (sizeof(T) > 1 && v < n);
 			}
 		}
 	}
@@ -1444,16 +1601,23 @@ __device__ __forceinline__ I2Batch i2_scan_batch(I2LzSmem<W> &S, int buf, uint32
 	return B;
 }
 
-// SEG: `list` holds huge streams; the tokens of a stream are the chain of segments k_seg_stitch accepted.
-template <int W, bool WIDE, bool SEG>
+// SEG: `list` holds huge streams; the tokens of a stream are the chain of segments k_seg_stitch accepted, walked by
+// this warp.  PAR: the work items are single segments of such chains (seg.par_items), executed over 16-bit symbols
+// into the symbol buffer `out` with the 32 KiB before the segment standing in as MARKERS (k_seg_window resolves them).
+template <int W, bool WIDE, bool SEG, bool PAR = false>
 __global__ void __launch_bounds__(128) k_inflate_lz(uint8_t *__restrict__ out, const otz_entry *__restrict__ ents, const uint32_t *__restrict__ list,
 	uint32_t n_list, uint32_t *__restrict__ work_counter, const uint8_t *__restrict__ scratch, const uint64_t *__restrict__ tok_ofs,
 	const I2TokRes *__restrict__ tokres, int32_t *__restrict__ status, uint32_t *__restrict__ produced_out, I2SegCtl seg) {
+	typedef typename I2ElemOf<PAR>::type T;
+	static_assert(!PAR || (SEG && !WIDE), "PAR executes segments of DEFLATE streams");
 	extern __shared__ __align__(16) uint8_t smem_raw[];
-	constexpr uint32_t MASK = I2Ring<W>::MASK, SEGB = I2Ring<W>::SEG, SPAN_MAX = I2Ring<W>::SPAN_MAX;
+	constexpr uint32_t MASK = I2Ring<W>::MASK, SEGB = I2Ring<W>::SEG, SPAN_MAX = I2Ring<W>::SPAN_MAX, VEC = I2Elem<T>::VEC;
 	const uint32_t lane = threadIdx.x & 31u;
-	I2LzSmem<W> &S = reinterpret_cast<I2LzSmem<W> *>(smem_raw)[threadIdx.x >> 5];
-	uint8_t *const rb = S.ring;
+	I2LzSmem<W, T> &S = reinterpret_cast<I2LzSmem<W, T> *>(smem_raw)[threadIdx.x >> 5];
+	T *const rb = S.ring;
+	if (PAR) {
+		n_list = *seg.n_par;
+	}
 	for (;;) {
 		uint32_t k = 0;
 		if (lane == 0) {
@@ -1464,9 +1628,16 @@ __global__ void __launch_bounds__(128) k_inflate_lz(uint8_t *__restrict__ out, c
 			break;
 		}
 		I2TokRes tr;
-		uint32_t nsegs = 1;
-		if (SEG) {
-			nsegs = seg.nlive[k];
+		uint32_t nsegs = 1, par_c = 0;
+		if (PAR) {
+			const uint32_t it = seg.par_items[k];
+			k = it >> 16;        // from here on: the stream
+			par_c = it & 0xFFFFu;
+			tr.ok = 1;
+			tr.status = 0;
+			tr.nseq = tr.nlit = 0;
+		} else if (SEG) {
+			nsegs = seg.par[k] ? 0u : seg.nlive[k];
 			tr.ok = nsegs != 0u;
 			tr.status = seg.seg_status[k];
 			tr.nseq = tr.nlit = 0;
@@ -1478,16 +1649,30 @@ __global__ void __launch_bounds__(128) k_inflate_lz(uint8_t *__restrict__ out, c
 		}
 		const uint32_t ei = list[k];
 		const otz_entry e = ents[ei];
-		uint8_t *const dstp = out + e.out_ofs;
-		const uint32_t mis = (uint32_t)(reinterpret_cast<uint64_t>(dstp) & 15u);
-		uint8_t *const gbase = dstp - mis;
-		uint32_t q = mis, qf = mis;   // linear write position / position up to which HBM holds the data
+		T *const dstp = PAR ? reinterpret_cast<T *>(out) + seg.sym_start[k * I2_MAXSEG + par_c] : reinterpret_cast<T *>(out + e.out_ofs);
+		const uint32_t mis = (uint32_t)((reinterpret_cast<uint64_t>(dstp) / sizeof(T)) & (VEC - 1u));
+		// PAR: linear position I2_PREWIN is the segment's first element; the markers sit below it
+		T *const gbase = dstp - mis - (PAR ? I2_PREWIN : 0u);
+		uint32_t q = mis + (PAR ? I2_PREWIN : 0u), qf = q;   // linear write position / position up to which HBM holds the data
+		if (PAR) {
+			// marker for the element m places before the segment: 256 + (I2_PREWIN - m).  HBM gets all the matches can
+			// reach, the ring the part of them a near match can address.
+			const uint32_t reach = min(seg.res[k * I2_MAXSEG + seg.live[k * I2_MAXSEG + par_c]].reach, (uint32_t)I2_PREWIN);
+			for (uint32_t m = 1u + lane; m <= reach; m += 32) {
+				const T v = (T)(256u + I2_PREWIN - m);
+				gbase[q - m] = v;
+				if (m <= (uint32_t)W) {
+					rb[(q - m) & MASK] = v;
+				}
+			}
+			__syncwarp();
+		}
 		for (uint32_t sgi = 0; sgi < nsegs; sgi++) {
 		const uint8_t *lits;
 		const uint32_t *seq_end;
 		uint32_t nseq, nlit;
 		if (SEG) {
-			const I2SegRes *r_ = &seg.res[k * I2_MAXSEG + seg.live[k * I2_MAXSEG + sgi]];
+			const I2SegRes *r_ = &seg.res[k * I2_MAXSEG + seg.live[k * I2_MAXSEG + (PAR ? par_c : sgi)]];
 			lits = scratch + r_->scr_lo;
 			seq_end = reinterpret_cast<const uint32_t *>(scratch + r_->scr_hi);
 			nseq = r_->nseq;
@@ -1519,7 +1704,7 @@ __global__ void __launch_bounds__(128) k_inflate_lz(uint8_t *__restrict__ out, c
 			recB = 32u + lane < nseq ? __ldcs(seq_end - 33 - lane) : 0u;
 		}
 		int buf = 0;
-		I2Batch cur = i2_scan_batch<W, WIDE>(S, 0, recA, offA, 0u, nseq, q, lp, lits, gbase, lane);
+		I2Batch cur = i2_scan_batch<W, WIDE, T>(S, 0, recA, offA, 0u, nseq, q, lp, lits, gbase, lane);
 		while (cur.ntake) {
 			// ---- scan batch k+1 and start its far copies
 			const uint32_t b2 = b + cur.ntake;
@@ -1540,7 +1725,7 @@ __global__ void __launch_bounds__(128) k_inflate_lz(uint8_t *__restrict__ out, c
 					recB = b2 + 32u + lane < nseq ? __ldcs(seq_end - 33 - (b2 + lane)) : 0u;
 				}
 			}
-			const I2Batch nxt = i2_scan_batch<W, WIDE>(S, buf ^ 1, recA, offA, b2, nseq, cur.q_end, lp + cur.tot_l, lits, gbase, lane);
+			const I2Batch nxt = i2_scan_batch<W, WIDE, T>(S, buf ^ 1, recA, offA, b2, nseq, cur.q_end, lp + cur.tot_l, lits, gbase, lane);
 			// ---- execute batch k: its far sources have landed in stage[buf]
 			asm volatile("cp.async.wait_group 1;" ::: "memory");
 			__syncwarp();
@@ -1548,7 +1733,7 @@ __global__ void __launch_bounds__(128) k_inflate_lz(uint8_t *__restrict__ out, c
 				// literal runs, all records at once
 				const uint32_t n4 = min(cur.lr, 4u);
 				for (uint32_t t = 0; t < n4; t++) {
-					rb[(cur.my_out + t) & MASK] = (uint8_t)(cur.lit4 >> (8u * t));
+					rb[(cur.my_out + t) & MASK] = (T)(uint8_t)(cur.lit4 >> (8u * t));
 				}
 #pragma unroll 1
 				for (uint32_t t = 4; t < cur.lr; t++) {
@@ -1562,7 +1747,7 @@ __global__ void __launch_bounds__(128) k_inflate_lz(uint8_t *__restrict__ out, c
 				dn = S.far_l[buf][(f + 1u) & 31u];   // next descriptor in flight while this match is copied
 				const uint32_t cst = d.y >> 9, len = d.y & 511u, src = S.far_s[buf][f];
 				if (cst != 127u) {
-					const uint8_t *sp = &S.stage[buf][16u * cst + (src & 15u)];
+					const T *sp = &S.stage[buf][VEC * cst + (src & (VEC - 1u))];
 					if (lane < len) {
 						rb[(d.x + lane) & MASK] = sp[lane];
 					}
@@ -1590,7 +1775,7 @@ __global__ void __launch_bounds__(128) k_inflate_lz(uint8_t *__restrict__ out, c
 				if (f + 1u < cur.n_near && (d1.x >> 31)) {
 					const uint32_t dqm1 = d1.x & 0xFFFFu, len1 = (d1.x >> 16) & 0x1FFu, sqm1 = d1.y & 0xFFFFu;
 					dn = S.near_l[buf][(f + 2u) & 31u];
-					uint8_t v0 = 0, v1 = 0;
+					T v0 = 0, v1 = 0;
 					if (lane < len) {
 						v0 = rb[(sqm + lane) & MASK];
 					}
@@ -1619,7 +1804,7 @@ __global__ void __launch_bounds__(128) k_inflate_lz(uint8_t *__restrict__ out, c
 						}
 					}
 				} else {
-					i2_copy_periodic<W>(rb, dqm, sqm, dd, len, lane);
+					i2_copy_periodic<W, T>(rb, dqm, sqm, dd, len, lane);
 				}
 			}
 			b = b2;
@@ -1628,7 +1813,7 @@ __global__ void __launch_bounds__(128) k_inflate_lz(uint8_t *__restrict__ out, c
 			__syncwarp();
 			const uint32_t qa = q & ~(SEGB - 1u);
 			if (qa > qf) {
-				i2_flush_range<W>(gbase, rb, qf, qa, lane);
+				i2_flush_range<W, T>(gbase, rb, qf, qa, lane);
 				qf = qa;
 				__syncwarp();
 			}
@@ -1647,16 +1832,16 @@ __global__ void __launch_bounds__(128) k_inflate_lz(uint8_t *__restrict__ out, c
 			__syncwarp();
 			const uint32_t qa = q & ~(SEGB - 1u);
 			if (qa > qf) {
-				i2_flush_range<W>(gbase, rb, qf, qa, lane);
+				i2_flush_range<W, T>(gbase, rb, qf, qa, lane);
 				qf = qa;
 				__syncwarp();
 			}
 		}
 		}   // segments
 		if (q > qf) {
-			i2_flush_range<W>(gbase, rb, qf, q, lane);
+			i2_flush_range<W, T>(gbase, rb, qf, q, lane);
 		}
-		if (lane == 0) {
+		if (!PAR && lane == 0) {
 			status[ei] = tr.status;
 			produced_out[ei] = e.uncomp_size;
 		}

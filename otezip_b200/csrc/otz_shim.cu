@@ -59,6 +59,11 @@ struct otz_ctx {
 	uint64_t ztok_cache_bytes;
 	uint8_t *d_tok_cache;   // grow-only token scratch of the two-phase inflate (literals + sequence records)
 	uint64_t tok_cache_bytes;
+	int seg_serial;         // OTZ_SEG_EXEC=serial: one warp walks the chain of a huge stream (no parallel segment execution)
+	int seg_ring;           // OTZ_SEG_PAR_RING: ring elements per warp of the parallel segment executor (4096 / 8192)
+	uint16_t *d_sym_cache;  // grow-only symbol buffer of the parallel segment execution
+	uint64_t sym_cache_elems;
+	uint64_t sym_limit;     // OTZ_SEG_SYM_LIMIT: cap of the symbol buffer in elements (tests: streams that do not fit are walked by one warp)
 };
 
 struct otz_plan {
@@ -76,6 +81,7 @@ struct otz_plan {
 	uint32_t n_inflate_huge;   // [0, n_inflate_huge): entries whose serial decode time sets the critical path of a batch
 	I2SegCtl seg;              // segmented decode of the huge entries (device arrays; null when there are none)
 	uint32_t huge_max_comp;
+	uint64_t sym_elems;        // symbol buffer the parallel execution of the huge streams may need
 	uint32_t *d_search_ofs;    // [n_huge + 1] first 256-byte search task of every huge stream
 	uint2 *d_surv;             // offsets that passed the cheap header checks of k_block_search
 	uint32_t surv_cap;
@@ -204,6 +210,12 @@ extern "C" int otz_ctx_create(int device, otz_ctx **out) {
 	c->inflate_mode = (t && !strcmp(t, "legacy")) ? 1 : 0;
 	t = getenv("OTZ_HUGE_MODE");
 	c->huge_legacy = (t && !strcmp(t, "legacy")) ? 1 : 0;
+	t = getenv("OTZ_SEG_EXEC");
+	c->seg_serial = (t && !strcmp(t, "serial")) ? 1 : 0;
+	t = getenv("OTZ_SEG_PAR_RING");
+	c->seg_ring = t ? atoi(t) : 4096;
+	t = getenv("OTZ_SEG_SYM_LIMIT");
+	c->sym_limit = t ? strtoull(t, nullptr, 0) : ~0ull;
 	t = getenv("OTZ_ZSTD_MODE");
 	c->zstd_legacy = (t && !strcmp(t, "legacy")) ? 1 : 0;
 	t = getenv("OTZ_LZ_RING");
@@ -223,6 +235,7 @@ extern "C" void otz_ctx_destroy(otz_ctx *c) {
 	cudaFree(c->d_arch_cache);
 	cudaFree(c->d_out_cache);
 	cudaFree(c->d_tok_cache);
+	cudaFree(c->d_sym_cache);
 	cudaFree(c->d_ztok_cache);
 	cudaEventDestroy(c->ev0);
 	cudaEventDestroy(c->ev1);
@@ -389,6 +402,11 @@ extern "C" void otz_plan_destroy(otz_ctx *c, otz_plan *p) {
 	cudaFree(p->seg.live);
 	cudaFree(p->seg.nlive);
 	cudaFree(p->seg.seg_status);
+	cudaFree(p->seg.par);
+	cudaFree(p->seg.par_items);
+	cudaFree(p->seg.n_par);
+	cudaFree(p->seg.sym_start);
+	cudaFree(p->seg.out_start);
 	cudaFree(p->d_tok_ofs);
 	cudaFree(p->d_tokres);
 	cudaFree(p->d_fb_list);
@@ -497,6 +515,10 @@ extern "C" int otz_plan_create(otz_ctx *c, const otz_entry *ents, uint32_t n, co
 		sofs[0] = 0;
 		for (size_t h = 0; h < nh; h++) {
 			sofs[h + 1] = sofs[h] + (ents[infl[h]].comp_size + 255u) / 256u;
+			// symbols of the stream + markers in front of every segment (a block of zlib is ~25 KB of compressed data;
+			// a stream with more segments than estimated here is executed by one warp)
+			p->sym_elems += (uint64_t)ents[infl[h]].uncomp_size +
+				(uint64_t)(I2_PREWIN + 16u) * std::min<uint64_t>(I2_MAXSEG, 2u + ents[infl[h]].comp_size / 12288u);
 		}
 		if ((rc = upload(&p->d_search_ofs, sofs, c->stream))) {
 			otz_plan_destroy(c, p);
@@ -511,7 +533,10 @@ extern "C" int otz_plan_create(otz_ctx *c, const otz_entry *ents, uint32_t n, co
 		if (cudaMalloc(&p->seg.count, nh * 4) != cudaSuccess || cudaMalloc(&p->seg.start, ns * 4) != cudaSuccess ||
 			cudaMalloc(&p->seg.res, ns * sizeof(I2SegRes)) != cudaSuccess || cudaMalloc(&p->seg.items, ns * 4) != cudaSuccess ||
 			cudaMalloc(&p->seg.n_items, 4) != cudaSuccess || cudaMalloc(&p->seg.live, ns * 4) != cudaSuccess ||
-			cudaMalloc(&p->seg.nlive, nh * 4) != cudaSuccess || cudaMalloc(&p->seg.seg_status, nh * 4) != cudaSuccess) {
+			cudaMalloc(&p->seg.nlive, nh * 4) != cudaSuccess || cudaMalloc(&p->seg.seg_status, nh * 4) != cudaSuccess ||
+			cudaMalloc(&p->seg.par, nh * 4) != cudaSuccess || cudaMalloc(&p->seg.par_items, ns * 4) != cudaSuccess ||
+			cudaMalloc(&p->seg.n_par, 4) != cudaSuccess || cudaMalloc(&p->seg.sym_start, ns * 8) != cudaSuccess ||
+			cudaMalloc(&p->seg.out_start, ns * 4) != cudaSuccess) {
 			otz_plan_destroy(c, p);
 			return fail_cuda(cudaGetLastError(), "cudaMalloc(segment tables)");
 		}
@@ -633,6 +658,34 @@ static int launch_lz(otz_ctx *c, otz_plan *p, uint8_t *d_out, uint32_t first, ui
 	return OTZ_SUCCESS;
 }
 
+// Parallel execution of the chains k_seg_stitch placed in the symbol buffer: one warp per segment over 16-bit symbols,
+// then the windows between the segments (one CTA per stream), then symbols -> bytes for everything else.
+template <int W>
+static int launch_seg_par(otz_ctx *c, otz_plan *p, uint8_t *d_out, const I2SegCtl &sg, cudaStream_t st) {
+	auto kern = k_inflate_lz<W, false, true, true>;
+	const int warps = 4;
+	const size_t smem = warps * sizeof(I2LzSmem<W, uint16_t>);
+	static bool attr_done = false;
+	if (!attr_done) {
+		CK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+		attr_done = true;
+	}
+	int per_sm = 0;
+	CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, 32 * warps, smem));
+	if (per_sm < 1) {
+		snprintf(g_err, sizeof(g_err), "k_inflate_lz<%d, symbols> does not fit an SM", W);
+		return OTZ_ERR_CUDA;
+	}
+	const uint32_t nh = p->n_inflate_huge;
+	kern<<<(uint32_t)(c->sm_count * per_sm), 32 * warps, smem, st>>>(reinterpret_cast<uint8_t *>(c->d_sym_cache), p->d_ents, p->d_inflate_list, 0u,
+		p->d_counter + 60, c->d_tok_cache, p->d_tok_ofs, p->d_tokres, p->d_status, p->d_produced, sg);
+	k_seg_window<<<nh, 1024, 0, st>>>(d_out, p->d_ents, p->d_inflate_list, nh, c->d_sym_cache, p->d_status, p->d_produced, sg);
+	k_seg_translate<<<(uint32_t)c->sm_count * 8u, 256, 0, st>>>(d_out, p->d_ents, p->d_inflate_list, c->d_sym_cache, p->d_counter + 61, sg);
+	c->launches += 3;
+	CK(cudaGetLastError());
+	return OTZ_SUCCESS;
+}
+
 // Two-phase inflate: lane-per-stream entropy decode into tokens, warp-per-stream LZ77 execution, then k_inflate over
 // whatever phase A declined (d_counter + 52 counts those entries).
 static int dispatch_inflate2(otz_ctx *c, otz_plan *p, const uint8_t *d_archive, uint8_t *d_out) {
@@ -672,12 +725,40 @@ static int dispatch_inflate2(otz_ctx *c, otz_plan *p, const uint8_t *d_archive, 
 		}
 		k_inflate_tok<true><<<sgrid, 32, I2_SMEM_BYTES(sl), s2>>>(d_archive, p->d_ents, p->d_est, p->d_status, p->d_inflate_list, 0u, p->d_counter + 57,
 			c->d_tok_cache, p->d_tok_ofs, p->d_tokres, p->d_fb_list, p->d_counter + 52, sl, p->seg);
-		k_seg_stitch<<<(nh + 63) / 64, 64, 0, s2>>>(p->d_ents, p->d_status, p->d_inflate_list, nh, p->seg, p->d_fb_list, p->d_counter + 52);
+		// parallel execution of the segments needs the symbol buffer (grow-only, like the token scratch); without it
+		// (or for a stream that does not fit) one warp walks the chain
+		I2SegCtl sg = p->seg;
+		sg.sym_top = reinterpret_cast<unsigned long long *>(p->d_counter + 62);
+		sg.out_mis = (uint32_t)(reinterpret_cast<uint64_t>(d_out) & 15u);
+		sg.sym_cap = 0;
+		if (!c->seg_serial && p->sym_elems) {
+			if (p->sym_elems > c->sym_cache_elems) {
+				CK(cudaStreamSynchronize(c->stream));
+				CK(cudaStreamSynchronize(s2));
+				cudaFree(c->d_sym_cache);
+				c->d_sym_cache = nullptr;
+				c->sym_cache_elems = 0;
+				if (cudaMalloc(&c->d_sym_cache, p->sym_elems * 2 + 64) == cudaSuccess) {
+					c->sym_cache_elems = p->sym_elems;
+				} else {
+					cudaGetLastError();
+				}
+			}
+			sg.sym_cap = c->d_sym_cache ? std::min<uint64_t>(p->sym_elems, c->sym_limit) : 0;
+		}
+		CK(cudaMemsetAsync(p->seg.n_par, 0, 4, s2));
+		k_seg_stitch<<<(nh + 63) / 64, 64, 0, s2>>>(p->d_ents, p->d_status, p->d_inflate_list, nh, sg, p->d_fb_list, p->d_counter + 52);
 		CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm2, k_inflate_lz<OTZ_SEG_RING, false, true>, 128, 4 * sizeof(I2LzSmem<OTZ_SEG_RING>)));
 		const uint32_t lgrid = std::max(1u, std::min((uint32_t)(c->sm_count * std::max(per_sm2, 1)), (nh + 3) / 4));
 		k_inflate_lz<OTZ_SEG_RING, false, true><<<lgrid, 128, 4 * sizeof(I2LzSmem<OTZ_SEG_RING>), s2>>>(d_out, p->d_ents, p->d_inflate_list, nh, p->d_counter + 58,
-			c->d_tok_cache, p->d_tok_ofs, p->d_tokres, p->d_status, p->d_produced, p->seg);
+			c->d_tok_cache, p->d_tok_ofs, p->d_tokres, p->d_status, p->d_produced, sg);
 		c->launches += 6;
+		if (sg.sym_cap) {
+			int rc_ = c->seg_ring == 8192 ? launch_seg_par<8192>(c, p, d_out, sg, s2) : launch_seg_par<4096>(c, p, d_out, sg, s2);
+			if (rc_) {
+				return rc_;
+			}
+		}
 		CK(cudaGetLastError());
 		CK(cudaEventRecord(c->ev_join, s2));
 		forked = true;

@@ -132,11 +132,15 @@ def test_many_uniform_streams_no_fallback(oracle):
     c.close()
 
 
+@pytest.mark.parametrize("seg_exec", [None, "serial", "limit", "ring8192"])
 @pytest.mark.parametrize("seg_grid", [None, "2"])
-def test_huge_streams_segmented(oracle, seg_grid):
+def test_huge_streams_segmented(oracle, seg_grid, seg_exec):
     """Entries >= 2 MiB: block-start search + one lane per block run + chain check (k_block_search / k_inflate_tok<true> /
     k_seg_stitch) against the oracle, in shapes that stress the chain: many blocks, stored and fixed blocks in between,
-    full-flush points, an incompressible middle, a stream that is one single block."""
+    full-flush points, an incompressible middle, a stream that is one single block.
+    seg_exec: how the accepted chains are executed — every segment by its own warp over 16-bit symbols with markers for
+    the 32 KiB before it (k_inflate_lz<.., PAR> + k_seg_window + k_seg_translate; default), one warp walking the chain
+    ("serial"), or a symbol buffer that only has room for some of the streams ("limit": both executors in one run)."""
     rnd = random.Random(9)
     ms = [synth.member("h0", synth.jsonlog_text(5 << 20, 1), 8),
           synth.member("h1", synth.jsonlog_text(3 << 20, 2), 8, level=1),
@@ -150,12 +154,19 @@ def test_huge_streams_segmented(oracle, seg_grid):
     img = synth.build_zip(ms)
     if seg_grid:   # two warps for all segments: every lane decodes many segments one after the other
         os.environ["OTZ_SEG_GRID"] = seg_grid
+    if seg_exec == "serial":
+        os.environ["OTZ_SEG_EXEC"] = "serial"
+    elif seg_exec == "limit":
+        os.environ["OTZ_SEG_SYM_LIMIT"] = str(9 << 20)
+    elif seg_exec == "ring8192":
+        os.environ["OTZ_SEG_PAR_RING"] = "8192"
     try:
         c = _ctx()
         fb, st, out = _check(img, oracle, c)
         c.close()
     finally:
-        os.environ.pop("OTZ_SEG_GRID", None)
+        for k in ("OTZ_SEG_GRID", "OTZ_SEG_EXEC", "OTZ_SEG_SYM_LIMIT", "OTZ_SEG_PAR_RING"):
+            os.environ.pop(k, None)
     assert fb <= 3, fb   # (the incompressible middle of h3 is stored blocks with payload: k_inflate takes that stream)
 
 
@@ -202,10 +213,12 @@ def test_corrupt_huge_streams_same_status_as_one_kernel_decoder():
     assert n_ok >= 3
 
 
-def test_random_encoder_settings_match_oracle(oracle):
+@pytest.mark.parametrize("huge_bytes", [None, "60000"])
+def test_random_encoder_settings_match_oracle(oracle, huge_bytes):
     """Streams from every corner of zlib's parameter space — window 512 B..32 KiB, memLevel 1..9 (memLevel 1 ends a block
     every 128 symbols: thousands of block headers per entry), all levels and strategies, sync / full flushes at random
-    points — through the lane-per-stream path, against the oracle."""
+    points — through the lane-per-stream path, against the oracle.  huge_bytes = 60000 sends the larger ones through the
+    segmented decode and the parallel segment execution instead (hundreds of tiny segments per stream)."""
     rnd = random.Random(77)
     ms = []
     for i in range(160):
@@ -231,6 +244,11 @@ def test_random_encoder_settings_match_oracle(oracle):
         parts.append(c.flush())
         ms.append(synth.Member("r%d" % i, 8, b"".join(parts), len(d), zlib.crc32(d) & 0xFFFFFFFF, raw=d))
     img = synth.build_zip(ms)
-    c = _ctx()
-    _check(img, oracle, c)
-    c.close()
+    if huge_bytes:
+        os.environ["OTZ_HUGE_BYTES"] = huge_bytes
+    try:
+        c = _ctx()
+        _check(img, oracle, c)
+        c.close()
+    finally:
+        os.environ.pop("OTZ_HUGE_BYTES", None)
