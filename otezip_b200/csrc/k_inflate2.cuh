@@ -1098,71 +1098,78 @@ __device__ __noinline__ bool i2_plausible_header(const uint8_t *in, uint64_t nbi
 	return eob && kl == 32768u && (kd == 32768u || nd <= 1u);
 }
 
-// grid: persistent (any size); task t = 256 consecutive bytes of one stream, task_ofs[h] = first task of stream h
+// grid: persistent (any size); task t = 256 consecutive bytes of one stream, task_ofs[h] = first task of stream h.
+// Every thread tests the 8 bit offsets of its byte, branch-free: BTYPE = 2, HLIT <= 29, HDIST <= 29, and the Kraft sum
+// of the code-length code — its (HCLEN + 4) 3-bit lengths are looked up four at a time in a 4096-entry table of
+// sum(2^(7 - len)), saturated at 255 — must be exactly 128 (a complete code; zlib never emits another one).
 __global__ void __launch_bounds__(256) k_block_search(const uint8_t *__restrict__ archive, const otz_entry *__restrict__ ents,
 	const OtzEntryState *__restrict__ est, const int32_t *__restrict__ status, const uint32_t *__restrict__ list, uint32_t n_huge,
 	const uint32_t *__restrict__ task_ofs, uint2 *__restrict__ surv, uint32_t surv_cap, uint32_t *__restrict__ n_surv) {
+	__shared__ uint8_t s_kraft[4096];
+	for (uint32_t i = threadIdx.x; i < 4096u; i += blockDim.x) {
+		uint32_t sum = 0;
+#pragma unroll
+		for (int f = 0; f < 4; f++) {
+			const uint32_t l = (i >> (3 * f)) & 7u;
+			sum += l ? (128u >> l) : 0u;
+		}
+		s_kraft[i] = (uint8_t)min(sum, 255u);
+	}
+	__syncthreads();
 	const uint32_t n_tasks = task_ofs[n_huge];
 	for (uint32_t t = blockIdx.x; t < n_tasks; t += gridDim.x) {
-	// stream of this task: the last h with task_ofs[h] <= t
-	uint32_t lo_h = 0, hi_h = n_huge;
-	while (hi_h - lo_h > 1) {
-		const uint32_t mid = (lo_h + hi_h) >> 1;
-		if (task_ofs[mid] <= t) {
-			lo_h = mid;
-		} else {
-			hi_h = mid;
+		// stream of this task: the last h with task_ofs[h] <= t
+		uint32_t lo_h = 0, hi_h = n_huge;
+		while (hi_h - lo_h > 1) {
+			const uint32_t mid = (lo_h + hi_h) >> 1;
+			if (task_ofs[mid] <= t) {
+				lo_h = mid;
+			} else {
+				hi_h = mid;
+			}
 		}
-	}
-	const uint32_t h = lo_h;
-	const uint32_t ei = list[h];
-	if (OTZ_ST_CODE(status[ei]) != OTZ_ST_OK) {
-		continue;
-	}
-	const uint32_t comp = ents[ei].comp_size;
-	const uint32_t byte = (t - task_ofs[h]) * 256u + threadIdx.x;
-	if (byte + 12u > comp) {
-		continue;   // a block header needs more than that; the tail belongs to the last segment anyway
-	}
-	const uint8_t *in = archive + est[ei].data_ofs;
-	const uint8_t *q = in + byte;
-	uint64_t lo = 0;
-	uint32_t hi = 0;
+		const uint32_t h = lo_h;
+		const uint32_t ei = list[h];
+		if (OTZ_ST_CODE(status[ei]) != OTZ_ST_OK) {
+			continue;
+		}
+		const uint32_t comp = ents[ei].comp_size;
+		const uint32_t byte = (t - task_ofs[h]) * 256u + threadIdx.x;
+		if (byte + 12u > comp) {
+			continue;   // a block header needs more than that; the tail belongs to the last segment anyway
+		}
+		// 12 bytes from `byte` on, as aligned words (the image is padded) shifted into place
+		const uint8_t *q = archive + est[ei].data_ofs + byte;
+		const uint32_t sh = (uint32_t)(reinterpret_cast<uint64_t>(q) & 3u) * 8u;
+		const uint32_t *qw = reinterpret_cast<const uint32_t *>(q - (sh >> 3));
+		const uint32_t w0 = __ldg(qw), w1 = __ldg(qw + 1), w2 = __ldg(qw + 2), w3 = __ldg(qw + 3);
+		const uint32_t b0 = __funnelshift_r(w0, w1, sh), b1 = __funnelshift_r(w1, w2, sh), b2 = __funnelshift_r(w2, w3, sh);
+		uint32_t hits = 0;
 #pragma unroll
-	for (int i = 0; i < 8; i++) {
-		lo |= (uint64_t)q[i] << (8 * i);
-	}
-#pragma unroll
-	for (int i = 0; i < 4; i++) {
-		hi |= (uint32_t)q[8 + i] << (8 * i);
-	}
-	for (uint32_t o = byte == 0 ? 1u : 0u; o < 8u; o++) {
-		const uint64_t v = o ? (lo >> o) | ((uint64_t)hi << (64u - o)) : lo;
-		const uint32_t w = (uint32_t)v;
-		if (((w >> 1) & 3u) != 2u) {
-			continue;
+		for (uint32_t o = 0; o < 8u; o++) {
+			// bits o .. o + 80 of the 96 loaded ones: header word (17 bits) and the 57 bits behind it
+			const uint32_t x0 = __funnelshift_r(b0, b1, o), x1 = __funnelshift_r(b1, b2, o), x2 = b2 >> o;
+			const uint32_t hl = (x0 >> 3) & 31u, hd = (x0 >> 8) & 31u, hc = ((x0 >> 13) & 15u) + 4u;
+			const bool head = ((x0 >> 1) & 3u) == 2u && hl <= 29u && hd <= 29u;
+			const uint64_t v2 = (((uint64_t)__funnelshift_r(x1, x2, 17) << 32) | __funnelshift_r(x0, x1, 17)) & ((1ull << (3u * hc)) - 1ull);
+			const uint32_t lo32 = (uint32_t)v2, hi32 = (uint32_t)(v2 >> 32);
+			const uint32_t kr = (uint32_t)s_kraft[lo32 & 4095u] + s_kraft[(lo32 >> 12) & 4095u] + s_kraft[__funnelshift_r(lo32, hi32, 24) & 4095u] +
+				s_kraft[(hi32 >> 4) & 4095u] + s_kraft[(hi32 >> 16) & 4095u];
+			hits |= (head && kr == 128u) ? (1u << o) : 0u;
 		}
-		const uint32_t hl = (w >> 3) & 31u, hd = (w >> 8) & 31u, hc = ((w >> 13) & 15u) + 4u;
-		if (hl > 29u || hd > 29u) {
-			continue;
-		}
-		// Kraft sum of the code-length code: 3 bits each from bit 17
-		const uint64_t v2 = (v >> 17) | ((uint64_t)(hi >> o) << (47u)) ;   // bits 17.. of the header (81 - 17 = 64 bits are enough: 19 * 3 = 57)
-		uint32_t kr = 0;
-		for (uint32_t i = 0; i < hc; i++) {
-			const uint32_t l = (uint32_t)(v2 >> (3u * i)) & 7u;
-			kr += l ? (128u >> l) : 0u;
-		}
-		if (kr != 128u) {
-			continue;
+		if (byte == 0) {
+			hits &= ~1u;   // bit 0 is the stream's own start
 		}
 		// survivors (~0.1 % of the offsets) go to a list: checking their code lengths here, one lane at a time,
 		// would cost more than everything else together
-		const uint32_t at = atomicAdd(n_surv, 1u);
-		if (at < surv_cap) {
-			surv[at] = make_uint2(h, byte * 8u + o);
+		while (hits) {
+			const uint32_t o = __ffs(hits) - 1u;
+			hits &= hits - 1u;
+			const uint32_t at = atomicAdd(n_surv, 1u);
+			if (at < surv_cap) {
+				surv[at] = make_uint2(h, byte * 8u + o);
+			}
 		}
-	}
 	}
 }
 
@@ -1341,9 +1348,12 @@ __global__ void __launch_bounds__(1024) k_seg_window(uint8_t *__restrict__ out, 
 	}
 }
 
-// One CTA per work item (segment): symbols [0, produced - 32 KiB) -> bytes.
-__global__ void __launch_bounds__(256) k_seg_translate(uint8_t *__restrict__ out, const otz_entry *__restrict__ ents, const uint32_t *__restrict__ list,
+// One CTA per work item (segment): symbols [0, produced - 32 KiB) -> bytes.  The 32 KiB before the segment (final
+// since k_seg_window) are staged in shared memory: in text most vectors still hold a marker or two.
+#define I2_TR_THREADS 512
+__global__ void __launch_bounds__(I2_TR_THREADS) k_seg_translate(uint8_t *__restrict__ out, const otz_entry *__restrict__ ents, const uint32_t *__restrict__ list,
 	const uint16_t *__restrict__ sym, uint32_t *__restrict__ work_counter, I2SegCtl seg) {
+	__shared__ __align__(16) uint8_t s_win[I2_PREWIN + 16];
 	__shared__ uint32_t s_k;
 	const uint32_t n = *seg.n_par;
 	for (;;) {
@@ -1357,24 +1367,38 @@ __global__ void __launch_bounds__(256) k_seg_translate(uint8_t *__restrict__ out
 			break;
 		}
 		const uint32_t it = seg.par_items[k], h = it >> 16, c = it & 0xFFFFu;
-		const uint32_t pr = seg.res[h * I2_MAXSEG + seg.live[h * I2_MAXSEG + c]].produced;
+		const I2SegRes *r_ = &seg.res[h * I2_MAXSEG + seg.live[h * I2_MAXSEG + c]];
+		const uint32_t pr = r_->produced;
 		if (pr <= I2_PREWIN) {
 			continue;
 		}
 		const uint32_t body = pr - I2_PREWIN, os = seg.out_start[h * I2_MAXSEG + c];
 		uint8_t *const o = out + ents[list[h]].out_ofs + os;        // o[i] <- sp[i]
-		const uint8_t *const win = o - I2_PREWIN;                      // marker j -> win[j]
 		const uint16_t *const sp = sym + seg.sym_start[h * I2_MAXSEG + c];
-		const uint32_t head = min(body, (16u - (uint32_t)(reinterpret_cast<uint64_t>(o) & 15u)) & 15u);
+		const uint32_t omis = (uint32_t)(reinterpret_cast<uint64_t>(o) & 15u);
+		if (r_->reach) {   // (no reach, no markers; and the first segment of a stream has nothing in front of it)
+			// (a segment in the first 32 KiB of its entry: nothing is read in front of the entry's output)
+			const int64_t avail = (int64_t)os + (int64_t)((reinterpret_cast<uint64_t>(o) - os) & 15u);
+			const uint4 *wa = reinterpret_cast<const uint4 *>(o - I2_PREWIN - omis);
+			for (uint32_t x = threadIdx.x; x < I2_PREWIN / 16u + 1u; x += blockDim.x) {
+				if ((int64_t)(I2_PREWIN + omis) - (int64_t)(16u * x) <= avail) {
+					reinterpret_cast<uint4 *>(s_win)[x] = __ldcg(wa + x);
+				}
+			}
+		}
+		__syncthreads();
+		const uint8_t *const win = s_win + omis;                    // marker j -> win[j]
+		const uint32_t head = min(body, (16u - omis) & 15u);
 		const uint32_t nvec = (body - head) >> 4, tail0 = head + (nvec << 4);
 		for (uint32_t i = threadIdx.x; i < head; i += blockDim.x) {
 			const uint32_t v = sp[i];
-			o[i] = v < 256u ? (uint8_t)v : __ldcg(win + (v - 256u));
+			o[i] = v < 256u ? (uint8_t)v : win[(v - 256u) & (I2_PREWIN - 1u)];
 		}
 		for (uint32_t i = tail0 + threadIdx.x; i < body; i += blockDim.x) {
 			const uint32_t v = sp[i];
-			o[i] = v < 256u ? (uint8_t)v : __ldcg(win + (v - 256u));
+			o[i] = v < 256u ? (uint8_t)v : win[(v - 256u) & (I2_PREWIN - 1u)];
 		}
+#pragma unroll 2
 		for (uint32_t x = threadIdx.x; x < nvec; x += blockDim.x) {
 			const uint32_t i = head + (x << 4);
 			const uint4 a = __ldcs(reinterpret_cast<const uint4 *>(sp + i)), b = __ldcs(reinterpret_cast<const uint4 *>(sp + i + 8));
@@ -1392,7 +1416,7 @@ __global__ void __launch_bounds__(256) k_seg_translate(uint8_t *__restrict__ out
 #pragma unroll
 					for (int t = 0; t < 4; t++) {
 						const uint32_t v = (w[2 * j + (t >> 1)] >> (16 * (t & 1))) & 0xFFFFu;
-						const uint32_t byte = v < 256u ? v : (uint32_t)__ldcg(win + (v - 256u));
+						const uint32_t byte = v < 256u ? v : (uint32_t)win[(v - 256u) & (I2_PREWIN - 1u)];
 						acc |= byte << (8 * t);
 					}
 					r[j] = acc;

@@ -680,7 +680,7 @@ static int launch_seg_par(otz_ctx *c, otz_plan *p, uint8_t *d_out, const I2SegCt
 	kern<<<(uint32_t)(c->sm_count * per_sm), 32 * warps, smem, st>>>(reinterpret_cast<uint8_t *>(c->d_sym_cache), p->d_ents, p->d_inflate_list, 0u,
 		p->d_counter + 60, c->d_tok_cache, p->d_tok_ofs, p->d_tokres, p->d_status, p->d_produced, sg);
 	k_seg_window<<<nh, 1024, 0, st>>>(d_out, p->d_ents, p->d_inflate_list, nh, c->d_sym_cache, p->d_status, p->d_produced, sg);
-	k_seg_translate<<<(uint32_t)c->sm_count * 8u, 256, 0, st>>>(d_out, p->d_ents, p->d_inflate_list, c->d_sym_cache, p->d_counter + 61, sg);
+	k_seg_translate<<<(uint32_t)c->sm_count * 4u, I2_TR_THREADS, 0, st>>>(d_out, p->d_ents, p->d_inflate_list, c->d_sym_cache, p->d_counter + 61, sg);
 	c->launches += 3;
 	CK(cudaGetLastError());
 	return OTZ_SUCCESS;
