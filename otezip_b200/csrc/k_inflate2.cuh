@@ -1602,22 +1602,17 @@ __device__ __forceinline__ I2Batch i2_scan_batch(I2LzSmem<W, T> &S, int buf, uin
 			const uint32_t j = __popc(far_m & lt_mask);
 			S.far_l[buf][j] = make_uint2(mq, ml | (cst << 9));
 			S.far_s[buf][j] = mq - dist;
-		}
-		__syncwarp();
-		for (uint32_t f = 0; f < B.n_far; f++) {
-			const uint2 d = S.far_l[buf][f];
-			const uint32_t cst = d.y >> 9;
 			if (cst != 127u) {
-				const uint32_t src = S.far_s[buf][f], len = d.y & 511u;
-				const uint32_t n = ((src & (VEC - 1u)) + len + VEC - 1u) / VEC;
-				uint32_t v = lane;
-				do {   // bytes: n <= 18, one trip; symbols: n <= 34
-					if (v < n) {
-						const uint32_t sa = (uint32_t)__cvta_generic_to_shared(&S.stage[buf][VEC * (cst + v)]);
-						asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(sa), "l"(gbase + (src & ~(VEC - 1u)) + VEC * v) : "memory");
-					}
-					v += 32;
-				} while (sizeof(T) > 1 && v < n);
+				// every lane fetches the vectors of its own match (cp.async groups are per thread: the executor waits for
+				// its own group and then syncs the warp)
+				uint32_t sa = (uint32_t)__cvta_generic_to_shared(&S.stage[buf][VEC * cst]);
+				const T *g = gbase + ((mq - dist) & ~(VEC - 1u));
+#pragma unroll 1
+				for (uint32_t v = 0; v < nch; v++) {
+					asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(sa), "l"(g) : "memory");
+					sa += 16u;
+					g += VEC;
+				}
 			}
 		}
 	}
