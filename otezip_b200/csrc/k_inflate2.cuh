@@ -374,6 +374,7 @@ struct I2SegRes {
 struct I2SegCtl {
 	uint32_t *count;     // [n_huge] candidates found / segments of the stream
 	uint32_t *start;     // [n_huge][I2_MAXSEG] start bit of every segment, ascending, [0] = 0
+	uint32_t *bucket;    // [n_huge][I2_MAXSEG] first candidate in every 1/255 of the stream (0xFFFFFFFF = none)
 	I2SegRes *res;       // [n_huge][I2_MAXSEG]
 	uint32_t *items;     // compact work list: stream << 16 | segment
 	uint32_t *n_items;
@@ -1188,11 +1189,16 @@ __global__ void __launch_bounds__(256) k_block_verify(const uint8_t *__restrict_
 			if (at < I2_MAXSEG - 1u) {
 				seg.start[h * I2_MAXSEG + 1u + at] = sv.y;
 			}
+			// for streams with more candidates than that: the first one of every 1/255 of the stream, so that the
+			// segments stay evenly spaced
+			const uint32_t bucket = (uint32_t)(((uint64_t)sv.y * (I2_MAXSEG - 1u)) / ((uint64_t)ents[ei].comp_size * 8u));
+			atomicMin(&seg.bucket[h * I2_MAXSEG + 1u + min(bucket, (uint32_t)I2_MAXSEG - 2u)], sv.y);
 		}
 	}
 }
 
-// One thread per huge stream: candidates in ascending order behind the true start (bit 0), result rows cleared, every
+// One thread per huge stream: candidates (all of them, or the first one of every bucket when there are more than 255) in
+// ascending order behind the true start (bit 0), result rows cleared, every
 // segment gets a slice of the stream's token scratch in proportion to its share of the compressed bits, and the
 // segments are appended to the work list.
 __global__ void k_seg_prepare(const otz_entry *__restrict__ ents, const uint32_t *__restrict__ list, uint32_t n_huge,
@@ -1202,18 +1208,29 @@ __global__ void k_seg_prepare(const otz_entry *__restrict__ ents, const uint32_t
 		return;
 	}
 	uint32_t *st = seg.start + h * I2_MAXSEG;
-	uint32_t n = min(seg.count[h], (uint32_t)I2_MAXSEG - 1u);
-	for (uint32_t i = 2; i <= n; i++) {   // insertion sort of st[1..n]
-		const uint32_t v = st[i];
-		uint32_t j = i;
-		while (j > 1 && st[j - 1] > v) {
-			st[j] = st[j - 1];
-			j--;
-		}
-		st[j] = v;
-	}
+	uint32_t n = seg.count[h];
 	st[0] = 0;
-	n += 1;
+	if (n <= I2_MAXSEG - 1u) {
+		for (uint32_t i = 2; i <= n; i++) {   // insertion sort of st[1..n]
+			const uint32_t v = st[i];
+			uint32_t j = i;
+			while (j > 1 && st[j - 1] > v) {
+				st[j] = st[j - 1];
+				j--;
+			}
+			st[j] = v;
+		}
+		n += 1;
+	} else {
+		const uint32_t *bk = seg.bucket + h * I2_MAXSEG;
+		n = 1;
+		for (uint32_t b = 1; b < I2_MAXSEG; b++) {   // the buckets are in ascending order by construction
+			const uint32_t v = bk[b];
+			if (v != 0xFFFFFFFFu) {
+				st[n++] = v;
+			}
+		}
+	}
 	seg.count[h] = n;
 	seg.nlive[h] = 0;
 	seg.par[h] = 0;

@@ -396,6 +396,7 @@ extern "C" void otz_plan_destroy(otz_ctx *c, otz_plan *p) {
 	cudaFree(p->d_surv);
 	cudaFree(p->seg.count);
 	cudaFree(p->seg.start);
+	cudaFree(p->seg.bucket);
 	cudaFree(p->seg.res);
 	cudaFree(p->seg.items);
 	cudaFree(p->seg.n_items);
@@ -476,7 +477,9 @@ extern "C" int otz_plan_create(otz_ctx *c, const otz_entry *ents, uint32_t n, co
 	const uint32_t big_bytes = 256u * 1024u;
 	const char *hb = getenv("OTZ_HUGE_BYTES");
 	const uint32_t huge_bytes = hb ? (uint32_t)strtoul(hb, nullptr, 0) : 1024u * 1024u;
-	auto cls = [&](uint32_t i) { return ents[i].uncomp_size >= huge_bytes ? 2 : ents[i].uncomp_size >= big_bytes ? 1 : 0; };
+	// (the segmented decode keeps bit positions in 32 bits: streams of 512 MiB and more stay on the other paths)
+	auto is_huge = [&](uint32_t i) { return ents[i].uncomp_size >= huge_bytes && ents[i].comp_size < (1u << 29); };
+	auto cls = [&](uint32_t i) { return is_huge(i) ? 2 : ents[i].uncomp_size >= big_bytes ? 1 : 0; };
 	std::stable_sort(infl.begin(), infl.end(), [&](uint32_t a, uint32_t b) {
 		const int ca = cls(a), cb = cls(b);
 		return ca != cb ? ca > cb : ents[a].comp_size > ents[b].comp_size;
@@ -485,8 +488,8 @@ extern "C" int otz_plan_create(otz_ctx *c, const otz_entry *ents, uint32_t n, co
 	p->n_inflate_huge = 0;
 	for (uint32_t i : infl) {
 		p->n_inflate_big += ents[i].uncomp_size >= big_bytes;
-		p->n_inflate_huge += ents[i].uncomp_size >= huge_bytes;
-		if (ents[i].uncomp_size >= huge_bytes) {
+		p->n_inflate_huge += is_huge(i);
+		if (is_huge(i)) {
 			p->huge_max_comp = std::max(p->huge_max_comp, ents[i].comp_size);
 		}
 	}
@@ -530,7 +533,7 @@ extern "C" int otz_plan_create(otz_ctx *c, const otz_entry *ents, uint32_t n, co
 			otz_plan_destroy(c, p);
 			return fail_cuda(cudaGetLastError(), "cudaMalloc(search survivors)");
 		}
-		if (cudaMalloc(&p->seg.count, nh * 4) != cudaSuccess || cudaMalloc(&p->seg.start, ns * 4) != cudaSuccess ||
+		if (cudaMalloc(&p->seg.count, nh * 4) != cudaSuccess || cudaMalloc(&p->seg.start, ns * 4) != cudaSuccess || cudaMalloc(&p->seg.bucket, ns * 4) != cudaSuccess ||
 			cudaMalloc(&p->seg.res, ns * sizeof(I2SegRes)) != cudaSuccess || cudaMalloc(&p->seg.items, ns * 4) != cudaSuccess ||
 			cudaMalloc(&p->seg.n_items, 4) != cudaSuccess || cudaMalloc(&p->seg.live, ns * 4) != cudaSuccess ||
 			cudaMalloc(&p->seg.nlive, nh * 4) != cudaSuccess || cudaMalloc(&p->seg.seg_status, nh * 4) != cudaSuccess ||
@@ -710,6 +713,7 @@ static int dispatch_inflate2(otz_ctx *c, otz_plan *p, const uint8_t *d_archive, 
 		CK(cudaEventRecord(c->ev_fork, s));
 		CK(cudaStreamWaitEvent(s2, c->ev_fork, 0));
 		CK(cudaMemsetAsync(p->seg.count, 0, nh * 4, s2));
+		CK(cudaMemsetAsync(p->seg.bucket, 0xFF, (size_t)nh * I2_MAXSEG * 4, s2));
 		CK(cudaMemsetAsync(p->seg.n_items, 0, 4, s2));
 		CK(cudaMemsetAsync(p->d_counter + 59, 0, 4, s2));
 		k_block_search<<<c->sm_count * 8, 256, 0, s2>>>(d_archive, p->d_ents, p->d_est, p->d_status, p->d_inflate_list, nh, p->d_search_ofs, p->d_surv,
