@@ -252,7 +252,8 @@ __device__ __noinline__ void dfl_build_code(DeflateSmem &S, uint32_t *hist, int 
 }
 
 // grid: persistent; one warp per chunk, chunks handed out in order.
-__global__ void __launch_bounds__(256) k_deflate_chunks(const uint8_t *__restrict__ in, const OtzDflChunk *__restrict__ chunks, uint32_t n_chunks,
+#define DFL_WARPS 3   // warps per CTA: six CTAs (18 chunks) fit the shared memory of an SM
+__global__ void __launch_bounds__(32 * DFL_WARPS) k_deflate_chunks(const uint8_t *__restrict__ in, const OtzDflChunk *__restrict__ chunks, uint32_t n_chunks,
 	uint32_t *__restrict__ tokens /* DFL_CHUNK per chunk slot */, uint8_t *__restrict__ cout, uint32_t *__restrict__ csize,
 	uint32_t *__restrict__ work_counter, uint32_t n_slots) {
 	extern __shared__ __align__(16) uint8_t smem_raw[];
@@ -311,20 +312,26 @@ __global__ void __launch_bounds__(256) k_deflate_chunks(const uint8_t *__restric
 				const uint32_t c = cand - 1;
 				const uint32_t maxl = min((uint32_t)DFL_MAX_MATCH, n - p);
 				uint32_t l = 0;
-				// 8 bytes per trip: the eight word loads of a trip are in flight together (the bytes read beyond maxl
-				// lie inside the padded input buffer and are cut off below)
+				// 16 bytes per trip: the ten word loads of a trip are in flight together, a trip costs one round trip to
+				// L1 / L2 (the bytes read beyond maxl lie inside the padded input buffer and are cut off below)
 				while (l < maxl) {
-					const uint32_t x0 = dfl_word(w, sh0 + c + l) ^ dfl_word(w, sh0 + p + l);
-					const uint32_t x1 = dfl_word(w, sh0 + c + l + 4) ^ dfl_word(w, sh0 + p + l + 4);
-					if (x0) {
-						l += (__ffs(x0) - 1) >> 3;
+					const uint32_t ca = sh0 + c + l, pa = sh0 + p + l;
+					const uint32_t ci = ca >> 2, cs = (ca & 3u) * 8u, pi = pa >> 2, ps = (pa & 3u) * 8u;
+					const uint32_t c0 = __ldg(w + ci), c1 = __ldg(w + ci + 1), c2 = __ldg(w + ci + 2), c3 = __ldg(w + ci + 3), c4 = __ldg(w + ci + 4);
+					const uint32_t p0 = __ldg(w + pi), p1 = __ldg(w + pi + 1), p2 = __ldg(w + pi + 2), p3 = __ldg(w + pi + 3), p4 = __ldg(w + pi + 4);
+					const uint32_t x0 = __funnelshift_r(c0, c1, cs) ^ __funnelshift_r(p0, p1, ps);
+					const uint32_t x1 = __funnelshift_r(c1, c2, cs) ^ __funnelshift_r(p1, p2, ps);
+					const uint32_t x2 = __funnelshift_r(c2, c3, cs) ^ __funnelshift_r(p2, p3, ps);
+					const uint32_t x3 = __funnelshift_r(c3, c4, cs) ^ __funnelshift_r(p3, p4, ps);
+					if (x0 | x1) {
+						l += x0 ? (__ffs(x0) - 1) >> 3 : 4 + ((__ffs(x1) - 1) >> 3);
 						break;
 					}
-					if (x1) {
-						l += 4 + ((__ffs(x1) - 1) >> 3);
+					if (x2 | x3) {
+						l += x2 ? 8 + ((__ffs(x2) - 1) >> 3) : 12 + ((__ffs(x3) - 1) >> 3);
 						break;
 					}
-					l += 8;
+					l += 16;
 				}
 				l = min(l, maxl);
 				if (l >= DFL_MIN_MATCH) {

@@ -1180,8 +1180,8 @@ extern "C" int otz_deflate_plan(otz_ctx *c, const uint64_t *in_ofs, const uint32
 	j->n_crc_chunks = (uint32_t)cchunks.size();
 	j->in_total = total;
 	// persistent grid for the compressor: 2 CTAs x 8 warps per SM
-	j->grid = std::max(1, std::min<int>(c->sm_count * 2, (int)((j->n_chunks + 7) / 8)));
-	j->n_slots = (uint32_t)j->grid * 8u;
+	j->grid = std::max(1, std::min<int>(c->sm_count * 6, (int)((j->n_chunks + DFL_WARPS - 1) / DFL_WARPS)));
+	j->n_slots = (uint32_t)j->grid * DFL_WARPS;
 	int rc;
 	if ((rc = upload(&j->d_ents, ents, c->stream)) || (rc = upload(&j->d_chunks, chunks, c->stream)) ||
 		(rc = upload(&j->d_crc_ents, cents, c->stream)) || (rc = upload(&j->d_crc_chunks, cchunks, c->stream))) {
@@ -1231,13 +1231,13 @@ extern "C" int otz_deflate_run(otz_ctx *c, otz_deflate_job *j, const uint8_t *d_
 	k_crc_finalize<<<(n + 255) / 256, 256, 0, s>>>(j->d_crc_ents, n, j->d_acc, j->d_crc, j->d_status, c->d_tabs);
 	c->launches++;
 	if (j->n_chunks) {
-		const size_t smem = 8 * sizeof(DeflateSmem);
+		const size_t smem = DFL_WARPS * sizeof(DeflateSmem);
 		static bool attr_done = false;
 		if (!attr_done) {
 			CK(cudaFuncSetAttribute(k_deflate_chunks, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
 			attr_done = true;
 		}
-		k_deflate_chunks<<<j->grid, 256, smem, s>>>(d_in, j->d_chunks, j->n_chunks, j->d_tokens, j->d_cout, j->d_csize, j->d_counter,
+		k_deflate_chunks<<<j->grid, 32 * DFL_WARPS, smem, s>>>(d_in, j->d_chunks, j->n_chunks, j->d_tokens, j->d_cout, j->d_csize, j->d_counter,
 			j->n_slots);
 		c->launches++;
 	}
