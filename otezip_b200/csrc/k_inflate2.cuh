@@ -1100,7 +1100,7 @@ __device__ __noinline__ bool i2_plausible_header(const uint8_t *in, uint64_t nbi
 }
 
 // grid: persistent (any size); task t = 256 consecutive bytes of one stream, task_ofs[h] = first task of stream h.
-// Every thread tests the 8 bit offsets of its byte, branch-free: BTYPE = 2, HLIT <= 29, HDIST <= 29, and the Kraft sum
+// Every thread tests the 8 bit offsets of its byte: BTYPE = 2, HLIT <= 29, HDIST <= 29, and the Kraft sum
 // of the code-length code — its (HCLEN + 4) 3-bit lengths are looked up four at a time in a 4096-entry table of
 // sum(2^(7 - len)), saturated at 255 — must be exactly 128 (a complete code; zlib never emits another one).
 __global__ void __launch_bounds__(256) k_block_search(const uint8_t *__restrict__ archive, const otz_entry *__restrict__ ents,
@@ -1145,18 +1145,26 @@ __global__ void __launch_bounds__(256) k_block_search(const uint8_t *__restrict_
 		const uint32_t *qw = reinterpret_cast<const uint32_t *>(q - (sh >> 3));
 		const uint32_t w0 = __ldg(qw), w1 = __ldg(qw + 1), w2 = __ldg(qw + 2), w3 = __ldg(qw + 3);
 		const uint32_t b0 = __funnelshift_r(w0, w1, sh), b1 = __funnelshift_r(w1, w2, sh), b2 = __funnelshift_r(w2, w3, sh);
-		uint32_t hits = 0;
+		// first the header fields of all 8 offsets (22 % pass), then the Kraft sums of those that passed
+		uint32_t cand = 0;
 #pragma unroll
 		for (uint32_t o = 0; o < 8u; o++) {
+			const uint32_t x0 = __funnelshift_r(b0, b1, o);
+			const bool head = ((x0 >> 1) & 3u) == 2u && ((x0 >> 3) & 31u) <= 29u && ((x0 >> 8) & 31u) <= 29u;
+			cand |= head ? (1u << o) : 0u;
+		}
+		uint32_t hits = 0;
+		while (cand) {
+			const uint32_t o = __ffs(cand) - 1u;
+			cand &= cand - 1u;
 			// bits o .. o + 80 of the 96 loaded ones: header word (17 bits) and the 57 bits behind it
 			const uint32_t x0 = __funnelshift_r(b0, b1, o), x1 = __funnelshift_r(b1, b2, o), x2 = b2 >> o;
-			const uint32_t hl = (x0 >> 3) & 31u, hd = (x0 >> 8) & 31u, hc = ((x0 >> 13) & 15u) + 4u;
-			const bool head = ((x0 >> 1) & 3u) == 2u && hl <= 29u && hd <= 29u;
+			const uint32_t hc = ((x0 >> 13) & 15u) + 4u;
 			const uint64_t v2 = (((uint64_t)__funnelshift_r(x1, x2, 17) << 32) | __funnelshift_r(x0, x1, 17)) & ((1ull << (3u * hc)) - 1ull);
 			const uint32_t lo32 = (uint32_t)v2, hi32 = (uint32_t)(v2 >> 32);
 			const uint32_t kr = (uint32_t)s_kraft[lo32 & 4095u] + s_kraft[(lo32 >> 12) & 4095u] + s_kraft[__funnelshift_r(lo32, hi32, 24) & 4095u] +
 				s_kraft[(hi32 >> 4) & 4095u] + s_kraft[(hi32 >> 16) & 4095u];
-			hits |= (head && kr == 128u) ? (1u << o) : 0u;
+			hits |= kr == 128u ? (1u << o) : 0u;
 		}
 		if (byte == 0) {
 			hits &= ~1u;   // bit 0 is the stream's own start

@@ -252,3 +252,33 @@ def test_random_encoder_settings_match_oracle(oracle, huge_bytes):
         c.close()
     finally:
         os.environ.pop("OTZ_HUGE_BYTES", None)
+
+
+@pytest.mark.parametrize("base", [0, 1, 7, 13])
+def test_packed_output_arena_any_alignment(oracle, base):
+    """The C-ABI puts no alignment requirement on out_ofs: entries packed back to back from an odd base offset —
+    STORE, reference-container method 93, small DEFLATE, huge DEFLATE (segments executed in parallel: the symbol
+    buffer follows the alignment of every segment's output) — must come out bit-exact."""
+    rnd = random.Random(100 + base)
+    ms = [synth.member("h0", synth.jsonlog_text((3 << 20) + 5, 41), 8),
+          synth.member("st", synth.random_bytes(100003, 1), 0),
+          synth.member("h1", synth.jsonlog_text((2 << 20) + 777, 42), 8, level=9),
+          synth.member("zr", synth.jsonlog_text(200001, 43), 93),
+          synth.member("h2", synth.jsonlog_text(1500001, 44), 8, level=1)]
+    ms += [synth.member("s%d" % i, synth.jsonlog_text(rnd.randint(1, 90000), 50 + i), 8) for i in range(40)]
+    img = synth.build_zip(ms)
+    tab = parse_central(img).copy()
+    pos = base
+    for i in range(len(tab)):
+        tab["out_ofs"][i] = pos
+        pos += int(tab["uncomp_size"][i])
+    c = _ctx()
+    out, crc, st = c.extract_host(img, tab, default_opts())
+    fb = int(c.L.otz_inflate_fallbacks(c.h))
+    c.close()
+    assert fb == 0, fb
+    for i, m in enumerate(ms):
+        assert (int(st[i]) & 0xFF) == 0 and not (int(st[i]) & 0x300), (m.name, hex(int(st[i])))
+        o, n = int(tab["out_ofs"][i]), int(tab["uncomp_size"][i])
+        assert bytes(out[o:o + n]) == m.raw, m.name
+        assert int(crc[i]) == m.crc32
