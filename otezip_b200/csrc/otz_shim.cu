@@ -705,6 +705,48 @@ static int dispatch_inflate2(otz_ctx *c, otz_plan *p, const uint8_t *d_archive, 
 		CK(cudaFuncSetAttribute(k_inflate_lz<OTZ_SEG_RING, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(4 * sizeof(I2LzSmem<OTZ_SEG_RING>))));
 		attr_done = true;
 	}
+	// phase A of everything that is not huge (from list position `first_`)
+	bool tok_launched = false;
+	auto launch_regular_tok = [&](uint32_t first_) -> int {
+		const uint32_t count = p->n_inflate - first_;
+		const uint32_t first = first_;
+		tok_launched = true;
+		if (!count) {
+			return OTZ_SUCCESS;
+		}
+		// A lock-step step costs the same for 1 or 28 live lanes and a stream advances one symbol per step, so the
+		// streams are spread over as many CTAs as the SM holds (more warps = more latency hidden): pick the number
+		// of resident CTAs per SM (8..4) that gives the most table slots for this batch, most CTAs first.
+		const long fixed = (long)I2_SMEM_BYTES(0);
+		const uint32_t per_sm_streams = (count + (uint32_t)c->sm_count - 1) / (uint32_t)c->sm_count;
+		uint32_t best_c = 4, best_l = 1, best_cov = 0;
+		for (uint32_t cw = 8; cw >= 4; cw--) {
+			const long budget = (long)(227 * 1024) / (long)cw - 1024 - fixed;
+			const uint32_t l = (uint32_t)std::max(1L, std::min<long>(I2_LANES, budget / I2_SLOT_BYTES));
+			const uint32_t cov = std::min(per_sm_streams, cw * l);
+			if (cov > best_cov) {
+				best_cov = cov;
+				best_c = cw;
+				best_l = l;
+			}
+		}
+		uint32_t lanes = std::max(1u, std::min(best_l, (per_sm_streams + best_c - 1) / best_c));
+		const size_t smem_l = (size_t)I2_SMEM_BYTES(best_l);
+		int per_sm = 0;
+		CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_inflate_tok<false>, 32, smem_l));
+		if (per_sm < 1) {
+			snprintf(g_err, sizeof(g_err), "k_inflate_tok does not fit an SM (%zu bytes of shared memory)", smem_l);
+			return OTZ_ERR_CUDA;
+		}
+		per_sm = std::min<int>(per_sm, (int)best_c);
+		const uint32_t grid = std::max(1u, std::min((uint32_t)(c->sm_count * per_sm), count));
+		lanes = std::max(lanes, std::min<uint32_t>(best_l, (count + grid - 1) / grid));
+		k_inflate_tok<false><<<grid, 32, I2_SMEM_BYTES(lanes), s>>>(d_archive, p->d_ents, p->d_est, p->d_status, p->d_inflate_list + first, count,
+			p->d_counter, c->d_tok_cache, p->d_tok_ofs + first, p->d_tokres + first, p->d_fb_list, p->d_counter + 52, lanes, I2SegCtl{});
+		c->launches++;
+		CK(cudaGetLastError());
+		return OTZ_SUCCESS;
+	};
 	if (p->n_inflate_huge && p->seg.count && !c->huge_legacy) {
 		// segmented decode: block search -> one lane per block run -> chain check -> one warp per stream executes the tokens
 		const uint32_t nh = p->n_inflate_huge;
@@ -712,6 +754,14 @@ static int dispatch_inflate2(otz_ctx *c, otz_plan *p, const uint8_t *d_archive, 
 		cudaStream_t s2 = c->stream2;
 		CK(cudaEventRecord(c->ev_fork, s));
 		CK(cudaStreamWaitEvent(s2, c->ev_fork, 0));
+		{
+			// the lane-per-stream tokenizer of the other entries goes first: it is latency-bound and small (8 warps per
+			// SM) and runs next to the search, which would otherwise occupy every thread slot until it is done
+			const int rc_ = launch_regular_tok(nh);
+			if (rc_) {
+				return rc_;
+			}
+		}
 		CK(cudaMemsetAsync(p->seg.count, 0, nh * 4, s2));
 		CK(cudaMemsetAsync(p->seg.bucket, 0xFF, (size_t)nh * I2_MAXSEG * 4, s2));
 		CK(cudaMemsetAsync(p->seg.n_items, 0, 4, s2));
@@ -782,37 +832,12 @@ static int dispatch_inflate2(otz_ctx *c, otz_plan *p, const uint8_t *d_archive, 
 		CK(cudaStreamWaitEvent(s, c->ev_join, 0));
 		return launch_inflate_cfg(c, p, d_archive, d_out, 32, 4096, 0, p->n_inflate, 16, s, p->d_fb_list, p->d_counter + 52);
 	}
-	// A lock-step step costs the same for 1 or 28 live lanes and a stream advances one symbol per step, so the
-	// streams are spread over as many CTAs as the SM holds (more warps = more latency hidden): pick the number
-	// of resident CTAs per SM (8..4) that gives the most table slots for this batch, most CTAs first.
-	const long fixed = (long)I2_SMEM_BYTES(0);
-	const uint32_t per_sm_streams = (count + (uint32_t)c->sm_count - 1) / (uint32_t)c->sm_count;
-	uint32_t best_c = 4, best_l = 1, best_cov = 0;
-	for (uint32_t cw = 8; cw >= 4; cw--) {
-		const long budget = (long)(227 * 1024) / (long)cw - 1024 - fixed;
-		const uint32_t l = (uint32_t)std::max(1L, std::min<long>(I2_LANES, budget / I2_SLOT_BYTES));
-		const uint32_t cov = std::min(per_sm_streams, cw * l);
-		if (cov > best_cov) {
-			best_cov = cov;
-			best_c = cw;
-			best_l = l;
+	if (!tok_launched) {
+		const int rc_ = launch_regular_tok(first);
+		if (rc_) {
+			return rc_;
 		}
 	}
-	uint32_t lanes = std::max(1u, std::min(best_l, (per_sm_streams + best_c - 1) / best_c));
-	const size_t smem_l = (size_t)I2_SMEM_BYTES(best_l);
-	int per_sm = 0;
-	CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_inflate_tok<false>, 32, smem_l));
-	if (per_sm < 1) {
-		snprintf(g_err, sizeof(g_err), "k_inflate_tok does not fit an SM (%zu bytes of shared memory)", smem_l);
-		return OTZ_ERR_CUDA;
-	}
-	per_sm = std::min<int>(per_sm, (int)best_c);
-	const uint32_t grid = std::max(1u, std::min((uint32_t)(c->sm_count * per_sm), count));
-	lanes = std::max(lanes, std::min<uint32_t>(best_l, (count + grid - 1) / grid));
-	k_inflate_tok<false><<<grid, 32, I2_SMEM_BYTES(lanes), s>>>(d_archive, p->d_ents, p->d_est, p->d_status, p->d_inflate_list + first, count,
-		p->d_counter, c->d_tok_cache, p->d_tok_ofs + first, p->d_tokres + first, p->d_fb_list, p->d_counter + 52, lanes, I2SegCtl{});
-	c->launches++;
-	CK(cudaGetLastError());
 	int rc;
 	switch (c->lz_ring) {
 	case 8192: rc = launch_lz<8192>(c, p, d_out, first, count, s); break;
