@@ -282,3 +282,30 @@ def test_packed_output_arena_any_alignment(oracle, base):
         o, n = int(tab["out_ofs"][i]), int(tab["uncomp_size"][i])
         assert bytes(out[o:o + n]) == m.raw, m.name
         assert int(crc[i]) == m.crc32
+
+
+def test_parallel_segments_long_reach_and_short_segments(oracle):
+    """Stress for the marker resolution: blocks of a few hundred symbols (memLevel 1-2: hundreds of segments per
+    stream, most of them shorter than the 32 KiB window, more candidates than the 255 a stream keeps), matches at
+    distances up to 32500 that cross many segment boundaries, byte runs (distance 1) running through block starts."""
+    blob = synth.random_bytes(32500, 21)                                      # (zlib matches up to 32768 - 262 back)
+    rnd = random.Random(22)
+    d0 = blob * 70                                                            # every match reaches 32500 back
+    d1 = b"".join(blob[rnd.randrange(30000):][:rnd.randint(3, 2000)] for _ in range(4000))   # far matches of all lengths
+    d2 = b"".join(bytes([rnd.randrange(256)]) * rnd.randint(1, 70000) for _ in range(60))    # runs across block starts
+    d3 = synth.jsonlog_text(2 << 20, 23)
+    ms = []
+    for i, d in enumerate((d0, d1, d2, d3)):
+        for ml in (1, 2, 8):
+            co = zlib.compressobj(9, zlib.DEFLATED, -15, ml)
+            pl = co.compress(d) + co.flush()
+            ms.append(synth.Member("p%d_%d" % (i, ml), 8, pl, len(d), zlib.crc32(d) & 0xFFFFFFFF, raw=d))
+    img = synth.build_zip(ms)
+    os.environ["OTZ_HUGE_BYTES"] = "200000"
+    try:
+        c = _ctx()
+        fb, st, out = _check(img, oracle, c)
+        c.close()
+    finally:
+        os.environ.pop("OTZ_HUGE_BYTES", None)
+    assert fb <= 6, fb   # (streams that open with stored blocks — the first 32500 random bytes — are k_inflate's)
