@@ -47,18 +47,20 @@ struct __align__(16) DeflateSmem {
 			uint16_t order[288];
 			uint8_t clens[320];
 			uint8_t rle[320 * 2];
+			// (the codes and the staging window are phase 2/3 as well: they share the hash table's space, which
+			// makes room for a seventh CTA per SM)
+			uint16_t code_ll[288];
+			uint16_t code_d[32];
+			uint8_t len_ll[288];
+			uint8_t len_d[32];
+			uint32_t hist_cl[19];
+			uint16_t code_cl[19];
+			uint8_t len_cl[19];
+			uint32_t stage[72];
 		} b;
 	} u;
 	uint32_t hist_ll[288];
 	uint32_t hist_d[32];
-	uint16_t code_ll[288];
-	uint16_t code_d[32];
-	uint8_t len_ll[288];
-	uint8_t len_d[32];
-	uint32_t hist_cl[19];
-	uint16_t code_cl[19];
-	uint8_t len_cl[19];
-	uint32_t stage[72];
 	uint32_t misc[4];   // [0] extra-bit total of the chunk, [1] final byte count
 };
 
@@ -252,7 +254,7 @@ __device__ __noinline__ void dfl_build_code(DeflateSmem &S, uint32_t *hist, int 
 }
 
 // grid: persistent; one warp per chunk, chunks handed out in order.
-#define DFL_WARPS 3   // warps per CTA: six CTAs (18 chunks) fit the shared memory of an SM
+#define DFL_WARPS 3   // warps per CTA: seven CTAs (21 chunks) fit the shared memory of an SM
 __global__ void __launch_bounds__(32 * DFL_WARPS) k_deflate_chunks(const uint8_t *__restrict__ in, const OtzDflChunk *__restrict__ chunks, uint32_t n_chunks,
 	uint32_t *__restrict__ tokens /* DFL_CHUNK per chunk slot */, uint8_t *__restrict__ cout, uint32_t *__restrict__ csize,
 	uint32_t *__restrict__ work_counter, uint32_t n_slots) {
@@ -389,26 +391,26 @@ __global__ void __launch_bounds__(32 * DFL_WARPS) k_deflate_chunks(const uint8_t
 		__syncwarp();
 
 		// ---------------- phase 2: Huffman codes + header cost
-		dfl_build_code(S, S.hist_ll, 286, 15, S.len_ll, S.code_ll);
-		dfl_build_code(S, S.hist_d, 30, 15, S.len_d, S.code_d);
+		dfl_build_code(S, S.hist_ll, 286, 15, S.u.b.len_ll, S.u.b.code_ll);
+		dfl_build_code(S, S.hist_d, 30, 15, S.u.b.len_d, S.u.b.code_d);
 		// code-length sequence with zero-run RLE (symbols 17/18), then the precode
 		uint32_t hlit = 286, hdist = 30, nrle = 0;
 		if (lane == 0) {
-			while (hlit > 257 && S.len_ll[hlit - 1] == 0) {
+			while (hlit > 257 && S.u.b.len_ll[hlit - 1] == 0) {
 				hlit--;
 			}
-			while (hdist > 1 && S.len_d[hdist - 1] == 0) {
+			while (hdist > 1 && S.u.b.len_d[hdist - 1] == 0) {
 				hdist--;
 			}
 			uint8_t *cl = S.u.b.clens;
 			for (uint32_t i = 0; i < hlit; i++) {
-				cl[i] = S.len_ll[i];
+				cl[i] = S.u.b.len_ll[i];
 			}
 			for (uint32_t i = 0; i < hdist; i++) {
-				cl[hlit + i] = S.len_d[i];
+				cl[hlit + i] = S.u.b.len_d[i];
 			}
 			for (int i = 0; i < 19; i++) {
-				S.hist_cl[i] = 0;
+				S.u.b.hist_cl[i] = 0;
 			}
 			const uint32_t tot = hlit + hdist;
 			uint8_t *rle = S.u.b.rle;   // pairs (symbol, extra value)
@@ -421,7 +423,7 @@ __global__ void __launch_bounds__(32 * DFL_WARPS) k_deflate_chunks(const uint8_t
 					if (run >= 11) {
 						rle[2 * nrle] = 18;
 						rle[2 * nrle + 1] = (uint8_t)(run - 11);
-						S.hist_cl[18]++;
+						S.u.b.hist_cl[18]++;
 						nrle++;
 						i += run;
 						continue;
@@ -429,7 +431,7 @@ __global__ void __launch_bounds__(32 * DFL_WARPS) k_deflate_chunks(const uint8_t
 					if (run >= 3) {
 						rle[2 * nrle] = 17;
 						rle[2 * nrle + 1] = (uint8_t)(run - 3);
-						S.hist_cl[17]++;
+						S.u.b.hist_cl[17]++;
 						nrle++;
 						i += run;
 						continue;
@@ -437,7 +439,7 @@ __global__ void __launch_bounds__(32 * DFL_WARPS) k_deflate_chunks(const uint8_t
 				}
 				rle[2 * nrle] = cl[i];
 				rle[2 * nrle + 1] = 0;
-				S.hist_cl[cl[i]]++;
+				S.u.b.hist_cl[cl[i]]++;
 				nrle++;
 				i++;
 			}
@@ -447,17 +449,17 @@ __global__ void __launch_bounds__(32 * DFL_WARPS) k_deflate_chunks(const uint8_t
 		nrle = __shfl_sync(0xFFFFFFFFu, nrle, 0);
 		__syncwarp();
 		// the precode build reuses S.u.b.A/order: keep the RLE list (it lives in u.b.rle/clens)
-		dfl_build_code(S, S.hist_cl, 19, 7, S.len_cl, S.code_cl);
+		dfl_build_code(S, S.u.b.hist_cl, 19, 7, S.u.b.len_cl, S.u.b.code_cl);
 		// exact size of the dynamic block
 		uint32_t bits = 0;
 		for (int s = lane; s < 286; s += 32) {
-			bits += S.hist_ll[s] * S.len_ll[s];
+			bits += S.hist_ll[s] * S.u.b.len_ll[s];
 		}
 		if (lane < 30) {
-			bits += S.hist_d[lane] * S.len_d[lane];
+			bits += S.hist_d[lane] * S.u.b.len_d[lane];
 		}
 		if (lane < 19) {
-			bits += S.hist_cl[lane] * S.len_cl[lane] + (lane == 17 ? 3 * S.hist_cl[17] : lane == 18 ? 7 * S.hist_cl[18] : 0);
+			bits += S.u.b.hist_cl[lane] * S.u.b.len_cl[lane] + (lane == 17 ? 3 * S.u.b.hist_cl[17] : lane == 18 ? 7 * S.u.b.hist_cl[18] : 0);
 		}
 		for (int o = 16; o > 0; o >>= 1) {
 			bits += __shfl_xor_sync(0xFFFFFFFFu, bits, o);
@@ -490,12 +492,12 @@ __global__ void __launch_bounds__(32 * DFL_WARPS) k_deflate_chunks(const uint8_t
 				bw.put(hdist - 1, 5);
 				bw.put(19 - 4, 4);
 				for (int i = 0; i < 19; i++) {
-					bw.put(S.len_cl[c_cl_order[i]], 3);
+					bw.put(S.u.b.len_cl[c_cl_order[i]], 3);
 				}
 				const uint8_t *rle = S.u.b.rle;
 				for (uint32_t i = 0; i < nrle; i++) {
 					const uint32_t s = rle[2 * i];
-					bw.put(S.code_cl[s], S.len_cl[s]);
+					bw.put(S.u.b.code_cl[s], S.u.b.len_cl[s]);
 					if (s == 17) {
 						bw.put(rle[2 * i + 1], 3);
 					} else if (s == 18) {
@@ -515,18 +517,18 @@ __global__ void __launch_bounds__(32 * DFL_WARPS) k_deflate_chunks(const uint8_t
 					if (tk & 0x80000000u) {
 						uint32_t xb, xv;
 						const uint32_t ls = dfl_len_sym(tk & 0xFFu, xb, xv);
-						v = S.code_ll[ls];
-						nb = S.len_ll[ls];
+						v = S.u.b.code_ll[ls];
+						nb = S.u.b.len_ll[ls];
 						v |= (uint64_t)xv << nb;
 						nb += xb;
 						const uint32_t ds = dfl_dist_sym((tk >> 8) & 0x7FFFu, xb, xv);
-						v |= (uint64_t)S.code_d[ds] << nb;
-						nb += S.len_d[ds];
+						v |= (uint64_t)S.u.b.code_d[ds] << nb;
+						nb += S.u.b.len_d[ds];
 						v |= (uint64_t)xv << nb;
 						nb += xb;
 					} else {
-						v = S.code_ll[tk];
-						nb = S.len_ll[tk];
+						v = S.u.b.code_ll[tk];
+						nb = S.u.b.len_ll[tk];
 					}
 				}
 				uint32_t incl = nb;
@@ -538,28 +540,28 @@ __global__ void __launch_bounds__(32 * DFL_WARPS) k_deflate_chunks(const uint8_t
 				}
 				const uint32_t total = __shfl_sync(0xFFFFFFFFu, incl, 31);
 				for (int i = lane; i < 72; i += 32) {
-					S.stage[i] = (i == 0) ? carry : 0u;
+					S.u.b.stage[i] = (i == 0) ? carry : 0u;
 				}
 				__syncwarp();
 				if (nb) {
 					const uint32_t o = off0 + incl - nb;
 					const uint32_t wi = o >> 5, sh = o & 31u;
-					atomicOr(&S.stage[wi], (uint32_t)(v << sh));
+					atomicOr(&S.u.b.stage[wi], (uint32_t)(v << sh));
 					const uint64_t hi = sh ? (v >> (32 - sh)) : (v >> 32);
 					if (sh + nb > 32) {
-						atomicOr(&S.stage[wi + 1], (uint32_t)hi);
+						atomicOr(&S.u.b.stage[wi + 1], (uint32_t)hi);
 					}
 					if (sh + nb > 64) {
-						atomicOr(&S.stage[wi + 2], (uint32_t)(hi >> 32));
+						atomicOr(&S.u.b.stage[wi + 2], (uint32_t)(hi >> 32));
 					}
 				}
 				__syncwarp();
 				const uint32_t endbit = off0 + total;
 				const uint32_t nfull = endbit >> 5;
 				for (uint32_t i = lane; i < nfull; i += 32) {
-					out32[wpos + i] = S.stage[i];
+					out32[wpos + i] = S.u.b.stage[i];
 				}
-				carry = S.stage[nfull];
+				carry = S.u.b.stage[nfull];
 				wpos += nfull;
 				off0 = endbit & 31u;
 				__syncwarp();
@@ -568,7 +570,7 @@ __global__ void __launch_bounds__(32 * DFL_WARPS) k_deflate_chunks(const uint8_t
 				bw.wpos = wpos;
 				bw.acc = carry;
 				bw.nacc = off0;
-				bw.put(S.code_ll[256], S.len_ll[256]);   // end of block
+				bw.put(S.u.b.code_ll[256], S.u.b.len_ll[256]);   // end of block
 				bw.put(ck.last ? 1u : 0u, 3);              // empty stored block: BFINAL, BTYPE=00
 				if (bw.nacc & 7) {
 					bw.put(0, 8 - (bw.nacc & 7));           // pad to a byte boundary

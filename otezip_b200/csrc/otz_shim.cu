@@ -1205,7 +1205,7 @@ extern "C" int otz_deflate_plan(otz_ctx *c, const uint64_t *in_ofs, const uint32
 	j->n_crc_chunks = (uint32_t)cchunks.size();
 	j->in_total = total;
 	// persistent grid for the compressor: 2 CTAs x 8 warps per SM
-	j->grid = std::max(1, std::min<int>(c->sm_count * 6, (int)((j->n_chunks + DFL_WARPS - 1) / DFL_WARPS)));
+	j->grid = std::max(1, std::min<int>(c->sm_count * 7, (int)((j->n_chunks + DFL_WARPS - 1) / DFL_WARPS)));
 	j->n_slots = (uint32_t)j->grid * DFL_WARPS;
 	int rc;
 	if ((rc = upload(&j->d_ents, ents, c->stream)) || (rc = upload(&j->d_chunks, chunks, c->stream)) ||
