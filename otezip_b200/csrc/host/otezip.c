@@ -58,6 +58,7 @@ struct otz_pending {              /* a queued source (write path) */
 	void *buf;
 	uint64_t len;
 	int owned;                    /* free(buf) after the archive is written */
+	int dirty;                    /* has bytes that zip_close must write (every new entry; a replaced existing one) */
 };
 
 static int index_enabled(void) {
@@ -862,7 +863,7 @@ zip_file_t *zip_fopen_index(zip_t *za, zip_uint64_t index, zip_flags_t flags) {
 	if (!is_valid (za) || !a || index >= za->n_entries) {
 		return NULL;
 	}
-	if (za->mode == 1 && index >= a->n_existing) {
+	if (za->mode == 1 && (index >= a->n_existing || (a->pend && a->pend[index].dirty))) {
 		return NULL; /* queued, not yet written */
 	}
 	struct otezip_entry *e = &za->entries[index];
@@ -1033,6 +1034,7 @@ zip_int64_t zip_file_add(zip_t *za, const char *name, zip_source_t *src, zip_fla
 		free (e->name);
 		return -1;
 	}
+	p->dirty = 1;
 	free (src); /* consumed, otezip.c:1175 */
 	zip_uint64_t idx = za->n_entries++;
 	za->next_index = za->n_entries;
@@ -1053,31 +1055,50 @@ int zip_set_file_compression(zip_t *za, zip_uint64_t index, zip_int32_t comp, zi
 	if (comp != OTEZIP_METHOD_STORE && comp != OTEZIP_METHOD_DEFLATE && comp != OTEZIP_METHOD_ZSTD) {
 		return -1;
 	}
-	if (index < a->n_existing) {
+	if (index < a->n_existing && !(a->pend && a->pend[index].dirty)) {
 		return -1; /* already on disk: relabelling would corrupt it (the reference's F4 bug) */
 	}
 	za->entries[index].method = (uint16_t)comp;
 	return 0;
 }
 
-/* otezip.c:1617-1663: replace the queued bytes of an entry added in this session */
+/* otezip.c:1617-1663: new bytes for an entry — one added in this session or one that is already in the archive
+ * (append mode).  The reference compresses and writes them at once and leaves `src` to the caller; here they are
+ * queued like every other source (always as a private copy, since the caller keeps `src`) and written by zip_close
+ * behind the existing data; the central directory then points at the new copy, as in the reference. */
 int zip_file_replace(zip_t *za, zip_uint64_t index, zip_source_t *src, zip_flags_t flags) {
 	(void)flags;
 	struct otz_archive *a = priv (za);
-	if (!is_valid (za) || !a || !src || za->mode != 1 || index >= za->n_entries || index < a->n_existing ||
-		(uint64_t)src->len > MAX_PAYLOAD) {
+	if (!is_valid (za) || !a || !src || za->mode != 1 || index >= za->n_entries || (uint64_t)src->len > MAX_PAYLOAD) {
 		return -1;
+	}
+	if (!a->pend) {
+		a->pend = (struct otz_pending *)calloc (za->n_entries, sizeof (*a->pend));
+		if (!a->pend) {
+			return -1;
+		}
 	}
 	struct otz_pending np;
 	memset (&np, 0, sizeof (np));
-	if (take_source (&np, src) != 0) {
-		return -1;
+	np.len = src->len;
+	if (src->len) {
+		np.buf = malloc ((size_t)src->len);
+		if (!np.buf) {
+			return -1;
+		}
+		memcpy (np.buf, src->buf, (size_t)src->len);
+		np.owned = 1;
 	}
+	np.dirty = 1;
 	if (a->pend[index].owned) {
 		free (a->pend[index].buf);
 	}
 	a->pend[index] = np;
 	za->entries[index].uncomp_size = (uint32_t)src->len;
+	if (za->entries[index].method != OTEZIP_METHOD_STORE && za->entries[index].method != OTEZIP_METHOD_DEFLATE &&
+		za->entries[index].method != OTEZIP_METHOD_ZSTD) {
+		za->entries[index].method = OTEZIP_METHOD_STORE; /* otezip_compress_data's default arm (otezip.c:803-812) */
+	}
 	return 0;
 }
 
@@ -1143,7 +1164,17 @@ static uint32_t write_cdh(FILE *fp, const struct otezip_entry *e, uint64_t lfh_o
  * entry in add order, the central directory and the EOCD (otezip.c:1240-1271, :1561-1590). */
 static int finalize_archive(struct otz_archive *a) {
 	zip_t *za = &a->pub;
-	const zip_uint64_t n_new = za->n_entries - a->n_existing;
+	/* the entries to write: replaced existing ones and everything added in this session, in index order */
+	zip_uint64_t n_new = 0;
+	zip_uint64_t *idx = (zip_uint64_t *)calloc (za->n_entries ? za->n_entries : 1, sizeof (zip_uint64_t));
+	if (!idx) {
+		return -1;
+	}
+	for (zip_uint64_t i = 0; i < za->n_entries; i++) {
+		if (i >= a->n_existing || (a->pend && a->pend[i].dirty)) {
+			idx[n_new++] = i;
+		}
+	}
 	uint64_t *in_ofs = NULL, *out_ofs = NULL;
 	uint32_t *in_len = NULL, *out_size = NULL, *crc = NULL;
 	uint16_t *method = NULL, *method_out = NULL;
@@ -1151,11 +1182,13 @@ static int finalize_archive(struct otz_archive *a) {
 	int rc = -1;
 	uint64_t pos = a->n_existing ? a->append_ofs : 0;
 	if (fseek (za->fp, (long)pos, SEEK_SET) != 0) {
+		free (idx);
 		return -1;
 	}
 	if (za->n_entries > a->lfh64_cap) {
 		uint64_t *nl64 = (uint64_t *)realloc (a->lfh64, za->n_entries * sizeof (uint64_t));
 		if (!nl64) {
+			free (idx);
 			return -1;
 		}
 		a->lfh64 = nl64;
@@ -1164,6 +1197,7 @@ static int finalize_archive(struct otz_archive *a) {
 	if (n_new) {
 		otz_ctx *ctx = otezip_b200_ctx ();
 		if (!ctx) {
+			free (idx);
 			return -1;
 		}
 		in_ofs = (uint64_t *)calloc (n_new, 8);
@@ -1178,9 +1212,9 @@ static int finalize_archive(struct otz_archive *a) {
 		}
 		uint64_t total = 0;
 		for (zip_uint64_t k = 0; k < n_new; k++) {
-			const struct otezip_entry *e = &za->entries[a->n_existing + k];
+			const struct otezip_entry *e = &za->entries[idx[k]];
 			in_ofs[k] = total;
-			in_len[k] = (uint32_t)a->pend[a->n_existing + k].len;
+			in_len[k] = (uint32_t)a->pend[idx[k]].len;
 			/* method 93: the reference's writer cannot produce a stream its reader accepts and always falls
 			 * back to STORE (zstd.inc.c:269, otezip.c:894-899) — same result here */
 			method[k] = e->method == OTEZIP_METHOD_DEFLATE ? OTZ_M_DEFLATE : OTZ_M_STORE;
@@ -1198,7 +1232,7 @@ static int finalize_archive(struct otz_archive *a) {
 		out = (uint8_t *)pout;
 		for (zip_uint64_t k = 0; k < n_new; k++) {
 			if (in_len[k]) {
-				memcpy (in + in_ofs[k], a->pend[a->n_existing + k].buf, in_len[k]);
+				memcpy (in + in_ofs[k], a->pend[idx[k]].buf, in_len[k]);
 			}
 		}
 		uint64_t out_total = 0;
@@ -1230,12 +1264,12 @@ static int finalize_archive(struct otz_archive *a) {
 			goto done;
 		}
 		for (zip_uint64_t k = 0; k < n_new; k++) {
-			struct otezip_entry *e = &za->entries[a->n_existing + k];
+			struct otezip_entry *e = &za->entries[idx[k]];
 			e->crc32 = crc[k];
 			e->comp_size = out_size[k];
 			e->method = method_out[k];
 			e->local_hdr_ofs = (uint32_t)pos;   /* (the reference gives up beyond 4 GiB, otezip.c:1140; ZIP64 here) */
-			a->lfh64[a->n_existing + k] = pos;
+			a->lfh64[idx[k]] = pos;
 			/* chunk index for multi-chunk DEFLATE entries */
 			uint8_t *extra = NULL;
 			uint16_t extra_len = 0;
@@ -1322,6 +1356,7 @@ static int finalize_archive(struct otz_archive *a) {
 		rc = 0;
 	}
 done:
+	free (idx);
 	if (in) {
 		otz_host_free (in);
 	}

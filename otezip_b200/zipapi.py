@@ -59,6 +59,7 @@ class ZipApi:
         L.zip_file_add.restype = C.c_int64
         L.zip_file_add.argtypes = [P(ZipT), C.c_char_p, C.c_void_p, C.c_int]
         L.zip_set_file_compression.argtypes = [P(ZipT), C.c_uint64, C.c_int32, C.c_uint32]
+        L.zip_file_replace.argtypes = [P(ZipT), C.c_uint64, C.c_void_p, C.c_int]
         L.otezip_method_from_string.argtypes = [C.c_char_p]
         self.verify_crc = C.c_int.in_dll(L, "otezip_verify_crc")
         self.ignore_zipbomb = C.c_int.in_dll(L, "otezip_ignore_zipbomb")

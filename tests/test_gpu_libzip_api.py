@@ -206,3 +206,58 @@ def test_chunk_index_roundtrip_and_fallback(api, tmp_path, reflib):
     q = str(tmp_path / "lie.zip")
     open(q, "wb").write(bytes(b))
     assert api.read_all(q)[2] == want
+
+
+def test_append_and_replace(api, tmp_path, reflib):
+    """Append mode (zip_open with ZIP_CREATE on an existing archive, otezip.c:730-733, :776-779) and zip_file_replace
+    (otezip.c:1617-1663) on the batched writer: new entries and new bytes for an EXISTING entry are queued and written
+    behind the old data by zip_close; the result must read back through this library and through the compiled
+    reference."""
+    from otezip_b200.zipapi import ZIP_CREATE
+    import ctypes as C
+    L = api.L
+    p = tmp_path / "a.zip"
+    f = [("f%d.json" % i, synth.jsonlog_text(50000 + 1000 * i, 300 + i)) for i in range(4)]
+    assert api.write_archive(str(p), f, ZIP_CM_DEFLATE) == 0
+    size0 = p.stat().st_size
+    err = C.c_int(-99)
+    za = L.zip_open(str(p).encode(), ZIP_CREATE, C.byref(err))
+    assert za and err.value == 0 and L.zip_get_num_files(za) == 4
+
+    def source(data):   # freep = 0: the caller keeps the buffer
+        buf = C.create_string_buffer(data, max(len(data), 1))
+        return L.zip_source_buffer(za, buf, len(data), 0), buf
+
+    keep = []
+    g0, g1 = synth.jsonlog_text(300000, 310), synth.random_bytes(20000, 311)
+    s, b = source(g0); keep.append(b)
+    i0 = L.zip_file_add(za, b"g0.json", s, 0)
+    s, b = source(g1); keep.append(b)
+    i1 = L.zip_file_add(za, b"g1.bin", s, 0)
+    assert (i0, i1) == (4, 5)
+    assert L.zip_set_file_compression(za, i0, ZIP_CM_DEFLATE, 0) == 0
+    assert L.zip_set_file_compression(za, 2, ZIP_CM_STORE, 0) == -1          # on disk, untouched: cannot be relabelled
+    new1, newg0 = synth.jsonlog_text(123457, 320), synth.jsonlog_text(77777, 321)
+    s, b = source(new1); keep.append(b)
+    assert L.zip_file_replace(za, 1, s, 0) == 0                               # an entry that is already in the archive
+    L.zip_source_free(s)                                                      # (the reference leaves src to the caller)
+    assert not L.zip_fopen_index(za, 1, 0)                                    # queued, not readable before zip_close
+    s, b = source(newg0); keep.append(b)
+    assert L.zip_file_replace(za, i0, s, 0) == 0                              # an entry added in this session
+    L.zip_source_free(s)
+    assert L.zip_file_replace(za, 99, s, 0) == -1
+    zf = L.zip_fopen_index(za, 0, 0)                                          # existing entries stay readable
+    assert zf and zf.contents.size == len(f[0][1])
+    L.zip_fclose(zf)
+    assert L.zip_close(za) == 0
+    assert p.stat().st_size > size0
+    want_names = [n.encode() for n, _ in f] + [b"g0.json", b"g1.bin"]
+    want = [f[0][1], new1, f[2][1], f[3][1], newg0, g1]
+    err2, names, datas = api.read_all(str(p))
+    assert err2 == 0 and names == want_names and datas == want
+    rerr, rdatas = reflib.extract_bytes(p.read_bytes(), verify_crc=1)
+    assert rerr == 0 and rdatas == want
+    # Python's zipfile agrees on the directory (the replaced entry's old bytes are dead space, not an entry)
+    import zipfile
+    with zipfile.ZipFile(str(p)) as z:
+        assert z.testzip() is None and [i.filename.encode() for i in z.infolist()] == want_names
