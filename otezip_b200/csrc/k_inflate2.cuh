@@ -27,9 +27,9 @@
 //            stores.  The same kernel executes Zstandard sequences (8-byte records, k_zstd.cuh) and the token
 //            chains of segmented huge streams (below).
 //
-// Phase A only commits streams that are plainly valid: final block reached, exactly uncomp_size bytes, no
-// stored block with payload, tables within the fixed budget.  Anything else (errors, short streams, stored
-// payloads, exotic code sets) is appended to a fallback list and decoded from scratch by k_inflate, whose
+// Phase A only commits streams that are plainly valid: final block reached, exactly uncomp_size bytes, regular
+// stored-block headers (their payload joins the literals), tables within the fixed budget.  Anything else (errors,
+// short streams, exotic code sets) is appended to a fallback list and decoded from scratch by k_inflate, whose
 // status words define the behaviour in those cases; the two kernels agree bit for bit on every stream both
 // can decode, so the split is invisible to the caller.  The reference's end-of-input rule (dec:811-816,
 // SURVEY.md F1) is evaluated in phase A and reported as OTZ_STF_REF_EOB exactly as k_inflate reports it.
@@ -399,6 +399,7 @@ struct I2SegCtl {
 #define I2_S_BUILD 2u    // code lengths parsed into the slot; waiting for the cooperative table build
 #define I2_S_DEC 3u      // decoding symbols
 #define I2_S_DONE 4u     // no more work
+#define I2_S_COPY 5u     // at the payload of a stored block; waiting for the cooperative copy
 
 __device__ __forceinline__ uint32_t i2_ld_le16(const uint8_t *p) { return (uint32_t)p[0] | ((uint32_t)p[1] << 8); }
 
@@ -407,6 +408,7 @@ __device__ __forceinline__ uint32_t i2_ld_le16(const uint8_t *p) { return (uint3
 #define I2_A_BUILD 1u      // code lengths are in the slot: build the tables, then decode
 #define I2_A_COMMIT 2u     // the stream (or chunk) ended here
 #define I2_A_FALLBACK 3u   // k_inflate takes the stream
+#define I2_A_STORED 4u     // a stored block with payload: st_src / st_len say where it is
 
 // dec:811-816 as k_inflate evaluates it: after a step that leaves the stream unfinished
 #define I2_HDR_STEP_CHECK()                               \
@@ -419,10 +421,11 @@ __device__ __forceinline__ uint32_t i2_ld_le16(const uint8_t *p) { return (uint3
 		}                                                 \
 	}
 
-// One block header (dec:613-627) of the lane's stream: stored blocks (dec:269-319; only empty ones stay on this path),
-// fixed (dec:322-349) and dynamic (dec:122-266) code lengths into the lane's slot.  Lanes run this in lock-step.
+// One block header (dec:613-627) of the lane's stream: stored blocks (dec:269-319; the payload of a non-empty one is
+// copied by the whole warp afterwards), fixed (dec:322-349) and dynamic (dec:122-266) code lengths into the lane's
+// slot.  Lanes run this in lock-step.
 __device__ __forceinline__ uint32_t i2_header(I2Reader &br, uint8_t *slot, const uint8_t *in, uint32_t comp, uint32_t rflags, uint32_t &final_blk,
-	uint32_t &ref_eob, uint32_t &hlit, uint32_t &hdist) {
+	uint32_t &ref_eob, uint32_t &hlit, uint32_t &hdist, uint32_t &st_src, uint32_t &st_len) {
 	const bool chunk_mid = (rflags & OTZ_EF_CHUNK) && !(rflags & OTZ_EF_LAST_CHUNK);
 	br.norm_hdr();
 	uint32_t bits = br.peek();
@@ -431,11 +434,20 @@ __device__ __forceinline__ uint32_t i2_header(I2Reader &br, uint8_t *slot, const
 	br.pos += 3;
 	I2_HDR_STEP_CHECK();
 	if (btype == 0) {
-		// stored block (dec:269-319): only the empty ones (flush points, chunk terminators) stay on this path
+		// stored block (dec:269-319).  Anything irregular — a bad length pair, a payload that runs past the input — is
+		// left to k_inflate, which knows what the reference answers
 		const int64_t rem = br.remaining_bits();
 		const uint64_t bpos = (uint64_t)comp - (uint64_t)(rem >> 3);
-		if ((uint64_t)comp - bpos < 4 || i2_ld_le16(in + bpos) != 0u || i2_ld_le16(in + bpos + 2) != 0xFFFFu) {
+		if ((uint64_t)comp - bpos < 4 || (i2_ld_le16(in + bpos) ^ i2_ld_le16(in + bpos + 2)) != 0xFFFFu) {
 			return I2_A_FALLBACK;
+		} else if (i2_ld_le16(in + bpos) != 0u) {
+			st_len = i2_ld_le16(in + bpos);
+			st_src = (uint32_t)(bpos + 4);
+			if ((uint64_t)comp - (bpos + 4) < st_len) {
+				return I2_A_FALLBACK;
+			} else {
+				return I2_A_STORED;
+			}
 		} else {
 			const uint64_t npos = bpos + 4;
 			br.init(in + npos, (uint64_t)comp - npos);
@@ -614,6 +626,7 @@ __global__ void __launch_bounds__(32) k_inflate_tok(const uint8_t *__restrict__ 
 	uint8_t *litp = nullptr;
 	uint32_t *seqp = nullptr;
 	uint32_t final_blk = 0, ref_eob = 0, hlit = 0, hdist = 0;
+	uint32_t st_src = 0, st_len = 0;   // payload of the stored block the lane stands at (offset in the stream, bytes)
 	// step parsed but not yet emitted (software pipeline of the decode loop): entries and bit windows
 	bool pv = false;
 	uint32_t pe = 0, pd = 0, pb = 0, pb2 = 0;
@@ -772,9 +785,11 @@ __global__ void __launch_bounds__(32) k_inflate_tok(const uint8_t *__restrict__ 
 			}
 		}
 		if (state == I2_S_HDR) {
-			const uint32_t act_ = i2_header(br, slot, in, comp, rflags, final_blk, ref_eob, hlit, hdist);
+			const uint32_t act_ = i2_header(br, slot, in, comp, rflags, final_blk, ref_eob, hlit, hdist, st_src, st_len);
 			if (act_ == I2_A_BUILD) {
 				state = I2_S_BUILD;
+			} else if (act_ == I2_A_STORED) {
+				state = I2_S_COPY;
 			} else if (act_ == I2_A_COMMIT) {
 				I2_COMMIT();
 			} else if (act_ == I2_A_FALLBACK) {
@@ -808,6 +823,51 @@ __global__ void __launch_bounds__(32) k_inflate_tok(const uint8_t *__restrict__ 
 					} else {
 						state = I2_S_DEC;
 						I2_STEP_CHECK();
+					}
+				}
+			}
+		}
+		// ---- (2c) payloads of stored blocks (dec:269-319), one requesting lane at a time, whole warp: the bytes join the
+		// literals of the stream (a run of more than 511 literals becomes escape records when the next match is emitted)
+		{
+			uint32_t need = __ballot_sync(0xFFFFFFFFu, state == I2_S_COPY);
+			while (need) {
+				const int x = __ffs(need) - 1;
+				need &= need - 1;
+				bool room = nl + mb + st_len <= cap;   // (else k_inflate reports the overflow, dec:296-300)
+				if (SEG) {
+					room = room && (int64_t)((uint8_t *)seqp - (seq_floor + nl)) >= (int64_t)st_len + (int64_t)(4u * ((nl - nl0 + st_len) / I2_SEQ_ESC)) + 64;
+				}
+				room = __shfl_sync(0xFFFFFFFFu, (int)room, x) != 0;
+				const uint32_t xlen = __shfl_sync(0xFFFFFFFFu, st_len, x);
+				const uint8_t *sp = reinterpret_cast<const uint8_t *>(__shfl_sync(0xFFFFFFFFu, (unsigned long long)reinterpret_cast<uint64_t>(in + st_src), x));
+				uint8_t *dp = reinterpret_cast<uint8_t *>(__shfl_sync(0xFFFFFFFFu, (unsigned long long)reinterpret_cast<uint64_t>(litp + nl), x));
+				if (room) {
+#pragma unroll 4
+					for (uint32_t i = lane; i < xlen; i += 32) {
+						dp[i] = sp[i];
+					}
+				}
+				__syncwarp();
+				if ((int)lane == x) {
+					if (!room) {
+						I2_FALLBACK();
+					} else {
+						nl += st_len;
+						const uint64_t npos = (uint64_t)st_src + st_len;
+						const bool chunk_mid = (rflags & OTZ_EF_CHUNK) && !(rflags & OTZ_EF_LAST_CHUNK);
+						br.init(in + npos, (uint64_t)comp - npos);
+						if (final_blk) {
+							I2_COMMIT();
+						} else if (npos >= comp) {
+							if (chunk_mid) {
+								I2_COMMIT();   // end of this chunk
+							} else {
+								I2_FALLBACK();   // unfinished stream out of input
+							}
+						} else {
+							state = I2_S_HDR;
+						}
 					}
 				}
 			}

@@ -309,3 +309,31 @@ def test_parallel_segments_long_reach_and_short_segments(oracle):
     finally:
         os.environ.pop("OTZ_HUGE_BYTES", None)
     assert fb <= 6, fb   # (streams that open with stored blocks — the first 32500 random bytes — are k_inflate's)
+
+
+def test_stored_blocks_stay_on_the_fast_path(oracle):
+    """Stored blocks WITH payload (dec:269-319) — incompressible data, level 0, stored blocks between dynamic ones, in
+    small entries and inside the segments of huge ones: the tokenizer copies the payload into the literals of the
+    stream (whole warp) instead of handing the stream to k_inflate."""
+    rnd = random.Random(55)
+    txt = synth.jsonlog_text(400000, 61)
+    ms = [synth.member("rand", synth.random_bytes(200000, 62), 8),
+          synth.member("lvl0", txt[:150000], 8, level=0),
+          synth.member("mixed", txt[:90000] + synth.random_bytes(120000, 63) + txt[90000:200000], 8),
+          synth.member("one", b"x", 8, level=0),
+          synth.member("tiny0", synth.random_bytes(70, 64), 8, level=0),
+          synth.member("huge_mixed", synth.jsonlog_text(2 << 20, 65) + synth.random_bytes(700000, 66) + synth.jsonlog_text(1 << 20, 67), 8),
+          synth.member("huge_mixed2", synth.jsonlog_text(2 << 20, 65) + synth.random_bytes(700000, 66) + synth.jsonlog_text(100000, 67), 8),
+          synth.member("huge_lvl0", synth.jsonlog_text(1500000, 68), 8, level=0),
+          synth.member("huge_rand", synth.random_bytes(1300000, 69), 8)]
+    for i in range(30):
+        parts = [synth.jsonlog_text(rnd.randint(1, 40000), 70 + i) if rnd.random() < 0.5 else synth.random_bytes(rnd.randint(1, 90000), 100 + i)
+                 for _ in range(rnd.randint(1, 5))]
+        ms.append(synth.member("m%d" % i, b"".join(parts), 8, level=rnd.choice([0, 1, 6, 9])))
+    img = synth.build_zip(ms)
+    c = _ctx()
+    fb, st, out = _check(img, oracle, c)
+    c.close()
+    # (a block that mixes random bytes and text can have a code with more long codes than the second-level tables of
+    # the lane-per-stream decoder hold — such a stream is k_inflate's; without the stored-block path all of these were)
+    assert fb <= 3, fb
