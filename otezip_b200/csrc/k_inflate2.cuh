@@ -144,6 +144,9 @@ struct I2Reader {
 		const uint32_t nw = (uint32_t)((skipb + nbytes + 3) >> 2);
 		nvec = (i0 + nw + 3) >> 2;
 		pad_bits = (uint32_t)(((uint64_t)nw << 5) - ((skipb + nbytes) << 3));
+		// (a restart in the middle of a stream — behind a stored block, at a chunk — must not race with copies that are
+		// still on their way into the same slots)
+		asm volatile("cp.async.wait_group 0;" ::: "memory");
 		for (fu = 0; fu < 4u; fu++) {
 			const uint32_t cc = fu < nvec ? fu : nvec;
 			const uint32_t sa = col_sa + ((fu & 7u) << 9);
