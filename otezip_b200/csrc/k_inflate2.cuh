@@ -1775,175 +1775,175 @@ __global__ void __launch_bounds__(128) k_inflate_lz(uint8_t *__restrict__ out, c
 			__syncwarp();
 		}
 		for (uint32_t sgi = 0; sgi < nsegs; sgi++) {
-		const uint8_t *lits;
-		const uint32_t *seq_end;
-		uint32_t nseq, nlit;
-		if (SEG) {
-			const I2SegRes *r_ = &seg.res[k * I2_MAXSEG + seg.live[k * I2_MAXSEG + (PAR ? par_c : sgi)]];
-			lits = scratch + r_->scr_lo;
-			seq_end = reinterpret_cast<const uint32_t *>(scratch + r_->scr_hi);
-			nseq = r_->nseq;
-			nlit = r_->nlit;
-		} else {
-			lits = scratch + tok_ofs[k];
-			seq_end = reinterpret_cast<const uint32_t *>(scratch + tok_ofs[k + 1]);
-			nseq = tr.nseq;
-			nlit = tr.nlit;
-		}
-		uint32_t lp = 0, b = 0;       // literals / records consumed
-		__syncwarp();
-		// records b + lane (recA) and b + 32 + lane (recB); WIDE: their second words in offA / offB
-		const uint2 *const seq_end2 = reinterpret_cast<const uint2 *>(seq_end);
-		uint32_t recA = 0, recB = 0, offA = 0, offB = 0;
-		if (WIDE) {
-			if (lane < nseq) {
-				const uint2 r = seq_end2[-1 - (int32_t)lane];
-				recA = r.x;
-				offA = r.y;
+			const uint8_t *lits;
+			const uint32_t *seq_end;
+			uint32_t nseq, nlit;
+			if (SEG) {
+				const I2SegRes *r_ = &seg.res[k * I2_MAXSEG + seg.live[k * I2_MAXSEG + (PAR ? par_c : sgi)]];
+				lits = scratch + r_->scr_lo;
+				seq_end = reinterpret_cast<const uint32_t *>(scratch + r_->scr_hi);
+				nseq = r_->nseq;
+				nlit = r_->nlit;
+			} else {
+				lits = scratch + tok_ofs[k];
+				seq_end = reinterpret_cast<const uint32_t *>(scratch + tok_ofs[k + 1]);
+				nseq = tr.nseq;
+				nlit = tr.nlit;
 			}
-			if (32u + lane < nseq) {
-				const uint2 r = seq_end2[-33 - (int32_t)lane];
-				recB = r.x;
-				offB = r.y;
-			}
-		} else {
-			recA = lane < nseq ? __ldcs(seq_end - 1 - lane) : 0u;
-			recB = 32u + lane < nseq ? __ldcs(seq_end - 33 - lane) : 0u;
-		}
-		int buf = 0;
-		I2Batch cur = i2_scan_batch<W, WIDE, T>(S, 0, recA, offA, 0u, nseq, q, lp, lits, gbase, lane);
-		while (cur.ntake) {
-			// ---- scan batch k+1 and start its far copies
-			const uint32_t b2 = b + cur.ntake;
-			{
-				const uint32_t j = cur.ntake + lane;
-				const uint32_t fromA = __shfl_sync(0xFFFFFFFFu, recA, j & 31u), fromB = __shfl_sync(0xFFFFFFFFu, recB, j & 31u);
-				recA = j < 32u ? fromA : fromB;
-				if (WIDE) {
-					const uint32_t oA = __shfl_sync(0xFFFFFFFFu, offA, j & 31u), oB = __shfl_sync(0xFFFFFFFFu, offB, j & 31u);
-					offA = j < 32u ? oA : oB;
-					recB = offB = 0;
-					if (b2 + 32u + lane < nseq) {
-						const uint2 r = seq_end2[-33 - (int32_t)(b2 + lane)];
-						recB = r.x;
-						offB = r.y;
-					}
-				} else {
-					recB = b2 + 32u + lane < nseq ? __ldcs(seq_end - 33 - (b2 + lane)) : 0u;
-				}
-			}
-			const I2Batch nxt = i2_scan_batch<W, WIDE, T>(S, buf ^ 1, recA, offA, b2, nseq, cur.q_end, lp + cur.tot_l, lits, gbase, lane);
-			// ---- execute batch k: its far sources have landed in stage[buf]
-			asm volatile("cp.async.wait_group 1;" ::: "memory");
+			uint32_t lp = 0, b = 0;       // literals / records consumed
 			__syncwarp();
-			{
-				// literal runs, all records at once
-				const uint32_t n4 = min(cur.lr, 4u);
-				for (uint32_t t = 0; t < n4; t++) {
-					rb[(cur.my_out + t) & MASK] = (T)(uint8_t)(cur.lit4 >> (8u * t));
+			// records b + lane (recA) and b + 32 + lane (recB); WIDE: their second words in offA / offB
+			const uint2 *const seq_end2 = reinterpret_cast<const uint2 *>(seq_end);
+			uint32_t recA = 0, recB = 0, offA = 0, offB = 0;
+			if (WIDE) {
+				if (lane < nseq) {
+					const uint2 r = seq_end2[-1 - (int32_t)lane];
+					recA = r.x;
+					offA = r.y;
 				}
-#pragma unroll 1
-				for (uint32_t t = 4; t < cur.lr; t++) {
-					rb[(cur.my_out + t) & MASK] = lits[cur.my_lit + t];
+				if (32u + lane < nseq) {
+					const uint2 r = seq_end2[-33 - (int32_t)lane];
+					recB = r.x;
+					offB = r.y;
 				}
+			} else {
+				recA = lane < nseq ? __ldcs(seq_end - 1 - lane) : 0u;
+				recB = 32u + lane < nseq ? __ldcs(seq_end - 33 - lane) : 0u;
 			}
-			uint2 dn = S.far_l[buf][0];
-#pragma unroll 1
-			for (uint32_t f = 0; f < cur.n_far; f++) {
-				const uint2 d = dn;
-				dn = S.far_l[buf][(f + 1u) & 31u];   // next descriptor in flight while this match is copied
-				const uint32_t cst = d.y >> 9, len = d.y & 511u, src = S.far_s[buf][f];
-				if (cst != 127u) {
-					const T *sp = &S.stage[buf][VEC * cst + (src & (VEC - 1u))];
-					if (lane < len) {
-						rb[(d.x + lane) & MASK] = sp[lane];
+			int buf = 0;
+			I2Batch cur = i2_scan_batch<W, WIDE, T>(S, 0, recA, offA, 0u, nseq, q, lp, lits, gbase, lane);
+			while (cur.ntake) {
+				// ---- scan batch k+1 and start its far copies
+				const uint32_t b2 = b + cur.ntake;
+				{
+					const uint32_t j = cur.ntake + lane;
+					const uint32_t fromA = __shfl_sync(0xFFFFFFFFu, recA, j & 31u), fromB = __shfl_sync(0xFFFFFFFFu, recB, j & 31u);
+					recA = j < 32u ? fromA : fromB;
+					if (WIDE) {
+						const uint32_t oA = __shfl_sync(0xFFFFFFFFu, offA, j & 31u), oB = __shfl_sync(0xFFFFFFFFu, offB, j & 31u);
+						offA = j < 32u ? oA : oB;
+						recB = offB = 0;
+						if (b2 + 32u + lane < nseq) {
+							const uint2 r = seq_end2[-33 - (int32_t)(b2 + lane)];
+							recB = r.x;
+							offB = r.y;
+						}
+					} else {
+						recB = b2 + 32u + lane < nseq ? __ldcs(seq_end - 33 - (b2 + lane)) : 0u;
 					}
-					if (len > 32u) {
+				}
+				const I2Batch nxt = i2_scan_batch<W, WIDE, T>(S, buf ^ 1, recA, offA, b2, nseq, cur.q_end, lp + cur.tot_l, lits, gbase, lane);
+				// ---- execute batch k: its far sources have landed in stage[buf]
+				asm volatile("cp.async.wait_group 1;" ::: "memory");
+				__syncwarp();
+				{
+					// literal runs, all records at once
+					const uint32_t n4 = min(cur.lr, 4u);
+					for (uint32_t t = 0; t < n4; t++) {
+						rb[(cur.my_out + t) & MASK] = (T)(uint8_t)(cur.lit4 >> (8u * t));
+					}
 #pragma unroll 1
-						for (uint32_t x = lane + 32u; x < len; x += 32) {
-							rb[(d.x + x) & MASK] = sp[x];
+					for (uint32_t t = 4; t < cur.lr; t++) {
+						rb[(cur.my_out + t) & MASK] = lits[cur.my_lit + t];
+					}
+				}
+				uint2 dn = S.far_l[buf][0];
+#pragma unroll 1
+				for (uint32_t f = 0; f < cur.n_far; f++) {
+					const uint2 d = dn;
+					dn = S.far_l[buf][(f + 1u) & 31u];   // next descriptor in flight while this match is copied
+					const uint32_t cst = d.y >> 9, len = d.y & 511u, src = S.far_s[buf][f];
+					if (cst != 127u) {
+						const T *sp = &S.stage[buf][VEC * cst + (src & (VEC - 1u))];
+						if (lane < len) {
+							rb[(d.x + lane) & MASK] = sp[lane];
+						}
+						if (len > 32u) {
+#pragma unroll 1
+							for (uint32_t x = lane + 32u; x < len; x += 32) {
+								rb[(d.x + x) & MASK] = sp[x];
+							}
+						}
+					} else {
+#pragma unroll 1
+						for (uint32_t x = lane; x < len; x += 32) {
+							rb[(d.x + x) & MASK] = __ldcg(gbase + src + x);
 						}
 					}
-				} else {
-#pragma unroll 1
-					for (uint32_t x = lane; x < len; x += 32) {
-						rb[(d.x + x) & MASK] = __ldcg(gbase + src + x);
-					}
 				}
-			}
-			// the rest in stream order, ring -> ring; two independent short matches per step where the scan said so
-			dn = S.near_l[buf][0];
+				// the rest in stream order, ring -> ring; two independent short matches per step where the scan said so
+				dn = S.near_l[buf][0];
 #pragma unroll 1
-			for (uint32_t f = 0; f < cur.n_near;) {
-				const uint2 d = dn;
-				const uint2 d1 = S.near_l[buf][(f + 1u) & 31u];
-				const uint32_t dqm = d.x & 0xFFFFu, len = (d.x >> 16) & 0x1FFu, sqm = d.y & 0xFFFFu, dd = d.y >> 16;
-				__syncwarp();   // earlier ring stores are visible to the loads below
-				if (f + 1u < cur.n_near && (d1.x >> 31)) {
-					const uint32_t dqm1 = d1.x & 0xFFFFu, len1 = (d1.x >> 16) & 0x1FFu, sqm1 = d1.y & 0xFFFFu;
-					dn = S.near_l[buf][(f + 2u) & 31u];
-					T v0 = 0, v1 = 0;
-					if (lane < len) {
-						v0 = rb[(sqm + lane) & MASK];
-					}
-					if (lane < len1) {
-						v1 = rb[(sqm1 + lane) & MASK];
-					}
-					if (lane < len) {
-						rb[(dqm + lane) & MASK] = v0;
-					}
-					if (lane < len1) {
-						rb[(dqm1 + lane) & MASK] = v1;
-					}
-					f += 2;
-					continue;
-				}
-				dn = d1;
-				f += 1;
-				if (dd >= len) {
-					if (lane < len) {
-						rb[(dqm + lane) & MASK] = rb[(sqm + lane) & MASK];
-					}
-					if (len > 32u) {
-#pragma unroll 1
-						for (uint32_t x = lane + 32u; x < len; x += 32) {
-							rb[(dqm + x) & MASK] = rb[(sqm + x) & MASK];
+				for (uint32_t f = 0; f < cur.n_near;) {
+					const uint2 d = dn;
+					const uint2 d1 = S.near_l[buf][(f + 1u) & 31u];
+					const uint32_t dqm = d.x & 0xFFFFu, len = (d.x >> 16) & 0x1FFu, sqm = d.y & 0xFFFFu, dd = d.y >> 16;
+					__syncwarp();   // earlier ring stores are visible to the loads below
+					if (f + 1u < cur.n_near && (d1.x >> 31)) {
+						const uint32_t dqm1 = d1.x & 0xFFFFu, len1 = (d1.x >> 16) & 0x1FFu, sqm1 = d1.y & 0xFFFFu;
+						dn = S.near_l[buf][(f + 2u) & 31u];
+						T v0 = 0, v1 = 0;
+						if (lane < len) {
+							v0 = rb[(sqm + lane) & MASK];
 						}
+						if (lane < len1) {
+							v1 = rb[(sqm1 + lane) & MASK];
+						}
+						if (lane < len) {
+							rb[(dqm + lane) & MASK] = v0;
+						}
+						if (lane < len1) {
+							rb[(dqm1 + lane) & MASK] = v1;
+						}
+						f += 2;
+						continue;
 					}
-				} else {
-					i2_copy_periodic<W, T>(rb, dqm, sqm, dd, len, lane);
+					dn = d1;
+					f += 1;
+					if (dd >= len) {
+						if (lane < len) {
+							rb[(dqm + lane) & MASK] = rb[(sqm + lane) & MASK];
+						}
+						if (len > 32u) {
+#pragma unroll 1
+							for (uint32_t x = lane + 32u; x < len; x += 32) {
+								rb[(dqm + x) & MASK] = rb[(sqm + x) & MASK];
+							}
+						}
+					} else {
+						i2_copy_periodic<W, T>(rb, dqm, sqm, dd, len, lane);
+					}
+				}
+				b = b2;
+				lp += cur.tot_l;
+				q = cur.q_end;
+				__syncwarp();
+				const uint32_t qa = q & ~(SEGB - 1u);
+				if (qa > qf) {
+					i2_flush_range<W, T>(gbase, rb, qf, qa, lane);
+					qf = qa;
+					__syncwarp();
+				}
+				cur = nxt;
+				buf ^= 1;
+			}
+			asm volatile("cp.async.wait_group 0;" ::: "memory");
+			// literals after the last match
+			while (lp < nlit) {
+				const uint32_t n = min(nlit - lp, SPAN_MAX);
+				for (uint32_t t = lane; t < n; t += 32) {
+					rb[(q + t) & MASK] = lits[lp + t];
+				}
+				lp += n;
+				q += n;
+				__syncwarp();
+				const uint32_t qa = q & ~(SEGB - 1u);
+				if (qa > qf) {
+					i2_flush_range<W, T>(gbase, rb, qf, qa, lane);
+					qf = qa;
+					__syncwarp();
 				}
 			}
-			b = b2;
-			lp += cur.tot_l;
-			q = cur.q_end;
-			__syncwarp();
-			const uint32_t qa = q & ~(SEGB - 1u);
-			if (qa > qf) {
-				i2_flush_range<W, T>(gbase, rb, qf, qa, lane);
-				qf = qa;
-				__syncwarp();
-			}
-			cur = nxt;
-			buf ^= 1;
-		}
-		asm volatile("cp.async.wait_group 0;" ::: "memory");
-		// literals after the last match
-		while (lp < nlit) {
-			const uint32_t n = min(nlit - lp, SPAN_MAX);
-			for (uint32_t t = lane; t < n; t += 32) {
-				rb[(q + t) & MASK] = lits[lp + t];
-			}
-			lp += n;
-			q += n;
-			__syncwarp();
-			const uint32_t qa = q & ~(SEGB - 1u);
-			if (qa > qf) {
-				i2_flush_range<W, T>(gbase, rb, qf, qa, lane);
-				qf = qa;
-				__syncwarp();
-			}
-		}
 		}   // segments
 		if (q > qf) {
 			i2_flush_range<W, T>(gbase, rb, qf, q, lane);
