@@ -189,8 +189,10 @@ struct ZsBackW {
 };
 // take the top n (<= 32) bits of x and shift them out
 __device__ __forceinline__ uint32_t zs_take(uint64_t &x, uint32_t n) {
-	const uint32_t v = n ? (uint32_t)(x >> (64u - n)) : 0u;
-	x <<= n;
+	// three clamped funnel shifts on the two halves (n = 0 and n = 32 need no special case)
+	const uint32_t hi = (uint32_t)(x >> 32), lo = (uint32_t)x;
+	const uint32_t v = __funnelshift_lc(hi, 0u, n);
+	x = ((uint64_t)__funnelshift_lc(lo, hi, n) << 32) | __funnelshift_lc(0u, lo, n);
 	return v;
 }
 
