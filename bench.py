@@ -119,7 +119,7 @@ def workload(name: str, rank: int, n_entries: int | None, alloc):
         method, per = 8, 60000
         desc = "DEFLATE inflate + CRC-32, %d entries x 64 KiB JSON-log text, zlib level 6, ref-safe tail" % n
     elif name == "c3":
-        n = n_entries or 2000
+        n = n_entries or 10000   # the named configuration (20 GB out, ~1 min of host-side generation); --entries 2000 for quick runs
         sizes = synth.config_c3_sizes(n, seed=3 + rank, lo=12, hi=24)
         method, per = 8, 60000
         desc = "DEFLATE inflate + CRC-32, %d mixed entries 4 KiB-16 MiB JSON-log text, zlib level 6" % n
