@@ -1156,6 +1156,9 @@ __device__ __noinline__ bool i2_plausible_header(const uint8_t *in, uint64_t nbi
 					nd++;
 				}
 			}
+			if (kl > 32768u || kd > 32768u) {
+				return false;   // over-subscribed: what most false candidates are after a few dozen lengths
+			}
 		}
 		idx += rep;
 	}
