@@ -380,7 +380,8 @@ def run_reference(args, dist: Dist):
         os.unlink(path)
     v = cores * args.steps * nbytes / dt / GB
     print(json.dumps({
-        "impl": "reference", "metric": "extract GB/s (uncompressed output) — reference CPU path on the host cores",
+        "impl": "reference", "metric": "extract GB/s (uncompressed output, device-timed)",   # the same metric name as the GPU arm
+        "timing": "host wall clock: the reference's CPU path (compiled from its own sources) on all host cores",
         "value": v, "unit": "GB/s", "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": dt / args.steps * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": "u8", "data": "synthetic", "config": {"workload": WORKLOADS[args.workload]},
