@@ -1069,9 +1069,11 @@ __global__ void __launch_bounds__(32) k_inflate_tok(const uint8_t *__restrict__ 
 // far — the code lengths themselves: exactly HLIT + HDIST of them, an end-of-block code, complete literal/length
 // and distance codes.  grid: (ceil(max comp / 256), n_huge).
 __device__ __forceinline__ uint32_t i2_bits_at(const uint8_t *p, uint64_t bit, uint32_t n) {   // n <= 24
-	const uint8_t *q = p + (bit >> 3);
-	const uint32_t v = (uint32_t)q[0] | ((uint32_t)q[1] << 8) | ((uint32_t)q[2] << 16) | ((uint32_t)q[3] << 24);
-	return (v >> (bit & 7)) & ((1u << n) - 1u);
+	// two aligned words and one funnel shift (the image is padded: the word behind the stream is readable)
+	const uint64_t a = reinterpret_cast<uint64_t>(p) + (bit >> 3);
+	const uint32_t *w = reinterpret_cast<const uint32_t *>(a & ~3ull);
+	const uint32_t sh = (uint32_t)(a & 3ull) * 8u + (uint32_t)(bit & 7u);   // <= 31
+	return __funnelshift_r(__ldg(w), __ldg(w + 1), sh) & ((1u << n) - 1u);
 }
 
 __device__ __noinline__ bool i2_plausible_header(const uint8_t *in, uint64_t nbits, uint64_t p, uint32_t hlit, uint32_t hdist, uint32_t hclen) {
