@@ -202,7 +202,8 @@ __device__ __forceinline__ uint16_t i2_symbol_entry(uint32_t s, uint32_t cb) {
 
 // length and position in sorted[] of the code that covers the 15-bit left-aligned value c15 (len 16 = none);
 // lim[j] = S.limit15[j], held in registers by the caller
-__device__ __forceinline__ void i2_lookup15(const I2WarpScratch &S, const uint32_t (&lim)[16], uint32_t c15, uint32_t &len, uint32_t &idx) {
+template <typename WS>
+__device__ __forceinline__ void i2_lookup15(const WS &S, const uint32_t (&lim)[16], uint32_t c15, uint32_t &len, uint32_t &idx) {
 	uint32_t l = 1;
 #pragma unroll
 	for (int j = 1; j <= 15; j++) {
@@ -213,8 +214,8 @@ __device__ __forceinline__ void i2_lookup15(const I2WarpScratch &S, const uint32
 	idx = S.offs[ll] + ((c15 - S.first15[ll]) >> (15u - ll));
 }
 
-template <bool IS_DIST, int ROOT, int CAP>
-__device__ __noinline__ int i2_build_table(I2WarpScratch &S, const uint32_t (&lens)[10], uint32_t b0, uint32_t n, uint16_t *tbl) {
+template <bool IS_DIST, int ROOT, int CAP, typename WS>
+__device__ __noinline__ int i2_build_table(WS &S, const uint32_t (&lens)[10], uint32_t b0, uint32_t n, uint16_t *tbl) {
 	const uint32_t lane = threadIdx.x & 31u;
 	constexpr uint16_t INVALID = IS_DIST ? I2_DST_INVALID : I2_LIT_INVALID;
 	if (lane < 16) {

@@ -11,6 +11,7 @@
 #include "k_crc32.cuh"
 #include "k_inflate.cuh"
 #include "k_inflate2.cuh"
+#include "k_inflate3.cuh"
 #include "k_deflate.cuh"
 #include "k_resolve.cuh"
 #include "k_zstd.cuh"
@@ -50,7 +51,8 @@ struct otz_ctx {
 	uint64_t launches;
 	int inflate_tile;   // lanes per DEFLATE stream (OTZ_INFLATE_TILE; 0 = per batch)
 	int inflate_ring;   // bytes of shared-memory output ring per stream (OTZ_INFLATE_RING; 0 = per batch)
-	int inflate_mode;   // OTZ_INFLATE_MODE: 0 = two-phase (k_inflate_tok + k_inflate_lz, k_inflate as fallback), 1 = k_inflate only
+	int inflate_mode;   // OTZ_INFLATE_MODE: 0 = two-phase (k_inflate_spec + k_inflate_lz, k_inflate as fallback), 1 ("legacy") = k_inflate only,
+	                    // 2 ("lanes") = the lane-per-stream tokenizer k_inflate_tok + block search for huge entries
 	int lz_ring;        // OTZ_LZ_RING: ring bytes per warp of k_inflate_lz (4096 / 8192 / 16384)
 	uint32_t last_fallbacks;   // DEFLATE streams of the last collected run that phase A handed to k_inflate
 	int huge_legacy;        // OTZ_HUGE_MODE=legacy: huge DEFLATE entries on k_inflate<32,16384> instead of the segmented decode
@@ -207,7 +209,7 @@ extern "C" int otz_ctx_create(int device, otz_ctx **out) {
 	t = getenv("OTZ_INFLATE_RING");
 	c->inflate_ring = t ? atoi(t) : 0;
 	t = getenv("OTZ_INFLATE_MODE");
-	c->inflate_mode = (t && !strcmp(t, "legacy")) ? 1 : 0;
+	c->inflate_mode = (t && !strcmp(t, "legacy")) ? 1 : (t && !strcmp(t, "lanes")) ? 2 : 0;
 	t = getenv("OTZ_HUGE_MODE");
 	c->huge_legacy = (t && !strcmp(t, "legacy")) ? 1 : 0;
 	t = getenv("OTZ_SEG_EXEC");
@@ -521,7 +523,7 @@ extern "C" int otz_plan_create(otz_ctx *c, const otz_entry *ents, uint32_t n, co
 			// symbols of the stream + markers in front of every segment (a block of zlib is ~25 KB of compressed data;
 			// a stream with more segments than estimated here is executed by one warp)
 			p->sym_elems += (uint64_t)ents[infl[h]].uncomp_size +
-				(uint64_t)(I2_PREWIN + 16u) * std::min<uint64_t>(I2_MAXSEG, 2u + ents[infl[h]].comp_size / 12288u);
+				(uint64_t)(I2_PREWIN + 16u) * std::min<uint64_t>(I2_MAXSEG, 2u + std::max<uint64_t>(ents[infl[h]].comp_size / 12288u, ents[infl[h]].uncomp_size / I3_SEG_MIN));
 		}
 		if ((rc = upload(&p->d_search_ofs, sofs, c->stream))) {
 			otz_plan_destroy(c, p);
@@ -853,8 +855,113 @@ static int dispatch_inflate2(otz_ctx *c, otz_plan *p, const uint8_t *d_archive, 
 	return launch_inflate_cfg(c, p, d_archive, d_out, 32, 4096, 0, p->n_inflate, 16, s, p->d_fb_list, p->d_counter + 52);
 }
 
+// Two-phase inflate, warp-per-stream speculative tokenizer (k_inflate3.cuh): ONE tokenizer launch for every DEFLATE
+// stream of the batch (longest first); huge streams come out as segment tables, which k_seg_stitch places in the symbol
+// buffer for the parallel execution (second stream), everything else goes to k_inflate_lz; then k_inflate over whatever
+// phase A declined (d_counter + 52 counts those entries).
+static int dispatch_inflate3(otz_ctx *c, otz_plan *p, const uint8_t *d_archive, uint8_t *d_out) {
+	cudaStream_t s = c->stream, s2 = c->stream2;
+	static bool attr_done = false;
+	const size_t smem1 = I3_WARPS * sizeof(I3Smem<1>), smem4 = sizeof(I3Smem<4>);
+	if (!attr_done) {
+		CK(cudaFuncSetAttribute(k_inflate_spec<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem1));
+		CK(cudaFuncSetAttribute(k_inflate_spec<1>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
+		CK(cudaFuncSetAttribute(k_inflate_spec<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem4));
+		CK(cudaFuncSetAttribute(k_inflate_lz<OTZ_SEG_RING, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(4 * sizeof(I2LzSmem<OTZ_SEG_RING>))));
+		attr_done = true;
+	}
+	const uint32_t nh = (p->n_inflate_huge && p->seg.count && !c->huge_legacy) ? p->n_inflate_huge : 0u;
+	const uint32_t count = p->n_inflate - nh;
+	const char *gs = getenv("OTZ_SPEC_GRID");   // (tests: few groups, so that every group decodes many streams)
+	bool forked = false;
+	if (nh) {
+		// huge streams: the 4 warps of a CTA decode one stream together; second stream, next to the warp-per-stream kernel
+		CK(cudaEventRecord(c->ev_fork, s));
+		CK(cudaStreamWaitEvent(s2, c->ev_fork, 0));
+		int per_sm4 = 0;
+		CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm4, k_inflate_spec<4>, 128, smem4));
+		if (per_sm4 < 1) {
+			snprintf(g_err, sizeof(g_err), "k_inflate_spec<4> does not fit an SM (%zu bytes of shared memory)", smem4);
+			return OTZ_ERR_CUDA;
+		}
+		const uint32_t grid4 = gs ? (uint32_t)atoi(gs) : std::max(1u, std::min((uint32_t)(c->sm_count * per_sm4), nh));
+		k_inflate_spec<4><<<grid4, 128, smem4, s2>>>(d_archive, p->d_ents, p->d_est, p->d_status, p->d_inflate_list, 0u, nh, p->d_counter + 57,
+			c->d_tok_cache, p->d_tok_ofs, p->d_tokres, p->d_fb_list, p->d_counter + 52, nh, p->seg);
+		c->launches++;
+		CK(cudaGetLastError());
+	}
+	if (count) {
+		int per_sm = 0;
+		CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_inflate_spec<1>, 32 * I3_WARPS, smem1));
+		if (per_sm < 1) {
+			snprintf(g_err, sizeof(g_err), "k_inflate_spec<1> does not fit an SM (%zu bytes of shared memory)", smem1);
+			return OTZ_ERR_CUDA;
+		}
+		const uint32_t grid = gs ? (uint32_t)atoi(gs) : std::max(1u, std::min((uint32_t)(c->sm_count * per_sm), (count + I3_WARPS - 1) / I3_WARPS));
+		k_inflate_spec<1><<<grid, 32 * I3_WARPS, smem1, s>>>(d_archive, p->d_ents, p->d_est, p->d_status, p->d_inflate_list, nh, p->n_inflate, p->d_counter,
+			c->d_tok_cache, p->d_tok_ofs, p->d_tokres, p->d_fb_list, p->d_counter + 52, nh, p->seg);
+		c->launches++;
+		CK(cudaGetLastError());
+	}
+	if (nh) {
+		I2SegCtl sg = p->seg;
+		sg.sym_top = reinterpret_cast<unsigned long long *>(p->d_counter + 62);
+		sg.out_mis = (uint32_t)(reinterpret_cast<uint64_t>(d_out) & 15u);
+		sg.sym_cap = 0;
+		if (!c->seg_serial && p->sym_elems) {
+			if (p->sym_elems > c->sym_cache_elems) {
+				CK(cudaStreamSynchronize(c->stream));
+				CK(cudaStreamSynchronize(s2));
+				cudaFree(c->d_sym_cache);
+				c->d_sym_cache = nullptr;
+				c->sym_cache_elems = 0;
+				if (cudaMalloc(&c->d_sym_cache, p->sym_elems * 2 + 64) == cudaSuccess) {
+					c->sym_cache_elems = p->sym_elems;
+				} else {
+					cudaGetLastError();
+				}
+			}
+			sg.sym_cap = c->d_sym_cache ? std::min<uint64_t>(p->sym_elems, c->sym_limit) : 0;
+		}
+		CK(cudaMemsetAsync(p->seg.n_par, 0, 4, s2));
+		CK(cudaMemsetAsync(p->seg.nlive, 0, nh * 4, s2));
+		CK(cudaMemsetAsync(p->seg.par, 0, nh * 4, s2));
+		k_seg_stitch<<<(nh + 63) / 64, 64, 0, s2>>>(p->d_ents, p->d_status, p->d_inflate_list, nh, sg, p->d_fb_list, p->d_counter + 52);
+		int per_sm2 = 0;
+		CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm2, k_inflate_lz<OTZ_SEG_RING, false, true>, 128, 4 * sizeof(I2LzSmem<OTZ_SEG_RING>)));
+		const uint32_t lgrid = std::max(1u, std::min((uint32_t)(c->sm_count * std::max(per_sm2, 1)), (nh + 3) / 4));
+		k_inflate_lz<OTZ_SEG_RING, false, true><<<lgrid, 128, 4 * sizeof(I2LzSmem<OTZ_SEG_RING>), s2>>>(d_out, p->d_ents, p->d_inflate_list, nh, p->d_counter + 58,
+			c->d_tok_cache, p->d_tok_ofs, p->d_tokres, p->d_status, p->d_produced, sg);
+		c->launches += 2;
+		if (sg.sym_cap) {
+			int rc_ = c->seg_ring == 8192 ? launch_seg_par<8192>(c, p, d_out, sg, s2) : launch_seg_par<4096>(c, p, d_out, sg, s2);
+			if (rc_) {
+				return rc_;
+			}
+		}
+		CK(cudaGetLastError());
+		CK(cudaEventRecord(c->ev_join, s2));
+		forked = true;
+	}
+	if (count) {
+		int rc;
+		switch (c->lz_ring) {
+		case 8192: rc = launch_lz<8192>(c, p, d_out, nh, count, s); break;
+		case 16384: rc = launch_lz<16384>(c, p, d_out, nh, count, s); break;
+		default: rc = launch_lz<4096>(c, p, d_out, nh, count, s); break;
+		}
+		if (rc) {
+			return rc;
+		}
+	}
+	if (forked) {
+		CK(cudaStreamWaitEvent(s, c->ev_join, 0));   // (k_seg_stitch appends to the same fallback list)
+	}
+	return launch_inflate_cfg(c, p, d_archive, d_out, 32, 4096, 0, p->n_inflate, 16, s, p->d_fb_list, p->d_counter + 52);
+}
+
 static int dispatch_inflate(otz_ctx *c, otz_plan *p, const uint8_t *d_archive, uint8_t *d_out) {
-	if (!c->inflate_mode && !c->inflate_tile && !c->inflate_ring) {
+	if (c->inflate_mode != 1 && !c->inflate_tile && !c->inflate_ring) {
 		// token scratch: grow-only, shared by the runs of this context (they are ordered on its stream)
 		if (p->tok_bytes + 64 > c->tok_cache_bytes) {
 			CK(cudaStreamSynchronize(c->stream));
@@ -868,7 +975,7 @@ static int dispatch_inflate(otz_ctx *c, otz_plan *p, const uint8_t *d_archive, u
 			}
 		}
 		if (c->d_tok_cache) {
-			return dispatch_inflate2(c, p, d_archive, d_out);
+			return c->inflate_mode == 2 ? dispatch_inflate2(c, p, d_archive, d_out) : dispatch_inflate3(c, p, d_archive, d_out);
 		}
 	}
 	if (c->inflate_tile || c->inflate_ring) {   // explicit configuration (tests, sweeps): one kernel for everything
