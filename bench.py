@@ -1,17 +1,20 @@
 #!/usr/bin/env python
 """bench.py — extract GB/s (uncompressed output, device-timed) of the otezip_b200 hot path.
 
-  python bench.py [--gpus N] [--steps K] [--warmup W] [--workload c2|c1|c3|c4] [--impl reference]
+  python bench.py [--gpus N] [--steps K] [--warmup W] [--workload c3|c1|c2|c4|c4z|c5|c3w|c2x] [--impl reference]
 
-One "step" = one pass of the batched extract over one synthetic archive set.  The default
-workload (N=1 headline) is BASELINE.json configs[1]: STORE + CRC-32 verify only, 10,000 entries
-of 1 MiB random bytes, laid out as an archive set of 8 x 1,250-entry ZIP32 files
-resident in HBM as one image.  Under torchrun (N>1) every rank owns one GPU and its own archive
-set (entries shard by index, no data-path collective): weak scaling, value = all ranks' bytes
-over the max-over-ranks device time.
+One "step" = one pass of the batched extract over one synthetic archive.  The default workload (the headline) is
+BASELINE.json configs[2]: DEFLATE inflate of 10,000 mixed-size entries (4 KiB-16 MiB, JSON-log text, zlib level 6),
+20.5 GB of output — the configuration the north star's target is quoted on; it fits one B200.  Under torchrun (N > 1)
+the ONE archive is sharded: otz_partition cuts the entry table into N contiguous index ranges balanced by
+comp + uncomp bytes, every rank owns one GPU and its byte range of the archive (strong scaling, no data-path
+collective: torch.distributed only carries the barrier and the max / sum of the reported scalars); value = all
+entries' bytes over the max-over-ranks device time.
 
-Output: ONE JSON line (see the contract in the task statement), with `roofline` for the dominant
-kernel and `cpu_baseline` = the compiled reference (oracle/_ref) on the host cores.
+Output: ONE JSON line (contract in the task statement) with `roofline` for the dominant kernels, `cpu_baseline` =
+the compiled reference (oracle/_ref) on the host cores over a stride subsample of the same entry list, `e2e`
+through the C-ABI host-buffer call, and — at N = 1 — `secondary`: the other BASELINE configurations (value,
+roofline fraction, e2e) measured in the same process.
 """
 from __future__ import annotations
 
@@ -31,9 +34,77 @@ ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
 GB = 1e9
+NCPU = os.cpu_count() or 4
+
+WORKLOADS = {
+    "c3": "configs[2]: DEFLATE inflate of 10,000 mixed-size entries (4 KiB-16 MiB, synthetic log/JSON text)",
+    "c1": "configs[0]: 1,000-entry DEFLATE archive, 64 KiB text-like entries, CRC-32 check",
+    "c2": "configs[1]: STORE + CRC-32 verify only, 10,000 entries of 1 MiB random bytes",
+    "c4": "configs[3]: method 93 decode of 10,000 entries of 256 KiB (the reference's method-93 container)",
+    "c4z": "configs[3] shape with real Zstandard (RFC 8878) frames from libzstd level 3 (parity pinned by libzstd, not by the reference)",
+    "c5": "configs[4]: archive creation, batched DEFLATE compress + CRC-32, 4 GiB synthetic corpus",
+    "c3w": "configs[2] shape, archive written by this library (chunk-indexed DEFLATE entries)",
+    "c2x": "configs[1] shape, STORE entries extracted (copied to the arena) and CRC-checked",
+}
+DEFAULT_ENTRIES = {"c3": 10000, "c1": 1000, "c2": 10000, "c2x": 10000, "c4": 10000, "c4z": 10000, "c5": 16384, "c3w": 2000}
+METRIC = {
+    "c2": "CRC-32 verify GB/s (STORE payload bytes, device-timed)",
+    "c5": "compress GB/s (uncompressed input, device-timed; CRC-32 + DEFLATE + compaction)",
+}
+DECODE_KERNELS = {
+    "c1": "k_inflate_spec + k_inflate_lz (+ k_inflate for declined streams)",
+    "c3": "k_inflate_spec<1> + k_inflate_lz; entries >= 1 MiB: k_inflate_spec<4> + k_inflate_lz<symbols> + k_seg_window + k_seg_translate",
+    "c3w": "k_inflate_spec + k_inflate_lz (+ k_inflate for declined streams)",
+    "c4": "k_zstdref", "c4z": "k_zstd_tok + k_inflate_lz<wide>", "c2": "k_store_copy", "c2x": "k_store_copy",
+}
+# stride of the entry subsample the CPU legs time (the reference needs ~1 min per pass of configs[2] on
+# 16 cores; every stride-th entry of the same list keeps the size distribution)
+REF_STRIDE = {"c3": 16, "c1": 1, "c2": 16, "c2x": 16, "c4": 4, "c4z": 4, "c3w": 16, "c5": 16}
+
+
+def metric_name(wl: str) -> str:
+    return METRIC.get(wl, "extract GB/s (uncompressed output, device-timed)")
 
 
 # ----------------------------------------------------------------------------- workloads
+def entry_plan(name: str, n: int):
+    """The deterministic part of a workload: sizes, method, text seed.  Same on every rank and in both arms."""
+    from otezip_b200 import synth
+    if name in ("c2", "c2x"):
+        return dict(sizes=[1 << 20] * n, method=0, seed=2, sizes_desc="1 MiB each", data="seeded random bytes (PCG64)", codec="STORE")
+    if name in ("c1",):
+        return dict(sizes=[65536] * n, method=8, seed=1234, sizes_desc="64 KiB each", data="JSON-log text (synth.TextPool, seed 1234)",
+                    codec="raw DEFLATE, zlib level 6, Z_SYNC_FLUSH + Z_FINISH tail (SURVEY F1)")
+    if name in ("c3", "c3w"):
+        return dict(sizes=synth.config_c3_sizes(n, seed=3, lo=12, hi=24), method=8, seed=3, sizes_desc="floor(2^U(12,24)), random.Random(3)",
+                    data="JSON-log text (synth.TextPool, seed 3)", codec="raw DEFLATE, zlib level 6, Z_SYNC_FLUSH + Z_FINISH tail (SURVEY F1)")
+    if name == "c4":
+        return dict(sizes=[262144] * n, method=93, seed=4, sizes_desc="256 KiB each", data="JSON-log text (synth.TextPool, seed 4)",
+                    codec="method 93, the reference's raw-block container (SURVEY F3)")
+    if name == "c4z":
+        return dict(sizes=[262144] * n, method=93, seed=4, sizes_desc="256 KiB each", data="JSON-log text (synth.TextPool, seed 4)",
+                    codec="method 93, real Zstandard frames (libzstd level 3)")
+    if name == "c5":
+        return dict(sizes=[262144] * n, method=8, seed=5, sizes_desc="256 KiB each", data="JSON-log text (synth.TextPool, seed 5)",
+                    codec="DEFLATE compress (GPU), zero-length / incompressible -> STORE")
+    raise SystemExit("unknown workload " + name)
+
+
+def wl_config(name: str, n: int, world: int, scaling: str) -> dict:
+    """`config` of the JSON line: only what defines the workload — identical in the GPU arm and the reference arm."""
+    pl = entry_plan(name, n)
+    un = int(sum(pl["sizes"]))
+    if world == 1:
+        par = "1 GPU"
+    elif scaling == "strong":
+        par = "ONE archive sharded over %d GPUs: contiguous index ranges balanced by comp+uncomp bytes (otz_partition), no collective" % world
+    else:
+        par = "%d GPUs, one full archive each (weak scaling), no collective" % world
+    return {"workload": WORKLOADS[name], "entries": n, "uncomp_bytes": un * (world if scaling == "weak" else 1), "entry_sizes": pl["sizes_desc"],
+            "payload": pl["data"], "codec": pl["codec"], "parallelism": par,
+            "cache": "inputs larger than L2 (no flush needed)" if un > 256e6 else "inputs smaller than L2: steady-state L2-resident"}
+
+
 def _zip_headers(name: bytes, method: int, crc: int, comp: int, uncomp: int, lfh_ofs: int):
     lfh = struct.pack("<IHHHHHIIIHH", 0x04034B50, 20, 0, method, 0, 0x21, crc, comp, uncomp, len(name), 0) + name
     cdh = struct.pack("<IHHHHHHIIIHHHHHII", 0x02014B50, 0x031E, 20, 0, method, 0, 0x21, crc, comp, uncomp, len(name),
@@ -41,114 +112,111 @@ def _zip_headers(name: bytes, method: int, crc: int, comp: int, uncomp: int, lfh
     return lfh, cdh
 
 
-def build_archive_set(alloc, payloads_fn, n_entries: int, per_archive: int, method: int, threads: int = 8):
-    """Lay out ceil(n/per_archive) ZIP32 archives back to back in one buffer from alloc(nbytes).
-    payloads_fn(i) -> (payload bytes-like, uncomp_size, crc32).  Returns (image, entry table)."""
+def build_archive_set(alloc, payloads_fn, indices, per_archive: int, method: int, threads: int = NCPU):
+    """Lay out ceil(n/per_archive) ZIP32 archives back to back in one buffer from alloc(nbytes) (one ZIP32
+    file holds at most 4 GiB / 65,535 entries).  indices = global entry numbers of this image;
+    payloads_fn(i) -> (payload bytes-like, uncomp_size, crc32).  Returns (image, entry table, arena bytes)."""
     from otezip_b200.native import ENTRY_DTYPE
-    # pass 1: sizes
-    metas = []
+    indices = list(indices)
     with cf.ThreadPoolExecutor(threads) as ex:
-        metas = list(ex.map(payloads_fn, range(n_entries)))
-    n_arch = (n_entries + per_archive - 1) // per_archive
+        metas = list(ex.map(payloads_fn, indices))
+    n = len(indices)
     total = 0
     layout = []
-    for a in range(n_arch):
+    for a in range(0, n, per_archive):
         base = total
-        ents = range(a * per_archive, min(n_entries, (a + 1) * per_archive))
-        pos = 0
-        cd_len = 0
+        pos = cd_len = 0
         recs = []
-        for i in ents:
-            name = b"e/%05d.bin" % i
-            recs.append((i, pos, name))
-            pos += 30 + len(name) + len(metas[i][0])
+        for k in range(a, min(n, a + per_archive)):
+            name = b"e/%05d.bin" % indices[k]
+            recs.append((k, pos, name))
+            pos += 30 + len(name) + len(metas[k][0])
             cd_len += 46 + len(name)
         layout.append((base, recs, pos, cd_len))
-        total += pos + cd_len + 22
-        total = (total + 15) & ~15
-    img = alloc(total)
-    tab = np.zeros(n_entries, dtype=ENTRY_DTYPE)
+        total = (total + pos + cd_len + 22 + 15) & ~15
+    img = alloc(total + 64)
+    tab = np.zeros(n, dtype=ENTRY_DTYPE)
     out_ofs = 0
     for base, recs, cd_ofs, cd_len in layout:
         cd = bytearray()
-        for i, pos, name in recs:
-            payload, uncomp, crc = metas[i]
+        for k, pos, name in recs:
+            payload, uncomp, crc = metas[k]
             lfh, cdh = _zip_headers(name, method, crc, len(payload), uncomp, pos)
             o = base + pos
             img[o:o + len(lfh)] = np.frombuffer(lfh, dtype=np.uint8)
             o += len(lfh)
             img[o:o + len(payload)] = np.frombuffer(payload, dtype=np.uint8)
             cd += cdh
-            tab[i] = (base + pos, out_ofs, len(payload), uncomp, crc, method, 0)
+            tab[k] = (base + pos, out_ofs, len(payload), uncomp, crc, method, 0)
             out_ofs += (uncomp + 15) & ~15
+            metas[k] = None
         o = base + cd_ofs
         img[o:o + len(cd)] = np.frombuffer(bytes(cd), dtype=np.uint8)
         o += len(cd)
-        eocd = struct.pack("<IHHHHIIH", 0x06054B50, 0, 0, len(recs), len(recs), len(cd), cd_ofs, 0)
+        eocd = struct.pack("<IHHHHIIH", 0x06054B50, 0, 0, len(recs) & 0xFFFF, len(recs) & 0xFFFF, len(cd), cd_ofs, 0)
         img[o:o + 22] = np.frombuffer(eocd, dtype=np.uint8)
-    return img, tab, out_ofs
+    return img[:total], tab, out_ofs
 
 
-def workload(name: str, rank: int, n_entries: int | None, alloc):
-    """-> dict(image, table, out_bytes, uncomp_bytes, algo_bytes, opts, desc)"""
+def shard_of(name: str, sizes, world: int, rank: int):
+    """This rank's contiguous index range of the ONE archive (strong scaling).  The split is otz_partition over the
+    directory sizes; so that a rank only has to compress its own shard, the compressed sizes that enter the weights
+    are the size model of this text (ratio 9.3 for DEFLATE level 6, 7.6 for zstd-3, 1 for STORE / the container)."""
+    from otezip_b200.native import ENTRY_DTYPE, partition
+    if world == 1:
+        return 0, len(sizes)
+    ratio = {"c1": 9.3, "c3": 9.3, "c3w": 6.9, "c4z": 7.6}.get(name, 1.0)
+    t = np.zeros(len(sizes), dtype=ENTRY_DTYPE)
+    t["uncomp_size"] = np.array(sizes, dtype=np.uint32)
+    t["comp_size"] = (np.array(sizes, dtype=np.float64) / ratio).astype(np.uint32)
+    first = partition(t, world)
+    return int(first[rank]), int(first[rank + 1])
+
+
+def workload(name: str, rank: int, world: int, n_entries: int | None, alloc, scaling: str = "strong", indices=None):
+    """-> dict(image, table, out_bytes, uncomp_bytes, algo_bytes, opts, dominant, n_entries, lo, hi).
+    indices: explicit global entry numbers (the CPU legs' stride subsample) instead of this rank's shard."""
     from otezip_b200 import synth
     from otezip_b200.native import default_opts
-    if name in ("c2", "c2x"):
-        n = n_entries or 10000
-        size = 1 << 20
-
-        def gen(i):
-            rng = np.random.Generator(np.random.PCG64([2, rank, i]))
-            d = rng.bit_generator.random_raw(size // 8).view(np.uint8)
-            return d, size, zlib.crc32(d) & 0xFFFFFFFF
-        img, tab, out_bytes = build_archive_set(alloc, gen, n, 1250, 0)
-        un = int(tab["uncomp_size"].astype(np.int64).sum())
-        if name == "c2x":   # STORE extract: payload copied to the arena, then CRC'd
-            return dict(image=img, table=tab, out_bytes=out_bytes, uncomp_bytes=un, algo_bytes=2 * un, opts=default_opts(),
-                        desc="STORE extract (copy + CRC-32), %d entries x 1 MiB random bytes (archive set of %d ZIP32 files)"
-                        % (n, (n + 1249) // 1250), dominant="decode")
-        return dict(image=img, table=tab, out_bytes=0, uncomp_bytes=un, algo_bytes=un, opts=default_opts(verify_only=1),
-                    desc="STORE + CRC-32 verify only, %d entries x 1 MiB random bytes (archive set of %d ZIP32 files)"
-                    % (n, (n + 1249) // 1250), dominant="crc")
     if name == "c3w":
         return workload_c3w(rank, n_entries, alloc)
-    pool = synth.TextPool(64 << 20, seed={"c1": 1234, "c3": 3, "c4": 4, "c4z": 4}[name] + 7919 * rank)
-    if name == "c1":
-        n = n_entries or 1000
-        sizes = [65536] * n
-        method, per = 8, 60000
-        desc = "DEFLATE inflate + CRC-32, %d entries x 64 KiB JSON-log text, zlib level 6, ref-safe tail" % n
-    elif name == "c3":
-        n = n_entries or 10000   # the named configuration (20 GB out, ~1 min of host-side generation); --entries 2000 for quick runs
-        sizes = synth.config_c3_sizes(n, seed=3 + rank, lo=12, hi=24)
-        method, per = 8, 60000
-        desc = "DEFLATE inflate + CRC-32, %d mixed entries 4 KiB-16 MiB JSON-log text, zlib level 6" % n
-    elif name == "c4":
-        n = n_entries or 10000
-        sizes = [262144] * n
-        method, per = 93, 15000
-        desc = "method-93 (reference container) decode + CRC-32, %d entries x 256 KiB" % n
-    elif name == "c4z":
-        n = n_entries or 10000
-        sizes = [262144] * n
-        method, per = 93, 60000
-        desc = "method 93 with REAL Zstandard frames (libzstd level 3) decode + CRC-32, %d entries x 256 KiB" % n
-        from otezip_b200.zstdlib import Zstd
-        zs = Zstd()
+    n = n_entries or DEFAULT_ENTRIES[name]
+    pl = entry_plan(name, n)
+    sizes, method = pl["sizes"], pl["method"]
+    seed_shift = 7919 * rank if (scaling == "weak" and world > 1) else 0
+    if indices is None:
+        lo, hi = shard_of(name, sizes, world, rank) if scaling == "strong" else (0, n)
+        indices = range(lo, hi)
     else:
-        raise SystemExit("unknown workload " + name)
-    datas = [pool.take(s) for s in sizes]
+        lo, hi = 0, n
+    if name in ("c2", "c2x"):
+        def gen(i):
+            rng = np.random.Generator(np.random.PCG64([2, seed_shift, i]))
+            d = rng.bit_generator.random_raw(sizes[i] // 8).view(np.uint8)
+            return d, sizes[i], zlib.crc32(d) & 0xFFFFFFFF
+        per = 1250
+    else:
+        pool = synth.TextPool(64 << 20, seed=pl["seed"] + seed_shift)
+        offs = pool.offsets(sizes)
+        zs = None
+        if name == "c4z":
+            from otezip_b200.zstdlib import Zstd
+            zs = Zstd()
 
-    def gen(i):
-        d = datas[i]
-        crc = zlib.crc32(d) & 0xFFFFFFFF
-        pl = synth.deflate_raw(d, 6, True) if method == 8 else (zs.compress(d, 3) if name == "c4z" else synth.zstdref_container(d))
-        return pl, len(d), crc
-    img, tab, out_bytes = build_archive_set(alloc, gen, n, per, method)
+        def gen(i):
+            d = pool.at(offs[i], sizes[i])
+            crc = zlib.crc32(d) & 0xFFFFFFFF
+            pay = synth.deflate_raw(d, 6, True) if method == 8 else (zs.compress(d, 3) if zs else synth.zstdref_container(d))
+            return pay, len(d), crc
+        per = 15000 if name == "c4" else 60000
+    img, tab, out_bytes = build_archive_set(alloc, gen, indices, per, method)
     un = int(tab["uncomp_size"].astype(np.int64).sum())
     comp = int(tab["comp_size"].astype(np.int64).sum())
-    return dict(image=img, table=tab, out_bytes=out_bytes, uncomp_bytes=un, algo_bytes=un + comp,
-                opts=default_opts(), desc=desc, dominant="decode")
+    if name == "c2":
+        return dict(image=img, table=tab, out_bytes=0, uncomp_bytes=un, algo_bytes=un, opts=default_opts(verify_only=1), dominant="crc",
+                    n_entries=n, lo=lo, hi=hi)
+    return dict(image=img, table=tab, out_bytes=out_bytes, uncomp_bytes=un, algo_bytes=(2 * un if name == "c2x" else un + comp),
+                opts=default_opts(), dominant="decode", n_entries=n, lo=lo, hi=hi)
 
 
 def workload_c3w(rank: int, n_entries: int | None, alloc):
@@ -182,9 +250,10 @@ def workload_c3w(rank: int, n_entries: int | None, alloc):
     first, cnt, cs, cb = ctx.deflate_chunks(job, n)
     ctx.deflate_destroy(job)
     ctx.dev_free(d_in)
+    ctx.pinned_free(src)
     ctx.close()
     # ZIP32 image with the chunk index in the LFH extra field (what otezip.c:finalize_archive writes)
-    parts, cd, tabrows = [], [], []
+    parts, tabrows = [], []
     o = 0
     out_ofs = 0
     for i in range(n):
@@ -205,9 +274,7 @@ def workload_c3w(rank: int, n_entries: int | None, alloc):
     tab = expand_chunk_index(img, np.array(tabrows, dtype=ENTRY_DTYPE))
     un = int(sum(sizes))
     return dict(image=img, table=tab, out_bytes=out_ofs, uncomp_bytes=un, algo_bytes=un + int(total), opts=default_opts(),
-                desc="DEFLATE inflate + CRC-32, %d mixed entries 4 KiB-16 MiB, archive written by this library's GPU compressor "
-                     "(chunk-indexed, ratio %.2f), %d rows incl. chunk rows" % (n, un / total, len(tab)), dominant="decode",
-                n_entries=n)
+                dominant="decode", n_entries=n, lo=0, hi=n)
 
 
 # ----------------------------------------------------------------------------- clocks
@@ -249,6 +316,10 @@ class ClockSampler(threading.Thread):
     def mark(self):
         self.marks.append(time.perf_counter())
 
+    def stop(self):
+        self.stop_ev.set()
+        self.join(timeout=2)
+
     def summary(self):
         if not self.ok or not self.samples:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "note": "NVML unavailable"}
@@ -289,76 +360,111 @@ class Dist:
             if self.dev.type == "cuda":
                 self.torch.cuda.synchronize()
 
-    def max(self, v: float) -> float:
+    def _red(self, v: float, op) -> float:
         if self.world == 1:
             return v
         t = self.torch.tensor([v], dtype=self.torch.float64, device=self.dev)
-        self.dist.all_reduce(t, op=self.dist.ReduceOp.MAX)
+        self.dist.all_reduce(t, op=op)
         return float(t.item())
 
+    def max(self, v: float) -> float:
+        return self._red(v, self.dist.ReduceOp.MAX) if self.world > 1 else v
+
     def sum(self, v: float) -> float:
-        if self.world == 1:
-            return v
-        t = self.torch.tensor([v], dtype=self.torch.float64, device=self.dev)
-        self.dist.all_reduce(t, op=self.dist.ReduceOp.SUM)
-        return float(t.item())
+        return self._red(v, self.dist.ReduceOp.SUM) if self.world > 1 else v
 
     def close(self):
         if self.world > 1:
             self.dist.destroy_process_group()
 
 
-# ----------------------------------------------------------------------------- reference arm (CPU)
-def reference_sample_archive(wl_name: str, tmpdir: str):
-    """A bounded sample of the workload as one ZIP32 file on disk (the reference reads FILE*)."""
-    from otezip_b200 import synth
-    if wl_name in ("c2", "c2x"):
-        ms = synth.config_c2(64, 1 << 20, seed=2)
-        what = "64 x 1 MiB STORE entries per thread per pass"
-    elif wl_name in ("c1", "c3w"):
-        ms = synth.config_c1(8, 65536)
-        what = "8 x 64 KiB DEFLATE entries per thread per pass"
-    elif wl_name == "c3":
-        ms = synth.config_c3(8, seed=3, lo=12, hi=18)
-        what = "8 mixed DEFLATE entries (4-256 KiB) per thread per pass"
-    else:
-        ms = synth.config_c4(32, 262144)
-        what = "32 x 256 KiB method-93 entries per thread per pass"
-    path = os.path.join(tmpdir, "otz_ref_sample_%s_%d.zip" % (wl_name, os.getpid()))
-    with open(path, "wb") as f:
-        f.write(synth.build_zip(ms))
-    return path, sum(m.uncomp_size for m in ms), what
+# ----------------------------------------------------------------------------- the reference on the host cores
+def numa_cpus_of_gpu(pci_bus_id: str):
+    """CPUs of the NUMA node the GPU hangs off (sysfs), or None."""
+    try:
+        node = int(open("/sys/bus/pci/devices/%s/numa_node" % pci_bus_id.lower()).read())
+        if node < 0:
+            return None
+        cpus = set()
+        for part in open("/sys/devices/system/node/node%d/cpulist" % node).read().strip().split(","):
+            a, _, b = part.partition("-")
+            cpus.update(range(int(a), int(b or a) + 1))
+        return cpus
+    except Exception:
+        return None
 
 
-def reference_pass(ref, path: str, threads: int) -> float:
-    """All threads run zip_open -> zip_fopen_index(i) -> zip_fclose over the sample; returns seconds."""
-    def one(_):
-        err, res = ref.extract_file(path, verify_crc=1, keep_data=False)
-        assert err == 0 and all(r is not None for r in res)
+def reference_sample(wl_name: str, n_entries: int | None, tmpdir: str):
+    """The CPU legs' input: every stride-th entry of the workload's own entry list (same sizes, same text, same codec)
+    as ZIP32 file(s) on disk (the reference reads FILE*).  -> (paths, per-file entry sizes, bytes, description)"""
+    n = n_entries or DEFAULT_ENTRIES[wl_name]
+    name = "c4" if wl_name == "c4z" else ("c3" if wl_name in ("c3w", "c5") else wl_name)   # the reference rejects real Zstandard frames (F3)
+    stride = REF_STRIDE[wl_name]
+    idx = list(range(0, n, stride))
+    bufs = []
+    wl = workload(name, 0, 1, n, lambda nbytes: bufs.append(np.zeros(nbytes, dtype=np.uint8)) or bufs[-1], indices=idx)
+    img, tab = wl["image"], wl["table"]
+    # build_archive_set lays ZIP32 archives back to back: one file per archive
+    paths, sizes = [], []
+    per = 1250 if name in ("c2", "c2x") else 15000 if name == "c4" else 60000
+    for a in range(0, len(idx), per):
+        t = tab[a:a + per]
+        lo = int(t["lfh_ofs"][0])
+        hi = int(tab["lfh_ofs"][a + per]) if a + per < len(idx) else len(img)
+        p = os.path.join(tmpdir, "otz_ref_sample_%s_%d_%d.zip" % (wl_name, os.getpid(), a))
+        blob = img[lo:hi].tobytes()
+        with open(p, "wb") as f:
+            f.write(blob[:blob.rfind(b"PK\x05\x06") + 22])   # (without the alignment padding behind the EOCD record)
+        paths.append(p)
+        sizes.append(t["uncomp_size"].astype(np.int64))
+    what = "every %d%s entry of the workload's entry list (%d entries, %.3f GB)" % (
+        stride, "th" if stride != 1 else "st", len(idx), wl["uncomp_bytes"] / GB)
+    if wl_name == "c4z":
+        what += "; reference-container payloads — the reference rejects real Zstandard frames (SURVEY F3)"
+    if wl_name == "c5":
+        what += "; the reference's DEFLATE writer is broken (SURVEY F2), so the CPU leg is its READ path over the same text"
+    return paths, sizes, wl["uncomp_bytes"], what
+
+
+def reference_pass(ref, paths, sizes, threads: int) -> float:
+    """zip_open -> zip_fopen_index(i) -> zip_fclose (otezip_verify_crc = 1) over every entry of the sample, the entries
+    dealt to `threads` workers longest first (the reference is single-threaded: one archive handle per worker).
+    Returns seconds."""
+    jobs = sorted(((int(s), f, i) for f, sz in enumerate(sizes) for i, s in enumerate(sz)), reverse=True)
+    buckets = [[] for _ in range(threads)]
+    load = [0] * threads
+    for s, f, i in jobs:   # LPT
+        t = load.index(min(load))
+        buckets[t].append((f, i))
+        load[t] += s + 4096
+
+    def one(b):
+        byfile = {}
+        for f, i in b:
+            byfile.setdefault(f, []).append(i)
+        for f, ii in byfile.items():
+            err, res = ref.extract_indices(paths[f], ii, verify_crc=1)
+            assert err == 0 and all(r is not None for r in res)
     t0 = time.perf_counter()
     with cf.ThreadPoolExecutor(threads) as ex:
-        list(ex.map(one, range(threads)))
+        list(ex.map(one, [b for b in buckets if b]))
     return time.perf_counter() - t0
 
 
-def cpu_baseline(wl_name: str, budget_s: float = 12.0):
+def cpu_baseline(wl_name: str, n_entries: int | None):
     from oracle import RefLib
     ref = RefLib()
-    cores = os.cpu_count() or 1
     tmp = "/dev/shm" if os.path.isdir("/dev/shm") else "/tmp"
-    path, nbytes, what = reference_sample_archive(wl_name, tmp)
+    paths, sizes, nbytes, what = reference_sample(wl_name, n_entries, tmp)
     try:
-        t = reference_pass(ref, path, cores)          # also warms the page cache
-        passes = max(1, min(50, int(budget_s / max(t, 1e-3))))
-        t0 = time.perf_counter()
-        for _ in range(passes):
-            reference_pass(ref, path, cores)
-        dt = time.perf_counter() - t0
+        reference_pass(ref, paths, sizes, NCPU) if nbytes < 300e6 else None   # warm the page cache for small samples
+        dt = reference_pass(ref, paths, sizes, NCPU)
     finally:
-        os.unlink(path)
-    return {"value": cores * passes * nbytes / dt / GB, "unit": "GB/s", "cores": cores, "kind": "reference",
-            "sample": "%s, %d threads x %d passes (compiled reference oracle/_ref, zip_open/zip_fopen_index/zip_fclose, "
-                      "otezip_verify_crc=1)" % (what, cores, passes)}
+        for p in paths:
+            os.unlink(p)
+    return {"value": nbytes / dt / GB, "unit": "GB/s", "cores": NCPU, "kind": "reference",
+            "sample": "%s, one pass on %d threads (compiled reference oracle/_ref: zip_open / zip_fopen_index / zip_fclose, "
+                      "otezip_verify_crc=1)" % (what, NCPU)}
 
 
 def run_reference(args, dist: Dist):
@@ -366,98 +472,126 @@ def run_reference(args, dist: Dist):
         return
     from oracle import RefLib
     ref = RefLib()
-    cores = os.cpu_count() or 1
     tmp = "/dev/shm" if os.path.isdir("/dev/shm") else "/tmp"
-    path, nbytes, what = reference_sample_archive(args.workload, tmp)
+    paths, sizes, nbytes, what = reference_sample(args.workload, args.entries, tmp)
     try:
         for _ in range(args.warmup):
-            reference_pass(ref, path, cores)
+            reference_pass(ref, paths, sizes, NCPU)
         t0 = time.perf_counter()
         for _ in range(args.steps):
-            reference_pass(ref, path, cores)
+            reference_pass(ref, paths, sizes, NCPU)
         dt = time.perf_counter() - t0
     finally:
-        os.unlink(path)
-    v = cores * args.steps * nbytes / dt / GB
+        for p in paths:
+            os.unlink(p)
+    v = args.steps * nbytes / dt / GB
+    n = args.entries or DEFAULT_ENTRIES[args.workload]
     print(json.dumps({
-        "impl": "reference", "metric": "extract GB/s (uncompressed output, device-timed)",   # the same metric name as the GPU arm
-        "timing": "host wall clock: the reference's CPU path (compiled from its own sources) on all host cores",
+        "impl": "reference", "metric": metric_name(args.workload),
+        "timing": "host wall clock: the reference's own CPU implementation (compiled from its sources, oracle/_ref) on all host cores",
         "value": v, "unit": "GB/s", "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
-        "ms_per_step": dt / args.steps * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-        "dtype": "u8", "data": "synthetic", "config": {"workload": WORKLOADS[args.workload]},
-        "cpu_baseline": {"value": v, "unit": "GB/s", "cores": cores, "kind": "reference",
-                         "sample": "each step: " + what + ", %d threads" % cores},
+        "ms_per_step": dt / args.steps * 1e3, "higher_is_better": True, "scaling": args.scaling, "vs_baseline": None,
+        "dtype": "u8", "data": "synthetic", "config": wl_config(args.workload, n, max(1, args.gpus), args.scaling),
+        "cpu_baseline": {"value": v, "unit": "GB/s", "cores": NCPU, "kind": "reference",
+                         "sample": "each step: " + what + ", %d threads" % NCPU},
         "e2e": {"value": v, "unit": "GB/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0}))
 
 
-def run_c5(args, dist: "Dist"):
+# ----------------------------------------------------------------------------- GPU arm: the write path (configs[4])
+def run_c5(ctx, dist: "Dist", n_entries, steps, warmup, e2e_steps, sampler=None):
     """configs[4]: archive creation — batched DEFLATE compress + CRC-32 of a synthetic corpus (default 16,384 x 256 KiB
-    JSON-log = 4 GiB), device-timed; every stream verified (zlib on all entries, the compiled reference on a sample)."""
+    JSON-log = 4 GiB), device-timed; every stream verified through zlib and the compiled reference."""
     import ctypes as C
-    from otezip_b200 import Ctx, synth
-    ctx = Ctx(dist.local)
-    n = args.entries or 16384
+    from otezip_b200 import synth
+    n = n_entries or DEFAULT_ENTRIES["c5"]
     size = 262144
-    pool = synth.TextPool(64 << 20, seed=5 + 7919 * dist.rank)
-    stride = size
-    img = ctx.pinned(n * stride)
+    lo, hi = (0, n) if dist.world == 1 else shard_of("c5", [size] * n, dist.world, dist.rank)
+    m = hi - lo
+    pool = synth.TextPool(64 << 20, seed=5)
+    offs = pool.offsets([size] * n)
+    img = ctx.pinned(max(m, 1) * size)
     srcs = []
-    for i in range(n):
-        d = pool.take(size)
-        img[i * stride:(i + 1) * stride] = np.frombuffer(d, dtype=np.uint8)
+    for k, i in enumerate(range(lo, hi)):
+        d = pool.at(offs[i], size)
+        img[k * size:(k + 1) * size] = np.frombuffer(d, dtype=np.uint8)
         srcs.append(d)
-    in_ofs = np.arange(n, dtype=np.uint64) * stride
-    in_len = np.full(n, size, dtype=np.uint32)
-    meth = np.full(n, 8, dtype=np.uint16)
+    in_ofs = np.arange(m, dtype=np.uint64) * size
+    in_len = np.full(m, size, dtype=np.uint32)
+    meth = np.full(m, 8, dtype=np.uint16)
     d_in = ctx.dev_alloc(img.nbytes)
     ctx.h2d(d_in, img)
     job = ctx.deflate_plan(in_ofs, in_len, meth)
     ctx.sync()
-    sampler = ClockSampler(ctx.pci_bus_id())
-    sampler.start()
-    for _ in range(args.warmup):
+    for _ in range(warmup):
         ctx.deflate_run(job, d_in, img.nbytes)
     ctx.sync()
     dist.barrier()
     ctx.sync()
     l0 = ctx.launches()
-    sampler.mark()
+    if sampler:
+        sampler.mark()
     ctx.timer_start()
-    for _ in range(args.steps):
+    for _ in range(steps):
         ctx.deflate_run(job, d_in, img.nbytes)
     ms = ctx.timer_stop()
-    sampler.mark()
+    if sampler:
+        sampler.mark()
     dist.barrier()
     launches = ctx.launches() - l0
-    ofs, sz, crc, m, total = ctx.deflate_results(job, n)
+    ofs, sz, crc, mo, total = ctx.deflate_results(job, m)
     out = ctx.deflate_fetch(job, total)
-    # verification: every stream through zlib, CRCs against zlib.crc32, a sample through the compiled reference
+
+    # verification: every stream through zlib, CRCs against zlib.crc32, every stream through the compiled reference
     def chk(i):
         p = bytes(out[int(ofs[i]):int(ofs[i]) + int(sz[i])])
-        ok = (zlib.decompress(p, -15) if m[i] == 8 else p) == srcs[i] and int(crc[i]) == (zlib.crc32(srcs[i]) & 0xFFFFFFFF)
-        return ok
-    with cf.ThreadPoolExecutor(os.cpu_count() or 4) as ex:
-        n_ok = sum(ex.map(chk, range(n)))
-    ref_ok = None
+        return (zlib.decompress(p, -15) if mo[i] == 8 else p) == srcs[i] and int(crc[i]) == (zlib.crc32(srcs[i]) & 0xFFFFFFFF)
+    with cf.ThreadPoolExecutor(NCPU) as ex:
+        n_ok = sum(ex.map(chk, range(m)))
+    ref_ok, ref_n = None, 0
     try:
         from oracle import RefLib
-        k = min(n, 32)
-        ms_ = [synth.Member("f%d" % i, int(m[i]), bytes(out[int(ofs[i]):int(ofs[i]) + int(sz[i])]), size, int(crc[i])) for i in range(k)]
-        err, got = RefLib().extract_bytes(synth.build_zip(ms_), verify_crc=1)
-        ref_ok = err == 0 and got == srcs[:k]
+        ref = RefLib()
+        # ZIP32 archives of <= 3 GiB of payload each, read back by the reference on all cores
+        tmp = "/dev/shm" if os.path.isdir("/dev/shm") else "/tmp"
+        groups, cur, cur_b = [], [], 0
+        for i in range(m):
+            if cur and cur_b + int(sz[i]) > (3 << 30):
+                groups.append(cur)
+                cur, cur_b = [], 0
+            cur.append(i)
+            cur_b += int(sz[i])
+        if cur:
+            groups.append(cur)
+        ref_ok = True
+        for g in groups:
+            ms_ = [synth.Member("f%d" % i, int(mo[i]), bytes(out[int(ofs[i]):int(ofs[i]) + int(sz[i])]), size, int(crc[i])) for i in g]
+            path = os.path.join(tmp, "otz_c5_%d.zip" % os.getpid())
+            with open(path, "wb") as f:
+                f.write(synth.build_zip(ms_))
+            try:
+                parts = [list(range(t, len(g), NCPU)) for t in range(NCPU)]
+
+                def rd(ii):
+                    err, got = ref.extract_indices(path, ii, verify_crc=1, keep_data=True)
+                    return err == 0 and all(got[k] == srcs[g[i]] for k, i in enumerate(ii))
+                with cf.ThreadPoolExecutor(NCPU) as ex:
+                    ref_ok = ref_ok and all(ex.map(rd, [p for p in parts if p]))
+            finally:
+                os.unlink(path)
+            ref_n += len(g)
     except Exception as e:  # pragma: no cover
         ref_ok = "unavailable: %r" % e
-    if n_ok != n or ref_ok is False:
-        raise SystemExit("bench c5: %d/%d streams verified, reference sample ok=%s" % (n_ok, n, ref_ok))
+    if n_ok != m or ref_ok is False:
+        raise SystemExit("bench c5: %d/%d streams verified by zlib, compiled reference ok=%s" % (n_ok, m, ref_ok))
     # e2e: host buffers through otz_deflate_host
-    e2e_steps = args.e2e_steps or 3
-    o_ofs = np.zeros(n, dtype=np.uint64); o_sz = np.zeros(n, dtype=np.uint32); o_crc = np.zeros(n, dtype=np.uint32)
-    o_m = np.zeros(n, dtype=np.uint16); tot = C.c_uint64()
+    o_ofs = np.zeros(m, dtype=np.uint64); o_sz = np.zeros(m, dtype=np.uint32); o_crc = np.zeros(m, dtype=np.uint32)
+    o_m = np.zeros(m, dtype=np.uint16); tot = C.c_uint64()
     out_host = ctx.pinned(img.nbytes)
     vp = lambda a: a.ctypes.data_as(C.c_void_p)
+
     def e2e_step():
-        ctx.lib.check(ctx.L.otz_deflate_host(ctx.h, vp(img), img.nbytes, vp(in_ofs), vp(in_len), vp(meth), n, vp(out_host), out_host.nbytes,
+        ctx.lib.check(ctx.L.otz_deflate_host(ctx.h, vp(img), img.nbytes, vp(in_ofs), vp(in_len), vp(meth), m, vp(out_host), out_host.nbytes,
                                              vp(o_ofs), vp(o_sz), vp(o_crc), vp(o_m), C.byref(tot)), "otz_deflate_host")
     e2e_step()
     dist.barrier(); ctx.sync()
@@ -466,83 +600,44 @@ def run_c5(args, dist: "Dist"):
         e2e_step()
     ctx.sync()
     e2e_s = time.perf_counter() - t0
-    sampler.stop_ev.set(); sampler.join(timeout=2)
     ms_max = dist.max(ms)
-    tot_in = dist.sum(float(n * size))
+    tot_in = dist.sum(float(m * size))
+    tot_out = dist.sum(float(total))
     e2e_max = dist.max(e2e_s)
-    if dist.rank == 0:
-        peaks = {}
-        try:
-            peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
-        except Exception:
-            pass
-        peak = float(peaks.get("hbm_gbs", 6650.0))
-        algo = n * size + total
-        achieved = algo / (ms / args.steps / 1e3) / GB
-        print(json.dumps({
-            "metric": "compress GB/s (uncompressed input, device-timed; CRC-32 + DEFLATE + compaction)",
-            "value": tot_in * args.steps / (ms_max / 1e3) / GB, "unit": "GB/s", "n_gpus": dist.world, "steps": args.steps,
-            "warmup": args.warmup, "ms_per_step": ms_max / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-            "dtype": "u8", "data": "synthetic",
-            "config": {"workload": WORKLOADS["c5"], "entries_per_gpu": n, "uncomp_bytes_per_gpu": n * size, "compressed_bytes_per_gpu": total,
-                       "ratio": n * size / total, "reference_ratio_same_level": 4.36, "zlib6_ratio": 9.0,
-                       "verified": {"zlib_streams_ok": n_ok, "of": n, "compiled_reference_sample_ok": ref_ok},
-                       "cache": "inputs larger than L2 (no flush needed)"},
-            "roofline": {"bound": "hbm", "kernel": "k_deflate_chunks (+crc, scan, gather)", "achieved": achieved, "peak": peak, "unit": "GB/s",
-                         "frac": achieved / peak, "traffic": None, "peak_source": "measured (MEASURED_PEAKS.json hbm_gbs)" if peaks else "fallback"},
-            "e2e": {"value": tot_in * e2e_steps / e2e_max / GB, "unit": "GB/s", "h2d_bytes_per_step": int(img.nbytes),
-                    "d2h_bytes_per_step": int(total + 18 * n), "steps": e2e_steps,
-                    "timing": "host wall clock around otz_deflate_host (C-ABI, pinned host buffers), device-synchronised"},
-            "gpu_launches": int(launches), "clocks": sampler.summary()}))
     ctx.deflate_destroy(job)
-    dist.close()
+    ctx.dev_free(d_in)
+    ctx.pinned_free(img)
+    ctx.pinned_free(out_host)
+    peak, peak_src = hbm_peak()
+    algo = m * size + total
+    achieved = algo / (ms / steps / 1e3) / GB
+    return {
+        "metric": metric_name("c5"), "value": tot_in * steps / (ms_max / 1e3) / GB, "unit": "GB/s", "ms_per_step": ms_max / steps,
+        "run": {"entries_this_rank": m, "compressed_bytes": int(tot_out), "ratio": tot_in / max(tot_out, 1.0), "reference_ratio_same_level": 4.36,
+                "zlib6_ratio": 9.0, "verified": {"zlib_streams_ok": n_ok, "compiled_reference_streams_ok": ref_n if ref_ok is True else ref_ok, "of": m}},
+        "roofline": {"bound": "hbm", "kernel": "k_deflate_chunks (+crc, scan, gather)", "achieved": achieved, "peak": peak, "unit": "GB/s",
+                     "frac": achieved / peak, "traffic": None, "peak_source": peak_src, "algorithmic_bytes": int(algo)},
+        "e2e": {"value": tot_in * e2e_steps / e2e_max / GB, "unit": "GB/s", "h2d_bytes_per_step": int(img.nbytes),
+                "d2h_bytes_per_step": int(total + 18 * m), "steps": e2e_steps,
+                "timing": "host wall clock around otz_deflate_host (C-ABI, pinned host buffers), device-synchronised"},
+        "gpu_launches": int(launches)}
 
 
-DECODE_KERNELS = {
-    "c1": "k_inflate_tok + k_inflate_lz (+ k_inflate for declined / huge streams)",
-    "c3": "k_inflate_tok + k_inflate_lz; entries >= 1 MiB: k_block_search + k_inflate_tok<segments> + k_inflate_lz<symbols> + k_seg_window + k_seg_translate",
-    "c3w": "k_inflate_tok + k_inflate_lz (+ k_inflate for declined / huge streams)",
-    "c4": "k_zstdref", "c4z": "k_zstd", "c2": "k_store_copy", "c2x": "k_store_copy",
-}
-
-WORKLOADS = {
-    "c2": "configs[1]: STORE + CRC-32 verify only, 10,000 entries of 1 MiB random bytes",
-    "c1": "configs[0]: 1,000-entry DEFLATE archive, 64 KiB text-like entries, CRC-32 check",
-    "c3": "configs[2]: DEFLATE inflate of mixed-size entries (4 KiB-16 MiB) JSON-log text",
-    "c4": "configs[3]: method 93 decode of 256 KiB entries (reference container)",
-    "c5": "configs[4]: archive creation, batched DEFLATE compress + CRC-32, 4 GiB synthetic corpus",
-    "c3w": "configs[2] shape, archive written by this library (chunk-indexed DEFLATE entries)",
-    "c2x": "configs[1] shape, STORE entries extracted (copied to the arena) and CRC-checked",
-    "c4z": "configs[3] shape with real Zstandard (RFC 8878) frames from libzstd level 3",
-}
+def hbm_peak():
+    try:
+        peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+        if "hbm_gbs" in peaks:
+            return float(peaks["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+    except Exception:
+        pass
+    return 6650.0, "fallback 6.65 TB/s (B200_PROFILING.md)"
 
 
-# ----------------------------------------------------------------------------- main arm
-def main():
-    ap = argparse.ArgumentParser()
-    ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=50)
-    ap.add_argument("--warmup", type=int, default=5)
-    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
-    ap.add_argument("--workload", default="c2", choices=list(WORKLOADS))
-    ap.add_argument("--entries", type=int, default=None, help="override the entry count (quick runs)")
-    ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--e2e-steps", type=int, default=None)
-    args = ap.parse_args()
-    args.warmup = max(args.warmup, 3) if args.impl == "b200" else args.warmup
-    dist = Dist(args.gpus)
-    if args.impl == "reference":
-        run_reference(args, dist)
-        dist.close()
-        return
-
-    if args.workload == "c5":
-        run_c5(args, dist)
-        return
-    from otezip_b200 import Ctx
-    from otezip_b200 import native
-    ctx = Ctx(dist.local)
-    wl = workload(args.workload, dist.rank, args.entries, ctx.pinned)
+# ----------------------------------------------------------------------------- GPU arm: the read path
+def run_extract(ctx, dist: Dist, name: str, n_entries, steps, warmup, e2e_steps, scaling="strong", sampler=None):
+    """Device-timed batched extract of one workload + the end-to-end host-buffer call.  -> dict (parts of the JSON line)."""
+    import ctypes as C
+    wl = workload(name, dist.rank, dist.world, n_entries, ctx.pinned, scaling)
     img, tab = wl["image"], wl["table"]
     n = len(tab)
     d_img = ctx.dev_alloc(img.nbytes)
@@ -554,45 +649,44 @@ def main():
     def step():
         ctx.run(plan, d_img, img.nbytes, d_out, wl["out_bytes"])
 
-    sampler = ClockSampler(ctx.pci_bus_id())
-    sampler.start()
-    for _ in range(args.warmup):
+    for _ in range(warmup):
         step()
     ctx.sync()
     crc, st = ctx.results(plan, n)
     inflate_fallbacks = int(ctx.L.otz_inflate_fallbacks(ctx.h))
     real = (tab["flags"] & 2) == 0          # chunk rows carry no CRC of their own
-    ok_mask = 0x200 if args.workload == "c4z" else 0      # real Zstandard frames carry the "reference rejects" flag
+    ok_mask = 0x200 if name == "c4z" else 0      # real Zstandard frames carry the "reference rejects" flag
     bad = int(np.count_nonzero((st & ~ok_mask) != 0))
     if bad or not np.array_equal(crc[real], tab["crc32"][real]):
-        raise SystemExit("bench: %d entries failed on the GPU path (status/CRC) — number would be invalid" % bad)
+        raise SystemExit("bench %s: %d entries failed on the GPU path (status/CRC) — number would be invalid" % (name, bad))
 
     # ---- device-timed region: K steps, inputs resident in HBM
     dist.barrier()
     ctx.sync()
     ctx.profile(1)
     l0 = ctx.launches()
-    sampler.mark()
+    if sampler:
+        sampler.mark()
     ctx.timer_start()
-    for _ in range(args.steps):
+    for _ in range(steps):
         step()
     ms = ctx.timer_stop()
-    sampler.mark()
+    if sampler:
+        sampler.mark()
     dist.barrier()
     launches = ctx.launches() - l0
     prof = ctx.profile_read()
     ctx.profile(0)
     ms_max = dist.max(ms)
     total_uncomp = dist.sum(float(wl["uncomp_bytes"]))
-    value = total_uncomp * args.steps / (ms_max / 1e3) / GB
+    total_algo = dist.sum(float(wl["algo_bytes"]))
+    value = total_uncomp * steps / (ms_max / 1e3) / GB
 
     # ---- end to end through the C-ABI host-buffer call: pinned host image -> H2D -> kernels -> D2H
-    e2e_steps = args.e2e_steps or max(3, min(args.steps, 10))
     out_host = ctx.pinned(wl["out_bytes"]) if wl["out_bytes"] else None
     L = ctx.L
-    import ctypes as C
-    crc_h = np.zeros(n, dtype=np.uint32)
-    st_h = np.zeros(n, dtype=np.int32)
+    crc_h = np.zeros(max(n, 1), dtype=np.uint32)
+    st_h = np.zeros(max(n, 1), dtype=np.int32)
 
     def e2e_step():
         ctx.lib.check(L.otz_extract_host(ctx.h, img.ctypes.data_as(C.c_void_p), img.nbytes, tab.ctypes.data_as(C.c_void_p), n,
@@ -609,59 +703,110 @@ def main():
     ctx.sync()
     e2e_s = time.perf_counter() - t0
     dist.barrier()
-    assert not np.count_nonzero(st_h & ~ok_mask) and np.array_equal(crc_h[real], tab["crc32"][real])
+    assert not np.count_nonzero(st_h[:n] & ~ok_mask) and np.array_equal(crc_h[:n][real], tab["crc32"][real])
     e2e_max = dist.max(e2e_s)
     e2e_value = total_uncomp * e2e_steps / e2e_max / GB
-    sampler.stop_ev.set()
-    sampler.join(timeout=2)
+    h2d = dist.sum(float(img.nbytes + tab.nbytes))
+    d2h = dist.sum(float(wl["out_bytes"] + 8 * n))
 
-    if dist.rank == 0:
-        peaks = {}
-        try:
-            peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
-        except Exception:
-            pass
-        peak = float(peaks.get("hbm_gbs", 6650.0))
-        peak_src = "measured (MEASURED_PEAKS.json hbm_gbs)" if "hbm_gbs" in peaks else "fallback 6.65 TB/s (B200_PROFILING.md)"
-        idx = {"resolve": 0, "decode": 1, "crc": 2, "finalize": 3}
-        dom = wl["dominant"]
-        k_ms = float(np.mean([p[idx[dom]] for p in prof])) if prof else float("nan")
-        shares = {k: float(np.mean([p[i] for p in prof])) for k, i in idx.items()} if prof else {}
-        achieved = wl["algo_bytes"] / (k_ms / 1e3) / GB
-        # DRAM bytes of one launch of the dominant kernel from the committed `ncu --set full` capture of this very
-        # configuration (tools/profile_final.sh writes the file); null when the entry count differs
-        traffic = None
-        try:
-            tr = json.load(open(os.path.join(ROOT, "profiles", "roofline_traffic.json"))).get(args.workload)
-            if tr and int(tr.get("entries", -1)) == int(wl.get("n_entries", n)):
-                traffic = tr["traffic"]
-        except Exception:
-            pass
-        line = {
-            "metric": "extract GB/s (uncompressed output, device-timed)", "value": value, "unit": "GB/s",
-            "n_gpus": dist.world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_max / args.steps,
-            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u8", "data": "synthetic",
-            "config": {"workload": WORKLOADS[args.workload], "detail": wl["desc"], "entries_per_gpu": int(wl.get("n_entries", n)), "table_rows_per_gpu": n,
-                       "uncomp_bytes_per_gpu": wl["uncomp_bytes"], "algorithmic_bytes_per_gpu": wl["algo_bytes"],
-                       "cache": "inputs larger than L2 (no flush needed)" if wl["algo_bytes"] > 256e6 else
-                                "inputs smaller than L2: steady-state L2-resident", "parallelism": "entries sharded by index, no collective",
-                       "inflate_fallbacks": inflate_fallbacks},
-            "roofline": {"bound": "hbm", "kernel": {"crc": "k_crc_chunks", "decode": DECODE_KERNELS.get(args.workload, "decode")}[dom],
-                         "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": traffic,
-                         "peak_source": peak_src, "kernel_ms": k_ms, "phase_ms": shares},
-            "e2e": {"value": e2e_value, "unit": "GB/s", "h2d_bytes_per_step": int(img.nbytes + tab.nbytes),
-                    "d2h_bytes_per_step": int(wl["out_bytes"] + 8 * n), "steps": e2e_steps,
-                    "timing": "host wall clock around otz_extract_host (C-ABI, pinned host buffers), device-synchronised, max over ranks"},
-            "gpu_launches": int(launches),
-            "clocks": sampler.summary(),
-        }
-        if dist.world == 1 and not args.no_cpu_baseline:
+    peak, peak_src = hbm_peak()
+    idx = {"resolve": 0, "decode": 1, "crc": 2, "finalize": 3}
+    dom = wl["dominant"]
+    k_ms = float(np.mean([p[idx[dom]] for p in prof])) if prof else float("nan")
+    shares = {k: float(np.mean([p[i] for p in prof])) for k, i in idx.items()} if prof else {}
+    achieved = wl["algo_bytes"] / (k_ms / 1e3) / GB
+    # DRAM bytes of one launch of the dominant kernel from the committed `ncu --set full` capture of this very
+    # configuration (tools/profile_*.sh write the file); null when the entry count differs
+    traffic, traffic_src = None, None
+    try:
+        tr = json.load(open(os.path.join(ROOT, "profiles", "roofline_traffic.json"))).get(name)
+        if tr and int(tr.get("entries", -1)) == int(wl["n_entries"]) and dist.world == 1:
+            traffic, traffic_src = tr["traffic"], "committed ncu --set full capture (profiles/roofline_traffic.json), not measured in this run"
+    except Exception:
+        pass
+    res = {
+        "metric": metric_name(name), "value": value, "unit": "GB/s", "ms_per_step": ms_max / steps,
+        "run": {"entries_this_rank": int(wl["hi"] - wl["lo"]), "table_rows_this_rank": n, "uncomp_bytes_this_rank": wl["uncomp_bytes"],
+                "algorithmic_bytes_this_rank": wl["algo_bytes"], "algorithmic_bytes_all_ranks": total_algo, "inflate_fallbacks": inflate_fallbacks},
+        "roofline": {"bound": "hbm", "kernel": {"crc": "k_crc_chunks", "decode": DECODE_KERNELS.get(name, "decode")}[dom],
+                     "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": traffic, "traffic_source": traffic_src,
+                     "peak_source": peak_src, "kernel_ms": k_ms, "phase_ms": shares,
+                     "note": "achieved = algorithmic bytes of this rank (comp + uncomp; configs[1]: uncomp) / event-timed duration of the phase"},
+        "e2e": {"value": e2e_value, "unit": "GB/s", "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h), "steps": e2e_steps,
+                "timing": "host wall clock around otz_extract_host (C-ABI, pinned host buffers; H2D of the archive image and D2H of the "
+                          "extracted bytes inside), device-synchronised, max over ranks"},
+        "gpu_launches": int(launches),
+    }
+    ctx.plan_destroy(plan)
+    ctx.dev_free(d_img)
+    if d_out is not None:
+        ctx.dev_free(d_out)
+    ctx.pinned_free(img)
+    if out_host is not None:
+        ctx.pinned_free(out_host)
+    return res
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--workload", default="c3", choices=list(WORKLOADS))
+    ap.add_argument("--entries", type=int, default=None, help="override the entry count (quick runs)")
+    ap.add_argument("--scaling", default="strong", choices=["strong", "weak"], help="N > 1: shard ONE archive (default) or one archive per rank")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-secondary", action="store_true", help="skip the other BASELINE configurations (N = 1 default run only)")
+    ap.add_argument("--e2e-steps", type=int, default=None)
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3) if args.impl == "b200" else args.warmup
+    dist = Dist(args.gpus)
+    if args.impl == "reference":
+        run_reference(args, dist)
+        dist.close()
+        return
+    if args.workload == "c3w":
+        args.scaling = "weak"   # (written by the GPU compressor of every rank: one archive per rank)
+    from otezip_b200 import Ctx
+    ctx = Ctx(dist.local)
+    sampler = ClockSampler(ctx.pci_bus_id())
+    sampler.start()
+    n = args.entries or DEFAULT_ENTRIES[args.workload]
+    e2e_steps = args.e2e_steps or max(3, min(args.steps, 5))
+    if args.workload == "c5":
+        res = run_c5(ctx, dist, args.entries, args.steps, args.warmup, e2e_steps, sampler)
+    else:
+        res = run_extract(ctx, dist, args.workload, args.entries, args.steps, args.warmup, e2e_steps, args.scaling, sampler)
+    clocks = sampler.summary()
+    line = {
+        "metric": res["metric"], "value": res["value"], "unit": "GB/s", "n_gpus": dist.world, "steps": args.steps, "warmup": args.warmup,
+        "ms_per_step": res["ms_per_step"], "higher_is_better": True, "scaling": args.scaling, "vs_baseline": None,
+        "dtype": "u8", "data": "synthetic", "config": wl_config(args.workload, n, dist.world, args.scaling),
+        "run": res["run"], "roofline": res["roofline"], "e2e": res["e2e"], "gpu_launches": res["gpu_launches"], "clocks": clocks,
+    }
+    if dist.world == 1 and dist.rank == 0:
+        if not args.no_cpu_baseline:
             try:
-                line["cpu_baseline"] = cpu_baseline(args.workload)
+                line["cpu_baseline"] = cpu_baseline(args.workload, args.entries)
             except Exception as e:
                 line["cpu_baseline"] = {"value": None, "unit": "GB/s", "cores": 0, "kind": "reference", "sample": "unavailable: %r" % e}
+        if not args.no_secondary and args.workload == "c3" and args.entries is None:
+            # the other BASELINE configurations, same process, fewer steps: nothing the headline change would hide
+            sec = {}
+            for w in ("c1", "c2", "c4", "c4z", "c5"):
+                try:
+                    r = (run_c5(ctx, dist, None, 3, 3, 1) if w == "c5" else run_extract(ctx, dist, w, None, 5, 3, 2))
+                    sec[w] = {"workload": WORKLOADS[w], "metric": r["metric"], "value": r["value"], "unit": "GB/s", "ms_per_step": r["ms_per_step"],
+                              "roofline_frac": r["roofline"]["frac"], "roofline_kernel": r["roofline"]["kernel"], "e2e": r["e2e"]["value"],
+                              "run": r["run"]}
+                except BaseException as e:  # a failing secondary must not take the headline with it
+                    sec[w] = {"workload": WORKLOADS[w], "error": repr(e)}
+            line["secondary"] = sec
+    sampler.stop()
+    if dist.rank == 0:
         print(json.dumps(line))
-    ctx.plan_destroy(plan)
+    ctx.close()
     dist.close()
 
 

@@ -189,6 +189,13 @@ int otz_extract_produced(otz_ctx *ctx, otz_plan *plan, uint32_t *produced);
  * implement dec:547-831 with identical results; this is a performance counter. */
 uint32_t otz_inflate_fallbacks(otz_ctx *ctx);
 
+/* ---- multi-GPU sharding (the reference has no counterpart: entries are independent,
+ * otezip.c:399-477) ----
+ * Split entries [0, n) into `parts` contiguous index ranges balanced by comp_size + uncomp_size (what a device
+ * reads and writes): first[g] .. first[g + 1] is the range of part g, first[parts] = n.  Contiguous ranges keep
+ * each part a contiguous byte range of the archive.  Pure host code (no device needed). */
+int otz_partition(const otz_entry *entries, uint32_t n, uint32_t parts, uint32_t *first);
+
 /* Policy helper shared by the host library and the tests: does a status word
  * mean "zip_fopen_index returns the buffer" under the given globals?
  * ref_compat != 0 reproduces the reference's end-of-block rule (F1). */

@@ -167,6 +167,27 @@ class RefLib:
         self.lib.zip_close(za)
         return 0, res
 
+    def extract_indices(self, path: str, indices, verify_crc: int = 1, keep_data: bool = False):
+        """zip_open -> zip_fopen_index(i) -> zip_fclose for the given entry numbers.  -> (err, [bytes | size | None])"""
+        self.verify_crc.value = verify_crc
+        err = C.c_int(0)
+        za = self.lib.zip_open(path.encode(), 0, C.byref(err))
+        if not za:
+            return err.value, None
+        res = []
+        for i in indices:
+            zf = self.lib.zip_fopen_index(za, i, 0)
+            if not zf:
+                res.append(None)
+                continue
+            if keep_data:
+                res.append(C.string_at(zf.contents.data, zf.contents.size) if zf.contents.size else b"")
+            else:
+                res.append(zf.contents.size)
+            self.lib.zip_fclose(zf)
+        self.lib.zip_close(za)
+        return 0, res
+
     def extract_bytes(self, img: bytes, verify_crc: int = 1):
         p = self.open_bytes(img)
         try:

@@ -1563,10 +1563,7 @@ struct I2Ring {
 template <int W, typename T = uint8_t>
 struct __align__(16) I2LzSmem {
 	T ring[W];
-	T stage[2][I2Elem<T>::STAGE];
-	uint2 far_l[2][32];    // {destination (linear), length | staging vector << 9 (127 = fetch directly)}
-	uint32_t far_s[2][32]; // source of the far match (linear)
-	uint2 near_l[2][32];   // {ring index of the destination | length << 16, ring index of the source | distance << 16}
+	T stage[2][I2Elem<T>::STAGE];   // (directly behind the ring: a match source is ONE index from the ring's base, see I2Batch::mb)
 };
 
 // write ring[a, b) (linear positions) to HBM; whole warp, ring contents visible (caller synced)
@@ -1610,15 +1607,24 @@ struct I2Batch {
 	uint32_t ntake;     // records in the batch (0 = none left)
 	uint32_t tot_l;     // literals it consumes
 	uint32_t q_end;     // linear output position behind it
-	uint32_t n_far, n_near;
 	uint32_t lr;        // this lane's record: literal run,
 	uint32_t my_lit;    //   its first literal,
 	uint32_t my_out;    //   its linear output position
 	uint32_t lit4;      //   and its first four literal bytes
+	// the match of this lane's record, as the executor wants it (it walks the records in stream order and fetches
+	// these two words with one shuffle each):
+	uint32_t ma;        //   ring index of the destination | length << 16 | I2_MF_* << 28   (length 0: no match)
+	uint32_t mb;        //   source, as an element index from the ring's base: a ring index (masked when used), or — bit 31 — an
+	                    //   index into the staging buffer behind the ring (a FAR source, fetched while the batch before ran)
+	uint32_t m_src;     //   linear position of the source (far matches that did not fit the staging buffer are fetched directly)
+	uint32_t m_dist;    //   distance (overlapping matches are extended periodically)
 };
+#define I2_MF_LONG 1u       // longer than 32 elements
+#define I2_MF_PERIODIC 2u   // distance < length
+#define I2_MF_DIRECT 4u     // far source not staged: read from HBM
 
-// scan records [b, b + 32) (this lane holds record b + lane in `rec`), write the match descriptors of the batch into
-// list buffer `buf` and start the copies of its far sources into staging buffer `buf`.
+// scan records [b, b + 32) (this lane holds record b + lane in `rec`): positions by warp prefix sums, the match descriptor
+// of every record (kept in its lane), and the copies of the batch's far sources into staging buffer `buf` are started.
 // WIDE: 8-byte records {literal run | (length - 3) << 9, distance} (Zstandard: distances beyond 32 KiB); `rec` is the first
 // word, `wdist` the second.  Otherwise the distance sits in rec[31:17].
 template <int W, bool WIDE, typename T>
@@ -1664,24 +1670,14 @@ __device__ __forceinline__ I2Batch i2_scan_batch(I2LzSmem<W, T> &S, int buf, uin
 	const bool is_match = mine && ml != 0u;
 	const bool is_far = is_match && dist > (uint32_t)W - (B.q_end - mq);
 	const uint32_t far_m = __ballot_sync(0xFFFFFFFFu, is_far);
-	const uint32_t near_m = __ballot_sync(0xFFFFFFFFu, is_match && !is_far);
-	B.n_far = __popc(far_m);
-	B.n_near = __popc(near_m);
-	{
-		// x bit 31: this match and the near match before it are short, plain (distance >= length) and independent
-		// (it does not read what the other writes), so the executor runs the two as one step
-		const uint32_t before = near_m & lt_mask;
-		const int pl = before ? 31 - __clz(before) : 0;
-		const uint32_t pmq = __shfl_sync(0xFFFFFFFFu, mq, pl), pml = __shfl_sync(0xFFFFFFFFu, ml, pl), pdist = __shfl_sync(0xFFFFFFFFu, dist, pl);
-		if (is_match && !is_far) {
-			const uint32_t src = mq - dist;
-			const bool pair = before != 0u && dist >= ml && ml <= 32u && pdist >= pml && pml <= 32u && (src + ml <= pmq || src >= pmq + pml);
-			S.near_l[buf][__popc(before)] = make_uint2((mq & MASK) | (ml << 16) | (pair ? 0x80000000u : 0u), (src & MASK) | (dist << 16));   // near: dist < W <= 16 KiB
-		}
-	}
+	const uint32_t src_lin = mq - dist;
+	uint32_t flags = is_match ? ((ml > 32u ? I2_MF_LONG : 0u) | ((!is_far && dist < ml) ? I2_MF_PERIODIC : 0u)) : 0u;
+	B.mb = src_lin & MASK;
+	B.m_src = src_lin;
+	B.m_dist = dist;
 	if (far_m) {
 		// staging vectors per far match (the source is copied as whole 16-byte vectors)
-		const uint32_t soff = (mq - dist) & (VEC - 1u);
+		const uint32_t soff = src_lin & (VEC - 1u);
 		const uint32_t nch = is_far ? (soff + ml + VEC - 1u) / VEC : 0u;
 		uint32_t incl = nch;
 #pragma unroll
@@ -1692,24 +1688,25 @@ __device__ __forceinline__ I2Batch i2_scan_batch(I2LzSmem<W, T> &S, int buf, uin
 			}
 		}
 		if (is_far) {
-			const uint32_t cst = incl <= STAGE_VECS ? incl - nch : 127u;
-			const uint32_t j = __popc(far_m & lt_mask);
-			S.far_l[buf][j] = make_uint2(mq, ml | (cst << 9));
-			S.far_s[buf][j] = mq - dist;
-			if (cst != 127u) {
+			if (incl <= STAGE_VECS) {
+				const uint32_t cst = incl - nch;
+				B.mb = 0x80000000u | ((uint32_t)W + (uint32_t)buf * I2Elem<T>::STAGE + VEC * cst + soff);
 				// every lane fetches the vectors of its own match (cp.async groups are per thread: the executor waits for
 				// its own group and then syncs the warp)
 				uint32_t sa = (uint32_t)__cvta_generic_to_shared(&S.stage[buf][VEC * cst]);
-				const T *g = gbase + ((mq - dist) & ~(VEC - 1u));
+				const T *g = gbase + (src_lin & ~(VEC - 1u));
 #pragma unroll 1
 				for (uint32_t v = 0; v < nch; v++) {
 					asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(sa), "l"(g) : "memory");
 					sa += 16u;
 					g += VEC;
 				}
+			} else {
+				flags |= I2_MF_DIRECT;
 			}
 		}
 	}
+	B.ma = (mq & MASK) | ((is_match ? ml : 0u) << 16) | (flags << 28);
 	asm volatile("cp.async.commit_group;" ::: "memory");
 	return B;
 }
@@ -1853,71 +1850,31 @@ __global__ void __launch_bounds__(128) k_inflate_lz(uint8_t *__restrict__ out, c
 						rb[(cur.my_out + t) & MASK] = lits[cur.my_lit + t];
 					}
 				}
-				uint2 dn = S.far_l[buf][0];
+				// the matches in stream order: one shuffle pair fetches the record's descriptor, lanes < length copy one element each
+				// (source: ring or staging buffer — one index space), longer / overlapping / unstaged ones take the side exit
 #pragma unroll 1
-				for (uint32_t f = 0; f < cur.n_far; f++) {
-					const uint2 d = dn;
-					dn = S.far_l[buf][(f + 1u) & 31u];   // next descriptor in flight while this match is copied
-					const uint32_t cst = d.y >> 9, len = d.y & 511u, src = S.far_s[buf][f];
-					if (cst != 127u) {
-						const T *sp = &S.stage[buf][VEC * cst + (src & (VEC - 1u))];
+				for (uint32_t r = 0; r < cur.ntake; r++) {
+					const uint32_t a = __shfl_sync(0xFFFFFFFFu, cur.ma, r), bsrc = __shfl_sync(0xFFFFFFFFu, cur.mb, r);
+					const uint32_t len = (a >> 16) & 0x1FFu, dq = a & 0xFFFFu;
+					const uint32_t smask = MASK | (uint32_t)(((int32_t)bsrc >> 31) & 0x7FFFF000);   // staged sources are not wrapped
+					__syncwarp();   // earlier ring stores are visible to the loads below
+					if ((a >> 28) == 0u) {
 						if (lane < len) {
-							rb[(d.x + lane) & MASK] = sp[lane];
+							rb[(dq + lane) & MASK] = rb[(bsrc + lane) & smask];
 						}
-						if (len > 32u) {
+					} else if ((a >> 28) & I2_MF_PERIODIC) {
+						i2_copy_periodic<W, T>(rb, dq, bsrc, __shfl_sync(0xFFFFFFFFu, cur.m_dist, r), len, lane);
+					} else if ((a >> 28) & I2_MF_DIRECT) {
+						const uint32_t src = __shfl_sync(0xFFFFFFFFu, cur.m_src, r);
 #pragma unroll 1
-							for (uint32_t x = lane + 32u; x < len; x += 32) {
-								rb[(d.x + x) & MASK] = sp[x];
-							}
+						for (uint32_t x = lane; x < len; x += 32) {
+							rb[(dq + x) & MASK] = __ldcg(gbase + src + x);
 						}
 					} else {
 #pragma unroll 1
 						for (uint32_t x = lane; x < len; x += 32) {
-							rb[(d.x + x) & MASK] = __ldcg(gbase + src + x);
+							rb[(dq + x) & MASK] = rb[(bsrc + x) & smask];
 						}
-					}
-				}
-				// the rest in stream order, ring -> ring; two independent short matches per step where the scan said so
-				dn = S.near_l[buf][0];
-#pragma unroll 1
-				for (uint32_t f = 0; f < cur.n_near;) {
-					const uint2 d = dn;
-					const uint2 d1 = S.near_l[buf][(f + 1u) & 31u];
-					const uint32_t dqm = d.x & 0xFFFFu, len = (d.x >> 16) & 0x1FFu, sqm = d.y & 0xFFFFu, dd = d.y >> 16;
-					__syncwarp();   // earlier ring stores are visible to the loads below
-					if (f + 1u < cur.n_near && (d1.x >> 31)) {
-						const uint32_t dqm1 = d1.x & 0xFFFFu, len1 = (d1.x >> 16) & 0x1FFu, sqm1 = d1.y & 0xFFFFu;
-						dn = S.near_l[buf][(f + 2u) & 31u];
-						T v0 = 0, v1 = 0;
-						if (lane < len) {
-							v0 = rb[(sqm + lane) & MASK];
-						}
-						if (lane < len1) {
-							v1 = rb[(sqm1 + lane) & MASK];
-						}
-						if (lane < len) {
-							rb[(dqm + lane) & MASK] = v0;
-						}
-						if (lane < len1) {
-							rb[(dqm1 + lane) & MASK] = v1;
-						}
-						f += 2;
-						continue;
-					}
-					dn = d1;
-					f += 1;
-					if (dd >= len) {
-						if (lane < len) {
-							rb[(dqm + lane) & MASK] = rb[(sqm + lane) & MASK];
-						}
-						if (len > 32u) {
-#pragma unroll 1
-							for (uint32_t x = lane + 32u; x < len; x += 32) {
-								rb[(dqm + x) & MASK] = rb[(sqm + x) & MASK];
-							}
-						}
-					} else {
-						i2_copy_periodic<W, T>(rb, dqm, sqm, dd, len, lane);
 					}
 				}
 				b = b2;

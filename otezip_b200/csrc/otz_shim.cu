@@ -1205,6 +1205,40 @@ extern "C" int otz_extract_host_ex(otz_ctx *c, const uint8_t *archive, uint64_t 
 	return rc;
 }
 
+// ---------------------------------------------------------------- multi-GPU sharding (host only)
+extern "C" int otz_partition(const otz_entry *ents, uint32_t n, uint32_t parts, uint32_t *first) {
+	if (!first || !parts || (n && !ents)) {
+		return OTZ_ERR_ARG;
+	}
+	uint64_t total = 0;
+	for (uint32_t i = 0; i < n; i++) {
+		total += (uint64_t)ents[i].comp_size + ents[i].uncomp_size + 64u;   // (+ a constant per entry: empty entries cost a table row)
+	}
+	// boundary g = the first index whose prefix weight reaches g/parts of the total (rounded to the nearer side)
+	uint64_t acc = 0;
+	uint32_t g = 1;
+	first[0] = 0;
+	for (uint32_t i = 0; i < n && g < parts; i++) {
+		const uint64_t w = (uint64_t)ents[i].comp_size + ents[i].uncomp_size + 64u;
+		while (g < parts && (acc + w) * parts >= total * g) {
+			// entry i crosses boundary g: it goes to the side that leaves the smaller imbalance
+			const uint64_t target = total * g / parts;
+			first[g] = (target - acc) * 2 >= w ? i + 1 : i;
+			g++;
+		}
+		acc += w;
+	}
+	for (; g <= parts; g++) {
+		first[g] = n;
+	}
+	for (uint32_t k = 1; k <= parts; k++) {   // monotone
+		if (first[k] < first[k - 1]) {
+			first[k] = first[k - 1];
+		}
+	}
+	return OTZ_SUCCESS;
+}
+
 extern "C" int otz_status_accepts(int32_t st, int verify_crc, int ref_compat) {
 	if (OTZ_ST_CODE(st) != OTZ_ST_OK) {
 		return 0;

@@ -77,6 +77,7 @@ class Lib:
         L.otz_extract_results.argtypes = [vp, vp, vp, vp]
         L.otz_extract_host.argtypes = [vp, vp, u64, vp, C.c_uint32, C.POINTER(OtzOpts), vp, u64, vp, vp]
         L.otz_status_accepts.argtypes = [C.c_int32, C.c_int, C.c_int]
+        L.otz_partition.argtypes = [vp, C.c_uint32, C.c_uint32, vp]
         L.otz_inflate_fallbacks.argtypes = [vp]
         L.otz_inflate_fallbacks.restype = C.c_uint32
         L.otz_deflate_plan.argtypes = [vp, vp, vp, vp, C.c_uint32, C.POINTER(vp)]
@@ -102,6 +103,15 @@ class Lib:
 
 
 EF_PARENT, EF_CHUNK, EF_LAST_CHUNK = 1, 2, 4
+
+
+def partition(table: np.ndarray, parts: int) -> np.ndarray:
+    """otz_partition: contiguous index ranges balanced by comp + uncomp bytes -> first[parts + 1]."""
+    t = np.ascontiguousarray(table)
+    first = np.zeros(parts + 1, dtype=np.uint32)
+    lib = Lib.get()
+    lib.check(lib.L.otz_partition(t.ctypes.data_as(C.c_void_p), len(t), parts, first.ctypes.data_as(C.c_void_p)), "otz_partition")
+    return first
 
 
 def expand_chunk_index(img, tab: np.ndarray) -> np.ndarray:
@@ -229,6 +239,14 @@ class Ctx:
         self.lib.check(self.L.otz_host_alloc(nbytes, C.byref(p)), "otz_host_alloc")
         arr = np.ctypeslib.as_array(C.cast(p, C.POINTER(C.c_uint8)), shape=(max(nbytes, 1),))
         return arr[:nbytes]
+
+    def pinned_free(self, arr: np.ndarray):
+        """Release a buffer obtained from pinned() (the array must not be used afterwards)."""
+        if arr is not None and arr.size:
+            base = arr
+            while isinstance(getattr(base, "base", None), np.ndarray):
+                base = base.base
+            self.L.otz_host_free(C.c_void_p(base.ctypes.data))
 
     def h2d(self, d, h: np.ndarray, nbytes: int | None = None):
         self.lib.check(self.L.otz_h2d(self.h, d, h.ctypes.data_as(C.c_void_p), h.nbytes if nbytes is None else nbytes), "h2d")

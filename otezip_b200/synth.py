@@ -54,6 +54,16 @@ class TextPool:
         o = self.rnd.randrange(0, len(self.buf) - nbytes + 1)
         return self.buf[o:o + nbytes]
 
+    def offsets(self, sizes) -> list[int]:
+        """The offsets take() would use for these sizes, in order, without cutting the slices (a rank that owns a
+        shard of the entry list cuts only its own entries with at())."""
+        return [-1 if n >= len(self.buf) else self.rnd.randrange(0, len(self.buf) - n + 1) for n in sizes]
+
+    def at(self, offset: int, nbytes: int) -> bytes:
+        if offset < 0:
+            return (self.buf * (nbytes // len(self.buf) + 1))[:nbytes]
+        return self.buf[offset:offset + nbytes]
+
 
 def random_bytes(nbytes: int, seed: int) -> bytes:
     return np.random.default_rng(seed).bytes(nbytes)
