@@ -1613,13 +1613,13 @@ struct I2Batch {
 	uint32_t lit4;      //   and its first four literal bytes
 	// the match of this lane's record, as the executor wants it (it walks the records in stream order and fetches
 	// these two words with one shuffle each):
-	uint32_t ma;        //   ring index of the destination | length << 16 | I2_MF_* << 28   (length 0: no match)
-	uint32_t mb;        //   source, as an element index from the ring's base: a ring index (masked when used), or — bit 31 — an
-	                    //   index into the staging buffer behind the ring (a FAR source, fetched while the batch before ran)
+	uint32_t ma;        //   ring index of the destination | length << 16 | I2_MF_* << 28 | bit 31 = any flag   (length 0: no match)
+	uint32_t mb;        //   source, as an element index from the ring's base: a ring index (< W), or an index into the staging
+	                    //   buffer behind the ring (>= W: a FAR source, fetched while the batch before ran)
 	uint32_t m_src;     //   linear position of the source (far matches that did not fit the staging buffer are fetched directly)
 	uint32_t m_dist;    //   distance (overlapping matches are extended periodically)
 };
-#define I2_MF_LONG 1u       // longer than 32 elements
+#define I2_MF_LONG 1u       // longer than 64 elements, or a range that wraps around the ring
 #define I2_MF_PERIODIC 2u   // distance < length
 #define I2_MF_DIRECT 4u     // far source not staged: read from HBM
 
@@ -1671,7 +1671,9 @@ __device__ __forceinline__ I2Batch i2_scan_batch(I2LzSmem<W, T> &S, int buf, uin
 	const bool is_far = is_match && dist > (uint32_t)W - (B.q_end - mq);
 	const uint32_t far_m = __ballot_sync(0xFFFFFFFFu, is_far);
 	const uint32_t src_lin = mq - dist;
-	uint32_t flags = is_match ? ((ml > 32u ? I2_MF_LONG : 0u) | ((!is_far && dist < ml) ? I2_MF_PERIODIC : 0u)) : 0u;
+	// LONG: more than 64 elements, or the destination / a ring source wraps around the ring
+	uint32_t flags = is_match ? (((ml > 64u || (mq & MASK) + ml > (uint32_t)W || (!is_far && (src_lin & MASK) + ml > (uint32_t)W)) ? I2_MF_LONG : 0u) |
+		((!is_far && dist < ml) ? I2_MF_PERIODIC : 0u)) : 0u;
 	B.mb = src_lin & MASK;
 	B.m_src = src_lin;
 	B.m_dist = dist;
@@ -1690,7 +1692,7 @@ __device__ __forceinline__ I2Batch i2_scan_batch(I2LzSmem<W, T> &S, int buf, uin
 		if (is_far) {
 			if (incl <= STAGE_VECS) {
 				const uint32_t cst = incl - nch;
-				B.mb = 0x80000000u | ((uint32_t)W + (uint32_t)buf * I2Elem<T>::STAGE + VEC * cst + soff);
+				B.mb = (uint32_t)W + (uint32_t)buf * I2Elem<T>::STAGE + VEC * cst + soff;
 				// every lane fetches the vectors of its own match (cp.async groups are per thread: the executor waits for
 				// its own group and then syncs the warp)
 				uint32_t sa = (uint32_t)__cvta_generic_to_shared(&S.stage[buf][VEC * cst]);
@@ -1706,7 +1708,7 @@ __device__ __forceinline__ I2Batch i2_scan_batch(I2LzSmem<W, T> &S, int buf, uin
 			}
 		}
 	}
-	B.ma = (mq & MASK) | ((is_match ? ml : 0u) << 16) | (flags << 28);
+	B.ma = (mq & MASK) | ((is_match ? ml : 0u) << 16) | (flags << 28) | (flags ? 0x80000000u : 0u);
 	asm volatile("cp.async.commit_group;" ::: "memory");
 	return B;
 }
@@ -1850,21 +1852,36 @@ __global__ void __launch_bounds__(128) k_inflate_lz(uint8_t *__restrict__ out, c
 						rb[(cur.my_out + t) & MASK] = lits[cur.my_lit + t];
 					}
 				}
-				// the matches in stream order: one shuffle pair fetches the record's descriptor, lanes < length copy one element each
-				// (source: ring or staging buffer — one index space), longer / overlapping / unstaged ones take the side exit
+				// the matches in stream order: one shuffle pair fetches the record's descriptor; the common case — up to 64 elements,
+				// no overlap, neither range wraps around the ring — is two loads and two stores per lane without any index masking
+				// (source: ring or staging buffer, one index space); everything else takes the side exit
+				const uint32_t lane32 = lane + 32u;
 #pragma unroll 1
 				for (uint32_t r = 0; r < cur.ntake; r++) {
 					const uint32_t a = __shfl_sync(0xFFFFFFFFu, cur.ma, r), bsrc = __shfl_sync(0xFFFFFFFFu, cur.mb, r);
-					const uint32_t len = (a >> 16) & 0x1FFu, dq = a & 0xFFFFu;
-					const uint32_t smask = MASK | (uint32_t)(((int32_t)bsrc >> 31) & 0x7FFFF000);   // staged sources are not wrapped
 					__syncwarp();   // earlier ring stores are visible to the loads below
-					if ((a >> 28) == 0u) {
+					if ((int32_t)a >= 0) {
+						const uint32_t len = a >> 16, dq = a & 0xFFFFu;
+						T v0 = 0, v1 = 0;
 						if (lane < len) {
-							rb[(dq + lane) & MASK] = rb[(bsrc + lane) & smask];
+							v0 = rb[bsrc + lane];
 						}
-					} else if ((a >> 28) & I2_MF_PERIODIC) {
+						if (lane32 < len) {
+							v1 = rb[bsrc + lane32];
+						}
+						if (lane < len) {
+							rb[dq + lane] = v0;
+						}
+						if (lane32 < len) {
+							rb[dq + lane32] = v1;
+						}
+						continue;
+					}
+					const uint32_t len = (a >> 16) & 0x1FFu, dq = a & 0xFFFFu, fl = (a >> 28) & 7u;
+					const uint32_t smask = bsrc >= (uint32_t)W ? 0xFFFFFFFFu : MASK;   // staged sources are not wrapped
+					if (fl & I2_MF_PERIODIC) {
 						i2_copy_periodic<W, T>(rb, dq, bsrc, __shfl_sync(0xFFFFFFFFu, cur.m_dist, r), len, lane);
-					} else if ((a >> 28) & I2_MF_DIRECT) {
+					} else if (fl & I2_MF_DIRECT) {
 						const uint32_t src = __shfl_sync(0xFFFFFFFFu, cur.m_src, r);
 #pragma unroll 1
 						for (uint32_t x = lane; x < len; x += 32) {

@@ -65,6 +65,9 @@ struct otz_ctx {
 	int seg_ring;           // OTZ_SEG_PAR_RING: ring elements per warp of the parallel segment executor (4096 / 8192)
 	uint16_t *d_sym_cache;  // grow-only symbol buffer of the parallel segment execution
 	uint64_t sym_cache_elems;
+	otz_ctx *pipe[2];       // child contexts (own streams and scratch) of the pipelined host call otz_extract_host
+	void *h_res;            // pinned staging of its per-entry results
+	uint64_t h_res_bytes;
 	uint64_t sym_limit;     // OTZ_SEG_SYM_LIMIT: cap of the symbol buffer in elements (tests: streams that do not fit are walked by one warp)
 };
 
@@ -239,6 +242,11 @@ extern "C" void otz_ctx_destroy(otz_ctx *c) {
 	cudaFree(c->d_tok_cache);
 	cudaFree(c->d_sym_cache);
 	cudaFree(c->d_ztok_cache);
+	cudaFreeHost(c->h_res);
+	for (auto &pc : c->pipe) {
+		otz_ctx_destroy(pc);
+	}
+	cudaSetDevice(c->device);
 	cudaEventDestroy(c->ev0);
 	cudaEventDestroy(c->ev1);
 	for (auto &slot : c->pev) {
@@ -1161,47 +1169,272 @@ extern "C" int otz_extract_host(otz_ctx *c, const uint8_t *archive, uint64_t arc
 	return otz_extract_host_ex(c, archive, archive_len, ents, n, opts, out, out_len, crc, status, nullptr);
 }
 
+// Grow-only scratch of a context (token scratch of the two-phase decoders, symbol buffer of the parallel segment execution) for
+// the plan about to run: the pipelined host call reserves it before anything is in flight, so that no cudaFree / cudaMalloc
+// (which synchronise the device) lands between its asynchronous stages.  Failing to allocate is not an error here: the
+// dispatchers fall back to the decoders that need no scratch.
+static int reserve_scratch(otz_ctx *c, otz_plan *p) {
+	if (p->n_inflate && p->tok_bytes + 64 > c->tok_cache_bytes) {
+		CK(cudaStreamSynchronize(c->stream));
+		cudaFree(c->d_tok_cache);
+		c->d_tok_cache = nullptr;
+		c->tok_cache_bytes = 0;
+		if (cudaMalloc(&c->d_tok_cache, p->tok_bytes + 64) == cudaSuccess) {
+			c->tok_cache_bytes = p->tok_bytes + 64;
+		} else {
+			cudaGetLastError();
+		}
+	}
+	if (p->n_zstd && p->ztok_bytes + 64 > c->ztok_cache_bytes) {
+		CK(cudaStreamSynchronize(c->stream));
+		cudaFree(c->d_ztok_cache);
+		c->d_ztok_cache = nullptr;
+		c->ztok_cache_bytes = 0;
+		if (cudaMalloc(&c->d_ztok_cache, p->ztok_bytes + 64) == cudaSuccess) {
+			c->ztok_cache_bytes = p->ztok_bytes + 64;
+		} else {
+			cudaGetLastError();
+		}
+	}
+	if (p->sym_elems > c->sym_cache_elems && !c->seg_serial) {
+		CK(cudaStreamSynchronize(c->stream));
+		CK(cudaStreamSynchronize(c->stream2));
+		cudaFree(c->d_sym_cache);
+		c->d_sym_cache = nullptr;
+		c->sym_cache_elems = 0;
+		if (cudaMalloc(&c->d_sym_cache, p->sym_elems * 2 + 64) == cudaSuccess) {
+			c->sym_cache_elems = p->sym_elems;
+		} else {
+			cudaGetLastError();
+		}
+	}
+	return OTZ_SUCCESS;
+}
+
+// One sub-batch of the pipelined host call: a contiguous index range of the caller's table with its byte range of the
+// archive image and of the output arena.
+struct OtzSub {
+	uint32_t first, n;
+	uint64_t a_lo, a_hi;   // archive bytes [a_lo, a_hi) hold every LFH and payload of the range
+	uint64_t o_lo, o_hi;   // arena bytes the range writes
+	otz_plan *plan;
+};
+
+// Byte range of entry e in the host image: LFH + name + extra + payload (clamped to the image; the kernels re-check
+// everything on the device, this only decides what is uploaded).
+static void entry_span(const uint8_t *archive, uint64_t archive_len, const otz_entry &e, uint64_t *lo, uint64_t *hi) {
+	uint64_t b = std::min<uint64_t>(e.lfh_ofs, archive_len), t = b;
+	if (e.flags & OTZ_EF_CHUNK) {
+		t = b + e.comp_size;   // chunk rows address their payload directly
+	} else if (archive_len - b >= 30) {
+		const uint64_t nl = archive[b + 26] | (archive[b + 27] << 8), xl = archive[b + 28] | (archive[b + 29] << 8);
+		t = b + 30 + nl + xl + e.comp_size;
+	} else {
+		t = archive_len;
+	}
+	*lo = b & ~63ull;
+	*hi = std::min<uint64_t>(archive_len, (t + 63) & ~63ull);
+}
+
 extern "C" int otz_extract_host_ex(otz_ctx *c, const uint8_t *archive, uint64_t archive_len, const otz_entry *ents, uint32_t n,
 	const otz_extract_opts *opts, uint8_t *out, uint64_t out_len, uint32_t *crc, int32_t *status, uint32_t *produced) {
-	if (!c || !opts) {
+	if (!c || !opts || (n && !ents) || (archive_len && !archive)) {
 		return OTZ_ERR_ARG;
 	}
-	otz_plan *p = nullptr;
-	int rc = otz_plan_create(c, ents, n, opts, &p);
-	if (rc) {
+	CK(cudaSetDevice(c->device));
+	// ---- sub-batches: contiguous index ranges of ~OTZ_PIPE_BYTES of output whose archive ranges ascend without overlap
+	// (true for every archive laid out in index order).  Two lanes (child contexts: own streams and scratch) alternate,
+	// so H2D(k+1), the kernels of k and D2H(k-1) overlap.  Tables with chunk rows (their parent links are table
+	// indices) or out-of-order payloads go as one batch.
+	// (few, large sub-batches: the kernels of a batch lose efficiency when its largest stream becomes their critical path,
+	// while the copies — the bound of the whole call — do not care; six keep the ramp at ~1/6 of the copy time)
+	const char *pb = getenv("OTZ_PIPE_BYTES");
+	uint64_t target = pb ? strtoull(pb, nullptr, 0) : (768ull << 20);
+	if (!pb) {
+		uint64_t total = 0;
+		for (uint32_t i = 0; i < n; i++) {
+			total += (uint64_t)ents[i].uncomp_size + ents[i].comp_size;
+		}
+		target = std::max<uint64_t>(target, total / 6 + 1);
+	}
+	std::vector<OtzSub> subs;
+	bool pipelined = target != 0 && n > 1;
+	uint64_t need = 0;
+	for (uint32_t i = 0; i < n; i++) {
+		if (ents[i].flags & (OTZ_EF_CHUNK | OTZ_EF_PARENT)) {
+			pipelined = false;
+		}
+		if (!(opts->verify_only && ents[i].method == OTZ_M_STORE)) {
+			need = std::max<uint64_t>(need, ents[i].out_ofs + ents[i].uncomp_size);
+		}
+	}
+	if (need > out_len || (need && !out && !opts->verify_only)) {
+		snprintf(g_err, sizeof(g_err), "output arena too small: need %llu, have %llu", (unsigned long long)need, (unsigned long long)out_len);
+		return OTZ_ERR_ARG;
+	}
+	if (pipelined) {
+		OtzSub cur = { 0, 0, ~0ull, 0, ~0ull, 0, nullptr };
+		uint64_t bytes = 0, prev_a_hi = 0, prev_o_hi = 0;
+		for (uint32_t i = 0; i < n && pipelined; i++) {
+			uint64_t lo, hi;
+			entry_span(archive, archive_len, ents[i], &lo, &hi);
+			const bool writes = !(opts->verify_only && ents[i].method == OTZ_M_STORE);
+			const uint64_t olo = writes ? ents[i].out_ofs : ~0ull, ohi = writes ? ents[i].out_ofs + ents[i].uncomp_size : 0;
+			cur.a_lo = std::min(cur.a_lo, lo);
+			cur.a_hi = std::max(cur.a_hi, hi);
+			cur.o_lo = std::min(cur.o_lo, olo);
+			cur.o_hi = std::max(cur.o_hi, ohi);
+			cur.n++;
+			bytes += (uint64_t)ents[i].uncomp_size + ents[i].comp_size;
+			if (bytes >= target || i + 1 == n) {
+				// (ranges are 64-byte aligned: neighbours may share their boundary block, which then is copied twice with the same bytes —
+				// only real overlap, payloads out of index order, turns the pipeline off)
+				if (cur.a_lo + 64 < prev_a_hi || (cur.o_hi > cur.o_lo && cur.o_lo < prev_o_hi)) {
+					pipelined = false;
+					break;
+				}
+				prev_a_hi = cur.a_hi;
+				prev_o_hi = std::max(prev_o_hi, cur.o_hi);
+				subs.push_back(cur);
+				cur = OtzSub{ i + 1, 0, ~0ull, 0, ~0ull, 0, nullptr };
+				bytes = 0;
+			}
+		}
+		if (subs.size() < 2) {
+			pipelined = false;
+		}
+	}
+	// device staging buffers are kept (grow-only) so repeated calls pay only for the copies
+	int rc = OTZ_SUCCESS;
+	if (archive_len > c->arch_cache_bytes || !c->d_arch_cache) {
+		cudaFree(c->d_arch_cache);
+		c->d_arch_cache = nullptr;
+		c->arch_cache_bytes = 0;
+		if ((rc = otz_dev_alloc(c, archive_len, &c->d_arch_cache))) {
+			return rc;
+		}
+		c->arch_cache_bytes = archive_len;
+	}
+	if (need > c->out_cache_bytes) {
+		cudaFree(c->d_out_cache);
+		c->d_out_cache = nullptr;
+		c->out_cache_bytes = 0;
+		if ((rc = otz_dev_alloc(c, need, &c->d_out_cache))) {
+			return rc;
+		}
+		c->out_cache_bytes = need;
+	}
+	const uint8_t *d_arch = (const uint8_t *)c->d_arch_cache;
+	uint8_t *d_out = (uint8_t *)c->d_out_cache;
+	if (!pipelined) {
+		otz_plan *p = nullptr;
+		if ((rc = otz_plan_create(c, ents, n, opts, &p))) {
+			return rc;
+		}
+		do {
+			// only the bytes the entries of this call live in (a window of a large archive uploads its own range)
+			uint64_t lo = archive_len, hi = 0;
+			for (uint32_t i = 0; i < n; i++) {
+				uint64_t a, b;
+				entry_span(archive, archive_len, ents[i], &a, &b);
+				lo = std::min(lo, a);
+				hi = std::max(hi, b);
+			}
+			if (hi > lo && (rc = otz_h2d(c, (uint8_t *)c->d_arch_cache + lo, archive + lo, hi - lo))) break;
+			if ((rc = otz_extract_run(c, p, d_arch, archive_len, d_out, need))) break;
+			if (out && need && (rc = otz_d2h(c, out, c->d_out_cache, need))) break;
+			rc = otz_extract_results(c, p, crc, status);
+			if (!rc && produced) {
+				rc = otz_extract_produced(c, p, produced);
+			}
+		} while (0);
+		cudaStreamSynchronize(c->stream);
+		otz_plan_destroy(c, p);
 		return rc;
 	}
-	do {
-		// device staging buffers are kept (grow-only) so repeated calls pay only for the copies
-		if (archive_len > c->arch_cache_bytes || !c->d_arch_cache) {
-			cudaFree(c->d_arch_cache);
-			c->d_arch_cache = nullptr;
-			c->arch_cache_bytes = 0;
-			if ((rc = otz_dev_alloc(c, archive_len, &c->d_arch_cache))) break;
-			c->arch_cache_bytes = archive_len;
+	// ---- pipelined
+	for (int l = 0; l < 2; l++) {
+		if (!c->pipe[l] && (rc = otz_ctx_create(c->device, &c->pipe[l]))) {
+			return rc;
 		}
-		const uint64_t need = p->out_bytes_needed;
-		if (need > out_len) {
-			rc = OTZ_ERR_ARG;
+	}
+	// pinned staging for the per-entry results (a D2H copy into pageable memory would block the enqueueing thread)
+	const uint64_t res_bytes = (uint64_t)n * 12 + subs.size() * 4 + 64;
+	if (res_bytes > c->h_res_bytes) {
+		cudaFreeHost(c->h_res);
+		c->h_res = nullptr;
+		c->h_res_bytes = 0;
+		if (cudaHostAlloc(&c->h_res, res_bytes, cudaHostAllocDefault) != cudaSuccess) {
+			return fail_cuda(cudaGetLastError(), "cudaHostAlloc(result staging)");
+		}
+		c->h_res_bytes = res_bytes;
+	}
+	uint32_t *h_crc = (uint32_t *)c->h_res, *h_prod = h_crc + n, *h_fb = h_prod + n + n;
+	int32_t *h_st = (int32_t *)(h_prod + n);
+	for (auto &sb : subs) {   // all plans first: cudaMalloc / cudaFree must not sit between the asynchronous stages
+		otz_ctx *lc = c->pipe[(&sb - &subs[0]) & 1];
+		if ((rc = otz_plan_create(lc, ents + sb.first, sb.n, opts, &sb.plan))) {
 			break;
 		}
-		if (need > c->out_cache_bytes) {
-			cudaFree(c->d_out_cache);
-			c->d_out_cache = nullptr;
-			c->out_cache_bytes = 0;
-			if ((rc = otz_dev_alloc(c, need, &c->d_out_cache))) break;
-			c->out_cache_bytes = need;
+	}
+	if (!rc) {
+		// scratch of both lanes, sized for their largest sub-batch, before anything is in flight
+		for (auto &sb : subs) {
+			otz_ctx *lc = c->pipe[(&sb - &subs[0]) & 1];
+			if ((rc = reserve_scratch(lc, sb.plan))) {
+				break;
+			}
 		}
-		if ((rc = otz_h2d(c, c->d_arch_cache, archive, archive_len))) break;
-		if ((rc = otz_extract_run(c, p, (const uint8_t *)c->d_arch_cache, archive_len, (uint8_t *)c->d_out_cache, need))) break;
-		if (out && need && (rc = otz_d2h(c, out, c->d_out_cache, need))) break;
-		rc = otz_extract_results(c, p, crc, status);
-		if (!rc && produced) {
-			rc = otz_extract_produced(c, p, produced);
+	}
+	for (size_t k = 0; k < subs.size() && !rc; k++) {
+		OtzSub &sb = subs[k];
+		otz_ctx *lc = c->pipe[k & 1];
+		cudaStream_t st = lc->stream;
+		if (sb.a_hi > sb.a_lo) {
+			CK(cudaMemcpyAsync((uint8_t *)c->d_arch_cache + sb.a_lo, archive + sb.a_lo, sb.a_hi - sb.a_lo, cudaMemcpyHostToDevice, st));
 		}
-	} while (0);
-	cudaStreamSynchronize(c->stream);
-	otz_plan_destroy(c, p);
+		if ((rc = otz_extract_run(lc, sb.plan, d_arch, archive_len, d_out, need))) {
+			break;
+		}
+		if (out && sb.o_hi > sb.o_lo) {
+			CK(cudaMemcpyAsync(out + sb.o_lo, d_out + sb.o_lo, sb.o_hi - sb.o_lo, cudaMemcpyDeviceToHost, st));
+		}
+		CK(cudaMemcpyAsync(h_crc + sb.first, sb.plan->d_crc, sb.n * 4ull, cudaMemcpyDeviceToHost, st));
+		CK(cudaMemcpyAsync(h_st + sb.first, sb.plan->d_status, sb.n * 4ull, cudaMemcpyDeviceToHost, st));
+		CK(cudaMemcpyAsync(h_prod + sb.first, sb.plan->d_produced, sb.n * 4ull, cudaMemcpyDeviceToHost, st));
+		CK(cudaMemcpyAsync(h_fb + k, sb.plan->d_counter + 52, 4, cudaMemcpyDeviceToHost, st));
+	}
+	for (int l = 0; l < 2; l++) {
+		cudaError_t e = cudaStreamSynchronize(c->pipe[l]->stream);
+		if (e != cudaSuccess && !rc) {
+			rc = fail_cuda(e, "pipelined extract");
+		}
+	}
+	if (!rc) {
+		if (crc) {
+			memcpy(crc, h_crc, n * 4ull);
+		}
+		if (status) {
+			memcpy(status, h_st, n * 4ull);
+		}
+		if (produced) {
+			memcpy(produced, h_prod, n * 4ull);
+		}
+		c->last_fallbacks = 0;
+		for (size_t k = 0; k < subs.size(); k++) {
+			c->last_fallbacks += h_fb[k];
+		}
+	}
+	uint64_t child_launches = 0;
+	for (auto &sb : subs) {
+		otz_ctx *lc = c->pipe[(&sb - &subs[0]) & 1];
+		otz_plan_destroy(lc, sb.plan);
+	}
+	for (int l = 0; l < 2; l++) {
+		child_launches += c->pipe[l]->launches;
+		c->pipe[l]->launches = 0;
+	}
+	c->launches += child_launches;
 	return rc;
 }
 
