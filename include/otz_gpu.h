@@ -195,6 +195,12 @@ uint32_t otz_inflate_fallbacks(otz_ctx *ctx);
  * reads and writes): first[g] .. first[g + 1] is the range of part g, first[parts] = n.  Contiguous ranges keep
  * each part a contiguous byte range of the archive.  Pure host code (no device needed). */
 int otz_partition(const otz_entry *entries, uint32_t n, uint32_t parts, uint32_t *first);
+/* otz_extract_host_ex over several devices of one box: one context per device, the table cut by otz_partition, every
+ * device handed only its byte range of the image and of the arena, one host thread per device, no collective.
+ * Results are identical to the single-device call. */
+int otz_extract_host_multi(otz_ctx *const *ctxs, uint32_t n_ctx, const uint8_t *archive, uint64_t archive_len,
+	const otz_entry *entries, uint32_t n, const otz_extract_opts *opts, uint8_t *out, uint64_t out_len, uint32_t *crc,
+	int32_t *status, uint32_t *produced);
 
 /* Policy helper shared by the host library and the tests: does a status word
  * mean "zip_fopen_index returns the buffer" under the given globals?

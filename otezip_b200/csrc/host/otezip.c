@@ -52,6 +52,7 @@ struct otz_window {               /* one decoded batch of consecutive entries */
 	uint32_t *crc;
 	uint32_t refs;                /* zip_file_t handles pointing into arena */
 	int current;
+	int orphan;                   /* its archive was closed while handles were still open: the last zip_fclose frees it */
 };
 
 struct otz_pending {              /* a queued source (write path) */
@@ -90,24 +91,61 @@ struct otz_file {                 /* zip_file_t plus the window it borrows from 
 	uint8_t *own;                 /* malloc'd data (zero-length entries) */
 };
 
-static otz_ctx *g_ctx;
+/* Devices of the read path: OTEZIP_DEVICES = "all" or a comma list ("0,2,3") shards every batch of entries over those
+ * GPUs (otz_extract_host_multi: contiguous index ranges balanced by bytes, no collective — SURVEY.md §8e); otherwise the
+ * one device OTEZIP_DEVICE names (default 0).  The write path and the zlib-compatible single-stream calls use the first. */
+#define OTZ_MAX_DEVICES 16
+static otz_ctx *g_ctxs[OTZ_MAX_DEVICES];
+static uint32_t g_nctx;
 static int g_ctx_failed;
+
+static uint32_t otezip_b200_ctxs(otz_ctx ***out) {
+	if (!g_nctx && !g_ctx_failed) {
+		int devs[OTZ_MAX_DEVICES], nd = 0;
+		const char *e = getenv ("OTEZIP_DEVICES");
+		if (e && !strcmp (e, "all")) {
+			const int have = otz_device_count ();
+			for (int d = 0; d < have && nd < OTZ_MAX_DEVICES; d++) {
+				devs[nd++] = d;
+			}
+		} else if (e && *e) {
+			const char *q = e;
+			while (*q && nd < OTZ_MAX_DEVICES) {
+				char *end = NULL;
+				long d = strtol (q, &end, 10);
+				if (end == q) {
+					break;
+				}
+				devs[nd++] = (int)d;
+				q = *end == ',' ? end + 1 : end;
+			}
+		}
+		if (!nd) {
+			const char *one = getenv ("OTEZIP_DEVICE");
+			devs[nd++] = one ? atoi (one) : 0;
+		}
+		for (int i = 0; i < nd; i++) {
+			if (otz_ctx_create (devs[i], &g_ctxs[g_nctx]) != OTZ_SUCCESS) {
+				fprintf (stderr, "otezip-b200: no usable CUDA device %d (%s); this build has no CPU codec\n", devs[i], otz_last_error ());
+				for (uint32_t k = 0; k < g_nctx; k++) {
+					otz_ctx_destroy (g_ctxs[k]);
+					g_ctxs[k] = NULL;
+				}
+				g_nctx = 0;
+				g_ctx_failed = 1;
+				break;
+			}
+			g_nctx++;
+		}
+	}
+	*out = g_ctxs;
+	return g_nctx;
+}
 
 otz_ctx *otezip_b200_ctx(void);   /* shared with zcompat.c */
 otz_ctx *otezip_b200_ctx(void) {
-	if (!g_ctx && !g_ctx_failed) {
-		int dev = 0;
-		const char *e = getenv ("OTEZIP_DEVICE");
-		if (e) {
-			dev = atoi (e);
-		}
-		if (otz_ctx_create (dev, &g_ctx) != OTZ_SUCCESS) {
-			fprintf (stderr, "otezip-b200: no usable CUDA device (%s); this build has no CPU codec\n", otz_last_error ());
-			g_ctx_failed = 1;
-			g_ctx = NULL;
-		}
-	}
-	return g_ctx;
+	otz_ctx **c;
+	return otezip_b200_ctxs (&c) ? c[0] : NULL;
 }
 
 static struct otz_archive *priv(zip_t *za) {
@@ -592,7 +630,14 @@ static void free_windows(struct otz_archive *a) {
 	struct otz_window *w = a->windows;
 	while (w) {
 		struct otz_window *n = w->next;
-		free_window (w);
+		if (w->refs) {
+			/* zip_file_t handles still point into the arena.  In the reference every handle owns its buffer
+			 * (otezip.c:1326-1331), so zf->data stays valid after zip_close: keep the window until its last handle closes */
+			w->orphan = 1;
+			w->next = NULL;
+		} else {
+			free_window (w);
+		}
 		w = n;
 	}
 	a->windows = NULL;
@@ -696,17 +741,57 @@ static uint32_t chunk_index_of(const struct otz_archive *a, const struct otezip_
  * a chunk index become one parent row plus one row per chunk; if any chunk fails (or the CRC of the assembled
  * entry does not match) the entry is decoded again as one plain stream, so a wrong index can never change the
  * result the reference's sequential decoder would produce. */
+/* What k_resolve would say about an entry, decided on the host from the image (the head of otezip_extract_entry,
+ * otezip.c:403-487, in its order: LFH range and signature, payload range, zip-bomb rule, method, STORE size).  The
+ * reference rejects such an entry BEFORE it allocates anything (otezip.c:454-462 precede the malloc at :470); here it
+ * must not count towards the window's arena either: a crafted directory could otherwise claim gigabytes per entry. */
+static int32_t host_precheck(const struct otz_archive *a, const struct otezip_entry *e, uint64_t lfh) {
+	const uint64_t len = a->image_len;
+	if (lfh > len || len - lfh < 30) {
+		return OTZ_ST_LFH_RANGE;
+	}
+	const uint8_t *h = a->image + lfh;
+	if (otezip_read_le32 (h) != 0x04034b50u) {
+		return OTZ_ST_LFH_SIG;
+	}
+	const uint64_t data = lfh + 30u + otezip_read_le16 (h + 26) + otezip_read_le16 (h + 28);
+	if (data > len || (uint64_t)e->comp_size > MAX_PAYLOAD || (uint64_t)e->uncomp_size > MAX_PAYLOAD || data + e->comp_size > len) {
+		return OTZ_ST_DATA_RANGE;
+	}
+	if (bomb_rejects (e)) {
+		return OTZ_ST_ZIPBOMB;
+	}
+	if (e->method == OTEZIP_METHOD_STORE) {
+		if (e->comp_size != e->uncomp_size) {
+			return OTZ_ST_STORE_SIZE;
+		}
+	} else if (e->method != OTEZIP_METHOD_DEFLATE && e->method != OTEZIP_METHOD_ZSTD) {
+		return OTZ_ST_METHOD;
+	}
+	return OTZ_ST_OK;
+}
+
+/* Decode a batch starting at `index`: consecutive entries until the byte budget is reached.  Entries the host pre-check
+ * rejects get their status here and a zero-length slice — they are not part of the device table, so neither the pinned
+ * arena nor the device scratch is sized by what a directory merely claims.  Entries that carry a chunk index become one
+ * parent row plus one row per chunk; a chunk row is only accepted in the shape this library writes (it ends byte
+ * aligned behind an empty stored block, and only the last one holds the final block), and if any chunk fails or the CRC
+ * of the assembled entry does not match, the entry is decoded again as one plain stream.  (The CRC comparison is the
+ * backstop, not a proof: with otezip_ref_compat = 1 and otezip_verify_crc = 0 a crafted index whose chunks decode
+ * cleanly AND collide on CRC-32 could still differ from the sequential decode; OTEZIP_NO_INDEX=1 ignores the index.) */
 static struct otz_window *run_window(struct otz_archive *a, zip_uint64_t index) {
 	zip_t *za = &a->pub;
-	otz_ctx *ctx = otezip_b200_ctx ();
-	if (!ctx || load_image (a) != 0) {
+	otz_ctx **ctxs = NULL;
+	const uint32_t n_ctx = otezip_b200_ctxs (&ctxs);
+	if (!n_ctx || load_image (a) != 0) {
 		return NULL;
 	}
 	const uint64_t budget = batch_budget ();
 	zip_uint64_t last = index;
 	uint64_t bytes = 0;
 	while (last < za->n_entries) {
-		uint64_t sz = ((uint64_t)za->entries[last].uncomp_size + 15) & ~15ULL;
+		const struct otezip_entry *e = &za->entries[last];
+		uint64_t sz = host_precheck (a, e, entry_lfh (za, last)) == OTZ_ST_OK ? ((uint64_t)e->uncomp_size + 15) & ~15ULL : 0;
 		if (last > index && bytes + sz > budget) {
 			break;
 		}
@@ -714,46 +799,70 @@ static struct otz_window *run_window(struct otz_archive *a, zip_uint64_t index) 
 		last++;
 	}
 	const uint32_t n = (uint32_t)(last - index);
-	/* pass 0 counts rows, pass 1 fills them */
-	uint32_t n_rows = n;
-	for (uint32_t k = 0; k < n; k++) {
-		uint32_t cb;
-		const uint8_t *cs;
-		uint64_t dofs;
-		n_rows += chunk_index_of (a, &za->entries[index + k], &cb, &cs, &dofs);
+	/* rows of the device table: admitted entries first (compact), then their chunk rows */
+	int32_t *pre = (int32_t *)calloc (n ? n : 1, sizeof (int32_t));
+	uint32_t *rowof = (uint32_t *)calloc (n ? n : 1, sizeof (uint32_t));
+	if (!pre || !rowof) {
+		free (pre);
+		free (rowof);
+		return NULL;
 	}
+	uint32_t n_adm = 0, n_rows = 0;
+	for (uint32_t k = 0; k < n; k++) {
+		pre[k] = host_precheck (a, &za->entries[index + k], entry_lfh (za, index + k));
+		rowof[k] = 0xFFFFFFFFu;
+		if (pre[k] == OTZ_ST_OK) {
+			uint32_t cb;
+			const uint8_t *cs;
+			uint64_t dofs;
+			rowof[k] = n_adm++;
+			n_rows += chunk_index_of (a, &za->entries[index + k], &cb, &cs, &dofs);
+		}
+	}
+	n_rows += n_adm;
 	struct otz_window *w = (struct otz_window *)calloc (1, sizeof (*w));
-	otz_entry *tab = (otz_entry *)calloc (n_rows, sizeof (otz_entry));
-	int32_t *row_status = (int32_t *)calloc (n_rows, sizeof (int32_t));
-	uint32_t *row_crc = (uint32_t *)calloc (n_rows, sizeof (uint32_t));
-	if (!w || !tab || !row_status || !row_crc) {
-		free (w);
+	otz_entry *tab = (otz_entry *)calloc (n_rows ? n_rows : 1, sizeof (otz_entry));
+	int32_t *row_status = (int32_t *)calloc (n_rows ? n_rows : 1, sizeof (int32_t));
+	uint32_t *row_crc = (uint32_t *)calloc (n_rows ? n_rows : 1, sizeof (uint32_t));
+	if (w) {
+		w->ofs = (uint64_t *)calloc (n ? n : 1, sizeof (uint64_t));
+		w->status = (int32_t *)calloc (n ? n : 1, sizeof (int32_t));
+		w->crc = (uint32_t *)calloc (n ? n : 1, sizeof (uint32_t));
+	}
+	if (!w || !tab || !row_status || !row_crc || !w->ofs || !w->status || !w->crc) {
+		if (w) {
+			free_window (w);
+		}
 		free (tab);
 		free (row_status);
 		free (row_crc);
+		free (pre);
+		free (rowof);
 		return NULL;
 	}
 	w->first = index;
 	w->last = last;
-	w->ofs = (uint64_t *)calloc (n, sizeof (uint64_t));
-	w->status = (int32_t *)calloc (n, sizeof (int32_t));
-	w->crc = (uint32_t *)calloc (n, sizeof (uint32_t));
 	uint64_t out = 0;
-	uint32_t next_row = n; /* chunk rows follow the n entry rows */
+	uint32_t next_row = n_adm; /* chunk rows follow the entry rows */
 	for (uint32_t k = 0; k < n; k++) {
 		const struct otezip_entry *e = &za->entries[index + k];
-		tab[k].lfh_ofs = entry_lfh (za, index + k);
-		tab[k].out_ofs = out;
-		tab[k].comp_size = e->comp_size;
-		tab[k].uncomp_size = e->uncomp_size;
-		tab[k].crc32 = e->crc32;
-		tab[k].method = e->method;
+		w->ofs[k] = out;
+		if (pre[k] != OTZ_ST_OK) {
+			continue;
+		}
+		otz_entry *t = &tab[rowof[k]];
+		t->lfh_ofs = entry_lfh (za, index + k);
+		t->out_ofs = out;
+		t->comp_size = e->comp_size;
+		t->uncomp_size = e->uncomp_size;
+		t->crc32 = e->crc32;
+		t->method = e->method;
 		uint32_t cb = 0;
 		const uint8_t *cs = NULL;
 		uint64_t dofs = 0;
 		const uint32_t nc = chunk_index_of (a, e, &cb, &cs, &dofs);
 		if (nc) {
-			tab[k].flags = OTZ_EF_PARENT;
+			t->flags = OTZ_EF_PARENT;
 			uint64_t cofs = dofs, uofs = 0;
 			for (uint32_t c = 0; c < nc; c++) {
 				otz_entry *r = &tab[next_row++];
@@ -762,14 +871,13 @@ static struct otz_window *run_window(struct otz_archive *a, zip_uint64_t index) 
 				r->out_ofs = out + uofs;
 				r->comp_size = csz;
 				r->uncomp_size = (uint32_t)((uint64_t)e->uncomp_size - uofs < cb ? (uint64_t)e->uncomp_size - uofs : cb);
-				r->crc32 = k; /* parent row */
+				r->crc32 = rowof[k]; /* parent row */
 				r->method = OTZ_M_DEFLATE;
 				r->flags = (uint16_t)(OTZ_EF_CHUNK | (c + 1 == nc ? OTZ_EF_LAST_CHUNK : 0));
 				cofs += csz;
 				uofs += r->uncomp_size;
 			}
 		}
-		w->ofs[k] = out;
 		out += ((uint64_t)e->uncomp_size + 15) & ~15ULL;
 	}
 	w->arena_len = out;
@@ -782,11 +890,13 @@ static struct otz_window *run_window(struct otz_archive *a, zip_uint64_t index) 
 	int rc = otz_host_alloc (out + 64, &arena);
 	if (rc == OTZ_SUCCESS) {
 		w->arena = (uint8_t *)arena;
-		rc = otz_extract_host (ctx, a->image, a->image_len, tab, n_rows, &o, w->arena, out, row_crc, row_status);
+		if (n_rows) {
+			rc = otz_extract_host_multi (ctxs, n_ctx, a->image, a->image_len, tab, n_rows, &o, w->arena, out, row_crc, row_status, NULL);
+		}
 	}
 	/* entries whose indexed decode did not come out clean are decoded again as plain streams */
 	uint32_t n_redo = 0;
-	for (uint32_t k = 0; rc == OTZ_SUCCESS && k < n; k++) {
+	for (uint32_t k = 0; rc == OTZ_SUCCESS && k < n_adm; k++) {
 		if ((tab[k].flags & OTZ_EF_PARENT) && row_status[k] != OTZ_ST_OK) {
 			n_redo++;
 		}
@@ -797,14 +907,14 @@ static struct otz_window *run_window(struct otz_archive *a, zip_uint64_t index) 
 		uint32_t *rcv = (uint32_t *)calloc (n_redo, sizeof (uint32_t)), *map = (uint32_t *)calloc (n_redo, sizeof (uint32_t));
 		if (rt && rs && rcv && map) {
 			uint32_t m = 0;
-			for (uint32_t k = 0; k < n; k++) {
+			for (uint32_t k = 0; k < n_adm; k++) {
 				if ((tab[k].flags & OTZ_EF_PARENT) && row_status[k] != OTZ_ST_OK) {
 					rt[m] = tab[k];
 					rt[m].flags = 0;
 					map[m++] = k;
 				}
 			}
-			rc = otz_extract_host (ctx, a->image, a->image_len, rt, n_redo, &o, w->arena, out, rcv, rs);
+			rc = otz_extract_host_multi (ctxs, n_ctx, a->image, a->image_len, rt, n_redo, &o, w->arena, out, rcv, rs, NULL);
 			for (uint32_t i = 0; rc == OTZ_SUCCESS && i < n_redo; i++) {
 				row_status[map[i]] = rs[i];
 				row_crc[map[i]] = rcv[i];
@@ -818,12 +928,14 @@ static struct otz_window *run_window(struct otz_archive *a, zip_uint64_t index) 
 		free (map);
 	}
 	for (uint32_t k = 0; k < n; k++) {
-		w->status[k] = row_status[k];
-		w->crc[k] = row_crc[k];
+		w->status[k] = pre[k] != OTZ_ST_OK ? pre[k] : row_status[rowof[k]];
+		w->crc[k] = pre[k] != OTZ_ST_OK ? 0u : row_crc[rowof[k]];
 	}
 	free (tab);
 	free (row_status);
 	free (row_crc);
+	free (pre);
+	free (rowof);
 	if (rc != OTZ_SUCCESS) {
 		fprintf (stderr, "otezip-b200: GPU extract failed: %s\n", otz_last_error ());
 		free_window (w);
@@ -926,6 +1038,9 @@ int zip_fclose(zip_file_t *zf) { /* otezip.c:1336-1343: the library owns zf->dat
 	struct otz_file *f = (struct otz_file *)zf;
 	if (f->win && f->win->refs) {
 		f->win->refs--;
+		if (!f->win->refs && f->win->orphan) {
+			free_window (f->win);
+		}
 	}
 	free (f->own);
 	free (f);

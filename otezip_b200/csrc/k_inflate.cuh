@@ -613,6 +613,12 @@ __device__ __forceinline__ int32_t inflate_stream(const Tile &tile, InflateSmemV
 		const uint32_t btype = (hdr >> 1) & 3u;
 		br.skip(3);
 		INF_STEP_CHECK();
+		if (chunk_mid && final_blk) {
+			// a chunk that is not the last one never holds the final block: the sequential decoder would stop here and
+			// zero-pad the rest, so an index that says otherwise is wrong (the entry is then decoded as one stream)
+			err = OTZ_ST_DATA;
+			break;
+		}
 		if (btype == 0) {
 			// ---- stored block, dec:269-319
 			const int64_t rem = br.remaining_bits();
@@ -706,9 +712,9 @@ __device__ __forceinline__ int32_t inflate_stream(const Tile &tile, InflateSmemV
 			}
 			break;  // dec:714-716
 		}
-		if (chunk_mid && br.remaining_bits() < 8 && br.remaining_bits() >= 0) {
-			break;   // end of this chunk
-		}
+		// (a chunk that is not the last one ends only behind an empty stored block, byte aligned, exactly where its input
+		// ends — the shape k_deflate writes; a Huffman block that merely runs out of input is not a chunk boundary: the
+		// sequential decoder would read the next header from the bits left over)
 		INF_STEP_CHECK();
 	}
 #undef INF_STEP_CHECK

@@ -437,6 +437,9 @@ __device__ __forceinline__ uint32_t i2_header(I2Reader &br, uint8_t *slot, const
 	const uint32_t btype = (bits >> 1) & 3u;
 	br.pos += 3;
 	I2_HDR_STEP_CHECK();
+	if (chunk_mid && final_blk) {
+		return I2_A_FALLBACK;   // a final block inside a chunk that is not the last: k_inflate fails the chunk
+	}
 	if (btype == 0) {
 		// stored block (dec:269-319).  Anything irregular — a bad length pair, a payload that runs past the input — is
 		// left to k_inflate, which knows what the reference answers
@@ -473,8 +476,6 @@ __device__ __forceinline__ uint32_t i2_header(I2Reader &br, uint8_t *slot, const
 			// empty fixed block (zlib's Z_FINISH tail): end-of-block is the 7-bit code 0000000
 			br.pos += 7;
 			if (final_blk) {
-				return I2_A_COMMIT;
-			} else if (chunk_mid && br.remaining_bits() < 8 && br.remaining_bits() >= 0) {
 				return I2_A_COMMIT;
 			} else {
 				I2_HDR_STEP_CHECK();
@@ -1032,11 +1033,8 @@ __global__ void __launch_bounds__(32) k_inflate_tok(const uint8_t *__restrict__ 
 							I2_FALLBACK();
 						} else if (eob) {
 							// end of block, dec:711-716 (pos already stands behind the code)
-							const bool chunk_mid = (rflags & OTZ_EF_CHUNK) && !(rflags & OTZ_EF_LAST_CHUNK);
 							if (final_blk) {
 								I2_COMMIT();
-							} else if (chunk_mid && br.remaining_bits() < 8 && br.remaining_bits() >= 0) {
-								I2_COMMIT();   // end of this chunk
 							} else {
 								state = I2_S_HDR;
 								I2_STEP_CHECK();

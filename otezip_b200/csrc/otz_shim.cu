@@ -9,6 +9,8 @@
 
 #include "k_copy.cuh"
 #include "k_crc32.cuh"
+#include <string>
+#include <thread>
 #include "k_inflate.cuh"
 #include "k_inflate2.cuh"
 #include "k_inflate3.cuh"
@@ -66,6 +68,10 @@ struct otz_ctx {
 	uint16_t *d_sym_cache;  // grow-only symbol buffer of the parallel segment execution
 	uint64_t sym_cache_elems;
 	otz_ctx *pipe[2];       // child contexts (own streams and scratch) of the pipelined host call otz_extract_host
+	std::vector<otz_plan *> pc_plans;   // sub-plans of the last pipelined call (reused when the same table comes again)
+	std::vector<otz_entry> pc_ents;
+	otz_extract_opts pc_opts;
+	uint32_t pc_n;
 	void *h_res;            // pinned staging of its per-entry results
 	uint64_t h_res_bytes;
 	uint64_t sym_limit;     // OTZ_SEG_SYM_LIMIT: cap of the symbol buffer in elements (tests: streams that do not fit are walked by one warp)
@@ -186,8 +192,7 @@ extern "C" int otz_ctx_create(int device, otz_ctx **out) {
 	if (!c) {
 		return OTZ_ERR_NOMEM;
 	}
-	memset(c, 0, sizeof(*c));
-	c->device = device;
+	c->device = device;   // (value-initialised by new otz_ctx(): every field is zero)
 	cudaDeviceProp prop;
 	CK(cudaGetDeviceProperties(&prop, device));
 	c->sm_count = prop.multiProcessorCount;
@@ -242,6 +247,9 @@ extern "C" void otz_ctx_destroy(otz_ctx *c) {
 	cudaFree(c->d_tok_cache);
 	cudaFree(c->d_sym_cache);
 	cudaFree(c->d_ztok_cache);
+	for (size_t k = 0; k < c->pc_plans.size(); k++) {
+		otz_plan_destroy(c->pipe[k & 1], c->pc_plans[k]);
+	}
 	cudaFreeHost(c->h_res);
 	for (auto &pc : c->pipe) {
 		otz_ctx_destroy(pc);
@@ -286,7 +294,7 @@ extern "C" int otz_dev_free(otz_ctx *c, void *dptr) {
 	return OTZ_SUCCESS;
 }
 extern "C" int otz_host_alloc(uint64_t bytes, void **hptr) {
-	CK(cudaHostAlloc(hptr, bytes ? bytes : 1, cudaHostAllocDefault));
+	CK(cudaHostAlloc(hptr, bytes ? bytes : 1, cudaHostAllocPortable));   // (pinned for every device: the multi-GPU call shares one arena)
 	return OTZ_SUCCESS;
 }
 extern "C" int otz_host_free(void *hptr) {
@@ -443,6 +451,14 @@ extern "C" int otz_plan_create(otz_ctx *c, const otz_entry *ents, uint32_t n, co
 	memset(p, 0, sizeof(*p));
 	p->n = n;
 	p->opts = *opts;
+	for (uint32_t i = 0; i < n; i++) {
+		// a chunk row names its parent row in crc32: the decoders write status[parent] when a chunk fails
+		if ((ents[i].flags & OTZ_EF_CHUNK) && (ents[i].crc32 >= n || !(ents[ents[i].crc32].flags & OTZ_EF_PARENT))) {
+			delete p;
+			snprintf(g_err, sizeof(g_err), "entry table row %u: chunk row without a parent row", i);
+			return OTZ_ERR_ARG;
+		}
+	}
 	// Work lists.  CRC chunks: STORE entries first (they are also the copy list), then the rest.
 	std::vector<OtzCrcChunk> chunks;
 	std::vector<uint32_t> infl, zst;
@@ -1247,15 +1263,16 @@ extern "C" int otz_extract_host_ex(otz_ctx *c, const uint8_t *archive, uint64_t 
 	// so H2D(k+1), the kernels of k and D2H(k-1) overlap.  Tables with chunk rows (their parent links are table
 	// indices) or out-of-order payloads go as one batch.
 	// (few, large sub-batches: the kernels of a batch lose efficiency when its largest stream becomes their critical path,
-	// while the copies — the bound of the whole call — do not care; six keep the ramp at ~1/6 of the copy time)
+	// while the copies — the bound of the whole call — do not care; twelve keep the ramp, H2D + kernels of the first one, at
+	// a few percent of the copy time)
 	const char *pb = getenv("OTZ_PIPE_BYTES");
-	uint64_t target = pb ? strtoull(pb, nullptr, 0) : (768ull << 20);
+	uint64_t target = pb ? strtoull(pb, nullptr, 0) : (256ull << 20);
 	if (!pb) {
 		uint64_t total = 0;
 		for (uint32_t i = 0; i < n; i++) {
 			total += (uint64_t)ents[i].uncomp_size + ents[i].comp_size;
 		}
-		target = std::max<uint64_t>(target, total / 6 + 1);
+		target = std::max<uint64_t>(target, total / 12 + 1);
 	}
 	std::vector<OtzSub> subs;
 	bool pipelined = target != 0 && n > 1;
@@ -1371,9 +1388,24 @@ extern "C" int otz_extract_host_ex(otz_ctx *c, const uint8_t *archive, uint64_t 
 	}
 	uint32_t *h_crc = (uint32_t *)c->h_res, *h_prod = h_crc + n, *h_fb = h_prod + n + n;
 	int32_t *h_st = (int32_t *)(h_prod + n);
+	// the sub-plans (work lists, device tables: ~30 allocations each) of the last pipelined call are kept: a caller that
+	// extracts the same table again (same rows, same options) pays for the copies and the kernels only
+	const bool cached = c->pc_n == n && c->pc_plans.size() == subs.size() && !memcmp(&c->pc_opts, opts, sizeof(*opts)) &&
+		(n == 0 || !memcmp(c->pc_ents.data(), ents, (size_t)n * sizeof(otz_entry)));
+	if (!cached) {
+		for (size_t k = 0; k < c->pc_plans.size(); k++) {
+			otz_plan_destroy(c->pipe[k & 1], c->pc_plans[k]);
+		}
+		c->pc_plans.clear();
+		c->pc_n = 0;
+	}
 	for (auto &sb : subs) {   // all plans first: cudaMalloc / cudaFree must not sit between the asynchronous stages
-		otz_ctx *lc = c->pipe[(&sb - &subs[0]) & 1];
-		if ((rc = otz_plan_create(lc, ents + sb.first, sb.n, opts, &sb.plan))) {
+		const size_t k = &sb - &subs[0];
+		if (cached) {
+			sb.plan = c->pc_plans[k];
+			continue;
+		}
+		if ((rc = otz_plan_create(c->pipe[k & 1], ents + sb.first, sb.n, opts, &sb.plan))) {
 			break;
 		}
 	}
@@ -1386,18 +1418,39 @@ extern "C" int otz_extract_host_ex(otz_ctx *c, const uint8_t *archive, uint64_t 
 			}
 		}
 	}
+	// OTZ_PIPE_TRACE=1: event timestamps of every stage, printed to stderr after the call (evidence for the overlap)
+	const bool trace = getenv("OTZ_PIPE_TRACE") != nullptr;
+	std::vector<cudaEvent_t> tev;
+	if (trace) {
+		tev.resize(subs.size() * 4);
+		for (auto &e : tev) {
+			cudaEventCreate(&e);
+		}
+	}
 	for (size_t k = 0; k < subs.size() && !rc; k++) {
 		OtzSub &sb = subs[k];
 		otz_ctx *lc = c->pipe[k & 1];
 		cudaStream_t st = lc->stream;
+		if (trace) {
+			cudaEventRecord(tev[4 * k], st);
+		}
 		if (sb.a_hi > sb.a_lo) {
 			CK(cudaMemcpyAsync((uint8_t *)c->d_arch_cache + sb.a_lo, archive + sb.a_lo, sb.a_hi - sb.a_lo, cudaMemcpyHostToDevice, st));
+		}
+		if (trace) {
+			cudaEventRecord(tev[4 * k + 1], st);
 		}
 		if ((rc = otz_extract_run(lc, sb.plan, d_arch, archive_len, d_out, need))) {
 			break;
 		}
+		if (trace) {
+			cudaEventRecord(tev[4 * k + 2], st);
+		}
 		if (out && sb.o_hi > sb.o_lo) {
 			CK(cudaMemcpyAsync(out + sb.o_lo, d_out + sb.o_lo, sb.o_hi - sb.o_lo, cudaMemcpyDeviceToHost, st));
+		}
+		if (trace) {
+			cudaEventRecord(tev[4 * k + 3], st);
 		}
 		CK(cudaMemcpyAsync(h_crc + sb.first, sb.plan->d_crc, sb.n * 4ull, cudaMemcpyDeviceToHost, st));
 		CK(cudaMemcpyAsync(h_st + sb.first, sb.plan->d_status, sb.n * 4ull, cudaMemcpyDeviceToHost, st));
@@ -1408,6 +1461,19 @@ extern "C" int otz_extract_host_ex(otz_ctx *c, const uint8_t *archive, uint64_t 
 		cudaError_t e = cudaStreamSynchronize(c->pipe[l]->stream);
 		if (e != cudaSuccess && !rc) {
 			rc = fail_cuda(e, "pipelined extract");
+		}
+	}
+	if (trace) {
+		for (size_t k = 0; k < subs.size() && !rc; k++) {
+			float t[4];
+			for (int j = 0; j < 4; j++) {
+				cudaEventElapsedTime(&t[j], tev[0], tev[4 * k + j]);
+			}
+			fprintf(stderr, "otz pipe: sub %2zu lane %zu rows %6u  in %7.1f MB out %8.1f MB | start %7.2f  h2d-done %7.2f  kernels-done %7.2f  d2h-done %7.2f ms\n", k, k & 1,
+				subs[k].n, (subs[k].a_hi - subs[k].a_lo) / 1e6, (subs[k].o_hi > subs[k].o_lo ? subs[k].o_hi - subs[k].o_lo : 0) / 1e6, t[0], t[1], t[2], t[3]);
+		}
+		for (auto &e : tev) {
+			cudaEventDestroy(e);
 		}
 	}
 	if (!rc) {
@@ -1426,15 +1492,103 @@ extern "C" int otz_extract_host_ex(otz_ctx *c, const uint8_t *archive, uint64_t 
 		}
 	}
 	uint64_t child_launches = 0;
-	for (auto &sb : subs) {
-		otz_ctx *lc = c->pipe[(&sb - &subs[0]) & 1];
-		otz_plan_destroy(lc, sb.plan);
+	if (!rc) {
+		if (!cached) {
+			c->pc_plans.clear();
+			for (auto &sb : subs) {
+				c->pc_plans.push_back(sb.plan);
+			}
+			c->pc_ents.assign(ents, ents + n);
+			c->pc_opts = *opts;
+			c->pc_n = n;
+		}
+	} else {
+		for (auto &sb : subs) {
+			otz_plan_destroy(c->pipe[(&sb - &subs[0]) & 1], sb.plan);
+		}
+		c->pc_plans.clear();
+		c->pc_n = 0;
 	}
 	for (int l = 0; l < 2; l++) {
 		child_launches += c->pipe[l]->launches;
 		c->pipe[l]->launches = 0;
 	}
 	c->launches += child_launches;
+	return rc;
+}
+
+// Multi-GPU host call: entries are independent (otezip.c:399-477), so the table is cut into one contiguous
+// index range per device, balanced by comp + uncomp bytes (otz_partition); every device gets ONLY its byte range of the
+// archive image and of the arena (the offsets of its rows are rebased), runs the pipelined single-device call on its own
+// host thread, and the per-entry results land in the caller's arrays at the rows' positions.  No collective, no peer traffic.
+extern "C" int otz_extract_host_multi(otz_ctx *const *ctxs, uint32_t n_ctx, const uint8_t *archive, uint64_t archive_len, const otz_entry *ents,
+	uint32_t n, const otz_extract_opts *opts, uint8_t *out, uint64_t out_len, uint32_t *crc, int32_t *status, uint32_t *produced) {
+	if (!ctxs || !n_ctx || !ctxs[0] || !opts || (n && !ents)) {
+		return OTZ_ERR_ARG;
+	}
+	bool plain = true;
+	for (uint32_t i = 0; i < n; i++) {
+		plain = plain && !(ents[i].flags & (OTZ_EF_CHUNK | OTZ_EF_PARENT));   // (chunk rows link to table indices: one device)
+	}
+	if (n_ctx == 1 || n < 2 * n_ctx || !plain) {
+		return otz_extract_host_ex(ctxs[0], archive, archive_len, ents, n, opts, out, out_len, crc, status, produced);
+	}
+	std::vector<uint32_t> first(n_ctx + 1);
+	int rc = otz_partition(ents, n, n_ctx, first.data());
+	if (rc) {
+		return rc;
+	}
+	std::vector<int> rcs(n_ctx, OTZ_SUCCESS);
+	std::vector<std::string> errs(n_ctx);
+	std::vector<std::thread> th;
+	for (uint32_t g = 0; g < n_ctx; g++) {
+		const uint32_t a = first[g], cnt = first[g + 1] - first[g];
+		if (!cnt) {
+			continue;
+		}
+		th.emplace_back([=, &rcs, &errs]() {
+			// the part's byte ranges, then its rows rebased onto them
+			uint64_t a_lo = archive_len, a_hi = 0, o_lo = ~0ull, o_hi = 0;
+			for (uint32_t i = a; i < a + cnt; i++) {
+				uint64_t lo, hi;
+				entry_span(archive, archive_len, ents[i], &lo, &hi);
+				a_lo = std::min(a_lo, std::min<uint64_t>(lo, ents[i].lfh_ofs & ~63ull));
+				a_hi = std::max(a_hi, hi);
+				if (!(opts->verify_only && ents[i].method == OTZ_M_STORE)) {
+					o_lo = std::min<uint64_t>(o_lo, ents[i].out_ofs);   // (exact: the copy back must not touch a neighbour's bytes)
+					o_hi = std::max<uint64_t>(o_hi, ents[i].out_ofs + ents[i].uncomp_size);
+				}
+			}
+			if (o_hi <= o_lo) {
+				o_lo = o_hi = 0;
+			}
+			a_hi = std::max(a_hi, a_lo);
+			o_hi = std::min(o_hi, out_len);
+			std::vector<otz_entry> part(ents + a, ents + a + cnt);
+			for (auto &e : part) {
+				// (a row whose header lies outside the image keeps an offset beyond the part: k_resolve reports the range error)
+				e.lfh_ofs = e.lfh_ofs >= a_lo ? e.lfh_ofs - a_lo : ~0ull;
+				e.out_ofs = e.out_ofs >= o_lo ? e.out_ofs - o_lo : ~0ull;
+			}
+			rcs[g] = otz_extract_host_ex(ctxs[g], archive + a_lo, a_hi - a_lo, part.data(), cnt, opts, out ? out + o_lo : nullptr, o_hi - o_lo, crc ? crc + a : nullptr,
+				status ? status + a : nullptr, produced ? produced + a : nullptr);
+			if (rcs[g]) {
+				errs[g] = g_err;
+			}
+		});
+	}
+	for (auto &t : th) {
+		t.join();
+	}
+	uint32_t fb = 0;
+	for (uint32_t g = 0; g < n_ctx; g++) {
+		if (rcs[g] && !rc) {
+			rc = rcs[g];
+			snprintf(g_err, sizeof(g_err), "device %u: %s", g, errs[g].c_str());
+		}
+		fb += ctxs[g]->last_fallbacks;
+	}
+	ctxs[0]->last_fallbacks = fb;
 	return rc;
 }
 

@@ -1,0 +1,271 @@
+"""Round-2 additions on the GPU path: the multi-device host call, the pipelined host call, zip_open_from_source,
+handles that outlive zip_close, directories that claim gigabytes, hostile chunk indexes, and the writer's headers
+byte for byte against the reference's."""
+import ctypes as C
+import os
+import resource
+import struct
+import subprocess
+import time
+import zlib
+
+import numpy as np
+import pytest
+
+from otezip_b200 import Ctx, synth
+from otezip_b200.native import Lib, OtzOpts, default_opts, parse_central
+from otezip_b200.zipapi import ZipApi, ZipT
+from tests import cases
+
+pytestmark = pytest.mark.gpu
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+G = os.path.join(ROOT, "tests", "golden")
+REFDIR = os.path.join(ROOT, "oracle", "_ref")
+
+
+def _multi(ctxs, img, tab, opts=None):
+    """otz_extract_host_multi over the given contexts -> (out, crc, status)"""
+    L = Lib.get().L
+    L.otz_extract_host_multi.argtypes = [C.c_void_p, C.c_uint32, C.c_void_p, C.c_uint64, C.c_void_p, C.c_uint32, C.POINTER(OtzOpts), C.c_void_p,
+                                         C.c_uint64, C.c_void_p, C.c_void_p, C.c_void_p]
+    opts = opts or default_opts()
+    n = len(tab)
+    t = np.ascontiguousarray(tab)
+    out_len = int((t["out_ofs"].astype(np.int64) + t["uncomp_size"]).max()) if n else 0
+    out = np.zeros(max(out_len, 1), dtype=np.uint8)
+    crc = np.zeros(max(n, 1), dtype=np.uint32)
+    st = np.zeros(max(n, 1), dtype=np.int32)
+    buf = np.frombuffer(img, dtype=np.uint8)
+    arr = (C.c_void_p * len(ctxs))(*[c.h for c in ctxs])
+    rc = L.otz_extract_host_multi(arr, len(ctxs), buf.ctypes.data_as(C.c_void_p), buf.nbytes, t.ctypes.data_as(C.c_void_p), n, C.byref(opts),
+                                  out.ctypes.data_as(C.c_void_p), out_len, crc.ctypes.data_as(C.c_void_p), st.ctypes.data_as(C.c_void_p), None)
+    assert rc == 0, Lib.get().L.otz_last_error()
+    return out[:out_len], crc[:n], st[:n]
+
+
+@pytest.mark.parametrize("n_ctx", [2, 3])
+def test_multi_device_call_equals_single_device_call(n_ctx):
+    """otz_extract_host_multi: the table is cut by otz_partition, every context gets only its byte range
+    (rebased rows) and runs on its own host thread.  Contexts may share a device, so one GPU is enough to check that
+    the results — bytes, CRCs, status words, errors included — are those of the single-device call."""
+    ms = cases.mixed_archive(seed=91, n_tiny=80, n_mid=50, n_z=6, n_s=6)
+    ms += [synth.member("big%d" % i, synth.jsonlog_text((1 << 20) + 12345 * i, 60 + i), 8) for i in range(4)]
+    img = bytearray(synth.build_zip(ms))
+    tab = parse_central(bytes(img))
+    for i in (5, 40, 90):   # corrupt a header and two payloads
+        img[int(tab["lfh_ofs"][i]) + (0 if i == 5 else 30 + len(ms[i].name) + 3)] ^= 0x40
+    img = bytes(img)
+    one = Ctx(0)
+    out1, crc1, st1 = one.extract_host(img, tab, default_opts())
+    ctxs = [Ctx(0) for _ in range(n_ctx)]
+    outm, crcm, stm = _multi(ctxs, img, tab)
+    assert np.array_equal(st1, stm)
+    for i in range(len(tab)):
+        if (int(st1[i]) & 0xFF) == 0:
+            o, n = int(tab["out_ofs"][i]), int(tab["uncomp_size"][i])
+            assert np.array_equal(out1[o:o + n], outm[o:o + n]), i
+            assert int(crc1[i]) == int(crcm[i]), i
+    for c in ctxs + [one]:
+        c.close()
+
+
+@pytest.mark.parametrize("pipe_bytes", ["0", "300000", None])
+def test_pipelined_host_call_equals_one_batch(pipe_bytes, oracle):
+    """otz_extract_host cuts a batch into sub-batches that alternate on two lanes (H2D / kernels / D2H overlap).
+    OTZ_PIPE_BYTES=0 turns the pipeline off, 300000 makes dozens of tiny sub-batches."""
+    ms = cases.mixed_archive(seed=92, n_tiny=100, n_mid=60, n_z=8, n_s=8)
+    img = synth.build_zip(ms)
+    tab = parse_central(img)
+    if pipe_bytes is not None:
+        os.environ["OTZ_PIPE_BYTES"] = pipe_bytes
+    try:
+        c = Ctx(0)
+        out, crc, st = c.extract_host(img, tab, default_opts())
+        out2, crc2, st2 = c.extract_host(img, tab, default_opts())      # cached device buffers, second call
+        c.close()
+    finally:
+        os.environ.pop("OTZ_PIPE_BYTES", None)
+    assert np.array_equal(st, st2) and np.array_equal(crc, crc2) and np.array_equal(out, out2)
+    rc, oents = oracle.load_central(img)
+    ost, ocrc, oout, oofs = oracle.extract_all(img, oents)
+    for i in range(len(tab)):
+        ok = (int(st[i]) & 0xFF) == 0 and not (int(st[i]) & 0x300)
+        assert ok == (ost[i] == 0), (i, hex(int(st[i])), int(ost[i]))
+        if ok:
+            n = int(tab["uncomp_size"][i])
+            assert np.array_equal(out[int(tab["out_ofs"][i]):int(tab["out_ofs"][i]) + n], oout[int(oofs[i]):int(oofs[i]) + n]), i
+            assert int(crc[i]) == int(ocrc[i])
+
+
+def _tree(d):
+    out = {}
+    for root, _, fs in os.walk(d):
+        for f in fs:
+            q = os.path.join(root, f)
+            out[os.path.relpath(q, d)] = open(q, "rb").read()
+    return out
+
+
+@pytest.mark.skipif(not os.path.exists(os.path.join(REFDIR, "otezip_relinked")), reason="relinked CLI not built")
+def test_cli_with_several_devices_extracts_the_same_tree(tmp_path):
+    """OTEZIP_DEVICES shards every batch of the libzip read path over several contexts (here: the same GPU three times):
+    the unchanged reference CLI, relinked, must extract what the reference CLI extracts."""
+    z = os.path.join(G, "mixed.zip")
+    outs = {}
+    for tag, exe, env in (("ref", "otezip_ref", {}), ("multi", "otezip_relinked", {"OTEZIP_DEVICES": "0,0,0"}), ("all", "otezip_relinked", {"OTEZIP_DEVICES": "all"})):
+        d = tmp_path / tag
+        d.mkdir()
+        r = subprocess.run([os.path.join(REFDIR, exe), "-x", z, "--verify-crc"], cwd=d, capture_output=True, text=True, timeout=300,
+                           env=dict(os.environ, **env))
+        outs[tag] = (r.returncode, r.stdout, _tree(d))
+    assert outs["ref"][0] == outs["multi"][0] == outs["all"][0] == 0
+    assert outs["ref"][1] == outs["multi"][1] == outs["all"][1]
+    assert outs["ref"][2] == outs["multi"][2] == outs["all"][2] and len(outs["multi"][2]) > 100
+
+
+def test_zip_open_from_source(tmp_path):
+    """otezip.c:1406-1440: an archive held in memory is opened through the temp-file trampoline."""
+    api = ZipApi()
+    L = api.L
+    L.zip_open_from_source.restype = C.POINTER(ZipT)
+    L.zip_open_from_source.argtypes = [C.c_void_p, C.c_int, C.c_void_p]
+    L.zip_source_buffer_create.restype = C.c_void_p
+    L.zip_source_buffer_create.argtypes = [C.c_void_p, C.c_uint64, C.c_int, C.c_void_p]
+    files = [("a.json", synth.jsonlog_text(90000, 1)), ("b.bin", synth.random_bytes(5000, 2)), ("empty", b"")]
+    img = synth.build_zip([synth.member(n, d, 8 if i == 0 else 0) for i, (n, d) in enumerate(files)])
+    buf = C.create_string_buffer(img, len(img))
+    src = L.zip_source_buffer_create(buf, len(img), 0, None)
+    assert src
+    za = L.zip_open_from_source(src, 0, None)
+    assert za and L.zip_get_num_files(za) == 3
+    for i, (n, d) in enumerate(files):
+        assert L.zip_get_name(za, i, 0) == n.encode()
+        zf = L.zip_fopen_index(za, i, 0)
+        assert zf and zf.contents.size == len(d) and C.string_at(zf.contents.data, len(d)) == d
+        L.zip_fclose(zf)
+    assert L.zip_close(za) == 0
+    L.zip_source_free(src)
+    assert not L.zip_open_from_source(None, 0, None)
+    junk = C.create_string_buffer(b"not a zip", 9)
+    s2 = L.zip_source_buffer_create(junk, 9, 0, None)
+    assert not L.zip_open_from_source(s2, 0, None)
+    L.zip_source_free(s2)
+
+
+def test_handle_outlives_zip_close(tmp_path):
+    """In the reference every zip_file_t owns its buffer (otezip.c:1326-1331), so zf->data is still valid after zip_close;
+    here handles point into a batch arena, which therefore has to stay until its last handle is closed."""
+    api = ZipApi()
+    L = api.L
+    d0, d1 = synth.jsonlog_text(200000, 5), synth.jsonlog_text(3000, 6)
+    p = tmp_path / "h.zip"
+    p.write_bytes(synth.build_zip([synth.member("x", d0, 8), synth.member("y", d1, 8)]))
+    err = C.c_int(0)
+    za = L.zip_open(str(p).encode(), 0, C.byref(err))
+    zf0, zf1 = L.zip_fopen_index(za, 0, 0), L.zip_fopen_index(za, 1, 0)
+    assert zf0 and zf1
+    assert L.zip_close(za) == 0
+    junk = [bytearray(os.urandom(1 << 20)) for _ in range(8)]   # churn the heap
+    assert C.string_at(zf0.contents.data, len(d0)) == d0
+    buf = C.create_string_buffer(len(d1))
+    assert L.zip_fread(zf1, buf, len(d1)) == len(d1) and buf.raw == d1
+    assert L.zip_fclose(zf0) == 0 and L.zip_fclose(zf1) == 0
+    del junk
+
+
+def test_directory_claiming_gigabytes_allocates_nothing(tmp_path, capfd):
+    """otezip.c:454-462 rejects an implausible entry BEFORE any allocation.  A 10 KB archive whose 64 entries each claim
+    2 GiB must be answered the same way here: no pinned arena, no device scratch sized by the claim."""
+    api = ZipApi()
+    L = api.L
+    real = b"A" * 40
+    comp = zlib.compress(real, 9)[2:-4]
+    ms = [synth.Member("bomb%d" % i, 8, comp, (2 << 30) - 1 - i, zlib.crc32(real)) for i in range(64)]
+    ms.append(synth.member("fine", synth.jsonlog_text(5000, 1), 8))
+    p = tmp_path / "bomb.zip"
+    p.write_bytes(synth.build_zip(ms))
+    rss0 = resource.getrusage(resource.RUSAGE_SELF).ru_maxrss
+    t0 = time.time()
+    err = C.c_int(0)
+    za = L.zip_open(str(p).encode(), 0, C.byref(err))
+    assert za
+    for i in range(64):
+        assert not L.zip_fopen_index(za, i, 0)
+    zf = L.zip_fopen_index(za, 64, 0)
+    assert zf and C.string_at(zf.contents.data, zf.contents.size) == synth.jsonlog_text(5000, 1)
+    L.zip_fclose(zf)
+    assert L.zip_close(za) == 0
+    assert time.time() - t0 < 20
+    assert resource.getrusage(resource.RUSAGE_SELF).ru_maxrss - rss0 < 600 * 1024      # KiB: far from 64 x 2 GiB
+    assert capfd.readouterr().err.count("rejecting to avoid zipbomb") == 64
+
+
+def _oz_extra(cb, csizes):
+    body = struct.pack("<BBHII", 1, 0, 0, cb, len(csizes)) + b"".join(struct.pack("<I", c) for c in csizes)
+    return struct.pack("<HH", 0x5A4F, len(body)) + body
+
+
+def test_hostile_chunk_index_cannot_change_the_sequential_result(tmp_path, reflib, capfd):
+    """a crafted 'OZ' chunk index must not make this library return other bytes than the reference's
+    sequential decoder.  (1) chunk 0 ends with the stream's FINAL block: the sequential decoder stops there and
+    zero-pads, so the chunk decode (which would happily continue with chunk 1) must be refused.  (2) chunk 0 ends on a
+    Huffman block in the middle of a byte: the sequential decoder reads the next header from the bits left over."""
+    api = ZipApi()
+    part1, part2 = synth.jsonlog_text(65280, 1), synth.jsonlog_text(30000, 2)
+    whole = part1 + part2
+    # (1) two complete streams back to back, labelled as two chunks of one entry
+    s1, s2 = synth.deflate_raw(part1, 6, False), synth.deflate_raw(part2, 6, False)
+    m1 = synth.Member("final_inside", 8, s1 + s2, len(whole), zlib.crc32(whole), extra=_oz_extra(65280, [len(s1), len(s2)]))
+    # (2) chunk 0 = a non-final Huffman block that ends mid-byte (zlib sync flush without its stored block: cut 4 bytes 00 00 FF FF
+    # and the 3 header bits stay in the last byte), chunk 1 = a complete stream
+    co = zlib.compressobj(6, zlib.DEFLATED, -15)
+    a = co.compress(part1) + co.flush(zlib.Z_SYNC_FLUSH)
+    assert a.endswith(b"\x00\x00\xff\xff")
+    a = a[:-4]
+    m2 = synth.Member("midbyte", 8, a + s2, len(whole), zlib.crc32(whole), extra=_oz_extra(65280, [len(a), len(s2)]))
+    good = synth.member("good", whole, 8)
+    p = tmp_path / "hostile.zip"
+    p.write_bytes(synth.build_zip([m1, m2, good]))
+    api.ref_compat.value = 1
+    for verify in (0, 1):
+        err, names, datas = api.read_all(str(p), verify_crc=verify)
+        e2, ref = reflib.extract_file(str(p), verify_crc=verify)
+        assert err == 0 and e2 == 0
+        assert datas == ref, [None if d is None else len(d) for d in datas]
+    capfd.readouterr()
+
+
+@pytest.mark.skipif(not os.path.exists(os.path.join(REFDIR, "otezip_relinked")), reason="relinked CLI not built")
+def test_store_archive_headers_equal_the_reference_writer(tmp_path):
+    """otezip.c:1443-1590: LFH / CDH / EOCD of a STORE-only archive written through this library are, field for field,
+    what the reference writes — every byte except the DOS time and date (the two runs are seconds apart)."""
+    files = {"a.txt": b"hello\n", "b.bin": synth.random_bytes(4096, 3), "dir name/c d.txt": b"x" * 1000, "empty": b""}
+    src = tmp_path / "src"
+    for n, d in files.items():
+        q = src / n
+        q.parent.mkdir(parents=True, exist_ok=True)
+        q.write_bytes(d)
+    blobs = {}
+    for tag, exe in (("ref", "otezip_ref"), ("new", "otezip_relinked")):
+        z = tmp_path / (tag + ".zip")
+        r = subprocess.run([os.path.join(REFDIR, exe), "-c", str(z)] + list(files) + ["-z", "store"], cwd=src, capture_output=True, text=True, timeout=120)
+        assert r.returncode == 0, r.stderr
+        blobs[tag] = bytearray(z.read_bytes())
+    a, b = blobs["ref"], blobs["new"]
+    assert len(a) == len(b)
+    for blob in (a, b):   # blank the time / date fields: LFH +10..13, CDH +12..15
+        pos = 0
+        while True:
+            pos = blob.find(b"PK\x03\x04", pos)
+            if pos < 0:
+                break
+            blob[pos + 10:pos + 14] = b"\0\0\0\0"
+            pos += 30
+        pos = 0
+        while True:
+            pos = blob.find(b"PK\x01\x02", pos)
+            if pos < 0:
+                break
+            blob[pos + 12:pos + 16] = b"\0\0\0\0"
+            pos += 46
+    assert a == b
