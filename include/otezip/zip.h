@@ -184,5 +184,11 @@ extern int otezip_ignore_zipbomb;
 /* B200 build: 1 (default) reproduces the reference inflater's end-of-input rule so that
  * accept/reject is bit-identical; 0 accepts every valid RFC 1951 stream. */
 extern int otezip_ref_compat;
+/* Extension: 1 = zip_close writes every entry in the STREAMING layout — general-purpose flag
+ * bit 3, CRC and sizes zero in the local header and a data descriptor (PK\7\8, CRC-32, sizes) behind the payload —
+ * what a writer to a non-seekable sink has to emit.  The reference's reader tolerates bit 3 (it takes CRC and sizes
+ * from the central directory, otezip.c:355-358, :371-377), and so does this one.  Default 0: the reference's layout.
+ * Also set by the environment variable OTEZIP_DATA_DESCRIPTORS=1. */
+extern int otezip_write_data_descriptors;
 
 #endif /* OTEZIP_H_ */

@@ -104,6 +104,10 @@ int otz_device_count(void);
 int otz_ctx_create(int device, otz_ctx **out);
 void otz_ctx_destroy(otz_ctx *ctx);
 const char *otz_last_error(void);
+/* Debug build only (libotezip_b200_dbg.so, -DOTZ_BOUNDS_CHECK): violations counted by the kernels' software bounds
+ * checks since the library was loaded, one counter per check site; returns the number of counters, -1 when the checks
+ * are not compiled in (the release library). */
+int otz_debug_violations(uint64_t *out, int cap);
 int otz_sm_count(otz_ctx *ctx);
 int otz_pci_bus_id(otz_ctx *ctx, char *buf, int len);   /* for NVML clock sampling */
 

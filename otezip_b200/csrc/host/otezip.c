@@ -40,6 +40,7 @@ uint64_t otezip_max_expansion_ratio = 1000ULL;
 uint64_t otezip_max_expansion_slack = 1024ULL * 1024ULL;
 int otezip_ignore_zipbomb = 0;
 int otezip_ref_compat = 1;
+int otezip_write_data_descriptors = 0;
 
 /* ---- private archive state; `pub` must stay first: zip_t* == struct otz_archive* ---- */
 struct otz_window {               /* one decoded batch of consecutive entries */
@@ -1222,20 +1223,25 @@ int zip_replace(zip_t *za, zip_uint64_t index, zip_source_t *src) {
 }
 
 /* otezip.c:1443-1491 */
-static int write_lfh(FILE *fp, const struct otezip_entry *e, const uint8_t *extra, uint16_t extra_len) {
+static int streaming_layout(void) {
+	const char *e = getenv ("OTEZIP_DATA_DESCRIPTORS");
+	return otezip_write_data_descriptors || (e && *e && *e != '0');
+}
+
+static int write_lfh(FILE *fp, const struct otezip_entry *e, const uint8_t *extra, uint16_t extra_len, int streaming) {
 	uint8_t h[30];
 	uint16_t t, d;
 	size_t nl = strlen (e->name);
 	dos_now (&t, &d); /* the reference re-samples the clock here, otezip.c:1464-1467 */
 	otezip_write_le32 (h, SIG_LFH);
 	otezip_write_le16 (h + 4, 20);
-	otezip_write_le16 (h + 6, 0);
+	otezip_write_le16 (h + 6, streaming ? 0x0008 : 0); /* bit 3: CRC and sizes follow the payload (APPNOTE 4.3.9) */
 	otezip_write_le16 (h + 8, e->method);
 	otezip_write_le16 (h + 10, t);
 	otezip_write_le16 (h + 12, d);
-	otezip_write_le32 (h + 14, e->crc32);
-	otezip_write_le32 (h + 18, e->comp_size);
-	otezip_write_le32 (h + 22, e->uncomp_size);
+	otezip_write_le32 (h + 14, streaming ? 0 : e->crc32);
+	otezip_write_le32 (h + 18, streaming ? 0 : e->comp_size);
+	otezip_write_le32 (h + 22, streaming ? 0 : e->uncomp_size);
 	otezip_write_le16 (h + 26, (uint16_t)nl);
 	otezip_write_le16 (h + 28, extra_len);
 	return fwrite (h, 1, 30, fp) == 30 && fwrite (e->name, 1, nl, fp) == nl &&
@@ -1245,7 +1251,17 @@ static int write_lfh(FILE *fp, const struct otezip_entry *e, const uint8_t *extr
 }
 
 /* otezip.c:1494-1558; a local header beyond 4 GiB is written as the ZIP64 escape + extended information field */
-static uint32_t write_cdh(FILE *fp, const struct otezip_entry *e, uint64_t lfh_ofs) {
+/* data descriptor behind the payload of a streamed entry (APPNOTE 4.3.9, with the customary signature) */
+static int write_descriptor(FILE *fp, const struct otezip_entry *e) {
+	uint8_t h[16];
+	otezip_write_le32 (h, 0x08074b50u);
+	otezip_write_le32 (h + 4, e->crc32);
+	otezip_write_le32 (h + 8, e->comp_size);
+	otezip_write_le32 (h + 12, e->uncomp_size);
+	return fwrite (h, 1, 16, fp) == 16 ? 0 : -1;
+}
+
+static uint32_t write_cdh(FILE *fp, const struct otezip_entry *e, uint64_t lfh_ofs, int streaming) {
 	uint8_t h[46], x[12];
 	size_t nl = strlen (e->name);
 	const int z64 = lfh_ofs >= 0xFFFFFFFFULL;
@@ -1253,6 +1269,7 @@ static uint32_t write_cdh(FILE *fp, const struct otezip_entry *e, uint64_t lfh_o
 	otezip_write_le32 (h, SIG_CDH);
 	otezip_write_le16 (h + 4, 0x031e);
 	otezip_write_le16 (h + 6, z64 ? 45 : 20);
+	otezip_write_le16 (h + 8, streaming ? 0x0008 : 0);
 	otezip_write_le16 (h + 10, e->method);
 	otezip_write_le16 (h + 12, e->file_time);
 	otezip_write_le16 (h + 14, e->file_date);
@@ -1279,6 +1296,7 @@ static uint32_t write_cdh(FILE *fp, const struct otezip_entry *e, uint64_t lfh_o
  * entry in add order, the central directory and the EOCD (otezip.c:1240-1271, :1561-1590). */
 static int finalize_archive(struct otz_archive *a) {
 	zip_t *za = &a->pub;
+	const int streaming = streaming_layout ();
 	/* the entries to write: replaced existing ones and everything added in this session, in index order */
 	zip_uint64_t n_new = 0;
 	zip_uint64_t *idx = (zip_uint64_t *)calloc (za->n_entries ? za->n_entries : 1, sizeof (zip_uint64_t));
@@ -1404,13 +1422,14 @@ static int finalize_archive(struct otz_archive *a) {
 					extra_len = 0;
 				}
 			}
-			int wrc = write_lfh (za->fp, e, extra, extra_len);
+			int wrc = write_lfh (za->fp, e, extra, extra_len, streaming);
 			free (extra);
-			if (wrc != 0 || (out_size[k] && fwrite (out + out_ofs[k], 1, out_size[k], za->fp) != out_size[k])) {
+			if (wrc != 0 || (out_size[k] && fwrite (out + out_ofs[k], 1, out_size[k], za->fp) != out_size[k]) ||
+				(streaming && write_descriptor (za->fp, e) != 0)) {
 				ok = 0;
 				break;
 			}
-			pos += 30 + strlen (e->name) + extra_len + out_size[k];
+			pos += 30 + strlen (e->name) + extra_len + out_size[k] + (streaming ? 16u : 0u);
 		}
 		free (first_chunk);
 		free (n_chunks);
@@ -1422,7 +1441,7 @@ static int finalize_archive(struct otz_archive *a) {
 	{
 		uint64_t cd_size = 0;
 		for (zip_uint64_t i = 0; i < za->n_entries; i++) {
-			cd_size += write_cdh (za->fp, &za->entries[i], entry_lfh (za, i));
+			cd_size += write_cdh (za->fp, &za->entries[i], entry_lfh (za, i), streaming && (!a->n_existing || i >= a->n_existing || (a->pend && a->pend[i].dirty)));
 		}
 		/* otezip.c:1561-1590 truncates the counts to 16 bits and fails beyond 4 GiB (:1264); here the ZIP64 record and
 		 * locator (APPNOTE 4.3.14-4.3.15) are written whenever a field does not fit */

@@ -1,31 +1,24 @@
-// k_inflate2.cuh — two-phase batched raw-DEFLATE (RFC 1951) decoder: one LANE per stream for the entropy
-// stage, one WARP per stream for the LZ77 stage.
+// k_inflate2.cuh — phase B of the two-phase batched raw-DEFLATE (RFC 1951) decoder: the LZ77 executor, plus what the
+// two phases share (table format and builder, token format, segment tables of huge streams).
 //
-// Replaces inflateInit2/inflate/inflateEnd as driven by otezip_extract_entry
-// (/root/reference/src/lib/otezip.c:503-529; decoder src/lib/deflate-dec.inc.c:547-831, "dec" below), like
-// k_inflate.cuh, but splits the decoder the way the work parallelises:
+// Replaces the copy half of inflate() as driven by otezip_extract_entry
+// (/root/reference/src/lib/otezip.c:503-529; decoder src/lib/deflate-dec.inc.c:547-831, "dec" below; the byte-wise
+// window copy is dec:521-545).  The decoder is split the way the work parallelises:
 //
-//   phase A  k_inflate_tok   Huffman decoding is a serial bit chain per stream, so a warp that decodes one
-//            stream spends 32 lanes on one symbol.  Here every lane of a warp owns a different stream: its
-//            own bit reader (64-bit window in registers; the stream is staged through a per-lane shared-memory
-//            ring of eight 16-byte vectors filled by cp.async three vectors ahead), its own 16-bit two-level
-//            tables in shared memory (9-bit / 7-bit roots, 1796 bytes per lane, bank-skewed) and it emits, per
-//            stream, the literal bytes (dense) and one 32-bit sequence record per match
-//            {literal run : 9, length-3 : 8, distance-1 : 15}.  All lanes step in lock-step through straight-
-//            line code — one literal/length look-up and one distance look-up per step, the step software-
-//            pipelined over two iterations (parse step i, emit step i-1), everything unusual behind one warp
-//            vote — so one warp instruction advances up to 28 streams.  Dynamic block headers (dec:122-266) are
-//            parsed by the lanes that need one, all at the same time; the decoding tables are then built by the
-//            whole warp, one lane's block at a time (code lengths in registers, canonical order by match_any
-//            ranks, every table slot computed independently from the 15-bit left-aligned code boundaries).
+//   phase A  k_inflate_spec (k_inflate3.cuh)   entropy decoding: one warp (or, for huge streams, one 4-warp CTA) per
+//            stream, 32 / 128 pieces of the stream decoded speculatively in parallel, synchronised on symbol boundaries;
+//            emits, per stream, the literal bytes (dense) and one 32-bit sequence record per match
+//            {literal run : 9, length-3 : 8, distance-1 : 15}.  The 16-bit two-level tables (9-bit / 7-bit roots) are built
+//            by the warp from the code lengths (i2_build_table below: canonical order by match_any ranks, every table slot
+//            computed independently from the 15-bit left-aligned code boundaries).
 //   phase B  k_inflate_lz    one warp per stream executes the sequences: 32 records per coalesced load, warp
 //            prefix sums give every record its literal and output position; two batches are in flight — while
-//            batch k executes, batch k+1 has been scanned, its match descriptors compacted into near / far
-//            lists and the sources of its far matches (those that left the shared-memory ring) are on their
-//            way into a staging buffer by cp.async — so executing a batch touches shared memory only; near
-//            matches run ring -> ring in stream order; completed 512-byte segments leave as coalesced 16-byte
-//            stores.  The same kernel executes Zstandard sequences (8-byte records, k_zstd.cuh) and the token
-//            chains of segmented huge streams (below).
+//            batch k executes, batch k+1 has been scanned, the descriptor of every match sits in its lane's registers
+//            and the sources of its far matches (those that left the shared-memory ring) are on their way into a
+//            staging buffer behind the ring by cp.async — so executing a batch touches shared memory only; the
+//            matches run in stream order, one shuffle pair and up to 64 elements per step; completed 512-byte
+//            segments leave as coalesced 16-byte stores.  The same kernel executes Zstandard sequences (8-byte
+//            records, k_zstd.cuh) and the segments of huge streams over 16-bit symbols (below).
 //
 // Phase A only commits streams that are plainly valid: final block reached, exactly uncomp_size bytes, regular
 // stored-block headers (their payload joins the literals), tables within the fixed budget.  Anything else (errors,
@@ -41,10 +34,6 @@
 #define I2_DST_ROOT 7
 #define I2_LIT_CAP 704   // 512 root slots + 192 second-level slots
 #define I2_DST_CAP 192   // 128 root slots + 64 second-level slots
-#define I2_LANES 28      // most table slots per warp (4 warps x 28 slots fit the 227 KB of one SM)
-#define I2_SLOT_BYTES 1796   // (704 + 192) * 2 + 4: an odd number of 32-bit words, so equal indices of different lanes hit different banks
-#define I2_LENS_OFS 0        // header parse scratch inside the lane's slot (dead once the tables are built)
-#define I2_PRE_OFS 320
 
 // 16-bit entries.  tb = bits the symbol consumes at this table level INCLUDING its extra bits, so the bit
 // position advances by one field of the entry; what the extra bits mean is worked out off the critical path.
@@ -79,19 +68,6 @@ struct I2TokRes {
 	uint32_t ok;      // 1: phase B executes this stream; 0: it went to the fallback list
 };
 
-struct I2WarpScratch {
-	uint32_t ring[8 * 32 * 4];   // input staging: 8 vectors of 16 bytes per lane, [vector slot][lane][word]
-	uint32_t cnt[16];
-	uint32_t first15[16];   // first canonical code of each length, left-aligned to 15 bits
-	uint32_t limit15[16];   // one past the last code of each length, left-aligned to 15 bits
-	uint32_t offs[16];      // index in sorted[] of the first symbol of each length
-	uint32_t run[16];
-	uint16_t sorted[320];
-	uint16_t len_base[32];    // dec:720-725 by symbol - 257
-	uint16_t dist_base[32];   // dec:766-771 by symbol
-};
-
-#define I2_SMEM_BYTES(lanes) ((int)sizeof(I2WarpScratch) + (int)(lanes) * I2_SLOT_BYTES)
 
 // worst-case scratch of a stream of n output bytes: literals + 4 bytes per match (>= 3 bytes each) + escapes
 __host__ __device__ __forceinline__ uint64_t i2_scratch_bytes(uint64_t n) {
@@ -103,80 +79,6 @@ __device__ __forceinline__ uint32_t i2_len_base(uint32_t v, uint32_t xb) {
 	return v < 8u ? 3u + v : v == 28u ? 258u : 3u + ((4u + (v & 3u)) << xb);
 }
 __device__ __forceinline__ uint32_t i2_dist_base(uint32_t ds, uint32_t xb) { return ds < 4u ? 1u + ds : 1u + ((2u + (ds & 1u)) << xb); }
-
-// ------------------------------------------------------------------------------------------------
-// per-lane bit reader: {lo,hi} is a 64-bit window of the stream, pos < 32 after norm(); nx is the word after hi.
-// The stream is staged through shared memory as 16-byte vectors, eight slots per lane, requested with cp.async
-// three vectors (>= 8 decoding steps) ahead of their first use: in lock-step execution no lane's cache miss stalls
-// the other 31, and a refill is branch-free (two selects and one shared-memory load).
-struct I2Reader {
-	const uint4 *b16;        // 16-byte aligned base of the stream
-	uint32_t nvec;           // vectors that overlap the stream
-	uint32_t wi;             // word index (from b16) of nx
-	uint32_t lo, hi, nx, pos;
-	uint32_t wi_end;         // words_left() = wi_end - wi
-	uint32_t pad_bits;
-	uint32_t fu;             // vectors [0, fu) have been requested
-	volatile uint32_t *col;  // this lane's column of the staging ring (written by cp.async)
-	uint32_t col_sa;         // its shared-window address
-
-	// 32-bit words of the stream not yet moved into {lo,hi} (as BitReader::words_left in k_inflate.cuh)
-	__device__ __forceinline__ int32_t words_left() const { return (int32_t)(wi_end - wi); }
-	__device__ __forceinline__ uint32_t word(uint32_t i) const { return col[((i & 28u) << 5) | (i & 3u)]; }
-	// Keep vectors up to (wi >> 2) + 3 requested; at most one new vector per call, which is enough for one decoding
-	// step (<= 48 bits).  Straight-line: the copy is predicated, not branched around.
-	__device__ __forceinline__ void top() {
-		const uint32_t pred = fu <= (wi >> 2) + 3u;
-		const uint32_t cc = fu < nvec ? fu : nvec;   // never more than one vector past the stream
-		const uint32_t sa = col_sa + ((fu & 7u) << 9);
-		// one (possibly empty) copy group per call: "at most 6 groups pending" then means that everything requested
-		// seven or more steps ago has landed — a vector is requested at least 8 steps before its first word is read
-		asm volatile(
-			"{\n\t.reg .pred p;\n\tsetp.ne.u32 p, %2, 0;\n\t@p cp.async.cg.shared.global [%0], [%1], 16;\n\t}\n\t"
-			"cp.async.commit_group;\n\tcp.async.wait_group 6;" ::"r"(sa),
-			"l"(b16 + cc), "r"(pred));
-		fu += pred;
-	}
-	__device__ __forceinline__ void init(const uint8_t *p, uint64_t nbytes) {
-		const uint64_t a = reinterpret_cast<uint64_t>(p);
-		const uint32_t skipb = (uint32_t)(a & 3), i0 = (uint32_t)(a & 15) >> 2;
-		b16 = reinterpret_cast<const uint4 *>(a & ~15ull);
-		const uint32_t nw = (uint32_t)((skipb + nbytes + 3) >> 2);
-		nvec = (i0 + nw + 3) >> 2;
-		pad_bits = (uint32_t)(((uint64_t)nw << 5) - ((skipb + nbytes) << 3));
-		// (a restart in the middle of a stream — behind a stored block, at a chunk — must not race with copies that are
-		// still on their way into the same slots)
-		asm volatile("cp.async.wait_group 0;" ::: "memory");
-		for (fu = 0; fu < 4u; fu++) {
-			const uint32_t cc = fu < nvec ? fu : nvec;
-			const uint32_t sa = col_sa + ((fu & 7u) << 9);
-			asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n\tcp.async.commit_group;" ::"r"(sa), "l"(b16 + cc) : "memory");
-		}
-		asm volatile("cp.async.wait_group 0;" ::: "memory");
-		lo = word(i0);
-		hi = word(i0 + 1);
-		wi = i0 + 2;
-		nx = word(wi);
-		wi_end = wi + nw - 2u;
-		pos = 8 * skipb;
-	}
-	// pos < 64 on entry; the caller keeps the staging ring ahead with top()
-	__device__ __forceinline__ void norm() {
-		const bool p = pos >= 32u;
-		lo = p ? hi : lo;
-		hi = p ? nx : hi;
-		pos &= 31u;
-		wi += p;
-		nx = word(wi);
-	}
-	// for the (branchy, rare) header code: refill check + norm
-	__device__ __forceinline__ void norm_hdr() {
-		top();
-		norm();
-	}
-	__device__ __forceinline__ uint32_t peek() const { return __funnelshift_r(lo, hi, pos); }
-	__device__ __forceinline__ int64_t remaining_bits() const { return ((int64_t)words_left() << 5) + 64 - (int64_t)pos - (int64_t)pad_bits; }
-};
 
 // ------------------------------------------------------------------------------------------------
 // Warp-cooperative build of one two-level table from code lengths held in registers.
@@ -350,15 +252,12 @@ __device__ __noinline__ int i2_build_table(WS &S, const uint32_t (&lens)[10], ui
 }
 
 // ------------------------------------------------------------------------------------------------
-// Segmented decode of HUGE streams.  A stream advances one symbol per step wherever it is decoded, so one 16 MiB entry
-// (1.1 M symbols) sets the critical path of a whole batch.  Its entropy stage, however, only needs to know where
-// blocks start: k_block_search tests every bit offset of the stream for a plausible dynamic-block header (the
-// checks are so selective that false positives are practically absent), each candidate becomes a SEGMENT that a lane
-// of k_inflate_tok<true> decodes from its candidate to the next live one, and k_seg_stitch accepts the stream only if
-// the segments chain exactly (each one ends where the next starts, the last one with the final block, the sizes add
-// up, no match reaches before the stream).  Tokens do not care where they were produced: k_inflate_lz walks the
-// chain.  Nothing depends on the search being right — a wrong candidate is skipped (the decoder that passes it marks
-// it dead) or fails the chain, and the stream then goes to k_inflate like every other declined stream.
+// HUGE streams.  One warp executing the sequences of a 16 MiB entry one after the other would set the critical path
+// of a whole batch (~100 ms), so phase A cuts the token stream of a huge entry into SEGMENTS (at round boundaries,
+// each behind a match, >= 256 KiB of output; it knows every output position) and fills the tables below; k_seg_stitch
+// checks the chain once more (the sizes add up, no match reaches before the stream) and places the segments in the
+// symbol buffer; k_inflate_lz<.., PAR> executes every segment on its own warp over 16-bit symbols.  A chain that does
+// not close sends the stream to k_inflate like every other declined stream.
 #define I2_MAXSEG 256
 #define I2_PREWIN 32768u   // elements of history a segment may refer to (DEFLATE window)
 #define I2_SEGF_OK 1u
@@ -376,12 +275,9 @@ struct I2SegRes {
 };
 
 struct I2SegCtl {
-	uint32_t *count;     // [n_huge] candidates found / segments of the stream
-	uint32_t *start;     // [n_huge][I2_MAXSEG] start bit of every segment, ascending, [0] = 0
-	uint32_t *bucket;    // [n_huge][I2_MAXSEG] first candidate in every 1/255 of the stream (0xFFFFFFFF = none)
+	uint32_t *count;     // [n_huge] segments of the stream
+	uint32_t *start;     // [n_huge][I2_MAXSEG] start mark of every segment, ascending, [0] = 0 (= end mark of the one before)
 	I2SegRes *res;       // [n_huge][I2_MAXSEG]
-	uint32_t *items;     // compact work list: stream << 16 | segment
-	uint32_t *n_items;
 	uint32_t *live;      // [n_huge][I2_MAXSEG] the chain of segments that make up the stream
 	uint32_t *nlive;     // [n_huge] length of the chain (0 = the stream was declined)
 	int32_t *seg_status; // [n_huge] status word of an accepted stream
@@ -395,936 +291,6 @@ struct I2SegCtl {
 	uint64_t sym_cap;    // its capacity (0 = no parallel execution)
 	uint32_t out_mis;    // address of the output arena & 15
 };
-
-// ------------------------------------------------------------------------------------------------
-// lane states
-#define I2_S_IDLE 0u     // needs a stream
-#define I2_S_HDR 1u      // at a block header
-#define I2_S_BUILD 2u    // code lengths parsed into the slot; waiting for the cooperative table build
-#define I2_S_DEC 3u      // decoding symbols
-#define I2_S_DONE 4u     // no more work
-#define I2_S_COPY 5u     // at the payload of a stored block; waiting for the cooperative copy
-
-__device__ __forceinline__ uint32_t i2_ld_le16(const uint8_t *p) { return (uint32_t)p[0] | ((uint32_t)p[1] << 8); }
-
-// what a lane has to do after i2_header()
-#define I2_A_NONE 0u       // still at a block header (an empty stored / fixed block was consumed)
-#define I2_A_BUILD 1u      // code lengths are in the slot: build the tables, then decode
-#define I2_A_COMMIT 2u     // the stream (or chunk) ended here
-#define I2_A_FALLBACK 3u   // k_inflate takes the stream
-#define I2_A_STORED 4u     // a stored block with payload: st_src / st_len say where it is
-
-// dec:811-816 as k_inflate evaluates it: after a step that leaves the stream unfinished
-#define I2_HDR_STEP_CHECK()                               \
-	if (br.words_left() <= 1) {                           \
-		const int64_t rem_ = br.remaining_bits();         \
-		if (rem_ < 0) {                                   \
-			return I2_A_FALLBACK;                         \
-		} else if (rem_ < 8) {                            \
-			ref_eob = 1u;                                 \
-		}                                                 \
-	}
-
-// One block header (dec:613-627) of the lane's stream: stored blocks (dec:269-319; the payload of a non-empty one is
-// copied by the whole warp afterwards), fixed (dec:322-349) and dynamic (dec:122-266) code lengths into the lane's
-// slot.  Lanes run this in lock-step.
-__device__ __forceinline__ uint32_t i2_header(I2Reader &br, uint8_t *slot, const uint8_t *in, uint32_t comp, uint32_t rflags, uint32_t &final_blk,
-	uint32_t &ref_eob, uint32_t &hlit, uint32_t &hdist, uint32_t &st_src, uint32_t &st_len) {
-	const bool chunk_mid = (rflags & OTZ_EF_CHUNK) && !(rflags & OTZ_EF_LAST_CHUNK);
-	br.norm_hdr();
-	uint32_t bits = br.peek();
-	final_blk = bits & 1u;
-	const uint32_t btype = (bits >> 1) & 3u;
-	br.pos += 3;
-	I2_HDR_STEP_CHECK();
-	if (chunk_mid && final_blk) {
-		return I2_A_FALLBACK;   // a final block inside a chunk that is not the last: k_inflate fails the chunk
-	}
-	if (btype == 0) {
-		// stored block (dec:269-319).  Anything irregular — a bad length pair, a payload that runs past the input — is
-		// left to k_inflate, which knows what the reference answers
-		const int64_t rem = br.remaining_bits();
-		const uint64_t bpos = (uint64_t)comp - (uint64_t)(rem >> 3);
-		if ((uint64_t)comp - bpos < 4 || (i2_ld_le16(in + bpos) ^ i2_ld_le16(in + bpos + 2)) != 0xFFFFu) {
-			return I2_A_FALLBACK;
-		} else if (i2_ld_le16(in + bpos) != 0u) {
-			st_len = i2_ld_le16(in + bpos);
-			st_src = (uint32_t)(bpos + 4);
-			if ((uint64_t)comp - (bpos + 4) < st_len) {
-				return I2_A_FALLBACK;
-			} else {
-				return I2_A_STORED;
-			}
-		} else {
-			const uint64_t npos = bpos + 4;
-			br.init(in + npos, (uint64_t)comp - npos);
-			if (final_blk) {
-				return I2_A_COMMIT;
-			} else if (npos >= comp) {
-				if (chunk_mid) {
-					return I2_A_COMMIT;   // end of this chunk
-				} else {
-					return I2_A_FALLBACK;   // unfinished stream out of input
-				}
-			}
-		}
-	} else if (btype == 3) {
-		return I2_A_FALLBACK;   // dec:657-658
-	} else if (btype == 1) {
-		br.norm_hdr();
-		if ((br.peek() & 127u) == 0u) {
-			// empty fixed block (zlib's Z_FINISH tail): end-of-block is the 7-bit code 0000000
-			br.pos += 7;
-			if (final_blk) {
-				return I2_A_COMMIT;
-			} else {
-				I2_HDR_STEP_CHECK();
-			}
-		} else {
-			uint8_t *lens = slot + I2_LENS_OFS;   // dec:322-349
-			for (int i = 0; i < 320; i++) {
-				lens[i] = i < 144 ? 8 : i < 256 ? 9 : i < 280 ? 7 : i < 288 ? 8 : 5;
-			}
-			hlit = 288;
-			hdist = 32;
-			return I2_A_BUILD;
-		}
-	} else {
-		// dynamic block header, dec:122-266
-		uint8_t *lens = slot + I2_LENS_OFS;
-		uint8_t *pre = slot + I2_PRE_OFS;
-		br.norm_hdr();
-		bits = br.peek();
-		hlit = (bits & 31u) + 257u;
-		hdist = ((bits >> 5) & 31u) + 1u;
-		const uint32_t hclen = ((bits >> 10) & 15u) + 4u;
-		br.pos += 14;
-		bool bad = hlit > 286u || hdist > 30u;
-		uint64_t cl = 0;    // 19 code-length-code lengths, 3 bits each
-		uint64_t cnt = 0;   // packed byte counters per length
-		for (uint32_t i = 0; i < hclen; i++) {
-			br.norm_hdr();
-			const uint32_t v = br.peek() & 7u;
-			br.pos += 3;
-			cl |= (uint64_t)v << (3u * c_cl_order[i]);
-			cnt += 1ull << (8u * v);
-		}
-		uint64_t next = 0;   // packed next canonical code per length
-		{
-			int left = 1;
-			uint32_t code = 0;
-			for (uint32_t l = 1; l <= 7; l++) {
-				const uint32_t c = (uint32_t)(cnt >> (8u * l)) & 0xFFu;
-				left = (left << 1) - (int)c;
-				bad |= left < 0;
-				code = (code + (l > 1 ? (uint32_t)(cnt >> (8u * (l - 1))) & 0xFFu : 0u)) << 1;
-				next |= (uint64_t)(code & 0xFFu) << (8u * l);
-			}
-			bad |= left != 0;   // the code-length code must be complete
-		}
-		if (!bad) {
-			for (uint32_t s = 0; s < 19; s++) {
-				const uint32_t l = (uint32_t)(cl >> (3u * s)) & 7u;
-				if (l) {
-					const uint32_t c = (uint32_t)(next >> (8u * l)) & 0xFFu;
-					next += 1ull << (8u * l);
-					const uint32_t rev = __brev(c) >> (32u - l);
-					for (uint32_t x = rev; x < 128u; x += (1u << l)) {
-						pre[x] = (uint8_t)(s | (l << 5));
-					}
-				}
-			}
-			const uint32_t total = hlit + hdist;
-			uint32_t idx = 0, prev = 0;
-			while (idx < total) {
-				br.norm_hdr();
-				bits = br.peek();
-				const uint32_t e = pre[bits & 127u];
-				const uint32_t sym = e & 31u, cb = e >> 5;
-				if (sym < 16u) {
-					br.pos += cb;
-					lens[idx++] = (uint8_t)sym;
-					prev = sym;
-					continue;
-				}
-				uint32_t rep, val = 0;
-				if (sym == 16u) {   // dec:209-219
-					if (idx == 0) {
-						bad = true;
-						break;
-					}
-					val = prev;
-					rep = 3u + ((bits >> cb) & 3u);
-					br.pos += cb + 2;
-				} else if (sym == 17u) {   // dec:221-228
-					rep = 3u + ((bits >> cb) & 7u);
-					br.pos += cb + 3;
-				} else {   // dec:230-237
-					rep = 11u + ((bits >> cb) & 127u);
-					br.pos += cb + 7;
-				}
-				if (idx + rep > total) {
-					bad = true;   // dec:244
-					break;
-				}
-				for (uint32_t i = 0; i < rep; i++) {
-					lens[idx + i] = (uint8_t)val;
-				}
-				idx += rep;
-				prev = val;
-			}
-			for (uint32_t i = total; i < 320u; i++) {
-				lens[i] = 0;
-			}
-			bad |= !bad && lens[256] == 0;   // no end-of-block code
-		}
-		if (bad || br.remaining_bits() < 0) {
-			return I2_A_FALLBACK;
-		} else {
-			return I2_A_BUILD;
-		}
-	}
-		return I2_A_NONE;
-}
-#undef I2_HDR_STEP_CHECK
-
-// phase A.  grid: persistent, one warp per CTA; the first `lanes_active` (<= I2_LANES) lanes of every warp pull list
-// indices from *work_counter.  (Few streams are spread over all resident warps rather than packed into few:
-// a lock-step step costs the same whatever the number of live lanes.)
-// SEG: the work items are the segments of huge streams (`list`, `tok_ofs` index those streams; see I2SegCtl).
-template <bool SEG>
-__global__ void __launch_bounds__(32) k_inflate_tok(const uint8_t *__restrict__ archive, const otz_entry *__restrict__ ents,
-	const OtzEntryState *__restrict__ est, const int32_t *__restrict__ status, const uint32_t *__restrict__ list, uint32_t n_list,
-	uint32_t *__restrict__ work_counter, uint8_t *__restrict__ scratch, const uint64_t *__restrict__ tok_ofs, I2TokRes *__restrict__ tokres,
-	uint32_t *__restrict__ fb_list, uint32_t *__restrict__ fb_count, uint32_t lanes_active, I2SegCtl seg) {
-	if (SEG) {
-		n_list = *seg.n_items;
-	}
-	extern __shared__ __align__(16) uint8_t smem_raw[];
-	const uint32_t lane = threadIdx.x;
-	// shared memory: the warp scratch, then `lanes_active` table slots.  Lanes without a slot never become active;
-	// their (predicated-off) table reads go to slot 0
-	I2WarpScratch &WS = *reinterpret_cast<I2WarpScratch *>(smem_raw);
-	uint8_t *const slots = smem_raw + sizeof(I2WarpScratch);
-	uint8_t *const slot = slots + (lane < lanes_active ? lane : 0u) * I2_SLOT_BYTES;
-	const uint16_t *const lit = reinterpret_cast<const uint16_t *>(slot);
-	const uint16_t *const dst = lit + I2_LIT_CAP;
-
-	{
-		const uint32_t xl = (lane < 8u || lane == 28u) ? 0u : (lane - 4u) >> 2, xd = lane < 4u ? 0u : (lane - 2u) >> 1;
-		WS.len_base[lane] = (uint16_t)(lane < 29u ? i2_len_base(lane, xl) : 0u);
-		WS.dist_base[lane] = (uint16_t)(lane < 30u ? i2_dist_base(lane, xd) : 0u);
-	}
-	__syncwarp();
-	uint32_t state = lane < lanes_active ? I2_S_IDLE : I2_S_DONE;
-	I2Reader br;
-	// lanes that never get a stream still run the (predicated-off) refill logic: give them a harmless source
-	br.b16 = reinterpret_cast<const uint4 *>(reinterpret_cast<uint64_t>(archive) & ~15ull);
-	br.nvec = br.wi = br.lo = br.hi = br.nx = br.pos = br.pad_bits = br.wi_end = 0;
-	br.fu = 8;   // nothing to request
-	br.col = WS.ring + lane * 4u;
-	br.col_sa = (uint32_t)__cvta_generic_to_shared(WS.ring + lane * 4u);
-	const uint8_t *in = nullptr;
-	uint32_t comp = 0, cap = 0, rflags = 0, k = 0, ei = 0;
-	// output bytes so far = nl + mb; the current literal run = nl - nl0
-	uint32_t nl = 0, nl0 = 0, mb = 0, nseq = 0;
-	uint8_t *litp = nullptr;
-	uint32_t *seqp = nullptr;
-	uint32_t final_blk = 0, ref_eob = 0, hlit = 0, hdist = 0;
-	uint32_t st_src = 0, st_len = 0;   // payload of the stored block the lane stands at (offset in the stream, bytes)
-	// step parsed but not yet emitted (software pipeline of the decode loop): entries and bit windows
-	bool pv = false;
-	uint32_t pe = 0, pd = 0, pb = 0, pb2 = 0;
-	// SEG: stream / segment of this lane, the next candidate start, bytes a match reached before the segment
-	uint32_t sh = 0, sj = 0, sjn = 0, s_next = 0xFFFFFFFFu, s_own = 0, reach = 0;
-	uint8_t *seq_floor = nullptr;   // SEG: the records must stay above the literals (scr_lo .. scr_hi is a guess)
-
-// leave the current stream: FALLBACK = hand it to k_inflate, COMMIT = release it to phase B
-// (SEG: the segment is left without the OK flag / with its result; k_seg_stitch decides about the stream)
-#define I2_FALLBACK()                                                     \
-	do {                                                                  \
-		if (!SEG) {                                                       \
-			fb_list[atomicAdd(fb_count, 1u)] = ei;                        \
-			tokres[k].ok = 0u;                                            \
-		}                                                                 \
-		state = I2_S_IDLE;                                                \
-	} while (0)
-#define I2_SEG_COMMIT(final_)                                                               \
-	do {                                                                                    \
-		const int64_t rem_c = br.remaining_bits();                                          \
-		if (rem_c >= 0) {                                                                   \
-			I2SegRes *r_ = &seg.res[sh * I2_MAXSEG + sj];                                   \
-			r_->nseq = nseq;                                                                \
-			r_->nlit = nl;                                                                  \
-			r_->produced = nl + mb;                                                         \
-			r_->end_bit = (uint32_t)((int64_t)comp * 8 - rem_c);                            \
-			r_->reach = reach;                                                              \
-			atomicOr(&r_->flags, I2_SEGF_OK | ((final_) ? I2_SEGF_FINAL : 0u) | (ref_eob ? I2_SEGF_REF_EOB : 0u)); \
-		}                                                                                   \
-		state = I2_S_IDLE;                                                                  \
-	} while (0)
-#define I2_COMMIT()                                                                         \
-	do {                                                                                    \
-		if (SEG) {                                                                          \
-			I2_SEG_COMMIT(true);                                                            \
-		} else if (br.remaining_bits() < 0 || nl + mb != cap) {                             \
-			I2_FALLBACK();                                                                  \
-		} else {                                                                            \
-			I2TokRes r;                                                                     \
-			r.nseq = nseq;                                                                  \
-			r.nlit = nl;                                                                    \
-			r.status = (rflags & OTZ_EF_CHUNK) ? OTZ_ST_OK : (OTZ_ST_OK | (ref_eob ? OTZ_STF_REF_EOB : 0)); \
-			r.ok = 1u;                                                                      \
-			tokres[k] = r;                                                                  \
-			state = I2_S_IDLE;                                                              \
-		}                                                                                   \
-	} while (0)
-// dec:811-816 as k_inflate evaluates it: after a step that leaves the stream unfinished
-#define I2_STEP_CHECK()                                   \
-	if (br.words_left() <= 1) {                             \
-		const int64_t rem_ = br.remaining_bits();         \
-		if (rem_ < 0) {                                   \
-			I2_FALLBACK();                                \
-		} else if (rem_ < 8) {                            \
-			ref_eob = 1u;                                 \
-		}                                                 \
-	}
-// one literal byte / one match into the stream's token scratch
-#define I2_EMIT_LIT(byte_)                      \
-	do {                                        \
-		litp[nl] = (uint8_t)(byte_);            \
-		nl++;                                   \
-	} while (0)
-#define I2_EMIT_MATCH(run_, len_, dist_)                                              \
-	do {                                                                              \
-		*--seqp = (run_) | (((len_) - 3u) << 9) | (((dist_) - 1u) << 17);             \
-		nseq++;                                                                       \
-		nl0 = nl;                                                                     \
-		mb += (len_);                                                                 \
-	} while (0)
-
-	for (;;) {
-		// ---- (1) hand streams to idle lanes
-		{
-			const uint32_t idle = __ballot_sync(0xFFFFFFFFu, state == I2_S_IDLE);
-			if (idle) {
-				uint32_t base = 0;
-				if (lane == (uint32_t)(__ffs(idle) - 1)) {
-					base = atomicAdd(work_counter, (uint32_t)__popc(idle));
-				}
-				base = __shfl_sync(0xFFFFFFFFu, base, __ffs(idle) - 1);
-				if (state == I2_S_IDLE) {
-					k = base + __popc(idle & ((1u << lane) - 1u));
-					if (k >= n_list) {
-						state = I2_S_DONE;
-					} else if (SEG) {
-						const uint32_t item = seg.items[k];
-						sh = item >> 16;
-						sj = item & 0xFFFFu;
-						ei = list[sh];
-						const otz_entry e = ents[ei];
-						in = archive + est[ei].data_ofs;
-						comp = e.comp_size;
-						cap = e.uncomp_size;
-						rflags = e.flags;
-						const uint32_t cnt = seg.count[sh];
-						s_own = seg.start[sh * I2_MAXSEG + sj];
-						sjn = sj + 1;
-						s_next = sjn < cnt ? seg.start[sh * I2_MAXSEG + sjn] : 0xFFFFFFFFu;
-						I2SegRes *r_ = &seg.res[sh * I2_MAXSEG + sj];
-						litp = scratch + r_->scr_lo;
-						seq_floor = litp;
-						seqp = reinterpret_cast<uint32_t *>(scratch + r_->scr_hi);
-						nl = nl0 = mb = nseq = 0;
-						ref_eob = 0;
-						reach = 0;
-						pv = false;
-						if (r_->scr_hi - r_->scr_lo >= 128u) {
-							br.init(in + (s_own >> 3), (uint64_t)comp - (s_own >> 3));
-							br.pos += s_own & 7u;
-							state = I2_S_HDR;
-						}   // else: two candidates a few bits apart, no room for tokens — the segment simply fails (stays idle)
-					} else {
-						ei = list[k];
-						if (OTZ_ST_CODE(status[ei]) == OTZ_ST_OK) {
-							const otz_entry e = ents[ei];
-							in = archive + est[ei].data_ofs;
-							comp = e.comp_size;
-							cap = e.uncomp_size;
-							rflags = e.flags;
-							litp = scratch + tok_ofs[k];
-							seqp = reinterpret_cast<uint32_t *>(scratch + tok_ofs[k + 1]);
-							nl = nl0 = mb = nseq = 0;
-							ref_eob = 0;
-							if (comp == 0) {
-								I2_FALLBACK();   // dec:610: k_inflate answers TRUNCATED
-							} else {
-								br.init(in, comp);
-								state = I2_S_HDR;
-							}
-						} else {
-							tokres[k].ok = 0u;   // failed in k_resolve: nothing to decode (stays idle, picks the next one)
-						}
-					}
-				}
-			}
-			if (__all_sync(0xFFFFFFFFu, state == I2_S_DONE)) {
-				break;
-			}
-		}
-		// ---- (2) block headers (dec:613-627), every lane that stands at one, in lock-step
-		if (SEG && state == I2_S_HDR) {
-			// a block boundary: the segment ends where the next live candidate starts; candidates it has run past
-			// were false (or inside a block) and are marked dead
-			const uint32_t P = (uint32_t)((int64_t)comp * 8 - br.remaining_bits());
-			if (P != s_own) {
-				const uint32_t cnt = seg.count[sh];
-				while (P > s_next) {
-					atomicOr(&seg.res[sh * I2_MAXSEG + sjn].flags, I2_SEGF_DEAD);
-					sjn++;
-					s_next = sjn < cnt ? seg.start[sh * I2_MAXSEG + sjn] : 0xFFFFFFFFu;
-				}
-				if (P == s_next) {
-					I2_SEG_COMMIT(false);
-				}
-			}
-		}
-		if (state == I2_S_HDR) {
-			const uint32_t act_ = i2_header(br, slot, in, comp, rflags, final_blk, ref_eob, hlit, hdist, st_src, st_len);
-			if (act_ == I2_A_BUILD) {
-				state = I2_S_BUILD;
-			} else if (act_ == I2_A_STORED) {
-				state = I2_S_COPY;
-			} else if (act_ == I2_A_COMMIT) {
-				I2_COMMIT();
-			} else if (act_ == I2_A_FALLBACK) {
-				I2_FALLBACK();
-			}
-		}
-		// ---- (2b) tables, one requesting lane at a time, whole warp
-		{
-			uint32_t need = __ballot_sync(0xFFFFFFFFu, state == I2_S_BUILD);
-			while (need) {
-				const int x = __ffs(need) - 1;
-				need &= need - 1;
-				__syncwarp();
-				const uint8_t *xl = slots + x * I2_SLOT_BYTES + I2_LENS_OFS;
-				uint32_t lens[10];
-#pragma unroll
-				for (int j = 0; j < 10; j++) {
-					lens[j] = xl[32 * j + lane];
-				}
-				__syncwarp();
-				const uint32_t xh = __shfl_sync(0xFFFFFFFFu, hlit, x), xd = __shfl_sync(0xFFFFFFFFu, hdist, x);
-				uint16_t *xt = reinterpret_cast<uint16_t *>(slots + x * I2_SLOT_BYTES);
-				int r = i2_build_table<false, I2_LIT_ROOT, I2_LIT_CAP>(WS, lens, 0u, xh, xt);
-				if (!r) {
-					r = i2_build_table<true, I2_DST_ROOT, I2_DST_CAP>(WS, lens, xh, xd, xt + I2_LIT_CAP);
-				}
-				__syncwarp();
-				if ((int)lane == x) {
-					if (r) {
-						I2_FALLBACK();
-					} else {
-						state = I2_S_DEC;
-						I2_STEP_CHECK();
-					}
-				}
-			}
-		}
-		// ---- (2c) payloads of stored blocks (dec:269-319), one requesting lane at a time, whole warp: the bytes join the
-		// literals of the stream (a run of more than 511 literals becomes escape records when the next match is emitted)
-		{
-			uint32_t need = __ballot_sync(0xFFFFFFFFu, state == I2_S_COPY);
-			while (need) {
-				const int x = __ffs(need) - 1;
-				need &= need - 1;
-				bool room = nl + mb + st_len <= cap;   // (else k_inflate reports the overflow, dec:296-300)
-				if (SEG) {
-					room = room && (int64_t)((uint8_t *)seqp - (seq_floor + nl)) >= (int64_t)st_len + (int64_t)(4u * ((nl - nl0 + st_len) / I2_SEQ_ESC)) + 64;
-				}
-				room = __shfl_sync(0xFFFFFFFFu, (int)room, x) != 0;
-				const uint32_t xlen = __shfl_sync(0xFFFFFFFFu, st_len, x);
-				const uint8_t *sp = reinterpret_cast<const uint8_t *>(__shfl_sync(0xFFFFFFFFu, (unsigned long long)reinterpret_cast<uint64_t>(in + st_src), x));
-				uint8_t *dp = reinterpret_cast<uint8_t *>(__shfl_sync(0xFFFFFFFFu, (unsigned long long)reinterpret_cast<uint64_t>(litp + nl), x));
-				if (room) {
-#pragma unroll 4
-					for (uint32_t i = lane; i < xlen; i += 32) {
-						dp[i] = sp[i];
-					}
-				}
-				__syncwarp();
-				if ((int)lane == x) {
-					if (!room) {
-						I2_FALLBACK();
-					} else {
-						nl += st_len;
-						const uint64_t npos = (uint64_t)st_src + st_len;
-						const bool chunk_mid = (rflags & OTZ_EF_CHUNK) && !(rflags & OTZ_EF_LAST_CHUNK);
-						br.init(in + npos, (uint64_t)comp - npos);
-						if (final_blk) {
-							I2_COMMIT();
-						} else if (npos >= comp) {
-							if (chunk_mid) {
-								I2_COMMIT();   // end of this chunk
-							} else {
-								I2_FALLBACK();   // unfinished stream out of input
-							}
-						} else {
-							state = I2_S_HDR;
-						}
-					}
-				}
-			}
-		}
-		// ---- (3) symbols (dec:662-799).  One literal/length symbol and — used by the lanes that got a length —
-		// one distance symbol per step, as straight-line code: every lane runs the same instructions.  A step is
-		// software-pipelined over two iterations: iteration i PARSES step i (bit position, two table lookups — the
-		// serial chain of the stream) and EMITS step i-1 (length/distance arithmetic, bounds, token stores) from the
-		// entries and bit windows saved in registers, so the two dependency chains interleave in the one warp.
-		// Everything unusual (second-level tables, end of block, long literal runs, errors, end of input) is left
-		// untouched by the main path and finished, lane by lane, behind ONE warp vote at the end of the iteration.
-		while (__all_sync(0xFFFFFFFFu, state == I2_S_DEC || state == I2_S_DONE) && __any_sync(0xFFFFFFFFu, state == I2_S_DEC)) {
-			bool leave = false;
-#pragma unroll 1
-			for (int burst = 0; burst < 64 && !leave; burst++) {
-				const bool act = state == I2_S_DEC;
-				// ---- emit step i-1
-				bool e_special;
-				{
-					const uint32_t tb = pe & 15u, kind = (pe >> 4) & 3u, xb = (pe >> 6) & 7u, v = (pe >> 9) & 31u;
-					const uint32_t length = WS.len_base[v] + ((pb >> (tb - xb)) & ((1u << xb) - 1u));
-					const uint32_t tb2 = pd & 31u, dxb = (pd >> 5) & 15u, ds = (pd >> 9) & 31u;
-					const uint32_t dist = WS.dist_base[ds] + ((pb2 >> (tb2 - dxb)) & ((1u << dxb) - 1u));
-					const uint32_t run = nl - nl0, opos = nl + mb;
-					const bool e_lit = pv && kind == I2_K_LIT, e_len = pv && kind == I2_K_LEN;
-					// SEG (not the first segment): the output position in the stream is unknown; remember how far back
-					// the matches reach instead (k_seg_stitch checks it against the position the chain gives)
-					const bool e_ok = e_len && run < I2_SEQ_ESC && (SEG ? (s_own != 0u || dist <= opos) : dist <= opos);
-					if (SEG && e_ok && dist > opos) {
-						reach = max(reach, dist - opos);
-					}
-					if (e_lit) {
-						I2_EMIT_LIT((pe >> 6) & 0xFFu);
-					}
-					if (e_ok) {
-						I2_EMIT_MATCH(run, length, dist);
-					}
-					// (the token scratch has room for the one literal or record that may exceed `cap` here)
-					pv = e_len && !e_ok;   // still pending only if the special path has to finish it
-					e_special = pv || (act && (nl + mb > cap || (SEG && (uint8_t *)seqp - (seq_floor + nl) < 32)));
-				}
-				// ---- parse step i
-				br.top();
-				br.norm();
-				const uint32_t bits = br.peek();
-				const uint32_t e = lit[bits & ((1u << I2_LIT_ROOT) - 1u)];
-				const uint32_t kind = (e >> 4) & 3u;
-				br.pos += act ? (e & 15u) : 0u;   // (0 for a LINK entry)
-				br.norm();
-				const uint32_t bits2 = br.peek();
-				const uint32_t d = dst[bits2 & ((1u << I2_DST_ROOT) - 1u)];
-				const bool p_len = act && kind == I2_K_LEN, p_root = (d >> 14) == 0u;
-				br.pos += (p_len && p_root) ? (d & 31u) : 0u;
-				const bool p_plain = act && (kind == I2_K_LIT || (p_len && p_root));
-				const bool special = e_special || (act && (!p_plain || br.words_left() <= 1));
-				if (__any_sync(0xFFFFFFFFu, special)) {
-					if (special) {
-						bool bad = false;
-						// -- finish step i-1 (a match after >= 511 literals, or an error)
-						if (pv) {
-							const uint32_t tb = pe & 15u, xb = (pe >> 6) & 7u, v = (pe >> 9) & 31u;
-							const uint32_t length = WS.len_base[v] + ((pb >> (tb - xb)) & ((1u << xb) - 1u));
-							const uint32_t tb2 = pd & 31u, dxb = (pd >> 5) & 15u, ds = (pd >> 9) & 31u;
-							const uint32_t dist = WS.dist_base[ds] + ((pb2 >> (tb2 - dxb)) & ((1u << dxb) - 1u));
-							uint32_t r3 = nl - nl0;
-							if ((dist > nl + mb && !(SEG && s_own != 0u)) ||
-								(SEG && (uint8_t *)seqp - (seq_floor + nl) < (int64_t)(4u * (r3 / I2_SEQ_ESC) + 32u))) {
-								bad = true;   // reaches before the start of the output (strict; dec:785 does not check) / slice full
-							} else {
-								if (SEG && dist > nl + mb) {
-									reach = max(reach, dist - (nl + mb));
-								}
-								while (r3 >= I2_SEQ_ESC) {
-									*--seqp = I2_SEQ_ESC;
-									nseq++;
-									r3 -= I2_SEQ_ESC;
-								}
-								I2_EMIT_MATCH(r3, length, dist);
-							}
-							pv = false;
-						}
-						bad = bad || nl + mb > cap;   // dec:700-703, dec:791-793
-						bad = bad || (SEG && (uint8_t *)seqp - (seq_floor + nl) < 32);   // the guessed scratch slice is full
-						// -- step i, when it is not a plain literal / root-level match: decode and emit it here
-						bool eob = false;
-						if (!bad && act && !p_plain) {
-							bool want_dist = p_len;   // (then the length code is consumed, the distance code is not)
-							uint32_t len2 = 0;
-							if (p_len) {
-								const uint32_t tb = e & 15u, xb = (e >> 6) & 7u;
-								len2 = WS.len_base[(e >> 9) & 31u] + ((bits >> (tb - xb)) & ((1u << xb) - 1u));
-							} else if (kind == I2_K_EOB) {
-								eob = true;
-							} else {
-								// second-level literal/length table
-								const uint32_t sb = I2_LIT_LINK_BITS(e);
-								if (sb == 0u) {
-									bad = true;   // dec:693-695: no code matches
-								} else {
-									const uint32_t e2 = lit[I2_LIT_LINK_OFS(e) + ((bits >> I2_LIT_ROOT) & ((1u << sb) - 1u))];
-									const uint32_t k2 = (e2 >> 4) & 3u, t2 = e2 & 15u;
-									if (k2 == I2_K_LINK) {
-										bad = true;
-									} else {
-										br.pos += I2_LIT_ROOT + t2;
-										if (k2 == I2_K_LIT) {
-											I2_EMIT_LIT((e2 >> 6) & 0xFFu);
-											bad = nl + mb > cap;
-										} else if (k2 == I2_K_EOB) {
-											eob = true;
-										} else {
-											const uint32_t x2 = (e2 >> 6) & 7u;
-											len2 = WS.len_base[(e2 >> 9) & 31u] + ((bits >> (I2_LIT_ROOT + t2 - x2)) & ((1u << x2) - 1u));
-											want_dist = true;
-										}
-									}
-								}
-							}
-							if (!bad && want_dist) {
-								br.norm_hdr();
-								const uint32_t b3 = br.peek();
-								uint32_t dd = dst[b3 & ((1u << I2_DST_ROOT) - 1u)];
-								uint32_t used = 0;
-								if ((dd >> 14) != 0u) {
-									const uint32_t sb = I2_DST_LINK_BITS(dd);
-									if (sb == 0u) {
-										bad = true;   // dec:762-764
-									} else {
-										dd = dst[I2_DST_LINK_OFS(dd) + ((b3 >> I2_DST_ROOT) & ((1u << sb) - 1u))];
-										used = I2_DST_ROOT;
-										bad = (dd >> 14) != 0u;
-									}
-								}
-								if (!bad) {
-									const uint32_t t3 = dd & 31u, x3 = (dd >> 5) & 15u;
-									const uint32_t dist3 = WS.dist_base[(dd >> 9) & 31u] + ((b3 >> (used + t3 - x3)) & ((1u << x3) - 1u));
-									br.pos += used + t3;
-									uint32_t r3 = nl - nl0;
-									if ((dist3 > nl + mb && !(SEG && s_own != 0u)) ||
-										(SEG && (uint8_t *)seqp - (seq_floor + nl) < (int64_t)(4u * (r3 / I2_SEQ_ESC) + 32u))) {
-										bad = true;
-									} else {
-										if (SEG && dist3 > nl + mb) {
-											reach = max(reach, dist3 - (nl + mb));
-										}
-										while (r3 >= I2_SEQ_ESC) {
-											*--seqp = I2_SEQ_ESC;
-											nseq++;
-											r3 -= I2_SEQ_ESC;
-										}
-										I2_EMIT_MATCH(r3, len2, dist3);
-										bad = nl + mb > cap;
-									}
-								}
-							}
-						}
-						if (bad) {
-							I2_FALLBACK();
-						} else if (eob) {
-							// end of block, dec:711-716 (pos already stands behind the code)
-							if (final_blk) {
-								I2_COMMIT();
-							} else {
-								state = I2_S_HDR;
-								I2_STEP_CHECK();
-							}
-						} else if (act) {
-							I2_STEP_CHECK();
-						}
-					}
-					leave = __any_sync(0xFFFFFFFFu, state != I2_S_DEC && state != I2_S_DONE);
-				}
-				// step i waits for the next iteration if it is plain and its lane is still decoding
-				pv = pv || (p_plain && state == I2_S_DEC);
-				pe = p_plain ? e : pe;
-				pd = p_plain ? d : pd;
-				pb = p_plain ? bits : pb;
-				pb2 = p_plain ? bits2 : pb2;
-			}
-		}
-	}
-#undef I2_FALLBACK
-#undef I2_SEG_COMMIT
-#undef I2_COMMIT
-#undef I2_STEP_CHECK
-#undef I2_EMIT_LIT
-#undef I2_EMIT_MATCH
-}
-
-// ------------------------------------------------------------------------------------------------
-// k_block_search: one thread per byte of a huge stream tests its 8 bit offsets for a dynamic-block header:
-// BTYPE = 2, HLIT <= 29, HDIST <= 29, a complete code-length code (Kraft sum), then — for the ~0.1 % that get this
-// far — the code lengths themselves: exactly HLIT + HDIST of them, an end-of-block code, complete literal/length
-// and distance codes.  grid: (ceil(max comp / 256), n_huge).
-__device__ __forceinline__ uint32_t i2_bits_at(const uint8_t *p, uint64_t bit, uint32_t n) {   // n <= 24
-	// two aligned words and one funnel shift (the image is padded: the word behind the stream is readable)
-	const uint64_t a = reinterpret_cast<uint64_t>(p) + (bit >> 3);
-	const uint32_t *w = reinterpret_cast<const uint32_t *>(a & ~3ull);
-	const uint32_t sh = (uint32_t)(a & 3ull) * 8u + (uint32_t)(bit & 7u);   // <= 31
-	return __funnelshift_r(__ldg(w), __ldg(w + 1), sh) & ((1u << n) - 1u);
-}
-
-__device__ __noinline__ bool i2_plausible_header(const uint8_t *in, uint64_t nbits, uint64_t p, uint32_t hlit, uint32_t hdist, uint32_t hclen) {
-	// (in + nbits/8 + 4 is readable: the image is padded)
-	uint8_t pre[128];
-	uint32_t cl[19];
-	uint64_t q = p + 17;
-	for (uint32_t i = 0; i < 19; i++) {
-		cl[i] = 0;
-	}
-	for (uint32_t i = 0; i < hclen; i++) {
-		cl[c_cl_order[i]] = i2_bits_at(in, q, 3);
-		q += 3;
-	}
-	uint32_t next[8], cnt[8];
-	for (int l = 0; l < 8; l++) {
-		cnt[l] = 0;
-	}
-	for (uint32_t i = 0; i < 19; i++) {
-		cnt[cl[i]]++;
-	}
-	uint32_t code = 0;
-	cnt[0] = 0;
-	for (int l = 1; l < 8; l++) {
-		code = (code + cnt[l - 1]) << 1;
-		next[l] = code;
-	}
-	for (uint32_t sym = 0; sym < 19; sym++) {
-		const uint32_t l = cl[sym];
-		if (l) {
-			const uint32_t c = next[l]++;
-			const uint32_t rev = __brev(c) >> (32u - l);
-			for (uint32_t x = rev; x < 128u; x += (1u << l)) {
-				pre[x] = (uint8_t)(sym | (l << 5));
-			}
-		}
-	}
-	const uint32_t total = hlit + hdist;
-	uint32_t idx = 0, prev = 0;
-	uint32_t kl = 0, kd = 0, nd = 0;   // Kraft sums (units of 2^-15), distance codes used
-	bool eob = false;
-	while (idx < total) {
-		if (q + 14 > nbits) {
-			return false;
-		}
-		const uint32_t bits = i2_bits_at(in, q, 14);
-		const uint32_t e = pre[bits & 127u];
-		const uint32_t sym = e & 31u, cb = e >> 5;
-		uint32_t rep = 1, val = sym;
-		if (sym < 16u) {
-			q += cb;
-			prev = sym;
-		} else if (sym == 16u) {
-			if (idx == 0) {
-				return false;
-			}
-			val = prev;
-			rep = 3u + ((bits >> cb) & 3u);
-			q += cb + 2;
-		} else if (sym == 17u) {
-			val = 0;
-			rep = 3u + ((bits >> cb) & 7u);
-			q += cb + 3;
-			prev = 0;
-		} else {
-			val = 0;
-			rep = 11u + ((bits >> cb) & 127u);
-			q += cb + 7;
-			prev = 0;
-		}
-		if (idx + rep > total) {
-			return false;
-		}
-		if (val) {
-			for (uint32_t i = 0; i < rep; i++) {
-				const uint32_t sidx = idx + i;
-				if (sidx < hlit) {
-					kl += 32768u >> val;
-					eob = eob || sidx == 256u;
-				} else {
-					kd += 32768u >> val;
-					nd++;
-				}
-			}
-			if (kl > 32768u || kd > 32768u) {
-				return false;   // over-subscribed: what most false candidates are after a few dozen lengths
-			}
-		}
-		idx += rep;
-	}
-	return eob && kl == 32768u && (kd == 32768u || nd <= 1u);
-}
-
-// grid: persistent (any size); task t = 256 consecutive bytes of one stream, task_ofs[h] = first task of stream h.
-// Every thread tests the 8 bit offsets of its byte: BTYPE = 2, HLIT <= 29, HDIST <= 29, and the Kraft sum
-// of the code-length code — its (HCLEN + 4) 3-bit lengths are looked up four at a time in a 4096-entry table of
-// sum(2^(7 - len)), saturated at 255 — must be exactly 128 (a complete code; zlib never emits another one).
-__global__ void __launch_bounds__(256) k_block_search(const uint8_t *__restrict__ archive, const otz_entry *__restrict__ ents,
-	const OtzEntryState *__restrict__ est, const int32_t *__restrict__ status, const uint32_t *__restrict__ list, uint32_t n_huge,
-	const uint32_t *__restrict__ task_ofs, uint2 *__restrict__ surv, uint32_t surv_cap, uint32_t *__restrict__ n_surv) {
-	__shared__ uint8_t s_kraft[4096];
-	for (uint32_t i = threadIdx.x; i < 4096u; i += blockDim.x) {
-		uint32_t sum = 0;
-#pragma unroll
-		for (int f = 0; f < 4; f++) {
-			const uint32_t l = (i >> (3 * f)) & 7u;
-			sum += l ? (128u >> l) : 0u;
-		}
-		s_kraft[i] = (uint8_t)min(sum, 255u);
-	}
-	__syncthreads();
-	const uint32_t n_tasks = task_ofs[n_huge];
-	for (uint32_t t = blockIdx.x; t < n_tasks; t += gridDim.x) {
-		// stream of this task: the last h with task_ofs[h] <= t
-		uint32_t lo_h = 0, hi_h = n_huge;
-		while (hi_h - lo_h > 1) {
-			const uint32_t mid = (lo_h + hi_h) >> 1;
-			if (task_ofs[mid] <= t) {
-				lo_h = mid;
-			} else {
-				hi_h = mid;
-			}
-		}
-		const uint32_t h = lo_h;
-		const uint32_t ei = list[h];
-		if (OTZ_ST_CODE(status[ei]) != OTZ_ST_OK) {
-			continue;
-		}
-		const uint32_t comp = ents[ei].comp_size;
-		const uint32_t byte = (t - task_ofs[h]) * 256u + threadIdx.x;
-		if (byte + 12u > comp) {
-			continue;   // a block header needs more than that; the tail belongs to the last segment anyway
-		}
-		// 12 bytes from `byte` on, as aligned words (the image is padded) shifted into place
-		const uint8_t *q = archive + est[ei].data_ofs + byte;
-		const uint32_t sh = (uint32_t)(reinterpret_cast<uint64_t>(q) & 3u) * 8u;
-		const uint32_t *qw = reinterpret_cast<const uint32_t *>(q - (sh >> 3));
-		const uint32_t w0 = __ldg(qw), w1 = __ldg(qw + 1), w2 = __ldg(qw + 2), w3 = __ldg(qw + 3);
-		const uint32_t b0 = __funnelshift_r(w0, w1, sh), b1 = __funnelshift_r(w1, w2, sh), b2 = __funnelshift_r(w2, w3, sh);
-		// first the header fields of all 8 offsets (22 % pass), then the Kraft sums of those that passed
-		uint32_t cand = 0;
-#pragma unroll
-		for (uint32_t o = 0; o < 8u; o++) {
-			const uint32_t x0 = __funnelshift_r(b0, b1, o);
-			const bool head = ((x0 >> 1) & 3u) == 2u && ((x0 >> 3) & 31u) <= 29u && ((x0 >> 8) & 31u) <= 29u;
-			cand |= head ? (1u << o) : 0u;
-		}
-		uint32_t hits = 0;
-		while (cand) {
-			const uint32_t o = __ffs(cand) - 1u;
-			cand &= cand - 1u;
-			// bits o .. o + 80 of the 96 loaded ones: header word (17 bits) and the 57 bits behind it
-			const uint32_t x0 = __funnelshift_r(b0, b1, o), x1 = __funnelshift_r(b1, b2, o), x2 = b2 >> o;
-			const uint32_t hc = ((x0 >> 13) & 15u) + 4u;
-			const uint64_t v2 = (((uint64_t)__funnelshift_r(x1, x2, 17) << 32) | __funnelshift_r(x0, x1, 17)) & ((1ull << (3u * hc)) - 1ull);
-			const uint32_t lo32 = (uint32_t)v2, hi32 = (uint32_t)(v2 >> 32);
-			const uint32_t kr = (uint32_t)s_kraft[lo32 & 4095u] + s_kraft[(lo32 >> 12) & 4095u] + s_kraft[__funnelshift_r(lo32, hi32, 24) & 4095u] +
-				s_kraft[(hi32 >> 4) & 4095u] + s_kraft[(hi32 >> 16) & 4095u];
-			hits |= kr == 128u ? (1u << o) : 0u;
-		}
-		if (byte == 0) {
-			hits &= ~1u;   // bit 0 is the stream's own start
-		}
-		// survivors (~0.1 % of the offsets) go to a list: checking their code lengths here, one lane at a time,
-		// would cost more than everything else together
-		while (hits) {
-			const uint32_t o = __ffs(hits) - 1u;
-			hits &= hits - 1u;
-			const uint32_t at = atomicAdd(n_surv, 1u);
-			if (at < surv_cap) {
-				surv[at] = make_uint2(h, byte * 8u + o);
-			}
-		}
-	}
-}
-
-// second stage of the search: one thread per surviving offset decodes the code lengths of the would-be header
-__global__ void __launch_bounds__(256) k_block_verify(const uint8_t *__restrict__ archive, const otz_entry *__restrict__ ents,
-	const OtzEntryState *__restrict__ est, const uint32_t *__restrict__ list, const uint2 *__restrict__ surv, uint32_t surv_cap,
-	const uint32_t *__restrict__ n_surv, I2SegCtl seg) {
-	const uint32_t n = min(*n_surv, surv_cap);
-	for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
-		const uint2 sv = surv[i];
-		const uint32_t h = sv.x, ei = list[h];
-		const uint8_t *in = archive + est[ei].data_ofs;
-		const uint32_t w = i2_bits_at(in, sv.y, 17);
-		if (i2_plausible_header(in, (uint64_t)ents[ei].comp_size * 8u, sv.y, ((w >> 3) & 31u) + 257u, ((w >> 8) & 31u) + 1u, ((w >> 13) & 15u) + 4u)) {
-			const uint32_t at = atomicAdd(&seg.count[h], 1u);
-			if (at < I2_MAXSEG - 1u) {
-				seg.start[h * I2_MAXSEG + 1u + at] = sv.y;
-			}
-			// for streams with more candidates than that: the first one of every 1/255 of the stream, so that the
-			// segments stay evenly spaced
-			const uint32_t bucket = (uint32_t)(((uint64_t)sv.y * (I2_MAXSEG - 1u)) / ((uint64_t)ents[ei].comp_size * 8u));
-			atomicMin(&seg.bucket[h * I2_MAXSEG + 1u + min(bucket, (uint32_t)I2_MAXSEG - 2u)], sv.y);
-		}
-	}
-}
-
-// One thread per huge stream: candidates (all of them, or the first one of every bucket when there are more than 255) in
-// ascending order behind the true start (bit 0), result rows cleared, every
-// segment gets a slice of the stream's token scratch in proportion to its share of the compressed bits, and the
-// segments are appended to the work list.
-__global__ void k_seg_prepare(const otz_entry *__restrict__ ents, const uint32_t *__restrict__ list, uint32_t n_huge,
-	const uint64_t *__restrict__ tok_ofs, I2SegCtl seg) {
-	const uint32_t h = blockIdx.x * blockDim.x + threadIdx.x;
-	if (h >= n_huge) {
-		return;
-	}
-	uint32_t *st = seg.start + h * I2_MAXSEG;
-	uint32_t n = seg.count[h];
-	st[0] = 0;
-	if (n <= I2_MAXSEG - 1u) {
-		for (uint32_t i = 2; i <= n; i++) {   // insertion sort of st[1..n]
-			const uint32_t v = st[i];
-			uint32_t j = i;
-			while (j > 1 && st[j - 1] > v) {
-				st[j] = st[j - 1];
-				j--;
-			}
-			st[j] = v;
-		}
-		n += 1;
-	} else {
-		const uint32_t *bk = seg.bucket + h * I2_MAXSEG;
-		n = 1;
-		for (uint32_t b = 1; b < I2_MAXSEG; b++) {   // the buckets are in ascending order by construction
-			const uint32_t v = bk[b];
-			if (v != 0xFFFFFFFFu) {
-				st[n++] = v;
-			}
-		}
-	}
-	seg.count[h] = n;
-	seg.nlive[h] = 0;
-	seg.par[h] = 0;
-	const uint32_t ei = list[h];
-	const double bits_total = (double)ents[ei].comp_size * 8.0;
-	const uint64_t base = tok_ofs[h], total = tok_ofs[h + 1] - tok_ofs[h];
-	const uint32_t at = atomicAdd(seg.n_items, n);
-	uint64_t lo = base;
-	for (uint32_t j = 0; j < n; j++) {
-		const uint64_t hi = j + 1 < n ? base + ((uint64_t)((double)total * ((double)st[j + 1] / bits_total)) & ~15ull) : base + total;
-		I2SegRes r;
-		r.nseq = r.nlit = r.produced = r.end_bit = r.reach = r.flags = 0;
-		r.scr_lo = lo;
-		r.scr_hi = hi;
-		seg.res[h * I2_MAXSEG + j] = r;
-		seg.items[at + j] = (h << 16) | j;
-		lo = hi;
-	}
-}
 
 // One thread per huge stream: follow the chain of segments.  The stream is accepted (nlive > 0) only if every link
 // fits; otherwise it is appended to the fallback list of k_inflate.
@@ -1555,7 +521,8 @@ struct I2Ring {
 	static constexpr uint32_t SEG = 512;
 	// output bytes per batch.  W >= 2 * SPAN_MAX + SEG + 258 guarantees that a far source of batch k+1 has been
 	// flushed to HBM before batch k starts (when its copy is issued).
-	static constexpr uint32_t SPAN_MAX = W >= 8192 ? 2048u : 1024u;
+	static constexpr uint32_t SPAN_MAX = W >= 8192 ? 2048u : 1024u;   // (>= 769: a batch always takes at least one record)
+	static_assert(W >= 4096, "the ring must hold two batches, a flush segment and one match (see above)");
 };
 
 template <int W, typename T = uint8_t>
@@ -1599,6 +566,8 @@ __device__ __noinline__ void i2_copy_periodic(T *rb, uint32_t dq, uint32_t sq, u
 		r = r >= dd ? r - dd : r;
 	}
 }
+
+__device__ __forceinline__ uint32_t i2_ld_le16(const uint8_t *p) { return (uint32_t)p[0] | ((uint32_t)p[1] << 8); }
 
 // what the scan of one batch leaves in registers for its execution
 struct I2Batch {
@@ -1690,6 +659,7 @@ __device__ __forceinline__ I2Batch i2_scan_batch(I2LzSmem<W, T> &S, int buf, uin
 		if (is_far) {
 			if (incl <= STAGE_VECS) {
 				const uint32_t cst = incl - nch;
+				OTZ_CHK(VEC * cst + soff + ml <= I2Elem<T>::STAGE, OTZ_CK_LZ_STAGE);
 				B.mb = (uint32_t)W + (uint32_t)buf * I2Elem<T>::STAGE + VEC * cst + soff;
 				// every lane fetches the vectors of its own match (cp.async groups are per thread: the executor waits for
 				// its own group and then syncs the warp)
@@ -1764,6 +734,10 @@ __global__ void __launch_bounds__(128) k_inflate_lz(uint8_t *__restrict__ out, c
 		// PAR: linear position I2_PREWIN is the segment's first element; the markers sit below it
 		T *const gbase = dstp - mis - (PAR ? I2_PREWIN : 0u);
 		uint32_t q = mis + (PAR ? I2_PREWIN : 0u), qf = q;   // linear write position / position up to which HBM holds the data
+#ifdef OTZ_BOUNDS_CHECK
+		// (linear position behind the last element this work item may write)
+		const uint32_t q_limit = q + (PAR ? seg.res[k * I2_MAXSEG + seg.live[k * I2_MAXSEG + par_c]].produced : e.uncomp_size);
+#endif
 		if (PAR) {
 			// marker for the element m places before the segment: 256 + (I2_PREWIN - m).  HBM gets all the matches can
 			// reach, the ring the part of them a near match can address.
@@ -1861,6 +835,8 @@ __global__ void __launch_bounds__(128) k_inflate_lz(uint8_t *__restrict__ out, c
 					if ((int32_t)a >= 0) {
 						const uint32_t len = a >> 16, dq = a & 0xFFFFu;
 						T v0 = 0, v1 = 0;
+						OTZ_CHK(len == 0u || (dq + len <= (uint32_t)W && bsrc + len <= (uint32_t)W + 2u * I2Elem<T>::STAGE && (bsrc >= (uint32_t)W || bsrc + len <= (uint32_t)W)),
+							len && dq + len > (uint32_t)W ? OTZ_CK_LZ_RING_DST : OTZ_CK_LZ_RING_SRC);
 						if (lane < len) {
 							v0 = rb[bsrc + lane];
 						}
@@ -1898,6 +874,7 @@ __global__ void __launch_bounds__(128) k_inflate_lz(uint8_t *__restrict__ out, c
 				__syncwarp();
 				const uint32_t qa = q & ~(SEGB - 1u);
 				if (qa > qf) {
+					OTZ_CHK(qa <= q_limit, OTZ_CK_LZ_FLUSH);
 					i2_flush_range<W, T>(gbase, rb, qf, qa, lane);
 					qf = qa;
 					__syncwarp();
@@ -1917,6 +894,7 @@ __global__ void __launch_bounds__(128) k_inflate_lz(uint8_t *__restrict__ out, c
 				__syncwarp();
 				const uint32_t qa = q & ~(SEGB - 1u);
 				if (qa > qf) {
+					OTZ_CHK(qa <= q_limit, OTZ_CK_LZ_FLUSH);
 					i2_flush_range<W, T>(gbase, rb, qf, qa, lane);
 					qf = qa;
 					__syncwarp();
@@ -1924,6 +902,7 @@ __global__ void __launch_bounds__(128) k_inflate_lz(uint8_t *__restrict__ out, c
 			}
 		}   // segments
 		if (q > qf) {
+			OTZ_CHK(q <= q_limit, OTZ_CK_LZ_FLUSH);
 			i2_flush_range<W, T>(gbase, rb, qf, q, lane);
 		}
 		if (!PAR && lane == 0) {

@@ -225,8 +225,8 @@ __device__ __forceinline__ void i3_scan2(I3Smem<NW> &S, uint32_t lane, uint32_t 
 
 // grid: persistent.  NW = 1: I3_WARPS independent warps per CTA, one stream each; NW > 1: the NW warps of a CTA
 // decode one (huge) stream together.  Every group pulls list slots [k0, k1) from *work_counter (longest streams first).
-template <int NW>
-__global__ void __launch_bounds__(32 * (NW == 1 ? I3_WARPS : NW), NW == 1 ? 8 : 16 / NW) k_inflate_spec(const uint8_t *__restrict__ archive,
+template <int NW, int MINB = (NW == 1 ? 8 : 16 / NW)>
+__global__ void __launch_bounds__(32 * (NW == 1 ? I3_WARPS : NW), MINB) k_inflate_spec(const uint8_t *__restrict__ archive,
 	const otz_entry *__restrict__ ents, const OtzEntryState *__restrict__ est, const int32_t *__restrict__ status, const uint32_t *__restrict__ list,
 	uint32_t k0, uint32_t k1, uint32_t *__restrict__ work_counter, uint8_t *__restrict__ scratch, const uint64_t *__restrict__ tok_ofs,
 	I2TokRes *__restrict__ tokres, uint32_t *__restrict__ fb_list, uint32_t *__restrict__ fb_count, uint32_t n_huge, I2SegCtl seg) {
@@ -479,6 +479,7 @@ __global__ void __launch_bounds__(32 * (NW == 1 ? I3_WARPS : NW), NW == 1 ? 8 : 
 					act = I3_A_FALLBACK;   // k_inflate reports the overflow (dec:296-300)
 					break;
 				}
+				OTZ_CHK((uint64_t)st_src + st_len <= comp && litp + nl_tot + st_len <= reinterpret_cast<uint8_t *>(seq_end - nseq_tot), OTZ_CK_SPEC_STORED);
 				for (uint32_t i = tid; i < st_len; i += G) {
 					litp[nl_tot + i] = in[st_src + i];
 				}
@@ -563,6 +564,8 @@ __global__ void __launch_bounds__(32 * (NW == 1 ? I3_WARPS : NW), NW == 1 ? 8 : 
 						const uint32_t kd = i3_step<0>(lit, dst, pw, q, Pend, nx, v_, d_);
 						if (on) {
 							const uint32_t bit = q - base, w = bit >> 5;
+							OTZ_CHK(bit < S_bits && (q >> 5) - (w0 + tid * wpl) <= wpl, OTZ_CK_SPEC_PIECE);
+							OTZ_CHK(w < wpl, OTZ_CK_SPEC_VIS);
 							if (w != curw) {
 								vis[curw * G + tid] = curmask;
 								curw = w;
@@ -607,6 +610,7 @@ __global__ void __launch_bounds__(32 * (NW == 1 ? I3_WARPS : NW), NW == 1 ? 8 : 
 						const uint32_t kd = i3_step<0>(lit, dst, pw, q, Pend, nx, v_, d_);
 						if (on) {
 							const uint32_t bit = q - base;
+							OTZ_CHK(bit < S_bits && (q >> 5) - (w0 + tid * wpl) <= wpl, OTZ_CK_SPEC_PIECE);
 							if ((vis[(bit >> 5) * G + tid] >> (bit & 31u)) & 1u) {
 								hit = true;
 								on = false;
@@ -669,6 +673,7 @@ __global__ void __launch_bounds__(32 * (NW == 1 ? I3_WARPS : NW), NW == 1 ? 8 : 
 						uint32_t nx, v_, d_;
 						const uint32_t kd = i3_step<1>(lit, dst, pw, q, Pend, nx, v_, d_);
 						if (on) {
+							OTZ_CHK(q >= R && q - base < S_bits && (q >> 5) - (w0 + tid * wpl) <= wpl, OTZ_CK_SPEC_PIECE);
 							const bool isl = kd == I2_K_LEN, isb = kd == I2_K_LIT;
 							lead = (isl && nm == 0u) ? since : lead;
 							nl += isb;
@@ -738,7 +743,9 @@ __global__ void __launch_bounds__(32 * (NW == 1 ? I3_WARPS : NW), NW == 1 ? 8 : 
 						const uint32_t kd = i3_step<2>(lit, dst, pw, q, Pend, nx, v_, d_);
 						if (on) {
 							const bool isl = kd == I2_K_LEN, isb = kd == I2_K_LIT;
+							OTZ_CHK(q >= R && q - base < S_bits && (q >> 5) - (w0 + tid * wpl) <= wpl, OTZ_CK_SPEC_PIECE);
 							if (isb) {
+								OTZ_CHK(lp >= litp && lp < reinterpret_cast<uint8_t *>(seq_end), OTZ_CK_SPEC_LIT);
 								*lp++ = (uint8_t)v_;
 							}
 							if (isl) {
@@ -748,6 +755,7 @@ __global__ void __launch_bounds__(32 * (NW == 1 ? I3_WARPS : NW), NW == 1 ? 8 : 
 									*--sp = I2_SEQ_ESC;
 									run -= I2_SEQ_ESC;
 								}
+								OTZ_CHK(sp > reinterpret_cast<uint32_t *>(litp + nl_tot + tot_nl) && sp <= seq_end, OTZ_CK_SPEC_SEQ);
 								*--sp = run | ((v_ - 3u) << 9) | ((d_ - 1u) << 17);
 							}
 							run = isl ? 0u : run + isb;
@@ -793,6 +801,7 @@ __global__ void __launch_bounds__(32 * (NW == 1 ? I3_WARPS : NW), NW == 1 ? 8 : 
 				block_done = lastk == I2_K_EOB;
 				// HUGE: close a segment behind the last match once it is long enough
 				if (huge && (ob_tot - run_carry) - sg_out0 >= sg_target && nseg < I2_MAXSEG - 2u) {
+					OTZ_CHK(nseg + 1u < I2_MAXSEG, OTZ_CK_SEG_TABLE);
 					if (tid == 0) {
 						I2SegRes r;
 						r.nseq = nseq_tot - sg_seq0;

@@ -9,6 +9,38 @@
 
 namespace cg = cooperative_groups;
 
+// ---------------------------------------------------------------- software bounds checks (debug build)
+// compute-sanitizer is not available on the GPU pool this was developed on, so the kernels written with unmasked /
+// word-granular / per-lane indexed accesses carry their own checks: `make debug` builds libotezip_b200_dbg.so with
+// -DOTZ_BOUNDS_CHECK, every OTZ_CHK site counts its violations in g_otz_violations[code], tests/test_gpu_bounds.py runs
+// the parity suite's hardest cases against that build and requires all counters to be zero (otz_debug_violations).
+// In the release build the macro compiles to nothing.
+#define OTZ_CHK_SLOTS 24
+#ifdef OTZ_BOUNDS_CHECK
+__device__ unsigned long long g_otz_violations[OTZ_CHK_SLOTS];
+#define OTZ_CHK(cond, code)                                     \
+	do {                                                        \
+		if (!(cond)) {                                          \
+			atomicAdd(&g_otz_violations[(code)], 1ull);         \
+		}                                                       \
+	} while (0)
+#else
+#define OTZ_CHK(cond, code) \
+	do {                    \
+	} while (0)
+#endif
+// check sites
+#define OTZ_CK_SPEC_PIECE 0     // k_inflate_spec: a decoding position left the words staged for its piece
+#define OTZ_CK_SPEC_VIS 1       // k_inflate_spec: visited-bitmap index outside the piece
+#define OTZ_CK_SPEC_LIT 2       // k_inflate_spec: literal store outside the stream's token scratch
+#define OTZ_CK_SPEC_SEQ 3       // k_inflate_spec: record store outside the stream's token scratch / below the literals
+#define OTZ_CK_SPEC_STORED 4    // k_inflate_spec: stored-block payload copy outside input or scratch
+#define OTZ_CK_LZ_RING_DST 5    // k_inflate_lz: unmasked ring store outside the ring
+#define OTZ_CK_LZ_RING_SRC 6    // k_inflate_lz: unmasked source load outside ring + staging buffers
+#define OTZ_CK_LZ_STAGE 7       // k_inflate_lz: far source staged outside its staging buffer
+#define OTZ_CK_LZ_FLUSH 9       // k_inflate_lz: ring flush outside the entry's slice of the arena / symbol buffer
+#define OTZ_CK_SEG_TABLE 12     // k_inflate_spec: segment table index beyond I2_MAXSEG
+
 #define OTZ_SIG_LFH 0x04034b50u
 #define OTZ_MAX_PAYLOAD (2ull * 1024ull * 1024ull * 1024ull)  // otezip.c:102
 

@@ -21,16 +21,16 @@
 
 static thread_local char g_err[512] = "";
 
-static int fail_cuda(cudaError_t e, const char *what) {
-	snprintf(g_err, sizeof(g_err), "%s: %s", what, cudaGetErrorString(e));
+static int fail_cuda(cudaError_t e, const char *what, int line = 0) {
+	snprintf(g_err, sizeof(g_err), "%s (otz_shim.cu:%d): %s", what, line, cudaGetErrorString(e));
 	return OTZ_ERR_CUDA;
 }
-#define CK(call)                          \
-	do {                                  \
-		cudaError_t e_ = (call);          \
-		if (e_ != cudaSuccess) {          \
-			return fail_cuda(e_, #call);  \
-		}                                 \
+#define CK(call)                                    \
+	do {                                            \
+		cudaError_t e_ = (call);                    \
+		if (e_ != cudaSuccess) {                    \
+			return fail_cuda(e_, #call, __LINE__);  \
+		}                                           \
 	} while (0)
 
 // ring of the LZ executor for huge (segmented) streams: few streams, each one the critical path — a large ring keeps
@@ -53,8 +53,7 @@ struct otz_ctx {
 	uint64_t launches;
 	int inflate_tile;   // lanes per DEFLATE stream (OTZ_INFLATE_TILE; 0 = per batch)
 	int inflate_ring;   // bytes of shared-memory output ring per stream (OTZ_INFLATE_RING; 0 = per batch)
-	int inflate_mode;   // OTZ_INFLATE_MODE: 0 = two-phase (k_inflate_spec + k_inflate_lz, k_inflate as fallback), 1 ("legacy") = k_inflate only,
-	                    // 2 ("lanes") = the lane-per-stream tokenizer k_inflate_tok + block search for huge entries
+	int inflate_mode;   // OTZ_INFLATE_MODE: 0 = two-phase (k_inflate_spec + k_inflate_lz, k_inflate as fallback), 1 ("legacy") = k_inflate only
 	int lz_ring;        // OTZ_LZ_RING: ring bytes per warp of k_inflate_lz (4096 / 8192 / 16384)
 	uint32_t last_fallbacks;   // DEFLATE streams of the last collected run that phase A handed to k_inflate
 	int huge_legacy;        // OTZ_HUGE_MODE=legacy: huge DEFLATE entries on k_inflate<32,16384> instead of the segmented decode
@@ -91,11 +90,7 @@ struct otz_plan {
 	uint32_t n_inflate_big;
 	uint32_t n_inflate_huge;   // [0, n_inflate_huge): entries whose serial decode time sets the critical path of a batch
 	I2SegCtl seg;              // segmented decode of the huge entries (device arrays; null when there are none)
-	uint32_t huge_max_comp;
 	uint64_t sym_elems;        // symbol buffer the parallel execution of the huge streams may need
-	uint32_t *d_search_ofs;    // [n_huge + 1] first 256-byte search task of every huge stream
-	uint2 *d_surv;             // offsets that passed the cheap header checks of k_block_search
-	uint32_t surv_cap;
 	uint64_t *d_tok_ofs;       // two-phase inflate: scratch offset of every list slot (+ end), bytes
 	uint64_t tok_bytes;
 	I2TokRes *d_tokres;
@@ -173,6 +168,25 @@ static void build_crc_tables(OtzCrcTables *t) {
 // ---------------------------------------------------------------- context
 extern "C" const char *otz_last_error(void) { return g_err; }
 
+// debug build (-DOTZ_BOUNDS_CHECK, `make debug`): violations counted by the OTZ_CHK sites of the kernels since the library was
+// loaded; returns the number of counters, -1 in the release build (no checks compiled in)
+extern "C" int otz_debug_violations(uint64_t *out, int cap) {
+#ifdef OTZ_BOUNDS_CHECK
+	unsigned long long h[OTZ_CHK_SLOTS];
+	if (cudaMemcpyFromSymbol(h, g_otz_violations, sizeof(h)) != cudaSuccess) {
+		return fail_cuda(cudaGetLastError(), "cudaMemcpyFromSymbol(g_otz_violations)");
+	}
+	for (int i = 0; i < OTZ_CHK_SLOTS && i < cap; i++) {
+		out[i] = h[i];
+	}
+	return OTZ_CHK_SLOTS;
+#else
+	(void)out;
+	(void)cap;
+	return -1;
+#endif
+}
+
 extern "C" int otz_device_count(void) {
 	int n = 0;
 	if (cudaGetDeviceCount(&n) != cudaSuccess) {
@@ -217,7 +231,7 @@ extern "C" int otz_ctx_create(int device, otz_ctx **out) {
 	t = getenv("OTZ_INFLATE_RING");
 	c->inflate_ring = t ? atoi(t) : 0;
 	t = getenv("OTZ_INFLATE_MODE");
-	c->inflate_mode = (t && !strcmp(t, "legacy")) ? 1 : (t && !strcmp(t, "lanes")) ? 2 : 0;
+	c->inflate_mode = (t && !strcmp(t, "legacy")) ? 1 : 0;
 	t = getenv("OTZ_HUGE_MODE");
 	c->huge_legacy = (t && !strcmp(t, "legacy")) ? 1 : 0;
 	t = getenv("OTZ_SEG_EXEC");
@@ -410,14 +424,9 @@ extern "C" void otz_plan_destroy(otz_ctx *c, otz_plan *p) {
 	cudaFree(p->d_produced);
 	cudaFree(p->d_chunks);
 	cudaFree(p->d_inflate_list);
-	cudaFree(p->d_search_ofs);
-	cudaFree(p->d_surv);
 	cudaFree(p->seg.count);
 	cudaFree(p->seg.start);
-	cudaFree(p->seg.bucket);
 	cudaFree(p->seg.res);
-	cudaFree(p->seg.items);
-	cudaFree(p->seg.n_items);
 	cudaFree(p->seg.live);
 	cudaFree(p->seg.nlive);
 	cudaFree(p->seg.seg_status);
@@ -515,9 +524,6 @@ extern "C" int otz_plan_create(otz_ctx *c, const otz_entry *ents, uint32_t n, co
 	for (uint32_t i : infl) {
 		p->n_inflate_big += ents[i].uncomp_size >= big_bytes;
 		p->n_inflate_huge += is_huge(i);
-		if (is_huge(i)) {
-			p->huge_max_comp = std::max(p->huge_max_comp, ents[i].comp_size);
-		}
 	}
 	p->n_chunks = (uint32_t)chunks.size();
 	p->n_inflate = (uint32_t)infl.size();
@@ -540,28 +546,14 @@ extern "C" int otz_plan_create(otz_ctx *c, const otz_entry *ents, uint32_t n, co
 	}
 	if (p->n_inflate_huge && p->n_inflate_huge <= 4096u) {
 		const size_t nh = p->n_inflate_huge, ns = nh * I2_MAXSEG;
-		std::vector<uint32_t> sofs(nh + 1);
-		sofs[0] = 0;
 		for (size_t h = 0; h < nh; h++) {
-			sofs[h + 1] = sofs[h] + (ents[infl[h]].comp_size + 255u) / 256u;
-			// symbols of the stream + markers in front of every segment (a block of zlib is ~25 KB of compressed data;
-			// a stream with more segments than estimated here is executed by one warp)
+			// symbols of the stream + markers in front of every segment (a stream with more segments than estimated here is
+			// executed by one warp)
 			p->sym_elems += (uint64_t)ents[infl[h]].uncomp_size +
-				(uint64_t)(I2_PREWIN + 16u) * std::min<uint64_t>(I2_MAXSEG, 2u + std::max<uint64_t>(ents[infl[h]].comp_size / 12288u, ents[infl[h]].uncomp_size / I3_SEG_MIN));
+				(uint64_t)(I2_PREWIN + 16u) * std::min<uint64_t>(I2_MAXSEG, 2u + ents[infl[h]].uncomp_size / I3_SEG_MIN);
 		}
-		if ((rc = upload(&p->d_search_ofs, sofs, c->stream))) {
-			otz_plan_destroy(c, p);
-			return rc;
-		}
-		CK(cudaStreamSynchronize(c->stream));   // sofs dies here
-		p->surv_cap = std::max<uint32_t>(1u << 16, sofs[nh] * 4u);   // one per 64 bytes of compressed data (expected: one per ~135)
-		if (cudaMalloc(&p->d_surv, (size_t)p->surv_cap * sizeof(uint2)) != cudaSuccess) {
-			otz_plan_destroy(c, p);
-			return fail_cuda(cudaGetLastError(), "cudaMalloc(search survivors)");
-		}
-		if (cudaMalloc(&p->seg.count, nh * 4) != cudaSuccess || cudaMalloc(&p->seg.start, ns * 4) != cudaSuccess || cudaMalloc(&p->seg.bucket, ns * 4) != cudaSuccess ||
-			cudaMalloc(&p->seg.res, ns * sizeof(I2SegRes)) != cudaSuccess || cudaMalloc(&p->seg.items, ns * 4) != cudaSuccess ||
-			cudaMalloc(&p->seg.n_items, 4) != cudaSuccess || cudaMalloc(&p->seg.live, ns * 4) != cudaSuccess ||
+		if (cudaMalloc(&p->seg.count, nh * 4) != cudaSuccess || cudaMalloc(&p->seg.start, ns * 4) != cudaSuccess ||
+			cudaMalloc(&p->seg.res, ns * sizeof(I2SegRes)) != cudaSuccess || cudaMalloc(&p->seg.live, ns * 4) != cudaSuccess ||
 			cudaMalloc(&p->seg.nlive, nh * 4) != cudaSuccess || cudaMalloc(&p->seg.seg_status, nh * 4) != cudaSuccess ||
 			cudaMalloc(&p->seg.par, nh * 4) != cudaSuccess || cudaMalloc(&p->seg.par_items, ns * 4) != cudaSuccess ||
 			cudaMalloc(&p->seg.n_par, 4) != cudaSuccess || cudaMalloc(&p->seg.sym_start, ns * 8) != cudaSuccess ||
@@ -706,177 +698,23 @@ static int launch_seg_par(otz_ctx *c, otz_plan *p, uint8_t *d_out, const I2SegCt
 		return OTZ_ERR_CUDA;
 	}
 	const uint32_t nh = p->n_inflate_huge;
+	const bool dbg = getenv("OTZ_DEBUG_SYNC") != nullptr;
 	kern<<<(uint32_t)(c->sm_count * per_sm), 32 * warps, smem, st>>>(reinterpret_cast<uint8_t *>(c->d_sym_cache), p->d_ents, p->d_inflate_list, 0u,
 		p->d_counter + 60, c->d_tok_cache, p->d_tok_ofs, p->d_tokres, p->d_status, p->d_produced, sg);
+	if (dbg) {
+		CK(cudaStreamSynchronize(st));
+	}
 	k_seg_window<<<nh, 1024, 0, st>>>(d_out, p->d_ents, p->d_inflate_list, nh, c->d_sym_cache, p->d_status, p->d_produced, sg);
+	if (dbg) {
+		CK(cudaStreamSynchronize(st));
+	}
 	k_seg_translate<<<(uint32_t)c->sm_count * 4u, I2_TR_THREADS, 0, st>>>(d_out, p->d_ents, p->d_inflate_list, c->d_sym_cache, p->d_counter + 61, sg);
+	if (dbg) {
+		CK(cudaStreamSynchronize(st));
+	}
 	c->launches += 3;
 	CK(cudaGetLastError());
 	return OTZ_SUCCESS;
-}
-
-// Two-phase inflate: lane-per-stream entropy decode into tokens, warp-per-stream LZ77 execution, then k_inflate over
-// whatever phase A declined (d_counter + 52 counts those entries).
-static int dispatch_inflate2(otz_ctx *c, otz_plan *p, const uint8_t *d_archive, uint8_t *d_out) {
-	cudaStream_t s = c->stream;
-	// Huge entries: a stream advances one symbol per step wherever it is decoded, so the largest entries set the
-	// critical path of the batch.  They go to the decoder with the shortest step — one warp per stream with a 16 KiB
-	// ring (k_inflate) — on the second stream, next to the lane-per-stream kernels that take everything else.
-	uint32_t first = 0;
-	bool forked = false;
-	static bool attr_done = false;
-	if (!attr_done) {
-		CK(cudaFuncSetAttribute(k_inflate_tok<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, I2_SMEM_BYTES(I2_LANES)));
-		CK(cudaFuncSetAttribute(k_inflate_tok<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, I2_SMEM_BYTES(I2_LANES)));
-		CK(cudaFuncSetAttribute(k_inflate_lz<OTZ_SEG_RING, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(4 * sizeof(I2LzSmem<OTZ_SEG_RING>))));
-		attr_done = true;
-	}
-	// phase A of everything that is not huge (from list position `first_`)
-	bool tok_launched = false;
-	auto launch_regular_tok = [&](uint32_t first_) -> int {
-		const uint32_t count = p->n_inflate - first_;
-		const uint32_t first = first_;
-		tok_launched = true;
-		if (!count) {
-			return OTZ_SUCCESS;
-		}
-		// A lock-step step costs the same for 1 or 28 live lanes and a stream advances one symbol per step, so the
-		// streams are spread over as many CTAs as the SM holds (more warps = more latency hidden): pick the number
-		// of resident CTAs per SM (8..4) that gives the most table slots for this batch, most CTAs first.
-		const long fixed = (long)I2_SMEM_BYTES(0);
-		const uint32_t per_sm_streams = (count + (uint32_t)c->sm_count - 1) / (uint32_t)c->sm_count;
-		uint32_t best_c = 4, best_l = 1, best_cov = 0;
-		for (uint32_t cw = 8; cw >= 4; cw--) {
-			const long budget = (long)(227 * 1024) / (long)cw - 1024 - fixed;
-			const uint32_t l = (uint32_t)std::max(1L, std::min<long>(I2_LANES, budget / I2_SLOT_BYTES));
-			const uint32_t cov = std::min(per_sm_streams, cw * l);
-			if (cov > best_cov) {
-				best_cov = cov;
-				best_c = cw;
-				best_l = l;
-			}
-		}
-		uint32_t lanes = std::max(1u, std::min(best_l, (per_sm_streams + best_c - 1) / best_c));
-		const size_t smem_l = (size_t)I2_SMEM_BYTES(best_l);
-		int per_sm = 0;
-		CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_inflate_tok<false>, 32, smem_l));
-		if (per_sm < 1) {
-			snprintf(g_err, sizeof(g_err), "k_inflate_tok does not fit an SM (%zu bytes of shared memory)", smem_l);
-			return OTZ_ERR_CUDA;
-		}
-		per_sm = std::min<int>(per_sm, (int)best_c);
-		const uint32_t grid = std::max(1u, std::min((uint32_t)(c->sm_count * per_sm), count));
-		lanes = std::max(lanes, std::min<uint32_t>(best_l, (count + grid - 1) / grid));
-		k_inflate_tok<false><<<grid, 32, I2_SMEM_BYTES(lanes), s>>>(d_archive, p->d_ents, p->d_est, p->d_status, p->d_inflate_list + first, count,
-			p->d_counter, c->d_tok_cache, p->d_tok_ofs + first, p->d_tokres + first, p->d_fb_list, p->d_counter + 52, lanes, I2SegCtl{});
-		c->launches++;
-		CK(cudaGetLastError());
-		return OTZ_SUCCESS;
-	};
-	if (p->n_inflate_huge && p->seg.count && !c->huge_legacy) {
-		// segmented decode: block search -> one lane per block run -> chain check -> one warp per stream executes the tokens
-		const uint32_t nh = p->n_inflate_huge;
-		first = nh;
-		cudaStream_t s2 = c->stream2;
-		CK(cudaEventRecord(c->ev_fork, s));
-		CK(cudaStreamWaitEvent(s2, c->ev_fork, 0));
-		{
-			// the lane-per-stream tokenizer of the other entries goes first: it is latency-bound and small (8 warps per
-			// SM) and runs next to the search, which would otherwise occupy every thread slot until it is done
-			const int rc_ = launch_regular_tok(nh);
-			if (rc_) {
-				return rc_;
-			}
-		}
-		CK(cudaMemsetAsync(p->seg.count, 0, nh * 4, s2));
-		CK(cudaMemsetAsync(p->seg.bucket, 0xFF, (size_t)nh * I2_MAXSEG * 4, s2));
-		CK(cudaMemsetAsync(p->seg.n_items, 0, 4, s2));
-		CK(cudaMemsetAsync(p->d_counter + 59, 0, 4, s2));
-		k_block_search<<<c->sm_count * 8, 256, 0, s2>>>(d_archive, p->d_ents, p->d_est, p->d_status, p->d_inflate_list, nh, p->d_search_ofs, p->d_surv,
-			p->surv_cap, p->d_counter + 59);
-		k_block_verify<<<c->sm_count * 8, 256, 0, s2>>>(d_archive, p->d_ents, p->d_est, p->d_inflate_list, p->d_surv, p->surv_cap, p->d_counter + 59, p->seg);
-		k_seg_prepare<<<(nh + 63) / 64, 64, 0, s2>>>(p->d_ents, p->d_inflate_list, nh, p->d_tok_ofs, p->seg);
-		const uint32_t sl = 12;   // lanes per warp: 8 warps x 12 table slots per SM
-		int per_sm2 = 0;
-		CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm2, k_inflate_tok<true>, 32, I2_SMEM_BYTES(sl)));
-		uint32_t sgrid = (uint32_t)c->sm_count * (uint32_t)std::max(1, std::min(per_sm2, 8));
-		if (getenv("OTZ_SEG_GRID")) {
-			sgrid = (uint32_t)atoi(getenv("OTZ_SEG_GRID"));   // (tests: few lanes, so that every lane decodes many segments)
-		}
-		k_inflate_tok<true><<<sgrid, 32, I2_SMEM_BYTES(sl), s2>>>(d_archive, p->d_ents, p->d_est, p->d_status, p->d_inflate_list, 0u, p->d_counter + 57,
-			c->d_tok_cache, p->d_tok_ofs, p->d_tokres, p->d_fb_list, p->d_counter + 52, sl, p->seg);
-		// parallel execution of the segments needs the symbol buffer (grow-only, like the token scratch); without it
-		// (or for a stream that does not fit) one warp walks the chain
-		I2SegCtl sg = p->seg;
-		sg.sym_top = reinterpret_cast<unsigned long long *>(p->d_counter + 62);
-		sg.out_mis = (uint32_t)(reinterpret_cast<uint64_t>(d_out) & 15u);
-		sg.sym_cap = 0;
-		if (!c->seg_serial && p->sym_elems) {
-			if (p->sym_elems > c->sym_cache_elems) {
-				CK(cudaStreamSynchronize(c->stream));
-				CK(cudaStreamSynchronize(s2));
-				cudaFree(c->d_sym_cache);
-				c->d_sym_cache = nullptr;
-				c->sym_cache_elems = 0;
-				if (cudaMalloc(&c->d_sym_cache, p->sym_elems * 2 + 64) == cudaSuccess) {
-					c->sym_cache_elems = p->sym_elems;
-				} else {
-					cudaGetLastError();
-				}
-			}
-			sg.sym_cap = c->d_sym_cache ? std::min<uint64_t>(p->sym_elems, c->sym_limit) : 0;
-		}
-		CK(cudaMemsetAsync(p->seg.n_par, 0, 4, s2));
-		k_seg_stitch<<<(nh + 63) / 64, 64, 0, s2>>>(p->d_ents, p->d_status, p->d_inflate_list, nh, sg, p->d_fb_list, p->d_counter + 52);
-		CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm2, k_inflate_lz<OTZ_SEG_RING, false, true>, 128, 4 * sizeof(I2LzSmem<OTZ_SEG_RING>)));
-		const uint32_t lgrid = std::max(1u, std::min((uint32_t)(c->sm_count * std::max(per_sm2, 1)), (nh + 3) / 4));
-		k_inflate_lz<OTZ_SEG_RING, false, true><<<lgrid, 128, 4 * sizeof(I2LzSmem<OTZ_SEG_RING>), s2>>>(d_out, p->d_ents, p->d_inflate_list, nh, p->d_counter + 58,
-			c->d_tok_cache, p->d_tok_ofs, p->d_tokres, p->d_status, p->d_produced, sg);
-		c->launches += 6;
-		if (sg.sym_cap) {
-			int rc_ = c->seg_ring == 8192 ? launch_seg_par<8192>(c, p, d_out, sg, s2) : launch_seg_par<4096>(c, p, d_out, sg, s2);
-			if (rc_) {
-				return rc_;
-			}
-		}
-		CK(cudaGetLastError());
-		CK(cudaEventRecord(c->ev_join, s2));
-		forked = true;
-	} else if (p->n_inflate_huge && p->n_inflate_huge <= (uint32_t)c->sm_count * 10u) {
-		first = p->n_inflate_huge;
-		CK(cudaEventRecord(c->ev_fork, s));
-		CK(cudaStreamWaitEvent(c->stream2, c->ev_fork, 0));
-		int rc_ = launch_inflate_cfg(c, p, d_archive, d_out, 32, 16384, 0, first, 56, c->stream2);
-		if (rc_) {
-			return rc_;
-		}
-		CK(cudaEventRecord(c->ev_join, c->stream2));
-		forked = true;
-	}
-	const uint32_t count = p->n_inflate - first;
-	if (!count) {
-		CK(cudaStreamWaitEvent(s, c->ev_join, 0));
-		return launch_inflate_cfg(c, p, d_archive, d_out, 32, 4096, 0, p->n_inflate, 16, s, p->d_fb_list, p->d_counter + 52);
-	}
-	if (!tok_launched) {
-		const int rc_ = launch_regular_tok(first);
-		if (rc_) {
-			return rc_;
-		}
-	}
-	int rc;
-	switch (c->lz_ring) {
-	case 8192: rc = launch_lz<8192>(c, p, d_out, first, count, s); break;
-	case 16384: rc = launch_lz<16384>(c, p, d_out, first, count, s); break;
-	default: rc = launch_lz<4096>(c, p, d_out, first, count, s); break;
-	}
-	if (rc) {
-		return rc;
-	}
-	if (forked) {
-		CK(cudaStreamWaitEvent(s, c->ev_join, 0));   // (the segmented decode of the huge entries appends to the same list)
-	}
-	return launch_inflate_cfg(c, p, d_archive, d_out, 32, 4096, 0, p->n_inflate, 16, s, p->d_fb_list, p->d_counter + 52);
 }
 
 // Two-phase inflate, warp-per-stream speculative tokenizer (k_inflate3.cuh): ONE tokenizer launch for every DEFLATE
@@ -890,7 +728,7 @@ static int dispatch_inflate3(otz_ctx *c, otz_plan *p, const uint8_t *d_archive, 
 	if (!attr_done) {
 		CK(cudaFuncSetAttribute(k_inflate_spec<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem1));
 		CK(cudaFuncSetAttribute(k_inflate_spec<1>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
-		CK(cudaFuncSetAttribute(k_inflate_spec<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem4));
+		CK(cudaFuncSetAttribute(k_inflate_spec<4, 8>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem4));
 		CK(cudaFuncSetAttribute(k_inflate_lz<OTZ_SEG_RING, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(4 * sizeof(I2LzSmem<OTZ_SEG_RING>))));
 		attr_done = true;
 	}
@@ -903,13 +741,16 @@ static int dispatch_inflate3(otz_ctx *c, otz_plan *p, const uint8_t *d_archive, 
 		CK(cudaEventRecord(c->ev_fork, s));
 		CK(cudaStreamWaitEvent(s2, c->ev_fork, 0));
 		int per_sm4 = 0;
-		CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm4, k_inflate_spec<4>, 128, smem4));
+		auto kern4 = k_inflate_spec<4, 8>;   // (64 registers: 8 CTAs = 32 warps per SM; 4 CTAs at 104 registers measured 4 % slower on configs[2])
+		CK(cudaFuncSetAttribute(kern4, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem4));
+		CK(cudaFuncSetAttribute(kern4, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
+		CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm4, kern4, 128, smem4));
 		if (per_sm4 < 1) {
 			snprintf(g_err, sizeof(g_err), "k_inflate_spec<4> does not fit an SM (%zu bytes of shared memory)", smem4);
 			return OTZ_ERR_CUDA;
 		}
 		const uint32_t grid4 = gs ? (uint32_t)atoi(gs) : std::max(1u, std::min((uint32_t)(c->sm_count * per_sm4), nh));
-		k_inflate_spec<4><<<grid4, 128, smem4, s2>>>(d_archive, p->d_ents, p->d_est, p->d_status, p->d_inflate_list, 0u, nh, p->d_counter + 57,
+		kern4<<<grid4, 128, smem4, s2>>>(d_archive, p->d_ents, p->d_est, p->d_status, p->d_inflate_list, 0u, nh, p->d_counter + 57,
 			c->d_tok_cache, p->d_tok_ofs, p->d_tokres, p->d_fb_list, p->d_counter + 52, nh, p->seg);
 		c->launches++;
 		CK(cudaGetLastError());
@@ -999,7 +840,7 @@ static int dispatch_inflate(otz_ctx *c, otz_plan *p, const uint8_t *d_archive, u
 			}
 		}
 		if (c->d_tok_cache) {
-			return c->inflate_mode == 2 ? dispatch_inflate2(c, p, d_archive, d_out) : dispatch_inflate3(c, p, d_archive, d_out);
+			return dispatch_inflate3(c, p, d_archive, d_out);
 		}
 	}
 	if (c->inflate_tile || c->inflate_ring) {   // explicit configuration (tests, sweeps): one kernel for everything

@@ -12,7 +12,8 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 
 
 def lib_path() -> str:
-    return os.path.join(HERE, "libotezip_b200.so")
+    """OTEZIP_B200_LIB selects another build of the same library (the bounds-checked one, libotezip_b200_dbg.so)."""
+    return os.environ.get("OTEZIP_B200_LIB") or os.path.join(HERE, "libotezip_b200.so")
 
 
 class OtzEntry(C.Structure):  # struct otz_entry, include/otz_gpu.h

@@ -1,5 +1,6 @@
-"""Two-phase inflate (k_inflate_tok lane-per-stream entropy decode + k_inflate_lz warp-per-stream LZ77 execution,
-k_inflate as the fallback for declined streams) against the oracle and against the one-kernel decoder."""
+"""Two-phase inflate (k_inflate_spec: warp-per-stream / CTA-per-huge-stream speculative entropy decode; k_inflate_lz:
+warp-per-stream LZ77 execution; k_inflate as the fallback for declined streams) against the oracle and against the
+one-kernel decoder."""
 import os
 import random
 import zlib
@@ -135,9 +136,9 @@ def test_many_uniform_streams_no_fallback(oracle):
 @pytest.mark.parametrize("seg_exec", [None, "serial", "limit", "ring8192"])
 @pytest.mark.parametrize("seg_grid", [None, "2"])
 def test_huge_streams_segmented(oracle, seg_grid, seg_exec):
-    """Entries >= 2 MiB: block-start search + one lane per block run + chain check (k_block_search / k_inflate_tok<true> /
-    k_seg_stitch) against the oracle, in shapes that stress the chain: many blocks, stored and fixed blocks in between,
-    full-flush points, an incompressible middle, a stream that is one single block.
+    """Entries >= 2 MiB: one 4-warp CTA per stream (k_inflate_spec<4>: 128 pieces per round), token stream cut into
+    segments, chain check (k_seg_stitch) against the oracle, in shapes that stress it: many blocks, stored and fixed
+    blocks in between, full-flush points, an incompressible middle, a stream that is one single block.
     seg_exec: how the accepted chains are executed — every segment by its own warp over 16-bit symbols with markers for
     the 32 KiB before it (k_inflate_lz<.., PAR> + k_seg_window + k_seg_translate; default), one warp walking the chain
     ("serial"), or a symbol buffer that only has room for some of the streams ("limit": both executors in one run)."""
@@ -152,20 +153,20 @@ def test_huge_streams_segmented(oracle, seg_grid, seg_exec):
           synth.member("h7", synth.jsonlog_text(2200000, 10), 8, strategy=zlib.Z_HUFFMAN_ONLY)]
     ms += [synth.member("s%d" % i, synth.jsonlog_text(rnd.randint(1000, 300000), 20 + i), 8) for i in range(30)]
     img = synth.build_zip(ms)
-    if seg_grid:   # two warps for all segments: every lane decodes many segments one after the other
-        os.environ["OTZ_SEG_GRID"] = seg_grid
+    if seg_grid:   # two CTAs for all streams: every group decodes many streams one after the other
+        os.environ["OTZ_SPEC_GRID"] = seg_grid
     if seg_exec == "serial":
         os.environ["OTZ_SEG_EXEC"] = "serial"
     elif seg_exec == "limit":
         os.environ["OTZ_SEG_SYM_LIMIT"] = str(9 << 20)
-    elif seg_exec == "ring8192":
-        os.environ["OTZ_SEG_PAR_RING"] = "8192"
+    elif seg_exec in ("ring8192", "ring4096"):
+        os.environ["OTZ_SEG_PAR_RING"] = seg_exec[4:]
     try:
         c = _ctx()
         fb, st, out = _check(img, oracle, c)
         c.close()
     finally:
-        for k in ("OTZ_SEG_GRID", "OTZ_SEG_EXEC", "OTZ_SEG_SYM_LIMIT", "OTZ_SEG_PAR_RING"):
+        for k in ("OTZ_SPEC_GRID", "OTZ_SEG_EXEC", "OTZ_SEG_SYM_LIMIT", "OTZ_SEG_PAR_RING"):
             os.environ.pop(k, None)
     assert fb <= 3, fb   # (the incompressible middle of h3 is stored blocks with payload: k_inflate takes that stream)
 

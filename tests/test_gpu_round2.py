@@ -269,3 +269,37 @@ def test_store_archive_headers_equal_the_reference_writer(tmp_path):
             blob[pos + 12:pos + 16] = b"\0\0\0\0"
             pos += 46
     assert a == b
+
+
+def test_streaming_layout_with_data_descriptors(tmp_path, reflib):
+    """SURVEY §8f rank 2, write side: with otezip_write_data_descriptors (or OTEZIP_DATA_DESCRIPTORS=1) zip_close emits
+    the streaming layout — flag bit 3, zero CRC / sizes in the local header, a data descriptor behind the payload.
+    Python's zipfile, the compiled reference (it reads CRC and sizes from the directory) and this library read it back."""
+    import zipfile
+    api = ZipApi()
+    flag = C.c_int.in_dll(api.L, "otezip_write_data_descriptors")
+    files = [("t.json", synth.jsonlog_text(200000, 7)), ("r.bin", synth.random_bytes(3000, 8)), ("empty", b""), ("s.txt", b"hello\n")]
+    p = str(tmp_path / "dd.zip")
+    flag.value = 1
+    try:
+        assert api.write_archive(p, files, 8) == 0
+    finally:
+        flag.value = 0
+    raw = open(p, "rb").read()
+    assert raw.count(b"PK\x07\x08") >= len(files)
+    pos = 0
+    for name, data in files:   # local headers: bit 3, zeros; descriptor: the real values
+        assert raw[pos:pos + 4] == b"PK\x03\x04"
+        flags, method, _, _, crc, comp, uncomp, nl, xl = struct.unpack_from("<HHHHIIIHH", raw, pos + 6)
+        assert flags == 8 and crc == 0 and comp == 0 and uncomp == 0
+        with zipfile.ZipFile(p) as z:
+            info = z.getinfo(name)
+        dpos = pos + 30 + nl + xl + info.compress_size
+        assert struct.unpack_from("<IIII", raw, dpos) == (0x08074B50, zlib.crc32(data), info.compress_size, len(data))
+        pos = dpos + 16
+    with zipfile.ZipFile(p) as z:
+        assert z.testzip() is None and [z.read(n) for n, _ in files] == [d for _, d in files]
+        assert all(i.flag_bits & 8 for i in z.infolist())
+    assert api.read_all(p)[2] == [d for _, d in files]
+    e2, got = reflib.extract_file(p, verify_crc=1)
+    assert e2 == 0 and got == [d for _, d in files]
