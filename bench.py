@@ -623,6 +623,55 @@ def run_c5(ctx, dist: "Dist", n_entries, steps, warmup, e2e_steps, sampler=None)
         "gpu_launches": int(launches)}
 
 
+# ----------------------------------------------------------------------------- configs[0] as written: the CLI
+def cli_config0():
+    """BASELINE configs[0] is DEFINED as `otezip -x` on a 1,000-entry DEFLATE archive (64 KiB text-like entries) with the
+    CRC-32 check (/root/reference/src/main.c:429-585).  Wall clock of the reference CLI (oracle/_ref/otezip_ref, CPU) and of
+    the SAME main.c relinked against libotezip_b200.so (oracle/_ref/otezip_relinked), process start, CUDA initialisation and
+    the 1,000 file writes included; both trees compared byte for byte."""
+    import shutil
+    import subprocess
+    import tempfile
+    from otezip_b200 import synth
+    refdir = os.path.join(ROOT, "oracle", "_ref")
+    exes = {"reference_cli": os.path.join(refdir, "otezip_ref"), "b200_cli": os.path.join(refdir, "otezip_relinked")}
+    if not all(os.path.exists(e) for e in exes.values()):
+        return {"error": "oracle/_ref CLIs not built"}
+    tmp = tempfile.mkdtemp(prefix="otz_cli_", dir="/dev/shm" if os.path.isdir("/dev/shm") else None)
+    try:
+        z = os.path.join(tmp, "c1.zip")
+        ms = synth.config_c1(1000, 65536)
+        with open(z, "wb") as f:
+            f.write(synth.build_zip(ms))
+        total = sum(m.uncomp_size for m in ms)
+        res, trees = {}, {}
+        for tag, exe in exes.items():
+            best = None
+            for rep in range(2 if tag == "b200_cli" else 1):     # (the GPU run twice: the first one pages the CUDA libraries in)
+                d = os.path.join(tmp, "%s_%d" % (tag, rep))
+                os.mkdir(d)
+                t0 = time.perf_counter()
+                r = subprocess.run([exe, "-x", z, "--verify-crc"], cwd=d, capture_output=True, text=True, timeout=600)
+                dt = time.perf_counter() - t0
+                if r.returncode != 0:
+                    return {"error": "%s exit %d: %s" % (tag, r.returncode, r.stderr[-300:])}
+                best = dt if best is None else min(best, dt)
+                tree = {}
+                for root, _, fs in os.walk(d):
+                    for fn in fs:
+                        q = os.path.join(root, fn)
+                        tree[os.path.relpath(q, d)] = zlib.crc32(open(q, "rb").read())
+                trees[tag] = tree
+                shutil.rmtree(d)
+            res[tag] = {"seconds": best, "MB_per_s": total / best / 1e6}
+        res["identical_trees"] = trees["reference_cli"] == trees["b200_cli"] and len(trees["b200_cli"]) == 1000
+        res["speedup"] = res["reference_cli"]["seconds"] / res["b200_cli"]["seconds"]
+        res["what"] = "otezip -x c1.zip --verify-crc, 1,000 x 64 KiB (64 MiB) into /dev/shm; wall clock incl. process start, CUDA init and file writes"
+        return res
+    finally:
+        shutil.rmtree(tmp, ignore_errors=True)
+
+
 def hbm_peak():
     try:
         peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
@@ -802,6 +851,10 @@ def main():
                               "run": r["run"]}
                 except BaseException as e:  # a failing secondary must not take the headline with it
                     sec[w] = {"workload": WORKLOADS[w], "error": repr(e)}
+            try:
+                sec["c1_cli"] = cli_config0()
+            except BaseException as e:
+                sec["c1_cli"] = {"error": repr(e)}
             line["secondary"] = sec
     sampler.stop()
     if dist.rank == 0:

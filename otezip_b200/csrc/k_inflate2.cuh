@@ -30,6 +30,9 @@
 #include "otz_common.cuh"
 #include "k_inflate.cuh"
 
+#ifndef OTZ_PAR_STAGE_VECS
+#define OTZ_PAR_STAGE_VECS 96u
+#endif
 #define I2_LIT_ROOT 9
 #define I2_DST_ROOT 7
 #define I2_LIT_CAP 704   // 512 root slots + 192 second-level slots
@@ -409,11 +412,21 @@ __global__ void __launch_bounds__(1024) k_seg_window(uint8_t *__restrict__ out, 
 // One CTA per work item (segment): symbols [0, produced - 32 KiB) -> bytes.  The 32 KiB before the segment (final
 // since k_seg_window) are staged in shared memory: in text most vectors still hold a marker or two.
 #define I2_TR_THREADS 512
+// The window — up to 32 KiB + 16 contiguous, 16-byte aligned bytes — is staged by ONE bulk-copy instruction (TMA:
+// cp.async.bulk global -> shared, completion counted in bytes on an mbarrier) issued by one thread, instead of 2,049
+// vector loads and stores through registers; the other 511 threads go straight to the wait.
 __global__ void __launch_bounds__(I2_TR_THREADS) k_seg_translate(uint8_t *__restrict__ out, const otz_entry *__restrict__ ents, const uint32_t *__restrict__ list,
 	const uint16_t *__restrict__ sym, uint32_t *__restrict__ work_counter, I2SegCtl seg) {
 	__shared__ __align__(16) uint8_t s_win[I2_PREWIN + 16];
+	__shared__ __align__(8) uint64_t s_mbar;
 	__shared__ uint32_t s_k;
 	const uint32_t n = *seg.n_par;
+	const uint32_t mbar_sa = (uint32_t)__cvta_generic_to_shared(&s_mbar), win_sa = (uint32_t)__cvta_generic_to_shared(s_win);
+	if (threadIdx.x == 0) {
+		asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(mbar_sa) : "memory");
+		asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+	}
+	uint32_t phase = 0;
 	for (;;) {
 		__syncthreads();
 		if (threadIdx.x == 0) {
@@ -437,14 +450,26 @@ __global__ void __launch_bounds__(I2_TR_THREADS) k_seg_translate(uint8_t *__rest
 		if (r_->reach) {   // (no reach, no markers; and the first segment of a stream has nothing in front of it)
 			// (a segment in the first 32 KiB of its entry: nothing is read in front of the entry's output)
 			const int64_t avail = (int64_t)os + (int64_t)((reinterpret_cast<uint64_t>(o) - os) & 15u);
-			const uint4 *wa = reinterpret_cast<const uint4 *>(o - I2_PREWIN - omis);
-			for (uint32_t x = threadIdx.x; x < I2_PREWIN / 16u + 1u; x += blockDim.x) {
-				if ((int64_t)(I2_PREWIN + omis) - (int64_t)(16u * x) <= avail) {
-					reinterpret_cast<uint4 *>(s_win)[x] = __ldcg(wa + x);
-				}
+			const int64_t lack = (int64_t)(I2_PREWIN + omis) - avail;
+			const uint32_t x0 = lack > 0 ? (uint32_t)((lack + 15) >> 4) : 0u;   // first 16-byte vector of the window that exists
+			const uint32_t bytes = (I2_PREWIN / 16u + 1u - x0) * 16u;
+			if (threadIdx.x == 0) {
+				// (the reads of the previous item's window — generic proxy — are ordered before this write by the async proxy)
+				asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+				asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(mbar_sa), "r"(bytes) : "memory");
+				asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(win_sa + 16u * x0),
+					"l"(o - I2_PREWIN - omis + 16u * x0), "r"(bytes), "r"(mbar_sa)
+					: "memory");
 			}
+			uint32_t done = 0;
+			do {
+				asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+					: "=r"(done)
+					: "r"(mbar_sa), "r"(phase)
+					: "memory");
+			} while (!done);
+			phase ^= 1u;
 		}
-		__syncthreads();
 		const uint8_t *const win = s_win + omis;                    // marker j -> win[j]
 		const uint32_t head = min(body, (16u - omis) & 15u);
 		const uint32_t nvec = (body - head) >> 4, tail0 = head + (nvec << 4);
@@ -502,7 +527,7 @@ __global__ void __launch_bounds__(I2_TR_THREADS) k_seg_translate(uint8_t *__rest
 template <typename T>
 struct I2Elem {
 	static constexpr uint32_t VEC = 16u / sizeof(T);
-	static constexpr uint32_t STAGE_VECS = sizeof(T) == 1 ? 64u : 96u;   // staging vectors per batch; far matches beyond them are fetched directly
+	static constexpr uint32_t STAGE_VECS = sizeof(T) == 1 ? 64u : OTZ_PAR_STAGE_VECS;   // staging vectors per batch; far matches beyond them are fetched directly
 	static constexpr uint32_t STAGE = STAGE_VECS * VEC;
 };
 

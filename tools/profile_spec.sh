@@ -15,5 +15,9 @@ for K in ${KERNELS:-spec1 spec4 lz}; do
     spec1) full spec1 "k_inflate_spec" "$C1" 2 ;;
     spec4) full spec4 "k_inflate_spec" "$C3" 2 ;;   # per pass: spec<4>, spec<1>
     lz) full lz "k_inflate_lz" "$C1" 2 ;;
+    par) full par "k_inflate_lz" "$C3" 4 ;;     # per pass: serial chain walk (empty), symbols, regular -> the symbol executor of pass 2
+    lz3) full lz3 "k_inflate_lz" "$C3" 5 ;;     # the byte executor of pass 2 on configs[2]
+    win) full win "k_seg_window" "$C3" 1 ;;
+    tr) full tr "k_seg_translate" "$C3" 1 ;;
   esac
 done
