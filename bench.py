@@ -819,6 +819,17 @@ def main():
         args.scaling = "weak"   # (written by the GPU compressor of every rank: one archive per rank)
     from otezip_b200 import Ctx
     ctx = Ctx(dist.local)
+    # pinned host buffers are placed where the allocating thread runs: keep this rank on the CPUs of its GPU's NUMA node
+    numa = None
+    try:
+        cpus = numa_cpus_of_gpu(ctx.pci_bus_id())
+        if cpus:
+            cpus &= os.sched_getaffinity(0)
+            if cpus:
+                os.sched_setaffinity(0, cpus)
+                numa = "rank bound to the %d CPUs of its GPU's NUMA node" % len(cpus)
+    except Exception:
+        pass
     sampler = ClockSampler(ctx.pci_bus_id())
     sampler.start()
     n = args.entries or DEFAULT_ENTRIES[args.workload]
@@ -834,6 +845,8 @@ def main():
         "dtype": "u8", "data": "synthetic", "config": wl_config(args.workload, n, dist.world, args.scaling),
         "run": res["run"], "roofline": res["roofline"], "e2e": res["e2e"], "gpu_launches": res["gpu_launches"], "clocks": clocks,
     }
+    if numa:
+        line["run"]["host_placement"] = numa
     if dist.world == 1 and dist.rank == 0:
         if not args.no_cpu_baseline:
             try:
