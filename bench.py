@@ -43,13 +43,15 @@ WORKLOADS = {
     "c4": "configs[3]: method 93 decode of 10,000 entries of 256 KiB (the reference's method-93 container)",
     "c4z": "configs[3] shape with real Zstandard (RFC 8878) frames from libzstd level 3 (parity pinned by libzstd, not by the reference)",
     "c5": "configs[4]: archive creation, batched DEFLATE compress + CRC-32, 4 GiB synthetic corpus",
+    "c5z": "configs[4] shape, method 93: batched Zstandard compress (real RFC 8878 frames) + CRC-32, 4 GiB synthetic corpus",
     "c3w": "configs[2] shape, archive written by this library (chunk-indexed DEFLATE entries)",
     "c2x": "configs[1] shape, STORE entries extracted (copied to the arena) and CRC-checked",
 }
-DEFAULT_ENTRIES = {"c3": 10000, "c1": 1000, "c2": 10000, "c2x": 10000, "c4": 10000, "c4z": 10000, "c5": 16384, "c3w": 2000}
+DEFAULT_ENTRIES = {"c3": 10000, "c1": 1000, "c2": 10000, "c2x": 10000, "c4": 10000, "c4z": 10000, "c5": 16384, "c5z": 16384, "c3w": 2000}
 METRIC = {
     "c2": "CRC-32 verify GB/s (STORE payload bytes, device-timed)",
     "c5": "compress GB/s (uncompressed input, device-timed; CRC-32 + DEFLATE + compaction)",
+    "c5z": "compress GB/s (uncompressed input, device-timed; CRC-32 + Zstandard + compaction)",
 }
 DECODE_KERNELS = {
     "c1": "k_inflate_spec + k_inflate_lz (+ k_inflate for declined streams)",
@@ -59,7 +61,7 @@ DECODE_KERNELS = {
 }
 # stride of the entry subsample the CPU legs time (the reference needs ~1 min per pass of configs[2] on
 # 16 cores; every stride-th entry of the same list keeps the size distribution)
-REF_STRIDE = {"c3": 16, "c1": 1, "c2": 16, "c2x": 16, "c4": 4, "c4z": 4, "c3w": 16, "c5": 16}
+REF_STRIDE = {"c3": 16, "c1": 1, "c2": 16, "c2x": 16, "c4": 4, "c4z": 4, "c3w": 16, "c5": 16, "c5z": 16}
 
 
 def metric_name(wl: str) -> str:
@@ -84,9 +86,9 @@ def entry_plan(name: str, n: int):
     if name == "c4z":
         return dict(sizes=[262144] * n, method=93, seed=4, sizes_desc="256 KiB each", data="JSON-log text (synth.TextPool, seed 4)",
                     codec="method 93, real Zstandard frames (libzstd level 3)")
-    if name == "c5":
-        return dict(sizes=[262144] * n, method=8, seed=5, sizes_desc="256 KiB each", data="JSON-log text (synth.TextPool, seed 5)",
-                    codec="DEFLATE compress (GPU), zero-length / incompressible -> STORE")
+    if name in ("c5", "c5z"):
+        return dict(sizes=[262144] * n, method=8 if name == "c5" else 93, seed=5, sizes_desc="256 KiB each", data="JSON-log text (synth.TextPool, seed 5)",
+                    codec=("DEFLATE" if name == "c5" else "Zstandard (real frames)") + " compress (GPU), zero-length / incompressible -> STORE")
     raise SystemExit("unknown workload " + name)
 
 
@@ -398,7 +400,7 @@ def reference_sample(wl_name: str, n_entries: int | None, tmpdir: str):
     """The CPU legs' input: every stride-th entry of the workload's own entry list (same sizes, same text, same codec)
     as ZIP32 file(s) on disk (the reference reads FILE*).  -> (paths, per-file entry sizes, bytes, description)"""
     n = n_entries or DEFAULT_ENTRIES[wl_name]
-    name = "c4" if wl_name == "c4z" else ("c3" if wl_name in ("c3w", "c5") else wl_name)   # the reference rejects real Zstandard frames (F3)
+    name = "c4" if wl_name == "c4z" else ("c3" if wl_name in ("c3w", "c5", "c5z") else wl_name)   # the reference rejects real Zstandard frames (F3)
     stride = REF_STRIDE[wl_name]
     idx = list(range(0, n, stride))
     bufs = []
@@ -421,7 +423,7 @@ def reference_sample(wl_name: str, n_entries: int | None, tmpdir: str):
         stride, "th" if stride != 1 else "st", len(idx), wl["uncomp_bytes"] / GB)
     if wl_name == "c4z":
         what += "; reference-container payloads — the reference rejects real Zstandard frames (SURVEY F3)"
-    if wl_name == "c5":
+    if wl_name in ("c5", "c5z"):
         what += "; the reference's DEFLATE writer is broken (SURVEY F2), so the CPU leg is its READ path over the same text"
     return paths, sizes, wl["uncomp_bytes"], what
 
@@ -499,7 +501,7 @@ def run_reference(args, dist: Dist):
 
 
 # ----------------------------------------------------------------------------- GPU arm: the write path (configs[4])
-def run_c5(ctx, dist: "Dist", n_entries, steps, warmup, e2e_steps, sampler=None):
+def run_c5(ctx, dist: "Dist", n_entries, steps, warmup, e2e_steps, sampler=None, method=8):
     """configs[4]: archive creation — batched DEFLATE compress + CRC-32 of a synthetic corpus (default 16,384 x 256 KiB
     JSON-log = 4 GiB), device-timed; every stream verified through zlib and the compiled reference."""
     import ctypes as C
@@ -518,7 +520,7 @@ def run_c5(ctx, dist: "Dist", n_entries, steps, warmup, e2e_steps, sampler=None)
         srcs.append(d)
     in_ofs = np.arange(m, dtype=np.uint64) * size
     in_len = np.full(m, size, dtype=np.uint32)
-    meth = np.full(m, 8, dtype=np.uint16)
+    meth = np.full(m, method, dtype=np.uint16)
     d_in = ctx.dev_alloc(img.nbytes)
     ctx.h2d(d_in, img)
     job = ctx.deflate_plan(in_ofs, in_len, meth)
@@ -543,13 +545,21 @@ def run_c5(ctx, dist: "Dist", n_entries, steps, warmup, e2e_steps, sampler=None)
     out = ctx.deflate_fetch(job, total)
 
     # verification: every stream through zlib, CRCs against zlib.crc32, every stream through the compiled reference
+    zs = None
+    if method == 93:
+        from otezip_b200.zstdlib import Zstd
+        zs = Zstd()
+
     def chk(i):
         p = bytes(out[int(ofs[i]):int(ofs[i]) + int(sz[i])])
-        return (zlib.decompress(p, -15) if mo[i] == 8 else p) == srcs[i] and int(crc[i]) == (zlib.crc32(srcs[i]) & 0xFFFFFFFF)
+        dec = zlib.decompress(p, -15) if mo[i] == 8 else zs.decompress(p, size) if mo[i] == 93 else p
+        return dec == srcs[i] and int(crc[i]) == (zlib.crc32(srcs[i]) & 0xFFFFFFFF)
     with cf.ThreadPoolExecutor(NCPU) as ex:
         n_ok = sum(ex.map(chk, range(m)))
     ref_ok, ref_n = None, 0
     try:
+        if method == 93:
+            raise RuntimeError("the reference rejects real Zstandard frames (SURVEY F3): libzstd is the checker")
         from oracle import RefLib
         ref = RefLib()
         # ZIP32 archives of <= 3 GiB of payload each, read back by the reference on all cores
@@ -612,10 +622,10 @@ def run_c5(ctx, dist: "Dist", n_entries, steps, warmup, e2e_steps, sampler=None)
     algo = m * size + total
     achieved = algo / (ms / steps / 1e3) / GB
     return {
-        "metric": metric_name("c5"), "value": tot_in * steps / (ms_max / 1e3) / GB, "unit": "GB/s", "ms_per_step": ms_max / steps,
+        "metric": metric_name("c5" if method == 8 else "c5z"), "value": tot_in * steps / (ms_max / 1e3) / GB, "unit": "GB/s", "ms_per_step": ms_max / steps,
         "run": {"entries_this_rank": m, "compressed_bytes": int(tot_out), "ratio": tot_in / max(tot_out, 1.0), "reference_ratio_same_level": 4.36,
-                "zlib6_ratio": 9.0, "verified": {"zlib_streams_ok": n_ok, "compiled_reference_streams_ok": ref_n if ref_ok is True else ref_ok, "of": m}},
-        "roofline": {"bound": "hbm", "kernel": "k_deflate_chunks (+crc, scan, gather)", "achieved": achieved, "peak": peak, "unit": "GB/s",
+                "zlib6_ratio": 9.0, "verified": {("zlib_streams_ok" if method == 8 else "libzstd_frames_ok"): n_ok, "compiled_reference_streams_ok": ref_n if ref_ok is True else ref_ok, "of": m}},
+        "roofline": {"bound": "hbm", "kernel": "k_deflate_chunks%s (+crc, scan, gather)" % ("" if method == 8 else " -> zse_emit_block"), "achieved": achieved, "peak": peak, "unit": "GB/s",
                      "frac": achieved / peak, "traffic": None, "peak_source": peak_src, "algorithmic_bytes": int(algo)},
         "e2e": {"value": tot_in * e2e_steps / e2e_max / GB, "unit": "GB/s", "h2d_bytes_per_step": int(img.nbytes),
                 "d2h_bytes_per_step": int(total + 18 * m), "steps": e2e_steps,
@@ -834,8 +844,8 @@ def main():
     sampler.start()
     n = args.entries or DEFAULT_ENTRIES[args.workload]
     e2e_steps = args.e2e_steps or max(3, min(args.steps, 5))
-    if args.workload == "c5":
-        res = run_c5(ctx, dist, args.entries, args.steps, args.warmup, e2e_steps, sampler)
+    if args.workload in ("c5", "c5z"):
+        res = run_c5(ctx, dist, args.entries, args.steps, args.warmup, e2e_steps, sampler, 8 if args.workload == "c5" else 93)
     else:
         res = run_extract(ctx, dist, args.workload, args.entries, args.steps, args.warmup, e2e_steps, args.scaling, sampler)
     clocks = sampler.summary()
@@ -856,9 +866,9 @@ def main():
         if not args.no_secondary and args.workload == "c3" and args.entries is None:
             # the other BASELINE configurations, same process, fewer steps: nothing the headline change would hide
             sec = {}
-            for w in ("c1", "c2", "c4", "c4z", "c5"):
+            for w in ("c1", "c2", "c4", "c4z", "c5", "c5z"):
                 try:
-                    r = (run_c5(ctx, dist, None, 3, 3, 1) if w == "c5" else run_extract(ctx, dist, w, None, 5, 3, 2))
+                    r = (run_c5(ctx, dist, None, 3, 3, 1, None, 8 if w == "c5" else 93) if w in ("c5", "c5z") else run_extract(ctx, dist, w, None, 5, 3, 2))
                     sec[w] = {"workload": WORKLOADS[w], "metric": r["metric"], "value": r["value"], "unit": "GB/s", "ms_per_step": r["ms_per_step"],
                               "roofline_frac": r["roofline"]["frac"], "roofline_kernel": r["roofline"]["kernel"], "e2e": r["e2e"]["value"],
                               "run": r["run"]}

@@ -190,5 +190,10 @@ extern int otezip_ref_compat;
  * from the central directory, otezip.c:355-358, :371-377), and so does this one.  Default 0: the reference's layout.
  * Also set by the environment variable OTEZIP_DATA_DESCRIPTORS=1. */
 extern int otezip_write_data_descriptors;
+/* Extension: 1 = method 93 means REAL Zstandard (RFC 8878) frames on both paths: zip_close
+ * compresses entries set to ZIP_CM_ZSTD / `-z zstd` with the GPU Zstandard encoder (the reference's raw-block stub always
+ * ends up at STORE, otezip.c:894-899), and zip_fopen_index hands out real frames, which the reference's reader rejects
+ * (SURVEY F3).  Default 0: the reference's observable behaviour.  Also set by OTEZIP_ZSTD_FRAMES=1. */
+extern int otezip_zstd_frames;
 
 #endif /* OTEZIP_H_ */

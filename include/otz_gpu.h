@@ -153,7 +153,9 @@ int otz_extract_host(otz_ctx *ctx, const uint8_t *archive, uint64_t archive_len,
 
 /* ---- write path ----
  * Batched otezip_compress_data (otezip.c:788-852) + CRC (otezip.c:1124) for n sources laid out in one
- * input buffer: source i = in[in_ofs[i] .. in_ofs[i]+in_len[i]), requested method[i] in {0, 8}.
+ * input buffer: source i = in[in_ofs[i] .. in_ofs[i]+in_len[i]), requested method[i] in {0, 8, 93}
+ * (93: real Zstandard frames, one block per 65,280-byte chunk, k_zstd_enc.cuh — an extension: the reference's method-93
+ * writer is a stub that always ends up at STORE).
  * Per source: zero length -> STORE; DEFLATE whose stream is not smaller than the input -> STORE
  * (otezip.c:793-801, :846-850).  Results: method_out[i], out_size[i], out_ofs[i] (offset in the dense
  * output arena), crc[i] = CRC-32 of the uncompressed bytes. */

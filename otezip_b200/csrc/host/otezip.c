@@ -41,6 +41,7 @@ uint64_t otezip_max_expansion_slack = 1024ULL * 1024ULL;
 int otezip_ignore_zipbomb = 0;
 int otezip_ref_compat = 1;
 int otezip_write_data_descriptors = 0;
+int otezip_zstd_frames = 0;
 
 /* ---- private archive state; `pub` must stay first: zip_t* == struct otz_archive* ---- */
 struct otz_window {               /* one decoded batch of consecutive entries */
@@ -520,6 +521,7 @@ zip_t *zip_open_from_source(zip_source_t *src, int flags, zip_error_t *error) {
 }
 
 static int finalize_archive(struct otz_archive *a);
+static int zstd_frames(void);
 
 int zip_close(zip_t *za) {
 	struct otz_archive *a = priv (za);
@@ -1010,7 +1012,7 @@ zip_file_t *zip_fopen_index(zip_t *za, zip_uint64_t index, zip_flags_t flags) {
 			e->name ? e->name : "<unknown>", e->uncomp_size);
 		return NULL;
 	}
-	if (OTZ_ST_CODE (st) != OTZ_ST_OK || (otezip_ref_compat && (st & OTZ_STF_REF_EOB))) {
+	if (OTZ_ST_CODE (st) != OTZ_ST_OK || (otezip_ref_compat && (st & OTZ_STF_REF_EOB) && !(e->method == OTEZIP_METHOD_ZSTD && zstd_frames ()))) {
 		return NULL;
 	}
 	if (st & OTZ_STF_CRC_MISMATCH) { /* otezip.c:669-678 */
@@ -1223,6 +1225,15 @@ int zip_replace(zip_t *za, zip_uint64_t index, zip_source_t *src) {
 }
 
 /* otezip.c:1443-1491 */
+/* 1: method 93 means real Zstandard frames on both paths — zip_close compresses entries whose
+ * method is ZSTD with the GPU Zstandard encoder (k_zstd_enc.cuh) instead of ending up at STORE as the reference's raw-block
+ * stub always does (otezip.c:894-899), and zip_fopen_index hands out the bytes of real frames although the reference's
+ * reader rejects them (F3).  Default 0: the reference's observable behaviour. */
+static int zstd_frames(void) {
+	const char *e = getenv ("OTEZIP_ZSTD_FRAMES");
+	return otezip_zstd_frames || (e && *e && *e != '0');
+}
+
 static int streaming_layout(void) {
 	const char *e = getenv ("OTEZIP_DATA_DESCRIPTORS");
 	return otezip_write_data_descriptors || (e && *e && *e != '0');
@@ -1350,7 +1361,7 @@ static int finalize_archive(struct otz_archive *a) {
 			in_len[k] = (uint32_t)a->pend[idx[k]].len;
 			/* method 93: the reference's writer cannot produce a stream its reader accepts and always falls
 			 * back to STORE (zstd.inc.c:269, otezip.c:894-899) — same result here */
-			method[k] = e->method == OTEZIP_METHOD_DEFLATE ? OTZ_M_DEFLATE : OTZ_M_STORE;
+			method[k] = e->method == OTEZIP_METHOD_DEFLATE ? OTZ_M_DEFLATE : (e->method == OTEZIP_METHOD_ZSTD && zstd_frames ()) ? OTZ_M_ZSTD : OTZ_M_STORE;
 			total += ((uint64_t)in_len[k] + 15) & ~15ULL;
 		}
 		void *pin = NULL, *pout = NULL;

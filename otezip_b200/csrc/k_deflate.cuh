@@ -24,6 +24,7 @@
 #pragma once
 #include "otz_common.cuh"
 #include "k_copy.cuh"
+#include "k_zstd_enc.cuh"
 
 #define DFL_CHUNK 65280u                      // <= 65535 so the stored fallback is one block
 #define DFL_OUT_STRIDE (DFL_CHUNK + 256u)     // per-chunk output slot (4-byte aligned)
@@ -35,8 +36,8 @@ struct OtzDflChunk {
 	uint64_t in_ofs;     // absolute offset of the chunk in the input buffer
 	uint32_t len;
 	uint32_t entry;
-	uint32_t last;       // last chunk of its entry
-	uint32_t pad;
+	uint32_t last;       // bit 0: last chunk of its entry, bit 1: first chunk, bit 2: method 93 (Zstandard block instead of DEFLATE)
+	uint32_t pad;        // length of the whole entry (Frame_Content_Size of a Zstandard frame)
 };
 
 struct __align__(16) DeflateSmem {
@@ -384,6 +385,15 @@ __global__ void __launch_bounds__(32 * DFL_WARPS) k_deflate_chunks(const uint8_t
 			cur += i;
 		}
 		__syncwarp();
+		if (ck.last & 4u) {
+			// method 93: the same tokens as one Zstandard block (k_zstd_enc.cuh)
+			const uint32_t ob = zse_emit_block(in + ck.in_ofs, n, tok, ntok, co, (ck.last & 2u) != 0u, (ck.last & 1u) != 0u, ck.pad, lane);
+			if (lane == 0) {
+				csize[ci] = ob;
+			}
+			__syncwarp();
+			continue;
+		}
 		xbits = S.misc[0];
 		if (lane == 0) {
 			S.hist_ll[256] = 1;   // end of block
@@ -471,7 +481,7 @@ __global__ void __launch_bounds__(32 * DFL_WARPS) k_deflate_chunks(const uint8_t
 		if (dyn_bytes >= stored_bytes) {
 			// ---------------- stored block: [BFINAL|00 padded][LEN][NLEN][bytes]
 			if (lane == 0) {
-				co[0] = (uint8_t)(ck.last ? 1 : 0);
+				co[0] = (uint8_t)(ck.last & 1u);
 				co[1] = (uint8_t)(n & 0xFF);
 				co[2] = (uint8_t)(n >> 8);
 				co[3] = (uint8_t)(~n & 0xFF);
@@ -571,7 +581,7 @@ __global__ void __launch_bounds__(32 * DFL_WARPS) k_deflate_chunks(const uint8_t
 				bw.acc = carry;
 				bw.nacc = off0;
 				bw.put(S.u.b.code_ll[256], S.u.b.len_ll[256]);   // end of block
-				bw.put(ck.last ? 1u : 0u, 3);              // empty stored block: BFINAL, BTYPE=00
+				bw.put(ck.last & 1u, 3);              // empty stored block: BFINAL, BTYPE=00
 				if (bw.nacc & 7) {
 					bw.put(0, 8 - (bw.nacc & 7));           // pad to a byte boundary
 				}
@@ -616,14 +626,15 @@ __global__ void k_deflate_entry_sizes(const OtzDflEntry *__restrict__ ents, uint
 	}
 	const OtzDflEntry e = ents[i];
 	uint64_t tot = 0;
-	if (e.method_in == OTZ_M_DEFLATE) {
+	const bool coded = e.method_in == OTZ_M_DEFLATE || e.method_in == OTZ_M_ZSTD;
+	if (coded) {
 		for (uint32_t k = 0; k < e.n_chunks; k++) {
 			tot += csize[e.first_chunk + k];
 		}
 	}
-	const bool deflated = e.method_in == OTZ_M_DEFLATE && e.len > 0 && tot < e.len;
-	method_out[i] = deflated ? OTZ_M_DEFLATE : OTZ_M_STORE;
-	out_size[i] = deflated ? (uint32_t)tot : e.len;
+	const bool smaller = coded && e.len > 0 && tot < e.len;   // otezip.c:846-850 / :894-899: a stream that is not smaller is stored
+	method_out[i] = smaller ? e.method_in : OTZ_M_STORE;
+	out_size[i] = smaller ? (uint32_t)tot : e.len;
 }
 
 // exclusive scan of out_size[] into out_ofs[] (single CTA; n <= a few hundred thousand)
@@ -666,7 +677,7 @@ __global__ void __launch_bounds__(256) k_deflate_gather(const uint8_t *__restric
 		const OtzDflChunk ck = chunks[c];
 		const OtzDflEntry e = ents[ck.entry];
 		const uint32_t k = c - e.first_chunk;
-		if (method_out[ck.entry] == OTZ_M_DEFLATE) {
+		if (method_out[ck.entry] != OTZ_M_STORE) {
 			uint64_t off = 0;
 			for (uint32_t j = lane; j < k; j += 32) {
 				off += csize[e.first_chunk + j];

@@ -43,7 +43,7 @@
 #define I3_SMAX 512        // bits per piece (lane and round), at most
 #define I3_PIECE_WORDS (I3_SMAX / 32 + 3)   // a lane's staged words: its piece + the 3 words a symbol may run over
 #define I3_BAD 4u          // (kinds 0..3 are I2_K_*)
-#define I3_SEG_MIN 262144u // least output bytes of a segment of a huge stream (k_seg_window resolves the last 32 KiB of each one serially)
+#define I3_SEG_MIN 524288u // least output bytes of a segment of a huge stream (k_seg_window resolves the last 32 KiB of each one serially)
 
 struct I3BuildScratch {
 	uint32_t cnt[16];
@@ -229,7 +229,7 @@ template <int NW, int MINB = (NW == 1 ? 8 : 16 / NW)>
 __global__ void __launch_bounds__(32 * (NW == 1 ? I3_WARPS : NW), MINB) k_inflate_spec(const uint8_t *__restrict__ archive,
 	const otz_entry *__restrict__ ents, const OtzEntryState *__restrict__ est, const int32_t *__restrict__ status, const uint32_t *__restrict__ list,
 	uint32_t k0, uint32_t k1, uint32_t *__restrict__ work_counter, uint8_t *__restrict__ scratch, const uint64_t *__restrict__ tok_ofs,
-	I2TokRes *__restrict__ tokres, uint32_t *__restrict__ fb_list, uint32_t *__restrict__ fb_count, uint32_t n_huge, I2SegCtl seg) {
+	I2TokRes *__restrict__ tokres, uint32_t *__restrict__ fb_list, uint32_t *__restrict__ fb_count, uint32_t n_huge, I2SegCtl seg, uint32_t seg_min) {
 	extern __shared__ __align__(16) uint8_t smem_raw[];
 	constexpr uint32_t G = 32u * NW;
 	const uint32_t lane = threadIdx.x & 31u;
@@ -288,7 +288,7 @@ __global__ void __launch_bounds__(32 * (NW == 1 ? I3_WARPS : NW), MINB) k_inflat
 		uint32_t final_blk = 0, ref_eob = 0;
 		// HUGE: the open segment
 		uint32_t nseg = 0, sg_lit0 = 0, sg_seq0 = 0, sg_out0 = 0, sg_minsrc = 0xFFFFFFFFu;
-		const uint32_t sg_target = max(I3_SEG_MIN, cap / (I2_MAXSEG - 8u) + 1u);
+		const uint32_t sg_target = max(seg_min, cap / (I2_MAXSEG - 8u) + 1u);
 		uint32_t act = comp == 0u ? I3_A_FALLBACK : I3_A_NONE;   // dec:610: k_inflate answers TRUNCATED
 		if (huge && tid == 0) {
 			seg.start[k * I2_MAXSEG] = 0u;

@@ -221,6 +221,11 @@ extern "C" int otz_ctx_create(int device, otz_ctx **out) {
 			CK(cudaEventCreate(&e));
 		}
 	}
+	{
+		ZseTables zt;   // Zstandard encoder tables (predefined distributions) -> constant memory of this device
+		zse_build_tables(&zt);
+		CK(cudaMemcpyToSymbol(c_zse, &zt, sizeof(zt)));
+	}
 	OtzCrcTables *h = new OtzCrcTables();
 	build_crc_tables(h);
 	CK(cudaMalloc(&c->d_tabs, sizeof(OtzCrcTables)));
@@ -735,6 +740,8 @@ static int dispatch_inflate3(otz_ctx *c, otz_plan *p, const uint8_t *d_archive, 
 	const uint32_t nh = (p->n_inflate_huge && p->seg.count && !c->huge_legacy) ? p->n_inflate_huge : 0u;
 	const uint32_t count = p->n_inflate - nh;
 	const char *gs = getenv("OTZ_SPEC_GRID");   // (tests: few groups, so that every group decodes many streams)
+	const char *sm_ = getenv("OTZ_SEG_MIN");       // least output bytes of a segment (>= I3_SEG_MIN: the symbol buffer is sized for that)
+	const uint32_t seg_min = sm_ ? std::max<uint32_t>(I3_SEG_MIN, (uint32_t)strtoul(sm_, nullptr, 0)) : I3_SEG_MIN;
 	bool forked = false;
 	if (nh) {
 		// huge streams: the 4 warps of a CTA decode one stream together; second stream, next to the warp-per-stream kernel
@@ -751,7 +758,7 @@ static int dispatch_inflate3(otz_ctx *c, otz_plan *p, const uint8_t *d_archive, 
 		}
 		const uint32_t grid4 = gs ? (uint32_t)atoi(gs) : std::max(1u, std::min((uint32_t)(c->sm_count * per_sm4), nh));
 		kern4<<<grid4, 128, smem4, s2>>>(d_archive, p->d_ents, p->d_est, p->d_status, p->d_inflate_list, 0u, nh, p->d_counter + 57,
-			c->d_tok_cache, p->d_tok_ofs, p->d_tokres, p->d_fb_list, p->d_counter + 52, nh, p->seg);
+			c->d_tok_cache, p->d_tok_ofs, p->d_tokres, p->d_fb_list, p->d_counter + 52, nh, p->seg, seg_min);
 		c->launches++;
 		CK(cudaGetLastError());
 	}
@@ -764,7 +771,7 @@ static int dispatch_inflate3(otz_ctx *c, otz_plan *p, const uint8_t *d_archive, 
 		}
 		const uint32_t grid = gs ? (uint32_t)atoi(gs) : std::max(1u, std::min((uint32_t)(c->sm_count * per_sm), (count + I3_WARPS - 1) / I3_WARPS));
 		k_inflate_spec<1><<<grid, 32 * I3_WARPS, smem1, s>>>(d_archive, p->d_ents, p->d_est, p->d_status, p->d_inflate_list, nh, p->n_inflate, p->d_counter,
-			c->d_tok_cache, p->d_tok_ofs, p->d_tokres, p->d_fb_list, p->d_counter + 52, nh, p->seg);
+			c->d_tok_cache, p->d_tok_ofs, p->d_tokres, p->d_fb_list, p->d_counter + 52, nh, p->seg, seg_min);
 		c->launches++;
 		CK(cudaGetLastError());
 	}
@@ -1537,7 +1544,7 @@ extern "C" int otz_deflate_plan(otz_ctx *c, const uint64_t *in_ofs, const uint32
 	std::vector<OtzCrcChunk> cchunks;
 	uint64_t total = 0;
 	for (uint32_t i = 0; i < n; i++) {
-		if (method[i] != OTZ_M_STORE && method[i] != OTZ_M_DEFLATE) {
+		if (method[i] != OTZ_M_STORE && method[i] != OTZ_M_DEFLATE && method[i] != OTZ_M_ZSTD) {
 			delete j;
 			snprintf(g_err, sizeof(g_err), "otz_deflate_plan: method %u is not on the GPU write path", method[i]);
 			return OTZ_ERR_ARG;
@@ -1555,8 +1562,8 @@ extern "C" int otz_deflate_plan(otz_ctx *c, const uint64_t *in_ofs, const uint32
 			ck.in_ofs = in_ofs[i] + (uint64_t)k * DFL_CHUNK;
 			ck.len = std::min<uint32_t>(DFL_CHUNK, in_len[i] - k * DFL_CHUNK);
 			ck.entry = i;
-			ck.last = (k + 1 == nc);
-			ck.pad = 0;
+			ck.last = (k + 1 == nc ? 1u : 0u) | (k == 0 ? 2u : 0u) | (method[i] == OTZ_M_ZSTD ? 4u : 0u);
+			ck.pad = in_len[i];
 			chunks.push_back(ck);
 		}
 		otz_entry &ce = cents[i];

@@ -303,3 +303,87 @@ def test_streaming_layout_with_data_descriptors(tmp_path, reflib):
     assert api.read_all(p)[2] == [d for _, d in files]
     e2, got = reflib.extract_file(p, verify_crc=1)
     assert e2 == 0 and got == [d for _, d in files]
+
+
+def test_zstandard_writer_real_frames(tmp_path, capfd):
+    """with otezip_zstd_frames (OTEZIP_ZSTD_FRAMES=1) `zip_set_file_compression(ZIP_CM_ZSTD)` produces REAL
+    Zstandard frames (k_zstd_enc.cuh) instead of ending up at STORE.  Every payload is decoded by libzstd (the format's
+    reference decoder) and by this library's own GPU decoder, bit for bit; incompressible and empty sources still fall
+    back to STORE (otezip.c:793-801, :894-899); without the switch the reference's behaviour stays: everything STORE."""
+    import zipfile
+    from otezip_b200.zstdlib import Zstd
+    api = ZipApi()
+    zs = Zstd()
+    rnd = __import__("random").Random(3)
+    files = [("log.json", synth.jsonlog_text(300000, 11)), ("small.txt", b"hello hello hello hello hello hello\n"), ("empty", b""),
+             ("rand.bin", synth.random_bytes(50000, 12)), ("runs", b"ab" * 40000 + b"x" * 70000), ("one", b"z"),
+             ("far", synth.random_bytes(30000, 13) * 3), ("big.json", synth.jsonlog_text((1 << 20) + 777, 14)),
+             ("mixed", synth.jsonlog_text(90000, 15) + synth.random_bytes(70000, 16) + synth.jsonlog_text(50000, 17)),
+             ("lits", bytes(rnd.randrange(97, 123) for _ in range(20000)))]
+    flag = C.c_int.in_dll(api.L, "otezip_zstd_frames")
+    p = str(tmp_path / "z.zip")
+    flag.value = 1
+    try:
+        assert api.write_archive(p, files, 93) == 0
+        with zipfile.ZipFile(p) as z:
+            infos = z.infolist()
+        raw = open(p, "rb").read()
+        n93 = 0
+        for info, (name, data) in zip(infos, files):
+            nl, xl = struct.unpack_from("<HH", raw, info.header_offset + 26)
+            payload = raw[info.header_offset + 30 + nl + xl:info.header_offset + 30 + nl + xl + info.compress_size]
+            assert info.file_size == len(data) and info.CRC == zlib.crc32(data)
+            if info.compress_type == 93:
+                n93 += 1
+                assert payload[:4] == b"\x28\xb5\x2f\xfd" and len(payload) < len(data)
+                assert zs.decompress(payload, len(data)) == data, name           # libzstd reads the frame
+            else:
+                assert info.compress_type == 0 and payload == data, name
+        types = dict((i.filename, i.compress_type) for i in infos)
+        print(types)
+        assert n93 >= 4 and all(types[k] == 93 for k in ("log.json", "runs", "big.json", "mixed")), types
+        assert all(types[k] == 0 for k in ("empty", "rand.bin", "one")), types   # not smaller than the input: STORE
+        assert infos[0].compress_size * 4 < infos[0].file_size                     # the log text really is compressed
+        err, names, datas = api.read_all(p)                                         # and so does the GPU decoder
+        assert err == 0 and datas == [d for _, d in files]
+    finally:
+        flag.value = 0
+    # the reference's observable behaviour without the switch: method 93 ends up at STORE, and real frames are not handed out
+    q = str(tmp_path / "s.zip")
+    assert api.write_archive(q, files[:2], 93) == 0
+    with zipfile.ZipFile(q) as z:
+        assert [i.compress_type for i in z.infolist()] == [0, 0]
+    err, names, datas = api.read_all(p)
+    assert datas[0] is None and datas[2] == b""
+    capfd.readouterr()
+
+
+@pytest.mark.skipif(not os.path.exists(os.path.join(REFDIR, "otezip_relinked")), reason="relinked CLI not built")
+def test_cli_create_with_zstd_frames(tmp_path):
+    """`otezip -c a.zip files -z zstd` through the unchanged main.c (it sets za->default_method, main.c:188-191): with
+    OTEZIP_ZSTD_FRAMES=1 the compressible file becomes a method-93 entry holding a frame libzstd decodes, and
+    `otezip -x` (same switch) extracts the tree again."""
+    import zipfile
+    from otezip_b200.zstdlib import Zstd
+    src = tmp_path / "src"
+    src.mkdir()
+    files = {"a.json": synth.jsonlog_text(150000, 21), "b.bin": synth.random_bytes(2000, 22)}
+    for n, d in files.items():
+        (src / n).write_bytes(d)
+    z = tmp_path / "c.zip"
+    env = dict(os.environ, OTEZIP_ZSTD_FRAMES="1")
+    r = subprocess.run([os.path.join(REFDIR, "otezip_relinked"), "-c", str(z)] + list(files) + ["-z", "zstd"], cwd=src, capture_output=True, text=True,
+                       timeout=120, env=env)
+    assert r.returncode == 0, r.stderr
+    raw = z.read_bytes()
+    with zipfile.ZipFile(z) as zf:
+        infos = {i.filename: i for i in zf.infolist()}
+    assert infos["a.json"].compress_type == 93 and infos["b.bin"].compress_type == 0
+    i = infos["a.json"]
+    nl, xl = struct.unpack_from("<HH", raw, i.header_offset + 26)
+    payload = raw[i.header_offset + 30 + nl + xl:i.header_offset + 30 + nl + xl + i.compress_size]
+    assert Zstd().decompress(payload, i.file_size) == files["a.json"]
+    out = tmp_path / "out"
+    out.mkdir()
+    r = subprocess.run([os.path.join(REFDIR, "otezip_relinked"), "-x", str(z), "--verify-crc"], cwd=out, capture_output=True, text=True, timeout=120, env=env)
+    assert r.returncode == 0 and _tree(out) == files
