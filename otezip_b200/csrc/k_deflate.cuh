@@ -256,6 +256,8 @@ __device__ __noinline__ void dfl_build_code(DeflateSmem &S, uint32_t *hist, int 
 
 // grid: persistent; one warp per chunk, chunks handed out in order.
 #define DFL_WARPS 3   // warps per CTA: seven CTAs (21 chunks) fit the shared memory of an SM
+// ZSTD: the job holds method-93 entries (their chunks become Zstandard blocks); a pure DEFLATE job runs the instantiation without that path
+template <bool ZSTD>
 __global__ void __launch_bounds__(32 * DFL_WARPS) k_deflate_chunks(const uint8_t *__restrict__ in, const OtzDflChunk *__restrict__ chunks, uint32_t n_chunks,
 	uint32_t *__restrict__ tokens /* DFL_CHUNK per chunk slot */, uint8_t *__restrict__ cout, uint32_t *__restrict__ csize,
 	uint32_t *__restrict__ work_counter, uint32_t n_slots) {
@@ -385,7 +387,7 @@ __global__ void __launch_bounds__(32 * DFL_WARPS) k_deflate_chunks(const uint8_t
 			cur += i;
 		}
 		__syncwarp();
-		if (ck.last & 4u) {
+		if (ZSTD && (ck.last & 4u)) {
 			// method 93: the same tokens as one Zstandard block (k_zstd_enc.cuh)
 			const uint32_t ob = zse_emit_block(in + ck.in_ofs, n, tok, ntok, co, (ck.last & 2u) != 0u, (ck.last & 1u) != 0u, ck.pad, lane);
 			if (lane == 0) {

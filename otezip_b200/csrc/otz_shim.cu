@@ -1489,6 +1489,7 @@ extern "C" int otz_status_accepts(int32_t st, int verify_crc, int ref_compat) {
 
 // ---------------------------------------------------------------- write path
 struct otz_deflate_job {
+	bool has_zstd;   // some entry asks for method 93: the compressor instantiation with the Zstandard block writer
 	uint32_t n, n_chunks, n_crc_chunks, n_slots;
 	uint64_t in_total;
 	OtzDflEntry *d_ents;
@@ -1564,6 +1565,7 @@ extern "C" int otz_deflate_plan(otz_ctx *c, const uint64_t *in_ofs, const uint32
 			ck.entry = i;
 			ck.last = (k + 1 == nc ? 1u : 0u) | (k == 0 ? 2u : 0u) | (method[i] == OTZ_M_ZSTD ? 4u : 0u);
 			ck.pad = in_len[i];
+			j->has_zstd = j->has_zstd || method[i] == OTZ_M_ZSTD;
 			chunks.push_back(ck);
 		}
 		otz_entry &ce = cents[i];
@@ -1635,11 +1637,12 @@ extern "C" int otz_deflate_run(otz_ctx *c, otz_deflate_job *j, const uint8_t *d_
 		const size_t smem = DFL_WARPS * sizeof(DeflateSmem);
 		static bool attr_done = false;
 		if (!attr_done) {
-			CK(cudaFuncSetAttribute(k_deflate_chunks, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+			CK(cudaFuncSetAttribute(k_deflate_chunks<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+			CK(cudaFuncSetAttribute(k_deflate_chunks<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
 			attr_done = true;
 		}
-		k_deflate_chunks<<<j->grid, 32 * DFL_WARPS, smem, s>>>(d_in, j->d_chunks, j->n_chunks, j->d_tokens, j->d_cout, j->d_csize, j->d_counter,
-			j->n_slots);
+		auto kern = j->has_zstd ? k_deflate_chunks<true> : k_deflate_chunks<false>;
+		kern<<<j->grid, 32 * DFL_WARPS, smem, s>>>(d_in, j->d_chunks, j->n_chunks, j->d_tokens, j->d_cout, j->d_csize, j->d_counter, j->n_slots);
 		c->launches++;
 	}
 	k_deflate_entry_sizes<<<(n + 255) / 256, 256, 0, s>>>(j->d_ents, n, j->d_csize, j->d_out_size, j->d_method_out);
