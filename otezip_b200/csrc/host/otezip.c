@@ -790,9 +790,32 @@ static struct otz_window *run_window(struct otz_archive *a, zip_uint64_t index) 
 		return NULL;
 	}
 	const uint64_t budget = batch_budget ();
+	/* A request BELOW every decoded window (reverse iteration, zip_name_locate-driven access) would otherwise decode a full
+	 * window forward from each index it touches: start such a window up to half a budget earlier, so that the entries in
+	 * front of the requested one are decoded with it. */
+	int below_all = a->windows != NULL;
+	zip_uint64_t lowest = za->n_entries;
+	for (struct otz_window *p = a->windows; p; p = p->next) {
+		below_all = below_all && index < p->first;
+		lowest = p->first < lowest ? p->first : lowest;
+	}
+	if (below_all) {
+		uint64_t back = ((uint64_t)za->entries[index].uncomp_size + 15) & ~15ULL;   /* (the requested entry itself must still fit) */
+		while (index > 0) {
+			const uint64_t sz = ((uint64_t)za->entries[index - 1].uncomp_size + 15) & ~15ULL;
+			if (back + sz > budget / 2) {
+				break;
+			}
+			back += sz;
+			index--;
+		}
+	}
 	zip_uint64_t last = index;
 	uint64_t bytes = 0;
 	while (last < za->n_entries) {
+		if (below_all && last >= lowest) {
+			break;   /* (what follows is decoded already) */
+		}
 		const struct otezip_entry *e = &za->entries[last];
 		uint64_t sz = host_precheck (a, e, entry_lfh (za, last)) == OTZ_ST_OK ? ((uint64_t)e->uncomp_size + 15) & ~15ULL : 0;
 		if (last > index && bytes + sz > budget) {

@@ -527,7 +527,7 @@ __global__ void __launch_bounds__(I2_TR_THREADS) k_seg_translate(uint8_t *__rest
 template <typename T>
 struct I2Elem {
 	static constexpr uint32_t VEC = 16u / sizeof(T);
-	static constexpr uint32_t STAGE_VECS = sizeof(T) == 1 ? 64u : OTZ_PAR_STAGE_VECS;   // staging vectors per batch; far matches beyond them are fetched directly
+	static constexpr uint32_t STAGE_VECS = sizeof(T) == 1 ? 64u : OTZ_PAR_STAGE_VECS;   // staging vectors per batch; a batch ends where they are used up
 	static constexpr uint32_t STAGE = STAGE_VECS * VEC;
 };
 
@@ -608,12 +608,10 @@ struct I2Batch {
 	uint32_t ma;        //   ring index of the destination | length << 16 | I2_MF_* << 28 | bit 31 = any flag   (length 0: no match)
 	uint32_t mb;        //   source, as an element index from the ring's base: a ring index (< W), or an index into the staging
 	                    //   buffer behind the ring (>= W: a FAR source, fetched while the batch before ran)
-	uint32_t m_src;     //   linear position of the source (far matches that did not fit the staging buffer are fetched directly)
 	uint32_t m_dist;    //   distance (overlapping matches are extended periodically)
 };
 #define I2_MF_LONG 1u       // longer than 64 elements, or a range that wraps around the ring
 #define I2_MF_PERIODIC 2u   // distance < length
-#define I2_MF_DIRECT 4u     // far source not staged: read from HBM
 
 // scan records [b, b + 32) (this lane holds record b + lane in `rec`): positions by warp prefix sums, the match descriptor
 // of every record (kept in its lane), and the copies of the batch's far sources into staging buffer `buf` are started.
@@ -663,12 +661,9 @@ __device__ __forceinline__ I2Batch i2_scan_batch(I2LzSmem<W, T> &S, int buf, uin
 	const bool is_far = is_match && dist > (uint32_t)W - (B.q_end - mq);
 	const uint32_t far_m = __ballot_sync(0xFFFFFFFFu, is_far);
 	const uint32_t src_lin = mq - dist;
-	// LONG: more than 64 elements, or the destination / a ring source wraps around the ring
-	uint32_t flags = is_match ? (((ml > 64u || (mq & MASK) + ml > (uint32_t)W || (!is_far && (src_lin & MASK) + ml > (uint32_t)W)) ? I2_MF_LONG : 0u) |
-		((!is_far && dist < ml) ? I2_MF_PERIODIC : 0u)) : 0u;
 	B.mb = src_lin & MASK;
-	B.m_src = src_lin;
 	B.m_dist = dist;
+	bool taken = mine;
 	if (far_m) {
 		// staging vectors per far match (the source is copied as whole 16-byte vectors)
 		const uint32_t soff = src_lin & (VEC - 1u);
@@ -681,27 +676,46 @@ __device__ __forceinline__ I2Batch i2_scan_batch(I2LzSmem<W, T> &S, int buf, uin
 				incl += a;
 			}
 		}
-		if (is_far) {
-			if (incl <= STAGE_VECS) {
-				const uint32_t cst = incl - nch;
-				OTZ_CHK(VEC * cst + soff + ml <= I2Elem<T>::STAGE, OTZ_CK_LZ_STAGE);
-				B.mb = (uint32_t)W + (uint32_t)buf * I2Elem<T>::STAGE + VEC * cst + soff;
-				// every lane fetches the vectors of its own match (cp.async groups are per thread: the executor waits for
-				// its own group and then syncs the warp)
-				uint32_t sa = (uint32_t)__cvta_generic_to_shared(&S.stage[buf][VEC * cst]);
-				const T *g = gbase + (src_lin & ~(VEC - 1u));
+		// the batch ends in front of the first record whose far source no longer fits the staging buffer (one match needs at
+		// most 34 vectors, so the first record always stays): a source fetched directly from HBM inside the execution loop
+		// would stall the whole warp for a memory round trip.  The far / near verdicts above used the longer batch's end —
+		// conservative in both directions (a far source lies even further below the shorter batch's window, a near one still
+		// inside the ring).
+		const uint32_t over = __ballot_sync(0xFFFFFFFFu, mine && incl > STAGE_VECS);
+		if (over) {
+			B.ntake = (uint32_t)__ffs(over) - 1u;
+			const uint32_t last2 = B.ntake - 1u;
+			B.tot_l = __shfl_sync(0xFFFFFFFFu, lsum, last2);
+			B.q_end = q + __shfl_sync(0xFFFFFFFFu, osum, last2);
+			taken = lane < B.ntake;
+			B.lr = taken ? B.lr : 0u;
+		}
+		if (is_far && taken) {
+			const uint32_t cst = incl - nch;
+			OTZ_CHK(VEC * cst + soff + ml <= I2Elem<T>::STAGE, OTZ_CK_LZ_STAGE);
+			B.mb = (uint32_t)W + (uint32_t)buf * I2Elem<T>::STAGE + VEC * cst + soff;
+			// every lane fetches the vectors of its own match (cp.async groups are per thread: the executor waits for
+			// its own group and then syncs the warp)
+			uint32_t sa = (uint32_t)__cvta_generic_to_shared(&S.stage[buf][VEC * cst]);
+			const T *g = gbase + (src_lin & ~(VEC - 1u));
 #pragma unroll 1
-				for (uint32_t v = 0; v < nch; v++) {
-					asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(sa), "l"(g) : "memory");
-					sa += 16u;
-					g += VEC;
-				}
-			} else {
-				flags |= I2_MF_DIRECT;
+			for (uint32_t v = 0; v < nch; v++) {
+				asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(sa), "l"(g) : "memory");
+				sa += 16u;
+				g += VEC;
 			}
 		}
 	}
-	B.ma = (mq & MASK) | ((is_match ? ml : 0u) << 16) | (flags << 28) | (flags ? 0x80000000u : 0u);
+	const bool has_match = is_match && taken;
+	// LONG: more than 64 elements, or the destination / a ring source wraps around the ring
+	const uint32_t flags = has_match ? (((ml > 64u || (mq & MASK) + ml > (uint32_t)W || (!is_far && (src_lin & MASK) + ml > (uint32_t)W)) ? I2_MF_LONG : 0u) |
+		((!is_far && dist < ml) ? I2_MF_PERIODIC : 0u)) : 0u;
+	// bit 27: the source reaches into what this batch itself writes (earlier matches, its literal runs), so the executor has
+	// to make the stores before it visible first; every other match only reads older ring data or its staged source and
+	// runs back to back with its neighbours (no WAR either: a near source lies above q_end - W, a slot no store of this
+	// batch touches)
+	const uint32_t dep = (has_match && src_lin + ml > q) ? 0x08000000u : 0u;
+	B.ma = (mq & MASK) | ((has_match ? ml : 0u) << 16) | dep | (flags << 28) | (flags ? 0x80000000u : 0u);
 	asm volatile("cp.async.commit_group;" ::: "memory");
 	return B;
 }
@@ -856,9 +870,11 @@ __global__ void __launch_bounds__(128) k_inflate_lz(uint8_t *__restrict__ out, c
 #pragma unroll 1
 				for (uint32_t r = 0; r < cur.ntake; r++) {
 					const uint32_t a = __shfl_sync(0xFFFFFFFFu, cur.ma, r), bsrc = __shfl_sync(0xFFFFFFFFu, cur.mb, r);
-					__syncwarp();   // earlier ring stores are visible to the loads below
+					if (a & 0x88000000u) {
+						__syncwarp();   // earlier ring stores of this batch are visible to the loads below (side exits: always)
+					}
 					if ((int32_t)a >= 0) {
-						const uint32_t len = a >> 16, dq = a & 0xFFFFu;
+						const uint32_t len = (a >> 16) & 0x1FFu, dq = a & 0xFFFFu;
 						T v0 = 0, v1 = 0;
 						OTZ_CHK(len == 0u || (dq + len <= (uint32_t)W && bsrc + len <= (uint32_t)W + 2u * I2Elem<T>::STAGE && (bsrc >= (uint32_t)W || bsrc + len <= (uint32_t)W)),
 							len && dq + len > (uint32_t)W ? OTZ_CK_LZ_RING_DST : OTZ_CK_LZ_RING_SRC);
@@ -880,12 +896,6 @@ __global__ void __launch_bounds__(128) k_inflate_lz(uint8_t *__restrict__ out, c
 					const uint32_t smask = bsrc >= (uint32_t)W ? 0xFFFFFFFFu : MASK;   // staged sources are not wrapped
 					if (fl & I2_MF_PERIODIC) {
 						i2_copy_periodic<W, T>(rb, dq, bsrc, __shfl_sync(0xFFFFFFFFu, cur.m_dist, r), len, lane);
-					} else if (fl & I2_MF_DIRECT) {
-						const uint32_t src = __shfl_sync(0xFFFFFFFFu, cur.m_src, r);
-#pragma unroll 1
-						for (uint32_t x = lane; x < len; x += 32) {
-							rb[(dq + x) & MASK] = __ldcg(gbase + src + x);
-						}
 					} else {
 #pragma unroll 1
 						for (uint32_t x = lane; x < len; x += 32) {

@@ -734,6 +734,7 @@ static int dispatch_inflate3(otz_ctx *c, otz_plan *p, const uint8_t *d_archive, 
 		CK(cudaFuncSetAttribute(k_inflate_spec<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem1));
 		CK(cudaFuncSetAttribute(k_inflate_spec<1>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
 		CK(cudaFuncSetAttribute(k_inflate_spec<4, 8>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem4));
+		CK(cudaFuncSetAttribute(k_inflate_spec<4, 8>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
 		CK(cudaFuncSetAttribute(k_inflate_lz<OTZ_SEG_RING, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(4 * sizeof(I2LzSmem<OTZ_SEG_RING>))));
 		attr_done = true;
 	}
@@ -762,7 +763,18 @@ static int dispatch_inflate3(otz_ctx *c, otz_plan *p, const uint8_t *d_archive, 
 		c->launches++;
 		CK(cudaGetLastError());
 	}
-	if (count) {
+	// few streams: a warp per stream leaves the machine idle while every stream waits for its own serial rounds — then the
+	// regular streams get a 4-warp CTA each as well (128 pieces per round; configs[0] as written: 1,000 streams on 148 SMs)
+	if (count && count <= (uint32_t)c->sm_count * 8u && !getenv("OTZ_SPEC_NO_WIDE")) {
+		int per_sm4 = 0;
+		auto kern4 = k_inflate_spec<4, 8>;
+		CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm4, kern4, 128, smem4));
+		const uint32_t grid4 = gs ? (uint32_t)atoi(gs) : std::max(1u, std::min((uint32_t)(c->sm_count * std::max(per_sm4, 1)), count));
+		kern4<<<grid4, 128, smem4, s>>>(d_archive, p->d_ents, p->d_est, p->d_status, p->d_inflate_list, nh, p->n_inflate, p->d_counter,
+			c->d_tok_cache, p->d_tok_ofs, p->d_tokres, p->d_fb_list, p->d_counter + 52, nh, p->seg, seg_min);
+		c->launches++;
+		CK(cudaGetLastError());
+	} else if (count) {
 		int per_sm = 0;
 		CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_inflate_spec<1>, 32 * I3_WARPS, smem1));
 		if (per_sm < 1) {

@@ -387,3 +387,33 @@ def test_cli_create_with_zstd_frames(tmp_path):
     out.mkdir()
     r = subprocess.run([os.path.join(REFDIR, "otezip_relinked"), "-x", str(z), "--verify-crc"], cwd=out, capture_output=True, text=True, timeout=120, env=env)
     assert r.returncode == 0 and _tree(out) == files
+
+
+def test_reverse_iteration_decodes_each_entry_once(tmp_path):
+    """a request below every decoded window used to decode a full window forward from each index it touched
+    (O(n x budget) for reverse iteration).  Windows now start up to half a budget earlier; reading 60 entries backwards
+    with a 1 MiB budget must be right and must take a handful of batches, not 60."""
+    api = ZipApi()
+    L = api.L
+    files = [("f%02d" % i, synth.jsonlog_text(40000 + 997 * i, 30 + i)) for i in range(60)]
+    p = tmp_path / "rev.zip"
+    p.write_bytes(synth.build_zip([synth.member(n, d, 8) for n, d in files]))
+    os.environ["OTEZIP_BATCH_BYTES"] = str(1 << 20)
+    try:
+        err = C.c_int(0)
+        za = L.zip_open(str(p).encode(), 0, C.byref(err))
+        assert za
+        ctxs = (C.c_void_p * 1)()
+        launches0 = None
+        for i in reversed(range(60)):
+            zf = L.zip_fopen_index(za, i, 0)
+            assert zf and C.string_at(zf.contents.data, zf.contents.size) == files[i][1], i
+            L.zip_fclose(zf)
+        # forward again, then a few random probes
+        for i in (0, 59, 17, 18, 3, 40):
+            zf = L.zip_fopen_index(za, i, 0)
+            assert zf and C.string_at(zf.contents.data, zf.contents.size) == files[i][1], i
+            L.zip_fclose(zf)
+        assert L.zip_close(za) == 0
+    finally:
+        del os.environ["OTEZIP_BATCH_BYTES"]
