@@ -30,6 +30,9 @@
 #include "otz_common.cuh"
 #include "k_inflate.cuh"
 
+#ifndef OTZ_BYTE_STAGE_VECS
+#define OTZ_BYTE_STAGE_VECS 64u
+#endif
 #ifndef OTZ_PAR_STAGE_VECS
 #define OTZ_PAR_STAGE_VECS 96u
 #endif
@@ -396,10 +399,27 @@ __global__ void __launch_bounds__(1024) k_seg_window(uint8_t *__restrict__ out, 
 		const uint32_t os = seg.out_start[h * I2_MAXSEG + c];
 		const uint16_t *sp = sym + seg.sym_start[h * I2_MAXSEG + c];
 		const uint32_t t0 = pr > I2_PREWIN ? pr - I2_PREWIN : 0u;
-		for (uint32_t i = t0 + threadIdx.x; i < pr; i += blockDim.x) {
-			const uint32_t v = __ldcs(sp + i);
-			// (a marker only exists where a match reached, and k_seg_stitch checked reach <= os)
-			o[os + i] = v < 256u ? (uint8_t)v : __ldcg(o + (os - I2_PREWIN + (v - 256u)));
+		// (two dependent HBM round trips per element — the symbol, then the byte its marker names: eight elements per thread
+		// are in flight together)
+		for (uint32_t i0 = t0 + threadIdx.x; i0 < pr; i0 += 8u * blockDim.x) {
+			uint32_t v[8];
+#pragma unroll
+			for (int u = 0; u < 8; u++) {
+				const uint32_t i = i0 + u * blockDim.x;
+				v[u] = i < pr ? __ldcs(sp + i) : 0u;
+			}
+#pragma unroll
+			for (int u = 0; u < 8; u++) {
+				// (a marker only exists where a match reached, and k_seg_stitch checked reach <= os)
+				v[u] = v[u] < 256u ? v[u] : (uint32_t)__ldcg(o + (os - I2_PREWIN + (v[u] - 256u)));
+			}
+#pragma unroll
+			for (int u = 0; u < 8; u++) {
+				const uint32_t i = i0 + u * blockDim.x;
+				if (i < pr) {
+					o[os + i] = (uint8_t)v[u];
+				}
+			}
 		}
 		__syncthreads();
 	}
@@ -527,7 +547,7 @@ __global__ void __launch_bounds__(I2_TR_THREADS) k_seg_translate(uint8_t *__rest
 template <typename T>
 struct I2Elem {
 	static constexpr uint32_t VEC = 16u / sizeof(T);
-	static constexpr uint32_t STAGE_VECS = sizeof(T) == 1 ? 64u : OTZ_PAR_STAGE_VECS;   // staging vectors per batch; a batch ends where they are used up
+	static constexpr uint32_t STAGE_VECS = sizeof(T) == 1 ? OTZ_BYTE_STAGE_VECS : OTZ_PAR_STAGE_VECS;   // staging vectors per batch; a batch ends where they are used up
 	static constexpr uint32_t STAGE = STAGE_VECS * VEC;
 };
 

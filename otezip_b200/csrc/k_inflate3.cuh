@@ -40,8 +40,7 @@
 #include "k_inflate2.cuh"
 
 #define I3_WARPS 4         // NW = 1: independent warps (streams) per CTA
-#define I3_SMAX 512        // bits per piece (lane and round), at most
-#define I3_PIECE_WORDS (I3_SMAX / 32 + 3)   // a lane's staged words: its piece + the 3 words a symbol may run over
+// WPLMAX = words per piece (lane and round), at most: 16 (512 bits) or, for CTA groups when a batch has few huge streams, 32
 #define I3_BAD 4u          // (kinds 0..3 are I2_K_*)
 #define I3_SEG_MIN 524288u // least output bytes of a segment of a huge stream (k_seg_window resolves the last 32 KiB of each one serially)
 
@@ -55,7 +54,7 @@ struct I3BuildScratch {
 };
 
 // shared memory of one GROUP = the NW warps that decode one stream together (NW * 32 pieces per round)
-template <int NW>
+template <int NW, int WPLMAX = 16>
 struct __align__(16) I3Smem {
 	static constexpr int G = 32 * NW;
 	uint16_t lit[I2_LIT_CAP];
@@ -65,8 +64,8 @@ struct __align__(16) I3Smem {
 	uint32_t bc[8];          // broadcast slots
 	union {
 		struct {
-			uint32_t stage[G * I3_PIECE_WORDS];   // words of piece t at [t * (words per piece + 3) ...]: odd stride, no bank conflicts between lanes at the same offset
-			uint32_t vis[(I3_SMAX / 32) * G];     // symbol boundaries visited in pass 1: word w of piece t at [w * G + t]
+			uint32_t stage[G * (WPLMAX + 3)];   // words of piece t at [t * (words per piece + 3) ...]: odd stride, no bank conflicts between lanes at the same offset
+			uint32_t vis[WPLMAX * G];           // symbol boundaries visited in pass 1: word w of piece t at [w * G + t]
 		} r;
 		struct {
 			I3BuildScratch b;
@@ -184,8 +183,8 @@ struct I3HdrBits {
 
 // exclusive prefix sums of (a, b) over the group + their totals.  NW > 1: per-warp sums go through S.ws[.][slot, slot + 1]
 // (one barrier; the slots are not reused before the next barrier of the caller)
-template <int NW>
-__device__ __forceinline__ void i3_scan2(I3Smem<NW> &S, uint32_t lane, uint32_t warp, int slot, uint32_t a, uint32_t b, uint32_t &apre, uint32_t &bpre,
+template <int NW, typename SM>
+__device__ __forceinline__ void i3_scan2(SM &S, uint32_t lane, uint32_t warp, int slot, uint32_t a, uint32_t b, uint32_t &apre, uint32_t &bpre,
 	uint32_t &atot, uint32_t &btot) {
 	uint32_t ai = a, bi = b;
 #pragma unroll
@@ -225,7 +224,7 @@ __device__ __forceinline__ void i3_scan2(I3Smem<NW> &S, uint32_t lane, uint32_t 
 
 // grid: persistent.  NW = 1: I3_WARPS independent warps per CTA, one stream each; NW > 1: the NW warps of a CTA
 // decode one (huge) stream together.  Every group pulls list slots [k0, k1) from *work_counter (longest streams first).
-template <int NW, int MINB = (NW == 1 ? 8 : 16 / NW)>
+template <int NW, int MINB = (NW == 1 ? 8 : 16 / NW), int WPLMAX = 16>
 __global__ void __launch_bounds__(32 * (NW == 1 ? I3_WARPS : NW), MINB) k_inflate_spec(const uint8_t *__restrict__ archive,
 	const otz_entry *__restrict__ ents, const OtzEntryState *__restrict__ est, const int32_t *__restrict__ status, const uint32_t *__restrict__ list,
 	uint32_t k0, uint32_t k1, uint32_t *__restrict__ work_counter, uint8_t *__restrict__ scratch, const uint64_t *__restrict__ tok_ofs,
@@ -235,7 +234,8 @@ __global__ void __launch_bounds__(32 * (NW == 1 ? I3_WARPS : NW), MINB) k_inflat
 	const uint32_t lane = threadIdx.x & 31u;
 	const uint32_t warp = NW == 1 ? 0u : threadIdx.x >> 5;   // warp within the group
 	const uint32_t tid = NW == 1 ? lane : threadIdx.x;        // thread within the group = its piece
-	I3Smem<NW> &S = reinterpret_cast<I3Smem<NW> *>(smem_raw)[NW == 1 ? threadIdx.x >> 5 : 0];
+	typedef I3Smem<NW, WPLMAX> Smem;
+	Smem &S = reinterpret_cast<Smem *>(smem_raw)[NW == 1 ? threadIdx.x >> 5 : 0];
 	const uint32_t lt_mask = (1u << lane) - 1u;
 
 	for (;;) {
@@ -279,7 +279,9 @@ __global__ void __launch_bounds__(32 * (NW == 1 ? I3_WARPS : NW), MINB) k_inflat
 		const uint32_t P0 = 8u * skipb, Pend = P0 + 8u * comp;
 		const uint32_t nw = (Pend + 31u) >> 5;
 		// pieces of 512 bits once a stream is long enough to fill a few rounds of them
-		const uint32_t wpl = comp >= 192u * G ? 16u : 8u;   // words per piece
+		// (longer pieces amortise the synchronisation walk — its length is set by the slowest of the G lanes, not by the piece —
+		// and are worth their shared memory only where a stream has hundreds of rounds: the 4-warp groups)
+		const uint32_t wpl = (WPLMAX >= 32 && comp >= 768u * G) ? 32u : comp >= 192u * G ? 16u : 8u;   // words per piece
 		const uint32_t S_bits = 32u * wpl;
 		uint8_t *const litp = scratch + tok_ofs[k];
 		uint32_t *const seq_end = reinterpret_cast<uint32_t *>(scratch + tok_ofs[k + 1]);
@@ -665,7 +667,7 @@ __global__ void __launch_bounds__(32 * (NW == 1 ? I3_WARPS : NW), MINB) k_inflat
 				}
 				const bool valid = tid <= lastl;
 				// ---- count
-				uint32_t nl = 0, nm = 0, ob = 0, lead = 0, since = 0;
+				uint32_t nl = 0, nm = 0, ob = 0, lead = 0, since = 0, esc_in = 0;   // esc_in: escape records in front of matches that are not the first of the piece
 				{
 					uint32_t q = T;
 					bool on = valid;
@@ -676,6 +678,7 @@ __global__ void __launch_bounds__(32 * (NW == 1 ? I3_WARPS : NW), MINB) k_inflat
 							OTZ_CHK(q >= R && q - base < S_bits && (q >> 5) - (w0 + tid * wpl) <= wpl, OTZ_CK_SPEC_PIECE);
 							const bool isl = kd == I2_K_LEN, isb = kd == I2_K_LIT;
 							lead = (isl && nm == 0u) ? since : lead;
+							esc_in += (isl && nm != 0u) ? since / I2_SEQ_ESC : 0u;   // (only pieces of more than 511 bits can hold such a run)
 							nl += isb;
 							nm += isl;
 							ob += isb ? 1u : isl ? v_ : 0u;
@@ -707,7 +710,7 @@ __global__ void __launch_bounds__(32 * (NW == 1 ? I3_WARPS : NW), MINB) k_inflat
 						S.ws[warp][4] = mm ? w_tail : wtot;
 					}
 				}
-				i3_scan2<NW>(S, lane, warp, 0, nl, ob, nlpre, obpre, tot_nl, tot_ob);   // (NW > 1: barrier — ws[.][3,4] are visible too)
+				i3_scan2<NW, Smem>(S, lane, warp, 0, nl, ob, nlpre, obpre, tot_nl, tot_ob);   // (NW > 1: barrier — ws[.][3,4] are visible too)
 				if (ob_tot + tot_ob > cap) {
 					act = I3_A_FALLBACK;   // dec:700-703, dec:791-793: k_inflate reports the overflow
 					break;
@@ -730,7 +733,7 @@ __global__ void __launch_bounds__(32 * (NW == 1 ? I3_WARPS : NW), MINB) k_inflat
 				const uint32_t carry_in = below ? tl + ((nl_w - nl) - sl) : w_carry + (nl_w - nl);
 				const uint32_t esc = nm ? (carry_in + lead) / I2_SEQ_ESC : 0u;
 				uint32_t sqpre, dummy_pre, tot_sq, dummy_tot;
-				i3_scan2<NW>(S, lane, warp, 8, nm + esc, 0u, sqpre, dummy_pre, tot_sq, dummy_tot);
+				i3_scan2<NW, Smem>(S, lane, warp, 8, nm + esc + esc_in, 0u, sqpre, dummy_pre, tot_sq, dummy_tot);
 				// ---- emit
 				uint32_t bad = 0, minsrc = 0xFFFFFFFFu, lastp = 0;
 				{
