@@ -729,14 +729,14 @@ static int launch_seg_par(otz_ctx *c, otz_plan *p, uint8_t *d_out, const I2SegCt
 static int dispatch_inflate3(otz_ctx *c, otz_plan *p, const uint8_t *d_archive, uint8_t *d_out) {
 	cudaStream_t s = c->stream, s2 = c->stream2;
 	static bool attr_done = false;
-	const size_t smem1 = I3_WARPS * sizeof(I3Smem<1>), smem4 = sizeof(I3Smem<4>), smem4w = sizeof(I3Smem<4, 32>);
+	const size_t smem1 = I3_WARPS * sizeof(I3Smem<1>), smem4 = sizeof(I3Smem<4>), smem8 = sizeof(I3Smem<8, 16>);
 	if (!attr_done) {
 		CK(cudaFuncSetAttribute(k_inflate_spec<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem1));
 		CK(cudaFuncSetAttribute(k_inflate_spec<1>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
 		CK(cudaFuncSetAttribute(k_inflate_spec<4, 8>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem4));
 		CK(cudaFuncSetAttribute(k_inflate_spec<4, 8>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
-		CK(cudaFuncSetAttribute(k_inflate_spec<4, 6, 32>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem4w));
-		CK(cudaFuncSetAttribute(k_inflate_spec<4, 6, 32>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
+		CK(cudaFuncSetAttribute(k_inflate_spec<8, 4, 16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem8));
+		CK(cudaFuncSetAttribute(k_inflate_spec<8, 4, 16>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
 		CK(cudaFuncSetAttribute(k_inflate_lz<OTZ_SEG_RING, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(4 * sizeof(I2LzSmem<OTZ_SEG_RING>))));
 		attr_done = true;
 	}
@@ -751,19 +751,21 @@ static int dispatch_inflate3(otz_ctx *c, otz_plan *p, const uint8_t *d_archive, 
 		CK(cudaEventRecord(c->ev_fork, s));
 		CK(cudaStreamWaitEvent(s2, c->ev_fork, 0));
 		int per_sm4 = 0;
-		// 64 registers: 8 CTAs = 32 warps per SM (4 CTAs at 104 registers measured 4 % slower on configs[2]).  Few huge streams
-		// (fewer than the 6 CTAs per SM the variant with 1,024-bit pieces holds): that variant — longer pieces amortise the
-		// synchronisation walk, 25 % fewer lock-step steps per byte, worth more than occupancy when every stream is a critical path
-		const bool wide = nh <= (uint32_t)c->sm_count * 6u && !getenv("OTZ_SPEC_NO_WIDE");
-		auto kern4 = wide ? k_inflate_spec<4, 6, 32> : k_inflate_spec<4, 8>;
-		const size_t smem4x = wide ? smem4w : smem4;
-		CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm4, kern4, 128, smem4x));
+		// 4-warp CTAs at 64 registers: 8 CTAs = 32 warps per SM (4 CTAs at 104 registers measured 4 % slower on configs[2]).
+		// Few huge streams — every one of them a critical path, SMs to spare (a shard of a multi-GPU run, a small archive):
+		// 8-warp CTAs, 256 pieces per round, half the rounds per stream (measured: 1,250 entries 21.3 -> 17.4 ms, 5,000 entries 46.7 -> 43.5 ms, 10,000 entries no gain;
+		// 4 warps with 1,024-bit pieces: 19.6 ms).  A DEFLATE block of zlib is ~27 KB, about one such round: more lanes would idle.
+		const bool wide = (nh <= (uint32_t)c->sm_count * 16u && !getenv("OTZ_SPEC_NO_WIDE")) || getenv("OTZ_SPEC_FORCE_WIDE");
+		auto kern4 = wide ? k_inflate_spec<8, 4, 16> : k_inflate_spec<4, 8>;
+		const size_t smem4x = wide ? smem8 : smem4;
+		const int thr4 = wide ? 256 : 128;
+		CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm4, kern4, thr4, smem4x));
 		if (per_sm4 < 1) {
 			snprintf(g_err, sizeof(g_err), "k_inflate_spec<4> does not fit an SM (%zu bytes of shared memory)", smem4x);
 			return OTZ_ERR_CUDA;
 		}
 		const uint32_t grid4 = gs ? (uint32_t)atoi(gs) : std::max(1u, std::min((uint32_t)(c->sm_count * per_sm4), nh));
-		kern4<<<grid4, 128, smem4x, s2>>>(d_archive, p->d_ents, p->d_est, p->d_status, p->d_inflate_list, 0u, nh, p->d_counter + 57,
+		kern4<<<grid4, thr4, smem4x, s2>>>(d_archive, p->d_ents, p->d_est, p->d_status, p->d_inflate_list, 0u, nh, p->d_counter + 57,
 			c->d_tok_cache, p->d_tok_ofs, p->d_tokres, p->d_fb_list, p->d_counter + 52, nh, p->seg, seg_min);
 		c->launches++;
 		CK(cudaGetLastError());

@@ -17,6 +17,7 @@ for K in ${KERNELS:-spec1 spec4 lz}; do
     lz) full lz "k_inflate_lz" "$C1" 2 ;;
     par) full par "k_inflate_lz" "$C3" 4 ;;     # per pass: serial chain walk (empty), symbols, regular -> the symbol executor of pass 2
     lz3) full lz3 "k_inflate_lz" "$C3" 5 ;;     # the byte executor of pass 2 on configs[2]
+    spec4w) full spec4w "k_inflate_spec" "python bench.py --workload c3 --entries 1250 --steps 1 --warmup 1 --no-cpu-baseline --e2e-steps 0" 2 ;;
     win) full win "k_seg_window" "$C3" 1 ;;
     tr) full tr "k_seg_translate" "$C3" 1 ;;
   esac
