@@ -305,8 +305,8 @@ struct I2SegCtl {
 // I2_PREWIN marker elements, then its output as 16-bit symbols, placed so that symbol i of the segment and output byte i
 // have the same index modulo 16 (k_seg_translate works on whole vectors of both).
 __global__ void k_seg_stitch(const otz_entry *__restrict__ ents, const int32_t *__restrict__ status, const uint32_t *__restrict__ list,
-	uint32_t n_huge, I2SegCtl seg, uint32_t *__restrict__ fb_list, uint32_t *__restrict__ fb_count) {
-	const uint32_t h = blockIdx.x * blockDim.x + threadIdx.x;
+	uint32_t n_huge, I2SegCtl seg, uint32_t *__restrict__ fb_list, uint32_t *__restrict__ fb_count, uint32_t h0) {
+	const uint32_t h = h0 + blockIdx.x * blockDim.x + threadIdx.x;   // streams [h0, n_huge) of the list: one group of huge streams
 	if (h >= n_huge) {
 		return;
 	}
@@ -386,8 +386,8 @@ __global__ void k_seg_stitch(const otz_entry *__restrict__ ents, const int32_t *
 // 32 KiB of every segment — the window of the next one — straight into the output; step c reads what steps < c
 // wrote.  k_seg_translate finally resolves everything in front of those tails, all segments at once.
 __global__ void __launch_bounds__(1024) k_seg_window(uint8_t *__restrict__ out, const otz_entry *__restrict__ ents, const uint32_t *__restrict__ list,
-	uint32_t n_huge, const uint16_t *__restrict__ sym, int32_t *__restrict__ status, uint32_t *__restrict__ produced_out, I2SegCtl seg) {
-	const uint32_t h = blockIdx.x;
+	uint32_t n_huge, const uint16_t *__restrict__ sym, int32_t *__restrict__ status, uint32_t *__restrict__ produced_out, I2SegCtl seg, uint32_t h0) {
+	const uint32_t h = h0 + blockIdx.x;
 	if (h >= n_huge || !seg.par[h]) {
 		return;
 	}
@@ -746,7 +746,7 @@ __device__ __forceinline__ I2Batch i2_scan_batch(I2LzSmem<W, T> &S, int buf, uin
 template <int W, bool WIDE, bool SEG, bool PAR = false>
 __global__ void __launch_bounds__(128) k_inflate_lz(uint8_t *__restrict__ out, const otz_entry *__restrict__ ents, const uint32_t *__restrict__ list,
 	uint32_t n_list, uint32_t *__restrict__ work_counter, const uint8_t *__restrict__ scratch, const uint64_t *__restrict__ tok_ofs,
-	const I2TokRes *__restrict__ tokres, int32_t *__restrict__ status, uint32_t *__restrict__ produced_out, I2SegCtl seg) {
+	const I2TokRes *__restrict__ tokres, int32_t *__restrict__ status, uint32_t *__restrict__ produced_out, I2SegCtl seg, uint32_t k_first) {
 	typedef typename I2ElemOf<PAR>::type T;
 	static_assert(!PAR || (SEG && !WIDE), "PAR executes segments of DEFLATE streams");
 	extern __shared__ __align__(16) uint8_t smem_raw[];
@@ -762,7 +762,7 @@ __global__ void __launch_bounds__(128) k_inflate_lz(uint8_t *__restrict__ out, c
 		if (lane == 0) {
 			k = atomicAdd(work_counter, 1u);
 		}
-		k = __shfl_sync(0xFFFFFFFFu, k, 0);
+		k = __shfl_sync(0xFFFFFFFFu, k, 0) + (PAR ? 0u : k_first);   // (list slots [k_first, n_list); PAR: items of seg.par_items)
 		if (k >= n_list) {
 			break;
 		}

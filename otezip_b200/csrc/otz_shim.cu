@@ -40,8 +40,8 @@ static int fail_cuda(cudaError_t e, const char *what, int line = 0) {
 struct otz_ctx {
 	int device;
 	int sm_count;
-	cudaStream_t stream, stream2;
-	cudaEvent_t ev0, ev1, ev_fork, ev_join;
+	cudaStream_t stream, stream2, stream3, stream4;
+	cudaEvent_t ev0, ev1, ev_fork, ev_join, ev_join3, ev_join4;
 	cudaEvent_t pev[OTZ_PROF_SLOTS][5];
 	int profile;
 	uint32_t prof_runs;      // runs recorded since otz_profile_enable(ctx, 1)
@@ -89,6 +89,8 @@ struct otz_plan {
 	uint32_t *d_inflate_list, n_inflate;   // DEFLATE entries, longest first; [0, n_inflate_big) are the large ones
 	uint32_t n_inflate_big;
 	uint32_t n_inflate_huge;   // [0, n_inflate_huge): entries whose serial decode time sets the critical path of a batch
+	uint32_t huge_split[2];    // [0, huge_split[0]): the huge entries of at least half the largest one's compressed size, [.., huge_split[1]): a quarter
+	                           // (their own groups when the huge streams are few)
 	I2SegCtl seg;              // segmented decode of the huge entries (device arrays; null when there are none)
 	uint64_t sym_elems;        // symbol buffer the parallel execution of the huge streams may need
 	uint64_t *d_tok_ofs;       // two-phase inflate: scratch offset of every list slot (+ end), bytes
@@ -212,8 +214,12 @@ extern "C" int otz_ctx_create(int device, otz_ctx **out) {
 	c->sm_count = prop.multiProcessorCount;
 	CK(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
 	CK(cudaStreamCreateWithFlags(&c->stream2, cudaStreamNonBlocking));
+	CK(cudaStreamCreateWithFlags(&c->stream3, cudaStreamNonBlocking));
+	CK(cudaStreamCreateWithFlags(&c->stream4, cudaStreamNonBlocking));
 	CK(cudaEventCreateWithFlags(&c->ev_fork, cudaEventDisableTiming));
 	CK(cudaEventCreateWithFlags(&c->ev_join, cudaEventDisableTiming));
+	CK(cudaEventCreateWithFlags(&c->ev_join3, cudaEventDisableTiming));
+	CK(cudaEventCreateWithFlags(&c->ev_join4, cudaEventDisableTiming));
 	CK(cudaEventCreate(&c->ev0));
 	CK(cudaEventCreate(&c->ev1));
 	for (auto &slot : c->pev) {
@@ -283,6 +289,10 @@ extern "C" void otz_ctx_destroy(otz_ctx *c) {
 	}
 	cudaEventDestroy(c->ev_fork);
 	cudaEventDestroy(c->ev_join);
+	cudaEventDestroy(c->ev_join3);
+	cudaEventDestroy(c->ev_join4);
+	cudaStreamDestroy(c->stream4);
+	cudaStreamDestroy(c->stream3);
 	cudaStreamDestroy(c->stream2);
 	cudaStreamDestroy(c->stream);
 	delete c;
@@ -552,6 +562,8 @@ extern "C" int otz_plan_create(otz_ctx *c, const otz_entry *ents, uint32_t n, co
 	if (p->n_inflate_huge && p->n_inflate_huge <= 4096u) {
 		const size_t nh = p->n_inflate_huge, ns = nh * I2_MAXSEG;
 		for (size_t h = 0; h < nh; h++) {
+			p->huge_split[0] += (uint64_t)ents[infl[h]].comp_size * 2u >= ents[infl[0]].comp_size;   // (the list is sorted by compressed size)
+			p->huge_split[1] += (uint64_t)ents[infl[h]].comp_size * 4u >= ents[infl[0]].comp_size;
 			// symbols of the stream + markers in front of every segment (a stream with more segments than estimated here is
 			// executed by one warp)
 			p->sym_elems += (uint64_t)ents[infl[h]].uncomp_size +
@@ -561,7 +573,7 @@ extern "C" int otz_plan_create(otz_ctx *c, const otz_entry *ents, uint32_t n, co
 			cudaMalloc(&p->seg.res, ns * sizeof(I2SegRes)) != cudaSuccess || cudaMalloc(&p->seg.live, ns * 4) != cudaSuccess ||
 			cudaMalloc(&p->seg.nlive, nh * 4) != cudaSuccess || cudaMalloc(&p->seg.seg_status, nh * 4) != cudaSuccess ||
 			cudaMalloc(&p->seg.par, nh * 4) != cudaSuccess || cudaMalloc(&p->seg.par_items, ns * 4) != cudaSuccess ||
-			cudaMalloc(&p->seg.n_par, 4) != cudaSuccess || cudaMalloc(&p->seg.sym_start, ns * 8) != cudaSuccess ||
+			cudaMalloc(&p->seg.n_par, 16) != cudaSuccess || cudaMalloc(&p->seg.sym_start, ns * 8) != cudaSuccess ||
 			cudaMalloc(&p->seg.out_start, ns * 4) != cudaSuccess) {
 			otz_plan_destroy(c, p);
 			return fail_cuda(cudaGetLastError(), "cudaMalloc(segment tables)");
@@ -678,7 +690,7 @@ static int launch_lz(otz_ctx *c, otz_plan *p, uint8_t *d_out, uint32_t first, ui
 	}
 	const uint32_t grid = std::max(1u, std::min((uint32_t)(c->sm_count * per_sm), (count + warps - 1) / warps));
 	kern<<<grid, 32 * warps, smem, st>>>(d_out, p->d_ents, p->d_inflate_list + first, count, p->d_counter + 48, c->d_tok_cache,
-		p->d_tok_ofs + first, p->d_tokres + first, p->d_status, p->d_produced, I2SegCtl{});
+		p->d_tok_ofs + first, p->d_tokres + first, p->d_status, p->d_produced, I2SegCtl{}, 0u);
 	c->launches++;
 	CK(cudaGetLastError());
 	return OTZ_SUCCESS;
@@ -687,7 +699,8 @@ static int launch_lz(otz_ctx *c, otz_plan *p, uint8_t *d_out, uint32_t first, ui
 // Parallel execution of the chains k_seg_stitch placed in the symbol buffer: one warp per segment over 16-bit symbols,
 // then the windows between the segments (one CTA per stream), then symbols -> bytes for everything else.
 template <int W>
-static int launch_seg_par(otz_ctx *c, otz_plan *p, uint8_t *d_out, const I2SegCtl &sg, cudaStream_t st) {
+static int launch_seg_par(otz_ctx *c, otz_plan *p, uint8_t *d_out, const I2SegCtl &sg, cudaStream_t st, uint32_t h0, uint32_t h1, uint32_t *cnt_par,
+	uint32_t *cnt_tr) {
 	auto kern = k_inflate_lz<W, false, true, true>;
 	const int warps = 4;
 	const size_t smem = warps * sizeof(I2LzSmem<W, uint16_t>);
@@ -702,21 +715,10 @@ static int launch_seg_par(otz_ctx *c, otz_plan *p, uint8_t *d_out, const I2SegCt
 		snprintf(g_err, sizeof(g_err), "k_inflate_lz<%d, symbols> does not fit an SM", W);
 		return OTZ_ERR_CUDA;
 	}
-	const uint32_t nh = p->n_inflate_huge;
-	const bool dbg = getenv("OTZ_DEBUG_SYNC") != nullptr;
-	kern<<<(uint32_t)(c->sm_count * per_sm), 32 * warps, smem, st>>>(reinterpret_cast<uint8_t *>(c->d_sym_cache), p->d_ents, p->d_inflate_list, 0u,
-		p->d_counter + 60, c->d_tok_cache, p->d_tok_ofs, p->d_tokres, p->d_status, p->d_produced, sg);
-	if (dbg) {
-		CK(cudaStreamSynchronize(st));
-	}
-	k_seg_window<<<nh, 1024, 0, st>>>(d_out, p->d_ents, p->d_inflate_list, nh, c->d_sym_cache, p->d_status, p->d_produced, sg);
-	if (dbg) {
-		CK(cudaStreamSynchronize(st));
-	}
-	k_seg_translate<<<(uint32_t)c->sm_count * 4u, I2_TR_THREADS, 0, st>>>(d_out, p->d_ents, p->d_inflate_list, c->d_sym_cache, p->d_counter + 61, sg);
-	if (dbg) {
-		CK(cudaStreamSynchronize(st));
-	}
+	kern<<<(uint32_t)(c->sm_count * per_sm), 32 * warps, smem, st>>>(reinterpret_cast<uint8_t *>(c->d_sym_cache), p->d_ents, p->d_inflate_list, 0u, cnt_par,
+		c->d_tok_cache, p->d_tok_ofs, p->d_tokres, p->d_status, p->d_produced, sg, 0u);
+	k_seg_window<<<h1 - h0, 1024, 0, st>>>(d_out, p->d_ents, p->d_inflate_list, h1, c->d_sym_cache, p->d_status, p->d_produced, sg, h0);
+	k_seg_translate<<<(uint32_t)c->sm_count * 4u, I2_TR_THREADS, 0, st>>>(d_out, p->d_ents, p->d_inflate_list, c->d_sym_cache, cnt_tr, sg);
 	c->launches += 3;
 	CK(cudaGetLastError());
 	return OTZ_SUCCESS;
@@ -746,29 +748,87 @@ static int dispatch_inflate3(otz_ctx *c, otz_plan *p, const uint8_t *d_archive, 
 	const char *sm_ = getenv("OTZ_SEG_MIN");       // least output bytes of a segment (>= I3_SEG_MIN: the symbol buffer is sized for that)
 	const uint32_t seg_min = sm_ ? std::max<uint32_t>(I3_SEG_MIN, (uint32_t)strtoul(sm_, nullptr, 0)) : I3_SEG_MIN;
 	bool forked = false;
+	// 4-warp CTAs at 64 registers: 8 CTAs = 32 warps per SM (4 CTAs at 104 registers measured 4 % slower on configs[2]).
+	// Few huge streams — every one of them a critical path, SMs to spare (a shard of a multi-GPU run, a small archive):
+	// 8-warp CTAs, 256 pieces per round, half the rounds per stream (measured: 1,250 entries 21.3 -> 17.4 ms, 5,000 entries
+	// 46.7 -> 43.5 ms, 10,000 entries no gain; 4 warps with 1,024-bit pieces: 19.6 ms).  A DEFLATE block of zlib is ~27 KB, about
+	// one such round: more lanes would idle.
+	const bool wide = nh && ((nh <= (uint32_t)c->sm_count * 16u && !getenv("OTZ_SPEC_NO_WIDE")) || getenv("OTZ_SPEC_FORCE_WIDE"));
+	// In that regime the huge streams are also cut into up to THREE groups by size, each with its own chain tokenizer -> stitch ->
+	// segment execution -> window -> translate on its own CUDA stream: group 0 = the streams of at least half the largest
+	// one's compressed size (their tokenizer runs ~10 ms for a 16 MiB entry whatever else happens), group 1 = down to a
+	// quarter, group 2 = the rest, whose segments are already executing while the larger ones are still being tokenized
+	// (1,250 entries: 17.6 -> 14.4 ms with two groups).
+	struct Grp {
+		uint32_t h0, h1;
+		cudaStream_t st;
+		cudaEvent_t join;
+		uint32_t c_spec, c_seglz, c_par, c_tr;   // words of d_counter
+		uint32_t par_slot;
+	} grp[3] = { { 0u, nh, s2, c->ev_join, 57u, 58u, 60u, 61u, 0u }, { 0u, 0u, c->stream3, c->ev_join3, 40u, 41u, 42u, 43u, 1u },
+		{ 0u, 0u, c->stream4, c->ev_join4, 44u, 45u, 46u, 47u, 2u } };
+	uint32_t n_grp = nh ? 1u : 0u;
+	if (wide && !getenv("OTZ_SPEC_ONE_GROUP")) {
+		const char *mg = getenv("OTZ_SPEC_GROUPS");
+		const uint32_t max_grp = mg ? (uint32_t)atoi(mg) : 3u;
+		uint32_t cut[2] = { p->huge_split[0], p->huge_split[1] };
+		uint32_t lo = 0;
+		n_grp = 0;
+		for (uint32_t g = 0; g < 2 && n_grp + 1 < max_grp; g++) {
+			if (cut[g] > lo && cut[g] < nh) {
+				grp[n_grp].h0 = lo;
+				grp[n_grp].h1 = cut[g];
+				lo = cut[g];
+				n_grp++;
+			}
+		}
+		grp[n_grp].h0 = lo;
+		grp[n_grp].h1 = nh;
+		n_grp++;
+	}
+	I2SegCtl sg = p->seg;
 	if (nh) {
-		// huge streams: the 4 warps of a CTA decode one stream together; second stream, next to the warp-per-stream kernel
+		// huge streams: the warps of a CTA decode one stream together; second (and third) stream, next to the warp-per-stream kernel
+		sg.sym_top = reinterpret_cast<unsigned long long *>(p->d_counter + 62);
+		sg.out_mis = (uint32_t)(reinterpret_cast<uint64_t>(d_out) & 15u);
+		sg.sym_cap = 0;
+		if (!c->seg_serial && p->sym_elems) {
+			if (p->sym_elems > c->sym_cache_elems) {
+				CK(cudaStreamSynchronize(c->stream));
+				CK(cudaStreamSynchronize(s2));
+				CK(cudaStreamSynchronize(c->stream3));
+				CK(cudaStreamSynchronize(c->stream4));
+				cudaFree(c->d_sym_cache);
+				c->d_sym_cache = nullptr;
+				c->sym_cache_elems = 0;
+				if (cudaMalloc(&c->d_sym_cache, p->sym_elems * 2 + 64) == cudaSuccess) {
+					c->sym_cache_elems = p->sym_elems;
+				} else {
+					cudaGetLastError();
+				}
+			}
+			sg.sym_cap = c->d_sym_cache ? std::min<uint64_t>(p->sym_elems, c->sym_limit) : 0;
+		}
 		CK(cudaEventRecord(c->ev_fork, s));
-		CK(cudaStreamWaitEvent(s2, c->ev_fork, 0));
-		int per_sm4 = 0;
-		// 4-warp CTAs at 64 registers: 8 CTAs = 32 warps per SM (4 CTAs at 104 registers measured 4 % slower on configs[2]).
-		// Few huge streams — every one of them a critical path, SMs to spare (a shard of a multi-GPU run, a small archive):
-		// 8-warp CTAs, 256 pieces per round, half the rounds per stream (measured: 1,250 entries 21.3 -> 17.4 ms, 5,000 entries 46.7 -> 43.5 ms, 10,000 entries no gain;
-		// 4 warps with 1,024-bit pieces: 19.6 ms).  A DEFLATE block of zlib is ~27 KB, about one such round: more lanes would idle.
-		const bool wide = (nh <= (uint32_t)c->sm_count * 16u && !getenv("OTZ_SPEC_NO_WIDE")) || getenv("OTZ_SPEC_FORCE_WIDE");
 		auto kern4 = wide ? k_inflate_spec<8, 4, 16> : k_inflate_spec<4, 8>;
 		const size_t smem4x = wide ? smem8 : smem4;
 		const int thr4 = wide ? 256 : 128;
+		int per_sm4 = 0;
 		CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm4, kern4, thr4, smem4x));
 		if (per_sm4 < 1) {
-			snprintf(g_err, sizeof(g_err), "k_inflate_spec<4> does not fit an SM (%zu bytes of shared memory)", smem4x);
+			snprintf(g_err, sizeof(g_err), "k_inflate_spec for huge streams does not fit an SM (%zu bytes of shared memory)", smem4x);
 			return OTZ_ERR_CUDA;
 		}
-		const uint32_t grid4 = gs ? (uint32_t)atoi(gs) : std::max(1u, std::min((uint32_t)(c->sm_count * per_sm4), nh));
-		kern4<<<grid4, thr4, smem4x, s2>>>(d_archive, p->d_ents, p->d_est, p->d_status, p->d_inflate_list, 0u, nh, p->d_counter + 57,
-			c->d_tok_cache, p->d_tok_ofs, p->d_tokres, p->d_fb_list, p->d_counter + 52, nh, p->seg, seg_min);
-		c->launches++;
-		CK(cudaGetLastError());
+		for (uint32_t g = 0; g < n_grp; g++) {
+			const Grp &G = grp[g];
+			CK(cudaStreamWaitEvent(G.st, c->ev_fork, 0));
+			const uint32_t ng = G.h1 - G.h0;
+			const uint32_t grid4 = gs ? (uint32_t)atoi(gs) : std::max(1u, std::min((uint32_t)(c->sm_count * per_sm4), ng));
+			kern4<<<grid4, thr4, smem4x, G.st>>>(d_archive, p->d_ents, p->d_est, p->d_status, p->d_inflate_list, G.h0, G.h1, p->d_counter + G.c_spec,
+				c->d_tok_cache, p->d_tok_ofs, p->d_tokres, p->d_fb_list, p->d_counter + 52, nh, p->seg, seg_min);
+			c->launches++;
+			CK(cudaGetLastError());
+		}
 	}
 	// few streams: a warp per stream leaves the machine idle while every stream waits for its own serial rounds — then the
 	// regular streams get a 4-warp CTA each as well (128 pieces per round; configs[0] as written: 1,000 streams on 148 SMs)
@@ -794,44 +854,31 @@ static int dispatch_inflate3(otz_ctx *c, otz_plan *p, const uint8_t *d_archive, 
 		c->launches++;
 		CK(cudaGetLastError());
 	}
-	if (nh) {
-		I2SegCtl sg = p->seg;
-		sg.sym_top = reinterpret_cast<unsigned long long *>(p->d_counter + 62);
-		sg.out_mis = (uint32_t)(reinterpret_cast<uint64_t>(d_out) & 15u);
-		sg.sym_cap = 0;
-		if (!c->seg_serial && p->sym_elems) {
-			if (p->sym_elems > c->sym_cache_elems) {
-				CK(cudaStreamSynchronize(c->stream));
-				CK(cudaStreamSynchronize(s2));
-				cudaFree(c->d_sym_cache);
-				c->d_sym_cache = nullptr;
-				c->sym_cache_elems = 0;
-				if (cudaMalloc(&c->d_sym_cache, p->sym_elems * 2 + 64) == cudaSuccess) {
-					c->sym_cache_elems = p->sym_elems;
-				} else {
-					cudaGetLastError();
-				}
-			}
-			sg.sym_cap = c->d_sym_cache ? std::min<uint64_t>(p->sym_elems, c->sym_limit) : 0;
-		}
-		CK(cudaMemsetAsync(p->seg.n_par, 0, 4, s2));
-		CK(cudaMemsetAsync(p->seg.nlive, 0, nh * 4, s2));
-		CK(cudaMemsetAsync(p->seg.par, 0, nh * 4, s2));
-		k_seg_stitch<<<(nh + 63) / 64, 64, 0, s2>>>(p->d_ents, p->d_status, p->d_inflate_list, nh, sg, p->d_fb_list, p->d_counter + 52);
+	for (uint32_t g = 0; g < n_grp; g++) {
+		const Grp &G = grp[g];
+		const uint32_t ng = G.h1 - G.h0;
+		I2SegCtl sgg = sg;
+		sgg.n_par = p->seg.n_par + G.par_slot;
+		sgg.par_items = p->seg.par_items + (size_t)G.h0 * I2_MAXSEG;
+		CK(cudaMemsetAsync(sgg.n_par, 0, 4, G.st));
+		CK(cudaMemsetAsync(p->seg.nlive + G.h0, 0, ng * 4, G.st));
+		CK(cudaMemsetAsync(p->seg.par + G.h0, 0, ng * 4, G.st));
+		k_seg_stitch<<<(ng + 63) / 64, 64, 0, G.st>>>(p->d_ents, p->d_status, p->d_inflate_list, G.h1, sgg, p->d_fb_list, p->d_counter + 52, G.h0);
 		int per_sm2 = 0;
 		CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm2, k_inflate_lz<OTZ_SEG_RING, false, true>, 128, 4 * sizeof(I2LzSmem<OTZ_SEG_RING>)));
-		const uint32_t lgrid = std::max(1u, std::min((uint32_t)(c->sm_count * std::max(per_sm2, 1)), (nh + 3) / 4));
-		k_inflate_lz<OTZ_SEG_RING, false, true><<<lgrid, 128, 4 * sizeof(I2LzSmem<OTZ_SEG_RING>), s2>>>(d_out, p->d_ents, p->d_inflate_list, nh, p->d_counter + 58,
-			c->d_tok_cache, p->d_tok_ofs, p->d_tokres, p->d_status, p->d_produced, sg);
+		const uint32_t lgrid = std::max(1u, std::min((uint32_t)(c->sm_count * std::max(per_sm2, 1)), (ng + 3) / 4));
+		k_inflate_lz<OTZ_SEG_RING, false, true><<<lgrid, 128, 4 * sizeof(I2LzSmem<OTZ_SEG_RING>), G.st>>>(d_out, p->d_ents, p->d_inflate_list, G.h1,
+			p->d_counter + G.c_seglz, c->d_tok_cache, p->d_tok_ofs, p->d_tokres, p->d_status, p->d_produced, sgg, G.h0);
 		c->launches += 2;
 		if (sg.sym_cap) {
-			int rc_ = c->seg_ring == 8192 ? launch_seg_par<8192>(c, p, d_out, sg, s2) : launch_seg_par<4096>(c, p, d_out, sg, s2);
+			int rc_ = c->seg_ring == 8192 ? launch_seg_par<8192>(c, p, d_out, sgg, G.st, G.h0, G.h1, p->d_counter + G.c_par, p->d_counter + G.c_tr)
+			                              : launch_seg_par<4096>(c, p, d_out, sgg, G.st, G.h0, G.h1, p->d_counter + G.c_par, p->d_counter + G.c_tr);
 			if (rc_) {
 				return rc_;
 			}
 		}
 		CK(cudaGetLastError());
-		CK(cudaEventRecord(c->ev_join, s2));
+		CK(cudaEventRecord(G.join, G.st));
 		forked = true;
 	}
 	if (count) {
@@ -846,7 +893,9 @@ static int dispatch_inflate3(otz_ctx *c, otz_plan *p, const uint8_t *d_archive, 
 		}
 	}
 	if (forked) {
-		CK(cudaStreamWaitEvent(s, c->ev_join, 0));   // (k_seg_stitch appends to the same fallback list)
+		for (uint32_t g = 0; g < n_grp; g++) {
+			CK(cudaStreamWaitEvent(s, grp[g].join, 0));   // (k_seg_stitch appends to the same fallback list)
+		}
 	}
 	return launch_inflate_cfg(c, p, d_archive, d_out, 32, 4096, 0, p->n_inflate, 16, s, p->d_fb_list, p->d_counter + 52);
 }
@@ -964,7 +1013,7 @@ extern "C" int otz_extract_run(otz_ctx *c, otz_plan *p, const uint8_t *d_archive
 			CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_inflate_lz<4096, true, false>, 128, 4 * sizeof(I2LzSmem<4096>)));
 			const uint32_t lgrid = std::max(1u, std::min((uint32_t)(c->sm_count * std::max(per_sm, 1)), (p->n_zstd + 3) / 4));
 			k_inflate_lz<4096, true, false><<<lgrid, 128, 4 * sizeof(I2LzSmem<4096>), s>>>(d_out, p->d_ents, p->d_zstd_list, p->n_zstd, p->d_counter + 36,
-				c->d_ztok_cache, p->d_ztok_ofs, p->d_ztokres, p->d_status, p->d_produced, I2SegCtl{});
+				c->d_ztok_cache, p->d_ztok_ofs, p->d_ztokres, p->d_status, p->d_produced, I2SegCtl{}, 0u);
 			c->launches++;
 		} else {
 			const size_t zsmem = 4 * sizeof(ZstdSmem);
