@@ -57,7 +57,7 @@ DECODE_KERNELS = {
     "c1": "k_inflate_spec + k_inflate_lz (+ k_inflate for declined streams)",
     "c3": "k_inflate_spec<1> + k_inflate_lz; entries >= 1 MiB: k_inflate_spec<4> + k_inflate_lz<symbols> + k_seg_window + k_seg_translate",
     "c3w": "k_inflate_spec + k_inflate_lz (+ k_inflate for declined streams)",
-    "c4": "k_zstdref", "c4z": "k_zstd_tok + k_inflate_lz<wide>", "c2": "k_store_copy", "c2x": "k_store_copy",
+    "c4": "k_zstdref", "c4z": "k_zstd_lit + k_zstd_seq + k_inflate_lz<wide>", "c2": "k_store_copy", "c2x": "k_store_copy",
 }
 # stride of the entry subsample the CPU legs time (the reference needs ~1 min per pass of configs[2] on
 # 16 cores; every stride-th entry of the same list keeps the size distribution)

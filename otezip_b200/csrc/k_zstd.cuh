@@ -8,11 +8,10 @@
 // reference rejects"), so the default reference-compatible policy still matches the reference bit for bit.
 // Parity for this kernel is pinned against libzstd 1.5.5 (tests/test_gpu_zstd.py), not against the reference.
 //
-// Two decoders live here.
-//   * k_zstd_tok + k_inflate_lz<W, true> (default): ONE LANE per entry parses everything — headers, FSE / Huffman
-//     tables in its own shared-memory slot, literals, sequences — and emits tokens (literal bytes + 8-byte sequence
-//     records); the lanes of a warp run on different entries in lock-step; the LZ executor of the inflate path
-//     (k_inflate2.cuh) then writes the bytes.  See zstd_tok_entry.
+// Two decoders live here and in k_zstd_tok.cuh.
+//   * k_zstd_lit + k_zstd_seq + k_inflate_lz<W, true> (default; k_zstd_tok.cuh): the literal sections and the sequence
+//     sections of all entries are decoded by two kernels that walk the same frame / block structure, and the LZ executor of
+//     the inflate path (k_inflate2.cuh) writes the bytes.
 //   * k_zstd (OTZ_ZSTD_MODE=legacy, or when the token scratch cannot be allocated): one warp per entry; lane 0 parses
 //     headers, builds the tables and runs the three interleaved FSE states, lanes 0..3 decode the 4 Huffman literal
 //     streams into a per-warp HBM scratch, all lanes execute batches of 32 sequences straight in HBM.
@@ -263,14 +262,17 @@ __device__ uint32_t zs_read_ncount(const uint8_t *p, uint32_t n, int16_t *norm, 
 	return used <= n ? used : 0;
 }
 
-// FSE_buildDTable: entry = symbol | nbBits << 8 | newStateBase << 16
-__device__ void zs_build_fse(uint32_t *tbl, const int16_t *norm, uint32_t nsym, uint32_t al) {
+// FSE_buildDTable.  32-bit entries: symbol | nbBits << 8 | newStateBase << 16.  16-bit entries (k_zstd_seq: half the
+// table memory per lane): symbol | nextState << 6 with nextState in [count, 2 count) — nbBits = log - highbit(nextState)
+// and newStateBase = (nextState << nbBits) - size follow from it (zs_fse16)
+template <typename E>
+__device__ void zs_build_fse(E *tbl, const int16_t *norm, uint32_t nsym, uint32_t al) {
 	const uint32_t size = 1u << al;
 	uint16_t next[64];
 	uint32_t high = size - 1;
 	for (uint32_t s = 0; s < nsym; s++) {
 		if (norm[s] == -1) {
-			tbl[high--] = s;
+			tbl[high--] = (E)s;
 			next[s] = 1;
 		} else {
 			next[s] = (uint16_t)norm[s];
@@ -280,7 +282,7 @@ __device__ void zs_build_fse(uint32_t *tbl, const int16_t *norm, uint32_t nsym, 
 	uint32_t pos = 0;
 	for (uint32_t s = 0; s < nsym; s++) {
 		for (int i = 0; i < norm[s]; i++) {
-			tbl[pos] = s;
+			tbl[pos] = (E)s;
 			pos = (pos + step) & mask;
 			while (pos > high) {
 				pos = (pos + step) & mask;
@@ -290,9 +292,20 @@ __device__ void zs_build_fse(uint32_t *tbl, const int16_t *norm, uint32_t nsym, 
 	for (uint32_t u = 0; u < size; u++) {
 		const uint32_t s = tbl[u] & 0xFF;
 		const uint32_t ns = next[s]++;
-		const uint32_t nb = al - (31 - __clz(ns));
-		tbl[u] = s | (nb << 8) | (((ns << nb) - size) << 16);
+		if (sizeof(E) == 2) {
+			tbl[u] = (E)(s | (ns << 6));
+		} else {
+			const uint32_t nb = al - (31 - __clz(ns));
+			tbl[u] = (E)(s | (nb << 8) | (((ns << nb) - size) << 16));
+		}
 	}
+}
+// a 16-bit entry taken apart: symbol, bits to read for the next state, base of the next state
+__device__ __forceinline__ void zs_fse16(uint32_t e, uint32_t log, uint32_t &sym, uint32_t &nb, uint32_t &base) {
+	const uint32_t ns = e >> 6;
+	sym = e & 63u;
+	nb = log - (31u - (uint32_t)__clz(ns));
+	base = (ns << nb) - (1u << log);
 }
 
 // Huffman decoding table from weights[0..n) (the last weight is implied); returns table log or 0
@@ -332,7 +345,8 @@ __device__ uint32_t zs_build_huf(uint16_t *tbl, uint8_t *w, uint32_t n) {
 }
 
 // Huffman tree description (RFC 8878 4.2.1); returns bytes consumed or 0
-__device__ uint32_t zs_read_huf(ZstdSmem &S, const uint8_t *p, uint32_t n) {
+template <typename SM>
+__device__ uint32_t zs_read_huf(SM &S, const uint8_t *p, uint32_t n) {
 	if (n == 0) {
 		return 0;
 	}
@@ -403,7 +417,8 @@ __device__ uint32_t zs_read_huf(ZstdSmem &S, const uint8_t *p, uint32_t n) {
 }
 
 // one Huffman-coded stream -> dst[0..count)
-__device__ bool zs_huf_stream(const ZstdSmem &S, const uint8_t *p, uint32_t n, uint8_t *dst, uint32_t count) {
+template <typename SM>
+__device__ bool zs_huf_stream(const SM &S, const uint8_t *p, uint32_t n, uint8_t *dst, uint32_t count) {
 	ZsBackW b;
 	if (!b.init(p, n)) {
 		return false;
@@ -429,7 +444,8 @@ __device__ bool zs_huf_stream(const ZstdSmem &S, const uint8_t *p, uint32_t n, u
 }
 
 // sequence table for one of LL / OF / ML according to its compression mode; returns bytes consumed or -1
-__device__ int zs_seq_table(uint32_t mode, const uint8_t *p, uint32_t n, uint32_t *tbl, uint32_t *log, uint32_t *have, const int16_t *def,
+template <typename E>
+__device__ int zs_seq_table(uint32_t mode, const uint8_t *p, uint32_t n, E *tbl, uint32_t *log, uint32_t *have, const int16_t *def,
 	uint32_t def_n, uint32_t def_log, uint32_t max_sym, uint32_t max_log) {
 	if (mode == 0) {
 		int16_t norm[53];
@@ -445,7 +461,7 @@ __device__ int zs_seq_table(uint32_t mode, const uint8_t *p, uint32_t n, uint32_
 		if (n < 1 || p[0] > max_sym) {
 			return -1;
 		}
-		tbl[0] = p[0];   // nbBits 0, base 0: a one-entry table
+		tbl[0] = (E)(sizeof(E) == 2 ? (p[0] | (1u << 6)) : p[0]);   // nbBits 0, base 0: a one-entry table
 		*log = 0;
 		*have = 1;
 		return 1;
@@ -964,475 +980,6 @@ __device__ int32_t zstd_decode_entry(ZstdSmem &S, const uint8_t *__restrict__ in
 	return op == cap ? OTZ_ST_OK : OTZ_ST_SIZE;
 }
 
-// ------------------------------------------------------------------------------------------------
-// Lane-per-entry tokenizer (phase A of the two-phase Zstandard path).  ONE THREAD parses all frames of one entry —
-// headers, FSE / Huffman tables in its own shared-memory slot, literals, sequences — and emits tokens for
-// k_inflate_lz<W, true>: the literal bytes (dense, in stream order) and 8-byte records {literal run | (length-3) << 9,
-// offset}, long literal runs and long matches split into <= 511 / <= 258 byte pieces.  The lanes of a warp run
-// this on different entries in lock-step: one warp instruction advances several entries, where the warp-per-entry
-// decoder (zstd_decode_entry) spends 32 lanes on lane 0's serial work.  Returns the status code.
-struct ZsTok {
-	uint8_t *L;        // literal bytes, ascending
-	uint2 *seq_end;    // records, descending from here
-	uint32_t nl;       // literals written
-	uint32_t nseq;     // records written
-	uint32_t run;      // literals since the last match
-	__device__ __forceinline__ void rec(uint32_t w0, uint32_t off) {
-		seq_end[-1 - (int32_t)nseq] = make_uint2(w0, off);
-		nseq++;
-	}
-	__device__ __forceinline__ void match(uint32_t len, uint32_t off) {   // len >= 3
-		while (run >= 511u) {
-			rec(511u, 0u);
-			run -= 511u;
-		}
-		uint32_t r = run;
-		run = 0;
-		while (len) {
-			const uint32_t piece = len > 258u ? (len - 258u < 3u ? len - 3u : 258u) : len;
-			rec(r | ((piece - 3u) << 9), off);
-			r = 0;
-			len -= piece;
-		}
-	}
-};
-
-__device__ int32_t zstd_tok_entry(ZstdSmem &S, const uint8_t *__restrict__ in, uint32_t n, uint32_t cap, ZsTok &T) {
-	uint32_t ip = 0, op = 0;
-	int32_t err = 0;
-	uint32_t n_frames = 0;
-	while (ip < n && !err) {
-		if (n - ip < 4) {
-			err = OTZ_ST_TRUNCATED;
-			break;
-		}
-		const uint32_t magic = ld_le32(in + ip);
-		if ((magic & 0xFFFFFFF0u) == 0x184D2A50u) {   // skippable frame
-			if (n - ip < 8 || n - ip - 8 < ld_le32(in + ip + 4)) {
-				err = OTZ_ST_TRUNCATED;
-				break;
-			}
-			ip += 8 + ld_le32(in + ip + 4);
-			continue;
-		}
-		if (magic != 0xFD2FB528u) {
-			err = OTZ_ST_DATA;
-			break;
-		}
-		ip += 4;
-		if (ip >= n) {
-			err = OTZ_ST_TRUNCATED;
-			break;
-		}
-		// ---- frame header (RFC 8878 3.1.1.1)
-		const uint32_t fhd = in[ip++];
-		const uint32_t fcs_flag = fhd >> 6, single = (fhd >> 5) & 1, has_cksum = (fhd >> 2) & 1, did_flag = fhd & 3;
-		if (fhd & 0x08) {
-			err = OTZ_ST_DATA;
-			break;
-		}
-		const uint32_t did_len = did_flag == 3 ? 4 : did_flag;
-		const uint32_t fcs_len = fcs_flag == 0 ? single : (fcs_flag == 1 ? 2 : fcs_flag == 2 ? 4 : 8);
-		if (n - ip < (single ? 0 : 1) + did_len + fcs_len) {
-			err = OTZ_ST_TRUNCATED;
-			break;
-		}
-		if (!single) {
-			ip++;   // window descriptor: the whole output is addressable here
-		}
-		uint32_t did = 0;
-		for (uint32_t i = 0; i < did_len; i++) {
-			did |= (uint32_t)in[ip++] << (8 * i);
-		}
-		if (did) {
-			err = OTZ_ST_DATA;   // dictionaries are not available to a ZIP entry
-			break;
-		}
-		uint64_t fcs = 0;
-		for (uint32_t i = 0; i < fcs_len; i++) {
-			fcs |= (uint64_t)in[ip++] << (8 * i);
-		}
-		if (fcs_len == 2) {
-			fcs += 256;
-		}
-		const uint32_t frame_start = op;
-		uint32_t rep1 = 1, rep2 = 4, rep3 = 8;
-		S.have_huf = S.have_ll = S.have_ml = S.have_of = 0;
-		S.err = 0;
-		// ---- blocks
-		for (;;) {
-			if (n - ip < 3) {
-				err = OTZ_ST_TRUNCATED;
-				break;
-			}
-			const uint32_t bh = in[ip] | (in[ip + 1] << 8) | (in[ip + 2] << 16);
-			ip += 3;
-			const uint32_t last = bh & 1, btype = (bh >> 1) & 3, bsz = bh >> 3;
-			if (btype == 3 || bsz > ZS_BLOCK_MAX) {
-				err = OTZ_ST_DATA;
-				break;
-			}
-			if (btype == 0) {   // raw
-				if (n - ip < bsz) {
-					err = OTZ_ST_TRUNCATED;
-					break;
-				}
-				if (cap - op < bsz) {
-					err = OTZ_ST_OVERFLOW;
-					break;
-				}
-				for (uint32_t i = 0; i < bsz; i++) {
-					T.L[T.nl + i] = in[ip + i];
-				}
-				T.nl += bsz;
-				T.run += bsz;
-				ip += bsz;
-				op += bsz;
-			} else if (btype == 1) {   // RLE
-				if (n - ip < 1) {
-					err = OTZ_ST_TRUNCATED;
-					break;
-				}
-				if (cap - op < bsz) {
-					err = OTZ_ST_OVERFLOW;
-					break;
-				}
-				const uint8_t b = in[ip++];
-				const uint32_t nlit = bsz <= 3u ? bsz : 1u;   // one literal, the rest a run-length match of offset 1
-				for (uint32_t i = 0; i < nlit; i++) {
-					T.L[T.nl++] = b;
-				}
-				T.run += nlit;
-				if (bsz > 3u) {
-					T.match(bsz - 1u, 1u);
-				}
-				op += bsz;
-			} else {   // compressed
-				if (n - ip < bsz || bsz < 2) {
-					err = n - ip < bsz ? OTZ_ST_TRUNCATED : OTZ_ST_DATA;
-					break;
-				}
-				const uint8_t *bp = in + ip;
-				ip += bsz;
-				// ---- literals section header
-				const uint32_t b0 = bp[0];
-				const uint32_t ltype = b0 & 3, sf = (b0 >> 2) & 3;
-				uint32_t regen, lcomp = 0, lhdr, nstreams = 1;
-				if (ltype < 2) {
-					if ((sf & 1) == 0) {
-						regen = b0 >> 3;
-						lhdr = 1;
-					} else if (sf == 1) {
-						regen = (b0 >> 4) | (bp[1] << 4);
-						lhdr = 2;
-					} else {
-						if (bsz < 3) {
-							err = OTZ_ST_DATA;
-							break;
-						}
-						regen = (b0 >> 4) | (bp[1] << 4) | (bp[2] << 12);
-						lhdr = 3;
-					}
-				} else {
-					if (bsz < 5) {
-						err = OTZ_ST_DATA;
-						break;
-					}
-					const uint64_t v = (uint64_t)ld_le32(bp) | ((uint64_t)bp[4] << 32);
-					if (sf <= 1) {
-						regen = (uint32_t)(v >> 4) & 0x3FF;
-						lcomp = (uint32_t)(v >> 14) & 0x3FF;
-						lhdr = 3;
-						nstreams = sf == 0 ? 1 : 4;
-					} else if (sf == 2) {
-						regen = (uint32_t)(v >> 4) & 0x3FFF;
-						lcomp = (uint32_t)(v >> 18) & 0x3FFF;
-						lhdr = 4;
-						nstreams = 4;
-					} else {
-						regen = (uint32_t)(v >> 4) & 0x3FFFF;
-						lcomp = (uint32_t)(v >> 22) & 0x3FFFF;
-						lhdr = 5;
-						nstreams = 4;
-					}
-				}
-				if (regen > ZS_BLOCK_MAX) {
-					err = OTZ_ST_DATA;
-					break;
-				}
-				if (regen > cap - T.nl) {
-					err = OTZ_ST_OVERFLOW;   // every literal is an output byte
-					break;
-				}
-				uint32_t lsec;   // bytes of the whole literals section
-				uint8_t *const lit = T.L + T.nl;   // the literals of this block go straight into the token scratch
-				if (ltype == 0) {
-					lsec = lhdr + regen;
-					if (lsec > bsz) {
-						err = OTZ_ST_DATA;
-						break;
-					}
-					for (uint32_t i = 0; i < regen; i++) {
-						lit[i] = bp[lhdr + i];
-					}
-				} else if (ltype == 1) {
-					lsec = lhdr + 1;
-					if (lsec > bsz) {
-						err = OTZ_ST_DATA;
-						break;
-					}
-					const uint8_t b = bp[lhdr];
-					for (uint32_t i = 0; i < regen; i++) {
-						lit[i] = b;
-					}
-				} else {
-					lsec = lhdr + lcomp;
-					if (lsec > bsz) {
-						err = OTZ_ST_DATA;
-						break;
-					}
-					const uint8_t *hp = bp + lhdr;
-					uint32_t hrem = lcomp;
-					if (ltype == 2) {
-						const uint32_t used = zs_read_huf(S, hp, hrem);
-						if (used == 0) {
-							S.err = OTZ_ST_DATA;
-						}
-						S.huf_used = used;
-					} else {
-						if (!S.have_huf) {
-							S.err = OTZ_ST_DATA;
-						}
-						S.huf_used = 0;
-					}
-					if (S.err) {
-						err = S.err;
-						break;
-					}
-					hp += S.huf_used;
-					hrem -= S.huf_used;
-					{
-						if (nstreams == 1) {
-							S.lit_ofs[0] = 0;
-							S.lit_ofs[1] = hrem;
-							S.lit_sizes[0] = regen;
-						} else if (hrem < 6) {
-							S.err = OTZ_ST_DATA;
-						} else {
-							const uint32_t s1 = ld_le16(hp), s2 = ld_le16(hp + 2), s3 = ld_le16(hp + 4);
-							if (6ull + s1 + s2 + s3 > hrem) {
-								S.err = OTZ_ST_DATA;
-							} else {
-								S.lit_ofs[0] = 6;
-								S.lit_ofs[1] = 6 + s1;
-								S.lit_ofs[2] = 6 + s1 + s2;
-								S.lit_ofs[3] = 6 + s1 + s2 + s3;
-								S.lit_ofs[4] = hrem;   // end of stream 4
-								const uint32_t q = (regen + 3) / 4;
-								S.lit_sizes[0] = S.lit_sizes[1] = S.lit_sizes[2] = q;
-								S.lit_sizes[3] = regen - 3 * q;
-								if (regen < 3 * q) {
-									S.err = OTZ_ST_DATA;
-								}
-							}
-						}
-					}
-					if (S.err) {
-						err = S.err;
-						break;
-					}
-					bool ok = true;
-					uint32_t dsto = 0;
-					for (uint32_t st = 0; st < nstreams && ok; st++) {
-						const uint32_t so = S.lit_ofs[st], se = nstreams == 1 ? S.lit_ofs[1] : S.lit_ofs[st + 1];
-						ok = zs_huf_stream(S, hp + so, se - so, lit + dsto, S.lit_sizes[st]);
-						dsto += S.lit_sizes[st];
-					}
-					if (!ok) {
-						err = OTZ_ST_DATA;
-						break;
-					}
-				}
-				T.nl += regen;
-				// ---- sequences section
-				const uint8_t *sp = bp + lsec;
-				uint32_t srem = bsz - lsec;
-				if (srem < 1) {
-					err = OTZ_ST_DATA;
-					break;
-				}
-				uint32_t nseq = sp[0], shdr = 1;
-				if (nseq >= 128) {
-					if (nseq == 255) {
-						if (srem < 3) {
-							err = OTZ_ST_DATA;
-							break;
-						}
-						nseq = sp[1] + (sp[2] << 8) + 0x7F00;
-						shdr = 3;
-					} else {
-						if (srem < 2) {
-							err = OTZ_ST_DATA;
-							break;
-						}
-						nseq = ((nseq - 128) << 8) + sp[1];
-						shdr = 2;
-					}
-				}
-				uint32_t lit_pos = 0;
-				if (nseq) {
-					if (srem < shdr + 1) {
-						err = OTZ_ST_DATA;
-						break;
-					}
-					const uint32_t modes = sp[shdr];
-					if (modes & 3) {
-						err = OTZ_ST_DATA;
-						break;
-					}
-					{
-						uint32_t o = shdr + 1;
-						int r = zs_seq_table(modes >> 6, sp + o, srem - o, S.ll, &S.ll_log, &S.have_ll, c_zs_ll_default, 36, 6, 35, ZS_LL_LOG_MAX);
-						if (r >= 0) {
-							o += r;
-							r = zs_seq_table((modes >> 4) & 3, sp + o, srem - o, S.of, &S.of_log, &S.have_of, c_zs_of_default, 29, 5, 31, ZS_OF_LOG_MAX);
-						}
-						if (r >= 0) {
-							o += r;
-							r = zs_seq_table((modes >> 2) & 3, sp + o, srem - o, S.ml, &S.ml_log, &S.have_ml, c_zs_ml_default, 53, 6, 52, ZS_ML_LOG_MAX);
-						}
-						if (r >= 0) {
-							o += r;
-						}
-						if (r < 0 || o > srem) {
-							S.err = OTZ_ST_DATA;
-						}
-						S.seq_start = o;
-					}
-					if (S.err) {
-						err = S.err;
-						break;
-					}
-					const uint32_t so = S.seq_start;
-					ZsBackW b;
-					if (!b.init(sp + so, srem - so)) {
-						err = OTZ_ST_DATA;
-						break;
-					}
-					uint32_t st_ll = b.read(S.ll_log), st_of = b.read(S.of_log), st_ml = b.read(S.ml_log);
-					for (uint32_t k = 0; k < nseq; k++) {
-						const uint32_t el = S.ll[st_ll], eo = S.of[st_of], em = S.ml[st_ml];
-						const uint32_t lc = el & 0xFF, oc = eo & 0xFF, mc = em & 0xFF;
-						if (lc > 35 || mc > 52 || oc > 31) {
-							err = OTZ_ST_DATA;
-							break;
-						}
-						// one window for the whole sequence: three extra-bit fields, then (unless it is the last
-						// sequence) the three state updates, in the RFC 8878 4.1.1 order
-						const bool last_seq = k + 1 >= nseq;
-						const uint32_t n_ml = c_zs_ml_bits[mc], n_ll = c_zs_ll_bits[lc];
-						const uint32_t u_ll = last_seq ? 0u : (el >> 8) & 0xFF, u_ml = last_seq ? 0u : (em >> 8) & 0xFF,
-						               u_of = last_seq ? 0u : (eo >> 8) & 0xFF;
-						uint64_t x = b.top64();
-						uint32_t ofv;
-						if (oc + n_ml + n_ll + u_ll + u_ml + u_of > 64u) {
-							ofv = (1u << oc) + zs_take(x, oc);   // (offset codes of 30+ bits: the rest is at most 58 bits)
-							b.skip(oc);
-							x = b.top64();
-							b.skip(n_ml + n_ll + u_ll + u_ml + u_of);
-						} else {
-							b.skip(oc + n_ml + n_ll + u_ll + u_ml + u_of);
-							ofv = (1u << oc) + zs_take(x, oc);
-						}
-						const uint32_t mlv = c_zs_ml_base[mc] + zs_take(x, n_ml);
-						const uint32_t llv = c_zs_ll_base[lc] + zs_take(x, n_ll);
-						if (!last_seq) {
-							st_ll = (el >> 16) + zs_take(x, u_ll);
-							st_ml = (em >> 16) + zs_take(x, u_ml);
-							st_of = (eo >> 16) + zs_take(x, u_of);
-						}
-						if (b.pos() < 0) {
-							err = OTZ_ST_DATA;
-							break;
-						}
-						uint32_t offset;
-						if (ofv > 3) {
-							offset = ofv - 3;
-							rep3 = rep2;
-							rep2 = rep1;
-							rep1 = offset;
-						} else {
-							const uint32_t idx = ofv + (llv == 0 ? 1 : 0);   // 1..4
-							if (idx == 1) {
-								offset = rep1;
-							} else {
-								offset = idx == 2 ? rep2 : idx == 3 ? rep3 : rep1 - 1;
-								if (offset == 0) {
-									err = OTZ_ST_DATA;
-									break;
-								}
-								if (idx != 2) {
-									rep3 = rep2;
-								}
-								rep2 = rep1;
-								rep1 = offset;
-							}
-						}
-						if (llv > regen - lit_pos || llv + mlv > cap - op || offset > op + llv - frame_start) {   // (llv, mlv < 2^18)
-							err = llv > regen - lit_pos ? OTZ_ST_DATA : (llv + mlv > cap - op ? OTZ_ST_OVERFLOW : OTZ_ST_DATA);
-							break;
-						}
-						op += llv;
-						lit_pos += llv;
-						T.run += llv;
-						T.match(mlv, offset);
-						op += mlv;
-					}
-					if (!err && b.pos() != 0) {
-						err = OTZ_ST_DATA;   // the bitstream must be consumed exactly
-					}
-					if (err) {
-						break;
-					}
-				}
-				// ---- literals after the last sequence stay pending in the run
-				const uint32_t tail = regen - lit_pos;
-				if (cap - op < tail) {
-					err = OTZ_ST_OVERFLOW;
-					break;
-				}
-				T.run += tail;
-				op += tail;
-			}
-			if (last) {
-				break;
-			}
-		}
-		if (err) {
-			break;
-		}
-		if (has_cksum) {
-			if (n - ip < 4) {
-				err = OTZ_ST_TRUNCATED;
-				break;
-			}
-			ip += 4;   // XXH64 low word: not verified here, the ZIP CRC-32 covers the entry
-		}
-		if (fcs_len && fcs != (uint64_t)(op - frame_start)) {
-			err = OTZ_ST_DATA;
-			break;
-		}
-		n_frames++;
-	}
-	if (err) {
-		return err;
-	}
-	if (n_frames == 0) {
-		return OTZ_ST_DATA;
-	}
-	return op == cap ? OTZ_ST_OK : OTZ_ST_SIZE;
-}
-
 // grid: persistent; one warp per method-93 entry that k_zstdref could not read as a reference container.
 __global__ void __launch_bounds__(128) k_zstd(const uint8_t *__restrict__ archive, uint8_t *__restrict__ out, const otz_entry *__restrict__ ents,
 	const OtzEntryState *__restrict__ est, int32_t *__restrict__ status, const uint32_t *__restrict__ list, uint32_t n_list,
@@ -1464,54 +1011,5 @@ __global__ void __launch_bounds__(128) k_zstd(const uint8_t *__restrict__ archiv
 			status[ei] = st;
 		}
 		__syncwarp();
-	}
-}
-
-// ------------------------------------------------------------------------------------------------
-// phase A of the two-phase Zstandard path: one lane per entry (see zstd_tok_entry), `lanes` lanes per warp, one warp
-// per CTA; each live lane owns a ZstdSmem slot (stride chosen so that equal indices of different lanes fall into
-// different banks).  Entries that k_zstdref resolved (status != PENDING) are skipped.  A valid frame is released to
-// k_inflate_lz<W, true> through tokres[]; an invalid one gets its status word here.
-#define ZS_LANE_STRIDE ((int)sizeof(ZstdSmem) + 64)   // 9680 + 64 bytes: 2436 words = 4 (mod 32)
-// worst-case token scratch of an entry of n output bytes: literals + 8 bytes per record (a match piece is >= 3 bytes,
-// an escape exactly 511 literals)
-__host__ __device__ __forceinline__ uint64_t zs_scratch_bytes(uint64_t n) { return ((n + 8 * (n / 3 + n / 511 + 8) + 64 + 15) / 16) * 16; }
-
-__global__ void __launch_bounds__(32) k_zstd_tok(const uint8_t *__restrict__ archive, const otz_entry *__restrict__ ents,
-	const OtzEntryState *__restrict__ est, int32_t *__restrict__ status, const uint32_t *__restrict__ list, uint32_t n_list,
-	uint8_t *__restrict__ scratch, const uint64_t *__restrict__ tok_ofs, I2TokRes *__restrict__ tokres, uint32_t *__restrict__ work_counter,
-	uint32_t lanes) {
-	extern __shared__ __align__(16) uint8_t smem_raw[];
-	const uint32_t lane = threadIdx.x;
-	if (lane >= lanes) {
-		return;
-	}
-	ZstdSmem &S = *reinterpret_cast<ZstdSmem *>(smem_raw + lane * ZS_LANE_STRIDE);
-	for (;;) {
-		const uint32_t k = atomicAdd(work_counter, 1u);
-		if (k >= n_list) {
-			break;
-		}
-		const uint32_t ei = list[k];
-		tokres[k].ok = 0u;
-		if (status[ei] != OTZ_ST_PENDING) {
-			continue;   // resolved as a reference container (or failed earlier)
-		}
-		const otz_entry e = ents[ei];
-		ZsTok T;
-		T.L = scratch + tok_ofs[k];
-		T.seq_end = reinterpret_cast<uint2 *>(scratch + tok_ofs[k + 1]);
-		T.nl = T.nseq = T.run = 0;
-		const int32_t st = zstd_tok_entry(S, archive + est[ei].data_ofs, e.comp_size, e.uncomp_size, T);
-		if (st == OTZ_ST_OK) {
-			I2TokRes r;
-			r.nseq = T.nseq;
-			r.nlit = T.nl;
-			r.status = OTZ_ST_OK | OTZ_STF_REF_EOB;   // a valid stream that the reference rejects
-			r.ok = 1u;
-			tokres[k] = r;
-		} else {
-			status[ei] = st;
-		}
 	}
 }

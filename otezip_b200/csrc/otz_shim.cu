@@ -16,7 +16,7 @@
 #include "k_inflate3.cuh"
 #include "k_deflate.cuh"
 #include "k_resolve.cuh"
-#include "k_zstd.cuh"
+#include "k_zstd_tok.cuh"
 #include "otz_common.cuh"
 
 static thread_local char g_err[512] = "";
@@ -600,7 +600,7 @@ extern "C" int otz_plan_create(otz_ctx *c, const otz_entry *ents, uint32_t n, co
 			zofs[k + 1] = zofs[k] + zs_scratch_bytes(ents[zst[k]].uncomp_size);
 		}
 		p->ztok_bytes = zofs.back();
-		if ((rc = upload(&p->d_ztok_ofs, zofs, c->stream)) || cudaMalloc(&p->d_ztokres, zst.size() * sizeof(I2TokRes)) != cudaSuccess) {
+		if ((rc = upload(&p->d_ztok_ofs, zofs, c->stream)) || cudaMalloc(&p->d_ztokres, zst.size() * (sizeof(I2TokRes) + 4)) != cudaSuccess   /* + the literal kernel's verdicts */) {
 			otz_plan_destroy(c, p);
 			return rc ? rc : fail_cuda(cudaGetLastError(), "cudaMalloc(two-phase zstd lists)");
 		}
@@ -997,24 +997,59 @@ extern "C" int otz_extract_run(otz_ctx *c, otz_plan *p, const uint8_t *d_archive
 		}
 		if (two_phase) {
 			static bool zattr2 = false;
-			const uint32_t zl = 5;   // lanes (entries) per warp: 4 warps x 5 slots of 9.7 KB per SM
-			const int zsmem2 = (int)zl * ZS_LANE_STRIDE;
+			const int zsmem2 = (int)(ZS_LIT_WARPS * 8 * sizeof(ZsLitSmem));
 			if (!zattr2) {
-				CK(cudaFuncSetAttribute(k_zstd_tok, cudaFuncAttributeMaxDynamicSharedMemorySize, zsmem2));
+				CK(cudaFuncSetAttribute(k_zstd_lit, cudaFuncAttributeMaxDynamicSharedMemorySize, zsmem2));
+				CK(cudaFuncSetAttribute(k_zstd_seq, cudaFuncAttributeMaxDynamicSharedMemorySize, ZS_SEQ_WARPS * ZS_SEQ_LPW_MAX * ZS_SEQ_TAB_BYTES));
 				CK(cudaFuncSetAttribute(k_inflate_lz<4096, true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(4 * sizeof(I2LzSmem<4096>))));
 				zattr2 = true;
 			}
+			uint32_t *const litres = reinterpret_cast<uint32_t *>(p->d_ztokres + p->n_zstd);
+			// OTZ_ZSTD_TRACE=1: durations of the three kernels of this path, printed to stderr (a diagnostic: it waits for them)
+			const bool ztrace = getenv("OTZ_ZSTD_TRACE") != nullptr;
+			cudaEvent_t zev[4] = { nullptr, nullptr, nullptr, nullptr };
+			if (ztrace) {
+				for (int i = 0; i < 4; i++) {
+					CK(cudaEventCreate(&zev[i]));
+				}
+				CK(cudaEventRecord(zev[0], s));
+			}
 			int per_sm = 0;
-			CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_zstd_tok, 32, zsmem2));
-			const uint32_t zgrid = std::max(1u, std::min((uint32_t)(c->sm_count * std::max(per_sm, 1)), (p->n_zstd + zl - 1) / zl));
-			k_zstd_tok<<<zgrid, 32, zsmem2, s>>>(d_archive, p->d_ents, p->d_est, p->d_status, p->d_zstd_list, p->n_zstd, c->d_ztok_cache,
-				p->d_ztok_ofs, p->d_ztokres, p->d_counter + 32, zl);
+			CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_zstd_lit, 32 * ZS_LIT_WARPS, zsmem2));
+			const uint32_t zgrid = std::max(1u, std::min((uint32_t)(c->sm_count * std::max(per_sm, 1)), (p->n_zstd + 8 * ZS_LIT_WARPS - 1) / (8 * ZS_LIT_WARPS)));
+			k_zstd_lit<<<zgrid, 32 * ZS_LIT_WARPS, zsmem2, s>>>(d_archive, p->d_ents, p->d_est, p->d_status, p->d_zstd_list, p->n_zstd, c->d_ztok_cache,
+				p->d_ztok_ofs, litres, p->d_counter + 32);
 			c->launches++;
+			if (ztrace) {
+				CK(cudaEventRecord(zev[1], s));
+			}
+			// sequences: one CTA of ZS_SEQ_WARPS warps per SM, as many lanes per warp as the batch needs (their tables are the shared memory)
+			const uint32_t zlpw = std::max(1u, std::min((uint32_t)ZS_SEQ_LPW_MAX, (p->n_zstd + c->sm_count * ZS_SEQ_WARPS - 1) / (c->sm_count * ZS_SEQ_WARPS)));
+			const uint32_t sgrid = std::max(1u, std::min((uint32_t)c->sm_count, (p->n_zstd + zlpw * ZS_SEQ_WARPS - 1) / (zlpw * ZS_SEQ_WARPS)));
+			k_zstd_seq<<<sgrid, 32 * ZS_SEQ_WARPS, ZS_SEQ_WARPS * zlpw * ZS_SEQ_TAB_BYTES, s>>>(d_archive, p->d_ents, p->d_est, p->d_status, p->d_zstd_list,
+				p->n_zstd, c->d_ztok_cache, p->d_ztok_ofs, p->d_ztokres, litres, p->d_counter + 34, zlpw);
+			c->launches++;
+			if (ztrace) {
+				CK(cudaEventRecord(zev[2], s));
+			}
 			CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_inflate_lz<4096, true, false>, 128, 4 * sizeof(I2LzSmem<4096>)));
 			const uint32_t lgrid = std::max(1u, std::min((uint32_t)(c->sm_count * std::max(per_sm, 1)), (p->n_zstd + 3) / 4));
 			k_inflate_lz<4096, true, false><<<lgrid, 128, 4 * sizeof(I2LzSmem<4096>), s>>>(d_out, p->d_ents, p->d_zstd_list, p->n_zstd, p->d_counter + 36,
 				c->d_ztok_cache, p->d_ztok_ofs, p->d_ztokres, p->d_status, p->d_produced, I2SegCtl{}, 0u);
 			c->launches++;
+			if (ztrace) {
+				CK(cudaEventRecord(zev[3], s));
+				CK(cudaEventSynchronize(zev[3]));
+				float t[3];
+				for (int i = 0; i < 3; i++) {
+					CK(cudaEventElapsedTime(&t[i], zev[i], zev[i + 1]));
+				}
+				fprintf(stderr, "otz zstd: %u entries | k_zstd_lit %.3f ms (grid %u)  k_zstd_seq %.3f ms (grid %u, %u lanes per warp)  k_inflate_lz<wide> %.3f ms\n",
+					p->n_zstd, t[0], zgrid, t[1], sgrid, zlpw, t[2]);
+				for (int i = 0; i < 4; i++) {
+					cudaEventDestroy(zev[i]);
+				}
+			}
 		} else {
 			const size_t zsmem = 4 * sizeof(ZstdSmem);
 			static bool zattr = false;

@@ -31,7 +31,8 @@ full storecopy k_store_copy "$C2X"
 full tok k_inflate_tok "$C1"
 full lz k_inflate_lz "$C1"
 full zstdref k_zstdref "$C4"
-full ztok k_zstd_tok "$C4Z"
+full zseq k_zstd_seq "$C4Z"
+full zlit k_zstd_lit "$C4Z"
 full search k_block_search "$C3" 1
 full lzseg k_inflate_lz "$C3" 4      # launches per pass: serial chain walk (empty), symbols (PAR), regular path -> the PAR one of pass 2
 full segtok k_inflate_tok "$C3" 2     # per pass: segments, regular path -> the segment tokenizer of pass 2
