@@ -44,14 +44,16 @@ WORKLOADS = {
     "c4z": "configs[3] shape with real Zstandard (RFC 8878) frames from libzstd level 3 (parity pinned by libzstd, not by the reference)",
     "c5": "configs[4]: archive creation, batched DEFLATE compress + CRC-32, 4 GiB synthetic corpus",
     "c5z": "configs[4] shape, method 93: batched Zstandard compress (real RFC 8878 frames) + CRC-32, 4 GiB synthetic corpus",
+    "c5f": "configs[4] at compression level 1 (zip_set_file_compression flags 1-3: single-candidate parse), 4 GiB synthetic corpus",
     "c3w": "configs[2] shape, archive written by this library (chunk-indexed DEFLATE entries)",
     "c2x": "configs[1] shape, STORE entries extracted (copied to the arena) and CRC-checked",
 }
-DEFAULT_ENTRIES = {"c3": 10000, "c1": 1000, "c2": 10000, "c2x": 10000, "c4": 10000, "c4z": 10000, "c5": 16384, "c5z": 16384, "c3w": 2000}
+DEFAULT_ENTRIES = {"c3": 10000, "c1": 1000, "c2": 10000, "c2x": 10000, "c4": 10000, "c4z": 10000, "c5": 16384, "c5z": 16384, "c5f": 16384, "c3w": 2000}
 METRIC = {
     "c2": "CRC-32 verify GB/s (STORE payload bytes, device-timed)",
     "c5": "compress GB/s (uncompressed input, device-timed; CRC-32 + DEFLATE + compaction)",
     "c5z": "compress GB/s (uncompressed input, device-timed; CRC-32 + Zstandard + compaction)",
+    "c5f": "compress GB/s (uncompressed input, device-timed; CRC-32 + DEFLATE level 1 + compaction)",
 }
 DECODE_KERNELS = {
     "c1": "k_inflate_spec + k_inflate_lz (+ k_inflate for declined streams)",
@@ -61,7 +63,8 @@ DECODE_KERNELS = {
 }
 # stride of the entry subsample the CPU legs time (the reference needs ~1 min per pass of configs[2] on
 # 16 cores; every stride-th entry of the same list keeps the size distribution)
-REF_STRIDE = {"c3": 16, "c1": 1, "c2": 16, "c2x": 16, "c4": 4, "c4z": 4, "c3w": 16, "c5": 16, "c5z": 16}
+C5_METHOD = {"c5": 8, "c5z": 93, "c5f": 8 | 0x100}   # 0x100 = OTZ_M_FAST (include/otz_gpu.h)
+REF_STRIDE = {"c3": 16, "c1": 1, "c2": 16, "c2x": 16, "c4": 4, "c4z": 4, "c3w": 16, "c5": 16, "c5z": 16, "c5f": 16}
 
 
 def metric_name(wl: str) -> str:
@@ -86,9 +89,9 @@ def entry_plan(name: str, n: int):
     if name == "c4z":
         return dict(sizes=[262144] * n, method=93, seed=4, sizes_desc="256 KiB each", data="JSON-log text (synth.TextPool, seed 4)",
                     codec="method 93, real Zstandard frames (libzstd level 3)")
-    if name in ("c5", "c5z"):
-        return dict(sizes=[262144] * n, method=8 if name == "c5" else 93, seed=5, sizes_desc="256 KiB each", data="JSON-log text (synth.TextPool, seed 5)",
-                    codec=("DEFLATE" if name == "c5" else "Zstandard (real frames)") + " compress (GPU), zero-length / incompressible -> STORE")
+    if name in ("c5", "c5z", "c5f"):
+        return dict(sizes=[262144] * n, method=93 if name == "c5z" else 8, seed=5, sizes_desc="256 KiB each", data="JSON-log text (synth.TextPool, seed 5)",
+                    codec=("DEFLATE" if name == "c5" else "DEFLATE level 1" if name == "c5f" else "Zstandard (real frames)") + " compress (GPU), zero-length / incompressible -> STORE")
     raise SystemExit("unknown workload " + name)
 
 
@@ -400,7 +403,7 @@ def reference_sample(wl_name: str, n_entries: int | None, tmpdir: str):
     """The CPU legs' input: every stride-th entry of the workload's own entry list (same sizes, same text, same codec)
     as ZIP32 file(s) on disk (the reference reads FILE*).  -> (paths, per-file entry sizes, bytes, description)"""
     n = n_entries or DEFAULT_ENTRIES[wl_name]
-    name = "c4" if wl_name == "c4z" else ("c3" if wl_name in ("c3w", "c5", "c5z") else wl_name)   # the reference rejects real Zstandard frames (F3)
+    name = "c4" if wl_name == "c4z" else ("c3" if wl_name in ("c3w", "c5", "c5z", "c5f") else wl_name)   # the reference rejects real Zstandard frames (F3)
     stride = REF_STRIDE[wl_name]
     idx = list(range(0, n, stride))
     bufs = []
@@ -423,7 +426,7 @@ def reference_sample(wl_name: str, n_entries: int | None, tmpdir: str):
         stride, "th" if stride != 1 else "st", len(idx), wl["uncomp_bytes"] / GB)
     if wl_name == "c4z":
         what += "; reference-container payloads — the reference rejects real Zstandard frames (SURVEY F3)"
-    if wl_name in ("c5", "c5z"):
+    if wl_name in ("c5", "c5z", "c5f"):
         what += "; the reference's DEFLATE writer is broken (SURVEY F2), so the CPU leg is its READ path over the same text"
     return paths, sizes, wl["uncomp_bytes"], what
 
@@ -622,9 +625,9 @@ def run_c5(ctx, dist: "Dist", n_entries, steps, warmup, e2e_steps, sampler=None,
     algo = m * size + total
     achieved = algo / (ms / steps / 1e3) / GB
     return {
-        "metric": metric_name("c5" if method == 8 else "c5z"), "value": tot_in * steps / (ms_max / 1e3) / GB, "unit": "GB/s", "ms_per_step": ms_max / steps,
+        "metric": metric_name("c5" if method == 8 else "c5f" if method == 0x108 else "c5z"), "value": tot_in * steps / (ms_max / 1e3) / GB, "unit": "GB/s", "ms_per_step": ms_max / steps,
         "run": {"entries_this_rank": m, "compressed_bytes": int(tot_out), "ratio": tot_in / max(tot_out, 1.0), "reference_ratio_same_level": 4.36,
-                "zlib6_ratio": 9.0, "verified": {("zlib_streams_ok" if method == 8 else "libzstd_frames_ok"): n_ok, "compiled_reference_streams_ok": ref_n if ref_ok is True else ref_ok, "of": m}},
+                "zlib6_ratio": 9.0, "verified": {("zlib_streams_ok" if method != 93 else "libzstd_frames_ok"): n_ok, "compiled_reference_streams_ok": ref_n if ref_ok is True else ref_ok, "of": m}},
         "roofline": {"bound": "hbm", "kernel": "k_deflate_chunks%s (+crc, scan, gather)" % ("" if method == 8 else " -> zse_emit_block"), "achieved": achieved, "peak": peak, "unit": "GB/s",
                      "frac": achieved / peak, "traffic": None, "peak_source": peak_src, "algorithmic_bytes": int(algo)},
         "e2e": {"value": tot_in * e2e_steps / e2e_max / GB, "unit": "GB/s", "h2d_bytes_per_step": int(img.nbytes),
@@ -844,8 +847,8 @@ def main():
     sampler.start()
     n = args.entries or DEFAULT_ENTRIES[args.workload]
     e2e_steps = args.e2e_steps or max(3, min(args.steps, 5))
-    if args.workload in ("c5", "c5z"):
-        res = run_c5(ctx, dist, args.entries, args.steps, args.warmup, e2e_steps, sampler, 8 if args.workload == "c5" else 93)
+    if args.workload in C5_METHOD:
+        res = run_c5(ctx, dist, args.entries, args.steps, args.warmup, e2e_steps, sampler, C5_METHOD[args.workload])
     else:
         res = run_extract(ctx, dist, args.workload, args.entries, args.steps, args.warmup, e2e_steps, args.scaling, sampler)
     clocks = sampler.summary()
@@ -866,9 +869,9 @@ def main():
         if not args.no_secondary and args.workload == "c3" and args.entries is None:
             # the other BASELINE configurations, same process, fewer steps: nothing the headline change would hide
             sec = {}
-            for w in ("c1", "c2", "c4", "c4z", "c5", "c5z"):
+            for w in ("c1", "c2", "c4", "c4z", "c5", "c5f", "c5z"):
                 try:
-                    r = (run_c5(ctx, dist, None, 3, 3, 1, None, 8 if w == "c5" else 93) if w in ("c5", "c5z") else run_extract(ctx, dist, w, None, 5, 3, 2))
+                    r = (run_c5(ctx, dist, None, 3, 3, 1, None, C5_METHOD[w]) if w in C5_METHOD else run_extract(ctx, dist, w, None, 5, 3, 2))
                     sec[w] = {"workload": WORKLOADS[w], "metric": r["metric"], "value": r["value"], "unit": "GB/s", "ms_per_step": r["ms_per_step"],
                               "roofline_frac": r["roofline"]["frac"], "roofline_kernel": r["roofline"]["kernel"], "e2e": r["e2e"]["value"],
                               "run": r["run"]}

@@ -67,6 +67,9 @@ extern "C" {
 #define OTZ_M_STORE 0
 #define OTZ_M_DEFLATE 8
 #define OTZ_M_ZSTD 93
+/* write path only: or-ed into method[i], compression level 1 ("fastest": one match candidate per position instead of the
+ * eight-way search at the start of every token; about 3x the speed at 0.85x the ratio on text) */
+#define OTZ_M_FAST 0x100
 
 /* One row of the device-side entry table (32 bytes). */
 typedef struct otz_entry {

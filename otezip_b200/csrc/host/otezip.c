@@ -62,6 +62,7 @@ struct otz_pending {              /* a queued source (write path) */
 	uint64_t len;
 	int owned;                    /* free(buf) after the archive is written */
 	int dirty;                    /* has bytes that zip_close must write (every new entry; a replaced existing one) */
+	int fast;                     /* zip_set_file_compression asked for level 1-3 (libzip: 1 = fastest) */
 };
 
 static int index_enabled(void) {
@@ -1188,7 +1189,6 @@ zip_int64_t zip_add(zip_t *za, const char *name, zip_source_t *src) {
 
 /* otezip.c:1186-1237 — the method now really applies, because nothing has been compressed yet */
 int zip_set_file_compression(zip_t *za, zip_uint64_t index, zip_int32_t comp, zip_uint32_t comp_flags) {
-	(void)comp_flags;
 	struct otz_archive *a = priv (za);
 	if (!is_valid (za) || !a || index >= za->n_entries || za->mode != 1) {
 		return -1;
@@ -1200,6 +1200,11 @@ int zip_set_file_compression(zip_t *za, zip_uint64_t index, zip_int32_t comp, zi
 		return -1; /* already on disk: relabelling would corrupt it (the reference's F4 bug) */
 	}
 	za->entries[index].method = (uint16_t)comp;
+	/* comp_flags is libzip's compression level (0 = default, 1 = fastest .. 9; the reference ignores it, otezip.c:1186):
+	 * 1-3 select the compressor's single-candidate parse (OTZ_M_FAST), everything else the default eight-way search */
+	if (a->pend) {
+		a->pend[index].fast = comp_flags >= 1 && comp_flags <= 3;
+	}
 	return 0;
 }
 
@@ -1385,6 +1390,9 @@ static int finalize_archive(struct otz_archive *a) {
 			/* method 93: the reference's writer cannot produce a stream its reader accepts and always falls
 			 * back to STORE (zstd.inc.c:269, otezip.c:894-899) — same result here */
 			method[k] = e->method == OTEZIP_METHOD_DEFLATE ? OTZ_M_DEFLATE : (e->method == OTEZIP_METHOD_ZSTD && zstd_frames ()) ? OTZ_M_ZSTD : OTZ_M_STORE;
+			if (a->pend[idx[k]].fast && method[k] != OTZ_M_STORE) {
+				method[k] |= OTZ_M_FAST;
+			}
 			total += ((uint64_t)in_len[k] + 15) & ~15ULL;
 		}
 		void *pin = NULL, *pout = NULL;

@@ -28,7 +28,9 @@
 
 #define DFL_CHUNK 65280u                      // <= 65535 so the stored fallback is one block
 #define DFL_OUT_STRIDE (DFL_CHUNK + 256u)     // per-chunk output slot (4-byte aligned)
-#define DFL_HASH_BITS 12
+#define DFL_HASH_BITS 12                      // 16-bit slots of the hash table: 8 KiB per chunk
+#define DFL_WAYS 8                            // slots per bucket: the last eight positions with the same hash
+#define DFL_BUCKET_BITS 9                     // 512 buckets (DFL_HASH_BITS - log2(DFL_WAYS))
 #define DFL_MIN_MATCH 4
 #define DFL_MAX_MATCH 258
 
@@ -36,7 +38,7 @@ struct OtzDflChunk {
 	uint64_t in_ofs;     // absolute offset of the chunk in the input buffer
 	uint32_t len;
 	uint32_t entry;
-	uint32_t last;       // bit 0: last chunk of its entry, bit 1: first chunk, bit 2: method 93 (Zstandard block instead of DEFLATE)
+	uint32_t last;       // bit 0: last chunk of its entry, bit 1: first chunk, bit 2: method 93 (Zstandard block instead of DEFLATE), bit 3: fast (first match pass only)
 	uint32_t pad;        // length of the whole entry (Frame_Content_Size of a Zstandard frame)
 };
 
@@ -63,6 +65,7 @@ struct __align__(16) DeflateSmem {
 	uint32_t hist_ll[288];
 	uint32_t hist_d[32];
 	uint32_t misc[4];   // [0] extra-bit total of the chunk, [1] final byte count
+	uint32_t best[32];  // phase 1, second pass: best (length << 16 | 32768 - distance) found for window position i
 };
 
 __device__ __forceinline__ uint32_t dfl_len_sym(uint32_t v /* len-3 */, uint32_t &xb, uint32_t &xv) {
@@ -254,6 +257,31 @@ __device__ __noinline__ void dfl_build_code(DeflateSmem &S, uint32_t *hist, int 
 	__syncwarp();
 }
 
+// length of the common prefix of the strings at chunk positions c < p, at most maxl: 16 bytes per trip
+__device__ __forceinline__ uint32_t dfl_extend(const uint32_t *__restrict__ w, uint32_t sh0, uint32_t c, uint32_t p, uint32_t maxl) {
+	uint32_t l = 0;
+	while (l < maxl) {
+		const uint32_t ca = sh0 + c + l, pa = sh0 + p + l;
+		const uint32_t ci = ca >> 2, cs = (ca & 3u) * 8u, pi = pa >> 2, ps = (pa & 3u) * 8u;
+		const uint32_t c0 = __ldg(w + ci), c1 = __ldg(w + ci + 1), c2 = __ldg(w + ci + 2), c3 = __ldg(w + ci + 3), c4 = __ldg(w + ci + 4);
+		const uint32_t p0 = __ldg(w + pi), p1 = __ldg(w + pi + 1), p2 = __ldg(w + pi + 2), p3 = __ldg(w + pi + 3), p4 = __ldg(w + pi + 4);
+		const uint32_t x0 = __funnelshift_r(c0, c1, cs) ^ __funnelshift_r(p0, p1, ps);
+		const uint32_t x1 = __funnelshift_r(c1, c2, cs) ^ __funnelshift_r(p1, p2, ps);
+		const uint32_t x2 = __funnelshift_r(c2, c3, cs) ^ __funnelshift_r(p2, p3, ps);
+		const uint32_t x3 = __funnelshift_r(c3, c4, cs) ^ __funnelshift_r(p3, p4, ps);
+		if (x0 | x1) {
+			l += x0 ? (__ffs(x0) - 1) >> 3 : 4 + ((__ffs(x1) - 1) >> 3);
+			break;
+		}
+		if (x2 | x3) {
+			l += x2 ? 8 + ((__ffs(x2) - 1) >> 3) : 12 + ((__ffs(x3) - 1) >> 3);
+			break;
+		}
+		l += 16;
+	}
+	return min(l, maxl);
+}
+
 // grid: persistent; one warp per chunk, chunks handed out in order.
 #define DFL_WARPS 3   // warps per CTA: seven CTAs (21 chunks) fit the shared memory of an SM
 // ZSTD: the job holds method-93 entries (their chunks become Zstandard blocks); a pure DEFLATE job runs the instantiation without that path
@@ -279,6 +307,7 @@ __global__ void __launch_bounds__(32 * DFL_WARPS) k_deflate_chunks(const uint8_t
 		}
 		const OtzDflChunk ck = chunks[ci];
 		const uint32_t n = ck.len;
+		const bool fast = (ck.last & 8u) != 0u;   // compression level 1: first pass only
 		const uint64_t ia = reinterpret_cast<uint64_t>(in + ck.in_ofs);
 		const uint32_t *w = reinterpret_cast<const uint32_t *>(ia & ~3ull);
 		const uint32_t sh0 = (uint32_t)(ia & 3ull);   // byte x of the chunk lives at word-array byte sh0 + x
@@ -302,57 +331,110 @@ __global__ void __launch_bounds__(32 * DFL_WARPS) k_deflate_chunks(const uint8_t
 			const uint32_t p = cur + lane;
 			uint32_t mlen = 0, mdist = 0;
 			const bool can = p + DFL_MIN_MATCH <= n;
-			uint32_t h = 0, cand = 0;
+			uint32_t h = 0, v = 0;
+			// default: the hash table is 512 buckets of the last DFL_WAYS earlier positions with this hash (position + 1, 0 = none;
+			// most recent in the low half of .x).  Fast entries: 4,096 single slots under a 12-bit hash.
+			uint4 bk = make_uint4(0u, 0u, 0u, 0u);
 			if (can) {
-				const uint32_t v = dfl_word(w, sh0 + p);
-				h = (v * 2654435761u) >> (32 - DFL_HASH_BITS);
-				cand = S.u.ht[h];   // position + 1 of the most recent earlier occurrence, 0 = none
+				v = dfl_word(w, sh0 + p);
+				if (fast) {
+					h = (v * 2654435761u) >> (32 - DFL_HASH_BITS);
+					bk.x = S.u.ht[h];
+				} else {
+					h = (v * 2654435761u) >> (32 - DFL_BUCKET_BITS);
+					bk = *reinterpret_cast<const uint4 *>(&S.u.ht[DFL_WAYS * h]);
+				}
 			}
-			// same-hash lanes: the highest lane (latest position) records itself, deterministically
+			// same-hash lanes: the highest lane (latest position) records itself, deterministically; a bucket moves up by one way
 			const uint32_t same = __match_any_sync(0xFFFFFFFFu, can ? h : 0xFFFFFFFFu);
 			if (can && lane == 31 - __clz(same)) {
-				S.u.ht[h] = (uint16_t)(p + 1);
-			}
-			if (can && cand && p - (cand - 1) <= 32768u) {   // RFC 1951 window
-				const uint32_t c = cand - 1;
-				const uint32_t maxl = min((uint32_t)DFL_MAX_MATCH, n - p);
-				uint32_t l = 0;
-				// 16 bytes per trip: the ten word loads of a trip are in flight together, a trip costs one round trip to
-				// L1 / L2 (the bytes read beyond maxl lie inside the padded input buffer and are cut off below)
-				while (l < maxl) {
-					const uint32_t ca = sh0 + c + l, pa = sh0 + p + l;
-					const uint32_t ci = ca >> 2, cs = (ca & 3u) * 8u, pi = pa >> 2, ps = (pa & 3u) * 8u;
-					const uint32_t c0 = __ldg(w + ci), c1 = __ldg(w + ci + 1), c2 = __ldg(w + ci + 2), c3 = __ldg(w + ci + 3), c4 = __ldg(w + ci + 4);
-					const uint32_t p0 = __ldg(w + pi), p1 = __ldg(w + pi + 1), p2 = __ldg(w + pi + 2), p3 = __ldg(w + pi + 3), p4 = __ldg(w + pi + 4);
-					const uint32_t x0 = __funnelshift_r(c0, c1, cs) ^ __funnelshift_r(p0, p1, ps);
-					const uint32_t x1 = __funnelshift_r(c1, c2, cs) ^ __funnelshift_r(p1, p2, ps);
-					const uint32_t x2 = __funnelshift_r(c2, c3, cs) ^ __funnelshift_r(p2, p3, ps);
-					const uint32_t x3 = __funnelshift_r(c3, c4, cs) ^ __funnelshift_r(p3, p4, ps);
-					if (x0 | x1) {
-						l += x0 ? (__ffs(x0) - 1) >> 3 : 4 + ((__ffs(x1) - 1) >> 3);
-						break;
-					}
-					if (x2 | x3) {
-						l += x2 ? 8 + ((__ffs(x2) - 1) >> 3) : 12 + ((__ffs(x3) - 1) >> 3);
-						break;
-					}
-					l += 16;
+				if (fast) {
+					S.u.ht[h] = (uint16_t)(p + 1u);
+				} else {
+					*reinterpret_cast<uint4 *>(&S.u.ht[DFL_WAYS * h]) =
+						make_uint4((bk.x << 16) | (p + 1u), (bk.y << 16) | (bk.x >> 16), (bk.z << 16) | (bk.y >> 16), (bk.w << 16) | (bk.z >> 16));
 				}
-				l = min(l, maxl);
-				if (l >= DFL_MIN_MATCH) {
-					mlen = l;
-					mdist = p - c;
+			}
+			// FIRST PASS: the most recent occurrence, for every position (16 bytes per trip: the ten word loads of a trip are in
+			// flight together, a trip costs one round trip to L1 / L2; the bytes read beyond maxl lie inside the padded input
+			// buffer and are cut off below)
+			const uint32_t maxl = can ? min((uint32_t)DFL_MAX_MATCH, n - p) : 0u;
+			{
+				const uint32_t cand = bk.x & 0xFFFFu;
+				if (can && cand && p - (cand - 1u) <= 32768u) {   // RFC 1951 window
+					const uint32_t l = dfl_extend(w, sh0, cand - 1u, p, maxl);
+					if (l >= DFL_MIN_MATCH) {
+						mlen = l;
+						mdist = p - (cand - 1u);
+					}
+				}
+			}
+			// SECOND PASS (not for fast entries): the other seven ways, but only for the positions where the parse of the first
+			// pass starts a token — about a third of them; the rest lies inside a match and is skipped whatever its candidates
+			// are.  The (token, way) pairs are dealt to the 32 lanes, so a round of the extension loop works on 32 candidates
+			// whatever their owners; a candidate that cannot beat the owner's match is dropped after ONE 4-byte comparison (the
+			// bytes that would make it longer: zlib's scan_end test — a 9-bit hash sends many strangers into a bucket).
+			if (!fast) {
+				const uint32_t lim1 = min(32u, n - cur);
+				uint32_t i1 = 0, t1 = 0, spos = 0;
+				while (i1 < lim1) {
+					const uint32_t L = __shfl_sync(0xFFFFFFFFu, mlen, i1 & 31u);
+					const uint32_t Ln = (i1 + 1 < 32) ? __shfl_sync(0xFFFFFFFFu, mlen, (i1 + 1) & 31) : 0u;
+					const uint32_t Ln2 = (i1 + 2 < 32) ? __shfl_sync(0xFFFFFFFFu, mlen, (i1 + 2) & 31) : 0u;
+					if ((uint32_t)lane == t1) {
+						spos = i1;
+					}
+					t1++;
+					i1 += (L >= DFL_MIN_MATCH && Ln <= L && Ln2 <= L + 1u) ? L : 1u;
+				}
+				S.best[lane] = 0u;
+				__syncwarp();
+				const uint32_t npairs = (DFL_WAYS - 1) * t1;
+				for (uint32_t q0 = 0; q0 < npairs; q0 += 32) {
+					const uint32_t q = q0 + lane;
+					const bool act = q < npairs;
+					const uint32_t tt = act ? q / (DFL_WAYS - 1) : 0u, wy = 1u + q % (DFL_WAYS - 1);
+					const uint32_t io = __shfl_sync(0xFFFFFFFFu, spos, tt);   // the owner: window position (= lane) of token tt
+					const uint32_t ox = __shfl_sync(0xFFFFFFFFu, bk.x, io), oy = __shfl_sync(0xFFFFFFFFu, bk.y, io);
+					const uint32_t oz = __shfl_sync(0xFFFFFFFFu, bk.z, io), ow = __shfl_sync(0xFFFFFFFFu, bk.w, io);
+					const uint32_t om = __shfl_sync(0xFFFFFFFFu, mlen, io), ov = __shfl_sync(0xFFFFFFFFu, v, io);
+					const uint32_t word = wy < 2 ? ox : wy < 4 ? oy : wy < 6 ? oz : ow;
+					const uint32_t cand = (wy & 1u) ? word >> 16 : word & 0xFFFFu;
+					const uint32_t po = cur + io;
+					const uint32_t omax = po + DFL_MIN_MATCH <= n ? min((uint32_t)DFL_MAX_MATCH, n - po) : 0u;
+					bool go = act && cand && po - (cand - 1u) <= 32768u && om < omax;
+					const uint32_t c = cand - 1u;
+					if (go) {
+						// bytes [t, t + 4) of both strings with t = max(om - 3, 0): equal for every candidate that matches om + 1 bytes
+						const uint32_t t = om >= DFL_MIN_MATCH ? om - 3u : 0u;
+						go = dfl_word(w, sh0 + c + t) == (t ? dfl_word(w, sh0 + po + t) : ov);
+					}
+					if (__any_sync(0xFFFFFFFFu, go)) {
+						if (go) {
+							const uint32_t l = dfl_extend(w, sh0, c, po, omax);
+							if (l >= DFL_MIN_MATCH && l > om) {
+								atomicMax(&S.best[io], (l << 16) | (32768u - (po - c)));   // (equal lengths: the nearer one)
+							}
+						}
+					}
+				}
+				__syncwarp();
+				const uint32_t bb = S.best[lane];
+				if ((bb >> 16) > mlen) {
+					mlen = bb >> 16;
+					mdist = 32768u - (bb & 0xFFFFu);
 				}
 			}
 			__syncwarp();
-			// greedy parse of the 32 positions with one-step lazy evaluation
+			// greedy parse of the 32 positions with two-step lazy evaluation
 			uint32_t i = 0, t = 0, mytok = 0;
 			const uint32_t lim = min(32u, n - cur);
 			while (i < lim) {
 				uint32_t L = __shfl_sync(0xFFFFFFFFu, mlen, i);
 				const uint32_t Ln = (i + 1 < 32) ? __shfl_sync(0xFFFFFFFFu, mlen, (i + 1) & 31) : 0u;
+				const uint32_t Ln2 = (i + 2 < 32) ? __shfl_sync(0xFFFFFFFFu, mlen, (i + 2) & 31) : 0u;
 				uint32_t tokv;
-				if (L >= DFL_MIN_MATCH && Ln <= L) {
+				if (L >= DFL_MIN_MATCH && Ln <= L && Ln2 <= L + 1u) {   // (a literal or two are worth a clearly longer match behind them)
 					const uint32_t D = __shfl_sync(0xFFFFFFFFu, mdist, i);
 					tokv = 0x80000000u | ((D - 1) << 8) | (L - 3);
 					i += L;

@@ -1254,7 +1254,10 @@ extern "C" int otz_extract_host_ex(otz_ctx *c, const uint8_t *archive, uint64_t 
 			cur.o_hi = std::max(cur.o_hi, ohi);
 			cur.n++;
 			bytes += (uint64_t)ents[i].uncomp_size + ents[i].comp_size;
-			if (bytes >= target || i + 1 == n) {
+			// (ramp: the first two sub-batches are a quarter and a half of the rest, so that the D2H stream — the bound of the
+			// call — starts after a quarter of a sub-batch's H2D + kernels instead of a whole one)
+			const uint64_t tgt = subs.size() == 0 ? target / 4 : subs.size() == 1 ? target / 2 : target;
+			if (bytes >= tgt || i + 1 == n) {
 				// (ranges are 64-byte aligned: neighbours may share their boundary block, which then is copied twice with the same bytes —
 				// only real overlap, payloads out of index order, turns the pipeline off)
 				if (cur.a_lo + 64 < prev_a_hi || (cur.o_hi > cur.o_lo && cur.o_lo < prev_o_hi)) {
@@ -1648,7 +1651,9 @@ extern "C" int otz_deflate_plan(otz_ctx *c, const uint64_t *in_ofs, const uint32
 	std::vector<OtzCrcChunk> cchunks;
 	uint64_t total = 0;
 	for (uint32_t i = 0; i < n; i++) {
-		if (method[i] != OTZ_M_STORE && method[i] != OTZ_M_DEFLATE && method[i] != OTZ_M_ZSTD) {
+		const uint16_t m_i = method[i] & (uint16_t)~OTZ_M_FAST;
+		const uint32_t fast_i = (method[i] & OTZ_M_FAST) ? 8u : 0u;
+		if (m_i != OTZ_M_STORE && m_i != OTZ_M_DEFLATE && m_i != OTZ_M_ZSTD) {
 			delete j;
 			snprintf(g_err, sizeof(g_err), "otz_deflate_plan: method %u is not on the GPU write path", method[i]);
 			return OTZ_ERR_ARG;
@@ -1656,7 +1661,7 @@ extern "C" int otz_deflate_plan(otz_ctx *c, const uint64_t *in_ofs, const uint32
 		OtzDflEntry &e = ents[i];
 		e.in_ofs = in_ofs[i];
 		e.len = in_len[i];
-		e.method_in = method[i];
+		e.method_in = m_i;
 		e.pad = 0;
 		e.first_chunk = (uint32_t)chunks.size();
 		const uint32_t nc = (in_len[i] + DFL_CHUNK - 1) / DFL_CHUNK;
@@ -1666,9 +1671,9 @@ extern "C" int otz_deflate_plan(otz_ctx *c, const uint64_t *in_ofs, const uint32
 			ck.in_ofs = in_ofs[i] + (uint64_t)k * DFL_CHUNK;
 			ck.len = std::min<uint32_t>(DFL_CHUNK, in_len[i] - k * DFL_CHUNK);
 			ck.entry = i;
-			ck.last = (k + 1 == nc ? 1u : 0u) | (k == 0 ? 2u : 0u) | (method[i] == OTZ_M_ZSTD ? 4u : 0u);
+			ck.last = (k + 1 == nc ? 1u : 0u) | (k == 0 ? 2u : 0u) | (m_i == OTZ_M_ZSTD ? 4u : 0u) | fast_i;
 			ck.pad = in_len[i];
-			j->has_zstd = j->has_zstd || method[i] == OTZ_M_ZSTD;
+			j->has_zstd = j->has_zstd || m_i == OTZ_M_ZSTD;
 			chunks.push_back(ck);
 		}
 		otz_entry &ce = cents[i];

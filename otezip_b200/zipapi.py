@@ -94,7 +94,7 @@ class ZipApi:
         return err.value, names, datas
 
     def write_archive(self, path: str, files, method: int | None = ZIP_CM_DEFLATE, use_default_method: bool = False):
-        """files: list of (name, bytes[, method]).  Per-file method via zip_set_file_compression after
+        """files: list of (name, bytes[, method[, level]]).  Per-file method (and libzip compression level) via zip_set_file_compression after
         zip_file_add (README.md:33-55 idiom) or via za->default_method (what main.c:188-191 does)."""
         libc = C.CDLL(None)
         libc.malloc.restype = C.c_void_p
@@ -113,5 +113,5 @@ class ZipApi:
             idx = self.L.zip_file_add(za, name.encode(), src, 0)
             assert idx >= 0
             if not use_default_method and m is not None:
-                assert self.L.zip_set_file_compression(za, idx, m, 0) == 0
+                assert self.L.zip_set_file_compression(za, idx, m, f[3] if len(f) > 3 else 0) == 0
         return self.L.zip_close(za)
