@@ -175,6 +175,11 @@ struct ZsBackW {
 				k = nk;
 				w0 = fix0(wm, k - 2);
 				wm = raw(k - 3);   // not needed before the next step down
+				if (k >= 19) {
+					// the stream is read backwards at ~30 bits per sequence: ask for the sector two below the one in use now, a
+					// dozen sequences before its first word is needed (a miss to HBM costs more than a sequence)
+					asm volatile("prefetch.global.L1 [%0];" ::"l"(w + (k - 19)));
+				}
 			} else {
 				reload();
 			}

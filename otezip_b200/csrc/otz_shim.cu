@@ -1024,9 +1024,10 @@ extern "C" int otz_extract_run(otz_ctx *c, otz_plan *p, const uint8_t *d_archive
 				CK(cudaEventRecord(zev[1], s));
 			}
 			// sequences: one CTA of ZS_SEQ_WARPS warps per SM, as many lanes per warp as the batch needs (their tables are the shared memory)
-			const uint32_t zlpw = std::max(1u, std::min((uint32_t)ZS_SEQ_LPW_MAX, (p->n_zstd + c->sm_count * ZS_SEQ_WARPS - 1) / (c->sm_count * ZS_SEQ_WARPS)));
-			const uint32_t sgrid = std::max(1u, std::min((uint32_t)c->sm_count, (p->n_zstd + zlpw * ZS_SEQ_WARPS - 1) / (zlpw * ZS_SEQ_WARPS)));
-			k_zstd_seq<<<sgrid, 32 * ZS_SEQ_WARPS, ZS_SEQ_WARPS * zlpw * ZS_SEQ_TAB_BYTES, s>>>(d_archive, p->d_ents, p->d_est, p->d_status, p->d_zstd_list,
+			const uint32_t zw = ZS_SEQ_WARPS;
+			const uint32_t zlpw = std::max(1u, std::min((uint32_t)ZS_SEQ_LPW_MAX, (p->n_zstd + c->sm_count * zw - 1) / (c->sm_count * zw)));
+			const uint32_t sgrid = std::max(1u, std::min((uint32_t)c->sm_count, (p->n_zstd + zlpw * zw - 1) / (zlpw * zw)));
+			k_zstd_seq<<<sgrid, 32 * zw, zw * zlpw * ZS_SEQ_TAB_BYTES, s>>>(d_archive, p->d_ents, p->d_est, p->d_status, p->d_zstd_list,
 				p->n_zstd, c->d_ztok_cache, p->d_ztok_ofs, p->d_ztokres, litres, p->d_counter + 34, zlpw);
 			c->launches++;
 			if (ztrace) {
