@@ -887,9 +887,13 @@ __global__ void __launch_bounds__(128) k_inflate_lz(uint8_t *__restrict__ out, c
 				// no overlap, neither range wraps around the ring — is two loads and two stores per lane without any index masking
 				// (source: ring or staging buffer, one index space); everything else takes the side exit
 				const uint32_t lane32 = lane + 32u;
+				// (the descriptor of record r + 1 is fetched while record r is executed: the shuffles are off the critical path)
+				uint32_t a_nx = __shfl_sync(0xFFFFFFFFu, cur.ma, 0), b_nx = __shfl_sync(0xFFFFFFFFu, cur.mb, 0);
 #pragma unroll 1
 				for (uint32_t r = 0; r < cur.ntake; r++) {
-					const uint32_t a = __shfl_sync(0xFFFFFFFFu, cur.ma, r), bsrc = __shfl_sync(0xFFFFFFFFu, cur.mb, r);
+					const uint32_t a = a_nx, bsrc = b_nx;
+					a_nx = __shfl_sync(0xFFFFFFFFu, cur.ma, (r + 1u) & 31u);
+					b_nx = __shfl_sync(0xFFFFFFFFu, cur.mb, (r + 1u) & 31u);
 					if (a & 0x88000000u) {
 						__syncwarp();   // earlier ring stores of this batch are visible to the loads below (side exits: always)
 					}
