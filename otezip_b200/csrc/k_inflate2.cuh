@@ -892,8 +892,8 @@ __global__ void __launch_bounds__(128) k_inflate_lz(uint8_t *__restrict__ out, c
 #pragma unroll 1
 				for (uint32_t r = 0; r < cur.ntake; r++) {
 					const uint32_t a = a_nx, bsrc = b_nx;
-					a_nx = __shfl_sync(0xFFFFFFFFu, cur.ma, (r + 1u) & 31u);
-					b_nx = __shfl_sync(0xFFFFFFFFu, cur.mb, (r + 1u) & 31u);
+					a_nx = __shfl_sync(0xFFFFFFFFu, cur.ma, r + 1u);
+					b_nx = __shfl_sync(0xFFFFFFFFu, cur.mb, r + 1u);
 					if (a & 0x88000000u) {
 						__syncwarp();   // earlier ring stores of this batch are visible to the loads below (side exits: always)
 					}

@@ -8,14 +8,8 @@
 // reference rejects"), so the default reference-compatible policy still matches the reference bit for bit.
 // Parity for this kernel is pinned against libzstd 1.5.5 (tests/test_gpu_zstd.py), not against the reference.
 //
-// Two decoders live here and in k_zstd_tok.cuh.
-//   * k_zstd_lit + k_zstd_seq + k_inflate_lz<W, true> (default; k_zstd_tok.cuh): the literal sections and the sequence
-//     sections of all entries are decoded by two kernels that walk the same frame / block structure, and the LZ executor of
-//     the inflate path (k_inflate2.cuh) writes the bytes.
-//   * k_zstd (OTZ_ZSTD_MODE=legacy, or when the token scratch cannot be allocated): one warp per entry; lane 0 parses
-//     headers, builds the tables and runs the three interleaved FSE states, lanes 0..3 decode the 4 Huffman literal
-//     streams into a per-warp HBM scratch, all lanes execute batches of 32 sequences straight in HBM.
-// Both use the word-based backward bit reader ZsBackW (one 64-bit window per sequence / per five Huffman symbols).
+// This file holds the shared pieces — bit readers, FSE / Huffman table builders, the Huffman stream decoder; the kernels
+// (k_zstd_lit + k_zstd_seq, whose tokens k_inflate_lz<W, true> executes) are in k_zstd_tok.cuh.
 #pragma once
 #include "otz_common.cuh"
 #include "k_copy.cuh"
@@ -26,22 +20,6 @@
 #define ZS_LL_LOG_MAX 9
 #define ZS_ML_LOG_MAX 9
 #define ZS_OF_LOG_MAX 8
-
-struct __align__(16) ZstdSmem {
-	uint16_t huf[1 << ZS_HUF_LOG_MAX];   // (symbol << 8) | nbits
-	uint32_t ll[1 << ZS_LL_LOG_MAX];     // symbol | nbits << 8 | new-state base << 16
-	uint32_t ml[1 << ZS_ML_LOG_MAX];
-	uint32_t of[1 << ZS_OF_LOG_MAX];
-	uint32_t seq_ll[32], seq_ml[32], seq_of[32];
-	uint32_t huf_log, ll_log, ml_log, of_log;
-	uint32_t have_huf, have_ll, have_ml, have_of;
-	int32_t err;
-	uint32_t n_batch;
-	uint32_t lit_sizes[4];   // regenerated sizes / stream byte offsets for the 4-stream literal decode
-	uint32_t lit_ofs[5];
-	uint32_t huf_used;       // bytes taken by the Huffman tree description
-	uint32_t seq_start;      // offset of the sequence bitstream inside the sequences section
-};
 
 __constant__ int16_t c_zs_ll_default[36] = { 4, 3, 2, 2, 2, 2, 2, 2, 2, 2, 2, 2, 2, 1, 1, 1, 2, 2, 2, 2, 2, 2, 2, 2, 2, 3, 2, 1, 1, 1, 1, 1, -1, -1, -1, -1 };
 __constant__ int16_t c_zs_ml_default[53] = { 1, 4, 3, 2, 2, 2, 2, 2, 2, 1, 1, 1, 1, 1, 1, 1, 1, 1, 1, 1, 1, 1, 1, 1, 1, 1, 1, 1, 1, 1, 1, 1, 1, 1, 1, 1, 1, 1, 1, 1, 1, 1, 1, 1, 1, 1, -1, -1, -1, -1, -1, -1, -1 };
@@ -335,18 +313,30 @@ __device__ uint32_t zs_build_huf(uint16_t *tbl, uint8_t *w, uint32_t n) {
 	}
 	w[n] = (uint8_t)(32 - __clz(rest));
 	n++;
-	uint32_t pos = 0;
-	for (uint32_t wt = 1; wt <= log; wt++) {
-		for (uint32_t s = 0; s < n; s++) {
-			if (w[s] == wt) {
-				const uint32_t cnt = 1u << (wt - 1), nb = log + 1 - wt;
-				for (uint32_t k = 0; k < cnt; k++) {
-					tbl[pos++] = (uint16_t)((s << 8) | nb);
-				}
+	// the table holds the symbols by ascending weight, symbols of one weight in ascending order, 2^(weight - 1) entries each:
+	// first entry of every weight class, then ONE pass over the symbols (instead of one per weight)
+	uint32_t start[ZS_HUF_LOG_MAX + 2];
+	for (uint32_t wt = 0; wt <= ZS_HUF_LOG_MAX + 1; wt++) {
+		start[wt] = 0;
+	}
+	for (uint32_t i = 0; i < n; i++) {
+		start[w[i] + 1u] += w[i] ? (1u << (w[i] - 1)) : 0u;   // (weight 0: no entries)
+	}
+	start[1] = 0;
+	for (uint32_t wt = 2; wt <= ZS_HUF_LOG_MAX + 1; wt++) {
+		start[wt] += start[wt - 1];
+	}
+	for (uint32_t i = 0; i < n; i++) {
+		const uint32_t wt = w[i];
+		if (wt) {
+			const uint32_t cnt = 1u << (wt - 1), e = (i << 8) | (log + 1 - wt), pos = start[wt];
+			start[wt] = pos + cnt;
+			for (uint32_t k = 0; k < cnt; k++) {
+				tbl[pos + k] = (uint16_t)e;
 			}
 		}
 	}
-	return pos == (1u << log) ? log : 0;
+	return log;   // (the weights sum to 2^log by construction of the last one)
 }
 
 // Huffman tree description (RFC 8878 4.2.1); returns bytes consumed or 0
@@ -484,537 +474,4 @@ __device__ int zs_seq_table(uint32_t mode, const uint8_t *p, uint32_t n, E *tbl,
 		return (int)used;
 	}
 	return *have ? 0 : -1;   // repeat mode needs a previous table
-}
-
-// Decode all frames of one entry.  Whole warp; returns the status code.
-__device__ int32_t zstd_decode_entry(ZstdSmem &S, const uint8_t *__restrict__ in, uint32_t n, uint8_t *__restrict__ out, uint32_t cap,
-	uint8_t *__restrict__ lit /* ZS_BLOCK_MAX + 32 bytes of scratch */, uint32_t *produced) {
-	const int lane = threadIdx.x & 31;
-	uint32_t ip = 0, op = 0;
-	int32_t err = 0;
-	uint32_t n_frames = 0;
-	while (ip < n && !err) {
-		if (n - ip < 4) {
-			err = OTZ_ST_TRUNCATED;
-			break;
-		}
-		const uint32_t magic = ld_le32(in + ip);
-		if ((magic & 0xFFFFFFF0u) == 0x184D2A50u) {   // skippable frame
-			if (n - ip < 8 || n - ip - 8 < ld_le32(in + ip + 4)) {
-				err = OTZ_ST_TRUNCATED;
-				break;
-			}
-			ip += 8 + ld_le32(in + ip + 4);
-			continue;
-		}
-		if (magic != 0xFD2FB528u) {
-			err = OTZ_ST_DATA;
-			break;
-		}
-		ip += 4;
-		if (ip >= n) {
-			err = OTZ_ST_TRUNCATED;
-			break;
-		}
-		// ---- frame header (RFC 8878 3.1.1.1)
-		const uint32_t fhd = in[ip++];
-		const uint32_t fcs_flag = fhd >> 6, single = (fhd >> 5) & 1, has_cksum = (fhd >> 2) & 1, did_flag = fhd & 3;
-		if (fhd & 0x08) {
-			err = OTZ_ST_DATA;
-			break;
-		}
-		const uint32_t did_len = did_flag == 3 ? 4 : did_flag;
-		const uint32_t fcs_len = fcs_flag == 0 ? single : (fcs_flag == 1 ? 2 : fcs_flag == 2 ? 4 : 8);
-		if (n - ip < (single ? 0 : 1) + did_len + fcs_len) {
-			err = OTZ_ST_TRUNCATED;
-			break;
-		}
-		if (!single) {
-			ip++;   // window descriptor: the whole output is addressable here
-		}
-		uint32_t did = 0;
-		for (uint32_t i = 0; i < did_len; i++) {
-			did |= (uint32_t)in[ip++] << (8 * i);
-		}
-		if (did) {
-			err = OTZ_ST_DATA;   // dictionaries are not available to a ZIP entry
-			break;
-		}
-		uint64_t fcs = 0;
-		for (uint32_t i = 0; i < fcs_len; i++) {
-			fcs |= (uint64_t)in[ip++] << (8 * i);
-		}
-		if (fcs_len == 2) {
-			fcs += 256;
-		}
-		const uint32_t frame_start = op;
-		uint32_t rep1 = 1, rep2 = 4, rep3 = 8;
-		if (lane == 0) {
-			S.have_huf = S.have_ll = S.have_ml = S.have_of = 0;
-			S.err = 0;
-		}
-		__syncwarp();
-		// ---- blocks
-		for (;;) {
-			if (n - ip < 3) {
-				err = OTZ_ST_TRUNCATED;
-				break;
-			}
-			const uint32_t bh = in[ip] | (in[ip + 1] << 8) | (in[ip + 2] << 16);
-			ip += 3;
-			const uint32_t last = bh & 1, btype = (bh >> 1) & 3, bsz = bh >> 3;
-			if (btype == 3 || bsz > ZS_BLOCK_MAX) {
-				err = OTZ_ST_DATA;
-				break;
-			}
-			if (btype == 0) {   // raw
-				if (n - ip < bsz) {
-					err = OTZ_ST_TRUNCATED;
-					break;
-				}
-				if (cap - op < bsz) {
-					err = OTZ_ST_OVERFLOW;
-					break;
-				}
-				tile_copy<32>(out + op, in + ip, bsz, lane);
-				ip += bsz;
-				op += bsz;
-			} else if (btype == 1) {   // RLE
-				if (n - ip < 1) {
-					err = OTZ_ST_TRUNCATED;
-					break;
-				}
-				if (cap - op < bsz) {
-					err = OTZ_ST_OVERFLOW;
-					break;
-				}
-				const uint8_t b = in[ip++];
-				for (uint32_t i = lane; i < bsz; i += 32) {
-					out[op + i] = b;
-				}
-				op += bsz;
-			} else {   // compressed
-				if (n - ip < bsz || bsz < 2) {
-					err = n - ip < bsz ? OTZ_ST_TRUNCATED : OTZ_ST_DATA;
-					break;
-				}
-				const uint8_t *bp = in + ip;
-				ip += bsz;
-				// ---- literals section header
-				const uint32_t b0 = bp[0];
-				const uint32_t ltype = b0 & 3, sf = (b0 >> 2) & 3;
-				uint32_t regen, lcomp = 0, lhdr, nstreams = 1;
-				if (ltype < 2) {
-					if ((sf & 1) == 0) {
-						regen = b0 >> 3;
-						lhdr = 1;
-					} else if (sf == 1) {
-						regen = (b0 >> 4) | (bp[1] << 4);
-						lhdr = 2;
-					} else {
-						if (bsz < 3) {
-							err = OTZ_ST_DATA;
-							break;
-						}
-						regen = (b0 >> 4) | (bp[1] << 4) | (bp[2] << 12);
-						lhdr = 3;
-					}
-				} else {
-					if (bsz < 5) {
-						err = OTZ_ST_DATA;
-						break;
-					}
-					const uint64_t v = (uint64_t)ld_le32(bp) | ((uint64_t)bp[4] << 32);
-					if (sf <= 1) {
-						regen = (uint32_t)(v >> 4) & 0x3FF;
-						lcomp = (uint32_t)(v >> 14) & 0x3FF;
-						lhdr = 3;
-						nstreams = sf == 0 ? 1 : 4;
-					} else if (sf == 2) {
-						regen = (uint32_t)(v >> 4) & 0x3FFF;
-						lcomp = (uint32_t)(v >> 18) & 0x3FFF;
-						lhdr = 4;
-						nstreams = 4;
-					} else {
-						regen = (uint32_t)(v >> 4) & 0x3FFFF;
-						lcomp = (uint32_t)(v >> 22) & 0x3FFFF;
-						lhdr = 5;
-						nstreams = 4;
-					}
-				}
-				if (regen > ZS_BLOCK_MAX) {
-					err = OTZ_ST_DATA;
-					break;
-				}
-				uint32_t lsec;   // bytes of the whole literals section
-				const uint8_t *litp = lit;   // where the literals of this block are
-				if (ltype == 0) {
-					lsec = lhdr + regen;
-					if (lsec > bsz) {
-						err = OTZ_ST_DATA;
-						break;
-					}
-					litp = bp + lhdr;   // raw literals are used in place
-				} else if (ltype == 1) {
-					lsec = lhdr + 1;
-					if (lsec > bsz) {
-						err = OTZ_ST_DATA;
-						break;
-					}
-					const uint8_t b = bp[lhdr];
-					for (uint32_t i = lane; i < regen; i += 32) {
-						lit[i] = b;
-					}
-				} else {
-					lsec = lhdr + lcomp;
-					if (lsec > bsz) {
-						err = OTZ_ST_DATA;
-						break;
-					}
-					const uint8_t *hp = bp + lhdr;
-					uint32_t hrem = lcomp;
-					if (lane == 0) {
-						if (ltype == 2) {
-							const uint32_t used = zs_read_huf(S, hp, hrem);
-							if (used == 0) {
-								S.err = OTZ_ST_DATA;
-							}
-							S.huf_used = used;
-						} else {
-							if (!S.have_huf) {
-								S.err = OTZ_ST_DATA;
-							}
-							S.huf_used = 0;
-						}
-					}
-					__syncwarp();
-					if (S.err) {
-						err = S.err;
-						break;
-					}
-					hp += S.huf_used;
-					hrem -= S.huf_used;
-					if (lane == 0) {
-						if (nstreams == 1) {
-							S.lit_ofs[0] = 0;
-							S.lit_ofs[1] = hrem;
-							S.lit_sizes[0] = regen;
-						} else if (hrem < 6) {
-							S.err = OTZ_ST_DATA;
-						} else {
-							const uint32_t s1 = ld_le16(hp), s2 = ld_le16(hp + 2), s3 = ld_le16(hp + 4);
-							if (6ull + s1 + s2 + s3 > hrem) {
-								S.err = OTZ_ST_DATA;
-							} else {
-								S.lit_ofs[0] = 6;
-								S.lit_ofs[1] = 6 + s1;
-								S.lit_ofs[2] = 6 + s1 + s2;
-								S.lit_ofs[3] = 6 + s1 + s2 + s3;
-								S.lit_ofs[4] = hrem;   // end of stream 4
-								const uint32_t q = (regen + 3) / 4;
-								S.lit_sizes[0] = S.lit_sizes[1] = S.lit_sizes[2] = q;
-								S.lit_sizes[3] = regen - 3 * q;
-								if (regen < 3 * q) {
-									S.err = OTZ_ST_DATA;
-								}
-							}
-						}
-					}
-					__syncwarp();
-					if (S.err) {
-						err = S.err;
-						break;
-					}
-					bool ok = true;
-					if ((uint32_t)lane < nstreams) {
-						const uint32_t so = S.lit_ofs[lane], se = nstreams == 1 ? S.lit_ofs[1] : S.lit_ofs[lane + 1];
-						uint32_t dsto = 0;
-						for (int k = 0; k < lane; k++) {
-							dsto += S.lit_sizes[k];
-						}
-						ok = zs_huf_stream(S, hp + so, se - so, lit + dsto, S.lit_sizes[lane]);
-					}
-					if (__any_sync(0xFFFFFFFFu, !ok)) {
-						err = OTZ_ST_DATA;
-						break;
-					}
-				}
-				__syncwarp();
-				// ---- sequences section
-				const uint8_t *sp = bp + lsec;
-				uint32_t srem = bsz - lsec;
-				if (srem < 1) {
-					err = OTZ_ST_DATA;
-					break;
-				}
-				uint32_t nseq = sp[0], shdr = 1;
-				if (nseq >= 128) {
-					if (nseq == 255) {
-						if (srem < 3) {
-							err = OTZ_ST_DATA;
-							break;
-						}
-						nseq = sp[1] + (sp[2] << 8) + 0x7F00;
-						shdr = 3;
-					} else {
-						if (srem < 2) {
-							err = OTZ_ST_DATA;
-							break;
-						}
-						nseq = ((nseq - 128) << 8) + sp[1];
-						shdr = 2;
-					}
-				}
-				uint32_t lit_pos = 0;
-				if (nseq) {
-					if (srem < shdr + 1) {
-						err = OTZ_ST_DATA;
-						break;
-					}
-					const uint32_t modes = sp[shdr];
-					if (modes & 3) {
-						err = OTZ_ST_DATA;
-						break;
-					}
-					if (lane == 0) {
-						uint32_t o = shdr + 1;
-						int r = zs_seq_table(modes >> 6, sp + o, srem - o, S.ll, &S.ll_log, &S.have_ll, c_zs_ll_default, 36, 6, 35, ZS_LL_LOG_MAX);
-						if (r >= 0) {
-							o += r;
-							r = zs_seq_table((modes >> 4) & 3, sp + o, srem - o, S.of, &S.of_log, &S.have_of, c_zs_of_default, 29, 5, 31, ZS_OF_LOG_MAX);
-						}
-						if (r >= 0) {
-							o += r;
-							r = zs_seq_table((modes >> 2) & 3, sp + o, srem - o, S.ml, &S.ml_log, &S.have_ml, c_zs_ml_default, 53, 6, 52, ZS_ML_LOG_MAX);
-						}
-						if (r >= 0) {
-							o += r;
-						}
-						if (r < 0 || o > srem) {
-							S.err = OTZ_ST_DATA;
-						}
-						S.seq_start = o;
-					}
-					__syncwarp();
-					if (S.err) {
-						err = S.err;
-						break;
-					}
-					const uint32_t so = S.seq_start;
-					// lane 0 owns the bitstream and the three states
-					ZsBackW b;
-					uint32_t st_ll = 0, st_of = 0, st_ml = 0;
-					if (lane == 0) {
-						if (!b.init(sp + so, srem - so)) {
-							S.err = OTZ_ST_DATA;
-						} else {
-							st_ll = b.read(S.ll_log);
-							st_of = b.read(S.of_log);
-							st_ml = b.read(S.ml_log);
-						}
-					}
-					__syncwarp();
-					if (S.err) {
-						err = S.err;
-						break;
-					}
-					for (uint32_t done = 0; done < nseq && !err;) {
-						const uint32_t nb = min(32u, nseq - done);
-						if (lane == 0) {
-							for (uint32_t k = 0; k < nb; k++) {
-								const uint32_t el = S.ll[st_ll], eo = S.of[st_of], em = S.ml[st_ml];
-								const uint32_t lc = el & 0xFF, oc = eo & 0xFF, mc = em & 0xFF;
-								if (lc > 35 || mc > 52 || oc > 31) {
-									S.err = OTZ_ST_DATA;
-									break;
-								}
-								// one window for the whole sequence: three extra-bit fields, then (unless it is the last
-								// sequence) the three state updates, in the RFC 8878 4.1.1 order
-								const bool last_seq = done + k + 1 >= nseq;
-								const uint32_t n_ml = c_zs_ml_bits[mc], n_ll = c_zs_ll_bits[lc];
-								const uint32_t u_ll = last_seq ? 0u : (el >> 8) & 0xFF, u_ml = last_seq ? 0u : (em >> 8) & 0xFF,
-								               u_of = last_seq ? 0u : (eo >> 8) & 0xFF;
-								uint64_t x = b.top64();
-								if (oc + n_ml + n_ll + u_ll + u_ml + u_of > 64u) {
-									// (offset codes of 30+ bits: take the offset field on its own; the rest is at most 58 bits)
-									const uint32_t f = zs_take(x, oc);
-									b.skip(oc);
-									const uint64_t y = b.top64();
-									b.skip(n_ml + n_ll + u_ll + u_ml + u_of);
-									uint64_t yy = y;
-									const uint32_t ofv_ = (1u << oc) + f;
-									const uint32_t mlv_ = c_zs_ml_base[mc] + zs_take(yy, n_ml);
-									const uint32_t llv_ = c_zs_ll_base[lc] + zs_take(yy, n_ll);
-									S.seq_ll[k] = llv_;
-									S.seq_ml[k] = mlv_;
-									S.seq_of[k] = ofv_;   // raw offset value; resolved below
-									if (!last_seq) {
-										st_ll = (el >> 16) + zs_take(yy, u_ll);
-										st_ml = (em >> 16) + zs_take(yy, u_ml);
-										st_of = (eo >> 16) + zs_take(yy, u_of);
-									}
-								} else {
-									b.skip(oc + n_ml + n_ll + u_ll + u_ml + u_of);
-									S.seq_of[k] = (1u << oc) + zs_take(x, oc);
-									S.seq_ml[k] = c_zs_ml_base[mc] + zs_take(x, n_ml);
-									S.seq_ll[k] = c_zs_ll_base[lc] + zs_take(x, n_ll);
-									if (!last_seq) {
-										st_ll = (el >> 16) + zs_take(x, u_ll);
-										st_ml = (em >> 16) + zs_take(x, u_ml);
-										st_of = (eo >> 16) + zs_take(x, u_of);
-									}
-								}
-								const uint32_t ofv = S.seq_of[k], mlv = S.seq_ml[k], llv = S.seq_ll[k];
-								uint32_t offset;
-								if (ofv > 3) {
-									offset = ofv - 3;
-									rep3 = rep2;
-									rep2 = rep1;
-									rep1 = offset;
-								} else {
-									const uint32_t idx = ofv + (llv == 0 ? 1 : 0);   // 1..4
-									if (idx == 1) {
-										offset = rep1;
-									} else {
-										offset = idx == 2 ? rep2 : idx == 3 ? rep3 : rep1 - 1;
-										if (offset == 0) {
-											S.err = OTZ_ST_DATA;
-											break;
-										}
-										if (idx != 2) {
-											rep3 = rep2;
-										}
-										rep2 = rep1;
-										rep1 = offset;
-									}
-								}
-								S.seq_of[k] = offset;
-								(void)mlv;
-								if (b.pos() < 0) {
-									S.err = OTZ_ST_DATA;
-									break;
-								}
-							}
-							if (done + nb == nseq && b.pos() != 0 && !S.err) {
-								S.err = OTZ_ST_DATA;   // the bitstream must be consumed exactly
-							}
-						}
-						__syncwarp();
-						if (S.err) {
-							err = S.err;
-							break;
-						}
-						for (uint32_t k = 0; k < nb; k++) {
-							const uint32_t llv = S.seq_ll[k], mlv = S.seq_ml[k], offset = S.seq_of[k];
-							if (llv > regen - lit_pos || (uint64_t)llv + mlv > (uint64_t)(cap - op)) {
-								err = llv > regen - lit_pos ? OTZ_ST_DATA : OTZ_ST_OVERFLOW;
-								break;
-							}
-							for (uint32_t i = lane; i < llv; i += 32) {
-								out[op + i] = litp[lit_pos + i];
-							}
-							op += llv;
-							lit_pos += llv;
-							if (offset > op - frame_start) {
-								err = OTZ_ST_DATA;
-								break;
-							}
-							__syncwarp();
-							const uint8_t *src = out + op - offset;
-							if (offset >= mlv) {
-								for (uint32_t i = lane; i < mlv; i += 32) {
-									out[op + i] = src[i];
-								}
-							} else {
-								uint32_t r = offset > (uint32_t)lane ? (uint32_t)lane : (uint32_t)lane % offset;
-								const uint32_t step = offset > 32u ? 32u : 32u % offset;
-								for (uint32_t i = lane; i < mlv; i += 32) {
-									out[op + i] = src[r];
-									r += step;
-									r = r >= offset ? r - offset : r;
-								}
-							}
-							op += mlv;
-							__syncwarp();
-						}
-						done += nb;
-					}
-					if (err) {
-						break;
-					}
-				}
-				// ---- literals after the last sequence
-				const uint32_t tail = regen - lit_pos;
-				if (cap - op < tail) {
-					err = OTZ_ST_OVERFLOW;
-					break;
-				}
-				for (uint32_t i = lane; i < tail; i += 32) {
-					out[op + i] = litp[lit_pos + i];
-				}
-				op += tail;
-				__syncwarp();
-			}
-			if (last) {
-				break;
-			}
-		}
-		if (err) {
-			break;
-		}
-		if (has_cksum) {
-			if (n - ip < 4) {
-				err = OTZ_ST_TRUNCATED;
-				break;
-			}
-			ip += 4;   // XXH64 low word: not verified here, the ZIP CRC-32 covers the entry
-		}
-		if (fcs_len && fcs != (uint64_t)(op - frame_start)) {
-			err = OTZ_ST_DATA;
-			break;
-		}
-		n_frames++;
-	}
-	*produced = op;
-	if (err) {
-		return err;
-	}
-	if (n_frames == 0) {
-		return OTZ_ST_DATA;
-	}
-	return op == cap ? OTZ_ST_OK : OTZ_ST_SIZE;
-}
-
-// grid: persistent; one warp per method-93 entry that k_zstdref could not read as a reference container.
-__global__ void __launch_bounds__(128) k_zstd(const uint8_t *__restrict__ archive, uint8_t *__restrict__ out, const otz_entry *__restrict__ ents,
-	const OtzEntryState *__restrict__ est, int32_t *__restrict__ status, const uint32_t *__restrict__ list, uint32_t n_list,
-	uint8_t *__restrict__ lit_scratch, uint32_t *__restrict__ work_counter) {
-	extern __shared__ __align__(16) uint8_t smem_raw[];
-	const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-	ZstdSmem &S = reinterpret_cast<ZstdSmem *>(smem_raw)[warp];
-	uint8_t *lit = lit_scratch + (uint64_t)(blockIdx.x * (blockDim.x >> 5) + warp) * (ZS_BLOCK_MAX + 64);
-	for (;;) {
-		uint32_t k = 0;
-		if (lane == 0) {
-			k = atomicAdd(work_counter, 1u);
-		}
-		k = __shfl_sync(0xFFFFFFFFu, k, 0);
-		if (k >= n_list) {
-			break;
-		}
-		const uint32_t ei = list[k];
-		if (status[ei] != OTZ_ST_PENDING) {
-			continue;   // resolved as a reference container (or failed earlier)
-		}
-		const otz_entry e = ents[ei];
-		uint32_t produced = 0;
-		int32_t st = zstd_decode_entry(S, archive + est[ei].data_ofs, e.comp_size, out + e.out_ofs, e.uncomp_size, lit, &produced);
-		if (st == OTZ_ST_OK) {
-			st |= OTZ_STF_REF_EOB;   // a valid stream that the reference rejects
-		}
-		if (lane == 0) {
-			status[ei] = st;
-		}
-		__syncwarp();
-	}
 }

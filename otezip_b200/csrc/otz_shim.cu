@@ -57,7 +57,6 @@ struct otz_ctx {
 	int lz_ring;        // OTZ_LZ_RING: ring bytes per warp of k_inflate_lz (4096 / 8192 / 16384)
 	uint32_t last_fallbacks;   // DEFLATE streams of the last collected run that phase A handed to k_inflate
 	int huge_legacy;        // OTZ_HUGE_MODE=legacy: huge DEFLATE entries on k_inflate<32,16384> instead of the segmented decode
-	int zstd_legacy;        // OTZ_ZSTD_MODE=legacy: warp-per-entry k_zstd instead of k_zstd_tok + k_inflate_lz
 	uint8_t *d_ztok_cache;  // grow-only token scratch of the two-phase Zstandard path
 	uint64_t ztok_cache_bytes;
 	uint8_t *d_tok_cache;   // grow-only token scratch of the two-phase inflate (literals + sequence records)
@@ -103,8 +102,6 @@ struct otz_plan {
 	uint64_t *d_ztok_ofs;      // two-phase Zstandard: token scratch offset of every method-93 list slot (+ end)
 	uint64_t ztok_bytes;
 	I2TokRes *d_ztokres;
-	uint8_t *d_zstd_lit;       // literal scratch of k_zstd, one slot per resident warp
-	uint32_t zstd_grid;
 	uint32_t *d_counter;
 	uint64_t out_bytes_needed;
 };
@@ -251,8 +248,6 @@ extern "C" int otz_ctx_create(int device, otz_ctx **out) {
 	c->seg_ring = t ? atoi(t) : 4096;
 	t = getenv("OTZ_SEG_SYM_LIMIT");
 	c->sym_limit = t ? strtoull(t, nullptr, 0) : ~0ull;
-	t = getenv("OTZ_ZSTD_MODE");
-	c->zstd_legacy = (t && !strcmp(t, "legacy")) ? 1 : 0;
 	t = getenv("OTZ_LZ_RING");
 	c->lz_ring = t ? atoi(t) : 4096;
 	*out = c;
@@ -455,7 +450,6 @@ extern "C" void otz_plan_destroy(otz_ctx *c, otz_plan *p) {
 	cudaFree(p->d_fb_list);
 	cudaFree(p->d_zstd_list);
 	cudaFree(p->d_zchunks);
-	cudaFree(p->d_zstd_lit);
 	cudaFree(p->d_ztok_ofs);
 	cudaFree(p->d_ztokres);
 	cudaFree(p->d_counter);
@@ -605,11 +599,6 @@ extern "C" int otz_plan_create(otz_ctx *c, const otz_entry *ents, uint32_t n, co
 			return rc ? rc : fail_cuda(cudaGetLastError(), "cudaMalloc(two-phase zstd lists)");
 		}
 		CK(cudaStreamSynchronize(c->stream));   // zofs dies here
-		p->zstd_grid = std::min<uint32_t>((uint32_t)c->sm_count * 5, (p->n_zstd + 3) / 4);   // 5 CTAs x 4 warps per SM (shared memory)
-		if (cudaMalloc(&p->d_zstd_lit, (size_t)p->zstd_grid * 4 * (ZS_BLOCK_MAX + 64)) != cudaSuccess) {
-			otz_plan_destroy(c, p);
-			return fail_cuda(cudaGetLastError(), "cudaMalloc(zstd literal scratch)");
-		}
 	}
 	CK(cudaMemsetAsync(p->d_counter, 0, 256, c->stream));
 	CK(cudaStreamSynchronize(c->stream));  // the host vectors die here
@@ -979,23 +968,19 @@ extern "C" int otz_extract_run(otz_ctx *c, otz_plan *p, const uint8_t *d_archive
 		k_zstdref<<<std::min((uint32_t)c->sm_count * 4, (p->n_zstd + 7) / 8), 256, 0, s>>>(d_archive, d_out, p->d_ents, p->d_est, p->d_status,
 			p->d_zstd_list, p->n_zstd);
 		c->launches++;
-		// entries that are not a reference container but carry the Zstandard magic: RFC 8878 frames.
-		// Two-phase (lane-per-entry tokenizer + the LZ executor of the inflate path) when the token scratch can be
-		// had and OTZ_ZSTD_MODE is not "legacy"; else the warp-per-entry decoder.
-		bool two_phase = !c->zstd_legacy;
-		if (two_phase && p->ztok_bytes + 64 > c->ztok_cache_bytes) {
+		// entries that are not a reference container but carry the Zstandard magic: RFC 8878 frames, decoded in two
+		// phases (literal / sequence tokenizers + the LZ executor of the inflate path) over the context's token scratch
+		if (p->ztok_bytes + 64 > c->ztok_cache_bytes) {
 			CK(cudaStreamSynchronize(c->stream));
 			cudaFree(c->d_ztok_cache);
 			c->d_ztok_cache = nullptr;
 			c->ztok_cache_bytes = 0;
-			if (cudaMalloc(&c->d_ztok_cache, p->ztok_bytes + 64) == cudaSuccess) {
-				c->ztok_cache_bytes = p->ztok_bytes + 64;
-			} else {
-				cudaGetLastError();
-				two_phase = false;
+			if (cudaMalloc(&c->d_ztok_cache, p->ztok_bytes + 64) != cudaSuccess) {
+				return fail_cuda(cudaGetLastError(), "cudaMalloc(Zstandard token scratch)");
 			}
+			c->ztok_cache_bytes = p->ztok_bytes + 64;
 		}
-		if (two_phase) {
+		{
 			static bool zattr2 = false;
 			const int zsmem2 = (int)(ZS_LIT_WARPS * 8 * sizeof(ZsLitSmem));
 			if (!zattr2) {
@@ -1051,16 +1036,6 @@ extern "C" int otz_extract_run(otz_ctx *c, otz_plan *p, const uint8_t *d_archive
 					cudaEventDestroy(zev[i]);
 				}
 			}
-		} else {
-			const size_t zsmem = 4 * sizeof(ZstdSmem);
-			static bool zattr = false;
-			if (!zattr) {
-				CK(cudaFuncSetAttribute(k_zstd, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)zsmem));
-				zattr = true;
-			}
-			k_zstd<<<p->zstd_grid, 128, zsmem, s>>>(d_archive, d_out, p->d_ents, p->d_est, p->d_status, p->d_zstd_list, p->n_zstd, p->d_zstd_lit,
-				p->d_counter + 32);
-			c->launches++;
 		}
 	}
 	if (p->n_inflate) {

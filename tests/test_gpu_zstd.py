@@ -1,4 +1,4 @@
-"""Real Zstandard (RFC 8878) frames in method-93 entries: k_zstd.cuh against libzstd 1.5.5.
+"""Real Zstandard (RFC 8878) frames in method-93 entries: k_zstd_tok.cuh (k_zstd_lit + k_zstd_seq + k_inflate_lz) against libzstd 1.5.5.
 Parity for this kernel is NOT pinned by the reference (which rejects such frames): the frames are
 made by libzstd and the decoded bytes must equal the source; the status carries the "reference rejects" flag so
 that the default reference-compatible policy still agrees with the reference."""
@@ -22,19 +22,9 @@ def zs():
         pytest.skip("libzstd.so.1 not present")
 
 
-@pytest.fixture(params=["twophase", "legacy"])
-def zctx(request):
-    """A context per Zstandard decoder: lane-per-entry tokenizer + k_inflate_lz (default) and the warp-per-entry k_zstd."""
-    import os
-    from otezip_b200 import Ctx
-    if request.param == "legacy":
-        os.environ["OTZ_ZSTD_MODE"] = "legacy"
-    try:
-        c = Ctx(0)
-    finally:
-        os.environ.pop("OTZ_ZSTD_MODE", None)
-    yield c
-    c.close()
+@pytest.fixture
+def zctx(ctx):
+    return ctx
 
 
 def sources():

@@ -49,8 +49,14 @@ C3S="python bench.py --workload c3 --entries 2000 --steps 1 --warmup 1 --no-cpu-
 full spec1 k_inflate_spec "$C1" 2
 full lz k_inflate_lz "$C1" 2
 full spec4 k_inflate_spec "$C3S" 2
-full par k_inflate_lz "$C3S" 4
-full translate k_seg_translate "$C3S" 1
+full par k_inflate_lz "$C3S" 8   # (per pass: segment walk / PAR of three size groups, then the regular streams: launch 8 = PAR of the largest streams, second pass)
+full translate k_seg_translate "$C3S" 3
+C4Z="python bench.py --workload c4z --steps 1 --warmup 1 --no-cpu-baseline --e2e-steps 0"
+C5="python bench.py --workload c5 --entries 2048 --steps 1 --warmup 1 --no-cpu-baseline --e2e-steps 0"
+full zseq k_zstd_seq "$C4Z" 1
+full zlit k_zstd_lit "$C4Z" 1
+full deflate k_deflate_chunks "$C5" 1
+OTZ_ZSTD_TRACE=1 $C4Z 2>&1 > /dev/null | grep "otz zstd" | head -3 > gpurun_out/${T}_zstd_trace.txt
 cuobjdump -sass otezip_b200/csrc/otz_shim.o 2>/dev/null | awk '/Function : .*k_seg_translate/{f=1} /Function : .*k_seg_window/{f=0} f' | grep -E "Function|UBLKCP|SYNCS|FENCE|LDS|STG|LDG" | head -60 > gpurun_out/${T}_sass_translate.txt
 cuobjdump -sass otezip_b200/csrc/otz_shim.o 2>/dev/null | awk '/Function : .*k_crc_chunks/{f=1} /Function : .*k_crc_finalize/{f=0} f' | grep -E "Function|LDG|SHF|LOP3|SHFL" | head -80 > gpurun_out/${T}_sass_crc.txt
 ls -la gpurun_out | grep ${T}_
