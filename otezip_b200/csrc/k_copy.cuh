@@ -210,7 +210,9 @@ __global__ void __launch_bounds__(256, 4) k_zstdref(const uint8_t *__restrict__ 
 			if (st != OTZ_ST_OK) {
 				// not a consistent reference container: if it carries the Zstandard magic, k_zstd_lit / k_zstd_seq try it as an
 				// RFC 8878 frame (the reference itself would reject it either way)
-				status[ei] = (n >= 4 && ld_le32(in) == 0xFD2FB528u) ? OTZ_ST_PENDING : st;
+				// (a frame, or a skippable frame in front of one: RFC 8878 3.1.2)
+				const uint32_t mg = n >= 4 ? ld_le32(in) : 0u;
+				status[ei] = (mg == 0xFD2FB528u || (mg & 0xFFFFFFF0u) == 0x184D2A50u) ? OTZ_ST_PENDING : st;
 			}
 		}
 	}

@@ -69,6 +69,50 @@ def test_zstd_frames_decode_bit_exact(zctx, zs, reflib):
         assert (g is None) == m.name.startswith("z") and (g is None or g == d)
 
 
+def test_zstd_frame_structure_variants(zctx, zs):
+    """What the walk shared by k_zstd_lit and k_zstd_seq (zs_walk) has to get through: several frames per entry, skippable
+    frames between them, frames with a content checksum, frames without Frame_Content_Size (window descriptor instead of
+    the single-segment flag), small windows, and entries made of raw / RLE blocks only."""
+    import struct
+    a, b, c = synth.jsonlog_text(200000, 21), synth.jsonlog_text(70000, 22), synth.random_bytes(3000, 23)
+    skip = struct.pack("<II", 0x184D2A53, 11) + b"hello world"
+    cases = {
+        "two_frames": (zs.compress(a, 3) + zs.compress(b, 9), a + b),
+        "skippable": (skip + zs.compress(a, 1) + skip + zs.compress(c, 3) + skip, a + c),
+        "checksum": (zs.compress_adv(a, 3, checksum=True), a),
+        "checksum_x2": (zs.compress_adv(a, 5, checksum=True) + zs.compress_adv(b, 1, checksum=True), a + b),
+        "no_fcs": (zs.compress_adv(a, 3, content_size=False), a),
+        "no_fcs_cksum_w17": (zs.compress_adv(a + b, 7, checksum=True, content_size=False, window_log=17), a + b),
+        "raw_blocks": (zs.compress(synth.random_bytes(300000, 24), 3), synth.random_bytes(300000, 24)),
+        "rle_blocks": (zs.compress(b"\x07" * 500000, 3), b"\x07" * 500000),
+        "rle_then_text": (zs.compress(b"z" * 140000 + a, 3), b"z" * 140000 + a),
+        "empty_then_text": (zs.compress(b"", 3) + zs.compress(b, 3), b),
+    }
+    ms, want = [], []
+    for name, (f, d) in cases.items():
+        assert zs.decompress(f, len(d)) == d or name in ("two_frames", "skippable", "checksum_x2", "empty_then_text")   # (ZSTD_decompress reads all frames; kept loose)
+        ms.append(synth.Member(name, 93, f, len(d), zlib.crc32(d) & 0xFFFFFFFF, raw=d))
+        want.append(d)
+    img = synth.build_zip(ms)
+    tab = parse_central(img)
+    out, crc, st = zctx.extract_host(img, tab, default_opts())
+    for i, (m, d) in enumerate(zip(ms, want)):
+        s = int(st[i])
+        assert (s & 0xFF) == 0 and not (s & native.STF_CRC_MISMATCH), (m.name, hex(s))
+        o = int(tab["out_ofs"][i])
+        assert bytes(out[o:o + len(d)]) == d, m.name
+        assert int(crc[i]) == m.crc32
+    # a frame cut inside its checksum, and a declared Frame_Content_Size that is wrong: never a clean success
+    bad = [zs.compress_adv(a, 3, checksum=True)[:-2], bytearray(zs.compress(b, 3))]
+    bad[1][5] ^= 0x10   # (byte 5 belongs to Frame_Content_Size in a single-segment frame of this size)
+    ms = [synth.Member("bad%d" % i, 93, bytes(f), len(d), zlib.crc32(d) & 0xFFFFFFFF) for i, (f, d) in enumerate(zip(bad, (a, b)))]
+    img = synth.build_zip(ms)
+    tab = parse_central(img)
+    out, crc, st = zctx.extract_host(img, tab, default_opts())
+    for i in range(2):
+        assert (int(st[i]) & 0xFF) != 0, (i, hex(int(st[i])))
+
+
 def test_corrupt_zstd_frames_are_rejected(zctx, zs):
     ctx = zctx
     d = synth.jsonlog_text(200000, 77)
