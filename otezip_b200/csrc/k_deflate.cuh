@@ -404,6 +404,7 @@ __global__ void __launch_bounds__(32 * DFL_WARPS) k_deflate_chunks(const uint8_t
 					const uint32_t omax = po + DFL_MIN_MATCH <= n ? min((uint32_t)DFL_MAX_MATCH, n - po) : 0u;
 					bool go = act && cand && po - (cand - 1u) <= 32768u && om < omax;
 					const uint32_t c = cand - 1u;
+					OTZ_CHK(!go || (io < 32u && c < po && po < n), OTZ_CK_DFL_PAIR);
 					if (go) {
 						// bytes [t, t + 4) of both strings with t = max(om - 3, 0): equal for every candidate that matches om + 1 bytes
 						const uint32_t t = om >= DFL_MIN_MATCH ? om - 3u : 0u;

@@ -403,6 +403,7 @@ __global__ void __launch_bounds__(32 * ZS_LIT_WARPS) k_zstd_lit(const uint8_t *_
 		if (blk) {
 			const uint8_t *hp = B.bp + B.lhdr;
 			uint32_t hrem = B.lcomp;
+			OTZ_CHK(T.nl + B.regen <= W.cap, OTZ_CK_ZS_LIT);
 			__syncwarp(gmask);
 			if (B.ltype == 2) {
 				const uint32_t used = zs_read_huf(S, hp, hrem);
@@ -489,6 +490,7 @@ __global__ void __launch_bounds__(32 * ZS_SEQ_WARPS, 1) k_zstd_seq(const uint8_t
 	ZsBlk B;
 	ZsBackW b;
 	uint32_t k = 0, ei = 0;
+	const uint8_t *rec_floor = nullptr;   // (bounds-check build: the records of the entry must stay above its literals)
 	bool busy = false, dry = lane >= lpw;
 	uint32_t rep1 = 1, rep2 = 4, rep3 = 8;
 	uint32_t ll_log = 0, of_log = 0, ml_log = 0, have_ll = 0, have_of = 0, have_ml = 0;
@@ -519,6 +521,7 @@ __global__ void __launch_bounds__(32 * ZS_SEQ_WARPS, 1) k_zstd_seq(const uint8_t
 				W.init(archive + est[ei].data_ofs, e.comp_size, e.uncomp_size);
 				T.seq_end = reinterpret_cast<uint2 *>(scratch + tok_ofs[k + 1]);
 				T.nl = T.nseq = T.run = 0;
+				rec_floor = scratch + tok_ofs[k];
 				busy = true;
 			}
 			if (zs_walk<ZS_PH_SEQ>(W, T, B, 0u, 1u)) {
@@ -635,6 +638,7 @@ __global__ void __launch_bounds__(32 * ZS_SEQ_WARPS, 1) k_zstd_seq(const uint8_t
 		while (__any_sync(0xFFFFFFFFu, on)) {
 			if (on) {
 				uint32_t lc, oc, mc, u_ll, u_of, u_ml, b_ll, b_of, b_ml;
+				OTZ_CHK(st_ll < (1u << ll_log) && st_of < (1u << of_log) && st_ml < (1u << ml_log), OTZ_CK_ZS_TABLE);
 				zs_fse16(t_ll[st_ll], ll_log, lc, u_ll, b_ll);
 				zs_fse16(t_of[st_of], of_log, oc, u_of, b_of);
 				zs_fse16(t_ml[st_ml], ml_log, mc, u_ml, b_ml);
@@ -684,6 +688,7 @@ __global__ void __launch_bounds__(32 * ZS_SEQ_WARPS, 1) k_zstd_seq(const uint8_t
 						lit_pos += llv;
 						T.run += llv;
 						T.match(mlv, offset);
+						OTZ_CHK(reinterpret_cast<const uint8_t *>(T.seq_end - T.nseq) >= rec_floor + T.nl, OTZ_CK_ZS_REC);
 						op += mlv;
 						kk++;
 						on = kk < nseq;

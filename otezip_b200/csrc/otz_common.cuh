@@ -40,6 +40,10 @@ __device__ unsigned long long g_otz_violations[OTZ_CHK_SLOTS];
 #define OTZ_CK_LZ_STAGE 7       // k_inflate_lz: far source staged outside its staging buffer
 #define OTZ_CK_LZ_FLUSH 9       // k_inflate_lz: ring flush outside the entry's slice of the arena / symbol buffer
 #define OTZ_CK_SEG_TABLE 12     // k_inflate_spec: segment table index beyond I2_MAXSEG
+#define OTZ_CK_ZS_TABLE 13      // k_zstd_seq: FSE state outside its table
+#define OTZ_CK_ZS_REC 14        // k_zstd_seq: sequence record stored below the literals of the entry's token scratch
+#define OTZ_CK_ZS_LIT 15        // k_zstd_lit: literals of a block outside the entry's token scratch
+#define OTZ_CK_DFL_PAIR 16      // k_deflate_chunks: (token, way) pair of the second search pass outside the window / the chunk
 
 #define OTZ_SIG_LFH 0x04034b50u
 #define OTZ_MAX_PAYLOAD (2ull * 1024ull * 1024ull * 1024ull)  // otezip.c:102

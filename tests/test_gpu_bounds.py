@@ -1,6 +1,7 @@
 """Software bounds checks (the pool's GPUs do not admit compute-sanitizer): the hardest shapes of the parity suite run
 against libotezip_b200_dbg.so — the same sources with -DOTZ_BOUNDS_CHECK, every unmasked / per-lane indexed access of the
-speculative tokenizer and the LZ executor guarded by a counter — in a child process; all counters must stay zero and
+speculative tokenizer, the LZ executor, the Zstandard tokenizers and the compressor's second search pass guarded by a
+counter — in a child process; all counters must stay zero and
 the results must still be the oracle's."""
 import json
 import os
@@ -31,6 +32,15 @@ ms += [synth.member("h0", synth.jsonlog_text(5 << 20, 1), 8), synth.member("h1",
        synth.member("h3", b"".join(bytes([rnd.randrange(256)]) * rnd.randint(1, 2000) for _ in range(3000)), 8, strategy=zlib.Z_RLE),
        synth.member("h4", synth.jsonlog_text(2200000, 10), 8, strategy=zlib.Z_HUFFMAN_ONLY),
        synth.member("h5", synth.random_bytes(32500, 21) * 70, 8, level=9)]
+try:   # real Zstandard frames (the oracle rejects them like the reference does; here only the counters matter)
+    from otezip_b200.zstdlib import Zstd
+    zs = Zstd()
+    for i, (d, lvl) in enumerate([(synth.jsonlog_text(300000, 31), 1), (synth.jsonlog_text(262144, 32), 3), (synth.jsonlog_text(150000, 33), 19),
+                                  (synth.random_bytes(200000, 34), 3), (b"q" * 300000 + synth.jsonlog_text(5000, 35), 3), (b"", 3)]):
+        f = zs.compress(d, lvl) if i != 1 else zs.compress(d[:100000], lvl) + zs.compress_adv(d[100000:], 5, checksum=True, content_size=False)
+        ms.append(synth.Member("zs%%d" %% i, 93, f, len(d), zlib.crc32(d) & 0xFFFFFFFF, raw=d))
+except OSError:
+    pass
 img = synth.build_zip(ms)
 tab = parse_central(img)
 o = Oracle()
@@ -52,6 +62,14 @@ for env in ({}, {"OTZ_SEG_PAR_RING": "8192"}, {"OTZ_LZ_RING": "16384", "OTZ_SPEC
             n = int(tab["uncomp_size"][i])
             if not np.array_equal(out[int(tab["out_ofs"][i]):int(tab["out_ofs"][i]) + n], oout[int(oofs[i]):int(oofs[i]) + n]):
                 bad += 1
+# the write path: both compression levels, every stream through zlib
+c = Ctx(0)
+src = [synth.jsonlog_text(n_, 40 + i) for i, n_ in enumerate([70000, 262144, 65280, 65281, 5])] + [synth.random_bytes(100000, 41), b"A" * 200000]
+for meth in (8, 8 | 0x100):
+    for s_, (m, p, crc_) in zip(src, c.deflate_host(src, [meth] * len(src))):
+        if (zlib.decompress(p, -15) if m == 8 else p) != s_ or crc_ != (zlib.crc32(s_) & 0xFFFFFFFF):
+            bad += 1
+c.close()
 v = (C.c_uint64 * 32)()
 n = L.otz_debug_violations(v, 32)
 print(json.dumps({"slots": n, "violations": [int(x) for x in v[:max(n, 0)]], "mismatches": bad, "entries": len(tab)}))
