@@ -15,13 +15,14 @@
 //            from there on the two decodes are identical, so its exit is the one pass 1 found — or leaves the piece
 //            at a new exit; repeated until no exit changes (lane 0 is exact from the start, so after iteration i
 //            lanes 0..i are exact: at most 31 iterations, 2-3 in practice);
-//   count    every lane decodes its piece from its true start: literals, matches, output bytes; warp prefix sums
-//            give every lane its place in the token stream and in the output;
-//   emit     the same decode once more writes the tokens: literal bytes (dense, ascending) and one 32-bit record
-//            per match {literal run : 9, length - 3 : 8, distance - 1 : 15} (descending) — the format
-//            k_inflate_lz (k_inflate2.cuh) executes.
+//   decode   every lane decodes its piece from its true start and writes the tokens — literal bytes and one 32-bit
+//            record per match {literal run : 9, length - 3 : 8, distance - 1 : 15} — into its own temp slot in
+//            global memory (L2 resident), counting literals, matches and output bytes on the way;
+//   place    warp prefix sums give every lane its place in the token stream and in the output, and the tokens move
+//            there: literals dense and ascending, records descending — the format k_inflate_lz (k_inflate2.cuh)
+//            executes.  (Round 2 first decoded every piece twice here, once to count and once to emit.)
 //
-// Four decodes of every symbol instead of one, but 32 symbols per warp instruction on one stream: a 64 KiB entry
+// Three decodes of every symbol instead of one, but 32 symbols per warp instruction on one stream: a 64 KiB entry
 // is ~9 rounds instead of 4,400 serial steps, a 16 MiB entry needs neither a block search nor a lane per block, and
 // table memory is per warp, not per stream (32 warps per SM).  Block headers (dec:122-266) are parsed by the warp
 // in lock-step from a register bit buffer; the tables are built by the warp (i2_build_table, k_inflate2.cuh).
@@ -42,6 +43,11 @@
 #define I3_WARPS 4         // NW = 1: independent warps (streams) per CTA
 // WPLMAX = words per piece (lane and round), at most: 16 (512 bits) or, for CTA groups when a batch has few huge streams, 32
 #define I3_BAD 4u          // (kinds 0..3 are I2_K_*)
+// temp slot of a lane: the tokens of its piece before their place in the stream's scratch is known (a piece spans at most
+// 32 * WPLMAX + 20 bits; a literal code has >= 1 bit, a match >= 2)
+#define I3_TMP_LIT 576u
+#define I3_TMP_REC 272u
+#define I3_TMP_BYTES (I3_TMP_LIT + 4u * I3_TMP_REC)
 #define I3_SEG_MIN 524288u // least output bytes of a segment of a huge stream (k_seg_window resolves the last 32 KiB of each one serially)
 
 struct I3BuildScratch {
@@ -228,15 +234,20 @@ template <int NW, int MINB = (NW == 1 ? 8 : 16 / NW), int WPLMAX = 16>
 __global__ void __launch_bounds__(32 * (NW == 1 ? I3_WARPS : NW), MINB) k_inflate_spec(const uint8_t *__restrict__ archive,
 	const otz_entry *__restrict__ ents, const OtzEntryState *__restrict__ est, const int32_t *__restrict__ status, const uint32_t *__restrict__ list,
 	uint32_t k0, uint32_t k1, uint32_t *__restrict__ work_counter, uint8_t *__restrict__ scratch, const uint64_t *__restrict__ tok_ofs,
-	I2TokRes *__restrict__ tokres, uint32_t *__restrict__ fb_list, uint32_t *__restrict__ fb_count, uint32_t n_huge, I2SegCtl seg, uint32_t seg_min) {
+	I2TokRes *__restrict__ tokres, uint32_t *__restrict__ fb_list, uint32_t *__restrict__ fb_count, uint32_t n_huge, I2SegCtl seg, uint32_t seg_min,
+	uint8_t *__restrict__ tmp) {
+	static_assert(32 * WPLMAX + 20 <= I3_TMP_LIT && (32 * WPLMAX + 20) / 2 <= I3_TMP_REC, "temp slot too small for this piece length");
 	extern __shared__ __align__(16) uint8_t smem_raw[];
 	constexpr uint32_t G = 32u * NW;
+	constexpr uint32_t I3_TMP_SMEM = 4u * WPLMAX;   // literals of a piece kept in shared memory: the WPLMAX words of the lane's boundary bitmap
 	const uint32_t lane = threadIdx.x & 31u;
 	const uint32_t warp = NW == 1 ? 0u : threadIdx.x >> 5;   // warp within the group
 	const uint32_t tid = NW == 1 ? lane : threadIdx.x;        // thread within the group = its piece
 	typedef I3Smem<NW, WPLMAX> Smem;
 	Smem &S = reinterpret_cast<Smem *>(smem_raw)[NW == 1 ? threadIdx.x >> 5 : 0];
 	const uint32_t lt_mask = (1u << lane) - 1u;
+	uint8_t *const tml = tmp + (size_t)(blockIdx.x * blockDim.x + threadIdx.x) * I3_TMP_BYTES;   // this lane's temp literals
+	uint32_t *const tmr = reinterpret_cast<uint32_t *>(tml + I3_TMP_LIT);                          // and records
 
 	for (;;) {
 		uint32_t k = 0;
@@ -666,23 +677,41 @@ __global__ void __launch_bounds__(32 * (NW == 1 ? I3_WARPS : NW), MINB) k_inflat
 					break;
 				}
 				const bool valid = tid <= lastl;
-				// ---- count
+				// ---- decode: the tokens of the piece go to the lane's temp slot (their place in the stream is not known yet), counted on the way
 				uint32_t nl = 0, nm = 0, ob = 0, lead = 0, since = 0, esc_in = 0;   // esc_in: escape records in front of matches that are not the first of the piece
+				uint32_t lastp = 0;
+				int32_t need = -0x40000000;   // max over the matches of (distance - output bytes of the piece in front of the match)
 				{
 					uint32_t q = T;
 					bool on = valid;
 					while (__any_sync(0xFFFFFFFFu, on)) {
 						uint32_t nx, v_, d_;
-						const uint32_t kd = i3_step<1>(lit, dst, pw, q, Pend, nx, v_, d_);
+						const uint32_t kd = i3_step<2>(lit, dst, pw, q, Pend, nx, v_, d_);
 						if (on) {
 							OTZ_CHK(q >= R && q - base < S_bits && (q >> 5) - (w0 + tid * wpl) <= wpl, OTZ_CK_SPEC_PIECE);
 							const bool isl = kd == I2_K_LEN, isb = kd == I2_K_LIT;
-							lead = (isl && nm == 0u) ? since : lead;
-							esc_in += (isl && nm != 0u) ? since / I2_SEQ_ESC : 0u;   // (only pieces of more than 511 bits can hold such a run)
+							if (isb) {
+								OTZ_CHK(nl < I3_TMP_LIT, OTZ_CK_SPEC_LIT);
+								// (the first I3_TMP_SMEM literals stay on chip, in the lane's words of the boundary bitmap — not needed any
+								// more in this round: one scattered byte store to global memory per literal is what the tokenizer can afford)
+								if (nl < I3_TMP_SMEM) {
+									reinterpret_cast<uint8_t *>(&vis[(nl >> 2) * G + tid])[nl & 3u] = (uint8_t)v_;
+								} else {
+									tml[nl] = (uint8_t)v_;
+								}
+							}
+							if (isl) {
+								OTZ_CHK(nm < I3_TMP_REC, OTZ_CK_SPEC_SEQ);
+								need = max(need, (int32_t)d_ - (int32_t)ob);
+								lead = nm == 0u ? since : lead;
+								esc_in += nm != 0u ? since / I2_SEQ_ESC : 0u;   // (only a piece of more than 511 bits can hold such a run)
+								tmr[nm] = (nm == 0u ? 0u : since & 511u) | ((v_ - 3u) << 9) | ((d_ - 1u) << 17);   // (first record: its run is set below)
+							}
 							nl += isb;
 							nm += isl;
 							ob += isb ? 1u : isl ? v_ : 0u;
 							since = isl ? 0u : since + isb;
+							lastp = (isl || isb) ? nx : lastp;
 							q = nx;
 							on = (isl || isb) && q < end;   // (I3_BAD cannot happen on the verified chain)
 						}
@@ -734,38 +763,36 @@ __global__ void __launch_bounds__(32 * (NW == 1 ? I3_WARPS : NW), MINB) k_inflat
 				const uint32_t esc = nm ? (carry_in + lead) / I2_SEQ_ESC : 0u;
 				uint32_t sqpre, dummy_pre, tot_sq, dummy_tot;
 				i3_scan2<NW, Smem>(S, lane, warp, 8, nm + esc + esc_in, 0u, sqpre, dummy_pre, tot_sq, dummy_tot);
-				// ---- emit
-				uint32_t bad = 0, minsrc = 0xFFFFFFFFu, lastp = 0;
+				if (i3_any<NW>(esc_in != 0u)) {
+					act = I3_A_FALLBACK;   // a run of 511 literals and more inside one piece (one-bit literal codes): k_inflate decodes the stream
+					break;
+				}
+				// ---- the tokens move from the temp slots to their places
+				uint32_t bad = 0, minsrc = 0xFFFFFFFFu;
 				{
-					uint32_t q = T, run = carry_in, opos = ob_tot + obpre;
 					uint8_t *lp = litp + nl_tot + nlpre;
-					uint32_t *sp = seq_end - (nseq_tot + sqpre);
-					bool on = valid;
-					while (__any_sync(0xFFFFFFFFu, on)) {
-						uint32_t nx, v_, d_;
-						const uint32_t kd = i3_step<2>(lit, dst, pw, q, Pend, nx, v_, d_);
-						if (on) {
-							const bool isl = kd == I2_K_LEN, isb = kd == I2_K_LIT;
-							OTZ_CHK(q >= R && q - base < S_bits && (q >> 5) - (w0 + tid * wpl) <= wpl, OTZ_CK_SPEC_PIECE);
-							if (isb) {
-								OTZ_CHK(lp >= litp && lp < reinterpret_cast<uint8_t *>(seq_end), OTZ_CK_SPEC_LIT);
-								*lp++ = (uint8_t)v_;
-							}
-							if (isl) {
-								bad |= d_ > opos;   // reaches before the start of the output (strict; dec:785 does not check)
-								minsrc = min(minsrc, opos - d_);
-								while (run >= I2_SEQ_ESC) {
-									*--sp = I2_SEQ_ESC;
-									run -= I2_SEQ_ESC;
-								}
-								OTZ_CHK(sp > reinterpret_cast<uint32_t *>(litp + nl_tot + tot_nl) && sp <= seq_end, OTZ_CK_SPEC_SEQ);
-								*--sp = run | ((v_ - 3u) << 9) | ((d_ - 1u) << 17);
-							}
-							run = isl ? 0u : run + isb;
-							opos += isb ? 1u : isl ? v_ : 0u;
-							lastp = (isl || isb) ? nx : lastp;
-							q = nx;
-							on = (isl || isb) && q < end;
+					OTZ_CHK(nl == 0u || (lp >= litp && lp + nl <= reinterpret_cast<uint8_t *>(seq_end)), OTZ_CK_SPEC_LIT);
+					const uint32_t n_on = min(nl, I3_TMP_SMEM);
+					for (uint32_t i = 0; i < n_on; i++) {
+						lp[i] = reinterpret_cast<const uint8_t *>(&vis[(i >> 2) * G + tid])[i & 3u];
+					}
+					for (uint32_t i = I3_TMP_SMEM; i < nl; i++) {
+						lp[i] = tml[i];
+					}
+					if (nm) {
+						const uint32_t opos = ob_tot + obpre;
+						bad = (int64_t)need > (int64_t)opos;   // reaches before the start of the output (strict; dec:785 does not check)
+						minsrc = opos - (uint32_t)need;
+						uint32_t *sp = seq_end - (nseq_tot + sqpre);
+						uint32_t run = carry_in + lead;
+						while (run >= I2_SEQ_ESC) {
+							*--sp = I2_SEQ_ESC;
+							run -= I2_SEQ_ESC;
+						}
+						OTZ_CHK(sp - nm >= reinterpret_cast<uint32_t *>(litp + nl_tot + tot_nl) && sp <= seq_end, OTZ_CK_SPEC_SEQ);
+						*--sp = (tmr[0] & ~511u) | run;
+						for (uint32_t j = 1; j < nm; j++) {
+							*--sp = tmr[j];
 						}
 					}
 				}

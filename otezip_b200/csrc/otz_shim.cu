@@ -59,6 +59,8 @@ struct otz_ctx {
 	int huge_legacy;        // OTZ_HUGE_MODE=legacy: huge DEFLATE entries on k_inflate<32,16384> instead of the segmented decode
 	uint8_t *d_ztok_cache;  // grow-only token scratch of the two-phase Zstandard path
 	uint64_t ztok_cache_bytes;
+	uint8_t *d_spec_tmp;    // temp token slots of k_inflate_spec: 4 regions (regular streams + three size groups of huge ones) of one slot per resident lane
+	uint64_t spec_tmp_region;
 	uint8_t *d_tok_cache;   // grow-only token scratch of the two-phase inflate (literals + sequence records)
 	uint64_t tok_cache_bytes;
 	int seg_serial;         // OTZ_SEG_EXEC=serial: one warp walks the chain of a huge stream (no parallel segment execution)
@@ -267,6 +269,7 @@ extern "C" void otz_ctx_destroy(otz_ctx *c) {
 	cudaFree(c->d_tok_cache);
 	cudaFree(c->d_sym_cache);
 	cudaFree(c->d_ztok_cache);
+	cudaFree(c->d_spec_tmp);
 	for (size_t k = 0; k < c->pc_plans.size(); k++) {
 		otz_plan_destroy(c->pipe[k & 1], c->pc_plans[k]);
 	}
@@ -717,8 +720,29 @@ static int launch_seg_par(otz_ctx *c, otz_plan *p, uint8_t *d_out, const I2SegCt
 // stream of the batch (longest first); huge streams come out as segment tables, which k_seg_stitch places in the symbol
 // buffer for the parallel execution (second stream), everything else goes to k_inflate_lz; then k_inflate over whatever
 // phase A declined (d_counter + 52 counts those entries).
+// temp token slots of k_inflate_spec (I3_TMP_BYTES per resident lane; at most 1,024 lanes of these kernels fit an SM): four
+// regions, because the tokenizer of the regular streams and those of up to three size groups of huge streams run at once.
+// Allocated once per context.
+static int reserve_spec_tmp(otz_ctx *c) {
+	if (c->d_spec_tmp) {
+		return OTZ_SUCCESS;
+	}
+	c->spec_tmp_region = (uint64_t)c->sm_count * 1024u * I3_TMP_BYTES;
+	if (cudaMalloc(&c->d_spec_tmp, 4 * c->spec_tmp_region) != cudaSuccess) {
+		c->d_spec_tmp = nullptr;
+		return fail_cuda(cudaGetLastError(), "cudaMalloc(tokenizer temp slots)");
+	}
+	return OTZ_SUCCESS;
+}
+
 static int dispatch_inflate3(otz_ctx *c, otz_plan *p, const uint8_t *d_archive, uint8_t *d_out) {
 	cudaStream_t s = c->stream, s2 = c->stream2;
+	{
+		const int rc_ = reserve_spec_tmp(c);
+		if (rc_) {
+			return rc_;
+		}
+	}
 	static bool attr_done = false;
 	const size_t smem1 = I3_WARPS * sizeof(I3Smem<1>), smem4 = sizeof(I3Smem<4>), smem8 = sizeof(I3Smem<8, 16>);
 	if (!attr_done) {
@@ -814,7 +838,7 @@ static int dispatch_inflate3(otz_ctx *c, otz_plan *p, const uint8_t *d_archive, 
 			const uint32_t ng = G.h1 - G.h0;
 			const uint32_t grid4 = gs ? (uint32_t)atoi(gs) : std::max(1u, std::min((uint32_t)(c->sm_count * per_sm4), ng));
 			kern4<<<grid4, thr4, smem4x, G.st>>>(d_archive, p->d_ents, p->d_est, p->d_status, p->d_inflate_list, G.h0, G.h1, p->d_counter + G.c_spec,
-				c->d_tok_cache, p->d_tok_ofs, p->d_tokres, p->d_fb_list, p->d_counter + 52, nh, p->seg, seg_min);
+				c->d_tok_cache, p->d_tok_ofs, p->d_tokres, p->d_fb_list, p->d_counter + 52, nh, p->seg, seg_min, c->d_spec_tmp + (1u + g) * c->spec_tmp_region);
 			c->launches++;
 			CK(cudaGetLastError());
 		}
@@ -827,7 +851,7 @@ static int dispatch_inflate3(otz_ctx *c, otz_plan *p, const uint8_t *d_archive, 
 		CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm4, kern4, 128, smem4));
 		const uint32_t grid4 = gs ? (uint32_t)atoi(gs) : std::max(1u, std::min((uint32_t)(c->sm_count * std::max(per_sm4, 1)), count));
 		kern4<<<grid4, 128, smem4, s>>>(d_archive, p->d_ents, p->d_est, p->d_status, p->d_inflate_list, nh, p->n_inflate, p->d_counter,
-			c->d_tok_cache, p->d_tok_ofs, p->d_tokres, p->d_fb_list, p->d_counter + 52, nh, p->seg, seg_min);
+			c->d_tok_cache, p->d_tok_ofs, p->d_tokres, p->d_fb_list, p->d_counter + 52, nh, p->seg, seg_min, c->d_spec_tmp);
 		c->launches++;
 		CK(cudaGetLastError());
 	} else if (count) {
@@ -839,7 +863,7 @@ static int dispatch_inflate3(otz_ctx *c, otz_plan *p, const uint8_t *d_archive, 
 		}
 		const uint32_t grid = gs ? (uint32_t)atoi(gs) : std::max(1u, std::min((uint32_t)(c->sm_count * per_sm), (count + I3_WARPS - 1) / I3_WARPS));
 		k_inflate_spec<1><<<grid, 32 * I3_WARPS, smem1, s>>>(d_archive, p->d_ents, p->d_est, p->d_status, p->d_inflate_list, nh, p->n_inflate, p->d_counter,
-			c->d_tok_cache, p->d_tok_ofs, p->d_tokres, p->d_fb_list, p->d_counter + 52, nh, p->seg, seg_min);
+			c->d_tok_cache, p->d_tok_ofs, p->d_tokres, p->d_fb_list, p->d_counter + 52, nh, p->seg, seg_min, c->d_spec_tmp);
 		c->launches++;
 		CK(cudaGetLastError());
 	}
@@ -1117,6 +1141,12 @@ extern "C" int otz_extract_host(otz_ctx *c, const uint8_t *archive, uint64_t arc
 // (which synchronise the device) lands between its asynchronous stages.  Failing to allocate is not an error here: the
 // dispatchers fall back to the decoders that need no scratch.
 static int reserve_scratch(otz_ctx *c, otz_plan *p) {
+	if (p->n_inflate) {
+		const int rc_ = reserve_spec_tmp(c);
+		if (rc_) {
+			return rc_;
+		}
+	}
 	if (p->n_inflate && p->tok_bytes + 64 > c->tok_cache_bytes) {
 		CK(cudaStreamSynchronize(c->stream));
 		cudaFree(c->d_tok_cache);
