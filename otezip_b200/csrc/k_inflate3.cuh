@@ -560,6 +560,10 @@ __global__ void __launch_bounds__(32 * (NW == 1 ? I3_WARPS : NW), MINB) k_inflat
 					for (uint32_t i = 0; i < wpl + 3u; i++) {
 						myst[i] = wb + i < nw ? __ldg(inw + wb + i) : 0u;
 					}
+					// (the words of the next round, about G pieces further on: an L2 hit instead of an HBM round trip at its start)
+					if (wb + G * wpl < nw) {
+						asm volatile("prefetch.global.L2 [%0];" ::"l"(inw + wb + G * wpl));
+					}
 					for (uint32_t w = 0; w < wpl; w++) {
 						vis[w * G + tid] = 0u;
 					}
