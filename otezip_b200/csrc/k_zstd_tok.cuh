@@ -24,8 +24,9 @@
 // lane (group) first walks its entry to the next block that has work for this kernel — fetching a new entry from the
 // work counter whenever its own is finished —, then all of them build their tables, then all of them run their decoding
 // loop.  The walk (zs_walk) is the one piece of code both kernels share, so they agree on the structure and on every
-// structural error; an entry is released to the LZ executor when both kernels accepted it, and otherwise gets the status
-// of the error that comes first in the stream.
+// structural error.  The two kernels run at the same time (the sequence kernel leaves a fifth of an SM's shared memory and
+// most of its issue slots free); k_zstd_join releases an entry to the LZ executor when both accepted it, and otherwise gives it
+// the status of the error that comes first in the stream.
 #pragma once
 #include "k_zstd.cuh"
 
@@ -316,7 +317,7 @@ struct __align__(16) ZsLitSmem {
 	uint32_t k;                          // list slot fetched by the group's first lane
 	uint32_t pad;                        // 4368 bytes = 1092 words = 4 (mod 32): equal indices of the 8 groups fall into different banks
 };
-#define ZS_LIT_WARPS 2
+#define ZS_LIT_WARPS 1   // (35 KB of shared memory per CTA: one fits next to a CTA of k_zstd_seq, which runs at the same time)
 
 // grid: persistent, ZS_LIT_WARPS warps per CTA, 8 entries per warp (4 lanes each)
 __global__ void __launch_bounds__(32 * ZS_LIT_WARPS) k_zstd_lit(const uint8_t *__restrict__ archive, const otz_entry *__restrict__ ents,
@@ -469,7 +470,7 @@ __global__ void __launch_bounds__(32 * ZS_LIT_WARPS) k_zstd_lit(const uint8_t *_
 // tables in its own slot of the dynamic shared memory (ZS_SEQ_WARPS * lpw * ZS_SEQ_TAB_BYTES)
 __global__ void __launch_bounds__(32 * ZS_SEQ_WARPS, 1) k_zstd_seq(const uint8_t *__restrict__ archive, const otz_entry *__restrict__ ents,
 	const OtzEntryState *__restrict__ est, int32_t *__restrict__ status, const uint32_t *__restrict__ list, uint32_t n_list,
-	uint8_t *__restrict__ scratch, const uint64_t *__restrict__ tok_ofs, I2TokRes *__restrict__ tokres, const uint32_t *__restrict__ litres,
+	uint8_t *__restrict__ scratch, const uint64_t *__restrict__ tok_ofs, I2TokRes *__restrict__ tokres, uint32_t *__restrict__ seqres,
 	uint32_t *__restrict__ work_counter, uint32_t lpw) {
 	extern __shared__ __align__(16) uint8_t smem_raw[];
 	// code -> base | extra bits << 24 (the lanes index these with different codes: shared memory, not the constant bank)
@@ -514,6 +515,7 @@ __global__ void __launch_bounds__(32 * ZS_SEQ_WARPS, 1) k_zstd_seq(const uint8_t
 				}
 				ei = list[k];
 				tokres[k].ok = 0u;
+				seqres[k] = 0u;
 				if (status[ei] != OTZ_ST_PENDING) {
 					continue;   // resolved as a reference container (or failed earlier)
 				}
@@ -530,17 +532,16 @@ __global__ void __launch_bounds__(32 * ZS_SEQ_WARPS, 1) k_zstd_seq(const uint8_t
 					W.err = W.n_frames == 0 ? OTZ_ST_DATA : (W.op == W.cap ? 0 : OTZ_ST_SIZE);
 					W.pos++;
 				}
-				const uint32_t vs = zs_verdict(W, ZS_PH_SEQ), vl = litres[k];
-				const uint32_t v = vs == 0u ? vl : vl == 0u ? vs : min(vs, vl);
-				if (v == 0u) {
+				// this kernel's verdict; k_zstd_join combines it with the literal kernel's (the two run at the same time)
+				const uint32_t vs = zs_verdict(W, ZS_PH_SEQ);
+				seqres[k] = vs;
+				if (vs == 0u) {
 					I2TokRes r;
 					r.nseq = T.nseq;
 					r.nlit = T.nl;
 					r.status = OTZ_ST_OK | OTZ_STF_REF_EOB;   // a valid stream that the reference rejects
 					r.ok = 1u;
 					tokres[k] = r;
-				} else {
-					status[ei] = (int32_t)(v & 0xFFu);
 				}
 				busy = false;
 				continue;
@@ -712,5 +713,21 @@ __global__ void __launch_bounds__(32 * ZS_SEQ_WARPS, 1) k_zstd_seq(const uint8_t
 				W.op = op + tail;
 			}
 		}
+	}
+}
+
+// the verdicts of the two tokenizers: an entry is executed when both accepted it, else it gets the status of the error
+// that comes first in the stream (0 = accepted, else (position << 8) | status code)
+__global__ void k_zstd_join(const uint32_t *__restrict__ list, uint32_t n_list, const uint32_t *__restrict__ litres, const uint32_t *__restrict__ seqres,
+	I2TokRes *__restrict__ tokres, int32_t *__restrict__ status) {
+	const uint32_t k = blockIdx.x * blockDim.x + threadIdx.x;
+	if (k >= n_list) {
+		return;
+	}
+	const uint32_t vl = litres[k], vs = seqres[k];
+	const uint32_t v = vs == 0u ? vl : vl == 0u ? vs : min(vs, vl);
+	if (v) {
+		tokres[k].ok = 0u;
+		status[list[k]] = (int32_t)(v & 0xFFu);
 	}
 }

@@ -597,7 +597,7 @@ extern "C" int otz_plan_create(otz_ctx *c, const otz_entry *ents, uint32_t n, co
 			zofs[k + 1] = zofs[k] + zs_scratch_bytes(ents[zst[k]].uncomp_size);
 		}
 		p->ztok_bytes = zofs.back();
-		if ((rc = upload(&p->d_ztok_ofs, zofs, c->stream)) || cudaMalloc(&p->d_ztokres, zst.size() * (sizeof(I2TokRes) + 4)) != cudaSuccess   /* + the literal kernel's verdicts */) {
+		if ((rc = upload(&p->d_ztok_ofs, zofs, c->stream)) || cudaMalloc(&p->d_ztokres, zst.size() * (sizeof(I2TokRes) + 8)) != cudaSuccess   /* + the verdicts of the two tokenizers */) {
 			otz_plan_destroy(c, p);
 			return rc ? rc : fail_cuda(cudaGetLastError(), "cudaMalloc(two-phase zstd lists)");
 		}
@@ -1023,21 +1023,30 @@ extern "C" int otz_extract_run(otz_ctx *c, otz_plan *p, const uint8_t *d_archive
 				}
 				CK(cudaEventRecord(zev[0], s));
 			}
+			uint32_t *const seqres = litres + p->n_zstd;
 			int per_sm = 0;
-			CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_zstd_lit, 32 * ZS_LIT_WARPS, zsmem2));
-			const uint32_t zgrid = std::max(1u, std::min((uint32_t)(c->sm_count * std::max(per_sm, 1)), (p->n_zstd + 8 * ZS_LIT_WARPS - 1) / (8 * ZS_LIT_WARPS)));
-			k_zstd_lit<<<zgrid, 32 * ZS_LIT_WARPS, zsmem2, s>>>(d_archive, p->d_ents, p->d_est, p->d_status, p->d_zstd_list, p->n_zstd, c->d_ztok_cache,
-				p->d_ztok_ofs, litres, p->d_counter + 32);
+			// sequences on the main stream FIRST (one CTA of ZS_SEQ_WARPS warps per SM, as many lanes per warp as the batch needs:
+			// their tables are the shared memory), literals on a side stream next to them: the CTAs of the literal kernel take the
+			// shared memory and the issue slots the sequence kernel leaves
+			const uint32_t zw = ZS_SEQ_WARPS;
+			const uint32_t zlpw = std::max(1u, std::min((uint32_t)ZS_SEQ_LPW_MAX, (p->n_zstd + c->sm_count * zw - 1) / (c->sm_count * zw)));
+			const uint32_t sgrid = std::max(1u, std::min((uint32_t)c->sm_count, (p->n_zstd + zlpw * zw - 1) / (zlpw * zw)));
+			CK(cudaEventRecord(c->ev_fork, s));
+			k_zstd_seq<<<sgrid, 32 * zw, zw * zlpw * ZS_SEQ_TAB_BYTES, s>>>(d_archive, p->d_ents, p->d_est, p->d_status, p->d_zstd_list,
+				p->n_zstd, c->d_ztok_cache, p->d_ztok_ofs, p->d_ztokres, seqres, p->d_counter + 34, zlpw);
 			c->launches++;
 			if (ztrace) {
 				CK(cudaEventRecord(zev[1], s));
 			}
-			// sequences: one CTA of ZS_SEQ_WARPS warps per SM, as many lanes per warp as the batch needs (their tables are the shared memory)
-			const uint32_t zw = ZS_SEQ_WARPS;
-			const uint32_t zlpw = std::max(1u, std::min((uint32_t)ZS_SEQ_LPW_MAX, (p->n_zstd + c->sm_count * zw - 1) / (c->sm_count * zw)));
-			const uint32_t sgrid = std::max(1u, std::min((uint32_t)c->sm_count, (p->n_zstd + zlpw * zw - 1) / (zlpw * zw)));
-			k_zstd_seq<<<sgrid, 32 * zw, zw * zlpw * ZS_SEQ_TAB_BYTES, s>>>(d_archive, p->d_ents, p->d_est, p->d_status, p->d_zstd_list,
-				p->n_zstd, c->d_ztok_cache, p->d_ztok_ofs, p->d_ztokres, litres, p->d_counter + 34, zlpw);
+			CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_zstd_lit, 32 * ZS_LIT_WARPS, zsmem2));
+			const uint32_t zgrid = std::max(1u, std::min((uint32_t)(c->sm_count * std::max(per_sm, 1)), (p->n_zstd + 8 * ZS_LIT_WARPS - 1) / (8 * ZS_LIT_WARPS)));
+			CK(cudaStreamWaitEvent(c->stream4, c->ev_fork, 0));
+			k_zstd_lit<<<zgrid, 32 * ZS_LIT_WARPS, zsmem2, c->stream4>>>(d_archive, p->d_ents, p->d_est, p->d_status, p->d_zstd_list, p->n_zstd, c->d_ztok_cache,
+				p->d_ztok_ofs, litres, p->d_counter + 32);
+			c->launches++;
+			CK(cudaEventRecord(c->ev_join4, c->stream4));
+			CK(cudaStreamWaitEvent(s, c->ev_join4, 0));
+			k_zstd_join<<<(p->n_zstd + 255) / 256, 256, 0, s>>>(p->d_zstd_list, p->n_zstd, litres, seqres, p->d_ztokres, p->d_status);
 			c->launches++;
 			if (ztrace) {
 				CK(cudaEventRecord(zev[2], s));
@@ -1054,8 +1063,8 @@ extern "C" int otz_extract_run(otz_ctx *c, otz_plan *p, const uint8_t *d_archive
 				for (int i = 0; i < 3; i++) {
 					CK(cudaEventElapsedTime(&t[i], zev[i], zev[i + 1]));
 				}
-				fprintf(stderr, "otz zstd: %u entries | k_zstd_lit %.3f ms (grid %u)  k_zstd_seq %.3f ms (grid %u, %u lanes per warp)  k_inflate_lz<wide> %.3f ms\n",
-					p->n_zstd, t[0], zgrid, t[1], sgrid, zlpw, t[2]);
+				fprintf(stderr, "otz zstd: %u entries | k_zstd_seq %.3f ms (grid %u, %u lanes per warp)  + k_zstd_lit on a side stream (grid %u) + join %.3f ms  k_inflate_lz<wide> %.3f ms\n",
+					p->n_zstd, t[0], sgrid, zlpw, zgrid, t[1], t[2]);
 				for (int i = 0; i < 4; i++) {
 					cudaEventDestroy(zev[i]);
 				}
