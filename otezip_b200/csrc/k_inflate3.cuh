@@ -767,12 +767,10 @@ __global__ void __launch_bounds__(32 * (NW == 1 ? I3_WARPS : NW), MINB) k_inflat
 				const uint32_t esc = nm ? (carry_in + lead) / I2_SEQ_ESC : 0u;
 				uint32_t sqpre, dummy_pre, tot_sq, dummy_tot;
 				i3_scan2<NW, Smem>(S, lane, warp, 8, nm + esc + esc_in, 0u, sqpre, dummy_pre, tot_sq, dummy_tot);
-				if (i3_any<NW>(esc_in != 0u)) {
-					act = I3_A_FALLBACK;   // a run of 511 literals and more inside one piece (one-bit literal codes): k_inflate decodes the stream
-					break;
-				}
 				// ---- the tokens move from the temp slots to their places
-				uint32_t bad = 0, minsrc = 0xFFFFFFFFu;
+				// (a run of 511 literals and more INSIDE one piece — one-bit literal codes — would need escape records between the
+				// piece's own records: such a stream goes to k_inflate, through the flags of the round below)
+				uint32_t bad = esc_in != 0u, minsrc = 0xFFFFFFFFu;
 				{
 					uint8_t *lp = litp + nl_tot + nlpre;
 					OTZ_CHK(nl == 0u || (lp >= litp && lp + nl <= reinterpret_cast<uint8_t *>(seq_end)), OTZ_CK_SPEC_LIT);
@@ -785,7 +783,7 @@ __global__ void __launch_bounds__(32 * (NW == 1 ? I3_WARPS : NW), MINB) k_inflat
 					}
 					if (nm) {
 						const uint32_t opos = ob_tot + obpre;
-						bad = (int64_t)need > (int64_t)opos;   // reaches before the start of the output (strict; dec:785 does not check)
+						bad |= (int64_t)need > (int64_t)opos;   // reaches before the start of the output (strict; dec:785 does not check)
 						minsrc = opos - (uint32_t)need;
 						uint32_t *sp = seq_end - (nseq_tot + sqpre);
 						uint32_t run = carry_in + lead;
