@@ -558,9 +558,12 @@ extern "C" int otz_plan_create(otz_ctx *c, const otz_entry *ents, uint32_t n, co
 	}
 	if (p->n_inflate_huge && p->n_inflate_huge <= 4096u) {
 		const size_t nh = p->n_inflate_huge, ns = nh * I2_MAXSEG;
+		// size groups of the few-streams regime (dispatch_inflate3), in percent of the largest stream's compressed size (75 / 50
+		// and 85 / 60 measured the same on a 1,250-entry shard: the chains are bound by the latency of the largest stream)
+		const uint64_t split_pct[2] = { 50u, 25u };
 		for (size_t h = 0; h < nh; h++) {
-			p->huge_split[0] += (uint64_t)ents[infl[h]].comp_size * 2u >= ents[infl[0]].comp_size;   // (the list is sorted by compressed size)
-			p->huge_split[1] += (uint64_t)ents[infl[h]].comp_size * 4u >= ents[infl[0]].comp_size;
+			p->huge_split[0] += (uint64_t)ents[infl[h]].comp_size * 100u >= (uint64_t)ents[infl[0]].comp_size * split_pct[0];   // (the list is sorted by compressed size)
+			p->huge_split[1] += (uint64_t)ents[infl[h]].comp_size * 100u >= (uint64_t)ents[infl[0]].comp_size * split_pct[1];
 			// symbols of the stream + markers in front of every segment (a stream with more segments than estimated here is
 			// executed by one warp)
 			p->sym_elems += (uint64_t)ents[infl[h]].uncomp_size +
@@ -799,6 +802,15 @@ static int dispatch_inflate3(otz_ctx *c, otz_plan *p, const uint8_t *d_archive, 
 		grp[n_grp].h1 = nh;
 		n_grp++;
 	}
+	// OTZ_INFLATE_TRACE=1: a timeline of the chains of one run, printed to stderr (a diagnostic: it waits for the run)
+	const bool itrace = getenv("OTZ_INFLATE_TRACE") != nullptr;
+	cudaEvent_t tev[12] = {};
+	if (itrace) {
+		for (int i = 0; i < 12; i++) {
+			CK(cudaEventCreate(&tev[i]));
+		}
+		CK(cudaEventRecord(tev[0], s));
+	}
 	I2SegCtl sg = p->seg;
 	if (nh) {
 		// huge streams: the warps of a CTA decode one stream together; second (and third) stream, next to the warp-per-stream kernel
@@ -841,6 +853,9 @@ static int dispatch_inflate3(otz_ctx *c, otz_plan *p, const uint8_t *d_archive, 
 				c->d_tok_cache, p->d_tok_ofs, p->d_tokres, p->d_fb_list, p->d_counter + 52, nh, p->seg, seg_min, c->d_spec_tmp + (1u + g) * c->spec_tmp_region);
 			c->launches++;
 			CK(cudaGetLastError());
+			if (itrace) {
+				CK(cudaEventRecord(tev[1 + g], G.st));
+			}
 		}
 	}
 	// few streams: a warp per stream leaves the machine idle while every stream waits for its own serial rounds — then the
@@ -883,6 +898,9 @@ static int dispatch_inflate3(otz_ctx *c, otz_plan *p, const uint8_t *d_archive, 
 		k_inflate_lz<OTZ_SEG_RING, false, true><<<lgrid, 128, 4 * sizeof(I2LzSmem<OTZ_SEG_RING>), G.st>>>(d_out, p->d_ents, p->d_inflate_list, G.h1,
 			p->d_counter + G.c_seglz, c->d_tok_cache, p->d_tok_ofs, p->d_tokres, p->d_status, p->d_produced, sgg, G.h0);
 		c->launches += 2;
+		if (itrace) {
+			CK(cudaEventRecord(tev[4 + g], G.st));
+		}
 		if (sg.sym_cap) {
 			int rc_ = c->seg_ring == 8192 ? launch_seg_par<8192>(c, p, d_out, sgg, G.st, G.h0, G.h1, p->d_counter + G.c_par, p->d_counter + G.c_tr)
 			                              : launch_seg_par<4096>(c, p, d_out, sgg, G.st, G.h0, G.h1, p->d_counter + G.c_par, p->d_counter + G.c_tr);
@@ -892,7 +910,13 @@ static int dispatch_inflate3(otz_ctx *c, otz_plan *p, const uint8_t *d_archive, 
 		}
 		CK(cudaGetLastError());
 		CK(cudaEventRecord(G.join, G.st));
+		if (itrace) {
+			CK(cudaEventRecord(tev[7 + g], G.st));
+		}
 		forked = true;
+	}
+	if (itrace) {
+		CK(cudaEventRecord(tev[10], s));   // (regular streams: tokenizer done)
 	}
 	if (count) {
 		int rc;
@@ -905,9 +929,29 @@ static int dispatch_inflate3(otz_ctx *c, otz_plan *p, const uint8_t *d_archive, 
 			return rc;
 		}
 	}
+	if (itrace) {
+		CK(cudaEventRecord(tev[11], s));   // (regular streams: executed)
+	}
 	if (forked) {
 		for (uint32_t g = 0; g < n_grp; g++) {
 			CK(cudaStreamWaitEvent(s, grp[g].join, 0));   // (k_seg_stitch appends to the same fallback list)
+		}
+	}
+	if (itrace) {
+		CK(cudaStreamSynchronize(s));
+		auto at = [&](int i) {
+			float t = 0;
+			cudaEventElapsedTime(&t, tev[0], tev[i]);
+			return t;
+		};
+		fprintf(stderr, "otz inflate: %u regular streams: tokenizer done %.2f ms, executed %.2f ms |", count, at(10), at(11));
+		for (uint32_t g = 0; g < n_grp; g++) {
+			fprintf(stderr, " group %u (%u huge streams): tokenizer %.2f, stitch + walk %.2f, segments / window / translate %.2f ms |", g, grp[g].h1 - grp[g].h0,
+				at(1 + g), at(4 + g), at(7 + g));
+		}
+		fprintf(stderr, "\n");
+		for (int i = 0; i < 12; i++) {
+			cudaEventDestroy(tev[i]);
 		}
 	}
 	return launch_inflate_cfg(c, p, d_archive, d_out, 32, 4096, 0, p->n_inflate, 16, s, p->d_fb_list, p->d_counter + 52);
