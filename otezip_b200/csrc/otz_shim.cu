@@ -784,7 +784,10 @@ static int dispatch_inflate3(otz_ctx *c, otz_plan *p, const uint8_t *d_archive, 
 	} grp[3] = { { 0u, nh, s2, c->ev_join, 57u, 58u, 60u, 61u, 0u }, { 0u, 0u, c->stream3, c->ev_join3, 40u, 41u, 42u, 43u, 1u },
 		{ 0u, 0u, c->stream4, c->ev_join4, 44u, 45u, 46u, 47u, 2u } };
 	uint32_t n_grp = nh ? 1u : 0u;
-	if (wide && !getenv("OTZ_SPEC_ONE_GROUP")) {
+	// (also with many huge streams, as far as the plan knows the cuts: while the segments of one group are executed — bound by
+	// instruction issue — the window chain (latency) and the translation (DRAM) of another run next to them: configs[2] as
+	// named 241 -> 246 GB/s)
+	if (nh && (wide || nh <= 4096u) && !getenv("OTZ_SPEC_ONE_GROUP")) {
 		const char *mg = getenv("OTZ_SPEC_GROUPS");
 		const uint32_t max_grp = mg ? (uint32_t)atoi(mg) : 3u;
 		uint32_t cut[2] = { p->huge_split[0], p->huge_split[1] };
