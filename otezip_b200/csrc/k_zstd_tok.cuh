@@ -16,7 +16,7 @@
 //                four lanes in turns.
 //   k_zstd_seq   ONE lane per entry for the serial part: the three interleaved FSE states of a sequences section.  Only
 //                the FSE decoding tables are needed here, as 16-bit entries 2.5 KiB per lane (round 1: 9.7 KB per lane
-//                for everything = 20 entries per SM; here up to 87), and the code -> base / extra-bits tables are shared
+//                for everything = 20 entries per SM; here up to 80), and the code -> base / extra-bits tables are shared
 //                by the CTA.  The chain state -> table entry -> bit counts -> next state is a few shared-memory round
 //                trips per sequence (with the tables in global memory it was L2 round trips: 3x slower).
 //
