@@ -1236,6 +1236,7 @@ int zip_file_replace(zip_t *za, zip_uint64_t index, zip_source_t *src, zip_flags
 		np.owned = 1;
 	}
 	np.dirty = 1;
+	np.fast = a->pend[index].fast; /* the level asked for with zip_set_file_compression stays with the entry */
 	if (a->pend[index].owned) {
 		free (a->pend[index].buf);
 	}
